@@ -1,0 +1,281 @@
+"""Generate golden vectors by EXECUTING THE REFERENCE (from /root/reference, under oracle/ref_shims.py).
+
+Run in the build container only:   python tests/golden/make_golden.py
+Writes tests/golden/<case>.npz.  The reference is a Python package and cannot travel to the GPU box, so the
+vectors it produced are committed as fixtures, together with this script.
+
+What is driven (unmodified reference code):
+  * BatchedVectorEnvRunner.{init,update_trajectory_buffers,generate_policy_request,advance_rollouts}
+    (algo/sampling/batched_sampling.py:154-388)
+  * the body of InferenceWorker._handle_policy_steps (algo/sampling/inference_worker.py:313-341), inlined because
+    the worker class itself needs a live signal_slot event loop
+  * BufferMgr / alloc_trajectory_tensors (algo/utils/shared_buffers.py)
+  * Learner.init / Learner.train (algo/learning/learner.py:178-255, 1036-1067), with _calculate_losses wrapped
+    only to RECORD its return values.
+The env is oracle.appo_oracle.TapeVecEnv (ours; registered through the reference's own register_env).
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_shims  # noqa: E402
+
+ref_shims.install()
+
+import gymnasium as gym  # noqa: E402  (shim)
+
+from oracle.appo_oracle import TapeVecEnv  # noqa: E402
+from sample_factory.algo.learning.learner import Learner  # noqa: E402
+from sample_factory.algo.sampling.batched_sampling import BatchedVectorEnvRunner  # noqa: E402
+from sample_factory.algo.utils.env_info import extract_env_info  # noqa: E402
+from sample_factory.algo.utils.make_env import make_env_func_batched  # noqa: E402
+from sample_factory.algo.utils.model_sharing import ParameterServer  # noqa: E402
+from sample_factory.algo.utils.rl_utils import prepare_and_normalize_obs  # noqa: E402
+from sample_factory.algo.utils.shared_buffers import BufferMgr  # noqa: E402
+from sample_factory.algo.utils.tensor_dict import TensorDict  # noqa: E402
+from sample_factory.cfg.arguments import default_cfg, preprocess_cfg  # noqa: E402
+from sample_factory.envs.env_utils import register_env  # noqa: E402
+from sample_factory.utils.timing import Timing  # noqa: E402
+
+OUT_DIR = os.path.dirname(os.path.abspath(__file__))
+
+
+class RefTapeEnv(gym.Env):
+    """Adapter: TapeVecEnv behind the reference's batched-env contract (make_env.py:147-237)."""
+
+    def __init__(self, tape_env: TapeVecEnv):
+        self.e = tape_env
+        self.num_agents = tape_env.num_agents
+        self.is_multiagent = True
+        self.observation_space = gym.spaces.Dict(
+            {"obs": gym.spaces.Box(-np.inf, np.inf, (tape_env.obs_dim,), np.float32)}
+        )
+        self.action_space = gym.spaces.Discrete(tape_env.num_actions)
+
+    def reset(self, **kw):
+        return {"obs": self.e.reset().clone()}, {}
+
+    def step(self, actions):
+        obs, rew, term, trunc = self.e.step(torch.as_tensor(actions))  # numpy int32 (batched_sampling.py:62-82)
+        return {"obs": obs.clone()}, rew, term, trunc, {}
+
+    def close(self):
+        pass
+
+
+def run_case(name: str, N: int, T: int, obs_dim: int, A: int, hidden, iters: int, overrides: dict, poison: bool):
+    torch.manual_seed(1234)
+    np.random.seed(1234)
+    tape_len = T * iters + 1
+    tape = torch.randn(tape_len, N, obs_dim) * 1.5 + 0.3
+    tape_env = TapeVecEnv(tape, A)
+
+    env_name = f"tape_{name}"
+    register_env(env_name, lambda full_env_name, cfg, env_config, render_mode=None: RefTapeEnv(tape_env))
+
+    cfg = default_cfg(env=env_name, experiment=f"golden_{name}")
+    cfg.device = "cpu"
+    cfg.serial_mode = True
+    cfg.async_rl = False
+    cfg.batched_sampling = True
+    cfg.num_workers = 1
+    cfg.num_envs_per_worker = 1
+    cfg.worker_num_splits = 1
+    cfg.use_rnn = False
+    cfg.encoder_mlp_layers = list(hidden)
+    cfg.rollout = T
+    cfg.seed = 0
+    cfg.train_dir = "/tmp/sfb200_golden"
+    cfg.env_gpu_actions = False
+    cfg.env_gpu_observations = False
+    cfg.use_env_info_cache = False
+    for k, v in overrides.items():
+        assert hasattr(cfg, k), k
+        setattr(cfg, k, v)
+
+    tmp_env = make_env_func_batched(cfg, env_config=None)
+    env_info = extract_env_info(tmp_env, cfg)
+    assert preprocess_cfg(cfg, env_info)
+
+    buffer_mgr = BufferMgr(cfg, env_info)
+    policy_versions = buffer_mgr.policy_versions
+    param_server = ParameterServer(0, policy_versions, cfg.serial_mode)
+    learner = Learner(cfg, env_info, policy_versions, 0, param_server)
+    learner.init()
+    ac = learner.actor_critic
+    init_state = {k: v.detach().clone().numpy() for k, v in ac.state_dict().items()}
+
+    timing = Timing()
+    runner = BatchedVectorEnvRunner(cfg, env_info, 1, 0, 0, buffer_mgr, "cpu", [None])
+    runner.init(timing)
+
+    rec_losses = []
+    orig_calc = learner._calculate_losses
+
+    def calc_wrapper(mb, num_invalids):
+        out = orig_calc(mb, num_invalids)
+        action_distribution, policy_loss, exploration_loss, kl_old, kl_loss, value_loss, summ = out
+        rec_losses.append(
+            dict(
+                policy_loss=float(policy_loss),
+                exploration_loss=float(exploration_loss),
+                kl_loss=float(kl_loss),
+                value_loss=float(value_loss),
+                adv_mean=float(summ["adv_mean"]),
+                adv_std=float(summ["adv_std"]),
+            )
+        )
+        return out
+
+    learner._calculate_losses = calc_wrapper
+
+    out = {}
+    out["tape"] = tape.numpy()
+    for k, v in init_state.items():
+        out[f"init/{k}"] = v
+
+    for it in range(iters):
+        noise_steps = []
+        for t in range(T):
+            assert runner.update_trajectory_buffers(timing)
+            req = runner.generate_policy_request()
+            assert req is not None
+            (traj_slice, step) = req[0]
+            # ---- InferenceWorker._handle_policy_steps body (inference_worker.py:313-341) ----
+            with torch.no_grad():
+                obs = TensorDict({k: v[traj_slice, step] for k, v in runner.traj_tensors["obs"].items()})
+                rnn_states = runner.traj_tensors["rnn_states"][traj_slice, step]
+                if ac.training:
+                    ac.eval()
+                normalized_obs = prepare_and_normalize_obs(ac, obs)
+                rng_before = torch.get_rng_state()
+                policy_outputs = ac(normalized_obs, rnn_states)
+                rng_after = torch.get_rng_state()
+                # recover the Exp(1) noise torch.multinomial consumed (SURVEY App.E) and prove the identity
+                torch.set_rng_state(rng_before)
+                probs = torch.softmax(policy_outputs["action_logits"], -1)
+                q = torch.empty_like(probs).exponential_()
+                torch.set_rng_state(rng_after)
+                assert torch.equal(torch.argmax(probs / q, -1), policy_outputs["actions"]), "multinomial identity"
+                noise_steps.append(q.clone())
+                policy_outputs["policy_version"] = torch.empty([N]).fill_(int(policy_versions[0].item()))
+                # _prepare_policy_outputs_batched :235-269
+                if policy_outputs["actions"].ndim < 2:
+                    policy_outputs["actions"] = policy_outputs["actions"].unsqueeze(-1)
+                for key in runner.policy_output_tensors.keys():
+                    runner.policy_output_tensors[key][:] = policy_outputs[key].reshape(
+                        runner.policy_output_tensors[key].shape
+                    )
+            complete, _stats = runner.advance_rollouts(0, timing)
+        assert len(complete) == 1
+        sl = complete[0]["traj_buffer_idx"]
+        batch = runner.traj_tensors[sl]
+
+        if poison and it == iters - 1:
+            # invalid-data splice in the spirit of tests/algo/test_learner.py:109-168: foreign policy id + stale version
+            g = torch.Generator().manual_seed(77)
+            mask = torch.rand(N, T, generator=g) < 0.15
+            batch["policy_id"][mask] = -1
+            stale = torch.rand(N, T, generator=g) < 0.05
+            batch["policy_version"][stale] = -5000.0
+
+        pre = {}
+        for k in ["actions", "action_logits", "log_prob_actions", "values", "policy_version", "rewards", "dones",
+                  "time_outs", "policy_id", "rnn_states"]:
+            pre[k] = batch[k].clone().numpy()
+        pre["obs"] = batch["obs"]["obs"].clone().numpy()
+        for k, v in pre.items():
+            out[f"it{it}/traj/{k}"] = v
+        out[f"it{it}/noise"] = torch.stack(noise_steps).numpy()
+        out[f"it{it}/train_step_before"] = np.int64(learner.train_step)
+
+        # capture _prepare_batch outputs by wrapping
+        captured = {}
+        orig_prepare = learner._prepare_batch
+
+        def prep_wrapper(b):
+            buff, n, ninv = orig_prepare(b)
+            for k in ["advantages", "returns", "valids", "values", "rewards", "log_prob_actions", "actions"]:
+                if k in buff:
+                    captured[k] = buff[k].clone().numpy()
+            captured["num_invalids"] = np.int64(ninv)
+            captured["bootstrap_values"] = b["values"][:, -1].clone().numpy()
+            return buff, n, ninv
+
+        learner._prepare_batch = prep_wrapper
+        n_before = len(rec_losses)
+        learner.train(batch)
+        learner._prepare_batch = orig_prepare
+        for k, v in captured.items():
+            out[f"it{it}/prep/{k}"] = v
+        ls = rec_losses[n_before:]
+        for key in ls[0].keys():
+            out[f"it{it}/loss/{key}"] = np.array([d[key] for d in ls], dtype=np.float64)
+        for k, v in ac.state_dict().items():
+            out[f"it{it}/state/{k}"] = v.detach().clone().numpy()
+        out[f"it{it}/train_step_after"] = np.int64(learner.train_step)
+        # hand the buffers back (sync mode: Batcher releases after training, batcher.py:220-267)
+        runner.traj_buffer_queue.put(sl)
+
+    meta = dict(N=N, T=T, obs_dim=obs_dim, A=A, hidden=list(hidden), iters=iters, poison=poison, **overrides)
+    out["meta"] = np.array(repr(meta))
+    # a few flags the oracle needs, straight from the reference cfg object
+    for k in ["gamma", "gae_lambda", "ppo_clip_ratio", "ppo_clip_value", "exploration_loss_coeff", "value_loss_coeff",
+              "kl_loss_coeff", "max_grad_norm", "learning_rate", "adam_eps", "adam_beta1", "adam_beta2",
+              "reward_scale", "reward_clip", "max_policy_lag", "batch_size", "num_batches_per_epoch", "num_epochs",
+              "recurrence", "vtrace_rho", "vtrace_c"]:
+        out[f"cfg/{k}"] = np.float64(getattr(cfg, k))
+    for k in ["normalize_input", "normalize_returns", "value_bootstrap", "with_vtrace"]:
+        out[f"cfg/{k}"] = np.bool_(getattr(cfg, k))
+    path = os.path.join(OUT_DIR, f"{name}.npz")
+    np.savez_compressed(path, **out)
+    print(f"wrote {path}: {os.path.getsize(path) / 1e6:.2f} MB, losses: {rec_losses[-1]}")
+
+
+def kat_action_distribution():
+    """The reference's own known-answer vector (tests/algo/test_action_distributions.py:142-173), re-evaluated with
+    the reference's CategoricalActionDistribution so the fixture carries reference outputs, not just literals."""
+    from sample_factory.algo.utils.action_distributions import CategoricalActionDistribution
+
+    logits = torch.tensor([[0.0, 1.0, 2.0]])
+    d = CategoricalActionDistribution(logits)
+    np.savez(
+        os.path.join(OUT_DIR, "kat_categorical.npz"),
+        logits=logits.numpy(),
+        probs=d.probs.numpy(),
+        log_probs=d.log_probs.numpy(),
+        entropy=d.entropy().numpy(),
+        log_prob_a2=d.log_prob(torch.tensor([[2]])).numpy(),
+        literal_probs=np.array([0.09003057, 0.24472847, 0.66524096], dtype=np.float32),
+    )
+
+
+if __name__ == "__main__":
+    kat_action_distribution()
+    # tiny dims, 2 iterations, invalids + value bootstrap + fixed-KL, 2 epochs x 2 minibatches
+    run_case(
+        "tiny_gae", N=32, T=8, obs_dim=16, A=8, hidden=[64, 64], iters=2,
+        overrides=dict(batch_size=128, num_batches_per_epoch=2, num_epochs=2, value_bootstrap=True,
+                       kl_loss_coeff=0.1, reward_scale=0.7, reward_clip=0.5),
+        poison=True,
+    )
+    # V-trace variant (requires recurrence == rollout, no returns normalisation: arguments.py:129-134,193-194)
+    run_case(
+        "tiny_vtrace", N=32, T=8, obs_dim=16, A=8, hidden=[64, 64], iters=2,
+        overrides=dict(batch_size=128, num_batches_per_epoch=2, num_epochs=1, with_vtrace=True, recurrence=8,
+                       normalize_returns=False),
+        poison=False,
+    )
+    # cfg-2 hyper-parameters and model (300 553 params) at a reduced env count
+    run_case(
+        "cfg2_small", N=64, T=32, obs_dim=64, A=8, hidden=[512, 512], iters=1,
+        overrides=dict(batch_size=512, num_batches_per_epoch=4, num_epochs=1),
+        poison=False,
+    )

@@ -1,0 +1,44 @@
+"""Helpers to load the committed reference-generated fixtures (tests/golden/*.npz, made by make_golden.py)."""
+import ast
+import os
+
+import numpy as np
+import torch
+
+from oracle import appo_oracle as O
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load_case(name):
+    z = np.load(os.path.join(GOLDEN_DIR, f"{name}.npz"), allow_pickle=False)
+    meta = ast.literal_eval(str(z["meta"]))
+    c = {k[4:]: z[k].item() for k in z.files if k.startswith("cfg/")}
+    cfg = O.OracleCfg(
+        obs_dim=meta["obs_dim"], num_actions=meta["A"], encoder_mlp_layers=list(meta["hidden"]),
+        rollout=meta["T"], recurrence=int(c["recurrence"]), batch_size=int(c["batch_size"]),
+        num_batches_per_epoch=int(c["num_batches_per_epoch"]), num_epochs=int(c["num_epochs"]),
+        gamma=c["gamma"], gae_lambda=c["gae_lambda"], ppo_clip_ratio=c["ppo_clip_ratio"],
+        ppo_clip_value=c["ppo_clip_value"], exploration_loss_coeff=c["exploration_loss_coeff"],
+        value_loss_coeff=c["value_loss_coeff"], kl_loss_coeff=c["kl_loss_coeff"], max_grad_norm=c["max_grad_norm"],
+        learning_rate=c["learning_rate"], adam_eps=c["adam_eps"], adam_beta1=c["adam_beta1"],
+        adam_beta2=c["adam_beta2"], normalize_input=bool(c["normalize_input"]),
+        normalize_returns=bool(c["normalize_returns"]), value_bootstrap=bool(c["value_bootstrap"]),
+        with_vtrace=bool(c["with_vtrace"]), vtrace_rho=c["vtrace_rho"], vtrace_c=c["vtrace_c"],
+        reward_scale=c["reward_scale"], reward_clip=c["reward_clip"], max_policy_lag=int(c["max_policy_lag"]),
+    )
+    return z, meta, cfg
+
+
+def state_from(z, prefix):
+    """prefix 'init/' or 'it0/state/' -> dict of torch tensors keyed by reference state_dict names."""
+    return {k[len(prefix):]: torch.from_numpy(z[k].copy()) for k in z.files if k.startswith(prefix)}
+
+
+def traj_from(z, it, cfg):
+    """Rebuild the trajectory batch (reference layout) the reference learner consumed in iteration `it`."""
+    p = f"it{it}/traj/"
+    t = {k[len(p):]: torch.from_numpy(z[k].copy()) for k in z.files if k.startswith(p)}
+    N = t["actions"].shape[0]
+    t["valids"] = torch.zeros((N, cfg.rollout + 1), dtype=torch.bool)
+    return t
