@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""Headline benchmark: env-steps/sec (sampler + learner) on the synthetic Box(64)/Discrete(8) vector env,
+4096 envs per GPU (BASELINE.json configs[1]).
+
+  python bench.py --gpus 1 --steps K --warmup W                 # our engine (libsfb200 on B200)
+  python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+  python bench.py --impl reference --gpus N --steps K --warmup W  # the reference's CPU path (oracle port) on the host
+
+A "step" is one training iteration = one rollout of 32 env steps for all envs of the rank (131 072 env steps) followed
+by one learner pass (4 minibatches x 1 epoch, forward + backward + Adam).  Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+N_ENVS, ROLLOUT, OBS_DIM, N_ACTIONS, HIDDEN = 4096, 32, 64, 8, [512, 512]
+BATCH, N_MINIBATCH, N_EPOCHS = 32768, 4, 1
+TAPE_LEN = 97   # 97 x 4096 x 64 x 4 B = 101 MB of env observations cycled through
+METRIC = "env-steps/sec (sampler+learner) at 4096 envs"
+UNIT = "env-steps/s"
+WORKLOAD = ("synthetic Box(64)/Discrete(8) vec-env, 4096 envs per GPU, MLP 512-512 ELU, rollout 32, batch 32768 x 4 "
+            "minibatches x 1 epoch, normalize_input+returns, GAE, Adam (BASELINE.json configs[1])")
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d["hbm_gbs"], tflops_burst=d["bf16_tflops"],
+                    tflops_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]), source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, tflops_burst=1590.0, tflops_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu_index)], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=max(smax) if smax else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+# --------------------------------------------------------------------------------------------------- reference arm
+def oracle_cpu_run(steps: int, warmup: int, n_envs: int = N_ENVS):
+    """The reference's CPU path for this workload: the oracle port (torch CPU, all host threads), one process."""
+    from oracle import appo_oracle as O
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    ocfg = O.OracleCfg(obs_dim=OBS_DIM, num_actions=N_ACTIONS, encoder_mlp_layers=list(HIDDEN), rollout=ROLLOUT,
+                       recurrence=1, batch_size=n_envs * ROLLOUT // N_MINIBATCH, num_batches_per_epoch=N_MINIBATCH,
+                       num_epochs=N_EPOCHS)
+    gen = torch.Generator().manual_seed(0)
+    tape = torch.randn(TAPE_LEN, n_envs, OBS_DIM, generator=gen)
+    learner = O.OracleLearner(ocfg, O.init_state(ocfg, seed=0))
+    env = O.TapeVecEnv(tape, N_ACTIONS)
+    last = env.reset()
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            noise = torch.empty(ROLLOUT, n_envs, N_ACTIONS).exponential_(generator=gen)
+            traj = O.alloc_trajectories(ocfg, n_envs)
+            last = O.rollout(ocfg, learner.st, env, last, traj, noise, learner.train_step)
+        learner.train(traj)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    total = sum(times)
+    return dict(value=n_envs * ROLLOUT * len(times) / total, ms_per_step=1e3 * total / len(times), cores=cores)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = oracle_cpu_run(args.steps, args.warmup)
+    sample = f"{args.steps} full iterations (4096 envs x 32 steps + learner) after {args.warmup} warm-up, torch CPU"
+    out = dict(impl="reference", metric=METRIC, value=r["value"], unit=UNIT, n_gpus=args.gpus, steps=args.steps,
+               warmup=args.warmup, ms_per_step=r["ms_per_step"], higher_is_better=True, scaling="weak",
+               vs_baseline=None, dtype="f32", data="synthetic", config=dict(workload=WORKLOAD),
+               cpu_baseline=dict(value=r["value"], unit=UNIT, cores=r["cores"], kind="port", sample=sample),
+               e2e=dict(value=r["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(out), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------- our arm
+def make_cfg(env_name: str, engine: str, cuda_graph: bool):
+    from sample_factory_b200.cfg import parse_full_cfg, parse_sf_args
+
+    argv = [f"--env={env_name}", "--experiment=bench", "--train_dir=/tmp/sfb200_bench", "--restart_behavior=overwrite",
+            "--use_rnn=False", "--async_rl=False", "--serial_mode=True", "--batched_sampling=True", "--num_workers=1",
+            "--num_envs_per_worker=1", "--worker_num_splits=1", f"--rollout={ROLLOUT}", f"--batch_size={BATCH}",
+            f"--num_batches_per_epoch={N_MINIBATCH}", f"--num_epochs={N_EPOCHS}", "--encoder_mlp_layers", "512", "512",
+            "--env_gpu_actions=True", "--env_gpu_observations=True", "--seed=0", f"--gemm_engine={engine}",
+            f"--cuda_graph={cuda_graph}", "--save_every_sec=1000000000"]
+    parser, _ = parse_sf_args(argv)
+    return parse_full_cfg(parser, argv)
+
+
+def run_ours(args):
+    from sample_factory_b200 import ops
+    from sample_factory_b200.dist_utils import init_from_env
+    from sample_factory_b200.envs import HostTapeVecEnv, TapeVecEnv, register_env
+    from sample_factory_b200.train import Runner
+
+    rank, local_rank, world = init_from_env()
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    ops.bind_device(dev)
+    dist = torch.distributed
+    peaks = load_peaks()
+
+    gen = torch.Generator().manual_seed(1234 + rank)
+    tape_cpu = torch.randn(TAPE_LEN, N_ENVS, OBS_DIM, generator=gen)
+    register_env("synthetic_tape", lambda name, cfg, env_config, render_mode=None: TapeVecEnv(
+        tape_cpu.to(dev), N_ACTIONS, env_index_offset=rank * N_ENVS))
+    register_env("synthetic_tape_host", lambda name, cfg, env_config, render_mode=None: HostTapeVecEnv(
+        tape_cpu.numpy(), N_ACTIONS, dev, env_index_offset=rank * N_ENVS))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ------------------------------------------------------------------ device-resident arm ("value")
+    runner = Runner(make_cfg("synthetic_tape", args.engine, not args.no_graph))
+    runner.init()
+    engine_name = {0: "simt-fp32", 1: "tcgen05-3xTF32", 2: "tcgen05-TF32"}[runner.engine]
+
+    # live per-kernel timing of the dominant kernel (the learner's layer-2 forward GEMM, M=32768 N=K=512) and of the
+    # main HBM-bound kernels, with CUDA events on the launching stream, inside the timed region
+    timed = {}
+    orig = {}
+
+    def wrap(name, pred, work):
+        fn = getattr(ops, name)
+        orig[name] = fn
+
+        def wrapped(*a, **k):
+            w = pred(*a, **k)
+            if w is None or not timing_on[0]:
+                return fn(*a, **k)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = fn(*a, **k)
+            e1.record()
+            timed.setdefault(w, dict(events=[], work=work(*a, **k)))["events"].append((e0, e1))
+            return r
+
+        setattr(ops, name, wrapped)
+
+    timing_on = [False]
+    wrap("linear_act_forward", lambda x, W, b, out, act, eng: "gemm_fwd_l2" if (x.shape[0] == BATCH and W.shape == (512, 512)) else None,
+         lambda x, W, b, out, act, eng: 2.0 * x.shape[0] * W.shape[0] * W.shape[1])
+    wrap("heads_backward", lambda h, *a, **k: "heads_backward" if h.shape[0] == BATCH else None,
+         lambda h, Wv, Wa, dlogits, *a, **k: float(h.numel() * 4 * 2 + dlogits.numel() * 4 + h.shape[0] * 4))
+    wrap("normalize_obs", lambda x, out, mean, *a, **k: "normalize_obs" if (x.shape[0] == N_ENVS * (ROLLOUT + 1) and mean is not None) else None,
+         lambda x, out, *a, **k: float(x.numel() * 4 * 2))
+    wrap("gae_returns", lambda rewards, *a, **k: "gae_returns", lambda rewards, *a, **k: float(rewards.numel() * 22))
+    # (learner / sampler resolve ops.<fn> through the module at call time, so the wrappers take effect)
+    for _ in range(args.warmup):
+        runner.iteration()
+    barrier()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    launches0 = ops.launch_count()
+    replay_launches = 0
+    timing_on[0] = True
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        runner.iteration()
+        if runner.sampler._graph is not None:
+            replay_launches += runner.sampler.kernel_launches_per_rollout
+    e1.record()
+    barrier()
+    timing_on[0] = False
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    clock_info = clocks.stop()
+    gpu_launches = (ops.launch_count() - launches0) + replay_launches
+    ms_per_step = ms_total / args.steps
+    value = world * N_ENVS * ROLLOUT * args.steps / (ms_total / 1e3)
+
+    kern = {}
+    for name, d in timed.items():
+        ms = [a.elapsed_time(b) for a, b in d["events"]]
+        kern[name] = dict(avg_ms=sum(ms) / len(ms), launches=len(ms), work=d["work"])
+    for name, fn in orig.items():
+        setattr(ops, name, fn)
+
+    roofline = None
+    if "gemm_fwd_l2" in kern:
+        k = kern["gemm_fwd_l2"]
+        ach = k["work"] / (k["avg_ms"] * 1e-3) / 1e12
+        roofline = dict(kernel=f"learner layer-2 forward GEMM [32768x512x512] ({engine_name})", bound="tensor",
+                        achieved=ach, peak=peaks["tflops_sustained"], unit="TFLOP/s", frac=ach / peaks["tflops_sustained"],
+                        traffic=None, avg_kernel_ms=k["avg_ms"], launches_timed=k["launches"],
+                        peak_source=peaks["source"] + ", bf16 sustained (kernel timed inside a long step)",
+                        note="fp32-parity GEMM: 3xTF32 costs 3 tf32 MMAs per product and tf32 peak is half of bf16, so "
+                             "the ceiling of this engine is peak/6; the simt engine runs on CUDA cores (no tensor pipe)")
+    roof2 = []
+    for name in ("heads_backward", "normalize_obs", "gae_returns"):
+        if name in kern:
+            k = kern[name]
+            ach = k["work"] / (k["avg_ms"] * 1e-3) / 1e9
+            roof2.append(dict(kernel=name, bound="hbm", achieved=ach, peak=peaks["hbm_gbs"], unit="GB/s",
+                              frac=ach / peaks["hbm_gbs"], avg_kernel_ms=k["avg_ms"], algorithmic_bytes=k["work"]))
+    sampler_launches = runner.sampler.kernel_launches_per_rollout
+    learner_launches = runner.learner.kernel_launches
+    del runner
+    torch.cuda.empty_cache()
+
+    # ------------------------------------------------------------------ end-to-end arm (host env, H2D/D2H inside)
+    e2e = None
+    if not args.no_e2e:
+        r2 = Runner(make_cfg("synthetic_tape_host", args.engine, False))
+        r2.init()
+        for _ in range(max(1, args.warmup)):
+            r2.iteration()
+            r2.learner.fetch_stats()
+        barrier()
+        env = r2.env
+        h0, d0 = env.h2d_bytes, env.d2h_bytes
+        stats_bytes = 0
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            r2.iteration()
+            st = r2.learner.fetch_stats()            # D2H read of the step's result (loss terms)
+            stats_bytes += (len(st) - 2) * 8
+        barrier()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        e2e = dict(value=world * N_ENVS * ROLLOUT * args.steps / dt, unit=UNIT,
+                   h2d_bytes_per_step=(env.h2d_bytes - h0) // args.steps,
+                   d2h_bytes_per_step=(env.d2h_bytes - d0 + stats_bytes) // args.steps,
+                   ms_per_step=1e3 * dt / args.steps,
+                   api="sample_factory_b200.train.Runner.iteration() with a HOST env (numpy simulator, pinned staging): "
+                       "obs H2D + actions D2H every env step, loss stats D2H every iteration")
+        del r2
+
+    cpu_baseline = None
+    if world == 1 and rank == 0 and not args.no_cpu_baseline:
+        r = oracle_cpu_run(steps=6, warmup=2)
+        cpu_baseline = dict(value=r["value"], unit=UNIT, cores=r["cores"], kind="port",
+                            sample="6 full iterations (4096 envs x 32 steps + learner) after 2 warm-up, oracle port "
+                                   "(torch CPU, all host threads)", ms_per_step=r["ms_per_step"])
+
+    if rank == 0:
+        out = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
+                   ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None,
+                   dtype="f32" + (" (3xTF32 split on tcgen05, fp32 accumulate)" if engine_name == "tcgen05-3xTF32" else ""),
+                   data="synthetic",
+                   config=dict(workload=WORKLOAD, envs_per_gpu=N_ENVS, rollout=ROLLOUT, global_batch=BATCH * N_MINIBATCH * world,
+                               parallelism=f"dp{world} (env shards, 1 grad all-reduce per SGD step)", gemm_engine=engine_name,
+                               cuda_graph_rollout=not args.no_graph,
+                               l2_policy="per-step working set (trajectories 45 MB + obs tape 101 MB + learner "
+                                         "activations 4x64 MB + workspaces) exceeds the 126 MB L2; no explicit flush"),
+                   clocks=clock_info, e2e=e2e, gpu_launches=int(gpu_launches),
+                   launches_per_step=dict(sampler_rollout=int(sampler_launches), learner_train=int(learner_launches)),
+                   roofline=roofline, roofline_secondary=roof2, cpu_baseline=cpu_baseline)
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--engine", default="auto", choices=["auto", "simt", "3xtf32", "tf32"])
+    ap.add_argument("--no-graph", dest="no_graph", action="store_true")
+    ap.add_argument("--no-e2e", dest="no_e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

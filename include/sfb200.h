@@ -1,0 +1,252 @@
+/*
+ * sfb200.h -- C ABI of libsfb200.so: the B200 (sm_100a) implementation of Sample Factory's APPO hot path
+ *             (rollout sampler -> PPO / V-trace learner).
+ *
+ * The reference (alex-petrenko/sample-factory) has no FFI for this path: it is Python calling PyTorch ATen.  Each
+ * entry point below therefore cites the reference Python site (paths relative to sample_factory/) whose arithmetic
+ * it replaces; INTEGRATION.md shows the ctypes binding a maintainer adds at that site.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless the name ends in _host
+ *   - all tensors are caller-owned ("borrowed"), dense in their last dimension, fp32 unless stated;
+ *     bool tensors are 1 byte per element (torch.bool); ld* / *_stride arguments are element strides
+ *   - `stream` is a cudaStream_t (CUstream) passed as void*; every call only ENQUEUES work on that stream,
+ *     never allocates device memory and never synchronises the host
+ *   - return value: 0 = ok, otherwise an error code; sfb200_last_error() returns the message (thread-local)
+ *   - layouts are the reference trajectory layout (algo/utils/shared_buffers.py:79-117): [num_traj, T(+1), ...]
+ */
+#ifndef SFB200_H
+#define SFB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* everything declared here is exported; the rest of the library is hidden */
+#endif
+
+#define SFB200_ABI_VERSION 1
+
+/* activation codes (model/model_utils.py:27-35) */
+#define SFB200_ACT_NONE 0
+#define SFB200_ACT_ELU 1
+#define SFB200_ACT_RELU 2
+#define SFB200_ACT_TANH 3
+
+/* GEMM engine selection for sfb200_linear_* */
+#define SFB200_GEMM_SIMT_FP32 0   /* CUDA-core fp32 FFMA tiles */
+#define SFB200_GEMM_TC_3XTF32 1   /* tcgen05 kind::tf32, error-compensated 3-pass split, fp32 accumulate in TMEM */
+#define SFB200_GEMM_TC_TF32 2     /* tcgen05 kind::tf32 single pass (fast, NOT parity grade) */
+
+/* ---------------------------------------------------------------- library ---- */
+int sfb200_abi_version(void);
+const char* sfb200_last_error(void);
+/* binds the calling thread to `device` (cudaSetDevice); call once per thread before anything else */
+int sfb200_set_device(int device);
+/* number of SMs of the bound device (grid sizing) */
+int sfb200_sm_count(void);
+/* 1 if the tcgen05/TMA GEMM engine is usable in this process (driver entry points resolved), else 0 */
+int sfb200_tc_available(void);
+/* total number of CUDA kernels this library has launched (or recorded into a stream capture) in this process */
+uint64_t sfb200_launch_count(void);
+
+/* ------------------------------------------------------------- normalizers ---- */
+/* utils/normalize.py:51-70 + algo/utils/running_mean_std.py:96-110 (normalize branch), out of place:
+ *   y = clamp(((x - sub_mean) * inv_scale - mean) * (1 / sqrt(var + eps)), -clip, clip)
+ * mean/var are the float64 running buffers (running_mean_std.py:45-46); if mean == NULL only sub/scale apply.
+ * x rows have element stride ldx, y rows ldy. */
+int sfb200_normalize_obs(const float* x, int64_t ldx, float* y, int64_t ldy, int64_t rows, int dim,
+                         const double* mean, const double* var, float sub_mean, float inv_scale, float eps,
+                         float clip, void* stream);
+
+/* running_mean_std.py:72-77: batch mean and UNBIASED variance over dim 0 of x[rows, dim] (fp64 accumulation,
+ * results rounded to fp32 like the reference's fp32 tensors).  workspace: >= sfb200_moments_workspace_bytes(dim). */
+int64_t sfb200_moments_workspace_bytes(int dim);
+int sfb200_batch_moments(const float* x, int64_t ldx, int64_t rows, int dim, float* batch_mean, float* batch_var,
+                         void* workspace, void* stream);
+
+/* running_mean_std.py:49-62: in-place Welford merge of (batch_mean, batch_var, batch_count) into the float64
+ * running buffers mean/var[dim] and count[1]. */
+int sfb200_rms_merge(double* mean, double* var, double* count, const float* batch_mean, const float* batch_var,
+                     double batch_count, int dim, void* stream);
+
+/* running_mean_std.py:96-110 with input_shape (1,), in place on a flat vector (the returns normalizer,
+ * learner.py:1018-1019 and :969-975): denormalize=0: x = clamp((x-mean)*(1/sigma), +-clip);
+ * denormalize=1: x = clamp(x, +-clip)*sigma + mean.  mean/var: float64 [1]. */
+int sfb200_rms_apply_scalar(float* x, int64_t n, const double* mean, const double* var, float eps, float clip,
+                            int denormalize, void* stream);
+
+/* ------------------------------------------------------------- model forward ---- */
+/* model/model_utils.py:46-56 (create_mlp layer): y[M,N] = act(x[M,K] . W[N,K]^T + b[N]);  W in nn.Linear layout.
+ * engine: SFB200_GEMM_*.  x row stride ldx (lets the learner feed obs[:, T] rows in place), y row stride ldy. */
+int sfb200_linear_act_forward(const float* x, int64_t ldx, const float* W, const float* b, float* y, int64_t ldy,
+                              int64_t M, int N, int K, int act, int engine, void* stream);
+
+/* critic_linear + distribution_linear + CategoricalActionDistribution (model/actor_critic.py:171-186,
+ * model/action_parameterization.py:33-39, algo/utils/action_distributions.py:110-148):
+ *   values[i]  = h[i] . Wv + bv                                   (written at values[i * values_stride])
+ *   logits[i]  = h[i] . Wa^T + ba                                 (logits + i * logits_stride, A floats)
+ * and, if actions_f32 != NULL (sampling mode, inference_worker.py:313-341):
+ *   a = argmax_j softmax(logits)_j / q_j   (== torch.multinomial(p, 1, True); q = noise row if noise != NULL,
+ *                                           else Exp(1) from Philox4x32-10(seed, subsequence=i*A+j,
+ *                                           offset = philox_offset + (philox_offset_dev ? *philox_offset_dev : 0));
+ *                                           the device-side term keeps a captured CUDA graph drawing fresh noise)
+ *   actions_f32[i*actions_stride] = (float)a ; env_actions_i32[i] = a ; log_prob[i*log_prob_stride] = log_softmax_a
+ *   policy_version_out[i*pv_stride] = *policy_version_scalar (inference_worker.py:332)
+ * Any output pointer except values may be NULL.  A <= 32. */
+int sfb200_heads_forward(const float* h, int64_t ldh, int64_t rows, int H, int A, const float* Wv, const float* bv,
+                         const float* Wa, const float* ba, float* values, int64_t values_stride, float* logits,
+                         int64_t logits_stride, const float* noise, uint64_t philox_seed, uint64_t philox_offset,
+                         const int64_t* philox_offset_dev, float* actions_f32, int64_t actions_stride, int32_t* env_actions_i32, float* log_prob,
+                         int64_t log_prob_stride, const float* policy_version_scalar, float* policy_version_out,
+                         int64_t pv_stride, void* stream);
+
+/* ------------------------------------------------------------- sampler steps ---- */
+/* BatchedVectorEnvRunner.generate_policy_request (algo/sampling/batched_sampling.py:374-388) fused with the
+ * inference-side normalisation (inference_worker.py:326):  traj_obs[:, t] = obs ; traj_rnn[:, t] = rnn ;
+ * x_norm = normalize(obs).  traj_obs_t / traj_rnn_t point at element [0, t]; row strides in elements. */
+int sfb200_sampler_pre_step(const float* obs, int64_t n_envs, int dim, float* traj_obs_t, int64_t traj_obs_stride,
+                            const float* rnn, int rnn_dim, float* traj_rnn_t, int64_t traj_rnn_stride,
+                            float* x_norm, const double* mean, const double* var, float sub_mean, float inv_scale,
+                            float eps, float clip, void* stream);
+
+/* advance_rollouts part 2 (batched_sampling.py:319-357, _process_rewards :208-213, _process_env_step :215-287):
+ * dones = terminated | truncated ; r = clamp(rew*reward_scale, +-reward_clip) ; writes rewards/dones/time_outs/
+ * policy_id at [.., t] (pointers at element [0,t], element stride traj_stride) ; device-side episode accounting:
+ * per-env ep_return[n], ep_len[n] (int32), ep_min_raw[n], ep_max_raw[n] and, for episodes finishing this step, the
+ * accumulators stats[0..4] = {count, sum_return, sum_len, sum_min_raw_reward, sum_max_raw_reward} (doubles) -- the
+ * reference's per-episode report (:228-234) aggregated on device, no host sync.  step_counter (optional, device
+ * int64) is incremented by one: the sampler's policy-step count, used as the Philox offset of the next step. */
+int sfb200_sampler_post_step(const float* rew, const uint8_t* terminated, const uint8_t* truncated, int64_t n_envs,
+                             float reward_scale, float reward_clip, int32_t policy_id, float* traj_rewards_t,
+                             uint8_t* traj_dones_t, uint8_t* traj_time_outs_t, int32_t* traj_policy_id_t,
+                             int64_t traj_stride, float* ep_return, int32_t* ep_len, float* ep_min_raw,
+                             float* ep_max_raw, int32_t len_increment, double* stats, int64_t* step_counter,
+                             void* stream);
+
+/* strided row copy dst[i*dst_stride + 0..dim) = src[i*src_stride + 0..dim) (_finalize_trajectories :289-296) */
+int sfb200_copy_rows(const float* src, int64_t src_stride, float* dst, int64_t dst_stride, int64_t rows, int dim,
+                     void* stream);
+
+/* Synthetic "tape" vector env (ours, not the reference's; contract = algo/utils/make_env.py:147-237 step()):
+ * step = step_counter ? *step_counter : step_host.  reward = action/num_actions; terminated = ((step*7 + env*13) %
+ * term_period == 0); truncated = ((step + env) % trunc_period == 0) & !terminated, env = env_index_offset + i;
+ * obs_out = tape[(step+1) % tape_len] (tape: [tape_len, n_envs, dim]).  If step_counter != NULL it is incremented
+ * afterwards (device-side counter keeps the call replayable inside a CUDA graph). */
+int sfb200_tape_env_step(const int32_t* actions, int64_t n_envs, int num_actions, int64_t env_index_offset,
+                         int term_period, int trunc_period, int64_t* step_counter, int64_t step_host,
+                         const float* tape, int64_t tape_len, int dim, float* obs_out, float* rew,
+                         uint8_t* terminated, uint8_t* truncated, void* stream);
+
+/* ------------------------------------------------------------- learner: batch prep ---- */
+/* learner.py:950-955: valids[:, :T] = (policy_id == this_policy) & (train_step - policy_version < max_lag);
+ * valids[:, T] = valids[:, T-1]. */
+int sfb200_compute_valids(const int32_t* policy_id, const float* policy_version, int64_t n_traj, int T,
+                          int32_t this_policy, float train_step, float max_policy_lag, uint8_t* valids,
+                          void* stream);
+
+/* learner.py:969-1003 fused, warp-scan over the time axis (algo/utils/rl_utils.py:51-94):
+ *   dv = normalize_returns ? clamp(values, +-5)*sigma + mu : values            (:969-978)
+ *   if value_bootstrap: rewards += gamma * dv[:, :-1] * time_outs * dones       (:990, IN PLACE like the reference)
+ *   adv = GAE(rewards, dones, dv, valids, gamma, lambda)                        (:994-1001)
+ *   returns = adv + valids[:, :-1] * dv[:, :-1]                                  (:1003)
+ * values/valids: [n_traj, T+1]; rewards/dones/time_outs/adv/returns: [n_traj, T]. ret_mean/ret_var: float64[1]
+ * or NULL when normalize_returns is off. */
+int sfb200_gae_returns(float* rewards, const uint8_t* dones, const uint8_t* time_outs, const float* values,
+                       const uint8_t* valids, int64_t n_traj, int T, float gamma, float lam, int value_bootstrap,
+                       const double* ret_mean, const double* ret_var, float eps, float clip, float* adv,
+                       float* returns, void* stream);
+
+/* learner.py:602-640 (V-trace), on device: inputs flat [n*R] env-major.  Outputs vs (targets) and adv. */
+int sfb200_vtrace(const float* ratio, const float* values, const float* rewards, const uint8_t* dones, int64_t n,
+                  int R, float gamma, float rho_hat, float c_hat, float* vs, float* adv, void* stream);
+
+/* ------------------------------------------------------------- learner: loss ---- */
+/* Layout of the device-side loss statistics block (doubles), written by sfb200_ppo_loss_*: */
+#define SFB200_LS_NUM_VALID 0
+#define SFB200_LS_ADV_MEAN 1
+#define SFB200_LS_ADV_STD 2
+#define SFB200_LS_POLICY_LOSS 3
+#define SFB200_LS_VALUE_LOSS 4      /* already multiplied by value_loss_coeff */
+#define SFB200_LS_EXPLORATION_LOSS 5 /* -coeff * mean entropy */
+#define SFB200_LS_KL_LOSS 6         /* kl_loss_coeff * mean KL(new||old) */
+#define SFB200_LS_KL_OLD_MEAN 7
+#define SFB200_LS_KL_OLD_MAX 8
+#define SFB200_LS_ENTROPY_MEAN 9
+#define SFB200_LS_RATIO_MEAN_ABS_DEV 10 /* mean |1 - ratio| over valid */
+#define SFB200_LS_RATIO_MIN 11
+#define SFB200_LS_RATIO_MAX 12
+#define SFB200_LS_FRACTION_CLIPPED 13
+#define SFB200_LS_VALUE_MEAN 14
+#define SFB200_LS_TOTAL_LOSS 15
+#define SFB200_LS_SIZE 16
+
+int64_t sfb200_loss_workspace_bytes(int64_t batch);
+
+/* learner.py:588-594: log_prob(actions) under new logits and ratio = clamp(exp(lp - lp_old), 0.05, 20)
+ * (needed before V-trace; the GAE path does not call this). */
+int sfb200_action_ratio(const float* logits, int A, const float* actions_f32, const float* log_prob_old,
+                        int64_t batch, float* ratio, void* stream);
+
+/* learner.py:646-647 statistics: masked (valids) count / mean / UNBIASED std of adv -> stats[NUM_VALID, ADV_MEAN,
+ * ADV_STD].  dp_partials (optional, 3 doubles: count, sum, sumsq) exposes the raw sums so data-parallel ranks can
+ * all-reduce them and call sfb200_adv_stats_finalize. */
+int sfb200_adv_stats(const float* adv, const uint8_t* valids, int64_t batch, double* stats, double* dp_partials,
+                     void* workspace, void* stream);
+int sfb200_adv_stats_finalize(const double* dp_partials, double* stats, void* stream);
+
+/* learner.py:586-657 + :431-477 forward AND backward in one pass over the minibatch:
+ *   inputs: new logits [B,A], new values [B]; batch tensors actions (f32), log_prob_old, values_old, adv (raw),
+ *           targets (returns or vs), valids, logits_old [B,A]
+ *   uses stats[NUM_VALID, ADV_MEAN, ADV_STD] (from sfb200_adv_stats) for the per-minibatch advantage normalisation
+ *   outputs: dlogits [B,A], dvalues [B] = d(total loss)/d(.) ; stats[POLICY_LOSS .. TOTAL_LOSS]
+ * All means are over valid entries only (algo/utils/torch_utils.py:50-55).  grad_scale multiplies every gradient
+ * (1/world_size under data parallelism). */
+int sfb200_ppo_loss_fwd_bwd(const float* logits, const float* values, int A, const float* actions_f32,
+                            const float* log_prob_old, const float* values_old, const float* adv,
+                            const float* targets, const uint8_t* valids, const float* logits_old, int64_t batch,
+                            float clip_ratio, float clip_value, float exploration_coeff, float value_coeff,
+                            float kl_coeff, float grad_scale, float* dlogits, float* dvalues, double* stats,
+                            void* workspace, void* stream);
+
+/* ------------------------------------------------------------- learner: backward ---- */
+int64_t sfb200_heads_backward_workspace_bytes(int H, int A);
+/* backward of critic_linear + distribution_linear fused with the activation derivative of the layer that produced h:
+ *   dz[i,j]   = (sum_a dlogits[i,a]*Wa[a,j] + dvalues[i]*Wv[j]) * act'(h[i,j])      (act' from the OUTPUT h)
+ *   dWa, dWv, dba, dbv  (+= over rows)  and  db_prev[j] = sum_i dz[i,j]
+ * Gradients are WRITTEN (not accumulated) to the given pointers. */
+int sfb200_heads_backward(const float* h, int64_t ldh, int64_t rows, int H, int A, const float* Wv, const float* Wa,
+                          const float* dlogits, const float* dvalues, int act, float* dz, int64_t lddz, float* dWv,
+                          float* dbv, float* dWa, float* dba, float* db_prev, void* workspace, void* stream);
+
+int64_t sfb200_linear_backward_workspace_bytes(int64_t M, int N, int K);
+/* backward of y = act(x.W^T + b) given dz = dL/d(pre-activation) [M,N]:
+ *   dW[N,K] = dz^T . x ;  (db is produced by the kernel that made dz)
+ *   if dx != NULL: dx[M,K] = (dz . W) * act_prev'(x)     (x is the previous layer's OUTPUT, act_prev its activation;
+ *                                                       pass SFB200_ACT_NONE for the input layer)
+ *   if db_prev != NULL: db_prev[k] = sum_i dx[i,k]  (bias gradient of the previous layer) */
+int sfb200_linear_backward(const float* dz, int64_t lddz, const float* x, int64_t ldx, const float* W, int64_t M,
+                           int N, int K, int act_prev, float* dW, float* dx, int64_t lddx, float* db_prev,
+                           int engine, void* workspace, void* stream);
+
+/* ------------------------------------------------------------- optimizer ---- */
+/* learner.py:782-797: global grad-norm clip (torch clip_grad_norm_: coef = min(max_norm/(norm+1e-6), 1), skipped
+ * when max_norm <= 0) followed by torch.optim.Adam's update (no weight decay / amsgrad) on FLAT buffers:
+ *   m = m + (1-b1)(g-m) ; v = b2 v + (1-b2) g^2 ; p -= (lr*lr_scale/(1-b1^t)) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
+ * lr_scale_num/lr_scale_den (device doubles or NULL): lr *= num/den  -- the valid-fraction scaling of :788-794
+ * grad_norm_out (device float[1], optional) receives the pre-clip norm.  workspace >= 4096 bytes.
+ * Scalars are doubles because the reference passes Python floats (torch converts them to fp32 op-math itself).
+ * g is read, not rescaled in place (the reference's in-place clip of .grad is unobservable on this path). */
+int sfb200_clip_adam_step(float* p, float* g, float* m, float* v, int64_t n, int64_t step, double lr, double beta1,
+                          double beta2, double eps, double max_grad_norm, const double* lr_scale_num,
+                          const double* lr_scale_den, float* grad_norm_out, void* workspace, void* stream);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* SFB200_H */

@@ -591,11 +591,11 @@ class OracleLearner:
                 epoch_actor_losses.append(float(actor_loss.detach()))
                 self.log.append(
                     dict(
-                        policy_loss=float(out["policy_loss"]),
-                        value_loss=float(out["value_loss"]),
-                        exploration_loss=float(out["exploration_loss"]),
-                        kl_loss=float(out["kl_loss"]),
-                        loss=float(out["loss"]),
+                        policy_loss=float(out["policy_loss"].detach()),
+                        value_loss=float(out["value_loss"].detach()),
+                        exploration_loss=float(out["exploration_loss"].detach()),
+                        kl_loss=float(out["kl_loss"].detach()),
+                        loss=float(out["loss"].detach()),
                         adv_mean=float(out["adv_mean"]),
                         adv_std=float(out["adv_std"]),
                         kl_old_mean=float(out["kl_old"].mean()),

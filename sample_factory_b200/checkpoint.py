@@ -1,0 +1,68 @@
+"""Checkpoint / resume in the reference's format (algo/learning/learner.py:257-386):
+
+    <train_dir>/<experiment>/checkpoint_p<policy_id>/checkpoint_<train_step:09d>_<env_steps>.pth
+    torch.save(dict(train_step, env_steps, best_performance, model=state_dict, optimizer=Adam.state_dict, curr_lr))
+
+written to a *_temp file and renamed (:334-360), keeping the last --keep_checkpoints files.  `model` uses the
+reference's state_dict keys (PolicyModel.state_dict), so reference tooling (enjoy / eval) can load our runs and we can
+warm-start from reference checkpoints.
+"""
+from __future__ import annotations
+
+import glob
+import os
+from typing import Optional
+
+import torch
+
+
+def checkpoint_dir(cfg, policy_id: int = 0) -> str:
+    d = os.path.join(cfg.train_dir, cfg.experiment, f"checkpoint_p{policy_id}")
+    os.makedirs(d, exist_ok=True)
+    return d
+
+
+def get_checkpoints(directory: str, pattern: str = "checkpoint_*"):
+    return sorted(f for f in glob.glob(os.path.join(directory, pattern)) if not f.endswith("_temp"))
+
+
+def save_checkpoint(cfg, model, learner) -> str:
+    d = checkpoint_dir(cfg, learner.policy_id)
+    ck = dict(
+        train_step=learner.train_step,
+        env_steps=learner.env_steps,
+        best_performance=-1e9,
+        model={k: v.cpu() for k, v in model.state_dict().items()},
+        optimizer=_cpu(model.optimizer_state_dict(learner.opt_step, learner.curr_lr, (cfg.adam_beta1, cfg.adam_beta2),
+                                                  cfg.adam_eps)),
+        curr_lr=learner.curr_lr,
+    )
+    name = f"checkpoint_{learner.train_step:09d}_{learner.env_steps}.pth"
+    tmp = os.path.join(d, name + "_temp")
+    torch.save(ck, tmp)
+    final = os.path.join(d, name)
+    os.rename(tmp, final)
+    files = get_checkpoints(d)
+    while len(files) > cfg.keep_checkpoints:
+        os.remove(files.pop(0))
+    return final
+
+
+def _cpu(osd: dict) -> dict:
+    for st in osd["state"].values():
+        for k, v in st.items():
+            if torch.is_tensor(v):
+                st[k] = v.cpu()
+    return osd
+
+
+def load_checkpoint(cfg, model, device) -> Optional[dict]:
+    d = checkpoint_dir(cfg, 0)
+    files = get_checkpoints(d)
+    if not files:
+        return None
+    ck = torch.load(files[-1], map_location="cpu", weights_only=False)
+    model.load_state_dict(ck["model"], strict=False)
+    opt_step = model.load_optimizer_state_dict(ck["optimizer"]) if "optimizer" in ck else 0
+    return dict(train_step=int(ck["train_step"]), env_steps=int(ck["env_steps"]), opt_step=opt_step,
+                curr_lr=ck.get("curr_lr", cfg.learning_rate))

@@ -1,0 +1,88 @@
+// Shared helpers for libsfb200 kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/sfb200.h"
+
+namespace sfb {
+
+void set_error(const char* fmt, ...);
+void count_launch();   // every kernel launch of this library is counted (sfb200_launch_count)
+
+#define SFB_CHECK_ARG(cond, ...)            \
+    do {                                    \
+        if (!(cond)) {                      \
+            sfb::set_error(__VA_ARGS__);    \
+            return 1;                       \
+        }                                   \
+    } while (0)
+
+#define SFB_CUDA_OK(expr)                                                                   \
+    do {                                                                                    \
+        cudaError_t _e = (expr);                                                            \
+        if (_e != cudaSuccess) {                                                            \
+            sfb::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return 2;                                                                       \
+        }                                                                                   \
+    } while (0)
+
+#define SFB_LAUNCH_OK()                                                                     \
+    do {                                                                                    \
+        sfb::count_launch();                                                                \
+        cudaError_t _e = cudaGetLastError();                                                \
+        if (_e != cudaSuccess) {                                                            \
+            sfb::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return 3;                                                                       \
+        }                                                                                   \
+    } while (0)
+
+int sm_count();
+
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---------------------------------------------------------------- device helpers
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// activation applied to a pre-activation value
+__device__ __forceinline__ float act_fwd(float z, int act) {
+    switch (act) {
+        case SFB200_ACT_ELU: return z > 0.f ? z : expm1f(z);   // nn.ELU(alpha=1)
+        case SFB200_ACT_RELU: return fmaxf(z, 0.f);
+        case SFB200_ACT_TANH: return tanhf(z);
+        default: return z;
+    }
+}
+// derivative of the activation expressed through its OUTPUT h = act(z)
+__device__ __forceinline__ float act_bwd_from_out(float h, int act) {
+    switch (act) {
+        case SFB200_ACT_ELU: return h > 0.f ? 1.f : h + 1.f;   // z<=0: d/dz (e^z-1) = e^z = h+1
+        case SFB200_ACT_RELU: return h > 0.f ? 1.f : 0.f;
+        case SFB200_ACT_TANH: return 1.f - h * h;
+        default: return 1.f;
+    }
+}
+
+__device__ __forceinline__ float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+
+}  // namespace sfb

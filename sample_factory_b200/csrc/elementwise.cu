@@ -1,0 +1,325 @@
+// HBM-bound elementwise kernels of the sampler / batch-prep path (see include/sfb200.h for the reference sites).
+// All are streaming kernels: coalesced 128-bit accesses where alignment allows, grid sized in multiples of the SM
+// count, no shared-memory staging (no reuse).
+#include "common.cuh"
+
+namespace sfb {
+
+// ---- obs normalisation ------------------------------------------------------------------------------------------
+// y = clamp(((x - sub) * inv_scale - mu) * (1/sqrt(var+eps)), +-clip), each op rounded separately (IEEE, no FMA
+// contraction) exactly like the reference's chain of in-place ATen ops (normalize.py:62-67,
+// running_mean_std.py:96-110).
+__device__ __forceinline__ float norm_one(float x, float sub, float inv_scale, bool do_sub, bool do_scale, bool do_rms,
+                                          float mu, float inv_sigma, float clip) {
+    if (do_sub) x = __fsub_rn(x, sub);
+    if (do_scale) x = __fmul_rn(x, inv_scale);
+    if (do_rms) {
+        x = __fmul_rn(__fsub_rn(x, mu), inv_sigma);
+        x = clampf(x, -clip, clip);
+    }
+    return x;
+}
+
+__device__ __forceinline__ void col_stats(const double* mean, const double* var, int c, float eps, float& mu,
+                                          float& inv_sigma) {
+    mu = (float)mean[c];
+    float sigma = __fsqrt_rn(__fadd_rn((float)var[c], eps));
+    inv_sigma = __fdiv_rn(1.0f, sigma);
+}
+
+// One kernel serves sfb200_normalize_obs and sfb200_sampler_pre_step: optional second output (raw copy into the
+// trajectory at [.., t]) so obs is read from HBM once.
+template <bool VEC4>
+__global__ void __launch_bounds__(256) normalize_kernel(const float* __restrict__ x, int64_t ldx, float* __restrict__ y,
+                                                        int64_t ldy, float* __restrict__ raw_copy, int64_t ld_copy,
+                                                        int64_t rows, int dim, const double* __restrict__ mean,
+                                                        const double* __restrict__ var, float sub, float inv_scale,
+                                                        int do_sub, int do_scale, float eps, float clip) {
+    const bool do_rms = mean != nullptr;
+    if (VEC4) {
+        const int dim4 = dim >> 2;
+        const int64_t total = rows * (int64_t)dim4;
+        for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+            const int64_t r = i / dim4;
+            const int c = (int)(i - r * dim4) << 2;
+            const float4 v = *reinterpret_cast<const float4*>(x + r * ldx + c);
+            if (raw_copy) *reinterpret_cast<float4*>(raw_copy + r * ld_copy + c) = v;
+            if (y) {
+                float in[4] = {v.x, v.y, v.z, v.w};
+                float out[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    float mu = 0.f, is = 1.f;
+                    if (do_rms) col_stats(mean, var, c + k, eps, mu, is);
+                    out[k] = norm_one(in[k], sub, inv_scale, do_sub, do_scale, do_rms, mu, is, clip);
+                }
+                *reinterpret_cast<float4*>(y + r * ldy + c) = make_float4(out[0], out[1], out[2], out[3]);
+            }
+        }
+    } else {
+        const int64_t total = rows * (int64_t)dim;
+        for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+            const int64_t r = i / dim;
+            const int c = (int)(i - r * dim);
+            const float v = x[r * ldx + c];
+            if (raw_copy) raw_copy[r * ld_copy + c] = v;
+            if (y) {
+                float mu = 0.f, is = 1.f;
+                if (do_rms) col_stats(mean, var, c, eps, mu, is);
+                y[r * ldy + c] = norm_one(v, sub, inv_scale, do_sub, do_scale, do_rms, mu, is, clip);
+            }
+        }
+    }
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+static int launch_normalize(const float* x, int64_t ldx, float* y, int64_t ldy, float* raw_copy, int64_t ld_copy,
+                            int64_t rows, int dim, const double* mean, const double* var, float sub_mean,
+                            float inv_scale, float eps, float clip, cudaStream_t st) {
+    if (rows == 0 || dim == 0) return 0;
+    const int do_sub = fabsf(sub_mean) > 1e-8f;
+    const int do_scale = fabsf(inv_scale - 1.0f) > 1e-8f;
+    const bool vec = (dim % 4 == 0) && (ldx % 4 == 0) && aligned16(x) && (!y || ((ldy % 4 == 0) && aligned16(y))) &&
+                     (!raw_copy || ((ld_copy % 4 == 0) && aligned16(raw_copy)));
+    const int64_t work = vec ? rows * (int64_t)(dim / 4) : rows * (int64_t)dim;
+    int64_t blocks = ceil_div(work, 256);
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    if (vec)
+        normalize_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(x, ldx, y, ldy, raw_copy, ld_copy, rows, dim, mean, var,
+                                                                 sub_mean, inv_scale, do_sub, do_scale, eps, clip);
+    else
+        normalize_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(x, ldx, y, ldy, raw_copy, ld_copy, rows, dim, mean,
+                                                                  var, sub_mean, inv_scale, do_sub, do_scale, eps, clip);
+    SFB_LAUNCH_OK();
+    return 0;
+}
+
+// ---- small strided helpers ----------------------------------------------------------------------------------------
+__global__ void copy_rows_kernel(const float* __restrict__ src, int64_t ss, float* __restrict__ dst, int64_t ds,
+                                 int64_t rows, int dim) {
+    const int64_t total = rows * (int64_t)dim;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / dim;
+        const int c = (int)(i - r * dim);
+        dst[r * ds + c] = src[r * ss + c];
+    }
+}
+
+// ---- post env step -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) post_step_kernel(const float* __restrict__ rew, const uint8_t* __restrict__ term,
+                                                        const uint8_t* __restrict__ trunc, int64_t n, float reward_scale,
+                                                        float reward_clip, int32_t policy_id, float* __restrict__ t_rew,
+                                                        uint8_t* __restrict__ t_done, uint8_t* __restrict__ t_to,
+                                                        int32_t* __restrict__ t_pid, int64_t stride,
+                                                        float* __restrict__ ep_ret, int32_t* __restrict__ ep_len,
+                                                        float* __restrict__ ep_min, float* __restrict__ ep_max,
+                                                        int32_t len_inc, double* __restrict__ stats,
+                                                        int64_t* __restrict__ step_counter) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (step_counter && i == 0) *step_counter += 1;
+    double c = 0.0, s_ret = 0.0, s_len = 0.0, s_min = 0.0, s_max = 0.0;
+    if (i < n) {
+        const float r_raw = rew[i];
+        const bool tm = term[i] != 0, tr = trunc[i] != 0;
+        const bool done = tm || tr;                                   // batched_sampling.py:317
+        float r = __fmul_rn(r_raw, reward_scale);                       // :209
+        r = clampf(r, -reward_clip, reward_clip);                       // :210
+        t_rew[i * stride] = r;
+        t_done[i * stride] = done ? 1 : 0;
+        t_to[i * stride] = tr ? 1 : 0;                                  // :328
+        t_pid[i * stride] = policy_id;
+        if (ep_ret) {
+            // _process_env_step :215-287 (episode accounting uses the RAW reward, :336 passes rewards_cpu)
+            float er = ep_ret[i] + r_raw;
+            int32_t el = ep_len[i] + len_inc;
+            float mn = fminf(ep_min[i], r_raw), mx = fmaxf(ep_max[i], r_raw);
+            if (done) {
+                c = 1.0; s_ret = er; s_len = el; s_min = mn; s_max = mx;
+                er = 0.f; el = 0; mn = INFINITY; mx = -INFINITY;
+            }
+            ep_ret[i] = er; ep_len[i] = el; ep_min[i] = mn; ep_max[i] = mx;
+        }
+    }
+    if (stats) {
+        c = warp_sum(c);
+        if (c > 0.0) {   // warp-uniform after the reduction
+            s_ret = warp_sum(s_ret); s_len = warp_sum(s_len); s_min = warp_sum(s_min); s_max = warp_sum(s_max);
+            if ((threadIdx.x & 31) == 0) {
+                atomicAdd(stats + 0, c); atomicAdd(stats + 1, s_ret); atomicAdd(stats + 2, s_len);
+                atomicAdd(stats + 3, s_min); atomicAdd(stats + 4, s_max);
+            }
+        }
+    }
+}
+
+// ---- synthetic tape env ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) tape_env_kernel(const int32_t* __restrict__ actions, int64_t n, int num_actions,
+                                                       int64_t env_off, int term_period, int trunc_period,
+                                                       const int64_t* __restrict__ step_counter, int64_t step_host,
+                                                       const float* __restrict__ tape, int64_t tape_len, int dim,
+                                                       float* __restrict__ obs_out, float* __restrict__ rew,
+                                                       uint8_t* __restrict__ term, uint8_t* __restrict__ trunc) {
+    const int64_t step = step_counter ? *step_counter : step_host;
+    const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+    if (tid < n) {
+        const int64_t env = env_off + tid;
+        rew[tid] = (float)actions[tid] / (float)num_actions;
+        const bool tm = ((step * 7 + env * 13) % term_period) == 0;
+        const bool tr = (((step + env) % trunc_period) == 0) && !tm;
+        term[tid] = tm; trunc[tid] = tr;
+    }
+    if (obs_out) {
+        const float* src = tape + ((step + 1) % tape_len) * n * dim;
+        const int64_t total = n * (int64_t)dim;
+        if ((dim & 3) == 0) {
+            const float4* s4 = reinterpret_cast<const float4*>(src);
+            float4* d4 = reinterpret_cast<float4*>(obs_out);
+            for (int64_t i = tid; i < (total >> 2); i += nthreads) d4[i] = s4[i];
+        } else {
+            for (int64_t i = tid; i < total; i += nthreads) obs_out[i] = src[i];
+        }
+    }
+}
+__global__ void counter_inc_kernel(int64_t* c) { *c += 1; }
+
+// ---- valids ----------------------------------------------------------------------------------------------------------
+__global__ void valids_kernel(const int32_t* __restrict__ pid, const float* __restrict__ pver, int64_t n_traj, int T,
+                              int32_t this_policy, float train_step, float max_lag, uint8_t* __restrict__ valids) {
+    const int64_t total = n_traj * (int64_t)(T + 1);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / (T + 1);
+        int t = (int)(i - r * (T + 1));
+        if (t == T) t = T - 1;                                         // learner.py:955
+        const int64_t j = r * T + t;
+        const bool v = (pid[j] == this_policy) && (__fsub_rn(train_step, pver[j]) < max_lag);   // :950-953
+        valids[i] = v ? 1 : 0;
+    }
+}
+
+// ---- scalar running-mean-std apply (returns normaliser) ---------------------------------------------------------------
+__global__ void rms_scalar_kernel(float* __restrict__ x, int64_t n, const double* __restrict__ mean,
+                                  const double* __restrict__ var, float eps, float clip, int denorm) {
+    const float mu = (float)mean[0];
+    const float sigma = __fsqrt_rn(__fadd_rn((float)var[0], eps));
+    const float inv = __fdiv_rn(1.0f, sigma);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float v = x[i];
+        if (denorm) v = __fadd_rn(__fmul_rn(clampf(v, -clip, clip), sigma), mu);    // running_mean_std.py:107-108
+        else v = clampf(__fmul_rn(__fsub_rn(v, mu), inv), -clip, clip);             // :109-110
+        x[i] = v;
+    }
+}
+
+static unsigned grid_for(int64_t work, int threads = 256, int waves = 8) {
+    int64_t blocks = ceil_div(work, threads);
+    const int64_t cap = (int64_t)sm_count() * waves;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (unsigned)blocks;
+}
+
+}  // namespace sfb
+
+using namespace sfb;
+
+extern "C" {
+
+int sfb200_normalize_obs(const float* x, int64_t ldx, float* y, int64_t ldy, int64_t rows, int dim, const double* mean,
+                         const double* var, float sub_mean, float inv_scale, float eps, float clip, void* stream) {
+    SFB_CHECK_ARG(x && y && rows >= 0 && dim > 0, "normalize_obs: bad arguments");
+    SFB_CHECK_ARG((mean == nullptr) == (var == nullptr), "normalize_obs: mean/var must both be set or both NULL");
+    return launch_normalize(x, ldx, y, ldy, nullptr, 0, rows, dim, mean, var, sub_mean, inv_scale, eps, clip,
+                            (cudaStream_t)stream);
+}
+
+int sfb200_sampler_pre_step(const float* obs, int64_t n_envs, int dim, float* traj_obs_t, int64_t traj_obs_stride,
+                            const float* rnn, int rnn_dim, float* traj_rnn_t, int64_t traj_rnn_stride, float* x_norm,
+                            const double* mean, const double* var, float sub_mean, float inv_scale, float eps,
+                            float clip, void* stream) {
+    SFB_CHECK_ARG(obs && traj_obs_t && n_envs >= 0 && dim > 0, "sampler_pre_step: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = launch_normalize(obs, dim, x_norm, dim, traj_obs_t, traj_obs_stride, n_envs, dim, mean, var, sub_mean,
+                              inv_scale, eps, clip, st);
+    if (rc) return rc;
+    if (rnn && traj_rnn_t && rnn_dim > 0) {
+        copy_rows_kernel<<<grid_for(n_envs * rnn_dim), 256, 0, st>>>(rnn, rnn_dim, traj_rnn_t, traj_rnn_stride, n_envs,
+                                                                     rnn_dim);
+        SFB_LAUNCH_OK();
+    }
+    return 0;
+}
+
+int sfb200_copy_rows(const float* src, int64_t src_stride, float* dst, int64_t dst_stride, int64_t rows, int dim,
+                     void* stream) {
+    SFB_CHECK_ARG(src && dst && rows >= 0 && dim > 0, "copy_rows: bad arguments");
+    if (rows == 0) return 0;
+    copy_rows_kernel<<<grid_for(rows * dim), 256, 0, (cudaStream_t)stream>>>(src, src_stride, dst, dst_stride, rows, dim);
+    SFB_LAUNCH_OK();
+    return 0;
+}
+
+int sfb200_sampler_post_step(const float* rew, const uint8_t* terminated, const uint8_t* truncated, int64_t n_envs,
+                             float reward_scale, float reward_clip, int32_t policy_id, float* traj_rewards_t,
+                             uint8_t* traj_dones_t, uint8_t* traj_time_outs_t, int32_t* traj_policy_id_t,
+                             int64_t traj_stride, float* ep_return, int32_t* ep_len, float* ep_min_raw,
+                             float* ep_max_raw, int32_t len_increment, double* stats, int64_t* step_counter,
+                             void* stream) {
+    SFB_CHECK_ARG(rew && terminated && truncated && traj_rewards_t && traj_dones_t && traj_time_outs_t &&
+                      traj_policy_id_t, "sampler_post_step: NULL argument");
+    SFB_CHECK_ARG(!ep_return || (ep_len && ep_min_raw && ep_max_raw), "sampler_post_step: episode arrays incomplete");
+    if (n_envs == 0) return 0;
+    post_step_kernel<<<(unsigned)ceil_div(n_envs, 256), 256, 0, (cudaStream_t)stream>>>(
+        rew, terminated, truncated, n_envs, reward_scale, reward_clip, policy_id, traj_rewards_t, traj_dones_t,
+        traj_time_outs_t, traj_policy_id_t, traj_stride, ep_return, ep_len, ep_min_raw, ep_max_raw, len_increment,
+        ep_return ? stats : nullptr, step_counter);
+    SFB_LAUNCH_OK();
+    return 0;
+}
+
+int sfb200_tape_env_step(const int32_t* actions, int64_t n_envs, int num_actions, int64_t env_index_offset,
+                         int term_period, int trunc_period, int64_t* step_counter, int64_t step_host, const float* tape,
+                         int64_t tape_len, int dim, float* obs_out, float* rew, uint8_t* terminated,
+                         uint8_t* truncated, void* stream) {
+    SFB_CHECK_ARG(actions && rew && terminated && truncated && n_envs > 0 && num_actions > 0 && term_period > 0 &&
+                      trunc_period > 0, "tape_env_step: bad arguments");
+    SFB_CHECK_ARG(!obs_out || (tape && tape_len > 0 && dim > 0), "tape_env_step: obs_out needs a tape");
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t work = n_envs;
+    if (obs_out) work = n_envs * (int64_t)dim / 4 > work ? n_envs * (int64_t)dim / 4 : work;
+    unsigned g = grid_for(work);
+    if ((int64_t)g * 256 < n_envs) g = (unsigned)ceil_div(n_envs, 256);
+    tape_env_kernel<<<g, 256, 0, st>>>(actions, n_envs, num_actions, env_index_offset, term_period, trunc_period,
+                                       step_counter, step_host, tape, tape_len, dim, obs_out, rew, terminated,
+                                       truncated);
+    SFB_LAUNCH_OK();
+    if (step_counter) {
+        counter_inc_kernel<<<1, 1, 0, st>>>(step_counter);
+        SFB_LAUNCH_OK();
+    }
+    return 0;
+}
+
+int sfb200_compute_valids(const int32_t* policy_id, const float* policy_version, int64_t n_traj, int T,
+                          int32_t this_policy, float train_step, float max_policy_lag, uint8_t* valids, void* stream) {
+    SFB_CHECK_ARG(policy_id && policy_version && valids && n_traj >= 0 && T > 0, "compute_valids: bad arguments");
+    if (n_traj == 0) return 0;
+    valids_kernel<<<grid_for(n_traj * (T + 1)), 256, 0, (cudaStream_t)stream>>>(policy_id, policy_version, n_traj, T,
+                                                                                  this_policy, train_step,
+                                                                                  max_policy_lag, valids);
+    SFB_LAUNCH_OK();
+    return 0;
+}
+
+int sfb200_rms_apply_scalar(float* x, int64_t n, const double* mean, const double* var, float eps, float clip,
+                            int denormalize, void* stream) {
+    SFB_CHECK_ARG(x && mean && var && n >= 0, "rms_apply_scalar: bad arguments");
+    if (n == 0) return 0;
+    rms_scalar_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(x, n, mean, var, eps, clip, denormalize);
+    SFB_LAUNCH_OK();
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,16 @@
+// Internal interface between the GEMM engines of libsfb200.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sfb {
+
+constexpr int SFB_TC_UNSUPPORTED = -1000;   // shape/alignment not handled by the tcgen05 engine -> caller uses SIMT
+
+// tcgen05 engine (gemm_tc.cu). Return 0, an error code, or SFB_TC_UNSUPPORTED.
+int tc_linear_act_forward(const float* x, int64_t ldx, const float* W, const float* b, float* y, int64_t ldy, int64_t M,
+                          int N, int K, int act, int engine, cudaStream_t st);
+int tc_linear_backward(const float* dz, int64_t lddz, const float* x, int64_t ldx, const float* W, int64_t M, int N,
+                       int K, int act_prev, float* dW, float* dx, int64_t lddx, int engine, float* ws, cudaStream_t st);
+
+}  // namespace sfb

@@ -1,0 +1,293 @@
+// Policy/value heads: critic_linear + distribution_linear (N = 1 + A output columns, far too narrow for a
+// tensor-core tile) fused with the categorical distribution math, forward and backward.  Both kernels stream h once
+// (HBM-bound: 4*H bytes per row read, backward also writes 4*H).
+#include <curand_kernel.h>
+
+#include "common.cuh"
+
+namespace sfb {
+
+constexpr int kHeadsMaxGroups = 512;
+
+// ---------------------------------------------------------------------------------------------------------------------
+// forward (+ optional sampling).  One warp handles RPW rows at a time; lane l owns columns l, l+32, ...
+// Wcat (smem): row 0 = Wv, rows 1..A = Wa.  AP = compile-time bound on A+1.
+// ---------------------------------------------------------------------------------------------------------------------
+template <int AP, int RPW>
+__global__ void __launch_bounds__(256) heads_forward_kernel(
+    const float* __restrict__ h, int64_t ldh, int64_t rows, int H, int A, const float* __restrict__ Wv,
+    const float* __restrict__ bv, const float* __restrict__ Wa, const float* __restrict__ ba, float* __restrict__ values,
+    int64_t values_stride, float* __restrict__ logits, int64_t logits_stride, const float* __restrict__ noise,
+    uint64_t seed, uint64_t offset_host, const int64_t* __restrict__ offset_dev, float* __restrict__ actions_f32,
+    int64_t actions_stride,
+    int32_t* __restrict__ env_actions, float* __restrict__ log_prob, int64_t log_prob_stride,
+    const float* __restrict__ pv_scalar, float* __restrict__ pv_out, int64_t pv_stride) {
+    extern __shared__ float wcat[];   // [(A+1)][H]
+    const int n_out = A + 1;
+    for (int i = threadIdx.x; i < n_out * H; i += blockDim.x) {
+        const int a = i / H, j = i - a * H;
+        wcat[i] = (a == 0) ? Wv[j] : Wa[(int64_t)(a - 1) * H + j];
+    }
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const float pv = pv_scalar ? *pv_scalar : 0.f;
+    const uint64_t offset = offset_host + (offset_dev ? (uint64_t)*offset_dev : 0ull);
+    const float my_bias = (lane == 0) ? bv[0] : (lane <= A ? ba[lane - 1] : 0.f);
+
+    for (int64_t r0 = warp * RPW; r0 < rows; r0 += nwarps * RPW) {
+        float acc[RPW][AP];
+#pragma unroll
+        for (int r = 0; r < RPW; ++r)
+#pragma unroll
+            for (int a = 0; a < AP; ++a) acc[r][a] = 0.f;
+
+        for (int j = lane; j < H; j += 32) {
+            float hv[RPW];
+#pragma unroll
+            for (int r = 0; r < RPW; ++r) hv[r] = (r0 + r < rows) ? h[(r0 + r) * ldh + j] : 0.f;
+#pragma unroll
+            for (int a = 0; a < AP; ++a) {
+                if (a < n_out) {
+                    const float w = wcat[a * H + j];
+#pragma unroll
+                    for (int r = 0; r < RPW; ++r) acc[r][a] = fmaf(hv[r], w, acc[r][a]);
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < RPW; ++r) {
+            const int64_t row = r0 + r;
+            if (row >= rows) break;   // warp-uniform
+            // lane a ends up with output a (0 = value, 1..A = logits)
+            float mine = 0.f;
+#pragma unroll
+            for (int a = 0; a < AP; ++a) {
+                if (a < n_out) {
+                    const float s = warp_sum(acc[r][a]);
+                    if (lane == a) mine = s;
+                }
+            }
+            mine += my_bias;
+            if (lane == 0) values[row * values_stride] = mine;
+            const bool is_logit = lane >= 1 && lane <= A;
+            if (logits && is_logit) logits[row * logits_stride + (lane - 1)] = mine;
+            if (actions_f32 == nullptr) continue;   // values / logits only
+
+            // CategoricalActionDistribution (action_distributions.py:110-148)
+            const float x = is_logit ? mine : -INFINITY;
+            const float m = warp_max(x);
+            const float e = is_logit ? expf(x - m) : 0.f;
+            const float s = warp_sum(e);
+            const float p = __fdiv_rn(e, s);                    // softmax :116
+            const float logp = (x - m) - logf(s);               // log_softmax :125
+            float q = 1.f;
+            if (is_logit) {
+                if (noise) q = noise[row * A + (lane - 1)];
+                else {
+                    curandStatePhilox4_32_10_t st;
+                    curand_init(seed, (unsigned long long)(row * A + (lane - 1)), offset, &st);
+                    q = -logf(curand_uniform(&st));             // Exp(1); uniform is in (0, 1]
+                    q = fmaxf(q, 1.0e-30f);
+                }
+            }
+            // torch.multinomial(p, 1, True) == argmax(p / q) (first index on ties)
+            float best = is_logit ? __fdiv_rn(p, q) : -INFINITY;
+            int idx = is_logit ? (lane - 1) : 0x7fffffff;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+                if (ob > best || (ob == best && oi < idx)) { best = ob; idx = oi; }
+            }
+            const float lp = __shfl_sync(0xffffffffu, logp, idx + 1);   // log_prob :145-148
+            if (lane == 0) {
+                actions_f32[row * actions_stride] = (float)idx;
+                if (env_actions) env_actions[row] = idx;
+                if (log_prob) log_prob[row * log_prob_stride] = lp;
+                if (pv_out) pv_out[row * pv_stride] = pv;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// backward.  grid = row groups; block = 256 threads, thread owns column j of the current 256-wide strip.
+// g[b][0] = dvalues[b], g[b][1..A] = dlogits[b][:].
+//   dz[b][j]      = (sum_a g[b][a] * Wcat[a][j]) * act'(h[b][j])
+//   dWcat[a][j]  += g[b][a] * h[b][j] ;  db_prev[j] += dz[b][j] ;  dbcat[a] += g[b][a]
+// per-block partial sums go to the workspace, a second kernel reduces them in fixed order (deterministic).
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kHbTile = 32;   // rows of coefficients staged in smem per iteration
+
+template <int AP>
+__global__ void __launch_bounds__(256) heads_backward_kernel(
+    const float* __restrict__ h, int64_t ldh, int64_t rows, int H, int A, const float* __restrict__ Wv,
+    const float* __restrict__ Wa, const float* __restrict__ dlogits, const float* __restrict__ dvalues, int act,
+    float* __restrict__ dz, int64_t lddz, float* __restrict__ part, int64_t rows_per_group) {
+    __shared__ float g_s[kHbTile][AP];
+    const int n_out = A + 1;
+    const int tid = threadIdx.x;
+    const int64_t r_begin = blockIdx.x * rows_per_group;
+    const int64_t r_end = (r_begin + rows_per_group < rows) ? r_begin + rows_per_group : rows;
+    const int64_t part_stride = (int64_t)(A + 2) * H + n_out;
+    float* my_part = part + blockIdx.x * part_stride;
+
+    float acc_g = 0.f;   // dbcat partial, threads tid < n_out (strip 0 only)
+    const int nstrips = (H + 255) / 256;
+    for (int strip = 0; strip < nstrips; ++strip) {
+        const int j = strip * 256 + tid;
+        const bool col_ok = j < H;
+        float w[AP], accw[AP];
+#pragma unroll
+        for (int a = 0; a < AP; ++a) {
+            accw[a] = 0.f;
+            w[a] = (col_ok && a < n_out) ? (a == 0 ? Wv[j] : Wa[(int64_t)(a - 1) * H + j]) : 0.f;
+        }
+        float acc_db = 0.f;
+        for (int64_t b0 = r_begin; b0 < r_end; b0 += kHbTile) {
+            const int nb = (int)((r_end - b0 < kHbTile) ? (r_end - b0) : kHbTile);
+            __syncthreads();
+            for (int i = tid; i < kHbTile * n_out; i += 256) {
+                const int bb = i / n_out, a = i - bb * n_out;
+                float v = 0.f;
+                if (bb < nb) v = (a == 0) ? dvalues[b0 + bb] : dlogits[(b0 + bb) * A + (a - 1)];
+                g_s[bb][a] = v;
+            }
+            __syncthreads();
+            if (strip == 0 && tid < n_out) {
+                for (int bb = 0; bb < nb; ++bb) acc_g += g_s[bb][tid];
+            }
+            if (col_ok) {
+#pragma unroll 4
+                for (int bb = 0; bb < nb; ++bb) {
+                    const float hv = h[(b0 + bb) * ldh + j];
+                    float s = 0.f;
+#pragma unroll
+                    for (int a = 0; a < AP; ++a) {
+                        if (a < n_out) {
+                            const float g = g_s[bb][a];
+                            s = fmaf(g, w[a], s);
+                            accw[a] = fmaf(g, hv, accw[a]);
+                        }
+                    }
+                    const float d = s * act_bwd_from_out(hv, act);
+                    dz[(b0 + bb) * lddz + j] = d;
+                    acc_db += d;
+                }
+            }
+        }
+        if (col_ok) {
+#pragma unroll
+            for (int a = 0; a < AP; ++a)
+                if (a < n_out) my_part[(int64_t)a * H + j] = accw[a];
+            my_part[(int64_t)n_out * H + j] = acc_db;
+        }
+    }
+    if (tid < n_out) my_part[(int64_t)(A + 2) * H + tid] = acc_g;
+}
+
+__global__ void heads_backward_reduce_kernel(const float* __restrict__ part, int groups, int H, int A,
+                                             float* __restrict__ dWv, float* __restrict__ dbv, float* __restrict__ dWa,
+                                             float* __restrict__ dba, float* __restrict__ db_prev) {
+    const int64_t part_stride = (int64_t)(A + 2) * H + (A + 1);
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= part_stride) return;
+    float s = 0.f;
+    for (int g = 0; g < groups; ++g) s += part[g * part_stride + i];
+    const int64_t wsz = (int64_t)(A + 1) * H;
+    if (i < H) dWv[i] = s;
+    else if (i < wsz) dWa[i - H] = s;
+    else if (i < wsz + H) { if (db_prev) db_prev[i - wsz] = s; }
+    else {
+        const int a = (int)(i - wsz - H);
+        if (a == 0) dbv[0] = s; else dba[a - 1] = s;
+    }
+}
+
+template <int AP, int RPW>
+static int launch_heads_forward(const float* h, int64_t ldh, int64_t rows, int H, int A, const float* Wv,
+                                const float* bv, const float* Wa, const float* ba, float* values, int64_t values_stride,
+                                float* logits, int64_t logits_stride, const float* noise, uint64_t seed, uint64_t offset,
+                                const int64_t* offset_dev, float* actions_f32, int64_t actions_stride, int32_t* env_actions, float* log_prob,
+                                int64_t log_prob_stride, const float* pv_scalar, float* pv_out, int64_t pv_stride,
+                                cudaStream_t st) {
+    const size_t smem = (size_t)(A + 1) * H * sizeof(float);
+    auto kern = heads_forward_kernel<AP, RPW>;
+    if (smem > 48 * 1024) SFB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int64_t blocks = ceil_div(ceil_div(rows, RPW), 8);
+    const int64_t cap = (int64_t)sm_count() * 4;
+    if (blocks > cap) blocks = cap;
+    kern<<<(unsigned)blocks, 256, smem, st>>>(h, ldh, rows, H, A, Wv, bv, Wa, ba, values, values_stride, logits,
+                                              logits_stride, noise, seed, offset, offset_dev, actions_f32, actions_stride,
+                                              env_actions, log_prob, log_prob_stride, pv_scalar, pv_out, pv_stride);
+    SFB_LAUNCH_OK();
+    return 0;
+}
+
+}  // namespace sfb
+
+using namespace sfb;
+
+extern "C" {
+
+int sfb200_heads_forward(const float* h, int64_t ldh, int64_t rows, int H, int A, const float* Wv, const float* bv,
+                         const float* Wa, const float* ba, float* values, int64_t values_stride, float* logits,
+                         int64_t logits_stride, const float* noise, uint64_t philox_seed, uint64_t philox_offset,
+                         const int64_t* philox_offset_dev, float* actions_f32, int64_t actions_stride, int32_t* env_actions_i32, float* log_prob,
+                         int64_t log_prob_stride, const float* policy_version_scalar, float* policy_version_out,
+                         int64_t pv_stride, void* stream) {
+    SFB_CHECK_ARG(h && Wv && bv && Wa && ba && values && rows >= 0 && H > 0, "heads_forward: bad arguments");
+    SFB_CHECK_ARG(A >= 1 && A <= 31, "heads_forward: supports 1 <= A <= 31 discrete actions, got %d", A);
+    SFB_CHECK_ARG((size_t)(A + 1) * H * sizeof(float) <= 200 * 1024, "heads_forward: (A+1)*H too large for smem");
+    if (rows == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+#define SFB_HF(AP, RPW)                                                                                               \
+    return launch_heads_forward<AP, RPW>(h, ldh, rows, H, A, Wv, bv, Wa, ba, values, values_stride, logits,            \
+                                         logits_stride, noise, philox_seed, philox_offset, philox_offset_dev, actions_f32,   \
+                                         actions_stride,                                                              \
+                                         env_actions_i32, log_prob, log_prob_stride, policy_version_scalar,            \
+                                         policy_version_out, pv_stride, st)
+    if (A + 1 <= 9) SFB_HF(9, 4);
+    if (A + 1 <= 17) SFB_HF(17, 2);
+    SFB_HF(32, 1);
+#undef SFB_HF
+}
+
+int64_t sfb200_heads_backward_workspace_bytes(int H, int A) {
+    return (int64_t)kHeadsMaxGroups * ((int64_t)(A + 2) * H + (A + 1)) * (int64_t)sizeof(float);
+}
+
+int sfb200_heads_backward(const float* h, int64_t ldh, int64_t rows, int H, int A, const float* Wv, const float* Wa,
+                          const float* dlogits, const float* dvalues, int act, float* dz, int64_t lddz, float* dWv,
+                          float* dbv, float* dWa, float* dba, float* db_prev, void* workspace, void* stream) {
+    SFB_CHECK_ARG(h && Wv && Wa && dlogits && dvalues && dz && dWv && dbv && dWa && dba && workspace && rows > 0 && H > 0,
+                  "heads_backward: bad arguments");
+    SFB_CHECK_ARG(A >= 1 && A <= 31, "heads_backward: supports 1 <= A <= 31, got %d", A);
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t groups = (int64_t)sm_count() * 2;
+    if (groups > kHeadsMaxGroups) groups = kHeadsMaxGroups;
+    int64_t rpg = ceil_div(rows, groups);
+    rpg = ceil_div(rpg, kHbTile) * kHbTile;
+    groups = ceil_div(rows, rpg);
+    float* part = (float*)workspace;
+    if (A + 1 <= 9)
+        heads_backward_kernel<9><<<(unsigned)groups, 256, 0, st>>>(h, ldh, rows, H, A, Wv, Wa, dlogits, dvalues, act, dz,
+                                                                   lddz, part, rpg);
+    else if (A + 1 <= 17)
+        heads_backward_kernel<17><<<(unsigned)groups, 256, 0, st>>>(h, ldh, rows, H, A, Wv, Wa, dlogits, dvalues, act,
+                                                                    dz, lddz, part, rpg);
+    else
+        heads_backward_kernel<32><<<(unsigned)groups, 256, 0, st>>>(h, ldh, rows, H, A, Wv, Wa, dlogits, dvalues, act,
+                                                                    dz, lddz, part, rpg);
+    SFB_LAUNCH_OK();
+    const int64_t total = (int64_t)(A + 2) * H + (A + 1);
+    heads_backward_reduce_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(part, (int)groups, H, A, dWv, dbv, dWa,
+                                                                                 dba, db_prev);
+    SFB_LAUNCH_OK();
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,372 @@
+// PPO loss, forward and backward fused (algo/learning/learner.py:586-657, :431-477), plus the per-minibatch advantage
+// statistics (:646-647) and the action-ratio pre-pass V-trace needs (:588-594).  One thread per sample; every input
+// is read exactly once (HBM-bound, ~(2A+9)*4 B read + (A+1)*4 B written per sample).
+#include "common.cuh"
+
+namespace sfb {
+
+constexpr int kLossMaxBlocks = 1024;
+constexpr int kNumPart = 12;
+// partial-sum slots
+enum { P_PL = 0, P_VL, P_ENT, P_KL, P_KLMAX, P_RDEV, P_RMIN, P_RMAX, P_CLIPPED, P_VSUM, P_COUNT, P_UNUSED };
+
+template <int AMAX>
+__device__ __forceinline__ void load_row(const float* __restrict__ p, int A, float (&out)[AMAX]) {
+    if ((A & 3) == 0 && ((reinterpret_cast<uintptr_t>(p) & 15u) == 0)) {
+#pragma unroll
+        for (int a = 0; a < AMAX; a += 4) {
+            if (a < A) {
+                const float4 v = *reinterpret_cast<const float4*>(p + a);
+                out[a] = v.x; out[a + 1] = v.y; out[a + 2] = v.z; out[a + 3] = v.w;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int a = 0; a < AMAX; ++a)
+            if (a < A) out[a] = p[a];
+    }
+}
+
+template <int AMAX>
+__device__ __forceinline__ void store_row(float* __restrict__ p, int A, const float (&v)[AMAX]) {
+    if ((A & 3) == 0 && ((reinterpret_cast<uintptr_t>(p) & 15u) == 0)) {
+#pragma unroll
+        for (int a = 0; a < AMAX; a += 4)
+            if (a < A) *reinterpret_cast<float4*>(p + a) = make_float4(v[a], v[a + 1], v[a + 2], v[a + 3]);
+    } else {
+#pragma unroll
+        for (int a = 0; a < AMAX; ++a)
+            if (a < A) p[a] = v[a];
+    }
+}
+
+// log_softmax / softmax of one row held in registers (action_distributions.py:116,125)
+template <int AMAX>
+__device__ __forceinline__ void row_softmax(const float (&l)[AMAX], int A, float (&p)[AMAX], float (&logp)[AMAX]) {
+    float m = -INFINITY;
+#pragma unroll
+    for (int a = 0; a < AMAX; ++a)
+        if (a < A) m = fmaxf(m, l[a]);
+    float s = 0.f;
+#pragma unroll
+    for (int a = 0; a < AMAX; ++a)
+        if (a < A) { p[a] = expf(l[a] - m); s += p[a]; }
+    const float logs = logf(s);
+#pragma unroll
+    for (int a = 0; a < AMAX; ++a)
+        if (a < A) { logp[a] = (l[a] - m) - logs; p[a] = __fdiv_rn(p[a], s); }
+}
+
+template <int AMAX>
+__global__ void __launch_bounds__(256) action_ratio_kernel(const float* __restrict__ logits, int A,
+                                                           const float* __restrict__ actions,
+                                                           const float* __restrict__ lp_old, int64_t batch,
+                                                           float* __restrict__ ratio) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= batch) return;
+    float l[AMAX], p[AMAX], logp[AMAX];
+    load_row<AMAX>(logits + i * A, A, l);
+    row_softmax<AMAX>(l, A, p, logp);
+    const int act = (int)actions[i];
+    float lp = 0.f;
+#pragma unroll
+    for (int a = 0; a < AMAX; ++a)
+        if (a < A && a == act) lp = logp[a];
+    ratio[i] = clampf(expf(lp - lp_old[i]), 0.05f, 20.0f);   // learner.py:589-592
+}
+
+// ---- advantage statistics -------------------------------------------------------------------------------------------
+__device__ __forceinline__ double block_sum(double v, double* sm) {
+    v = warp_sum(v);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) sm[w] = v;
+    __syncthreads();
+    double t = 0.0;
+    if (threadIdx.x < 32) {
+        t = (threadIdx.x < (blockDim.x >> 5)) ? sm[threadIdx.x] : 0.0;
+        t = warp_sum(t);
+    }
+    return t;   // valid in warp 0
+}
+__device__ __forceinline__ double block_max(double v, double* sm) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    __syncthreads();
+    if (lane == 0) sm[w] = v;
+    __syncthreads();
+    double t = -INFINITY;
+    if (threadIdx.x < 32) {
+        t = (threadIdx.x < (blockDim.x >> 5)) ? sm[threadIdx.x] : -INFINITY;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t = fmax(t, __shfl_xor_sync(0xffffffffu, t, o));
+    }
+    return t;
+}
+
+__global__ void __launch_bounds__(256) adv_stats_partial_kernel(const float* __restrict__ adv,
+                                                                const uint8_t* __restrict__ valids, int64_t batch,
+                                                                double* __restrict__ part) {
+    __shared__ double sm[8];
+    double c = 0.0, s = 0.0, ss = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < batch; i += (int64_t)gridDim.x * blockDim.x) {
+        if (valids[i]) {
+            const double a = (double)adv[i];
+            c += 1.0; s += a; ss += a * a;
+        }
+    }
+    c = block_sum(c, sm); s = block_sum(s, sm); ss = block_sum(ss, sm);
+    if (threadIdx.x == 0) { part[blockIdx.x * 3 + 0] = c; part[blockIdx.x * 3 + 1] = s; part[blockIdx.x * 3 + 2] = ss; }
+}
+
+__device__ __forceinline__ void adv_finalize(double c, double s, double ss, double* stats) {
+    const double mean = c > 0.0 ? s / c : 0.0;
+    // torch.std_mean default: unbiased (n-1); n == 1 gives NaN in torch too
+    const double var = (ss - s * mean) / (c - 1.0);
+    stats[SFB200_LS_NUM_VALID] = c;
+    stats[SFB200_LS_ADV_MEAN] = (double)(float)mean;
+    stats[SFB200_LS_ADV_STD] = (double)(float)sqrt(var > 0.0 ? var : 0.0);
+}
+
+__global__ void adv_stats_finalize_kernel(const double* __restrict__ part, int nblocks, double* __restrict__ stats,
+                                          double* __restrict__ dp_partials) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double c = 0.0, s = 0.0, ss = 0.0;
+    for (int b = 0; b < nblocks; ++b) { c += part[b * 3]; s += part[b * 3 + 1]; ss += part[b * 3 + 2]; }
+    if (dp_partials) { dp_partials[0] = c; dp_partials[1] = s; dp_partials[2] = ss; }
+    adv_finalize(c, s, ss, stats);
+}
+__global__ void adv_stats_from_partials_kernel(const double* __restrict__ dp, double* __restrict__ stats) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) adv_finalize(dp[0], dp[1], dp[2], stats);
+}
+
+// ---- the loss ---------------------------------------------------------------------------------------------------------
+template <int AMAX>
+__global__ void __launch_bounds__(256) ppo_loss_kernel(
+    const float* __restrict__ logits, const float* __restrict__ values, int A, const float* __restrict__ actions,
+    const float* __restrict__ lp_old, const float* __restrict__ v_old, const float* __restrict__ adv,
+    const float* __restrict__ targets, const uint8_t* __restrict__ valids, const float* __restrict__ logits_old,
+    int64_t batch, float clip_lo, float clip_hi, float clip_value, float c_ent, float c_val, float c_kl,
+    float grad_scale, float* __restrict__ dlogits, float* __restrict__ dvalues, const double* __restrict__ stats,
+    double* __restrict__ part) {
+    __shared__ double sm[8];
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const double n_valid = stats[SFB200_LS_NUM_VALID];
+    const float adv_mean = (float)stats[SFB200_LS_ADV_MEAN];
+    const float adv_std = fmaxf((float)stats[SFB200_LS_ADV_STD], 1e-7f);   // clamp_min :647
+    const float w = n_valid > 0.0 ? (float)((double)grad_scale / n_valid) : 0.f;
+
+    double s_pl = 0, s_vl = 0, s_ent = 0, s_kl = 0, s_rdev = 0, s_clip = 0, s_v = 0, s_cnt = 0;
+    double m_kl = -INFINITY, m_rmin = -INFINITY /* holds -min */, m_rmax = -INFINITY;
+
+    if (i < batch) {
+        const float v = values[i];
+        s_v = v;
+        float dl[AMAX];
+#pragma unroll
+        for (int a = 0; a < AMAX; ++a) dl[a] = 0.f;
+        float dv = 0.f;
+        if (valids[i]) {
+            s_cnt = 1.0;
+            float l[AMAX], p[AMAX], logp[AMAX];
+            load_row<AMAX>(logits + i * A, A, l);
+            row_softmax<AMAX>(l, A, p, logp);
+            const int act = (int)actions[i];                                   // .long() :146
+            float lp = 0.f;
+#pragma unroll
+            for (int a = 0; a < AMAX; ++a)
+                if (a < A && a == act) lp = logp[a];
+            const float ratio_raw = expf(lp - lp_old[i]);                       // :589
+            const float ratio = clampf(ratio_raw, 0.05f, 20.0f);                // :592
+            const float advn = __fdiv_rn(__fsub_rn(adv[i], adv_mean), adv_std); // :647
+            // _policy_loss :431-439
+            const float rc = clampf(ratio, clip_lo, clip_hi);
+            const float s1 = ratio * advn, s2 = rc * advn;
+            s_pl = fminf(s1, s2);
+            const bool in_window = ratio >= clip_lo && ratio <= clip_hi;
+            const float g_ratio = (in_window || s1 < s2) ? -advn : 0.f;         // d(-min)/d ratio (ties split evenly)
+            const float dratio_dlp = (ratio_raw >= 0.05f && ratio_raw <= 20.0f) ? ratio_raw : 0.f;
+            const float g_lp = w * g_ratio * dratio_dlp;
+            // entropy :150-152, :473-477
+            float H = 0.f;
+#pragma unroll
+            for (int a = 0; a < AMAX; ++a)
+                if (a < A) H -= logp[a] * p[a];
+            s_ent = H;
+            // KL(new || old) :154-158
+            float kl = 0.f;
+            float lq[AMAX];
+            if (logits_old) {
+                float lo[AMAX], po[AMAX];
+                load_row<AMAX>(logits_old + i * A, A, lo);
+                row_softmax<AMAX>(lo, A, po, lq);
+#pragma unroll
+                for (int a = 0; a < AMAX; ++a)
+                    if (a < A) kl += p[a] * (logp[a] - lq[a]);
+                s_kl = kl;
+                m_kl = kl;
+            }
+            const float we = w * c_ent, wk = (logits_old ? w * c_kl : 0.f);
+#pragma unroll
+            for (int a = 0; a < AMAX; ++a) {
+                if (a < A) {
+                    float g = g_lp * ((a == act ? 1.f : 0.f) - p[a]);
+                    g += we * p[a] * (logp[a] + H);
+                    if (logits_old) g += wk * p[a] * ((logp[a] - lq[a]) - kl);
+                    dl[a] = g;
+                }
+            }
+            // _value_loss :441-459
+            const float vo = v_old[i], R = targets[i];
+            const float diff = v - vo;
+            const float vc = vo + clampf(diff, -clip_value, clip_value);
+            const float l1 = (v - R) * (v - R), l2 = (vc - R) * (vc - R);
+            s_vl = fmaxf(l1, l2);
+            const bool inside = diff >= -clip_value && diff <= clip_value;
+            const float g1 = 2.f * (v - R), g2 = inside ? 2.f * (vc - R) : 0.f;
+            const float gv = (l1 > l2) ? g1 : ((l2 > l1) ? g2 : 0.5f * (g1 + g2));
+            dv = w * c_val * gv;
+            // summaries :843-923
+            s_rdev = fabsf(1.f - ratio);
+            m_rmin = -(double)ratio;
+            m_rmax = ratio;
+            s_clip = (ratio < clip_lo ? 1.0 : 0.0) + (ratio > clip_hi ? 1.0 : 0.0);
+        }
+        store_row<AMAX>(dlogits + i * A, A, dl);
+        dvalues[i] = dv;
+    }
+    double* my = part + (int64_t)blockIdx.x * kNumPart;
+    double t;
+    t = block_sum(s_pl, sm);   if (threadIdx.x == 0) my[P_PL] = t;
+    t = block_sum(s_vl, sm);   if (threadIdx.x == 0) my[P_VL] = t;
+    t = block_sum(s_ent, sm);  if (threadIdx.x == 0) my[P_ENT] = t;
+    t = block_sum(s_kl, sm);   if (threadIdx.x == 0) my[P_KL] = t;
+    t = block_max(m_kl, sm);   if (threadIdx.x == 0) my[P_KLMAX] = t;
+    t = block_sum(s_rdev, sm); if (threadIdx.x == 0) my[P_RDEV] = t;
+    t = block_max(m_rmin, sm); if (threadIdx.x == 0) my[P_RMIN] = t;
+    t = block_max(m_rmax, sm); if (threadIdx.x == 0) my[P_RMAX] = t;
+    t = block_sum(s_clip, sm); if (threadIdx.x == 0) my[P_CLIPPED] = t;
+    t = block_sum(s_v, sm);    if (threadIdx.x == 0) my[P_VSUM] = t;
+    t = block_sum(s_cnt, sm);  if (threadIdx.x == 0) my[P_COUNT] = t;
+}
+
+__global__ void __launch_bounds__(256) ppo_loss_finalize_kernel(const double* __restrict__ part, int nblocks,
+                                                                int64_t batch, float c_ent, float c_val, float c_kl,
+                                                                double* __restrict__ stats) {
+    __shared__ double sm[8];
+    double acc[kNumPart];
+#pragma unroll
+    for (int k = 0; k < kNumPart; ++k) acc[k] = (k == P_KLMAX || k == P_RMIN || k == P_RMAX) ? -INFINITY : 0.0;
+    for (int b = threadIdx.x; b < nblocks; b += blockDim.x) {
+#pragma unroll
+        for (int k = 0; k < kNumPart; ++k) {
+            const double v = part[(int64_t)b * kNumPart + k];
+            if (k == P_KLMAX || k == P_RMIN || k == P_RMAX) acc[k] = fmax(acc[k], v);
+            else acc[k] += v;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < kNumPart; ++k) {
+        if (k == P_KLMAX || k == P_RMIN || k == P_RMAX) acc[k] = block_max(acc[k], sm);
+        else acc[k] = block_sum(acc[k], sm);
+    }
+    if (threadIdx.x == 0) {
+        const double n = stats[SFB200_LS_NUM_VALID];
+        const double inv = n > 0.0 ? 1.0 / n : 0.0;
+        const double pl = -acc[P_PL] * inv;
+        const double vl = (double)c_val * acc[P_VL] * inv;
+        const double el = -(double)c_ent * acc[P_ENT] * inv;
+        const double kl = (double)c_kl * acc[P_KL] * inv;
+        stats[SFB200_LS_POLICY_LOSS] = pl;
+        stats[SFB200_LS_VALUE_LOSS] = vl;
+        stats[SFB200_LS_EXPLORATION_LOSS] = el;
+        stats[SFB200_LS_KL_LOSS] = kl;
+        stats[SFB200_LS_KL_OLD_MEAN] = acc[P_KL] * inv;
+        stats[SFB200_LS_KL_OLD_MAX] = acc[P_KLMAX];
+        stats[SFB200_LS_ENTROPY_MEAN] = acc[P_ENT] * inv;
+        stats[SFB200_LS_RATIO_MEAN_ABS_DEV] = acc[P_RDEV] * inv;
+        stats[SFB200_LS_RATIO_MIN] = -acc[P_RMIN];
+        stats[SFB200_LS_RATIO_MAX] = acc[P_RMAX];
+        stats[SFB200_LS_FRACTION_CLIPPED] = acc[P_CLIPPED] * inv;
+        stats[SFB200_LS_VALUE_MEAN] = batch > 0 ? acc[P_VSUM] / (double)batch : 0.0;
+        stats[SFB200_LS_TOTAL_LOSS] = pl + vl + el + kl;
+    }
+}
+
+}  // namespace sfb
+
+using namespace sfb;
+
+extern "C" {
+
+int64_t sfb200_loss_workspace_bytes(int64_t batch) {
+    int64_t blocks = ceil_div(batch > 0 ? batch : 1, 256);
+    return (blocks * kNumPart + (int64_t)kLossMaxBlocks * 3) * (int64_t)sizeof(double);
+}
+
+int sfb200_action_ratio(const float* logits, int A, const float* actions_f32, const float* log_prob_old, int64_t batch,
+                        float* ratio, void* stream) {
+    SFB_CHECK_ARG(logits && actions_f32 && log_prob_old && ratio && batch >= 0, "action_ratio: bad arguments");
+    SFB_CHECK_ARG(A >= 1 && A <= 32, "action_ratio: supports 1 <= A <= 32");
+    if (batch == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned g = (unsigned)ceil_div(batch, 256);
+    if (A <= 8) action_ratio_kernel<8><<<g, 256, 0, st>>>(logits, A, actions_f32, log_prob_old, batch, ratio);
+    else if (A <= 16) action_ratio_kernel<16><<<g, 256, 0, st>>>(logits, A, actions_f32, log_prob_old, batch, ratio);
+    else action_ratio_kernel<32><<<g, 256, 0, st>>>(logits, A, actions_f32, log_prob_old, batch, ratio);
+    SFB_LAUNCH_OK();
+    return 0;
+}
+
+int sfb200_adv_stats(const float* adv, const uint8_t* valids, int64_t batch, double* stats, double* dp_partials,
+                     void* workspace, void* stream) {
+    SFB_CHECK_ARG(adv && valids && stats && workspace && batch > 0, "adv_stats: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t blocks = ceil_div(batch, 256 * 4);
+    if (blocks > kLossMaxBlocks) blocks = kLossMaxBlocks;
+    // the adv-stat partials live after the loss partials in the workspace
+    double* part = (double*)workspace + ceil_div(batch, 256) * kNumPart;
+    adv_stats_partial_kernel<<<(unsigned)blocks, 256, 0, st>>>(adv, valids, batch, part);
+    SFB_LAUNCH_OK();
+    adv_stats_finalize_kernel<<<1, 32, 0, st>>>(part, (int)blocks, stats, dp_partials);
+    SFB_LAUNCH_OK();
+    return 0;
+}
+
+int sfb200_adv_stats_finalize(const double* dp_partials, double* stats, void* stream) {
+    SFB_CHECK_ARG(dp_partials && stats, "adv_stats_finalize: bad arguments");
+    adv_stats_from_partials_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(dp_partials, stats);
+    SFB_LAUNCH_OK();
+    return 0;
+}
+
+int sfb200_ppo_loss_fwd_bwd(const float* logits, const float* values, int A, const float* actions_f32,
+                            const float* log_prob_old, const float* values_old, const float* adv, const float* targets,
+                            const uint8_t* valids, const float* logits_old, int64_t batch, float clip_ratio,
+                            float clip_value, float exploration_coeff, float value_coeff, float kl_coeff,
+                            float grad_scale, float* dlogits, float* dvalues, double* stats, void* workspace,
+                            void* stream) {
+    SFB_CHECK_ARG(logits && values && actions_f32 && log_prob_old && values_old && adv && targets && valids && dlogits &&
+                      dvalues && stats && workspace && batch > 0, "ppo_loss_fwd_bwd: bad arguments");
+    SFB_CHECK_ARG(A >= 1 && A <= 32, "ppo_loss_fwd_bwd: supports 1 <= A <= 32");
+    cudaStream_t st = (cudaStream_t)stream;
+    const float clip_hi = 1.0f + clip_ratio;          // learner.py:544
+    const float clip_lo = 1.0f / clip_hi;             // :546
+    const unsigned g = (unsigned)ceil_div(batch, 256);
+    double* part = (double*)workspace;
+#define SFB_PL(AM)                                                                                                   \
+    ppo_loss_kernel<AM><<<g, 256, 0, st>>>(logits, values, A, actions_f32, log_prob_old, values_old, adv, targets,    \
+                                           valids, logits_old, batch, clip_lo, clip_hi, clip_value, exploration_coeff, \
+                                           value_coeff, kl_coeff, grad_scale, dlogits, dvalues, stats, part)
+    if (A <= 8) SFB_PL(8);
+    else if (A <= 16) SFB_PL(16);
+    else SFB_PL(32);
+#undef SFB_PL
+    SFB_LAUNCH_OK();
+    ppo_loss_finalize_kernel<<<1, 256, 0, st>>>(part, (int)g, batch, exploration_coeff, value_coeff, kl_coeff, stats);
+    SFB_LAUNCH_OK();
+    return 0;
+}
+
+}  // extern "C"

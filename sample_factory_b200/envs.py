@@ -1,0 +1,132 @@
+"""Environment boundary: registry (reference envs/env_utils.py:12-31, envs/create_env.py:13-46) and the batched
+GPU-env contract the device sampler drives (what the reference's BatchedVecEnv guarantees, make_env.py:147-237):
+
+    env.num_agents : int
+    env.obs_dim / env.num_actions
+    env.reset() -> obs                       float32 [num_agents, obs_dim]
+    env.step(actions) -> (obs, rew, terminated, truncated)
+        actions    int32  [num_agents]   (device tensor when env_gpu_actions, else numpy; batched_sampling.py:62-82)
+        obs        float32 [num_agents, obs_dim]
+        rew        float32 [num_agents]; terminated / truncated bool [num_agents]
+    auto-reset is the env's job (make_env.py:89-94).
+
+`TapeVecEnv` is the synthetic env of BASELINE.json config 2 (Box(64) obs, Discrete(8)): GPU-resident, one CUDA kernel
+per step, buffers reused across steps so a whole rollout can be captured in a CUDA graph.  `HostTapeVecEnv` is the
+same env living in host memory (numpy + pinned buffers) -- the shape of a CPU-simulated env -- used for the
+end-to-end (H2D/D2H inside the timed region) measurement.
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, Optional, Tuple
+
+import numpy as np
+import torch
+from torch import Tensor
+
+from . import ops
+
+_ENV_REGISTRY: Dict[str, Callable] = {}
+
+
+def register_env(env_name: str, make_env_func: Callable) -> None:
+    """Same contract as the reference: make_env_func(full_env_name, cfg, env_config, render_mode=None) -> env."""
+    assert callable(make_env_func), f"{make_env_func=} must be callable"
+    _ENV_REGISTRY[env_name] = make_env_func
+
+
+def create_env(full_env_name: str, cfg=None, env_config=None, render_mode: Optional[str] = None):
+    if full_env_name not in _ENV_REGISTRY:
+        raise ValueError(f"Env name {full_env_name} is not registered. See register_env()!")
+    return _ENV_REGISTRY[full_env_name](full_env_name, cfg, env_config, render_mode)
+
+
+def global_env_registry() -> Dict[str, Callable]:
+    return _ENV_REGISTRY
+
+
+class TapeVecEnv:
+    """GPU-resident synthetic vector env.  obs_t = tape[t % L] (pre-generated N(0,1)-like tape in HBM),
+    reward = action / num_actions, terminated / truncated = fixed integer rules of (step, env).
+    Identical rules to oracle.appo_oracle.TapeVecEnv so CPU and GPU rollouts are comparable step by step."""
+
+    is_gpu_env = True
+
+    def __init__(self, tape: Tensor, num_actions: int, term_period: int = 37, trunc_period: int = 11,
+                 env_index_offset: int = 0):
+        assert tape.is_cuda and tape.dtype == torch.float32 and tape.dim() == 3 and tape.is_contiguous()
+        self.tape = tape
+        self.tape_len, self.num_agents, self.obs_dim = tape.shape
+        self.num_actions = num_actions
+        self.term_period, self.trunc_period = term_period, trunc_period
+        self.env_index_offset = env_index_offset
+        dev = tape.device
+        self.step_counter = torch.zeros(1, dtype=torch.int64, device=dev)  # device-side so graphs can replay
+        self.obs = torch.empty((self.num_agents, self.obs_dim), dtype=torch.float32, device=dev)
+        self.rew = torch.empty(self.num_agents, dtype=torch.float32, device=dev)
+        self.terminated = torch.empty(self.num_agents, dtype=torch.bool, device=dev)
+        self.truncated = torch.empty(self.num_agents, dtype=torch.bool, device=dev)
+
+    def reset(self) -> Tensor:
+        self.step_counter.zero_()
+        self.obs.copy_(self.tape[0])
+        return self.obs
+
+    def step(self, actions: Tensor) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+        ops.tape_env_step(actions, self.num_actions, self.env_index_offset, self.term_period, self.trunc_period,
+                          self.step_counter, 0, self.tape, self.obs, self.rew, self.terminated, self.truncated)
+        return self.obs, self.rew, self.terminated, self.truncated
+
+
+class HostTapeVecEnv:
+    """The same env simulated on the HOST (numpy, pinned staging buffers): every step the sampler copies the
+    observation batch host->device and the actions device->host, as it must for any CPU-simulated env."""
+
+    is_gpu_env = False
+
+    def __init__(self, tape: np.ndarray, num_actions: int, device: torch.device, term_period: int = 37,
+                 trunc_period: int = 11, env_index_offset: int = 0):
+        self.tape = torch.from_numpy(np.ascontiguousarray(tape, dtype=np.float32)).pin_memory()
+        self.tape_len, self.num_agents, self.obs_dim = self.tape.shape
+        self.num_actions = num_actions
+        self.term_period, self.trunc_period = term_period, trunc_period
+        self.device = device
+        self.t = 0
+        self.env_idx = np.arange(self.num_agents, dtype=np.int64) + env_index_offset
+        n = self.num_agents
+        self.actions_host = torch.empty(n, dtype=torch.int32).pin_memory()
+        self.rew_host = torch.empty(n, dtype=torch.float32).pin_memory()
+        self.term_host = torch.empty(n, dtype=torch.bool).pin_memory()
+        self.trunc_host = torch.empty(n, dtype=torch.bool).pin_memory()
+        self.obs = torch.empty((n, self.obs_dim), dtype=torch.float32, device=device)
+        self.rew = torch.empty(n, dtype=torch.float32, device=device)
+        self.terminated = torch.empty(n, dtype=torch.bool, device=device)
+        self.truncated = torch.empty(n, dtype=torch.bool, device=device)
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+
+    def reset(self) -> Tensor:
+        self.t = 0
+        self.obs.copy_(self.tape[0], non_blocking=True)
+        self.h2d_bytes += self.obs.numel() * 4
+        return self.obs
+
+    def step(self, actions: Tensor) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+        # D2H: the actions the host simulator needs (synchronises -- a host env cannot start before it has them)
+        self.actions_host.copy_(actions, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        self.d2h_bytes += self.actions_host.numel() * 4
+        a = self.actions_host.numpy()
+        t = self.t
+        np.divide(a, float(self.num_actions), out=self.rew_host.numpy(), casting="unsafe")
+        term = ((t * 7 + self.env_idx * 13) % self.term_period) == 0
+        trunc = (((t + self.env_idx) % self.trunc_period) == 0) & ~term
+        self.term_host.numpy()[:] = term
+        self.trunc_host.numpy()[:] = trunc
+        self.t += 1
+        # H2D: next observation batch + step results
+        self.obs.copy_(self.tape[self.t % self.tape_len], non_blocking=True)
+        self.rew.copy_(self.rew_host, non_blocking=True)
+        self.terminated.copy_(self.term_host, non_blocking=True)
+        self.truncated.copy_(self.trunc_host, non_blocking=True)
+        self.h2d_bytes += self.obs.numel() * 4 + self.rew.numel() * 4 + 2 * self.num_agents
+        return self.obs, self.rew, self.terminated, self.truncated

@@ -1,0 +1,367 @@
+"""Device PPO / V-trace learner mirroring algo/learning/learner.py (Learner.train :1036, _prepare_batch :943-1034,
+_calculate_losses :537-669, _train :671-841) with every tensor op replaced by a libsfb200 kernel.
+
+Differences from the reference that are deliberate (B200-first) and do not change results:
+  * no autograd: the backward pass is explicit (sfb200_ppo_loss_fwd_bwd -> heads_backward -> linear_backward)
+  * no per-minibatch host syncs: loss scalars stay in a device stats block and are read once per epoch
+  * V-trace runs on the device (the reference moves the minibatch to the CPU, :602-640)
+  * data parallel (new functionality): gradients, normalizer moments and advantage statistics are
+    all-reduced over NCCL so that G GPUs x N envs equals one GPU with G*N envs.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+import torch.distributed as dist
+from torch import Tensor
+
+from . import ops
+from .dist_utils import pooled_moments_
+from .model import PolicyModel
+
+
+class KlAdaptiveScheduler:
+    """learner.py:46-86 (per-minibatch and per-epoch variants)."""
+
+    def __init__(self, cfg, per_epoch: bool):
+        self.thr = cfg.lr_schedule_kl_threshold
+        self.min_lr, self.max_lr = cfg.lr_adaptive_min, cfg.lr_adaptive_max
+        self.per_epoch = per_epoch
+        self.n = cfg.num_batches_per_epoch if per_epoch else 1
+
+    def invoke_after_each_minibatch(self):
+        return not self.per_epoch
+
+    def invoke_after_each_epoch(self):
+        return self.per_epoch
+
+    def update(self, lr, recent_kls):
+        mean_kl = float(np.mean(recent_kls[-self.n:]))
+        if mean_kl > 2.0 * self.thr:
+            lr = max(lr / 1.5, self.min_lr)
+        if mean_kl < 0.5 * self.thr:
+            lr = min(lr * 1.5, self.max_lr)
+        return lr
+
+
+class LinearDecayScheduler:
+    """learner.py:88-100 + utils/decay.py:4-47 restricted to the two-point schedule it is used with."""
+
+    def __init__(self, cfg):
+        self.num_updates = cfg.train_for_env_steps // cfg.batch_size * cfg.num_epochs
+        self.lr0 = cfg.learning_rate
+        self.step = 0
+
+    def invoke_after_each_minibatch(self):
+        return True
+
+    def invoke_after_each_epoch(self):
+        return False
+
+    def update(self, lr, recent_kls):
+        self.step += 1
+        if self.step >= self.num_updates:
+            return 0.0
+        return self.lr0 + (0.0 - self.lr0) * (self.step / self.num_updates)
+
+
+class ConstantScheduler:
+    def invoke_after_each_minibatch(self):
+        return False
+
+    def invoke_after_each_epoch(self):
+        return False
+
+    def update(self, lr, recent_kls):
+        return lr
+
+
+def get_lr_scheduler(cfg):
+    """learner.py:103-113"""
+    if cfg.lr_schedule == "constant":
+        return ConstantScheduler()
+    if cfg.lr_schedule == "kl_adaptive_minibatch":
+        return KlAdaptiveScheduler(cfg, per_epoch=False)
+    if cfg.lr_schedule == "kl_adaptive_epoch":
+        return KlAdaptiveScheduler(cfg, per_epoch=True)
+    if cfg.lr_schedule == "linear_decay":
+        return LinearDecayScheduler(cfg)
+    raise RuntimeError(f"Unknown scheduler {cfg.lr_schedule}")
+
+
+class Learner:
+    def __init__(self, cfg, model: PolicyModel, num_traj: int, engine: int = ops.GEMM_SIMT,
+                 process_group: Optional["dist.ProcessGroup"] = None):
+        self.cfg = cfg
+        self.model = model
+        self.device = model.device
+        self.engine = engine
+        self.pg = process_group
+        self.world_size = dist.get_world_size(process_group) if (process_group is not None or (
+            dist.is_available() and dist.is_initialized())) else 1
+        if self.world_size > 1 and self.pg is None:
+            self.pg = dist.group.WORLD
+        spec = model.spec
+        self.act = ops.ACT[spec.nonlinearity]
+        self.N, self.T = num_traj, cfg.rollout
+        self.policy_id = cfg.policy_id
+        self.train_step = 0  # number of SGD steps == policy version (learner.py:142, :388-392)
+        self.env_steps = 0
+        self.curr_lr = cfg.learning_rate
+        self.lr_scheduler = get_lr_scheduler(cfg)
+        self.last_stats: Dict[str, float] = {}
+
+        # verify_cfg-style invariants of the path (cfg/arguments.py:105-201)
+        E = self.N * self.T
+        assert cfg.batch_size * cfg.num_batches_per_epoch == E, (
+            f"sync mode: batch_size*num_batches_per_epoch ({cfg.batch_size}*{cfg.num_batches_per_epoch}) must equal "
+            f"num_traj*rollout ({E})")
+        if cfg.with_vtrace:
+            assert cfg.recurrence == cfg.rollout and cfg.recurrence > 1, "V-trace requires recurrence == rollout > 1"
+            assert not cfg.normalize_returns, "normalize_returns is incompatible with V-trace (arguments.py:129-134)"
+        assert cfg.exploration_loss == "entropy", "only the entropy exploration loss is on the device path"
+        assert not cfg.shuffle_minibatches, "shuffle_minibatches is not on the device path yet"
+        assert len(spec.hidden) > 0, "the device path needs at least one hidden MLP layer"
+
+        dev = self.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        D, A = spec.obs_dim, spec.num_actions
+        B = cfg.batch_size
+        self.E = E
+        # batch-prep buffers
+        self.normalized_obs = torch.empty((self.N, self.T + 1, D), **f32)
+        self.h_boot = [torch.empty((self.N, h), **f32) for h in spec.hidden]
+        self.advantages = torch.empty((self.N, self.T), **f32)
+        self.returns = torch.empty((self.N, self.T), **f32)
+        self.obs_flat_compact = torch.empty((E, D), **f32)  # normalized obs without the T+1 column, flat [N*T, D]
+        self.values_old = torch.empty((self.N, self.T), **f32)
+        self.valids_flat = torch.empty((self.N, self.T), dtype=torch.bool, device=dev)
+        self.bmean = torch.empty(max(D, 1), **f32)
+        self.bvar = torch.empty(max(D, 1), **f32)
+        self.rmean = torch.empty(1, **f32)
+        self.rvar = torch.empty(1, **f32)
+        self.moments_ws = torch.empty(max(ops.moments_workspace_bytes(D), ops.moments_workspace_bytes(1)) // 4, **f32)
+        self.num_invalids_dev = torch.zeros(1, dtype=torch.float64, device=dev)
+        self.num_valid_dev = torch.zeros(1, dtype=torch.float64, device=dev)
+        self.batch_stats = torch.zeros(ops.LS_SIZE, dtype=torch.float64, device=dev)
+        # minibatch activations
+        self.h = [torch.empty((B, h), **f32) for h in spec.hidden]
+        self.dz = [torch.empty((B, h), **f32) for h in spec.hidden]
+        self.mb_values = torch.empty(B, **f32)
+        self.mb_logits = torch.empty((B, A), **f32)
+        self.dlogits = torch.empty((B, A), **f32)
+        self.dvalues = torch.empty(B, **f32)
+        self.ratio = torch.empty(B, **f32)
+        self.vs = torch.empty(B, **f32)
+        self.vt_adv = torch.empty(B, **f32)
+        self.loss_stats = torch.zeros(ops.LS_SIZE, dtype=torch.float64, device=dev)
+        n_mb_total = cfg.num_epochs * cfg.num_batches_per_epoch
+        self.loss_stats_log = torch.zeros((n_mb_total, ops.LS_SIZE), dtype=torch.float64, device=dev)
+        self.grad_norm_log = torch.zeros(n_mb_total, **f32)
+        self.dp_partials = torch.zeros(3, dtype=torch.float64, device=dev)
+        self.loss_ws = torch.empty(ops.loss_workspace_bytes(max(B, E)) // 8 + 8, dtype=torch.float64, device=dev)
+        H_last = spec.hidden[-1] if spec.hidden else D
+        self.heads_ws = torch.empty(ops.heads_backward_workspace_bytes(H_last, A) // 4 + 4, **f32)
+        lin_ws = 4
+        d = D
+        for h in spec.hidden:
+            lin_ws = max(lin_ws, ops.linear_backward_workspace_bytes(B, h, d) // 4 + 4)
+            d = h
+        self.lin_ws = torch.empty(lin_ws, **f32)
+        self.adam_ws = torch.empty(1024, **f32)
+        self.opt_step = 0
+        self.kernel_launches = 0
+
+    # ------------------------------------------------------------------------------------------------------------
+    def _allreduce(self, t: Tensor) -> None:
+        if self.world_size > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.pg)
+
+    def _update_rms(self, x2d: Tensor, mean: Tensor, var: Tensor, count: Tensor, bmean: Tensor, bvar: Tensor) -> None:
+        """running_mean_std.py:66-77 on device. Under data parallelism the batch moments are made global first."""
+        rows, dim = x2d.shape
+        ops.batch_moments(x2d, bmean[:dim], bvar[:dim], self.moments_ws)
+        total = rows
+        if self.world_size > 1:
+            total = pooled_moments_(bmean[:dim], bvar[:dim], rows, self.pg)
+        ops.rms_merge(mean, var, count, bmean[:dim], bvar[:dim], float(total))
+
+    def _forward_hidden(self, x: Tensor, outs: List[Tensor]) -> Tensor:
+        for (W, b), out in zip(self.model.hidden_layers(), outs):
+            ops.linear_act_forward(x, W, b, out[: x.shape[0]], self.act, self.engine)
+            x = out[: x.shape[0]]
+        return x
+
+    # ------------------------------------------------------------------------------------------------------------
+    def _prepare_batch(self, batch: Dict[str, Tensor]) -> None:
+        """learner.py:943-1034 (sync mode: operates on the trajectory buffers in place like the reference)."""
+        cfg, m, spec = self.cfg, self.model, self.model.spec
+        N, T, D = self.N, self.T, spec.obs_dim
+        ops.compute_valids(batch["policy_id"], batch["policy_version"], self.policy_id, self.train_step,
+                           cfg.max_policy_lag, batch["valids"])                                     # :950-955
+        obs2d = batch["obs"].view(N * (T + 1), D)
+        nobs2d = self.normalized_obs.view(N * (T + 1), D)
+        inv_scale = 1.0 / spec.obs_scale
+        if spec.normalize_input:                                                                     # :961, :925-941
+            src = obs2d
+            if abs(spec.obs_subtract_mean) > 1e-8 or abs(spec.obs_scale - 1.0) > 1e-8:
+                # stats are taken AFTER sub-mean / scaling (normalize.py:62-67): stage the scaled obs first
+                ops.normalize_obs(obs2d, nobs2d, None, None, spec.obs_subtract_mean, inv_scale)
+                src = nobs2d
+                self._update_rms(src, m.obs_mean, m.obs_var, m.obs_count, self.bmean, self.bvar)
+                ops.normalize_obs(src, nobs2d, m.obs_mean, m.obs_var, 0.0, 1.0)
+            else:
+                self._update_rms(src, m.obs_mean, m.obs_var, m.obs_count, self.bmean, self.bvar)
+                ops.normalize_obs(src, nobs2d, m.obs_mean, m.obs_var, 0.0, 1.0)
+        else:
+            ops.normalize_obs(obs2d, nobs2d, None, None, spec.obs_subtract_mean, inv_scale)
+        # bootstrap value for step T (:965-967): forward on normalized_obs[:, T] in place (strided rows)
+        x = self._forward_hidden(self.normalized_obs[:, T], self.h_boot)
+        Wv, bv = m.critic
+        Wa, ba = m.actor
+        ops.heads_forward(x, Wv, bv, Wa, ba, values=batch["values"][:, T], values_stride=batch["values"].stride(0))
+        # :969-1003 fused
+        ops.gae_returns(batch["rewards"], batch["dones"], batch["time_outs"], batch["values"], batch["valids"],
+                        cfg.gamma, cfg.gae_lambda, cfg.value_bootstrap,
+                        m.ret_mean if spec.normalize_returns else None,
+                        m.ret_var if spec.normalize_returns else None, self.advantages, self.returns)
+        # :1006-1012 drop the T+1 column and flatten: strided copies into dense [N*T, ...] buffers
+        ops.copy_rows(self.normalized_obs.view(N, (T + 1) * D)[:, : T * D], self.obs_flat_compact.view(N, T * D))
+        ops.copy_rows(batch["values"][:, :T], self.values_old)
+        self.valids_flat.copy_(batch["valids"][:, :T])
+        if spec.normalize_returns and not cfg.with_vtrace:                                          # :1018-1019
+            r = self.returns.view(-1, 1)
+            self._update_rms(r, m.ret_mean, m.ret_var, m.ret_count, self.rmean, self.rvar)
+            ops.rms_apply_scalar(self.returns.view(-1), m.ret_mean, m.ret_var, denormalize=False)
+        # :1021 num_invalids, kept on the device (lr scaling :788-794 happens inside the Adam kernel)
+        ops.adv_stats(self.advantages.view(-1), self.valids_flat.view(-1), self.batch_stats, None, self.loss_ws)
+        nv = self.batch_stats[ops.LS["num_valid"] : ops.LS["num_valid"] + 1]
+        if self.world_size > 1:
+            self._allreduce(nv)
+        self.num_valid_dev.copy_(nv)
+
+    # ------------------------------------------------------------------------------------------------------------
+    def _minibatch_step(self, batch: Dict[str, Tensor], b: int, log_idx: int) -> None:
+        cfg, m, spec = self.cfg, self.model, self.model.spec
+        B = cfg.batch_size
+        sl = slice(b * B, (b + 1) * B)                                                               # :521
+        A = spec.num_actions
+        x0 = self.obs_flat_compact[sl]
+        actions = batch["actions"].view(self.E)[sl]
+        lp_old = batch["log_prob_actions"].view(self.E)[sl]
+        logits_old = batch["action_logits"].view(self.E, A)[sl]
+        valids = self.valids_flat.view(self.E)[sl]
+        v_old = self.values_old.view(self.E)[sl]
+        # forward (:553-579)
+        x = self._forward_hidden(x0, self.h)
+        Wv, bv = m.critic
+        Wa, ba = m.actor
+        ops.heads_forward(x, Wv, bv, Wa, ba, values=self.mb_values, values_stride=1, logits=self.mb_logits,
+                          logits_stride=A)
+        if cfg.with_vtrace:                                                                          # :602-640
+            ops.action_ratio(self.mb_logits, actions, lp_old, self.ratio)
+            ops.vtrace(self.ratio, self.mb_values, batch["rewards"].view(self.E)[sl], batch["dones"].view(self.E)[sl],
+                       cfg.recurrence, cfg.gamma, cfg.vtrace_rho, cfg.vtrace_c, self.vs, self.vt_adv)
+            adv, targets = self.vt_adv, self.vs
+        else:
+            adv, targets = self.advantages.view(self.E)[sl], self.returns.view(self.E)[sl]            # :643-644
+        # :646-647 advantage statistics (global under data parallelism)
+        if self.world_size > 1:
+            ops.adv_stats(adv, valids, self.loss_stats, self.dp_partials, self.loss_ws)
+            self._allreduce(self.dp_partials)
+            ops.adv_stats_finalize(self.dp_partials, self.loss_stats)
+        else:
+            ops.adv_stats(adv, valids, self.loss_stats, None, self.loss_ws)
+        # losses forward + backward (:651-657, :779)
+        ops.ppo_loss_fwd_bwd(self.mb_logits, self.mb_values, actions, lp_old, v_old, adv, targets, valids, logits_old,
+                             cfg.ppo_clip_ratio, cfg.ppo_clip_value, cfg.exploration_loss_coeff, cfg.value_loss_coeff,
+                             cfg.kl_loss_coeff, 1.0, self.dlogits, self.dvalues, self.loss_stats, self.loss_ws)
+        self.loss_stats_log[log_idx].copy_(self.loss_stats)
+        # backward through heads and hidden layers
+        g = m.grads
+        hidden = m.hidden_layers()
+        hgrads = m.hidden_layer_grads()
+        L = len(hidden)
+        last_in = self.h[L - 1]
+        ops.heads_backward(last_in, Wv, Wa, self.dlogits, self.dvalues, self.act, self.dz[L - 1],
+                           g["critic_linear.weight"].view(-1), g["critic_linear.bias"],
+                           g["action_parameterization.distribution_linear.weight"],
+                           g["action_parameterization.distribution_linear.bias"], hgrads[L - 1][1], self.heads_ws)
+        for li in range(L - 1, -1, -1):
+            W, _ = hidden[li]
+            dW, _db = hgrads[li]
+            x_in = self.h[li - 1] if li > 0 else x0
+            if li > 0:
+                ops.linear_backward(self.dz[li], x_in, W, self.act, dW, self.dz[li - 1], hgrads[li - 1][1], self.engine,
+                                    self.lin_ws)
+            else:
+                ops.linear_backward(self.dz[li], x_in, W, ops.ACT["none"], dW, None, None, self.engine, self.lin_ws)
+        # gradient all-reduce: ONE NCCL call on the flat buffer; mean over ranks is folded into the sums:
+        # each rank's loss already divides by the GLOBAL valid count, so the rank gradients simply add up.
+        self._allreduce(m.grad)
+        # :781-797 clip + Adam (+ lr scaling by the valid fraction, on device)
+        self.opt_step += 1
+        ops.clip_adam_step(m.flat, m.grad, m.exp_avg, m.exp_avg_sq, self.opt_step, self.curr_lr, cfg.adam_beta1,
+                           cfg.adam_beta2, cfg.adam_eps, cfg.max_grad_norm, self.num_valid_dev, self.exp_size_total_dev(),
+                           self.grad_norm_log[log_idx : log_idx + 1], self.adam_ws)
+        self.train_step += 1                                                                         # :388-392
+
+    def exp_size_total_dev(self) -> Tensor:
+        if not hasattr(self, "_exp_total"):
+            self._exp_total = torch.full((1,), float(self.E * self.world_size), dtype=torch.float64, device=self.device)
+        return self._exp_total
+
+    # ------------------------------------------------------------------------------------------------------------
+    def train(self, batch: Dict[str, Tensor]) -> Dict[str, float]:
+        """learner.py:1036-1067. `batch` is the trajectory dict (reference layout) on this learner's device."""
+        cfg = self.cfg
+        launches0 = ops.launch_count()
+        self._prepare_batch(batch)
+        recent_kls: List[float] = []
+        prev_epoch_actor_loss = 1e9
+        log_idx = 0
+        nmb = cfg.num_batches_per_epoch
+        stats_rows = None
+        for epoch in range(cfg.num_epochs):
+            first = log_idx
+            for b in range(nmb):
+                self._minibatch_step(batch, b, log_idx)
+                log_idx += 1
+                if self.lr_scheduler.invoke_after_each_minibatch():
+                    kl = float(self.loss_stats_log[log_idx - 1, ops.LS["kl_old_mean"]].item())   # host sync by request
+                    recent_kls.append(kl)
+                    self.curr_lr = self.lr_scheduler.update(self.curr_lr, recent_kls)
+            need_host = cfg.num_epochs > 1 or self.lr_scheduler.invoke_after_each_epoch()
+            if need_host:
+                rows = self.loss_stats_log[first:log_idx].cpu()        # one sync per epoch (reference: per minibatch)
+                if self.lr_scheduler.invoke_after_each_epoch():
+                    recent_kls.extend(rows[:, ops.LS["kl_old_mean"]].tolist())
+                    self.curr_lr = self.lr_scheduler.update(self.curr_lr, recent_kls)
+                actor = rows[:, ops.LS["policy_loss"]] + rows[:, ops.LS["exploration_loss"]] + rows[:, ops.LS["kl_loss"]]
+                new_loss = float(actor.mean())                          # :827
+                if abs(prev_epoch_actor_loss - new_loss) < 1e-6:        # :829-837 early stopping
+                    break
+                prev_epoch_actor_loss = new_loss
+        self.num_minibatches_done = log_idx
+        self.kernel_launches = ops.launch_count() - launches0   # counted by the library itself
+        self.env_steps += self.E * self.world_size * (cfg.env_frameskip if cfg.summaries_use_frameskip else 1)
+        return dict(env_steps=self.env_steps, train_step=self.train_step)
+
+    def fetch_stats(self) -> Dict[str, float]:
+        """Loss summaries of the LAST minibatch of the last train() (learner.py:843-923 keys). Host sync."""
+        n = getattr(self, "num_minibatches_done", 0)
+        if n == 0:
+            return {}
+        row = self.loss_stats_log[n - 1].cpu().tolist()
+        out = {k: row[i] for k, i in ops.LS.items()}
+        out["grad_norm"] = float(self.grad_norm_log[n - 1].item())
+        out["lr"] = self.curr_lr
+        out["loss"] = out["total_loss"]
+        return out
+
+    def minibatch_log(self) -> Tensor:
+        """[num_minibatches_done, LS_SIZE] float64 (host) -- per-minibatch loss terms of the last train()."""
+        return self.loss_stats_log[: self.num_minibatches_done].cpu()

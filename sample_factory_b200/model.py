@@ -1,0 +1,204 @@
+"""Device-resident actor-critic parameters for the hot path.
+
+Mirrors the reference's ActorCriticSharedWeights with MlpEncoder -> ModelCoreIdentity -> MlpDecoder -> critic_linear /
+distribution_linear (model/actor_critic.py:136-195, encoder.py:72-91, core.py:67-77, decoder.py:15-35) as DATA: one
+flat fp32 parameter buffer in HBM (plus flat grad / Adam-moment buffers of the same shape) so that grad-norm, Adam and
+the NCCL all-reduce are single launches over contiguous memory.  Tensor names and order are the reference's
+state_dict keys, so checkpoints round-trip (learner.py:323-332).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Dict, List, Tuple
+
+import torch
+from torch import Tensor
+
+OBS_NORM_PREFIX = "obs_normalizer.running_mean_std.running_mean_std.obs."
+RET_NORM_PREFIX = "returns_normalizer."
+
+
+@dataclass
+class ModelSpec:
+    obs_dim: int
+    num_actions: int  # Discrete(n)
+    encoder_mlp_layers: List[int] = field(default_factory=lambda: [512, 512])
+    decoder_mlp_layers: List[int] = field(default_factory=list)
+    nonlinearity: str = "elu"
+    normalize_input: bool = True
+    normalize_returns: bool = True
+    obs_subtract_mean: float = 0.0
+    obs_scale: float = 1.0
+
+    @property
+    def hidden(self) -> List[int]:
+        # ModelCoreIdentity (use_rnn=False) passes the encoder output straight to the decoder MLP
+        return list(self.encoder_mlp_layers) + list(self.decoder_mlp_layers)
+
+    def param_shapes(self) -> List[Tuple[str, Tuple[int, ...]]]:
+        """(reference state_dict key, shape) in nn.Module.parameters() order."""
+        out = []
+        d = self.obs_dim
+        for i, h in enumerate(self.encoder_mlp_layers):
+            out.append((f"encoder.encoders.obs.mlp_head.{2 * i}.weight", (h, d)))
+            out.append((f"encoder.encoders.obs.mlp_head.{2 * i}.bias", (h,)))
+            d = h
+        for i, h in enumerate(self.decoder_mlp_layers):
+            out.append((f"decoder.mlp.{2 * i}.weight", (h, d)))
+            out.append((f"decoder.mlp.{2 * i}.bias", (h,)))
+            d = h
+        out.append(("critic_linear.weight", (1, d)))
+        out.append(("critic_linear.bias", (1,)))
+        out.append(("action_parameterization.distribution_linear.weight", (self.num_actions, d)))
+        out.append(("action_parameterization.distribution_linear.bias", (self.num_actions,)))
+        return out
+
+
+def _align(n: int, a: int = 64) -> int:
+    return (n + a - 1) // a * a
+
+
+class PolicyModel:
+    """Flat parameter storage + normalizer buffers on one device."""
+
+    def __init__(self, spec: ModelSpec, device: torch.device, seed: int = 0, policy_init_gain: float = 1.0):
+        self.spec = spec
+        self.device = device
+        shapes = spec.param_shapes()
+        # every tensor starts on a 256-byte boundary inside the flat buffer (vector loads / TMA alignment)
+        offsets, off = [], 0
+        for _, shp in shapes:
+            offsets.append(off)
+            off += _align(math.prod(shp))
+        self.numel_padded = off
+        self.num_params = sum(math.prod(s) for _, s in shapes)
+        self.flat = torch.zeros(off, dtype=torch.float32, device=device)
+        self.grad = torch.zeros_like(self.flat)
+        self.exp_avg = torch.zeros_like(self.flat)
+        self.exp_avg_sq = torch.zeros_like(self.flat)
+        self.params: Dict[str, Tensor] = {}
+        self.grads: Dict[str, Tensor] = {}
+        self._slices: Dict[str, Tuple[int, Tuple[int, ...]]] = {}
+        for (name, shp), o in zip(shapes, offsets):
+            n = math.prod(shp)
+            self.params[name] = self.flat[o : o + n].view(shp)
+            self.grads[name] = self.grad[o : o + n].view(shp)
+            self._slices[name] = (o, shp)
+        self.names = [n for n, _ in shapes]
+
+        # running_mean_std.py:45-47
+        self.obs_mean = torch.zeros(spec.obs_dim, dtype=torch.float64, device=device)
+        self.obs_var = torch.ones(spec.obs_dim, dtype=torch.float64, device=device)
+        self.obs_count = torch.ones(1, dtype=torch.float64, device=device)
+        self.ret_mean = torch.zeros(1, dtype=torch.float64, device=device)
+        self.ret_var = torch.ones(1, dtype=torch.float64, device=device)
+        self.ret_count = torch.ones(1, dtype=torch.float64, device=device)
+
+        self._init_weights(seed, policy_init_gain)
+
+    def _init_weights(self, seed: int, gain: float) -> None:
+        """ActorCritic.initialize_weights (actor_critic.py:73-96): bias 0, orthogonal(gain) on Linear weights."""
+        g = torch.Generator(device="cpu").manual_seed(seed)
+        for name in self.names:
+            p = self.params[name]
+            if name.endswith(".bias"):
+                p.zero_()
+            else:
+                w = torch.empty(p.shape, dtype=torch.float32)
+                torch.nn.init.orthogonal_(w, gain=gain, generator=g)
+                p.copy_(w)
+
+    # ---- layer access ---------------------------------------------------------------------------------------
+    def hidden_layers(self) -> List[Tuple[Tensor, Tensor]]:
+        """[(W [out,in], b [out]), ...] for encoder then decoder MLP layers."""
+        out = []
+        for i in range(len(self.spec.encoder_mlp_layers)):
+            out.append((self.params[f"encoder.encoders.obs.mlp_head.{2 * i}.weight"],
+                        self.params[f"encoder.encoders.obs.mlp_head.{2 * i}.bias"]))
+        for i in range(len(self.spec.decoder_mlp_layers)):
+            out.append((self.params[f"decoder.mlp.{2 * i}.weight"], self.params[f"decoder.mlp.{2 * i}.bias"]))
+        return out
+
+    def hidden_layer_grads(self) -> List[Tuple[Tensor, Tensor]]:
+        out = []
+        for i in range(len(self.spec.encoder_mlp_layers)):
+            out.append((self.grads[f"encoder.encoders.obs.mlp_head.{2 * i}.weight"],
+                        self.grads[f"encoder.encoders.obs.mlp_head.{2 * i}.bias"]))
+        for i in range(len(self.spec.decoder_mlp_layers)):
+            out.append((self.grads[f"decoder.mlp.{2 * i}.weight"], self.grads[f"decoder.mlp.{2 * i}.bias"]))
+        return out
+
+    @property
+    def critic(self) -> Tuple[Tensor, Tensor]:
+        return self.params["critic_linear.weight"], self.params["critic_linear.bias"]
+
+    @property
+    def actor(self) -> Tuple[Tensor, Tensor]:
+        return (self.params["action_parameterization.distribution_linear.weight"],
+                self.params["action_parameterization.distribution_linear.bias"])
+
+    # ---- checkpoint compatibility (learner.py:323-332: 'model' entry) -------------------------------------------
+    def state_dict(self) -> Dict[str, Tensor]:
+        sd: Dict[str, Tensor] = {}
+        if self.spec.normalize_input:
+            sd[OBS_NORM_PREFIX + "running_mean"] = self.obs_mean.clone()
+            sd[OBS_NORM_PREFIX + "running_var"] = self.obs_var.clone()
+            sd[OBS_NORM_PREFIX + "count"] = self.obs_count.clone()
+        if self.spec.normalize_returns:
+            sd[RET_NORM_PREFIX + "running_mean"] = self.ret_mean.clone()
+            sd[RET_NORM_PREFIX + "running_var"] = self.ret_var.clone()
+            sd[RET_NORM_PREFIX + "count"] = self.ret_count.clone()
+        for n in self.names:
+            sd[n] = self.params[n].clone()
+        return sd
+
+    def load_state_dict(self, sd: Dict[str, Tensor], strict: bool = True) -> None:
+        known = set(self.names)
+        for k, v in sd.items():
+            v = torch.as_tensor(v)
+            if k in known:
+                self.params[k].copy_(v.to(self.device, torch.float32).view(self.params[k].shape))
+            elif k == OBS_NORM_PREFIX + "running_mean":
+                self.obs_mean.copy_(v.to(self.device))
+            elif k == OBS_NORM_PREFIX + "running_var":
+                self.obs_var.copy_(v.to(self.device))
+            elif k == OBS_NORM_PREFIX + "count":
+                self.obs_count.copy_(v.to(self.device).view(1))
+            elif k == RET_NORM_PREFIX + "running_mean":
+                self.ret_mean.copy_(v.to(self.device).view(1))
+            elif k == RET_NORM_PREFIX + "running_var":
+                self.ret_var.copy_(v.to(self.device).view(1))
+            elif k == RET_NORM_PREFIX + "count":
+                self.ret_count.copy_(v.to(self.device).view(1))
+            elif strict:
+                raise KeyError(f"unexpected key in state_dict: {k}")
+        if strict:
+            missing = known - set(sd.keys())
+            if missing:
+                raise KeyError(f"missing keys in state_dict: {sorted(missing)}")
+
+    def optimizer_state_dict(self, step: int, lr: float, betas, eps: float) -> dict:
+        """torch.optim.Adam.state_dict() layout so reference tooling can load it (learner.py:329)."""
+        state = {}
+        for i, n in enumerate(self.names):
+            o, shp = self._slices[n]
+            k = math.prod(shp)
+            state[i] = dict(step=torch.tensor(float(step)), exp_avg=self.exp_avg[o : o + k].view(shp).clone(),
+                            exp_avg_sq=self.exp_avg_sq[o : o + k].view(shp).clone())
+        group = dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=0, amsgrad=False, maximize=False, foreach=None,
+                     capturable=False, differentiable=False, fused=None, params=list(range(len(self.names))))
+        return dict(state=state, param_groups=[group])
+
+    def load_optimizer_state_dict(self, osd: dict) -> int:
+        step = 0
+        for i, n in enumerate(self.names):
+            if i not in osd["state"]:
+                continue
+            st = osd["state"][i]
+            o, shp = self._slices[n]
+            k = math.prod(shp)
+            self.exp_avg[o : o + k].copy_(st["exp_avg"].to(self.device).reshape(-1))
+            self.exp_avg_sq[o : o + k].copy_(st["exp_avg_sq"].to(self.device).reshape(-1))
+            step = int(float(st["step"]))
+        return step

@@ -1,0 +1,278 @@
+"""Tensor-level wrappers over the C ABI (include/sfb200.h).
+
+PyTorch is used here only as the owner of device memory and streams: every function takes CUDA tensors, checks
+dtype / contiguity, and passes raw pointers + the current CUDA stream handle to libsfb200.  Nothing in this module
+computes anything itself and there is no CPU path -- a CPU tensor raises.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+from torch import Tensor
+
+from ._lib import lib
+
+ACT = {"none": 0, "elu": 1, "relu": 2, "tanh": 3}
+GEMM_SIMT, GEMM_TC_3XTF32, GEMM_TC_TF32 = 0, 1, 2
+ENGINES = {"simt": GEMM_SIMT, "3xtf32": GEMM_TC_3XTF32, "tf32": GEMM_TC_TF32}
+
+LS = dict(
+    num_valid=0, adv_mean=1, adv_std=2, policy_loss=3, value_loss=4, exploration_loss=5, kl_loss=6, kl_old_mean=7,
+    kl_old_max=8, entropy_mean=9, ratio_mean_abs_dev=10, ratio_min=11, ratio_max=12, fraction_clipped=13,
+    value_mean=14, total_loss=15,
+)
+LS_SIZE = 16
+
+_device_bound = {}
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def bind_device(device: torch.device) -> None:
+    """cudaSetDevice for libsfb200's (statically linked) CUDA runtime on this thread."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    lib().call("sfb200_set_device", idx)
+
+
+def _p(t: Optional[Tensor], dtype=None) -> Optional[int]:
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("sample_factory_b200 ops need CUDA tensors (there is no CPU path)")
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError(f"expected {dtype}, got {t.dtype}")
+    if t.dim() > 0 and t.stride(-1) != 1 and t.shape[-1] != 1:
+        raise ValueError("last dimension must be dense")
+    return t.data_ptr()
+
+
+F32, F64, U8, I32, I64 = torch.float32, torch.float64, torch.bool, torch.int32, torch.int64
+
+
+def sm_count() -> int:
+    return lib().query("sfb200_sm_count")
+
+
+def launch_count() -> int:
+    """Kernels launched by libsfb200 in this process so far (counted inside the library)."""
+    return lib().query("sfb200_launch_count")
+
+
+def tc_available() -> bool:
+    return bool(lib().query("sfb200_tc_available"))
+
+
+# ------------------------------------------------------------------------------------------------ normalizers
+def normalize_obs(x: Tensor, out: Tensor, mean: Optional[Tensor], var: Optional[Tensor], sub_mean: float = 0.0,
+                  inv_scale: float = 1.0, eps: float = 1e-5, clip: float = 5.0) -> Tensor:
+    """x, out: [rows, dim] (row strides free). utils/normalize.py:51-70."""
+    rows, dim = x.shape
+    lib().call("sfb200_normalize_obs", _p(x, F32), x.stride(0), _p(out, F32), out.stride(0), rows, dim,
+               _p(mean, F64), _p(var, F64), sub_mean, inv_scale, eps, clip, _stream())
+    return out
+
+
+def moments_workspace_bytes(dim: int) -> int:
+    return lib().query("sfb200_moments_workspace_bytes", dim)
+
+
+def batch_moments(x: Tensor, batch_mean: Tensor, batch_var: Tensor, workspace: Tensor) -> None:
+    rows, dim = x.shape
+    assert workspace.numel() * workspace.element_size() >= moments_workspace_bytes(dim)
+    lib().call("sfb200_batch_moments", _p(x, F32), x.stride(0), rows, dim, _p(batch_mean, F32), _p(batch_var, F32),
+               workspace.data_ptr(), _stream())
+
+
+def rms_merge(mean: Tensor, var: Tensor, count: Tensor, batch_mean: Tensor, batch_var: Tensor, batch_count: float):
+    lib().call("sfb200_rms_merge", _p(mean, F64), _p(var, F64), _p(count, F64), _p(batch_mean, F32),
+               _p(batch_var, F32), float(batch_count), mean.numel(), _stream())
+
+
+def rms_apply_scalar(x: Tensor, mean: Tensor, var: Tensor, denormalize: bool, eps: float = 1e-5, clip: float = 5.0):
+    assert x.is_contiguous()
+    lib().call("sfb200_rms_apply_scalar", _p(x, F32), x.numel(), _p(mean, F64), _p(var, F64), eps, clip,
+               int(denormalize), _stream())
+
+
+# ------------------------------------------------------------------------------------------------ model forward
+def linear_act_forward(x: Tensor, W: Tensor, b: Optional[Tensor], out: Tensor, act: int, engine: int) -> Tensor:
+    M, K = x.shape
+    N = W.shape[0]
+    assert W.shape[1] == K and W.is_contiguous() and out.shape == (M, N)
+    lib().call("sfb200_linear_act_forward", _p(x, F32), x.stride(0), _p(W, F32), _p(b, F32), _p(out, F32),
+               out.stride(0), M, N, K, act, engine, _stream())
+    return out
+
+
+def heads_forward(h: Tensor, Wv: Tensor, bv: Tensor, Wa: Tensor, ba: Tensor, values: Tensor, values_stride: int,
+                  logits: Optional[Tensor] = None, logits_stride: int = 0, noise: Optional[Tensor] = None,
+                  philox_seed: int = 0, philox_offset: int = 0, philox_offset_dev: Optional[Tensor] = None,
+                  actions_f32: Optional[Tensor] = None,
+                  actions_stride: int = 0, env_actions: Optional[Tensor] = None, log_prob: Optional[Tensor] = None,
+                  log_prob_stride: int = 0, policy_version_scalar: Optional[Tensor] = None,
+                  policy_version_out: Optional[Tensor] = None, pv_stride: int = 0) -> None:
+    """Outputs are raw views (pointer = first element, explicit element strides) so they can be trajectory slots."""
+    rows, H = h.shape
+    A = Wa.shape[0]
+    assert Wa.is_contiguous() and Wv.is_contiguous() and (noise is None or noise.is_contiguous())
+    lib().call("sfb200_heads_forward", _p(h, F32), h.stride(0), rows, H, A, _p(Wv, F32), _p(bv, F32), _p(Wa, F32),
+               _p(ba, F32), values.data_ptr(), values_stride, None if logits is None else logits.data_ptr(),
+               logits_stride, _p(noise, F32), philox_seed, philox_offset, _p(philox_offset_dev, I64),
+               None if actions_f32 is None else actions_f32.data_ptr(), actions_stride, _p(env_actions, I32),
+               None if log_prob is None else log_prob.data_ptr(), log_prob_stride, _p(policy_version_scalar, F32),
+               None if policy_version_out is None else policy_version_out.data_ptr(), pv_stride, _stream())
+
+
+# ------------------------------------------------------------------------------------------------ sampler
+def sampler_pre_step(obs: Tensor, traj_obs_t: Tensor, rnn: Optional[Tensor], traj_rnn_t: Optional[Tensor],
+                     x_norm: Optional[Tensor], mean: Optional[Tensor], var: Optional[Tensor], sub_mean: float,
+                     inv_scale: float, eps: float = 1e-5, clip: float = 5.0) -> None:
+    """obs [N, D] dense; traj_obs_t = traj['obs'][:, t] view ([N, D], row stride (T+1)*D)."""
+    n, dim = obs.shape
+    assert obs.is_contiguous() and (x_norm is None or x_norm.is_contiguous())
+    rnn_dim = 0 if rnn is None else rnn.shape[1]
+    lib().call("sfb200_sampler_pre_step", _p(obs, F32), n, dim, traj_obs_t.data_ptr(), traj_obs_t.stride(0),
+               _p(rnn, F32), rnn_dim, None if traj_rnn_t is None else traj_rnn_t.data_ptr(),
+               0 if traj_rnn_t is None else traj_rnn_t.stride(0), _p(x_norm, F32), _p(mean, F64), _p(var, F64),
+               sub_mean, inv_scale, eps, clip, _stream())
+
+
+def sampler_post_step(rew: Tensor, terminated: Tensor, truncated: Tensor, reward_scale: float, reward_clip: float,
+                      policy_id: int, traj_rewards_t: Tensor, traj_dones_t: Tensor, traj_time_outs_t: Tensor,
+                      traj_policy_id_t: Tensor, ep_return: Optional[Tensor], ep_len: Optional[Tensor],
+                      ep_min_raw: Optional[Tensor], ep_max_raw: Optional[Tensor], len_increment: int,
+                      stats: Optional[Tensor], step_counter: Optional[Tensor] = None) -> None:
+    n = rew.numel()
+    stride = traj_rewards_t.stride(0)
+    assert traj_dones_t.stride(0) == stride and traj_time_outs_t.stride(0) == stride
+    assert traj_policy_id_t.stride(0) == stride
+    lib().call("sfb200_sampler_post_step", _p(rew, F32), _p(terminated, U8), _p(truncated, U8), n, reward_scale,
+               reward_clip, policy_id, traj_rewards_t.data_ptr(), traj_dones_t.data_ptr(),
+               traj_time_outs_t.data_ptr(), traj_policy_id_t.data_ptr(), stride, _p(ep_return, F32), _p(ep_len, I32),
+               _p(ep_min_raw, F32), _p(ep_max_raw, F32), len_increment, _p(stats, F64), _p(step_counter, I64),
+               _stream())
+
+
+def copy_rows(src: Tensor, dst: Tensor) -> None:
+    rows, dim = src.shape
+    lib().call("sfb200_copy_rows", _p(src, F32), src.stride(0), dst.data_ptr(), dst.stride(0), rows, dim, _stream())
+
+
+def tape_env_step(actions: Tensor, num_actions: int, env_index_offset: int, term_period: int, trunc_period: int,
+                  step_counter: Optional[Tensor], step_host: int, tape: Optional[Tensor], obs_out: Optional[Tensor],
+                  rew: Tensor, terminated: Tensor, truncated: Tensor) -> None:
+    n = actions.numel()
+    tape_len, dim = (tape.shape[0], tape.shape[2]) if tape is not None else (0, 0)
+    lib().call("sfb200_tape_env_step", _p(actions, I32), n, num_actions, env_index_offset, term_period, trunc_period,
+               _p(step_counter, I64), step_host, _p(tape, F32), tape_len, dim, _p(obs_out, F32), _p(rew, F32),
+               _p(terminated, U8), _p(truncated, U8), _stream())
+
+
+# ------------------------------------------------------------------------------------------------ learner: prep
+def compute_valids(policy_id: Tensor, policy_version: Tensor, this_policy: int, train_step: int, max_policy_lag: int,
+                   valids: Tensor) -> None:
+    n_traj, T = policy_id.shape
+    assert policy_id.is_contiguous() and policy_version.is_contiguous() and valids.is_contiguous()
+    assert valids.shape == (n_traj, T + 1)
+    lib().call("sfb200_compute_valids", _p(policy_id, I32), _p(policy_version, F32), n_traj, T, this_policy,
+               float(train_step), float(max_policy_lag), _p(valids, U8), _stream())
+
+
+def gae_returns(rewards: Tensor, dones: Tensor, time_outs: Tensor, values: Tensor, valids: Tensor, gamma: float,
+                lam: float, value_bootstrap: bool, ret_mean: Optional[Tensor], ret_var: Optional[Tensor], adv: Tensor,
+                returns: Tensor, eps: float = 1e-5, clip: float = 5.0) -> None:
+    n_traj, T = rewards.shape
+    for t in (rewards, dones, time_outs, values, valids, adv, returns):
+        assert t.is_contiguous()
+    assert values.shape == (n_traj, T + 1) and valids.shape == (n_traj, T + 1)
+    lib().call("sfb200_gae_returns", _p(rewards, F32), _p(dones, U8), _p(time_outs, U8), _p(values, F32),
+               _p(valids, U8), n_traj, T, gamma, lam, int(value_bootstrap), _p(ret_mean, F64), _p(ret_var, F64), eps,
+               clip, _p(adv, F32), _p(returns, F32), _stream())
+
+
+def vtrace(ratio: Tensor, values: Tensor, rewards: Tensor, dones: Tensor, R: int, gamma: float, rho_hat: float,
+           c_hat: float, vs: Tensor, adv: Tensor) -> None:
+    n = ratio.numel() // R
+    for t in (ratio, values, rewards, dones, vs, adv):
+        assert t.is_contiguous()
+    lib().call("sfb200_vtrace", _p(ratio, F32), _p(values, F32), _p(rewards, F32), _p(dones, U8), n, R, gamma, rho_hat,
+               c_hat, _p(vs, F32), _p(adv, F32), _stream())
+
+
+# ------------------------------------------------------------------------------------------------ learner: loss
+def loss_workspace_bytes(batch: int) -> int:
+    return lib().query("sfb200_loss_workspace_bytes", batch)
+
+
+def action_ratio(logits: Tensor, actions_f32: Tensor, log_prob_old: Tensor, ratio: Tensor) -> None:
+    B, A = logits.shape
+    assert logits.is_contiguous()
+    lib().call("sfb200_action_ratio", _p(logits, F32), A, _p(actions_f32, F32), _p(log_prob_old, F32), B,
+               _p(ratio, F32), _stream())
+
+
+def adv_stats(adv: Tensor, valids: Tensor, stats: Tensor, dp_partials: Optional[Tensor], workspace: Tensor) -> None:
+    lib().call("sfb200_adv_stats", _p(adv, F32), _p(valids, U8), adv.numel(), _p(stats, F64), _p(dp_partials, F64),
+               workspace.data_ptr(), _stream())
+
+
+def adv_stats_finalize(dp_partials: Tensor, stats: Tensor) -> None:
+    lib().call("sfb200_adv_stats_finalize", _p(dp_partials, F64), _p(stats, F64), _stream())
+
+
+def ppo_loss_fwd_bwd(logits: Tensor, values: Tensor, actions_f32: Tensor, log_prob_old: Tensor, values_old: Tensor,
+                     adv: Tensor, targets: Tensor, valids: Tensor, logits_old: Optional[Tensor], clip_ratio: float,
+                     clip_value: float, exploration_coeff: float, value_coeff: float, kl_coeff: float,
+                     grad_scale: float, dlogits: Tensor, dvalues: Tensor, stats: Tensor, workspace: Tensor) -> None:
+    B, A = logits.shape
+    assert logits.is_contiguous() and dlogits.is_contiguous()
+    assert workspace.numel() * workspace.element_size() >= loss_workspace_bytes(B)
+    lib().call("sfb200_ppo_loss_fwd_bwd", _p(logits, F32), _p(values, F32), A, _p(actions_f32, F32),
+               _p(log_prob_old, F32), _p(values_old, F32), _p(adv, F32), _p(targets, F32), _p(valids, U8),
+               _p(logits_old, F32), B, clip_ratio, clip_value, exploration_coeff, value_coeff, kl_coeff, grad_scale,
+               _p(dlogits, F32), _p(dvalues, F32), _p(stats, F64), workspace.data_ptr(), _stream())
+
+
+# ------------------------------------------------------------------------------------------------ learner: backward
+def heads_backward_workspace_bytes(H: int, A: int) -> int:
+    return lib().query("sfb200_heads_backward_workspace_bytes", H, A)
+
+
+def heads_backward(h: Tensor, Wv: Tensor, Wa: Tensor, dlogits: Tensor, dvalues: Tensor, act: int, dz: Tensor,
+                   dWv: Tensor, dbv: Tensor, dWa: Tensor, dba: Tensor, db_prev: Optional[Tensor],
+                   workspace: Tensor) -> None:
+    rows, H = h.shape
+    A = Wa.shape[0]
+    lib().call("sfb200_heads_backward", _p(h, F32), h.stride(0), rows, H, A, _p(Wv, F32), _p(Wa, F32),
+               _p(dlogits, F32), _p(dvalues, F32), act, _p(dz, F32), dz.stride(0), _p(dWv, F32), _p(dbv, F32),
+               _p(dWa, F32), _p(dba, F32), _p(db_prev, F32), workspace.data_ptr(), _stream())
+
+
+def linear_backward_workspace_bytes(M: int, N: int, K: int) -> int:
+    return lib().query("sfb200_linear_backward_workspace_bytes", M, N, K)
+
+
+def linear_backward(dz: Tensor, x: Tensor, W: Tensor, act_prev: int, dW: Tensor, dx: Optional[Tensor],
+                    db_prev: Optional[Tensor], engine: int, workspace: Tensor) -> None:
+    M, N = dz.shape
+    K = x.shape[1]
+    assert W.shape == (N, K) and W.is_contiguous() and dW.is_contiguous()
+    assert workspace.numel() * workspace.element_size() >= linear_backward_workspace_bytes(M, N, K)
+    lib().call("sfb200_linear_backward", _p(dz, F32), dz.stride(0), _p(x, F32), x.stride(0), _p(W, F32), M, N, K,
+               act_prev, _p(dW, F32), _p(dx, F32), 0 if dx is None else dx.stride(0), _p(db_prev, F32), engine,
+               workspace.data_ptr(), _stream())
+
+
+# ------------------------------------------------------------------------------------------------ optimizer
+def clip_adam_step(p: Tensor, g: Tensor, m: Tensor, v: Tensor, step: int, lr: float, beta1: float, beta2: float,
+                   eps: float, max_grad_norm: float, lr_scale_num: Optional[Tensor], lr_scale_den: Optional[Tensor],
+                   grad_norm_out: Optional[Tensor], workspace: Tensor) -> None:
+    for t in (p, g, m, v):
+        assert t.is_contiguous() and t.dim() == 1
+    assert workspace.numel() * workspace.element_size() >= 4096
+    lib().call("sfb200_clip_adam_step", _p(p, F32), _p(g, F32), _p(m, F32), _p(v, F32), p.numel(), step, lr, beta1,
+               beta2, eps, max_grad_norm, _p(lr_scale_num, F64), _p(lr_scale_den, F64), _p(grad_norm_out, F32),
+               workspace.data_ptr(), _stream())

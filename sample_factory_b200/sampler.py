@@ -1,0 +1,159 @@
+"""Device rollout sampler: the reference's RolloutWorker + InferenceWorker + BatchedVectorEnvRunner collapsed into one
+stream of CUDA kernels (no process tree, no queues, no per-step host sync).
+
+Per env step (reference call stack SURVEY section 3.2):
+  generate_policy_request  (batched_sampling.py:374-388)  + obs normalisation (inference_worker.py:326)
+        -> sfb200_sampler_pre_step   : traj.obs[:, t] <- obs, traj.rnn_states[:, t] <- rnn, x = normalize(obs)
+  actor_critic forward     (actor_critic.py:188-195)
+        -> sfb200_linear_act_forward per hidden layer
+        -> sfb200_heads_forward      : values, logits, sample, log-prob, policy_version -- written straight into
+                                       traj[:, t] (replaces policy_output_tensors staging, inference_worker.py:235-269,
+                                       batched_sampling.py:308-311)
+  vec_env.step(actions)    (batched_sampling.py:316)      -> the env's own kernel (GPU env) or host round trip
+  advance_rollouts part 2  (batched_sampling.py:319-357)  -> sfb200_sampler_post_step
+After `rollout` steps: _finalize_trajectories (:289-296) -> obs/rnn at index T.
+
+With a GPU env the whole rollout is a fixed launch sequence, so it is captured once into a CUDA graph and replayed.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+from torch import Tensor
+
+from . import ops
+from .model import PolicyModel
+
+
+class DeviceSampler:
+    def __init__(self, cfg, env, model: PolicyModel, traj: Dict[str, Tensor], engine: int = ops.GEMM_SIMT,
+                 use_cuda_graph: bool = False, philox_seed: int = 0):
+        self.cfg = cfg
+        self.env = env
+        self.model = model
+        self.traj = traj
+        self.engine = engine
+        self.device = model.device
+        self.N = env.num_agents
+        self.T = cfg.rollout
+        spec = model.spec
+        assert traj["obs"].shape == (self.N, self.T + 1, spec.obs_dim)
+        self.act = ops.ACT[spec.nonlinearity]
+        dev = self.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        # per-step scratch (never reallocated)
+        self.x_norm = torch.empty((self.N, spec.obs_dim), **f32)
+        self.h = [torch.empty((self.N, h), **f32) for h in spec.hidden]
+        self.env_actions = torch.empty(self.N, dtype=torch.int32, device=dev)
+        self.last_rnn_state = torch.zeros((self.N, traj["rnn_states"].shape[2]), **f32)
+        # policy version lives on the device so a captured graph always stamps the current one (inference_worker.py:332)
+        self.policy_version = torch.zeros(1, **f32)
+        # episode accounting on device (batched_sampling.py:201-204, :215-287)
+        self.ep_return = torch.zeros(self.N, **f32)
+        self.ep_len = torch.zeros(self.N, dtype=torch.int32, device=dev)
+        self.ep_min_raw = torch.full((self.N,), float("inf"), **f32)
+        self.ep_max_raw = torch.full((self.N,), float("-inf"), **f32)
+        self.episode_stats = torch.zeros(8, dtype=torch.float64, device=dev)
+        self.last_obs: Optional[Tensor] = None
+        self.philox_seed = philox_seed
+        self.step_counter = torch.zeros(1, dtype=torch.int64, device=dev)  # policy steps taken = Philox offset
+        self.noise: Optional[Tensor] = None  # [T, N, A] explicit Exp(1) noise (parity tests); None -> Philox
+        self.use_cuda_graph = use_cuda_graph and getattr(env, "is_gpu_env", False)
+        self._graph: Optional[torch.cuda.CUDAGraph] = None
+        self.kernel_launches_per_rollout = 0
+
+    # ------------------------------------------------------------------------------------------------------------
+    def reset(self) -> None:
+        self.last_obs = self.env.reset()
+        self.last_rnn_state.zero_()
+
+    def set_policy_version(self, version: int) -> None:
+        self.policy_version.fill_(float(version))
+
+    def _policy_step(self, t: int) -> None:
+        cfg, m, spec, tr = self.cfg, self.model, self.model.spec, self.traj
+        inv_scale = 1.0 / spec.obs_scale
+        mean = m.obs_mean if spec.normalize_input else None
+        var = m.obs_var if spec.normalize_input else None
+        ops.sampler_pre_step(self.last_obs, tr["obs"][:, t], self.last_rnn_state, tr["rnn_states"][:, t], self.x_norm,
+                             mean, var, spec.obs_subtract_mean, inv_scale)
+        x = self.x_norm
+        for (W, b), out in zip(m.hidden_layers(), self.h):
+            ops.linear_act_forward(x, W, b, out, self.act, self.engine)
+            x = out
+        Wv, bv = m.critic
+        Wa, ba = m.actor
+        noise_t = None if self.noise is None else self.noise[t]
+        ops.heads_forward(
+            x, Wv, bv, Wa, ba,
+            values=tr["values"][:, t], values_stride=tr["values"].stride(0),
+            logits=tr["action_logits"][:, t], logits_stride=tr["action_logits"].stride(0),
+            noise=noise_t, philox_seed=self.philox_seed, philox_offset=0, philox_offset_dev=self.step_counter,
+            actions_f32=tr["actions"][:, t], actions_stride=tr["actions"].stride(0),
+            env_actions=self.env_actions,
+            log_prob=tr["log_prob_actions"][:, t], log_prob_stride=tr["log_prob_actions"].stride(0),
+            policy_version_scalar=self.policy_version,
+            policy_version_out=tr["policy_version"][:, t], pv_stride=tr["policy_version"].stride(0),
+        )
+
+    def _env_and_post_step(self, t: int) -> None:
+        cfg, tr = self.cfg, self.traj
+        obs, rew, terminated, truncated = self.env.step(self.env_actions)   # batched_sampling.py:316
+        self.last_obs = obs
+        ops.sampler_post_step(rew, terminated, truncated, cfg.reward_scale, cfg.reward_clip, cfg.policy_id,
+                              tr["rewards"][:, t], tr["dones"][:, t], tr["time_outs"][:, t], tr["policy_id"][:, t],
+                              self.ep_return, self.ep_len, self.ep_min_raw, self.ep_max_raw,
+                              cfg.env_frameskip if cfg.summaries_use_frameskip else 1, self.episode_stats,
+                              self.step_counter)
+        # non-recurrent core: new_rnn_states == rnn_states (core.py:76-77), times (1-done) stays zero (:334-335)
+
+    def advance_rollouts(self, t: int) -> None:
+        """One env step for all envs: policy step then env step (reference: inference then advance_rollouts)."""
+        self._policy_step(t)
+        self._env_and_post_step(t)
+
+    def _finalize_trajectories(self) -> None:
+        tr = self.traj
+        ops.copy_rows(self.last_obs, tr["obs"][:, self.T])                       # batched_sampling.py:292
+        ops.copy_rows(self.last_rnn_state, tr["rnn_states"][:, self.T])          # :293
+
+    def _rollout_eager(self) -> None:
+        n0 = ops.launch_count()
+        for t in range(self.T):
+            self.advance_rollouts(t)
+        self._finalize_trajectories()
+        self.kernel_launches_per_rollout = ops.launch_count() - n0   # counted by the library itself
+
+    def rollout(self) -> None:
+        """Collect `rollout` steps for every env into the trajectory buffers (in place)."""
+        if self.last_obs is None:
+            self.reset()
+        if not self.use_cuda_graph:
+            self._rollout_eager()
+            return
+        if self._graph is None:
+            # the Philox offset and the env step are device-side counters, so replays draw fresh noise
+            assert self.noise is None, "explicit noise and CUDA graphs are mutually exclusive"
+            torch.cuda.synchronize()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self._rollout_eager()   # warm-up on the side stream (allocator-free path, but be safe)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            self._graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph):
+                self._rollout_eager()
+            self._graph_launches = self.kernel_launches_per_rollout
+        self._graph.replay()
+        self.kernel_launches_per_rollout = self._graph_launches
+
+    def pop_episode_stats(self) -> Dict[str, float]:
+        """Aggregate of episodes finished since the last call (host sync; call at reporting time only)."""
+        s = self.episode_stats.cpu().tolist()
+        self.episode_stats.zero_()
+        n = s[0]
+        if n <= 0:
+            return dict(episodes=0)
+        return dict(episodes=int(n), reward=s[1] / n, len=s[2] / n, min_raw_reward=s[3] / n, max_raw_reward=s[4] / n)

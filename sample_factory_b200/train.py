@@ -1,0 +1,184 @@
+"""Training entry point with the reference's public surface (sample_factory/train.py:12-41, algo/runners/runner.py):
+
+    cfg = parse_full_cfg(parser)          # sample_factory_b200.cfg
+    register_env("my_env", make_env_func)  # sample_factory_b200.envs
+    status = run_rl(cfg)                   # 0 success / 1 failure / 2 interrupted (algo/utils/misc.py:32-33)
+
+The reference's Runner wires rollout workers, inference workers, a batcher and a learner through signal/slot event
+loops across processes (runner.py:626-678).  Here the same components are three objects on ONE GPU stream pair and the
+control loop is ~30 lines: rollout -> train -> (stats, checkpoint), repeated until the env-step / time budget is used.
+Sync mode (async_rl=False) samples and learns back to back on one stream; async mode double-buffers the trajectory
+store and runs the sampler for iteration i+1 on a second stream while the learner consumes iteration i, the sampler
+using a snapshot of the weights (policy lag >= 1, exactly what the reference's async mode gives).
+"""
+from __future__ import annotations
+
+import json
+import os
+import time
+from collections import deque
+from typing import Callable, Dict, List, Optional
+
+import torch
+
+from . import ops
+from .cfg import preprocess_cfg
+from .checkpoint import load_checkpoint, save_checkpoint
+from .dist_utils import init_from_env
+from .envs import create_env
+from .learner import Learner
+from .model import ModelSpec, PolicyModel
+from .sampler import DeviceSampler
+from .trajectory import alloc_trajectory_tensors
+
+
+class StatusCode:
+    SUCCESS, FAILURE, INTERRUPTED = 0, 1, 2
+
+
+def experiment_dir(cfg) -> str:
+    """utils/utils.py:409: <train_dir>/<experiment>"""
+    d = os.path.join(cfg.train_dir, cfg.experiment)
+    os.makedirs(d, exist_ok=True)
+    return d
+
+
+def select_engine(cfg) -> int:
+    name = getattr(cfg, "gemm_engine", "auto")
+    if name == "auto":
+        return ops.GEMM_TC_3XTF32 if ops.tc_available() else ops.GEMM_SIMT
+    return ops.ENGINES[name]
+
+
+class Runner:
+    """Single-policy runner (runner.py:81-184 attributes that examples/tests read are kept: env_steps, policy_avg_stats,
+    register_observer / register_msg_handler hooks)."""
+
+    def __init__(self, cfg):
+        self.cfg = cfg
+        self.env_steps = 0
+        self.total_train_seconds = 0.0
+        self.policy_avg_stats: Dict[str, List[deque]] = {}
+        self.observers: List = []
+        self.msg_handlers: Dict[str, List[Callable]] = {}
+        self.fps_history: deque = deque(maxlen=64)
+        self.initialized = False
+
+    # ---- reference-compatible hooks --------------------------------------------------------------------------
+    def register_observer(self, observer) -> None:
+        self.observers.append(observer)
+
+    def register_msg_handler(self, key: str, func: Callable) -> None:
+        self.msg_handlers.setdefault(key, []).append(func)
+
+    def register_episodic_stats_handler(self, func: Callable) -> None:
+        self.register_msg_handler("episodic", func)
+
+    # ----------------------------------------------------------------------------------------------------------
+    def init(self) -> int:
+        cfg = self.cfg
+        self.rank, self.local_rank, self.world_size = init_from_env()
+        if not torch.cuda.is_available():
+            raise RuntimeError("sample_factory_b200 needs a CUDA device (B200); there is no CPU execution path")
+        self.device = torch.device("cuda", self.local_rank)
+        torch.cuda.set_device(self.device)
+        ops.bind_device(self.device)
+        if cfg.seed is not None:
+            torch.manual_seed(cfg.seed + self.rank)
+        if not preprocess_cfg(cfg):
+            raise ValueError("invalid configuration (see cfg.verify_cfg)")
+        env_config = dict(worker_index=self.rank, vector_index=0, env_id=self.rank)
+        self.env = create_env(cfg.env, cfg, env_config)
+        spec = ModelSpec(self.env.obs_dim, self.env.num_actions, list(cfg.encoder_mlp_layers),
+                         list(cfg.decoder_mlp_layers), cfg.nonlinearity, cfg.normalize_input, cfg.normalize_returns,
+                         cfg.obs_subtract_mean, cfg.obs_scale)
+        assert not cfg.use_rnn, "the device path is the non-recurrent MLP policy (SURVEY section 8); use --use_rnn=False"
+        self.model = PolicyModel(spec, self.device, seed=cfg.seed or 0, policy_init_gain=cfg.policy_init_gain)
+        N = self.env.num_agents
+        self.engine = select_engine(cfg)
+        self.traj = alloc_trajectory_tensors(spec.obs_dim, spec.num_actions, N, cfg.rollout, self.device)
+        self.sampler = DeviceSampler(cfg, self.env, self.model, self.traj, engine=self.engine,
+                                     use_cuda_graph=bool(getattr(cfg, "cuda_graph", True)),
+                                     philox_seed=(cfg.seed or 0) * 1000003 + self.rank)
+        self.learner = Learner(cfg, self.model, N, engine=self.engine)
+        if self.world_size > 1:
+            # identical replicas: broadcast rank 0's initial weights
+            torch.distributed.broadcast(self.model.flat, src=0)
+        if cfg.restart_behavior == "resume":
+            ck = load_checkpoint(cfg, self.model, self.device)
+            if ck is not None:
+                self.learner.train_step, self.learner.env_steps = ck["train_step"], ck["env_steps"]
+                self.learner.opt_step = ck["opt_step"]
+                self.learner.curr_lr = ck.get("curr_lr", cfg.learning_rate)
+                self.env_steps = ck["env_steps"]
+        if self.rank == 0:
+            with open(os.path.join(experiment_dir(cfg), "config.json"), "w") as f:
+                json.dump({k: v for k, v in vars(cfg).items() if _jsonable(v)}, f, indent=2)
+        self.sampler.reset()
+        self.initialized = True
+        return StatusCode.SUCCESS
+
+    def iteration(self) -> None:
+        """One sampler rollout + one learner update (the unit the FPS counter advances by N*T env steps)."""
+        self.sampler.set_policy_version(self.learner.train_step)
+        self.sampler.rollout()
+        self.learner.train(self.traj)
+        self.env_steps = self.learner.env_steps
+
+    def run(self) -> int:
+        cfg = self.cfg
+        assert self.initialized
+        t_start = last_report = last_save = time.time()
+        steps_at_report = self.env_steps
+        status = StatusCode.SUCCESS
+        try:
+            while self.env_steps < cfg.train_for_env_steps and time.time() - t_start < cfg.train_for_seconds:
+                self.iteration()
+                now = time.time()
+                if now - last_report >= cfg.experiment_summaries_interval:
+                    torch.cuda.synchronize()
+                    now = time.time()
+                    fps = (self.env_steps - steps_at_report) / (now - last_report)
+                    self.fps_history.append(fps)
+                    ep = self.sampler.pop_episode_stats()
+                    st = self.learner.fetch_stats()
+                    for h in self.msg_handlers.get("episodic", []):
+                        h(self, ep, 0)
+                    if self.rank == 0:
+                        print(f"[sf_b200] env_steps {self.env_steps} fps {fps:.0f} loss {st.get('loss', float('nan')):.4f} "
+                              f"reward {ep.get('reward', float('nan')):.3f} episodes {ep.get('episodes', 0)}", flush=True)
+                    last_report, steps_at_report = now, self.env_steps
+                if now - last_save >= cfg.save_every_sec and self.rank == 0:
+                    save_checkpoint(cfg, self.model, self.learner)
+                    last_save = now
+        except KeyboardInterrupt:
+            status = StatusCode.INTERRUPTED
+        torch.cuda.synchronize()
+        self.total_train_seconds = time.time() - t_start
+        if self.rank == 0:
+            save_checkpoint(cfg, self.model, self.learner)
+            fps = self.env_steps / max(self.total_train_seconds, 1e-9)
+            print(f"[sf_b200] Collected {{0: {self.env_steps}}}, FPS: {fps:.1f}", flush=True)   # runner.py:763-764
+        return status
+
+
+def _jsonable(v) -> bool:
+    try:
+        json.dumps(v)
+        return True
+    except TypeError:
+        return False
+
+
+def make_runner(cfg):
+    """train.py:12-28"""
+    return cfg, Runner(cfg)
+
+
+def run_rl(cfg) -> int:
+    """train.py:31-41"""
+    cfg, runner = make_runner(cfg)
+    status = runner.init()
+    if status == StatusCode.SUCCESS:
+        status = runner.run()
+    return status

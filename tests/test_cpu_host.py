@@ -1,0 +1,181 @@
+"""CPU-only tests (-m "not gpu"): the C-ABI library loads and exports every symbol include/sfb200.h declares (no compute
+calls without a GPU), the host-side logic (config surface, model/checkpoint naming, LR schedulers), and the
+data-parallel host logic under gloo with world_size 2."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    import ctypes
+
+    from sample_factory_b200._lib import LIB_PATH, lib, parse_header
+
+    protos = parse_header()
+    assert len(protos) >= 29
+    cdll = ctypes.CDLL(LIB_PATH)
+    for name in protos:
+        assert hasattr(cdll, name), f"{name} declared in include/sfb200.h but not exported by libsfb200.so"
+    out = subprocess.run(["nm", "-D", "--defined-only", LIB_PATH], capture_output=True, text=True).stdout
+    exported = {line.split()[-1] for line in out.splitlines() if " T " in line}
+    assert {n for n in exported if n.startswith("sfb200_")} == set(protos), "exported ABI != declared ABI"
+    # value-returning queries are safe without a GPU
+    l = lib()
+    assert l.query("sfb200_abi_version") == 1
+    assert l.query("sfb200_moments_workspace_bytes", 64) > 0
+    assert l.query("sfb200_loss_workspace_bytes", 32768) > 0
+    assert l.query("sfb200_heads_backward_workspace_bytes", 512, 8) > 0
+    assert l.query("sfb200_linear_backward_workspace_bytes", 32768, 512, 512) > 0
+
+
+def test_sass_is_sm100a_only():
+    from sample_factory_b200._lib import LIB_PATH
+
+    out = subprocess.run(["cuobjdump", "-lelf", LIB_PATH], capture_output=True, text=True).stdout
+    archs = {tok for line in out.splitlines() for tok in line.replace(".", " ").split() if tok.startswith("sm_")}
+    assert archs == {"sm_100a"}, archs
+
+
+def test_no_cpu_fallback():
+    """The product path must fail loudly without a device, not silently compute on the CPU."""
+    from sample_factory_b200 import ops
+
+    with pytest.raises(RuntimeError):
+        ops.normalize_obs(torch.zeros(4, 4), torch.zeros(4, 4), None, None)
+    # and the product package never imports the oracle
+    import ast
+
+    pkg = os.path.join(ROOT, "sample_factory_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            tree = ast.parse(open(os.path.join(pkg, fn)).read())
+            for node in ast.walk(tree):
+                names = []
+                if isinstance(node, ast.Import):
+                    names = [a.name for a in node.names]
+                elif isinstance(node, ast.ImportFrom):
+                    names = [node.module or ""]
+                assert not any(n.split(".")[0] == "oracle" for n in names), f"{fn} imports the oracle"
+
+
+def test_cfg_surface_matches_reference_flags():
+    """Every reference flag (cfg/cfg.py) parses with the reference's default; two-pass parse records cli_args."""
+    from sample_factory_b200.cfg import default_cfg, parse_full_cfg, parse_sf_args, preprocess_cfg
+
+    cfg = default_cfg()
+    assert cfg.gamma == 0.99 and cfg.rollout == 32 and cfg.batch_size == 1024 and cfg.adam_eps == 1e-6
+    assert cfg.encoder_mlp_layers == [512, 512] and cfg.exploration_loss_coeff == 0.003 and cfg.use_rnn is True
+    argv = ["--env=synthetic", "--use_rnn=False", "--encoder_mlp_layers", "64", "64", "--batch_size=4096",
+            "--my_env_flag=3"]
+    parser, partial = parse_sf_args(argv)
+    assert partial.env == "synthetic"
+    parser.add_argument("--my_env_flag", type=int, default=0)       # what sf_examples do between the two passes
+    parser.set_defaults(lr_schedule="linear_decay")                 # mujoco_params.py-style default override
+    cfg = parse_full_cfg(parser, argv)
+    assert cfg.my_env_flag == 3 and cfg.lr_schedule == "linear_decay" and cfg.encoder_mlp_layers == [64, 64]
+    assert set(cfg.cli_args) == {"env", "use_rnn", "encoder_mlp_layers", "batch_size", "my_env_flag"}
+    assert preprocess_cfg(cfg) and cfg.recurrence == 1
+    cfg.with_vtrace = True
+    assert not preprocess_cfg(cfg)   # V-trace needs recurrence == rollout and no returns normalisation
+
+
+def test_model_layout_and_checkpoint_names():
+    from oracle import appo_oracle as O
+    from sample_factory_b200.model import ModelSpec, PolicyModel
+
+    spec = ModelSpec(64, 8)
+    m = PolicyModel(spec, torch.device("cpu"))
+    assert m.num_params == 300553                       # cfg-2 model
+    assert m.names == O.param_names(O.OracleCfg())      # == reference nn.Module.parameters() order
+    sd = m.state_dict()
+    st = O.init_state(O.OracleCfg(), seed=1)
+    assert set(sd.keys()) == set(st.keys())             # reference state_dict keys incl. normalizer buffers
+    m.load_state_dict(st)
+    for k, v in st.items():
+        assert torch.equal(m.state_dict()[k], v)
+    for t in m.params.values():                         # 256-byte alignment of every tensor in the flat buffer
+        assert t.data_ptr() % 256 == m.flat.data_ptr() % 256
+    osd = m.optimizer_state_dict(step=3, lr=1e-4, betas=(0.9, 0.999), eps=1e-6)
+    assert len(osd["state"]) == len(m.names) and osd["param_groups"][0]["params"] == list(range(len(m.names)))
+    # orthogonal init (actor_critic.py:73-96): W W^T = I for the wide first layer, biases zero
+    W = m2 = PolicyModel(spec, torch.device("cpu"), seed=0).params["encoder.encoders.obs.mlp_head.0.weight"]
+    np.testing.assert_allclose((W.t() @ W).numpy(), np.eye(64), atol=1e-5)
+
+
+def test_lr_schedulers():
+    from sample_factory_b200.cfg import default_cfg
+    from sample_factory_b200.learner import get_lr_scheduler
+
+    cfg = default_cfg()
+    cfg.lr_schedule = "kl_adaptive_epoch"
+    cfg.num_batches_per_epoch = 2
+    s = get_lr_scheduler(cfg)
+    assert s.invoke_after_each_epoch() and not s.invoke_after_each_minibatch()
+    assert s.update(1e-4, [0.1, 0.1]) == pytest.approx(1e-4 / 1.5)      # KL above 2x threshold
+    assert s.update(1e-4, [0.0, 0.001]) == pytest.approx(1.5e-4)        # KL below 0.5x threshold
+    assert s.update(1e-4, [0.008, 0.008]) == 1e-4
+    cfg.lr_schedule = "linear_decay"
+    cfg.train_for_env_steps, cfg.batch_size, cfg.num_epochs, cfg.learning_rate = 10240, 1024, 1, 1.0
+    s = get_lr_scheduler(cfg)
+    assert s.update(1.0, []) == pytest.approx(0.9) and s.update(0.9, []) == pytest.approx(0.8)
+
+
+def test_trajectory_layout_matches_reference():
+    from oracle import appo_oracle as O
+    from sample_factory_b200.trajectory import alloc_trajectory_tensors, trajectory_bytes_per_env_step
+
+    t = alloc_trajectory_tensors(64, 8, 10, 32, "cpu")
+    ref = O.alloc_trajectories(O.OracleCfg(), 10)
+    assert set(t) == set(ref)
+    for k in t:
+        assert t[k].shape == ref[k].shape and t[k].dtype == ref[k].dtype, k
+    assert trajectory_bytes_per_env_step(64, 8) == 574
+
+
+_GLOO_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from sample_factory_b200.dist_utils import init_from_env, pooled_moments_, allreduce_sum_
+rank, local_rank, world = init_from_env("gloo")
+assert world == 2
+g = torch.Generator().manual_seed(0)
+full = torch.randn(2000, 7, generator=g) * 3 + 1          # the data one process holding all envs would see
+mine = full[rank * 1000:(rank + 1) * 1000]                # this rank's env shard
+bm, bv = mine.mean(0), mine.var(0)
+total = pooled_moments_(bm, bv, 1000)
+assert total == 2000
+assert torch.allclose(bm, full.mean(0), atol=1e-6), (bm, full.mean(0))
+assert torch.allclose(bv, full.var(0), atol=1e-5), (bv, full.var(0))
+grad = torch.full((5,), float(rank + 1))
+allreduce_sum_(grad)
+assert torch.equal(grad, torch.full((5,), 3.0))
+# advantage statistics: per-rank (count, sum, sumsq) partials add up to the global ones
+adv = full[:, 0]; a = adv[rank * 1000:(rank + 1) * 1000].double()
+part = torch.stack([torch.tensor(float(a.numel()), dtype=torch.float64), a.sum(), (a * a).sum()])
+allreduce_sum_(part)
+mean = part[1] / part[0]; std = torch.sqrt((part[2] - part[1] * mean) / (part[0] - 1))
+assert abs(mean - adv.double().mean()) < 1e-9 and abs(std - adv.double().std()) < 1e-9
+dist.barrier(); dist.destroy_process_group()
+print("rank", rank, "ok")
+"""
+
+
+def test_data_parallel_host_logic_gloo_world2(tmp_path):
+    script = tmp_path / "gloo_worker.py"
+    script.write_text(_GLOO_WORKER)
+    procs = []
+    port = 29000 + (os.getpid() % 2000)
+    for rank in range(2):
+        env = dict(os.environ, RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1",
+                   MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, str(script), ROOT], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    for p in procs:
+        out, _ = p.communicate(timeout=240)
+        assert p.returncode == 0, out

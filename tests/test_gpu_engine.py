@@ -1,0 +1,236 @@
+"""End-to-end parity of the device engine (DeviceSampler + Learner, through the C ABI) against
+  (a) the committed golden vectors produced by the reference itself (tests/golden/*.npz), and
+  (b) the CPU oracle on larger seeded inputs,
+plus size-independent properties at BASELINE.json's full size (N=4096, T=32)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import appo_oracle as O
+from tests.golden_utils import load_case, state_from, traj_from
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def make_cfg(ocfg: O.OracleCfg, **over):
+    from sample_factory_b200.cfg import default_cfg
+
+    cfg = default_cfg()
+    for k in ["rollout", "recurrence", "batch_size", "num_batches_per_epoch", "num_epochs", "gamma", "gae_lambda",
+              "ppo_clip_ratio", "ppo_clip_value", "exploration_loss_coeff", "value_loss_coeff", "kl_loss_coeff",
+              "max_grad_norm", "learning_rate", "adam_eps", "adam_beta1", "adam_beta2", "normalize_input",
+              "normalize_returns", "value_bootstrap", "with_vtrace", "vtrace_rho", "vtrace_c", "reward_scale",
+              "reward_clip", "max_policy_lag", "nonlinearity", "obs_subtract_mean", "obs_scale"]:
+        setattr(cfg, k, getattr(ocfg, k))
+    cfg.encoder_mlp_layers = list(ocfg.encoder_mlp_layers)
+    cfg.decoder_mlp_layers = list(ocfg.decoder_mlp_layers)
+    cfg.use_rnn = False
+    cfg.async_rl = False
+    for k, v in over.items():
+        setattr(cfg, k, v)
+    return cfg
+
+
+def build(ocfg: O.OracleCfg, N: int, state, tape, dev, engine="simt", graph=False):
+    from sample_factory_b200 import ops
+    from sample_factory_b200.envs import TapeVecEnv
+    from sample_factory_b200.learner import Learner
+    from sample_factory_b200.model import ModelSpec, PolicyModel
+    from sample_factory_b200.sampler import DeviceSampler
+    from sample_factory_b200.trajectory import alloc_trajectory_tensors
+
+    ops.bind_device(dev)
+    cfg = make_cfg(ocfg)
+    spec = ModelSpec(ocfg.obs_dim, ocfg.num_actions, list(ocfg.encoder_mlp_layers), list(ocfg.decoder_mlp_layers),
+                     ocfg.nonlinearity, ocfg.normalize_input, ocfg.normalize_returns, ocfg.obs_subtract_mean,
+                     ocfg.obs_scale)
+    model = PolicyModel(spec, dev)
+    model.load_state_dict(state, strict=False)
+    traj = alloc_trajectory_tensors(ocfg.obs_dim, ocfg.num_actions, N, ocfg.rollout, dev)
+    env = TapeVecEnv(tape.to(dev).contiguous(), ocfg.num_actions)
+    sampler = DeviceSampler(cfg, env, model, traj, engine=ops.ENGINES[engine], use_cuda_graph=graph)
+    learner = Learner(cfg, model, N, engine=ops.ENGINES[engine])
+    return cfg, model, traj, env, sampler, learner
+
+
+def upload_traj(traj_dev, traj_cpu):
+    for k, v in traj_cpu.items():
+        traj_dev[k].copy_(v.view(traj_dev[k].shape))
+
+
+@pytest.mark.parametrize("name", ["tiny_gae", "tiny_vtrace", "cfg2_small"])
+def test_rollout_matches_reference_golden(name):
+    """Sampler vs the REFERENCE's own trajectories (same weights, same obs tape, same Exp(1) noise)."""
+    dev = torch.device("cuda", 0)
+    z, meta, ocfg = load_case(name)
+    tape = torch.from_numpy(z["tape"])
+    cfg, model, traj, env, sampler, learner = build(ocfg, meta["N"], state_from(z, "init/"), tape, dev)
+    sampler.reset()
+    for it in range(meta["iters"]):
+        st = state_from(z, "init/") if it == 0 else state_from(z, f"it{it - 1}/state/")
+        model.load_state_dict(st, strict=False)
+        sampler.set_policy_version(int(z[f"it{it}/train_step_before"]))
+        sampler.noise = torch.from_numpy(z[f"it{it}/noise"]).to(dev).contiguous()
+        sampler.rollout()
+        poisoned = meta["poison"] and it == meta["iters"] - 1
+        got = {k: v.cpu() for k, v in traj.items()}
+        ref = {k: torch.from_numpy(z[f"it{it}/traj/{k}"]) for k in
+               ["obs", "actions", "action_logits", "log_prob_actions", "values", "policy_version", "rewards", "dones",
+                "time_outs", "policy_id", "rnn_states"]}
+        for k in ["obs", "rewards", "dones", "time_outs", "rnn_states"]:
+            assert torch.equal(got[k].view(ref[k].shape), ref[k]), k
+        if not poisoned:
+            assert torch.equal(got["policy_id"], ref["policy_id"])
+            assert torch.equal(got["policy_version"], ref["policy_version"])
+        np.testing.assert_allclose(got["action_logits"].numpy(), ref["action_logits"].numpy(), atol=TOL)
+        np.testing.assert_allclose(got["values"][:, :-1].numpy(), ref["values"][:, :-1].numpy(), atol=TOL)
+        # action indices: bit-exact (BASELINE.json). A flip would need p_i/q_i == p_j/q_j to within the 1e-6 logit
+        # difference -- none occurs on these seeded inputs.
+        assert torch.equal(got["actions"].view(ref["actions"].shape), ref["actions"]), "action indices must be bit-exact"
+        np.testing.assert_allclose(got["log_prob_actions"].numpy(), ref["log_prob_actions"].numpy(), atol=TOL)
+
+
+@pytest.mark.parametrize("name", ["tiny_gae", "tiny_vtrace", "cfg2_small"])
+def test_learner_matches_reference_golden(name):
+    """Learner.train on the REFERENCE's trajectories: returns / advantages / loss terms / post-Adam weights /
+    normalizer statistics against what the reference itself computed."""
+    from sample_factory_b200 import ops
+
+    dev = torch.device("cuda", 0)
+    z, meta, ocfg = load_case(name)
+    tape = torch.from_numpy(z["tape"])
+    cfg, model, traj, env, sampler, learner = build(ocfg, meta["N"], state_from(z, "init/"), tape, dev)
+    for it in range(meta["iters"]):
+        assert learner.train_step == int(z[f"it{it}/train_step_before"])
+        upload_traj(traj, traj_from(z, it, ocfg))
+        learner.train(traj)
+        torch.cuda.synchronize()
+        assert learner.train_step == int(z[f"it{it}/train_step_after"])
+        p = f"it{it}/prep/"
+        assert torch.equal(learner.valids_flat.view(-1).cpu(), torch.from_numpy(z[p + "valids"]))
+        np.testing.assert_allclose(traj["values"][:, -1].cpu().numpy(), z[p + "bootstrap_values"], atol=TOL)
+        np.testing.assert_allclose(traj["rewards"].view(-1).cpu().numpy(), z[p + "rewards"], atol=1e-6)
+        if not ocfg.with_vtrace:
+            np.testing.assert_allclose(learner.advantages.view(-1).cpu().numpy(), z[p + "advantages"], atol=TOL)
+            np.testing.assert_allclose(learner.returns.view(-1).cpu().numpy(), z[p + "returns"], atol=TOL)
+        log = learner.minibatch_log().numpy()
+        n_ref = len(z[f"it{it}/loss/policy_loss"])
+        assert log.shape[0] == n_ref
+        for key in ["policy_loss", "value_loss", "exploration_loss", "kl_loss", "adv_mean", "adv_std"]:
+            np.testing.assert_allclose(log[:, ops.LS[key]], z[f"it{it}/loss/{key}"], atol=TOL, rtol=1e-5, err_msg=key)
+        ref_state = state_from(z, f"it{it}/state/")
+        got_state = model.state_dict()
+        for k, v in ref_state.items():
+            tol = 1e-8 if v.dtype == torch.float64 else TOL
+            np.testing.assert_allclose(got_state[k].cpu().numpy(), v.numpy(), atol=tol, rtol=1e-6, err_msg=k)
+
+
+def test_closed_loop_vs_oracle_cfg2_shape():
+    """Sampler + learner for 2 iterations at N=256, T=32, cfg-2 model/hyper-parameters vs the oracle run on the same
+    tape / noise / initial weights (the tape env keeps both rollouts aligned)."""
+    from sample_factory_b200 import ops
+
+    dev = torch.device("cuda", 0)
+    N, T = 256, 32
+    ocfg = O.OracleCfg(rollout=T, recurrence=1, batch_size=N * T // 4, num_batches_per_epoch=4, num_epochs=1)
+    st0 = O.init_state(ocfg, seed=3)
+    gen = torch.Generator().manual_seed(11)
+    tape = torch.randn(2 * T + 1, N, ocfg.obs_dim, generator=gen) * 1.2 - 0.2
+    cfg, model, traj, env, sampler, learner = build(ocfg, N, st0, tape, dev)
+    olearner = O.OracleLearner(ocfg, st0)
+    oenv = O.TapeVecEnv(tape, ocfg.num_actions)
+    olast = oenv.reset()
+    sampler.reset()
+    for it in range(2):
+        noise = torch.empty(T, N, ocfg.num_actions).exponential_(generator=gen)
+        otraj = O.alloc_trajectories(ocfg, N)
+        olast = O.rollout(ocfg, olearner.st, oenv, olast, otraj, noise, olearner.train_step)
+        sampler.noise = noise.to(dev)
+        sampler.set_policy_version(learner.train_step)
+        sampler.rollout()
+        got = {k: v.cpu() for k, v in traj.items()}
+        mism = (got["actions"] != otraj["actions"]).float().mean().item()
+        assert mism == 0.0, f"action mismatch fraction {mism}"
+        for k in ["obs", "rewards", "dones", "time_outs", "policy_id", "policy_version"]:
+            assert torch.equal(got[k], otraj[k]), k
+        np.testing.assert_allclose(got["action_logits"].numpy(), otraj["action_logits"].numpy(), atol=TOL)
+        np.testing.assert_allclose(got["values"][:, :-1].numpy(), otraj["values"][:, :-1].numpy(), atol=TOL)
+        n0 = len(olearner.log)
+        buff = olearner.train(otraj)
+        learner.train(traj)
+        np.testing.assert_allclose(learner.returns.view(-1).cpu().numpy(), buff["returns"].numpy(), atol=TOL)
+        np.testing.assert_allclose(learner.advantages.view(-1).cpu().numpy(), buff["advantages"].numpy(), atol=TOL)
+        log = learner.minibatch_log().numpy()
+        for j, d in enumerate(olearner.log[n0:]):
+            for key in ["policy_loss", "value_loss", "exploration_loss", "kl_loss"]:
+                assert abs(log[j, ops.LS[key]] - d[key]) < TOL, (it, j, key, log[j, ops.LS[key]], d[key])
+            assert abs(learner.grad_norm_log[j].item() - d["grad_norm"]) < 1e-4
+        sd = model.state_dict()
+        for k in O.param_names(ocfg):
+            np.testing.assert_allclose(sd[k].cpu().numpy(), olearner.st[k].numpy(), atol=TOL, err_msg=k)
+
+
+def test_full_size_properties_and_graph_replay():
+    """N=4096, T=32 (BASELINE.json config 2): size-independent properties.
+    * CUDA-graph replay and eager execution of the same rollout produce identical trajectories (Philox noise is a
+      pure function of (seed, env, step) and both counters live on the device)
+    * GAE linearity in the rewards; value targets = adv + values; returns-normaliser round trip
+    * a training iteration changes the weights, keeps everything finite, and leaves padding untouched."""
+    from sample_factory_b200 import ops
+
+    dev = torch.device("cuda", 0)
+    N, T = 4096, 32
+    ocfg = O.OracleCfg(rollout=T, recurrence=1, batch_size=N * T // 4, num_batches_per_epoch=4)
+    st0 = O.init_state(ocfg, seed=5)
+    tape = torch.randn(3 * T + 1, N, ocfg.obs_dim, generator=torch.Generator().manual_seed(12))
+    cfgA, modelA, trajA, envA, samplerA, learnerA = build(ocfg, N, st0, tape, dev, graph=False)
+    cfgB, modelB, trajB, envB, samplerB, learnerB = build(ocfg, N, st0, tape, dev, graph=True)
+    samplerA.reset()
+    samplerB.reset()
+    samplerA.rollout()
+    samplerB.rollout()   # warm-up + capture + first replay start from the same counters? -> compare second rollouts
+    # Graph capture runs the rollout eagerly once (warm-up) before replaying, so B is ahead; re-align both and compare
+    for s, e in ((samplerA, envA), (samplerB, envB)):
+        s.reset()
+        s.step_counter.zero_()
+    samplerA.rollout()
+    samplerB.rollout()
+    torch.cuda.synchronize()
+    for k in trajA:
+        assert torch.equal(trajA[k], trajB[k]), f"graph replay differs from eager for {k}"
+    a = trajA["actions"]
+    assert a.min().item() >= 0 and a.max().item() <= ocfg.num_actions - 1
+    assert torch.all(trajA["policy_id"] == 0) and torch.isfinite(trajA["action_logits"]).all()
+    freq = torch.bincount(a.view(-1).long(), minlength=ocfg.num_actions).float() / a.numel()
+    assert freq.min().item() > 0.01, "every action should be sampled under near-uniform initial logits"
+
+    # GAE linearity at full size
+    r1 = torch.randn(N, T, device=dev)
+    r2 = torch.randn(N, T, device=dev)
+    dones = trajA["dones"]
+    zeros_v = torch.zeros(N, T + 1, device=dev)
+    ones_valid = torch.ones(N, T + 1, dtype=torch.bool, device=dev)
+    outs = []
+    for r in (r1, r2, r1 + r2):
+        adv = torch.empty(N, T, device=dev)
+        ret = torch.empty(N, T, device=dev)
+        ops.gae_returns(r.clone(), dones, trajA["time_outs"], zeros_v, ones_valid, 0.99, 0.95, False, None, None, adv, ret)
+        outs.append(adv)
+        assert torch.equal(adv, ret)   # values == 0 -> returns == advantages
+    assert (outs[0] + outs[1] - outs[2]).abs().max().item() < 1e-4
+
+    before = modelA.flat.clone()
+    learnerA.train(trajA)
+    torch.cuda.synchronize()
+    assert torch.isfinite(modelA.flat).all() and not torch.equal(before, modelA.flat)
+    stats = learnerA.fetch_stats()
+    assert all(np.isfinite(v) for v in stats.values()), stats
+    assert stats["num_valid"] == N * T // 4
+    assert torch.isfinite(learnerA.advantages).all() and torch.isfinite(learnerA.returns).all()
+    # padding between tensors in the flat buffer must stay zero (zero grad -> zero Adam update)
+    mask = torch.ones_like(modelA.flat, dtype=torch.bool)
+    for n in modelA.names:
+        o, shp = modelA._slices[n]
+        mask[o:o + int(np.prod(shp))] = False
+    assert torch.all(modelA.flat[mask] == 0)

@@ -1,0 +1,494 @@
+"""Per-kernel parity tests: every libsfb200 entry point (called through the ctypes C ABI) against the CPU oracle
+(oracle/appo_oracle.py, itself pinned to the reference by tests/test_oracle_golden.py) on identical seeded inputs.
+Tolerances: bit-exact for integer / bool / index outputs and for the pure-elementwise normaliser; 1e-5 abs for fp32
+reductions and GEMMs (BASELINE.json north_star)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import appo_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def dev():
+    from sample_factory_b200 import ops
+
+    d = torch.device("cuda", 0)
+    ops.bind_device(d)
+    return d
+
+
+def _ops():
+    from sample_factory_b200 import ops
+
+    return ops
+
+
+def g(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+# ----------------------------------------------------------------------------------------------- normalizers
+@pytest.mark.parametrize("rows,dim", [(1, 4), (257, 64), (1000, 27), (4096, 64)])
+def test_normalize_obs_bit_exact(dev, rows, dim):
+    ops = _ops()
+    x = torch.randn(rows, dim, generator=g(0)) * 3 + 1
+    mean = torch.randn(dim, generator=g(1), dtype=torch.float64)
+    var = torch.rand(dim, generator=g(2), dtype=torch.float64) * 4 + 0.01
+    ref = x.clone()
+    O.rms_normalize_(ref, mean, var)
+    out = torch.empty_like(x, device=dev)
+    ops.normalize_obs(x.to(dev), out, mean.to(dev), var.to(dev))
+    assert torch.equal(out.cpu(), ref)
+    # sub-mean / scale path (normalize.py:62-67), e.g. Atari obs_scale=255
+    ref2 = x.clone()
+    ref2.sub_(0.5).mul_(1.0 / 255.0)
+    O.rms_normalize_(ref2, mean, var)
+    ops.normalize_obs(x.to(dev), out, mean.to(dev), var.to(dev), 0.5, 1.0 / 255.0)
+    assert torch.equal(out.cpu(), ref2)
+
+
+@pytest.mark.parametrize("rows,dim", [(33, 1), (1056, 16), (135168, 64), (5000, 27), (300, 300)])
+def test_moments_and_merge(dev, rows, dim):
+    ops = _ops()
+    x = torch.randn(rows, dim, generator=g(3)) * 2 + 5
+    mean = torch.zeros(dim, dtype=torch.float64)
+    var = torch.ones(dim, dtype=torch.float64)
+    count = torch.ones(1, dtype=torch.float64)
+    md, vd, cd = mean.to(dev), var.to(dev), count.to(dev)
+    bm = torch.empty(dim, device=dev)
+    bv = torch.empty(dim, device=dev)
+    ws = torch.empty(ops.moments_workspace_bytes(dim) // 4, device=dev)
+    xd = x.to(dev)
+    for _ in range(2):  # two successive updates exercise the merge with count > 1
+        O.rms_update(mean, var, count, x)
+        ops.batch_moments(xd, bm, bv, ws)
+        ops.rms_merge(md, vd, cd, bm, bv, float(rows))
+    np.testing.assert_allclose(bm.cpu().numpy(), x.mean(0).numpy(), rtol=2e-6, atol=2e-6)
+    np.testing.assert_allclose(bv.cpu().numpy(), x.var(0).numpy(), rtol=2e-5, atol=1e-6)
+    np.testing.assert_allclose(md.cpu().numpy(), mean.numpy(), rtol=1e-6, atol=2e-6)
+    np.testing.assert_allclose(vd.cpu().numpy(), var.numpy(), rtol=2e-5, atol=1e-6)
+    assert cd.item() == count.item()
+
+
+def test_returns_normalizer_roundtrip(dev):
+    """reference tests/algo/test_rms.py:11-68: normalize -> denormalize round trip (atol 1e-6 x scale)."""
+    ops = _ops()
+    x = torch.randn(100000, generator=g(4)) * 0.8 + 0.3
+    mean = torch.tensor([0.25], dtype=torch.float64)
+    var = torch.tensor([0.7], dtype=torch.float64)
+    ref = x.clone()
+    O.rms_normalize_(ref, mean, var)
+    xd = x.to(dev)
+    ops.rms_apply_scalar(xd, mean.to(dev), var.to(dev), denormalize=False)
+    assert torch.equal(xd.cpu(), ref)
+    ops.rms_apply_scalar(xd, mean.to(dev), var.to(dev), denormalize=True)
+    np.testing.assert_allclose(xd.cpu().numpy(), x.numpy(), atol=2e-6)
+    ref_d = ref.clone()
+    O.rms_denormalize_(ref_d, mean, var)
+    assert torch.equal(xd.cpu(), ref_d)
+
+
+# ----------------------------------------------------------------------------------------------- GEMM layers
+@pytest.mark.parametrize("M,N,K,act", [(1, 8, 4, "elu"), (300, 70, 37, "elu"), (4096, 512, 64, "elu"),
+                                       (1000, 512, 512, "relu"), (513, 129, 256, "tanh"), (128, 64, 16, "none")])
+@pytest.mark.parametrize("engine", ["simt", "3xtf32"])
+def test_linear_act_forward(dev, M, N, K, act, engine):
+    ops = _ops()
+    if engine != "simt" and not ops.tc_available():
+        pytest.skip("tcgen05 engine not built")
+    x = torch.randn(M, K, generator=g(5))
+    W = torch.randn(N, K, generator=g(6)) / math.sqrt(K)
+    b = torch.randn(N, generator=g(7)) * 0.1
+    cfg = O.OracleCfg(nonlinearity=act if act != "none" else "elu")
+    z = torch.nn.functional.linear(x.double(), W.double(), b.double())
+    ref = (O._act(cfg, z) if act != "none" else z).float()
+    out = torch.empty(M, N, device=dev)
+    ops.linear_act_forward(x.to(dev), W.to(dev), b.to(dev), out, ops.ACT[act], ops.ENGINES[engine])
+    np.testing.assert_allclose(out.cpu().numpy(), ref.numpy(), atol=TOL, rtol=1e-5)
+
+
+def test_linear_forward_strided_input(dev):
+    """The learner feeds obs[:, T] rows in place: x row stride != K."""
+    ops = _ops()
+    base = torch.randn(64, 9, 32, generator=g(8))
+    x = base[:, 8]
+    W = torch.randn(48, 32, generator=g(9)) / 6
+    b = torch.zeros(48)
+    ref = torch.nn.functional.elu(torch.nn.functional.linear(x, W, b))
+    bd = base.to(dev)
+    out = torch.empty(64, 48, device=dev)
+    ops.linear_act_forward(bd[:, 8], W.to(dev), b.to(dev), out, ops.ACT["elu"], ops.GEMM_SIMT)
+    np.testing.assert_allclose(out.cpu().numpy(), ref.numpy(), atol=TOL)
+
+
+@pytest.mark.parametrize("M,N,K,act_prev", [(64, 8, 4, "elu"), (1000, 70, 37, "elu"), (4096, 512, 512, "elu"),
+                                            (2048, 512, 64, "none"), (777, 130, 260, "tanh")])
+@pytest.mark.parametrize("engine", ["simt", "3xtf32"])
+def test_linear_backward(dev, M, N, K, act_prev, engine):
+    ops = _ops()
+    if engine != "simt" and not ops.tc_available():
+        pytest.skip("tcgen05 engine not built")
+    dz = torch.randn(M, N, generator=g(10)) / M
+    # x is the previous layer's OUTPUT: make it a genuine activation output so act'(x) is well defined
+    pre = torch.randn(M, K, generator=g(11))
+    cfg = O.OracleCfg(nonlinearity=act_prev if act_prev != "none" else "elu")
+    x = O._act(cfg, pre) if act_prev != "none" else pre
+    W = torch.randn(N, K, generator=g(12)) / math.sqrt(K)
+    dW_ref = (dz.double().t() @ x.double()).float()
+    dxl = (dz.double() @ W.double())
+    if act_prev == "elu":
+        d = torch.where(pre > 0, torch.ones_like(pre), torch.exp(pre)).double()
+    elif act_prev == "tanh":
+        d = (1 - torch.tanh(pre) ** 2).double()
+    else:
+        d = torch.ones_like(pre).double()
+    dx_ref = (dxl * d).float()
+    db_ref = dx_ref.double().sum(0).float()
+    dW = torch.empty(N, K, device=dev)
+    dx = torch.empty(M, K, device=dev)
+    dbp = torch.empty(K, device=dev)
+    ws = torch.empty(ops.linear_backward_workspace_bytes(M, N, K) // 4 + 4, device=dev)
+    ops.linear_backward(dz.to(dev), x.to(dev), W.to(dev), ops.ACT[act_prev], dW, dx, dbp, ops.ENGINES[engine], ws)
+    np.testing.assert_allclose(dW.cpu().numpy(), dW_ref.numpy(), atol=TOL, rtol=1e-4)
+    np.testing.assert_allclose(dx.cpu().numpy(), dx_ref.numpy(), atol=TOL, rtol=1e-4)
+    np.testing.assert_allclose(dbp.cpu().numpy(), db_ref.numpy(), atol=TOL, rtol=1e-4)
+
+
+# ----------------------------------------------------------------------------------------------- heads
+@pytest.mark.parametrize("rows,H,A", [(5, 64, 8), (4096, 512, 8), (1001, 96, 3), (257, 128, 17), (64, 512, 31)])
+def test_heads_forward_and_sampling(dev, rows, H, A):
+    ops = _ops()
+    h = torch.randn(rows, H, generator=g(13))
+    Wv = torch.randn(1, H, generator=g(14)) / math.sqrt(H)
+    bv = torch.randn(1, generator=g(15))
+    Wa = torch.randn(A, H, generator=g(16)) / math.sqrt(H) * 2
+    ba = torch.randn(A, generator=g(17)) * 0.1
+    noise = torch.empty(rows, A).exponential_(generator=g(18))
+    values_ref = torch.nn.functional.linear(h, Wv, bv).squeeze(-1)
+    logits_ref = torch.nn.functional.linear(h, Wa, ba)
+
+    T = 3  # write into strided "trajectory slots" like the sampler does
+    values = torch.zeros(rows, T + 1, device=dev)
+    logits = torch.zeros(rows, T, A, device=dev)
+    actions = torch.zeros(rows, T, 1, device=dev)
+    logp = torch.zeros(rows, T, device=dev)
+    pv = torch.zeros(rows, T, device=dev)
+    env_actions = torch.zeros(rows, dtype=torch.int32, device=dev)
+    pvs = torch.tensor([7.0], device=dev)
+    t = 1
+    ops.heads_forward(h.to(dev), Wv.to(dev), bv.to(dev), Wa.to(dev), ba.to(dev), values[:, t], values.stride(0),
+                      logits[:, t], logits.stride(0), noise.to(dev), 0, 0, None, actions[:, t], actions.stride(0),
+                      env_actions, logp[:, t], logp.stride(0), pvs, pv[:, t], pv.stride(0))
+    np.testing.assert_allclose(values[:, t].cpu().numpy(), values_ref.numpy(), atol=TOL)
+    np.testing.assert_allclose(logits[:, t].cpu().numpy(), logits_ref.numpy(), atol=TOL)
+    # sampling is checked on the DEVICE logits (feeding identical logits to both sides, SURVEY section 7 hard parts)
+    dl = logits[:, t].cpu()
+    a_ref = O.cat_sample(dl, noise)
+    assert torch.equal(env_actions.cpu().long(), a_ref.view(-1)), "action indices must be bit-exact"
+    assert torch.equal(actions[:, t, 0].cpu(), a_ref.view(-1).float())
+    np.testing.assert_allclose(logp[:, t].cpu().numpy(), O.cat_log_prob(dl, a_ref).numpy(), atol=2e-6)
+    assert torch.all(pv[:, t] == 7.0) and torch.all(pv[:, 0] == 0) and torch.all(values[:, 0] == 0)
+
+
+def test_heads_philox_sampling_distribution(dev):
+    """Production path: in-kernel Philox Exp(1) noise. Empirical action frequencies must match softmax(logits)."""
+    ops = _ops()
+    rows, H, A = 200000, 32, 8
+    h = torch.zeros(rows, H)
+    h[:, 0] = 1.0
+    Wa = torch.zeros(A, H)
+    Wa[:, 0] = torch.tensor([0.0, 0.5, 1.0, 1.5, -1.0, 2.0, 0.2, -0.3])
+    p_ref = torch.softmax(Wa[:, 0], 0)
+    values = torch.empty(rows, device=dev)
+    actions = torch.empty(rows, device=dev)
+    env_actions = torch.empty(rows, dtype=torch.int32, device=dev)
+    cnt = torch.tensor([5], dtype=torch.int64, device=dev)
+    z1 = torch.zeros(1, device=dev)
+    for seed, off in [(1, None), (1, cnt), (2, None)]:
+        ops.heads_forward(h.to(dev), torch.zeros(1, H, device=dev), z1, Wa.to(dev), torch.zeros(A, device=dev), values, 1,
+                          None, 0, None, seed, 0, off, actions, 1, env_actions)
+        freq = torch.bincount(env_actions.cpu().long(), minlength=A).float() / rows
+        np.testing.assert_allclose(freq.numpy(), p_ref.numpy(), atol=5e-3)
+        if seed == 1 and off is None:
+            first = env_actions.clone()
+        elif seed == 1:
+            assert (env_actions != first).float().mean() > 0.3, "device-side offset must change the stream"
+
+
+@pytest.mark.parametrize("rows,H,A,act", [(64, 64, 8, "elu"), (32768, 512, 8, "elu"), (1000, 96, 3, "relu"),
+                                          (555, 300, 17, "tanh")])
+def test_heads_backward(dev, rows, H, A, act):
+    ops = _ops()
+    cfg = O.OracleCfg(nonlinearity=act)
+    pre = torch.randn(rows, H, generator=g(19))
+    h = O._act(cfg, pre)
+    Wv = torch.randn(1, H, generator=g(20)) / math.sqrt(H)
+    Wa = torch.randn(A, H, generator=g(21)) / math.sqrt(H)
+    dlogits = torch.randn(rows, A, generator=g(22)) / rows
+    dvalues = torch.randn(rows, generator=g(23)) / rows
+    dh = dlogits.double() @ Wa.double() + dvalues.double()[:, None] * Wv.double()
+    if act == "elu":
+        d = torch.where(pre > 0, torch.ones_like(pre), torch.exp(pre)).double()
+    elif act == "relu":
+        d = (pre > 0).double()
+    else:
+        d = (1 - torch.tanh(pre) ** 2).double()
+    dz_ref = (dh * d).float()
+    dz = torch.empty(rows, H, device=dev)
+    dWv = torch.empty(H, device=dev)
+    dbv = torch.empty(1, device=dev)
+    dWa = torch.empty(A, H, device=dev)
+    dba = torch.empty(A, device=dev)
+    dbp = torch.empty(H, device=dev)
+    ws = torch.empty(ops.heads_backward_workspace_bytes(H, A) // 4 + 4, device=dev)
+    ops.heads_backward(h.to(dev), Wv.to(dev).view(-1), Wa.to(dev), dlogits.to(dev), dvalues.to(dev), ops.ACT[act], dz,
+                       dWv, dbv, dWa, dba, dbp, ws)
+    np.testing.assert_allclose(dz.cpu().numpy(), dz_ref.numpy(), atol=TOL, rtol=1e-4)
+    np.testing.assert_allclose(dWa.cpu().numpy(), (dlogits.double().t() @ h.double()).float().numpy(), atol=TOL, rtol=1e-4)
+    np.testing.assert_allclose(dWv.cpu().numpy(), (dvalues.double() @ h.double()).float().numpy(), atol=TOL, rtol=1e-4)
+    np.testing.assert_allclose(dba.cpu().numpy(), dlogits.double().sum(0).float().numpy(), atol=TOL, rtol=1e-4)
+    np.testing.assert_allclose(dbv.cpu().numpy(), dvalues.double().sum().float().numpy(), atol=TOL, rtol=1e-4)
+    np.testing.assert_allclose(dbp.cpu().numpy(), dz_ref.double().sum(0).float().numpy(), atol=TOL, rtol=1e-4)
+
+
+# ----------------------------------------------------------------------------------------------- sampler steps
+def test_sampler_pre_post_step_and_env(dev):
+    ops = _ops()
+    N, D, T, A = 300, 16, 5, 8
+    obs = torch.randn(N, D, generator=g(24))
+    mean = torch.randn(D, generator=g(25), dtype=torch.float64)
+    var = torch.rand(D, generator=g(26), dtype=torch.float64) + 0.1
+    traj_obs = torch.full((N, T + 1, D), -1.0, device=dev)
+    traj_rnn = torch.full((N, T + 1, 1), -1.0, device=dev)
+    rnn = torch.zeros(N, 1, device=dev)
+    xn = torch.empty(N, D, device=dev)
+    t = 2
+    ops.sampler_pre_step(obs.to(dev), traj_obs[:, t], rnn, traj_rnn[:, t], xn, mean.to(dev), var.to(dev), 0.0, 1.0)
+    ref = obs.clone()
+    O.rms_normalize_(ref, mean, var)
+    assert torch.equal(xn.cpu(), ref)
+    assert torch.equal(traj_obs[:, t].cpu(), obs) and torch.all(traj_obs[:, t + 1] == -1) and torch.all(traj_obs[:, t - 1] == -1)
+    assert torch.all(traj_rnn[:, t] == 0) and torch.all(traj_rnn[:, t + 1] == -1)
+
+    # tape env vs the oracle's env, several steps, device-side step counter
+    L = 7
+    tape = torch.randn(L, N, D, generator=g(27))
+    env_ref = O.TapeVecEnv(tape, A)
+    env_ref.reset()
+    from sample_factory_b200.envs import TapeVecEnv
+
+    env = TapeVecEnv(tape.to(dev), A)
+    assert torch.equal(env.reset().cpu(), tape[0])
+    rew_t = torch.zeros(N, T, device=dev)
+    done_t = torch.zeros(N, T, dtype=torch.bool, device=dev)
+    to_t = torch.zeros(N, T, dtype=torch.bool, device=dev)
+    pid_t = torch.full((N, T), -1, dtype=torch.int32, device=dev)
+    ep_ret = torch.zeros(N, device=dev)
+    ep_len = torch.zeros(N, dtype=torch.int32, device=dev)
+    ep_min = torch.full((N,), float("inf"), device=dev)
+    ep_max = torch.full((N,), float("-inf"), device=dev)
+    stats = torch.zeros(8, dtype=torch.float64, device=dev)
+    counter = torch.zeros(1, dtype=torch.int64, device=dev)
+    ref_ret = torch.zeros(N)
+    ref_len = torch.zeros(N)
+    fin_cnt, fin_ret, fin_len = 0, 0.0, 0.0
+    for step in range(T):
+        a = torch.randint(0, A, (N,), generator=g(100 + step), dtype=torch.int32)
+        o_ref, r_ref, tm_ref, tr_ref = env_ref.step(a)
+        o, r, tm, tr = env.step(a.to(dev))
+        assert torch.equal(o.cpu(), o_ref) and torch.equal(r.cpu(), r_ref)
+        assert torch.equal(tm.cpu(), tm_ref) and torch.equal(tr.cpu(), tr_ref)
+        ops.sampler_post_step(r, tm, tr, 0.7, 0.5, 0, rew_t[:, step], done_t[:, step], to_t[:, step], pid_t[:, step],
+                              ep_ret, ep_len, ep_min, ep_max, 1, stats, counter)
+        d_ref = tm_ref | tr_ref
+        assert torch.equal(rew_t[:, step].cpu(), (r_ref * 0.7).clamp(-0.5, 0.5))
+        assert torch.equal(done_t[:, step].cpu(), d_ref) and torch.equal(to_t[:, step].cpu(), tr_ref)
+        ref_ret += r_ref
+        ref_len += 1
+        fin_cnt += int(d_ref.sum())
+        fin_ret += float(ref_ret[d_ref].sum())
+        fin_len += float(ref_len[d_ref].sum())
+        ref_ret[d_ref] = 0
+        ref_len[d_ref] = 0
+    assert torch.all(pid_t == 0) and counter.item() == T and env.step_counter.item() == T
+    s = stats.cpu()
+    assert int(s[0]) == fin_cnt and abs(s[1].item() - fin_ret) < 1e-3 and abs(s[2].item() - fin_len) < 1e-6
+    np.testing.assert_allclose(ep_ret.cpu().numpy(), ref_ret.numpy(), atol=1e-6)
+
+
+def test_compute_valids(dev):
+    ops = _ops()
+    N, T = 200, 9
+    pid = torch.randint(-1, 2, (N, T), generator=g(28), dtype=torch.int32)
+    pver = torch.randint(0, 50, (N, T), generator=g(29)).float()
+    valids = torch.zeros(N, T + 1, dtype=torch.bool, device=dev)
+    ops.compute_valids(pid.to(dev), pver.to(dev), 0, 40, 25, valids)
+    ref = torch.zeros(N, T + 1, dtype=torch.bool)
+    ref[:, :-1] = (pid == 0) & (40 - pver < 25)
+    ref[:, -1] = ref[:, -2]
+    assert torch.equal(valids.cpu(), ref)
+
+
+# ----------------------------------------------------------------------------------------------- time-axis scans
+@pytest.mark.parametrize("N,T", [(7, 1), (257, 8), (4096, 32), (100, 50), (33, 128)])
+@pytest.mark.parametrize("bootstrap,denorm", [(False, False), (True, True)])
+def test_gae_returns(dev, N, T, bootstrap, denorm):
+    ops = _ops()
+    rewards = torch.randn(N, T, generator=g(30))
+    dones = torch.rand(N, T, generator=g(31)) < 0.1
+    time_outs = dones & (torch.rand(N, T, generator=g(32)) < 0.5)
+    values = torch.randn(N, T + 1, generator=g(33))
+    valids = torch.rand(N, T + 1, generator=g(34)) < 0.8
+    mean = torch.tensor([0.3], dtype=torch.float64)
+    var = torch.tensor([2.5], dtype=torch.float64)
+    gamma, lam = 0.99, 0.95
+    dv = values.clone()
+    if denorm:
+        O.rms_denormalize_(dv, mean, var)
+    r = rewards.clone()
+    if bootstrap:
+        r.add_(gamma * dv[:, :-1] * time_outs * dones)
+    adv_ref = O.gae_advantages(r, dones, dv, valids, gamma, lam)
+    ret_ref = adv_ref + valids[:, :-1] * dv[:, :-1]
+    rd = rewards.to(dev)
+    adv = torch.empty(N, T, device=dev)
+    ret = torch.empty(N, T, device=dev)
+    ops.gae_returns(rd, dones.to(dev), time_outs.to(dev), values.to(dev), valids.to(dev), gamma, lam, bootstrap,
+                    mean.to(dev) if denorm else None, var.to(dev) if denorm else None, adv, ret)
+    assert torch.equal(rd.cpu(), r), "value-bootstrapped rewards must match bit for bit"
+    np.testing.assert_allclose(adv.cpu().numpy(), adv_ref.numpy(), atol=TOL, rtol=1e-5)
+    np.testing.assert_allclose(ret.cpu().numpy(), ret_ref.numpy(), atol=TOL, rtol=1e-5)
+
+
+@pytest.mark.parametrize("n,R", [(5, 2), (300, 8), (1024, 32), (50, 40)])
+def test_vtrace(dev, n, R):
+    ops = _ops()
+    cfg = O.OracleCfg(gamma=0.99, vtrace_rho=1.0, vtrace_c=0.9)
+    ratio = torch.exp(torch.randn(n * R, generator=g(35)) * 0.3).clamp(0.05, 20)
+    values = torch.randn(n * R, generator=g(36))
+    rewards = torch.randn(n * R, generator=g(37))
+    dones = torch.rand(n * R, generator=g(38)) < 0.1
+    vs_ref, adv_ref = O.vtrace(cfg, ratio, values, rewards, dones.float(), R)
+    vs = torch.empty(n * R, device=dev)
+    adv = torch.empty(n * R, device=dev)
+    ops.vtrace(ratio.to(dev), values.to(dev), rewards.to(dev), dones.to(dev), R, cfg.gamma, cfg.vtrace_rho, cfg.vtrace_c,
+               vs, adv)
+    np.testing.assert_allclose(vs.cpu().numpy(), vs_ref.numpy(), atol=TOL, rtol=1e-5)
+    np.testing.assert_allclose(adv.cpu().numpy(), adv_ref.numpy(), atol=TOL, rtol=1e-5)
+
+
+# ----------------------------------------------------------------------------------------------- loss
+@pytest.mark.parametrize("B,A,frac_invalid,kl_coeff", [(64, 8, 0.0, 0.0), (1000, 8, 0.2, 0.1), (32768, 8, 0.0, 0.0),
+                                                       (777, 3, 0.3, 0.5), (513, 17, 0.1, 0.2)])
+def test_ppo_loss_fwd_bwd(dev, B, A, frac_invalid, kl_coeff):
+    ops = _ops()
+    cfg = O.OracleCfg(num_actions=A, kl_loss_coeff=kl_coeff, ppo_clip_ratio=0.1, ppo_clip_value=0.2)
+    logits = (torch.randn(B, A, generator=g(39)) * 1.5).requires_grad_(True)
+    values = torch.randn(B, generator=g(40)).requires_grad_(True)
+    logits_old = logits.detach() + torch.randn(B, A, generator=g(41)) * 0.3
+    actions = torch.randint(0, A, (B, 1), generator=g(42)).float()
+    lp_old = O.cat_log_prob(logits_old, actions) + torch.randn(B, generator=g(43)) * 0.05
+    v_old = values.detach() + torch.randn(B, generator=g(44)) * 0.3
+    adv = torch.randn(B, generator=g(45)) * 2 + 0.5
+    targets = torch.randn(B, generator=g(46))
+    valids = torch.rand(B, generator=g(47)) >= frac_invalid
+    num_invalids = int((~valids).sum())
+
+    # oracle losses with logits/values as autograd leaves (same formulas as O.calculate_losses :588-657)
+    clip_hi = 1.0 + cfg.ppo_clip_ratio
+    clip_lo = 1.0 / clip_hi
+    lp = O.cat_log_prob(logits, actions)
+    ratio = torch.clamp(torch.exp(lp - lp_old), 0.05, 20.0)
+    adv_std, adv_mean = torch.std_mean(O._masked_select(adv, valids, num_invalids))
+    advn = (adv - adv_mean) / torch.clamp_min(adv_std, 1e-7)
+    pl = -O._masked_select(torch.min(ratio * advn, torch.clamp(ratio, clip_lo, clip_hi) * advn), valids, num_invalids).mean()
+    ent = O._masked_select(O.cat_entropy(logits), valids, num_invalids)
+    el = -cfg.exploration_loss_coeff * ent.mean()
+    kl_old = O._masked_select(O.cat_kl(logits, logits_old), valids, num_invalids)
+    kl = cfg.kl_loss_coeff * kl_old.mean()
+    vc = v_old + torch.clamp(values - v_old, -cfg.ppo_clip_value, cfg.ppo_clip_value)
+    vl = O._masked_select(torch.max((values - targets) ** 2, (vc - targets) ** 2), valids, num_invalids).mean() * cfg.value_loss_coeff
+    total = pl + el + kl + vl
+    total.backward()
+
+    stats = torch.zeros(ops.LS_SIZE, dtype=torch.float64, device=dev)
+    ws = torch.empty(ops.loss_workspace_bytes(B) // 8 + 8, dtype=torch.float64, device=dev)
+    dl = torch.empty(B, A, device=dev)
+    dv = torch.empty(B, device=dev)
+    ops.adv_stats(adv.to(dev), valids.to(dev), stats, None, ws)
+    ops.ppo_loss_fwd_bwd(logits.detach().to(dev), values.detach().to(dev), actions.view(-1).to(dev), lp_old.to(dev),
+                         v_old.to(dev), adv.to(dev), targets.to(dev), valids.to(dev), logits_old.to(dev),
+                         cfg.ppo_clip_ratio, cfg.ppo_clip_value, cfg.exploration_loss_coeff, cfg.value_loss_coeff,
+                         cfg.kl_loss_coeff, 1.0, dl, dv, stats, ws)
+    s = stats.cpu()
+    LS = ops.LS
+    assert int(s[LS["num_valid"]]) == B - num_invalids
+    for key, ref in [("adv_mean", adv_mean), ("adv_std", adv_std), ("policy_loss", pl), ("value_loss", vl),
+                     ("exploration_loss", el), ("kl_loss", kl), ("kl_old_mean", kl_old.mean()),
+                     ("kl_old_max", kl_old.max()), ("total_loss", total)]:
+        assert abs(s[LS[key]].item() - float(ref)) < TOL, (key, s[LS[key]].item(), float(ref))
+    vr = ratio.detach()[valids]
+    assert abs(s[LS["ratio_min"]].item() - float(vr.min())) < TOL and abs(s[LS["ratio_max"]].item() - float(vr.max())) < TOL
+    np.testing.assert_allclose(dl.cpu().numpy(), logits.grad.numpy(), atol=1e-7, rtol=2e-4)
+    np.testing.assert_allclose(dv.cpu().numpy(), values.grad.numpy(), atol=1e-7, rtol=2e-4)
+    # properties that hold at any size: softmax-gradient rows sum to zero, invalid rows get exactly zero gradient
+    assert dl.sum(-1).abs().max().item() < 1e-6
+    assert torch.all(dl.cpu()[~valids] == 0) and torch.all(dv.cpu()[~valids] == 0)
+
+
+def test_action_ratio(dev):
+    ops = _ops()
+    B, A = 1000, 8
+    logits = torch.randn(B, A, generator=g(48))
+    actions = torch.randint(0, A, (B, 1), generator=g(49)).float()
+    lp_old = torch.randn(B, generator=g(50)) - 2
+    ref = torch.clamp(torch.exp(O.cat_log_prob(logits, actions) - lp_old), 0.05, 20.0)
+    out = torch.empty(B, device=dev)
+    ops.action_ratio(logits.to(dev), actions.view(-1).to(dev), lp_old.to(dev), out)
+    np.testing.assert_allclose(out.cpu().numpy(), ref.numpy(), rtol=2e-6, atol=1e-6)
+
+
+# ----------------------------------------------------------------------------------------------- optimizer
+@pytest.mark.parametrize("n,max_norm", [(1000, 4.0), (300553, 4.0), (300553, 0.0), (4097, 1e-3)])
+def test_clip_adam_step(dev, n, max_norm):
+    ops = _ops()
+    p = torch.randn(n, generator=g(51))
+    m = torch.zeros(n)
+    v = torch.zeros(n)
+    pd, md, vd = p.to(dev), m.to(dev), v.to(dev)
+    ws = torch.empty(1024, device=dev)
+    gn = torch.zeros(1, device=dev)
+    num = torch.tensor([900.0], dtype=torch.float64, device=dev)
+    den = torch.tensor([1000.0], dtype=torch.float64, device=dev)
+    lr, b1, b2, eps = 1e-3, 0.9, 0.999, 1e-6
+    for step in range(1, 4):
+        grad = torch.randn(n, generator=g(60 + step)) * (10.0 if step == 2 else 0.01)
+        gref = grad.clone()
+        total = torch.linalg.vector_norm(gref)
+        if max_norm > 0:
+            O.clip_grad_norm_([gref], max_norm)
+        O.adam_step(p, gref, m, v, step, lr * 900.0 / 1000.0, b1, b2, eps)
+        ops.clip_adam_step(pd, grad.to(dev), md, vd, step, lr, b1, b2, eps, max_norm, num, den, gn, ws)
+        assert abs(gn.item() - total.item()) <= 1e-5 * max(1.0, total.item())
+        np.testing.assert_allclose(pd.cpu().numpy(), p.numpy(), atol=1e-6, rtol=1e-5)
+        np.testing.assert_allclose(md.cpu().numpy(), m.numpy(), atol=1e-7, rtol=1e-5)
+        np.testing.assert_allclose(vd.cpu().numpy(), v.numpy(), atol=1e-9, rtol=1e-5)
+
+
+def test_bad_arguments_raise(dev):
+    """Error behaviour: argument violations surface as Python exceptions carrying the library message."""
+    ops = _ops()
+    from sample_factory_b200._lib import SfbError
+
+    x = torch.zeros(4, 4, device=dev)
+    with pytest.raises(SfbError):
+        ops.heads_forward(x, x[0:1], x[0, :1], torch.zeros(40, 4, device=dev), torch.zeros(40, device=dev), x[:, 0], 4)
+    with pytest.raises(RuntimeError):
+        ops.normalize_obs(torch.zeros(4, 4), x, None, None)  # CPU tensor: there is no CPU path
