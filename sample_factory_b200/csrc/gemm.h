@@ -14,3 +14,9 @@ int tc_linear_backward(const float* dz, int64_t lddz, const float* x, int64_t ld
                        int K, int act_prev, float* dW, float* dx, int64_t lddx, int engine, float* ws, cudaStream_t st);
 
 }  // namespace sfb
+
+namespace sfb {
+// shared with the SIMT engine (gemm_simt.cu)
+int choose_splits(int64_t M, int N, int K);
+int splitk_reduce(const float* part, int splits, int64_t M, int N, float* C, int64_t ldc, cudaStream_t st);
+}  // namespace sfb

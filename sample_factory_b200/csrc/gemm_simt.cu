@@ -242,6 +242,16 @@ int gemm_simt(bool a_kcont, const float* A, int64_t lda, bool b_kcont, const flo
     return 0;
 }
 
+int splitk_reduce(const float* part, int splits, int64_t M, int N, float* C, int64_t ldc, cudaStream_t st) {
+    Epilogue none{0, 0, nullptr, nullptr, 0};
+    int64_t blocks = ceil_div(M * N, 256);
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    splitk_reduce_kernel<<<(unsigned)blocks, 256, 0, st>>>(part, splits, M, N, C, ldc, none);
+    SFB_LAUNCH_OK();
+    return 0;
+}
+
 constexpr int kColsumMaxGroups = 256;
 
 int colsum(const float* X, int64_t ldx, int64_t M, int N, float* out, float* ws, cudaStream_t st) {

@@ -1,16 +1,446 @@
-// tcgen05 / TMA GEMM engine -- placeholder until the tensor-core path lands (phase B).
+// tcgen05 / TMA GEMM engine for sm_100a (SFB200_GEMM_TC_3XTF32, SFB200_GEMM_TC_TF32).
+//
+//   C[m,n] = epilogue( sum_k A(m,k) * B(n,k) ),   fp32 in HBM, fp32 accumulate in TMEM.
+//
+// Precision: tcgen05 has no fp32 MMA. kind::tf32 keeps 10 mantissa bits, so a single pass is ~1e-3 relative -- not
+// parity grade.  The 3xTF32 mode splits every operand element in shared memory into  hi = a & ~0x1fff  (exactly
+// representable in tf32) and  lo = (a - hi) & ~0x1fff  and issues  hi*hi' + hi*lo' + lo*hi'  into the same TMEM
+// accumulator: each product is exact in fp32, the dropped lo*lo' term is 2^-22 relative, i.e. fp32-grade results.
+//
+// One 128 x BN output tile per CTA, 192 threads:
+//   warp 0      : TMA producer   (cp.async.bulk.tensor, 128B-swizzled boxes, mbarrier complete_tx)
+//   warp 1      : TMEM allocator + MMA issuer (one elected lane issues tcgen05.mma, tcgen05.commit frees the stage)
+//   warps 2..5  : per stage: split the raw fp32 tile in place (hi) + second buffer (lo), fence.proxy.async, arrive;
+//                 after the main loop: epilogue (tcgen05.ld accumulator -> bias/activation -> global)
+// Operands may be K-major ([rows, K], K contiguous) or MN-major ([K, rows], rows contiguous): the backward GEMMs
+// (dX = dZ.W, dW = dZ^T.X) read the activations in the layout the forward pass wrote them -- no transposed copies.
+// Split-K (grid.z) writes raw partial tiles to a workspace that the SIMT engine's fixed-order reduce kernel sums.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
 #include "common.cuh"
 #include "gemm.h"
 
 namespace sfb {
-int tc_linear_act_forward(const float*, int64_t, const float*, const float*, float*, int64_t, int64_t, int, int, int, int,
-                          cudaStream_t) {
-    return SFB_TC_UNSUPPORTED;
+
+constexpr int TBM = 128;        // tile rows  (UMMA M, cta_group::1)
+constexpr int TBK = 32;         // k per stage: 32 fp32 = 128 B = one swizzle row
+constexpr int UMMA_K = 8;       // tf32
+constexpr int TC_THREADS = 192;
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
-int tc_linear_backward(const float*, int64_t, const float*, int64_t, const float*, int64_t, int, int, int, float*, float*,
-                       int64_t, int, float*, cudaStream_t) {
-    return SFB_TC_UNSUPPORTED;
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra.uni WAIT_DONE;\n"
+        "bra.uni WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_result, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// D[tmem] (+)= A[smem desc] * B[smem desc], kind::tf32, issued by ONE thread
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive on an mbarrier when all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ------------------------------------------------------------------------------------------------ descriptors
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) |
+// version=1 [46,48) | layout SWIZZLE_128B=2 [61,64).
+//   K-major  tile [rows][32 fp32]: 128 B rows, 8-row swizzle atoms 1024 B apart          -> SBO = 1024, LBO unused (1)
+//   MN-major tile = boxes of [32 k][32 rows] (4096 B, k rows 128 B apart, 8-k groups 1024 B) -> LBO = 4096 (next 32
+//            rows), SBO = 1024 (next 8 k)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, bool mn_major) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
+    d |= (uint64_t)(mn_major ? (4096u >> 4) : 1u) << 16;
+    d |= (uint64_t)(1024u >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32=1 [4,6) | a/b_format TF32=2 [7,10)/[10,13) |
+// a_major [15] | b_major [16] | N>>3 [17,23) | M>>4 [24,29)
+__host__ __device__ constexpr uint32_t make_idesc(bool a_mn, bool b_mn, int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+struct TcEpilogue {
+    int mode;            // 0 plain, 1 act(acc + bias[n]), 2 acc * act'(aux[m,n])
+    int act;
+    const float* bias;
+    const float* aux;
+    int64_t ld_aux;
+};
+
+template <int BN, int STAGES>
+struct TcSmem {
+    // [stage][A hi | A lo | B hi | B lo]; every buffer is a multiple of 1024 B (swizzle-atom aligned)
+    static constexpr int A_BYTES = TBM * TBK * 4;
+    static constexpr int B_BYTES = BN * TBK * 4;
+    static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+    static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+// ------------------------------------------------------------------------------------------------ the kernel
+template <bool A_MN, bool B_MN, int BN, int STAGES, bool SPLIT3>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+               float* __restrict__ C, int64_t ldc, int64_t M, int N, int K, int k_chunk, TcEpilogue epi) {
+    using S = TcSmem<BN, STAGES>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES);
+    uint64_t* full = bars;                    // TMA bytes landed            (count 1 + tx)
+    uint64_t* conv = bars + STAGES;           // operands split & visible     (count 128)
+    uint64_t* empty = bars + 2 * STAGES;      // MMAs reading the stage done  (count 1, tcgen05.commit)
+    uint64_t* acc_full = bars + 3 * STAGES;   // accumulator complete         (count 1, tcgen05.commit)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t m0 = (int64_t)blockIdx.y * TBM;
+    const int n0 = blockIdx.x * BN;
+    const int k_begin = blockIdx.z * k_chunk;
+    const int k_end = (k_begin + k_chunk < K) ? k_begin + k_chunk : K;
+    const int num_kb = (k_end - k_begin + TBK - 1) / TBK;
+    if (gridDim.z > 1) C += (int64_t)blockIdx.z * M * ldc;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&conv[s], 128);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(acc_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, BN);   // BN fp32 accumulator columns (power of two >= 32)
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================================================== TMA producer
+        if (lane == 0) {
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (kb / STAGES) & 1;
+                mbar_wait(&empty[s], ph ^ 1);
+                uint8_t* st = smem + s * S::STAGE_BYTES;
+                mbar_expect_tx(&full[s], S::A_BYTES + S::B_BYTES);
+                const int k0 = k_begin + kb * TBK;
+                if (A_MN) {
+                    for (int j = 0; j < TBM / 32; ++j) tma_load_2d(st + j * 4096, &tmap_a, &full[s], (int)m0 + 32 * j, k0);
+                } else {
+                    tma_load_2d(st, &tmap_a, &full[s], k0, (int)m0);
+                }
+                uint8_t* sb = st + 2 * S::A_BYTES;
+                if (B_MN) {
+                    for (int j = 0; j < BN / 32; ++j) tma_load_2d(sb + j * 4096, &tmap_b, &full[s], n0 + 32 * j, k0);
+                } else {
+                    tma_load_2d(sb, &tmap_b, &full[s], k0, n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================== MMA issuer
+        constexpr uint32_t idesc = make_idesc(A_MN, B_MN, TBM, BN);
+        constexpr uint32_t A_KSTEP = A_MN ? (1024u >> 4) : (UMMA_K * 4u >> 4);   // descriptor start advance per k8
+        constexpr uint32_t B_KSTEP = B_MN ? (1024u >> 4) : (UMMA_K * 4u >> 4);
+        for (int kb = 0; kb < num_kb; ++kb) {
+            const int s = kb % STAGES;
+            const uint32_t ph = (kb / STAGES) & 1;
+            mbar_wait(&conv[s], ph);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t a_hi = smem_u32(smem + s * S::STAGE_BYTES);
+                const uint32_t a_lo = a_hi + S::A_BYTES;
+                const uint32_t b_hi = a_hi + 2 * S::A_BYTES;
+                const uint32_t b_lo = b_hi + S::B_BYTES;
+                const uint64_t da_hi = make_smem_desc(a_hi, A_MN), da_lo = make_smem_desc(a_lo, A_MN);
+                const uint64_t db_hi = make_smem_desc(b_hi, B_MN), db_lo = make_smem_desc(b_lo, B_MN);
+#pragma unroll
+                for (int k = 0; k < TBK / UMMA_K; ++k) {
+                    const uint64_t ao = (uint64_t)(k * A_KSTEP), bo = (uint64_t)(k * B_KSTEP);
+                    umma_tf32(tmem_base, da_hi + ao, db_hi + bo, idesc, (kb | k) != 0);
+                    if (SPLIT3) {
+                        umma_tf32(tmem_base, da_hi + ao, db_lo + bo, idesc, 1);
+                        umma_tf32(tmem_base, da_lo + ao, db_hi + bo, idesc, 1);
+                    }
+                }
+                umma_commit(&empty[s]);                       // stage reusable once these MMAs have read it
+                if (kb == num_kb - 1) umma_commit(acc_full);  // accumulator final
+            }
+            __syncwarp();
+        }
+    } else {
+        // ===================================================== operand split (per stage), then epilogue
+        const int ct = threadIdx.x - 64;   // 0..127
+        for (int kb = 0; kb < num_kb; ++kb) {
+            const int s = kb % STAGES;
+            const uint32_t ph = (kb / STAGES) & 1;
+            mbar_wait(&full[s], ph);
+            uint8_t* st = smem + s * S::STAGE_BYTES;
+            // the split is elementwise, so it is layout-agnostic: hi in place, lo at the same (swizzled) offset
+            auto split = [&](uint8_t* hi_buf, uint8_t* lo_buf, int bytes) {
+                uint4* h4 = reinterpret_cast<uint4*>(hi_buf);
+                uint4* l4 = reinterpret_cast<uint4*>(lo_buf);
+                for (int i = ct; i < bytes / 16; i += 128) {
+                    uint4 v = h4[i];
+                    uint4 h, l;
+                    h.x = v.x & 0xffffe000u; h.y = v.y & 0xffffe000u; h.z = v.z & 0xffffe000u; h.w = v.w & 0xffffe000u;
+                    l.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x)) & 0xffffe000u;
+                    l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y)) & 0xffffe000u;
+                    l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z)) & 0xffffe000u;
+                    l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w)) & 0xffffe000u;
+                    h4[i] = h;
+                    l4[i] = l;
+                }
+            };
+            if (SPLIT3) {
+                split(st, st + S::A_BYTES, S::A_BYTES);
+                split(st + 2 * S::A_BYTES, st + 2 * S::A_BYTES + S::B_BYTES, S::B_BYTES);
+            }
+            fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core (async proxy)
+            mbar_arrive(&conv[s]);
+        }
+
+        // ---- epilogue: TMEM -> registers -> global. warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32)
+        mbar_wait(acc_full, 0);
+        tc_fence_after();
+        const int lane_base = (warp & 3) * 32;
+        const int64_t m = m0 + lane_base + lane;
+        const bool do_epi = gridDim.z == 1;
+        const bool vec_ok = (ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15u) == 0);
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)c0, r);
+            if (m < M) {
+                float* dst = C + m * ldc + n0 + c0;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    float o[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int n = n0 + c0 + j + q;
+                        float v = __uint_as_float(r[j + q]);
+                        if (do_epi && n < N) {
+                            if (epi.mode == 1) v = act_fwd(v + (epi.bias ? epi.bias[n] : 0.f), epi.act);
+                            else if (epi.mode == 2) v = v * act_bwd_from_out(epi.aux[m * epi.ld_aux + n], epi.act);
+                        }
+                        o[q] = v;
+                    }
+                    const int n = n0 + c0 + j;
+                    if (vec_ok && n + 3 < N) *reinterpret_cast<float4*>(dst + j) = make_float4(o[0], o[1], o[2], o[3]);
+                    else {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            if (n + q < N) dst[j + q] = o[q];
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, BN);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+static int g_tc_state = 0;   // 0 unknown, 1 ok, -1 unavailable
+
+static bool tc_init() {
+    if (g_tc_state != 0) return g_tc_state > 0;
+    g_tc_state = -1;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
+        qres != cudaDriverEntryPointSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    int dev = 0, major = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess ||
+        major != 10) {
+        cudaGetLastError();
+        return false;
+    }
+    g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+    g_tc_state = 1;
+    return true;
+}
+
+// 2-D fp32 tensor map, 128B swizzle. dim0 = contiguous dimension.
+static bool make_tmap(CUtensorMap* out, const float* base, uint64_t dim0, uint64_t dim1, uint64_t stride1_elems,
+                      uint32_t box0, uint32_t box1) {
+    cuuint64_t gdim[2] = {dim0, dim1};
+    cuuint64_t gstride[1] = {stride1_elems * sizeof(float)};
+    cuuint32_t box[2] = {box0, box1};
+    cuuint32_t estride[2] = {1, 1};
+    CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estride,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+static bool operand_ok(const float* p, int64_t ld) {
+    return ((reinterpret_cast<uintptr_t>(p) & 15u) == 0) && (ld % 4 == 0) && ld > 0;
+}
+
+template <bool A_MN, bool B_MN, int BN, bool SPLIT3>
+static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, float* C, int64_t ldc, int64_t M, int N, int K,
+                     int k_chunk, int splits, const TcEpilogue& epi, cudaStream_t st) {
+    constexpr int STAGES = (BN == 128) ? 3 : 4;
+    using S = TcSmem<BN, STAGES>;
+    auto kern = gemm_tc_kernel<A_MN, B_MN, BN, STAGES, SPLIT3>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        SFB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+        attr_set = true;
+    }
+    dim3 grid((unsigned)ceil_div(N, BN), (unsigned)ceil_div(M, TBM), (unsigned)splits);
+    kern<<<grid, TC_THREADS, S::TOTAL, st>>>(ta, tb, C, ldc, M, N, K, k_chunk, epi);
+    SFB_LAUNCH_OK();
+    return 0;
+}
+
+// C[M,N] = epi( sum_k A(m,k) B(n,k) ). Returns SFB_TC_UNSUPPORTED when the shape/alignment is not covered.
+static int gemm_tc(bool a_mn, const float* A, int64_t lda, bool b_mn, const float* B, int64_t ldb, float* C, int64_t ldc,
+                   int64_t M, int N, int K, int splits, const TcEpilogue& epi, float* ws, bool split3, cudaStream_t st) {
+    if (!tc_init()) return SFB_TC_UNSUPPORTED;
+    if (!operand_ok(A, lda) || !operand_ok(B, ldb) || M < 1 || N < 8 || K < 8) return SFB_TC_UNSUPPORTED;
+    if (M > 0x7fffffff || ceil_div(M, TBM) > 65535) return SFB_TC_UNSUPPORTED;
+    const int BN = (N >= 128) ? 128 : 64;
+    CUtensorMap ta, tb;
+    bool ok;
+    if (a_mn) ok = make_tmap(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 32, TBK);
+    else ok = make_tmap(&ta, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, TBK, TBM);
+    if (b_mn) ok = ok && make_tmap(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 32, TBK);
+    else ok = ok && make_tmap(&tb, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, TBK, (uint32_t)BN);
+    if (!ok) return SFB_TC_UNSUPPORTED;
+
+    int k_chunk = K;
+    if (splits > 1) {
+        k_chunk = (int)(ceil_div(ceil_div(K, splits), TBK) * TBK);
+        splits = (int)ceil_div(K, k_chunk);
+    }
+    if (splits > 1 && !ws) return SFB_TC_UNSUPPORTED;
+    float* out = splits > 1 ? ws : C;
+    const int64_t ld_out = splits > 1 ? N : ldc;
+
+#define SFB_TC(AM, BM_, BNv)                                                                                           \
+    (split3 ? launch_tc<AM, BM_, BNv, true>(ta, tb, out, ld_out, M, N, K, k_chunk, splits, epi, st)                   \
+            : launch_tc<AM, BM_, BNv, false>(ta, tb, out, ld_out, M, N, K, k_chunk, splits, epi, st))
+    int rc;
+    if (BN == 128) {
+        if (!a_mn && !b_mn) rc = SFB_TC(false, false, 128);
+        else if (!a_mn && b_mn) rc = SFB_TC(false, true, 128);
+        else if (a_mn && b_mn) rc = SFB_TC(true, true, 128);
+        else return SFB_TC_UNSUPPORTED;
+    } else {
+        if (!a_mn && !b_mn) rc = SFB_TC(false, false, 64);
+        else if (!a_mn && b_mn) rc = SFB_TC(false, true, 64);
+        else if (a_mn && b_mn) rc = SFB_TC(true, true, 64);
+        else return SFB_TC_UNSUPPORTED;
+    }
+#undef SFB_TC
+    if (rc) return rc;
+    if (splits > 1) return splitk_reduce(ws, splits, M, N, C, ldc, st);
+    return 0;
+}
+
+int tc_linear_act_forward(const float* x, int64_t ldx, const float* W, const float* b, float* y, int64_t ldy, int64_t M,
+                          int N, int K, int act, int engine, cudaStream_t st) {
+    TcEpilogue epi{1, act, b, nullptr, 0};
+    return gemm_tc(false, x, ldx, false, W, K, y, ldy, M, N, K, 1, epi, nullptr, engine == SFB200_GEMM_TC_3XTF32, st);
+}
+
+int tc_linear_backward(const float* dz, int64_t lddz, const float* x, int64_t ldx, const float* W, int64_t M, int N, int K,
+                       int act_prev, float* dW, float* dx, int64_t lddx, int engine, float* ws, cudaStream_t st) {
+    const bool split3 = engine == SFB200_GEMM_TC_3XTF32;
+    // dW[n,k] = sum_m dz[m,n] x[m,k]: both operands are stored with the reduced index m as the row -> MN-major
+    TcEpilogue none{0, 0, nullptr, nullptr, 0};
+    const int splits = choose_splits(N, K, (int)M);
+    int rc = gemm_tc(true, dz, lddz, true, x, ldx, dW, K, N, K, (int)M, splits, none, ws, split3, st);
+    if (rc) return rc;
+    if (dx) {
+        // dx[m,k] = (sum_n dz[m,n] W[n,k]) * act_prev'(x[m,k]): A = dz K-major, B(k, n) = W[n,k] MN-major
+        TcEpilogue e{act_prev == SFB200_ACT_NONE ? 0 : 2, act_prev, nullptr, x, ldx};
+        rc = gemm_tc(false, dz, lddz, true, W, K, dx, lddx, M, K, N, 1, e, nullptr, split3, st);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
 }  // namespace sfb
 
-extern "C" int sfb200_tc_available(void) { return 0; }
+extern "C" int sfb200_tc_available(void) { return sfb::tc_init() ? 1 : 0; }

@@ -27,7 +27,8 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g,
 
 __global__ void __launch_bounds__(256) clip_adam_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                         float* __restrict__ m, float* __restrict__ v, int64_t n,
-                                                        double lr, double bc1, float bc2_sqrt, float beta1, float beta2,
+                                                        double lr, double bc1, float bc2_sqrt, float omb1, float beta2,
+                                                        float omb2,
                                                         float eps, float max_norm, const double* __restrict__ part,
                                                         int nparts, const double* __restrict__ lr_num,
                                                         const double* __restrict__ lr_den,
@@ -52,7 +53,6 @@ __global__ void __launch_bounds__(256) clip_adam_kernel(float* __restrict__ p, c
     }
     __syncthreads();
     const float coef = s_coef, step_size = s_step;
-    const float omb1 = 1.f - beta1, omb2 = 1.f - beta2;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const float gi = g[i] * coef;
         float mi = m[i], vi = v[i];
@@ -87,8 +87,8 @@ int sfb200_clip_adam_step(float* p, float* g, float* m, float* v, int64_t n, int
     int64_t blocks = ceil_div(n, 256 * 2);
     const int64_t cap = (int64_t)sm_count() * 4;
     if (blocks > cap) blocks = cap;
-    clip_adam_kernel<<<(unsigned)blocks, 256, 0, st>>>(p, g, m, v, n, lr, bc1, (float)sqrt(bc2), (float)beta1,
-                                                       (float)beta2, (float)eps, (float)max_grad_norm, part, (int)nb,
+    clip_adam_kernel<<<(unsigned)blocks, 256, 0, st>>>(p, g, m, v, n, lr, bc1, (float)sqrt(bc2), (float)(1.0 - beta1),
+                                                       (float)beta2, (float)(1.0 - beta2), (float)eps, (float)max_grad_norm, part, (int)nb,
                                                        lr_scale_num, lr_scale_den, grad_norm_out);
     SFB_LAUNCH_OK();
     return 0;

@@ -114,6 +114,26 @@ def test_linear_act_forward(dev, M, N, K, act, engine):
     np.testing.assert_allclose(out.cpu().numpy(), ref.numpy(), atol=TOL, rtol=1e-5)
 
 
+def test_tc_engine_precision_classes(dev):
+    """tcgen05 engine: the 3xTF32 split must be fp32-grade (same error class as the exact-fp32 CUDA-core engine),
+    the single-pass TF32 mode must be visibly coarser (proves the tensor-core path really ran and the split matters)."""
+    ops = _ops()
+    if not ops.tc_available():
+        pytest.skip("tcgen05 engine not available")
+    M, N, K = 2048, 512, 512
+    x = torch.randn(M, K, generator=g(70))
+    W = torch.randn(N, K, generator=g(71)) / math.sqrt(K)
+    b = torch.zeros(N)
+    ref = torch.nn.functional.linear(x.double(), W.double()).float()
+    errs = {}
+    for name in ("simt", "3xtf32", "tf32"):
+        out = torch.empty(M, N, device=dev)
+        ops.linear_act_forward(x.to(dev), W.to(dev), b.to(dev), out, ops.ACT["none"], ops.ENGINES[name])
+        errs[name] = (out.cpu() - ref).abs().max().item()
+    assert errs["simt"] < 1e-5 and errs["3xtf32"] < 1e-5, errs
+    assert errs["tf32"] > 20 * errs["3xtf32"] and errs["tf32"] < 2e-2, errs
+
+
 def test_linear_forward_strided_input(dev):
     """The learner feeds obs[:, T] rows in place: x row stride != K."""
     ops = _ops()
