@@ -4,8 +4,9 @@
 //
 // Precision: tcgen05 has no fp32 MMA. kind::tf32 keeps 10 mantissa bits, so a single pass is ~1e-3 relative -- not
 // parity grade.  The 3xTF32 mode splits every operand element in shared memory into  hi = a & ~0x1fff  (exactly
-// representable in tf32) and  lo = (a - hi) & ~0x1fff  and issues  hi*hi' + hi*lo' + lo*hi'  into the same TMEM
-// accumulator: each product is exact in fp32, the dropped lo*lo' term is 2^-22 relative, i.e. fp32-grade results.
+// representable in tf32) and  lo = (a - hi) & ~0x1fff  and issues  hi*hi'  into one TMEM accumulator and
+// hi*lo' + lo*hi'  into a second one (summed in the epilogue): each product is exact in fp32, the dropped lo*lo' term is
+// 2^-22 relative, i.e. fp32-grade results.
 //
 // One 128 x BN output tile per CTA, 192 threads:
 //   warp 0      : TMA producer   (cp.async.bulk.tensor, 128B-swizzled boxes, mbarrier complete_tx)
@@ -106,17 +107,20 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
 
 // ------------------------------------------------------------------------------------------------ descriptors
 // Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) |
-// version=1 [46,48) | layout SWIZZLE_128B=2 [61,64).
-//   K-major  tile [rows][32 fp32]: 128 B rows, 8-row swizzle atoms 1024 B apart          -> SBO = 1024, LBO unused (1)
-//   MN-major tile = boxes of [32 k][32 rows] (4096 B, k rows 128 B apart, 8-k groups 1024 B) -> LBO = 4096 (next 32
-//            rows), SBO = 1024 (next 8 k)
+// version=1 [46,48) | layout type [61,64).
+//   K-major  tile [rows][32 fp32], SWIZZLE_128B (type 2, 16 B chunks XOR row%8): 128 B rows, 8-row atoms 1024 B apart
+//            -> SBO = 1024, LBO unused (1)
+//   MN-major tile = boxes of [32 k][32 rows] (4096 B each, k rows 128 B apart).  For 32-bit MN-major operands the only
+//            legal layout is SWIZZLE_128B_BASE32B (type 1: 32 B chunks XOR k%4, atom = 4 k-rows = 512 B; CUTLASS
+//            sm100_common.inl:92 "for mn-major tf32 operands, SW128_32B is the only available smem layout"), written by
+//            TMA with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B  -> LBO = 4096 (next 32 rows), SBO = 512 (next 4 k)
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, bool mn_major) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
     d |= (uint64_t)(mn_major ? (4096u >> 4) : 1u) << 16;
-    d |= (uint64_t)(1024u >> 4) << 32;
+    d |= (uint64_t)((mn_major ? 512u : 1024u) >> 4) << 32;
     d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
+    d |= (uint64_t)(mn_major ? 1 : 2) << 61;
     return d;
 }
 // Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32=1 [4,6) | a/b_format TF32=2 [7,10)/[10,13) |
@@ -177,7 +181,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         mbar_init(acc_full, 1);
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, BN);   // BN fp32 accumulator columns (power of two >= 32)
+    // accumulators: columns [0,BN) = hi*hi', columns [BN,2BN) = the two cross terms.  The tensor core accumulates with
+    // truncation (measured: a shared accumulator gives a bias that grows with the number of MMAs); keeping the ~2^-11
+    // smaller cross terms in their own accumulator removes 2/3 of the roundings applied to the large partial sums.
+    constexpr uint32_t TMEM_COLS = SPLIT3 ? 2 * BN : BN;
+    if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -228,8 +236,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     const uint64_t ao = (uint64_t)(k * A_KSTEP), bo = (uint64_t)(k * B_KSTEP);
                     umma_tf32(tmem_base, da_hi + ao, db_hi + bo, idesc, (kb | k) != 0);
                     if (SPLIT3) {
-                        umma_tf32(tmem_base, da_hi + ao, db_lo + bo, idesc, 1);
-                        umma_tf32(tmem_base, da_lo + ao, db_hi + bo, idesc, 1);
+                        umma_tf32(tmem_base + BN, da_hi + ao, db_lo + bo, idesc, (kb | k) != 0);
+                        umma_tf32(tmem_base + BN, da_lo + ao, db_hi + bo, idesc, 1);
                     }
                 }
                 umma_commit(&empty[s]);                       // stage reusable once these MMAs have read it
@@ -280,6 +288,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         for (int c0 = 0; c0 < BN; c0 += 32) {
             uint32_t r[32];
             tmem_ld_32x32b_x32(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)c0, r);
+            if (SPLIT3) {
+                uint32_t r2[32];
+                tmem_ld_32x32b_x32(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(BN + c0), r2);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+            }
             if (m < M) {
                 float* dst = C + m * ldc + n0 + c0;
 #pragma unroll
@@ -310,7 +324,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, BN);
+        tmem_dealloc(tmem_base, TMEM_COLS);
     }
 }
 
@@ -341,13 +355,15 @@ static bool tc_init() {
 
 // 2-D fp32 tensor map, 128B swizzle. dim0 = contiguous dimension.
 static bool make_tmap(CUtensorMap* out, const float* base, uint64_t dim0, uint64_t dim1, uint64_t stride1_elems,
-                      uint32_t box0, uint32_t box1) {
+                      uint32_t box0, uint32_t box1, bool mn_major) {
     cuuint64_t gdim[2] = {dim0, dim1};
     cuuint64_t gstride[1] = {stride1_elems * sizeof(float)};
     cuuint32_t box[2] = {box0, box1};
     cuuint32_t estride[2] = {1, 1};
     CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estride,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
 }
@@ -382,10 +398,10 @@ static int gemm_tc(bool a_mn, const float* A, int64_t lda, bool b_mn, const floa
     const int BN = (N >= 128) ? 128 : 64;
     CUtensorMap ta, tb;
     bool ok;
-    if (a_mn) ok = make_tmap(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 32, TBK);
-    else ok = make_tmap(&ta, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, TBK, TBM);
-    if (b_mn) ok = ok && make_tmap(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 32, TBK);
-    else ok = ok && make_tmap(&tb, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, TBK, (uint32_t)BN);
+    if (a_mn) ok = make_tmap(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 32, TBK, true);
+    else ok = make_tmap(&ta, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, TBK, TBM, false);
+    if (b_mn) ok = ok && make_tmap(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 32, TBK, true);
+    else ok = ok && make_tmap(&tb, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, TBK, (uint32_t)BN, false);
     if (!ok) return SFB_TC_UNSUPPORTED;
 
     int k_chunk = K;

@@ -189,6 +189,91 @@ __global__ void __launch_bounds__(256) heads_backward_kernel(
     if (tid < n_out) my_part[(int64_t)(A + 2) * H + tid] = acc_g;
 }
 
+// Vectorised variant (H % 4 == 0, H/4 divides 256): a thread owns 4 consecutive columns (128-bit loads/stores) and
+// every RPB-th row of the group; row-lane partials are combined through shared memory at the end.
+template <int AP>
+__global__ void __launch_bounds__(256) heads_backward_vec4_kernel(
+    const float* __restrict__ h, int64_t ldh, int64_t rows, int H, int A, const float* __restrict__ Wv,
+    const float* __restrict__ Wa, const float* __restrict__ dlogits, const float* __restrict__ dvalues, int act,
+    float* __restrict__ dz, int64_t lddz, float* __restrict__ part, int64_t rows_per_group) {
+    __shared__ float g_s[kHbTile][AP];
+    extern __shared__ float red_s[];   // [(A+2)][H] cross-row-lane reduction
+    const int n_out = A + 1;
+    const int tid = threadIdx.x;
+    const int TPR = H >> 2, RPB = 256 / TPR;
+    const int c4 = tid % TPR, rl = tid / TPR;
+    const int j = c4 << 2;
+    const int64_t r_begin = blockIdx.x * rows_per_group;
+    const int64_t r_end = (r_begin + rows_per_group < rows) ? r_begin + rows_per_group : rows;
+    const int64_t part_stride = (int64_t)(A + 2) * H + n_out;
+    float* my_part = part + blockIdx.x * part_stride;
+
+    float4 w[AP], accw[AP];
+#pragma unroll
+    for (int a = 0; a < AP; ++a) {
+        accw[a] = make_float4(0.f, 0.f, 0.f, 0.f);
+        w[a] = (a < n_out) ? *reinterpret_cast<const float4*>((a == 0 ? Wv : Wa + (int64_t)(a - 1) * H) + j)
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float4 acc_db = make_float4(0.f, 0.f, 0.f, 0.f);
+    float acc_g = 0.f;
+    for (int64_t b0 = r_begin; b0 < r_end; b0 += kHbTile) {
+        const int nb = (int)((r_end - b0 < kHbTile) ? (r_end - b0) : kHbTile);
+        __syncthreads();
+        for (int i = tid; i < kHbTile * n_out; i += 256) {
+            const int bb = i / n_out, a = i - bb * n_out;
+            float v = 0.f;
+            if (bb < nb) v = (a == 0) ? dvalues[b0 + bb] : dlogits[(b0 + bb) * A + (a - 1)];
+            g_s[bb][a] = v;
+        }
+        __syncthreads();
+        if (tid < n_out)
+            for (int bb = 0; bb < nb; ++bb) acc_g += g_s[bb][tid];
+#pragma unroll 4
+        for (int bb = rl; bb < nb; bb += RPB) {
+            const float4 hv = *reinterpret_cast<const float4*>(h + (b0 + bb) * ldh + j);
+            float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int a = 0; a < AP; ++a) {
+                if (a < n_out) {
+                    const float g = g_s[bb][a];
+                    s.x = fmaf(g, w[a].x, s.x); s.y = fmaf(g, w[a].y, s.y);
+                    s.z = fmaf(g, w[a].z, s.z); s.w = fmaf(g, w[a].w, s.w);
+                    accw[a].x = fmaf(g, hv.x, accw[a].x); accw[a].y = fmaf(g, hv.y, accw[a].y);
+                    accw[a].z = fmaf(g, hv.z, accw[a].z); accw[a].w = fmaf(g, hv.w, accw[a].w);
+                }
+            }
+            float4 d;
+            d.x = s.x * act_bwd_from_out(hv.x, act); d.y = s.y * act_bwd_from_out(hv.y, act);
+            d.z = s.z * act_bwd_from_out(hv.z, act); d.w = s.w * act_bwd_from_out(hv.w, act);
+            *reinterpret_cast<float4*>(dz + (b0 + bb) * lddz + j) = d;
+            acc_db.x += d.x; acc_db.y += d.y; acc_db.z += d.z; acc_db.w += d.w;
+        }
+    }
+    // combine the RPB row lanes (fixed order -> deterministic)
+    for (int r = 0; r < RPB; ++r) {
+        __syncthreads();
+        if (rl == r) {
+#pragma unroll
+            for (int a = 0; a < AP; ++a) {
+                if (a < n_out) {
+                    float4* dst = reinterpret_cast<float4*>(red_s + a * H + j);
+                    float4 v = accw[a];
+                    if (r > 0) { const float4 o = *dst; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+                    *dst = v;
+                }
+            }
+            float4* dst = reinterpret_cast<float4*>(red_s + n_out * H + j);
+            float4 v = acc_db;
+            if (r > 0) { const float4 o = *dst; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+            *dst = v;
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < (A + 2) * H; i += 256) my_part[i] = red_s[i];
+    if (tid < n_out) my_part[(int64_t)(A + 2) * H + tid] = acc_g;
+}
+
 __global__ void heads_backward_reduce_kernel(const float* __restrict__ part, int groups, int H, int A,
                                              float* __restrict__ dWv, float* __restrict__ dbv, float* __restrict__ dWa,
                                              float* __restrict__ dba, float* __restrict__ db_prev) {
@@ -273,7 +358,14 @@ int sfb200_heads_backward(const float* h, int64_t ldh, int64_t rows, int H, int 
     rpg = ceil_div(rpg, kHbTile) * kHbTile;
     groups = ceil_div(rows, rpg);
     float* part = (float*)workspace;
-    if (A + 1 <= 9)
+    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+    const size_t red_bytes = (size_t)(A + 2) * H * sizeof(float);
+    const bool vec4 = (H % 4 == 0) && (H / 4 <= 256) && (256 % (H / 4) == 0) && (ldh % 4 == 0) && (lddz % 4 == 0) &&
+                      al16(h) && al16(dz) && al16(Wv) && al16(Wa) && red_bytes <= 40 * 1024 && A + 1 <= 9;
+    if (vec4)
+        heads_backward_vec4_kernel<9><<<(unsigned)groups, 256, red_bytes, st>>>(h, ldh, rows, H, A, Wv, Wa, dlogits,
+                                                                               dvalues, act, dz, lddz, part, rpg);
+    else if (A + 1 <= 9)
         heads_backward_kernel<9><<<(unsigned)groups, 256, 0, st>>>(h, ldh, rows, H, A, Wv, Wa, dlogits, dvalues, act, dz,
                                                                    lddz, part, rpg);
     else if (A + 1 <= 17)

@@ -130,7 +130,9 @@ def test_tc_engine_precision_classes(dev):
         out = torch.empty(M, N, device=dev)
         ops.linear_act_forward(x.to(dev), W.to(dev), b.to(dev), out, ops.ACT["none"], ops.ENGINES[name])
         errs[name] = (out.cpu() - ref).abs().max().item()
-    assert errs["simt"] < 1e-5 and errs["3xtf32"] < 1e-5, errs
+    print("max abs error vs fp64 (|out| up to ~4.5):", errs)
+    scale = ref.abs().max().item()
+    assert errs["simt"] < 1e-5 and errs["3xtf32"] < 3e-6 * scale, errs   # fp32-grade: <= ~25 ulp of the largest output
     assert errs["tf32"] > 20 * errs["3xtf32"] and errs["tf32"] < 2e-2, errs
 
 

@@ -1,7 +1,7 @@
 #!/bin/bash
 # round-1 GPU session 2: validate the tcgen05 engine, then full tests, bench (both engines), ncu launch list
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_gpu_kernels.py -q -k "tc_engine or 3xtf32" --timeout 120 --timeout-method=thread -p no:cacheprovider > gpurun_out/pytest_tc.log 2>&1
+timeout 300 python -m pytest tests/test_gpu_kernels.py -q -k "tc_engine or 3xtf32 or heads_backward" -s --timeout 120 --timeout-method=thread -p no:cacheprovider > gpurun_out/pytest_tc.log 2>&1
 TC_RC=$?
 echo "tc tests rc=$TC_RC"; tail -15 gpurun_out/pytest_tc.log
 if [ $TC_RC -eq 0 ]; then
