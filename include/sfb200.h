@@ -133,8 +133,9 @@ int sfb200_copy_rows(const float* src, int64_t src_stride, float* dst, int64_t d
 /* Synthetic "tape" vector env (ours, not the reference's; contract = algo/utils/make_env.py:147-237 step()):
  * step = step_counter ? *step_counter : step_host.  reward = action/num_actions; terminated = ((step*7 + env*13) %
  * term_period == 0); truncated = ((step + env) % trunc_period == 0) & !terminated, env = env_index_offset + i;
- * obs_out = tape[(step+1) % tape_len] (tape: [tape_len, n_envs, dim]).  If step_counter != NULL it is incremented
- * afterwards (device-side counter keeps the call replayable inside a CUDA graph). */
+ * obs_out = tape[(step+1) % tape_len] (tape: [tape_len, n_envs, dim]).  step_counter, if not NULL, points to int64[2]
+ * {step, ticket}: the last thread block to finish advances `step` (device-side counter keeps the call replayable
+ * inside a CUDA graph without an extra launch). */
 int sfb200_tape_env_step(const int32_t* actions, int64_t n_envs, int num_actions, int64_t env_index_offset,
                          int term_period, int trunc_period, int64_t* step_counter, int64_t step_host,
                          const float* tape, int64_t tape_len, int dim, float* obs_out, float* rew,

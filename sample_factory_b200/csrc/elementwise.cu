@@ -34,8 +34,18 @@ __global__ void __launch_bounds__(256) normalize_kernel(const float* __restrict_
                                                         int64_t ldy, float* __restrict__ raw_copy, int64_t ld_copy,
                                                         int64_t rows, int dim, const double* __restrict__ mean,
                                                         const double* __restrict__ var, float sub, float inv_scale,
-                                                        int do_sub, int do_scale, float eps, float clip) {
+                                                        int do_sub, int do_scale, float eps, float clip,
+                                                        const float* __restrict__ rnn_src, int rnn_dim,
+                                                        float* __restrict__ rnn_dst, int64_t rnn_dst_stride,
+                                                        int64_t rnn_rows) {
     const bool do_rms = mean != nullptr;
+    if (rnn_src) {   // sampler pre-step: traj.rnn_states[:, t] <- rnn (tiny; folded in to save a launch)
+        const int64_t tot = rnn_rows * rnn_dim;
+        for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < tot; i += (int64_t)gridDim.x * blockDim.x) {
+            const int64_t r = i / rnn_dim;
+            rnn_dst[r * rnn_dst_stride + (i - r * rnn_dim)] = rnn_src[i];
+        }
+    }
     if (VEC4) {
         const int dim4 = dim >> 2;
         const int64_t total = rows * (int64_t)dim4;
@@ -76,7 +86,8 @@ static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 static int launch_normalize(const float* x, int64_t ldx, float* y, int64_t ldy, float* raw_copy, int64_t ld_copy,
                             int64_t rows, int dim, const double* mean, const double* var, float sub_mean,
-                            float inv_scale, float eps, float clip, cudaStream_t st) {
+                            float inv_scale, float eps, float clip, cudaStream_t st, const float* rnn_src = nullptr,
+                            int rnn_dim = 0, float* rnn_dst = nullptr, int64_t rnn_dst_stride = 0) {
     if (rows == 0 || dim == 0) return 0;
     const int do_sub = fabsf(sub_mean) > 1e-8f;
     const int do_scale = fabsf(inv_scale - 1.0f) > 1e-8f;
@@ -88,10 +99,12 @@ static int launch_normalize(const float* x, int64_t ldx, float* y, int64_t ldy, 
     if (blocks > cap) blocks = cap;
     if (vec)
         normalize_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(x, ldx, y, ldy, raw_copy, ld_copy, rows, dim, mean, var,
-                                                                 sub_mean, inv_scale, do_sub, do_scale, eps, clip);
+                                                                 sub_mean, inv_scale, do_sub, do_scale, eps, clip, rnn_src,
+                                                                 rnn_dim, rnn_dst, rnn_dst_stride, rows);
     else
         normalize_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(x, ldx, y, ldy, raw_copy, ld_copy, rows, dim, mean,
-                                                                  var, sub_mean, inv_scale, do_sub, do_scale, eps, clip);
+                                                                  var, sub_mean, inv_scale, do_sub, do_scale, eps, clip, rnn_src,
+                                                                  rnn_dim, rnn_dst, rnn_dst_stride, rows);
     SFB_LAUNCH_OK();
     return 0;
 }
@@ -182,8 +195,19 @@ __global__ void __launch_bounds__(256) tape_env_kernel(const int32_t* __restrict
             for (int64_t i = tid; i < total; i += nthreads) obs_out[i] = src[i];
         }
     }
+    if (step_counter) {
+        // every block has read `step` before taking its ticket, so the last ticket holder may advance the counter
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            unsigned long long* ticket = reinterpret_cast<unsigned long long*>(const_cast<int64_t*>(step_counter) + 1);
+            if (atomicAdd(ticket, 1ull) == (unsigned long long)gridDim.x - 1ull) {
+                *ticket = 0ull;
+                const_cast<int64_t*>(step_counter)[0] = step + 1;
+            }
+        }
+    }
 }
-__global__ void counter_inc_kernel(int64_t* c) { *c += 1; }
 
 // ---- valids ----------------------------------------------------------------------------------------------------------
 __global__ void valids_kernel(const int32_t* __restrict__ pid, const float* __restrict__ pver, int64_t n_traj, int T,
@@ -241,15 +265,9 @@ int sfb200_sampler_pre_step(const float* obs, int64_t n_envs, int dim, float* tr
                             float clip, void* stream) {
     SFB_CHECK_ARG(obs && traj_obs_t && n_envs >= 0 && dim > 0, "sampler_pre_step: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
-    int rc = launch_normalize(obs, dim, x_norm, dim, traj_obs_t, traj_obs_stride, n_envs, dim, mean, var, sub_mean,
-                              inv_scale, eps, clip, st);
-    if (rc) return rc;
-    if (rnn && traj_rnn_t && rnn_dim > 0) {
-        copy_rows_kernel<<<grid_for(n_envs * rnn_dim), 256, 0, st>>>(rnn, rnn_dim, traj_rnn_t, traj_rnn_stride, n_envs,
-                                                                     rnn_dim);
-        SFB_LAUNCH_OK();
-    }
-    return 0;
+    const bool with_rnn = rnn && traj_rnn_t && rnn_dim > 0;
+    return launch_normalize(obs, dim, x_norm, dim, traj_obs_t, traj_obs_stride, n_envs, dim, mean, var, sub_mean,
+                            inv_scale, eps, clip, st, with_rnn ? rnn : nullptr, rnn_dim, traj_rnn_t, traj_rnn_stride);
 }
 
 int sfb200_copy_rows(const float* src, int64_t src_stride, float* dst, int64_t dst_stride, int64_t rows, int dim,
@@ -295,10 +313,6 @@ int sfb200_tape_env_step(const int32_t* actions, int64_t n_envs, int num_actions
                                        step_counter, step_host, tape, tape_len, dim, obs_out, rew, terminated,
                                        truncated);
     SFB_LAUNCH_OK();
-    if (step_counter) {
-        counter_inc_kernel<<<1, 1, 0, st>>>(step_counter);
-        SFB_LAUNCH_OK();
-    }
     return 0;
 }
 

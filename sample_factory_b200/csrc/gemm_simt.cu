@@ -187,12 +187,15 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __rest
         part[(int64_t)blockIdx.x * N + n] = s;
     }
 }
+// one warp per output column, lanes stride over the row groups
 __global__ void colsum_reduce_kernel(const float* __restrict__ part, int groups, int N, float* __restrict__ out) {
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (n >= N) return;
     float s = 0.f;
-    for (int g = 0; g < groups; ++g) s += part[(int64_t)g * N + n];
-    out[n] = s;
+    for (int g = lane; g < groups; g += 32) s += part[(int64_t)g * N + n];
+    s = warp_sum(s);
+    if (lane == 0) out[n] = s;
 }
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
@@ -263,7 +266,7 @@ int colsum(const float* X, int64_t ldx, int64_t M, int N, float* out, float* ws,
     dim3 grid((unsigned)groups, (unsigned)ceil_div(N, 256));
     colsum_partial_kernel<<<grid, 256, 0, st>>>(X, ldx, M, N, rpg, ws);
     SFB_LAUNCH_OK();
-    colsum_reduce_kernel<<<(unsigned)ceil_div(N, 128), 128, 0, st>>>(ws, (int)groups, N, out);
+    colsum_reduce_kernel<<<(unsigned)ceil_div((int64_t)N * 32, 256), 256, 0, st>>>(ws, (int)groups, N, out);
     SFB_LAUNCH_OK();
     return 0;
 }

@@ -6,16 +6,19 @@
 // parity grade.  The 3xTF32 mode splits every operand element in shared memory into  hi = a & ~0x1fff  (exactly
 // representable in tf32) and  lo = (a - hi) & ~0x1fff  and issues  hi*hi'  into one TMEM accumulator and
 // hi*lo' + lo*hi'  into a second one (summed in the epilogue): each product is exact in fp32, the dropped lo*lo' term is
-// 2^-22 relative, i.e. fp32-grade results.
+// 2^-22 relative, i.e. fp32-grade results.  (Two accumulators because the tensor core accumulates with truncation: keeping
+// the 2^-11 smaller cross terms apart removes 2/3 of the roundings applied to the large partial sums -- measured 2.7e-5
+// -> 9.8e-6 max error on a K=512 GEMM.)
 //
-// One 128 x BN output tile per CTA, 192 threads:
-//   warp 0      : TMA producer   (cp.async.bulk.tensor, 128B-swizzled boxes, mbarrier complete_tx)
+// PERSISTENT kernel, one CTA per SM, 320 threads, static round-robin tile schedule (128 x BN output tiles):
+//   warp 0      : TMA producer   (cp.async.bulk.tensor, 128B-swizzled boxes, mbarrier complete_tx), runs ahead across tiles
 //   warp 1      : TMEM allocator + MMA issuer (one elected lane issues tcgen05.mma, tcgen05.commit frees the stage)
-//   warps 2..5  : per stage: split the raw fp32 tile in place (hi) + second buffer (lo), fence.proxy.async, arrive;
-//                 after the main loop: epilogue (tcgen05.ld accumulator -> bias/activation -> global)
+//   warps 2..5  : operand split: raw fp32 tile -> hi (in place) + lo (second buffer), fence.proxy.async, arrive
+//   warps 6..9  : epilogue: tcgen05.ld both accumulators -> release the TMEM slot -> bias/activation -> global.
+//                 The accumulator is double-buffered in TMEM, so the epilogue of tile i overlaps the main loop of tile i+1.
 // Operands may be K-major ([rows, K], K contiguous) or MN-major ([K, rows], rows contiguous): the backward GEMMs
 // (dX = dZ.W, dW = dZ^T.X) read the activations in the layout the forward pass wrote them -- no transposed copies.
-// Split-K (grid.z) writes raw partial tiles to a workspace that the SIMT engine's fixed-order reduce kernel sums.
+// Split-K tiles write raw partial sums to a workspace that the SIMT engine's fixed-order reduce kernel sums.
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
@@ -27,7 +30,7 @@ namespace sfb {
 constexpr int TBM = 128;        // tile rows  (UMMA M, cta_group::1)
 constexpr int TBK = 32;         // k per stage: 32 fp32 = 128 B = one swizzle row
 constexpr int UMMA_K = 8;       // tf32
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -102,8 +105,8 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
           "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
           "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------------ descriptors
 // Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) |
@@ -144,31 +147,58 @@ struct TcSmem {
     static constexpr int A_BYTES = TBM * TBK * 4;
     static constexpr int B_BYTES = BN * TBK * 4;
     static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-    static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int NUM_BARS = 3 * STAGES + 4;
+    static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 512 /*barriers + tmem slot*/;
 };
+
+// ELU via the fast exponential: |error| <= ~2.4e-7 absolute (2 ulp of exp on [0,1]) -- inside the 1e-5 parity budget;
+// expm1f costs ~4x more instructions in the epilogue, which is the critical path of short-K tiles.
+__device__ __forceinline__ float act_fwd_fast(float z, int act) {
+    if (act == SFB200_ACT_ELU) return z > 0.f ? z : (__expf(z) - 1.f);
+    return act_fwd(z, act);
+}
+
+struct TileCoord {
+    int64_t m0;
+    int n0, k_begin, num_kb, z;
+};
+
+__device__ __forceinline__ TileCoord tile_coord(int tile, int tiles_n, int tiles_per_z, int BN, int K, int k_chunk) {
+    TileCoord t;
+    t.z = tile / tiles_per_z;
+    const int r = tile - t.z * tiles_per_z;
+    const int mb = r / tiles_n;
+    t.m0 = (int64_t)mb * TBM;
+    t.n0 = (r - mb * tiles_n) * BN;
+    t.k_begin = t.z * k_chunk;
+    const int k_end = (t.k_begin + k_chunk < K) ? t.k_begin + k_chunk : K;
+    t.num_kb = (k_end - t.k_begin + TBK - 1) / TBK;
+    return t;
+}
 
 // ------------------------------------------------------------------------------------------------ the kernel
 template <bool A_MN, bool B_MN, int BN, int STAGES, bool SPLIT3>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-               float* __restrict__ C, int64_t ldc, int64_t M, int N, int K, int k_chunk, TcEpilogue epi) {
+               float* __restrict__ C, int64_t ldc, int64_t M, int N, int K, int k_chunk, int splits, TcEpilogue epi) {
     using S = TcSmem<BN, STAGES>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES);
-    uint64_t* full = bars;                    // TMA bytes landed            (count 1 + tx)
-    uint64_t* conv = bars + STAGES;           // operands split & visible     (count 128)
-    uint64_t* empty = bars + 2 * STAGES;      // MMAs reading the stage done  (count 1, tcgen05.commit)
-    uint64_t* acc_full = bars + 3 * STAGES;   // accumulator complete         (count 1, tcgen05.commit)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 1);
+    uint64_t* full = bars;                      // TMA bytes landed             (count 1 + tx)
+    uint64_t* conv = bars + STAGES;             // operands split & visible      (count 128)
+    uint64_t* empty = bars + 2 * STAGES;        // MMAs reading the stage done   (count 1, tcgen05.commit)
+    uint64_t* acc_full = bars + 3 * STAGES;     // [2] accumulator slot complete (count 1, tcgen05.commit)
+    uint64_t* acc_empty = bars + 3 * STAGES + 2;  // [2] accumulator slot drained  (count 128 epilogue threads)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + S::NUM_BARS);
+
+    constexpr uint32_t ACC_COLS = SPLIT3 ? 2 * BN : BN;   // columns per accumulator slot ([0,BN) main, [BN,2BN) cross)
+    constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;          // two slots: 512 (BN=128, split) .. 128
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t m0 = (int64_t)blockIdx.y * TBM;
-    const int n0 = blockIdx.x * BN;
-    const int k_begin = blockIdx.z * k_chunk;
-    const int k_end = (k_begin + k_chunk < K) ? k_begin + k_chunk : K;
-    const int num_kb = (k_end - k_begin + TBK - 1) / TBK;
-    if (gridDim.z > 1) C += (int64_t)blockIdx.z * M * ldc;
+    const int tiles_n = (N + BN - 1) / BN;
+    const int tiles_per_z = tiles_n * (int)((M + TBM - 1) / TBM);
+    const int total_tiles = tiles_per_z * splits;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
@@ -178,13 +208,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             mbar_init(&conv[s], 128);
             mbar_init(&empty[s], 1);
         }
-        mbar_init(acc_full, 1);
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&acc_full[a], 1);
+            mbar_init(&acc_empty[a], 128);
+        }
         fence_barrier_init();
     }
-    // accumulators: columns [0,BN) = hi*hi', columns [BN,2BN) = the two cross terms.  The tensor core accumulates with
-    // truncation (measured: a shared accumulator gives a bias that grows with the number of MMAs); keeping the ~2^-11
-    // smaller cross terms in their own accumulator removes 2/3 of the roundings applied to the large partial sums.
-    constexpr uint32_t TMEM_COLS = SPLIT3 ? 2 * BN : BN;
     if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
     tc_fence_before();
     __syncthreads();
@@ -194,23 +223,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (warp == 0) {
         // ===================================================== TMA producer
         if (lane == 0) {
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (kb / STAGES) & 1;
-                mbar_wait(&empty[s], ph ^ 1);
-                uint8_t* st = smem + s * S::STAGE_BYTES;
-                mbar_expect_tx(&full[s], S::A_BYTES + S::B_BYTES);
-                const int k0 = k_begin + kb * TBK;
-                if (A_MN) {
-                    for (int j = 0; j < TBM / 32; ++j) tma_load_2d(st + j * 4096, &tmap_a, &full[s], (int)m0 + 32 * j, k0);
-                } else {
-                    tma_load_2d(st, &tmap_a, &full[s], k0, (int)m0);
-                }
-                uint8_t* sb = st + 2 * S::A_BYTES;
-                if (B_MN) {
-                    for (int j = 0; j < BN / 32; ++j) tma_load_2d(sb + j * 4096, &tmap_b, &full[s], n0 + 32 * j, k0);
-                } else {
-                    tma_load_2d(sb, &tmap_b, &full[s], k0, n0);
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const TileCoord tc = tile_coord(tile, tiles_n, tiles_per_z, BN, K, k_chunk);
+                for (int kb = 0; kb < tc.num_kb; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(&empty[s], ph ^ 1);
+                    uint8_t* st = smem + s * S::STAGE_BYTES;
+                    mbar_expect_tx(&full[s], S::A_BYTES + S::B_BYTES);
+                    const int k0 = tc.k_begin + kb * TBK;
+                    if (A_MN) {
+                        for (int j = 0; j < TBM / 32; ++j)
+                            tma_load_2d(st + j * 4096, &tmap_a, &full[s], (int)tc.m0 + 32 * j, k0);
+                    } else {
+                        tma_load_2d(st, &tmap_a, &full[s], k0, (int)tc.m0);
+                    }
+                    uint8_t* sb = st + 2 * S::A_BYTES;
+                    if (B_MN) {
+                        for (int j = 0; j < BN / 32; ++j) tma_load_2d(sb + j * 4096, &tmap_b, &full[s], tc.n0 + 32 * j, k0);
+                    } else {
+                        tma_load_2d(sb, &tmap_b, &full[s], k0, tc.n0);
+                    }
                 }
             }
         }
@@ -219,108 +253,153 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         constexpr uint32_t idesc = make_idesc(A_MN, B_MN, TBM, BN);
         constexpr uint32_t A_KSTEP = A_MN ? (1024u >> 4) : (UMMA_K * 4u >> 4);   // descriptor start advance per k8
         constexpr uint32_t B_KSTEP = B_MN ? (1024u >> 4) : (UMMA_K * 4u >> 4);
-        for (int kb = 0; kb < num_kb; ++kb) {
-            const int s = kb % STAGES;
-            const uint32_t ph = (kb / STAGES) & 1;
-            mbar_wait(&conv[s], ph);
+        uint32_t it = 0, tile_iter = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_iter) {
+            const TileCoord tc = tile_coord(tile, tiles_n, tiles_per_z, BN, K, k_chunk);
+            const uint32_t slot = tile_iter & 1, acc_ph = (tile_iter >> 1) & 1;
+            mbar_wait(&acc_empty[slot], acc_ph ^ 1);   // epilogue has drained this accumulator slot
             tc_fence_after();
-            if (lane == 0) {
-                const uint32_t a_hi = smem_u32(smem + s * S::STAGE_BYTES);
-                const uint32_t a_lo = a_hi + S::A_BYTES;
-                const uint32_t b_hi = a_hi + 2 * S::A_BYTES;
-                const uint32_t b_lo = b_hi + S::B_BYTES;
-                const uint64_t da_hi = make_smem_desc(a_hi, A_MN), da_lo = make_smem_desc(a_lo, A_MN);
-                const uint64_t db_hi = make_smem_desc(b_hi, B_MN), db_lo = make_smem_desc(b_lo, B_MN);
+            const uint32_t d_main = tmem_base + slot * ACC_COLS;
+            for (int kb = 0; kb < tc.num_kb; ++kb, ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                mbar_wait(&conv[s], ph);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t a_hi = smem_u32(smem + s * S::STAGE_BYTES);
+                    const uint32_t a_lo = a_hi + S::A_BYTES;
+                    const uint32_t b_hi = a_hi + 2 * S::A_BYTES;
+                    const uint32_t b_lo = b_hi + S::B_BYTES;
+                    const uint64_t da_hi = make_smem_desc(a_hi, A_MN), da_lo = make_smem_desc(a_lo, A_MN);
+                    const uint64_t db_hi = make_smem_desc(b_hi, B_MN), db_lo = make_smem_desc(b_lo, B_MN);
 #pragma unroll
-                for (int k = 0; k < TBK / UMMA_K; ++k) {
-                    const uint64_t ao = (uint64_t)(k * A_KSTEP), bo = (uint64_t)(k * B_KSTEP);
-                    umma_tf32(tmem_base, da_hi + ao, db_hi + bo, idesc, (kb | k) != 0);
-                    if (SPLIT3) {
-                        umma_tf32(tmem_base + BN, da_hi + ao, db_lo + bo, idesc, (kb | k) != 0);
-                        umma_tf32(tmem_base + BN, da_lo + ao, db_hi + bo, idesc, 1);
+                    for (int k = 0; k < TBK / UMMA_K; ++k) {
+                        const uint64_t ao = (uint64_t)(k * A_KSTEP), bo = (uint64_t)(k * B_KSTEP);
+                        umma_tf32(d_main, da_hi + ao, db_hi + bo, idesc, (kb | k) != 0);
+                        if (SPLIT3) {
+                            umma_tf32(d_main + BN, da_hi + ao, db_lo + bo, idesc, (kb | k) != 0);
+                            umma_tf32(d_main + BN, da_lo + ao, db_hi + bo, idesc, 1);
+                        }
                     }
+                    umma_commit(&empty[s]);                                  // stage reusable once these MMAs have read it
+                    if (kb == tc.num_kb - 1) umma_commit(&acc_full[slot]);   // accumulator slot final
                 }
-                umma_commit(&empty[s]);                       // stage reusable once these MMAs have read it
-                if (kb == num_kb - 1) umma_commit(acc_full);  // accumulator final
+                __syncwarp();
             }
-            __syncwarp();
+        }
+    } else if (warp < 6) {
+        // ===================================================== operand split (per stage)
+        const int ct = threadIdx.x - 64;   // 0..127
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const TileCoord tc = tile_coord(tile, tiles_n, tiles_per_z, BN, K, k_chunk);
+            for (int kb = 0; kb < tc.num_kb; ++kb, ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                mbar_wait(&full[s], ph);
+                if (SPLIT3) {
+                    uint8_t* st = smem + s * S::STAGE_BYTES;
+                    // elementwise, hence layout-agnostic: hi in place, lo at the same (swizzled) offset of the lo buffer
+                    auto split = [&](uint8_t* hi_buf, uint8_t* lo_buf, int n16) {
+                        uint4* h4 = reinterpret_cast<uint4*>(hi_buf);
+                        uint4* l4 = reinterpret_cast<uint4*>(lo_buf);
+#pragma unroll 4
+                        for (int i = ct; i < n16; i += 128) {
+                            const uint4 v = h4[i];
+                            uint4 h, l;
+                            h.x = v.x & 0xffffe000u; h.y = v.y & 0xffffe000u; h.z = v.z & 0xffffe000u; h.w = v.w & 0xffffe000u;
+                            l.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x)) & 0xffffe000u;
+                            l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y)) & 0xffffe000u;
+                            l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z)) & 0xffffe000u;
+                            l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w)) & 0xffffe000u;
+                            h4[i] = h;
+                            l4[i] = l;
+                        }
+                    };
+                    split(st, st + S::A_BYTES, S::A_BYTES / 16);
+                    split(st + 2 * S::A_BYTES, st + 2 * S::A_BYTES + S::B_BYTES, S::B_BYTES / 16);
+                }
+                fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core (async proxy)
+                mbar_arrive(&conv[s]);
+            }
         }
     } else {
-        // ===================================================== operand split (per stage), then epilogue
-        const int ct = threadIdx.x - 64;   // 0..127
-        for (int kb = 0; kb < num_kb; ++kb) {
-            const int s = kb % STAGES;
-            const uint32_t ph = (kb / STAGES) & 1;
-            mbar_wait(&full[s], ph);
-            uint8_t* st = smem + s * S::STAGE_BYTES;
-            // the split is elementwise, so it is layout-agnostic: hi in place, lo at the same (swizzled) offset
-            auto split = [&](uint8_t* hi_buf, uint8_t* lo_buf, int bytes) {
-                uint4* h4 = reinterpret_cast<uint4*>(hi_buf);
-                uint4* l4 = reinterpret_cast<uint4*>(lo_buf);
-                for (int i = ct; i < bytes / 16; i += 128) {
-                    uint4 v = h4[i];
-                    uint4 h, l;
-                    h.x = v.x & 0xffffe000u; h.y = v.y & 0xffffe000u; h.z = v.z & 0xffffe000u; h.w = v.w & 0xffffe000u;
-                    l.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x)) & 0xffffe000u;
-                    l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y)) & 0xffffe000u;
-                    l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z)) & 0xffffe000u;
-                    l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w)) & 0xffffe000u;
-                    h4[i] = h;
-                    l4[i] = l;
-                }
-            };
-            if (SPLIT3) {
-                split(st, st + S::A_BYTES, S::A_BYTES);
-                split(st + 2 * S::A_BYTES, st + 2 * S::A_BYTES + S::B_BYTES, S::B_BYTES);
-            }
-            fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core (async proxy)
-            mbar_arrive(&conv[s]);
-        }
-
-        // ---- epilogue: TMEM -> registers -> global. warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32)
-        mbar_wait(acc_full, 0);
-        tc_fence_after();
+        // ===================================================== epilogue: TMEM -> registers -> global
+        // warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32)
         const int lane_base = (warp & 3) * 32;
-        const int64_t m = m0 + lane_base + lane;
-        const bool do_epi = gridDim.z == 1;
         const bool vec_ok = (ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15u) == 0);
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            uint32_t r[32];
-            tmem_ld_32x32b_x32(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)c0, r);
-            if (SPLIT3) {
-                uint32_t r2[32];
-                tmem_ld_32x32b_x32(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(BN + c0), r2);
+        const bool bias_vec = epi.bias && ((reinterpret_cast<uintptr_t>(epi.bias) & 15u) == 0);
+        const bool aux_vec = epi.aux && (epi.ld_aux % 4 == 0) && ((reinterpret_cast<uintptr_t>(epi.aux) & 15u) == 0);
+        uint32_t tile_iter = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_iter) {
+            const TileCoord tc = tile_coord(tile, tiles_n, tiles_per_z, BN, K, k_chunk);
+            const uint32_t slot = tile_iter & 1, acc_ph = (tile_iter >> 1) & 1;
+            mbar_wait(&acc_full[slot], acc_ph);
+            tc_fence_after();
+            const uint32_t t_main = tmem_base + slot * ACC_COLS + ((uint32_t)lane_base << 16);
+            float acc[BN];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld_32x32b_x32(t_main + (uint32_t)c0, r);
+                if (SPLIT3) {
+                    uint32_t r2[32];
+                    tmem_ld_32x32b_x32(t_main + (uint32_t)(BN + c0), r2);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) acc[c0 + j] = __uint_as_float(r[j]) + __uint_as_float(r2[j]);
+                } else {
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) acc[c0 + j] = __uint_as_float(r[j]);
+                }
             }
+            // all TMEM reads of this thread are complete: hand the slot back so the next tile's MMAs can start
+            tc_fence_before();
+            mbar_arrive(&acc_empty[slot]);
+
+            const int64_t m = tc.m0 + lane_base + lane;
+            float* Cz = C + (splits > 1 ? (int64_t)tc.z * M * ldc : 0);
+            const bool do_epi = splits == 1;
             if (m < M) {
-                float* dst = C + m * ldc + n0 + c0;
+                float* dst = Cz + m * ldc + tc.n0;
+                const bool full_n = tc.n0 + BN <= N;
+                if (full_n && vec_ok && (!do_epi || epi.mode == 0 || (epi.mode == 1 && (bias_vec || !epi.bias)) ||
+                                         (epi.mode == 2 && aux_vec))) {
+                    // fast path: whole row segment in bounds, 128-bit everything
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    float o[4];
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const int n = n0 + c0 + j + q;
-                        float v = __uint_as_float(r[j + q]);
-                        if (do_epi && n < N) {
-                            if (epi.mode == 1) v = act_fwd(v + (epi.bias ? epi.bias[n] : 0.f), epi.act);
-                            else if (epi.mode == 2) v = v * act_bwd_from_out(epi.aux[m * epi.ld_aux + n], epi.act);
+                    for (int j = 0; j < BN; j += 4) {
+                        float4 o = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+                        if (do_epi && epi.mode == 1) {
+                            if (epi.bias) {
+                                const float4 b = __ldg(reinterpret_cast<const float4*>(epi.bias + tc.n0 + j));
+                                o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+                            }
+                            o.x = act_fwd_fast(o.x, epi.act); o.y = act_fwd_fast(o.y, epi.act);
+                            o.z = act_fwd_fast(o.z, epi.act); o.w = act_fwd_fast(o.w, epi.act);
+                        } else if (do_epi && epi.mode == 2) {
+                            const float4 h = *reinterpret_cast<const float4*>(epi.aux + m * epi.ld_aux + tc.n0 + j);
+                            o.x *= act_bwd_from_out(h.x, epi.act); o.y *= act_bwd_from_out(h.y, epi.act);
+                            o.z *= act_bwd_from_out(h.z, epi.act); o.w *= act_bwd_from_out(h.w, epi.act);
                         }
-                        o[q] = v;
+                        *reinterpret_cast<float4*>(dst + j) = o;
                     }
-                    const int n = n0 + c0 + j;
-                    if (vec_ok && n + 3 < N) *reinterpret_cast<float4*>(dst + j) = make_float4(o[0], o[1], o[2], o[3]);
-                    else {
-#pragma unroll
-                        for (int q = 0; q < 4; ++q)
-                            if (n + q < N) dst[j + q] = o[q];
+                } else {
+#pragma unroll   // fully unrolled so that acc[] stays in registers (no dynamic indexing)
+                    for (int j = 0; j < BN; ++j) {
+                        const int n = tc.n0 + j;
+                        if (n < N) {
+                            float v = acc[j];
+                            if (do_epi && epi.mode == 1) v = act_fwd_fast(v + (epi.bias ? epi.bias[n] : 0.f), epi.act);
+                            else if (do_epi && epi.mode == 2) v = v * act_bwd_from_out(epi.aux[m * epi.ld_aux + n], epi.act);
+                            dst[j] = v;
+                        }
                     }
                 }
             }
         }
-        tc_fence_before();
     }
+    tc_fence_before();
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
@@ -353,7 +432,7 @@ static bool tc_init() {
     return true;
 }
 
-// 2-D fp32 tensor map, 128B swizzle. dim0 = contiguous dimension.
+// 2-D fp32 tensor map, 128B swizzle (16 B chunks for K-major tiles, 32 B chunks for MN-major). dim0 = contiguous dim.
 static bool make_tmap(CUtensorMap* out, const float* base, uint64_t dim0, uint64_t dim1, uint64_t stride1_elems,
                       uint32_t box0, uint32_t box1, bool mn_major) {
     cuuint64_t gdim[2] = {dim0, dim1};
@@ -363,8 +442,7 @@ static bool make_tmap(CUtensorMap* out, const float* base, uint64_t dim0, uint64
     CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estride,
                           CU_TENSOR_MAP_INTERLEAVE_NONE,
                           mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
-                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
 }
 
@@ -383,8 +461,9 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, float* C, int
         SFB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
         attr_set = true;
     }
-    dim3 grid((unsigned)ceil_div(N, BN), (unsigned)ceil_div(M, TBM), (unsigned)splits);
-    kern<<<grid, TC_THREADS, S::TOTAL, st>>>(ta, tb, C, ldc, M, N, K, k_chunk, epi);
+    const int64_t tiles = ceil_div(N, BN) * ceil_div(M, TBM) * splits;
+    const int64_t grid = tiles < sm_count() ? tiles : sm_count();   // persistent: one CTA per SM
+    kern<<<(unsigned)grid, TC_THREADS, S::TOTAL, st>>>(ta, tb, C, ldc, M, N, K, k_chunk, splits, epi);
     SFB_LAUNCH_OK();
     return 0;
 }
@@ -394,7 +473,7 @@ static int gemm_tc(bool a_mn, const float* A, int64_t lda, bool b_mn, const floa
                    int64_t M, int N, int K, int splits, const TcEpilogue& epi, float* ws, bool split3, cudaStream_t st) {
     if (!tc_init()) return SFB_TC_UNSUPPORTED;
     if (!operand_ok(A, lda) || !operand_ok(B, ldb) || M < 1 || N < 8 || K < 8) return SFB_TC_UNSUPPORTED;
-    if (M > 0x7fffffff || ceil_div(M, TBM) > 65535) return SFB_TC_UNSUPPORTED;
+    if (M > 0x7fffffff || ceil_div(M, TBM) * ceil_div(N, 64) * 64 > 0x7fffffff) return SFB_TC_UNSUPPORTED;
     const int BN = (N >= 128) ? 128 : 64;
     CUtensorMap ta, tb;
     bool ok;

@@ -13,7 +13,7 @@ constexpr int kHeadsMaxGroups = 512;
 // forward (+ optional sampling).  One warp handles RPW rows at a time; lane l owns columns l, l+32, ...
 // Wcat (smem): row 0 = Wv, rows 1..A = Wa.  AP = compile-time bound on A+1.
 // ---------------------------------------------------------------------------------------------------------------------
-template <int AP, int RPW>
+template <int AP, int RPW, bool VEC>
 __global__ void __launch_bounds__(256) heads_forward_kernel(
     const float* __restrict__ h, int64_t ldh, int64_t rows, int H, int A, const float* __restrict__ Wv,
     const float* __restrict__ bv, const float* __restrict__ Wa, const float* __restrict__ ba, float* __restrict__ values,
@@ -24,11 +24,11 @@ __global__ void __launch_bounds__(256) heads_forward_kernel(
     const float* __restrict__ pv_scalar, float* __restrict__ pv_out, int64_t pv_stride) {
     extern __shared__ float wcat[];   // [(A+1)][H]
     const int n_out = A + 1;
-    for (int i = threadIdx.x; i < n_out * H; i += blockDim.x) {
+    for (int i = threadIdx.x; !VEC && i < n_out * H; i += blockDim.x) {
         const int a = i / H, j = i - a * H;
         wcat[i] = (a == 0) ? Wv[j] : Wa[(int64_t)(a - 1) * H + j];
     }
-    __syncthreads();
+    if (!VEC) __syncthreads();
 
     const int lane = threadIdx.x & 31;
     const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
@@ -44,16 +44,41 @@ __global__ void __launch_bounds__(256) heads_forward_kernel(
 #pragma unroll
             for (int a = 0; a < AP; ++a) acc[r][a] = 0.f;
 
-        for (int j = lane; j < H; j += 32) {
-            float hv[RPW];
+        if (VEC) {
+            // 128-bit path: lane owns 4 consecutive columns; the (A+1) x H weights (18 KB for cfg-2) are read through
+            // L1 with __ldg -- every warp of the SM reads the same lines, so no shared-memory staging is needed
+            for (int j = lane * 4; j < H; j += 128) {
+                float4 hv[RPW];
 #pragma unroll
-            for (int r = 0; r < RPW; ++r) hv[r] = (r0 + r < rows) ? h[(r0 + r) * ldh + j] : 0.f;
+                for (int r = 0; r < RPW; ++r)
+                    hv[r] = (r0 + r < rows) ? *reinterpret_cast<const float4*>(h + (r0 + r) * ldh + j)
+                                            : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int a = 0; a < AP; ++a) {
-                if (a < n_out) {
-                    const float w = wcat[a * H + j];
+                for (int a = 0; a < AP; ++a) {
+                    if (a < n_out) {
+                        const float4 w = __ldg(reinterpret_cast<const float4*>((a == 0 ? Wv : Wa + (int64_t)(a - 1) * H) + j));
 #pragma unroll
-                    for (int r = 0; r < RPW; ++r) acc[r][a] = fmaf(hv[r], w, acc[r][a]);
+                        for (int r = 0; r < RPW; ++r) {
+                            acc[r][a] = fmaf(hv[r].x, w.x, acc[r][a]);
+                            acc[r][a] = fmaf(hv[r].y, w.y, acc[r][a]);
+                            acc[r][a] = fmaf(hv[r].z, w.z, acc[r][a]);
+                            acc[r][a] = fmaf(hv[r].w, w.w, acc[r][a]);
+                        }
+                    }
+                }
+            }
+        } else {
+            for (int j = lane; j < H; j += 32) {
+                float hv[RPW];
+#pragma unroll
+                for (int r = 0; r < RPW; ++r) hv[r] = (r0 + r < rows) ? h[(r0 + r) * ldh + j] : 0.f;
+#pragma unroll
+                for (int a = 0; a < AP; ++a) {
+                    if (a < n_out) {
+                        const float w = wcat[a * H + j];
+#pragma unroll
+                        for (int r = 0; r < RPW; ++r) acc[r][a] = fmaf(hv[r], w, acc[r][a]);
+                    }
                 }
             }
         }
@@ -277,11 +302,15 @@ __global__ void __launch_bounds__(256) heads_backward_vec4_kernel(
 __global__ void heads_backward_reduce_kernel(const float* __restrict__ part, int groups, int H, int A,
                                              float* __restrict__ dWv, float* __restrict__ dbv, float* __restrict__ dWa,
                                              float* __restrict__ dba, float* __restrict__ db_prev) {
+    // one warp per output element, lanes stride over the row groups (fixed mapping + butterfly -> deterministic)
     const int64_t part_stride = (int64_t)(A + 2) * H + (A + 1);
-    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     if (i >= part_stride) return;
     float s = 0.f;
-    for (int g = 0; g < groups; ++g) s += part[g * part_stride + i];
+    for (int g = lane; g < groups; g += 32) s += part[g * part_stride + i];
+    s = warp_sum(s);
+    if (lane != 0) return;
     const int64_t wsz = (int64_t)(A + 1) * H;
     if (i < H) dWv[i] = s;
     else if (i < wsz) dWa[i - H] = s;
@@ -292,15 +321,15 @@ __global__ void heads_backward_reduce_kernel(const float* __restrict__ part, int
     }
 }
 
-template <int AP, int RPW>
+template <int AP, int RPW, bool VEC>
 static int launch_heads_forward(const float* h, int64_t ldh, int64_t rows, int H, int A, const float* Wv,
                                 const float* bv, const float* Wa, const float* ba, float* values, int64_t values_stride,
                                 float* logits, int64_t logits_stride, const float* noise, uint64_t seed, uint64_t offset,
                                 const int64_t* offset_dev, float* actions_f32, int64_t actions_stride, int32_t* env_actions, float* log_prob,
                                 int64_t log_prob_stride, const float* pv_scalar, float* pv_out, int64_t pv_stride,
                                 cudaStream_t st) {
-    const size_t smem = (size_t)(A + 1) * H * sizeof(float);
-    auto kern = heads_forward_kernel<AP, RPW>;
+    const size_t smem = VEC ? 0 : (size_t)(A + 1) * H * sizeof(float);
+    auto kern = heads_forward_kernel<AP, RPW, VEC>;
     if (smem > 48 * 1024) SFB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int64_t blocks = ceil_div(ceil_div(rows, RPW), 8);
     const int64_t cap = (int64_t)sm_count() * 4;
@@ -329,15 +358,24 @@ int sfb200_heads_forward(const float* h, int64_t ldh, int64_t rows, int H, int A
     SFB_CHECK_ARG((size_t)(A + 1) * H * sizeof(float) <= 200 * 1024, "heads_forward: (A+1)*H too large for smem");
     if (rows == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-#define SFB_HF(AP, RPW)                                                                                               \
-    return launch_heads_forward<AP, RPW>(h, ldh, rows, H, A, Wv, bv, Wa, ba, values, values_stride, logits,            \
-                                         logits_stride, noise, philox_seed, philox_offset, philox_offset_dev, actions_f32,   \
-                                         actions_stride,                                                              \
-                                         env_actions_i32, log_prob, log_prob_stride, policy_version_scalar,            \
-                                         policy_version_out, pv_stride, st)
-    if (A + 1 <= 9) SFB_HF(9, 4);
-    if (A + 1 <= 17) SFB_HF(17, 2);
-    SFB_HF(32, 1);
+#define SFB_HF(AP, RPW, VEC)                                                                                          \
+    return launch_heads_forward<AP, RPW, VEC>(h, ldh, rows, H, A, Wv, bv, Wa, ba, values, values_stride, logits,       \
+                                              logits_stride, noise, philox_seed, philox_offset, philox_offset_dev,     \
+                                              actions_f32, actions_stride, env_actions_i32, log_prob, log_prob_stride, \
+                                              policy_version_scalar, policy_version_out, pv_stride, st)
+    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+    const bool vec = (H % 4 == 0) && (ldh % 4 == 0) && al16(h) && al16(Wv) && al16(Wa);
+    if (A + 1 <= 9) {
+        if (vec && rows <= 8192) SFB_HF(9, 2, true);   // sampler-sized batch: more, smaller warps-of-work
+        if (vec) SFB_HF(9, 4, true);
+        SFB_HF(9, 4, false);
+    }
+    if (A + 1 <= 17) {
+        if (vec) SFB_HF(17, 2, true);
+        SFB_HF(17, 2, false);
+    }
+    if (vec) SFB_HF(32, 1, true);
+    SFB_HF(32, 1, false);
 #undef SFB_HF
 }
 
@@ -376,7 +414,7 @@ int sfb200_heads_backward(const float* h, int64_t ldh, int64_t rows, int H, int 
                                                                     dz, lddz, part, rpg);
     SFB_LAUNCH_OK();
     const int64_t total = (int64_t)(A + 2) * H + (A + 1);
-    heads_backward_reduce_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(part, (int)groups, H, A, dWv, dbv, dWa,
+    heads_backward_reduce_kernel<<<(unsigned)ceil_div(total * 32, 256), 256, 0, st>>>(part, (int)groups, H, A, dWv, dbv, dWa,
                                                                                  dba, db_prev);
     SFB_LAUNCH_OK();
     return 0;

@@ -40,21 +40,27 @@ __global__ void __launch_bounds__(256) moments_partial_kernel(const float* __res
     }
 }
 
+// one warp per column: lanes stride over the row-group partials (fixed lane->group mapping + butterfly -> deterministic)
 __global__ void moments_finalize_kernel(const float* __restrict__ x, const double2* __restrict__ partial, int groups,
                                         int64_t rows, int dim, float* __restrict__ mean, float* __restrict__ var) {
-    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int col = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (col >= dim) return;
     double s = 0.0, ss = 0.0;
-    for (int g = 0; g < groups; ++g) {   // fixed order -> deterministic
+    for (int g = lane; g < groups; g += 32) {
         const double2 p = partial[(int64_t)g * dim + col];
         s += p.x;
         ss += p.y;
     }
-    const double n = (double)rows;
-    const double m = s / n;
-    mean[col] = (float)((double)x[col] + m);
-    // unbiased (torch.var default correction=1); rows == 1 gives NaN in torch as well
-    var[col] = (float)((ss - s * m) / (n - 1.0));
+    s = warp_sum(s);
+    ss = warp_sum(ss);
+    if (lane == 0) {
+        const double n = (double)rows;
+        const double m = s / n;
+        mean[col] = (float)((double)x[col] + m);
+        // unbiased (torch.var default correction=1); rows == 1 gives NaN in torch as well
+        var[col] = (float)((ss - s * m) / (n - 1.0));
+    }
 }
 
 // running_mean_std.py:49-62, all in float64 like the TorchScript function.
@@ -96,7 +102,7 @@ int sfb200_batch_moments(const float* x, int64_t ldx, int64_t rows, int dim, flo
     moments_partial_kernel<<<grid, 256, (size_t)rpi * cpb * sizeof(double2), st>>>(x, ldx, rows, dim, cpb, rpi,
                                                                                    (double2*)workspace);
     SFB_LAUNCH_OK();
-    moments_finalize_kernel<<<(unsigned)ceil_div(dim, 128), 128, 0, st>>>(x, (const double2*)workspace, groups, rows, dim,
+    moments_finalize_kernel<<<(unsigned)ceil_div((int64_t)dim * 32, 128), 128, 0, st>>>(x, (const double2*)workspace, groups, rows, dim,
                                                                           batch_mean, batch_var);
     SFB_LAUNCH_OK();
     return 0;

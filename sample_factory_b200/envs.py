@@ -60,7 +60,8 @@ class TapeVecEnv:
         self.term_period, self.trunc_period = term_period, trunc_period
         self.env_index_offset = env_index_offset
         dev = tape.device
-        self.step_counter = torch.zeros(1, dtype=torch.int64, device=dev)  # device-side so graphs can replay
+        # device-side so CUDA graphs can replay: [0] = env step, [1] = block ticket used to advance it in-kernel
+        self.step_counter = torch.zeros(2, dtype=torch.int64, device=dev)
         self.obs = torch.empty((self.num_agents, self.obs_dim), dtype=torch.float32, device=dev)
         self.rew = torch.empty(self.num_agents, dtype=torch.float32, device=dev)
         self.terminated = torch.empty(self.num_agents, dtype=torch.bool, device=dev)

@@ -94,14 +94,14 @@ def get_lr_scheduler(cfg):
 
 class Learner:
     def __init__(self, cfg, model: PolicyModel, num_traj: int, engine: int = ops.GEMM_SIMT,
-                 process_group: Optional["dist.ProcessGroup"] = None):
+                 process_group: Optional["dist.ProcessGroup"] = None, data_parallel: bool = True):
         self.cfg = cfg
         self.model = model
         self.device = model.device
         self.engine = engine
         self.pg = process_group
-        self.world_size = dist.get_world_size(process_group) if (process_group is not None or (
-            dist.is_available() and dist.is_initialized())) else 1
+        self.world_size = dist.get_world_size(process_group) if (data_parallel and (process_group is not None or (
+            dist.is_available() and dist.is_initialized()))) else 1
         if self.world_size > 1 and self.pg is None:
             self.pg = dist.group.WORLD
         spec = model.spec

@@ -59,13 +59,25 @@ def upload_traj(traj_dev, traj_cpu):
         traj_dev[k].copy_(v.view(traj_dev[k].shape))
 
 
+ENGINES = ["simt", "3xtf32"]
+
+
+def _need(engine):
+    from sample_factory_b200 import ops
+
+    if engine != "simt" and not ops.tc_available():
+        pytest.skip("tcgen05 engine not available")
+
+
+@pytest.mark.parametrize("engine", ENGINES)
 @pytest.mark.parametrize("name", ["tiny_gae", "tiny_vtrace", "cfg2_small"])
-def test_rollout_matches_reference_golden(name):
+def test_rollout_matches_reference_golden(name, engine):
     """Sampler vs the REFERENCE's own trajectories (same weights, same obs tape, same Exp(1) noise)."""
+    _need(engine)
     dev = torch.device("cuda", 0)
     z, meta, ocfg = load_case(name)
     tape = torch.from_numpy(z["tape"])
-    cfg, model, traj, env, sampler, learner = build(ocfg, meta["N"], state_from(z, "init/"), tape, dev)
+    cfg, model, traj, env, sampler, learner = build(ocfg, meta["N"], state_from(z, "init/"), tape, dev, engine=engine)
     sampler.reset()
     for it in range(meta["iters"]):
         st = state_from(z, "init/") if it == 0 else state_from(z, f"it{it - 1}/state/")
@@ -91,16 +103,18 @@ def test_rollout_matches_reference_golden(name):
         np.testing.assert_allclose(got["log_prob_actions"].numpy(), ref["log_prob_actions"].numpy(), atol=TOL)
 
 
+@pytest.mark.parametrize("engine", ENGINES)
 @pytest.mark.parametrize("name", ["tiny_gae", "tiny_vtrace", "cfg2_small"])
-def test_learner_matches_reference_golden(name):
+def test_learner_matches_reference_golden(name, engine):
     """Learner.train on the REFERENCE's trajectories: returns / advantages / loss terms / post-Adam weights /
     normalizer statistics against what the reference itself computed."""
     from sample_factory_b200 import ops
 
+    _need(engine)
     dev = torch.device("cuda", 0)
     z, meta, ocfg = load_case(name)
     tape = torch.from_numpy(z["tape"])
-    cfg, model, traj, env, sampler, learner = build(ocfg, meta["N"], state_from(z, "init/"), tape, dev)
+    cfg, model, traj, env, sampler, learner = build(ocfg, meta["N"], state_from(z, "init/"), tape, dev, engine=engine)
     for it in range(meta["iters"]):
         assert learner.train_step == int(z[f"it{it}/train_step_before"])
         upload_traj(traj, traj_from(z, it, ocfg))
@@ -126,7 +140,8 @@ def test_learner_matches_reference_golden(name):
             np.testing.assert_allclose(got_state[k].cpu().numpy(), v.numpy(), atol=tol, rtol=1e-6, err_msg=k)
 
 
-def test_closed_loop_vs_oracle_cfg2_shape():
+@pytest.mark.parametrize("engine", ENGINES)
+def test_closed_loop_vs_oracle_cfg2_shape(engine):
     """Sampler + learner for 2 iterations at N=256, T=32, cfg-2 model/hyper-parameters vs the oracle run on the same
     tape / noise / initial weights (the tape env keeps both rollouts aligned)."""
     from sample_factory_b200 import ops
@@ -137,7 +152,8 @@ def test_closed_loop_vs_oracle_cfg2_shape():
     st0 = O.init_state(ocfg, seed=3)
     gen = torch.Generator().manual_seed(11)
     tape = torch.randn(2 * T + 1, N, ocfg.obs_dim, generator=gen) * 1.2 - 0.2
-    cfg, model, traj, env, sampler, learner = build(ocfg, N, st0, tape, dev)
+    _need(engine)
+    cfg, model, traj, env, sampler, learner = build(ocfg, N, st0, tape, dev, engine=engine)
     olearner = O.OracleLearner(ocfg, st0)
     oenv = O.TapeVecEnv(tape, ocfg.num_actions)
     olast = oenv.reset()

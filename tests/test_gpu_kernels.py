@@ -339,7 +339,8 @@ def test_sampler_pre_post_step_and_env(dev):
         fin_len += float(ref_len[d_ref].sum())
         ref_ret[d_ref] = 0
         ref_len[d_ref] = 0
-    assert torch.all(pid_t == 0) and counter.item() == T and env.step_counter.item() == T
+    assert torch.all(pid_t == 0) and counter.item() == T and env.step_counter[0].item() == T
+    assert env.step_counter[1].item() == 0
     s = stats.cpu()
     assert int(s[0]) == fin_cnt and abs(s[1].item() - fin_ret) < 1e-3 and abs(s[2].item() - fin_len) < 1e-6
     np.testing.assert_allclose(ep_ret.cpu().numpy(), ref_ret.numpy(), atol=1e-6)
