@@ -10,11 +10,11 @@
 // the 2^-11 smaller cross terms apart removes 2/3 of the roundings applied to the large partial sums -- measured 2.7e-5
 // -> 9.8e-6 max error on a K=512 GEMM.)
 //
-// PERSISTENT kernel, one CTA per SM, 320 threads, static round-robin tile schedule (128 x BN output tiles):
+// PERSISTENT kernel, one CTA per SM, 448 threads, static round-robin tile schedule (128 x BN output tiles):
 //   warp 0      : TMA producer   (cp.async.bulk.tensor, 128B-swizzled boxes, mbarrier complete_tx), runs ahead across tiles
 //   warp 1      : TMEM allocator + MMA issuer (one elected lane issues tcgen05.mma, tcgen05.commit frees the stage)
 //   warps 2..5  : operand split: raw fp32 tile -> hi (in place) + lo (second buffer), fence.proxy.async, arrive
-//   warps 6..9  : epilogue: tcgen05.ld both accumulators -> release the TMEM slot -> bias/activation -> global.
+//   warps 6..13 : epilogue: tcgen05.ld both accumulators -> release the TMEM slot -> bias/activation -> global.
 //                 The accumulator is double-buffered in TMEM, so the epilogue of tile i overlaps the main loop of tile i+1.
 // Operands may be K-major ([rows, K], K contiguous) or MN-major ([K, rows], rows contiguous): the backward GEMMs
 // (dX = dZ.W, dW = dZ^T.X) read the activations in the layout the forward pass wrote them -- no transposed copies.
@@ -30,7 +30,7 @@ namespace sfb {
 constexpr int TBM = 128;        // tile rows  (UMMA M, cta_group::1)
 constexpr int TBK = 32;         // k per stage: 32 fp32 = 128 B = one swizzle row
 constexpr int UMMA_K = 8;       // tf32
-constexpr int TC_THREADS = 320;
+constexpr int TC_THREADS = 448;   // TMA, MMA, 4 split warps, 8 epilogue warps
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -148,7 +148,8 @@ struct TcSmem {
     static constexpr int B_BYTES = BN * TBK * 4;
     static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
     static constexpr int NUM_BARS = 3 * STAGES + 4;
-    static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 512 /*barriers + tmem slot*/;
+    static constexpr int BIAS_FLOATS = 2048;   // bias staged in smem when N <= this
+    static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 512 /*barriers + tmem slot*/ + BIAS_FLOATS * 4;
 };
 
 // ELU via the fast exponential: |error| <= ~2.4e-7 absolute (2 ulp of exp on [0,1]) -- inside the 1e-5 parity budget;
@@ -156,6 +157,42 @@ struct TcSmem {
 __device__ __forceinline__ float act_fwd_fast(float z, int act) {
     if (act == SFB200_ACT_ELU) return z > 0.f ? z : (__expf(z) - 1.f);
     return act_fwd(z, act);
+}
+
+template <int ACT>
+__device__ __forceinline__ float act_fwd_ct(float z) {
+    if (ACT == SFB200_ACT_ELU) return z > 0.f ? z : (__expf(z) - 1.f);
+    if (ACT == SFB200_ACT_RELU) return fmaxf(z, 0.f);
+    if (ACT == SFB200_ACT_TANH) return tanhf(z);
+    return z;
+}
+template <int ACT>
+__device__ __forceinline__ float act_bwd_ct(float h) {
+    if (ACT == SFB200_ACT_ELU) return h > 0.f ? 1.f : h + 1.f;
+    if (ACT == SFB200_ACT_RELU) return h > 0.f ? 1.f : 0.f;
+    if (ACT == SFB200_ACT_TANH) return 1.f - h * h;
+    return 1.f;
+}
+
+// one output row segment (BN columns, fully in bounds, 16 B aligned) with the epilogue resolved at compile time
+template <int MODE, int ACT, int BN>
+__device__ __forceinline__ void write_row(const float (&acc)[BN], float* __restrict__ dst, const float* bias_n0,
+                                          const float4 (&auxv)[BN / 4]) {
+#pragma unroll
+    for (int j = 0; j < BN; j += 4) {
+        float4 o = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+        if (MODE == 1) {
+            if (bias_n0) {
+                const float4 b = *reinterpret_cast<const float4*>(bias_n0 + j);   // shared (staged) or global
+                o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+            }
+            o.x = act_fwd_ct<ACT>(o.x); o.y = act_fwd_ct<ACT>(o.y); o.z = act_fwd_ct<ACT>(o.z); o.w = act_fwd_ct<ACT>(o.w);
+        } else if (MODE == 2) {
+            const float4 h = auxv[j / 4];
+            o.x *= act_bwd_ct<ACT>(h.x); o.y *= act_bwd_ct<ACT>(h.y); o.z *= act_bwd_ct<ACT>(h.z); o.w *= act_bwd_ct<ACT>(h.w);
+        }
+        *reinterpret_cast<float4*>(dst + j) = o;
+    }
 }
 
 struct TileCoord {
@@ -191,6 +228,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     uint64_t* acc_full = bars + 3 * STAGES;     // [2] accumulator slot complete (count 1, tcgen05.commit)
     uint64_t* acc_empty = bars + 3 * STAGES + 2;  // [2] accumulator slot drained  (count 128 epilogue threads)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + S::NUM_BARS);
+    float* bias_s = reinterpret_cast<float*>(smem + STAGES * S::STAGE_BYTES + 512);
 
     constexpr uint32_t ACC_COLS = SPLIT3 ? 2 * BN : BN;   // columns per accumulator slot ([0,BN) main, [BN,2BN) cross)
     constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;          // two slots: 512 (BN=128, split) .. 128
@@ -210,7 +248,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&acc_full[a], 1);
-            mbar_init(&acc_empty[a], 128);
+            mbar_init(&acc_empty[a], 256);
         }
         fence_barrier_init();
     }
@@ -325,74 +363,107 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
     } else {
         // ===================================================== epilogue: TMEM -> registers -> global
-        // warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32)
+        // 8 warps: warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32); warps 6..9 take columns [0, BN/2) of their
+        // lane quadrant, warps 10..13 take [BN/2, BN).  One warp per scheduler was latency-bound (ncu: the epilogue
+        // warps were ~100% busy at IPC 0.12 and paced the whole kernel for short-K tiles).
+        constexpr int CH = BN / 2;                      // columns per thread
         const int lane_base = (warp & 3) * 32;
+        const int col0 = ((warp - 6) >> 2) * CH;
         const bool vec_ok = (ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15u) == 0);
-        const bool bias_vec = epi.bias && ((reinterpret_cast<uintptr_t>(epi.bias) & 15u) == 0);
         const bool aux_vec = epi.aux && (epi.ld_aux % 4 == 0) && ((reinterpret_cast<uintptr_t>(epi.aux) & 15u) == 0);
+        // bias for ALL N columns is staged once per kernel in shared memory (persistent CTA)
+        const bool bias_smem = epi.bias != nullptr && N <= S::BIAS_FLOATS;
+        if (bias_smem) {
+            for (int i = threadIdx.x - 192; i < N; i += 256) bias_s[i] = epi.bias[i];
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+        }
+        const float* bias_base = bias_smem ? bias_s : epi.bias;
+        const bool bias_vec = epi.bias && (bias_smem || ((reinterpret_cast<uintptr_t>(epi.bias) & 15u) == 0));
+        const bool do_epi = splits == 1;
+        const int mode = do_epi ? epi.mode : 0;
         uint32_t tile_iter = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_iter) {
             const TileCoord tc = tile_coord(tile, tiles_n, tiles_per_z, BN, K, k_chunk);
             const uint32_t slot = tile_iter & 1, acc_ph = (tile_iter >> 1) & 1;
+            const int64_t m = tc.m0 + lane_base + lane;
+            const int nbeg = tc.n0 + col0;
+            const bool fast = (m < M) && (nbeg + CH <= N) && vec_ok &&
+                              (mode == 0 || (mode == 1 && (bias_vec || !epi.bias)) || (mode == 2 && aux_vec));
+            // Processed in 32-column chunks so that the live set (32 accumulators + 32 cross-term temporaries + 8 float4
+            // of aux) fits the 128-register budget of a 448-thread CTA without spilling.
+            // mode 2: the activation-derivative operand of the first chunk is fetched BEFORE the accumulator is ready
+            // (hides its HBM latency behind the main loop of this tile).
+            const float* aux_row = (mode == 2 && fast) ? epi.aux + m * epi.ld_aux + nbeg : nullptr;
+            float4 auxv[8];
+            if (aux_row) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) auxv[j] = *reinterpret_cast<const float4*>(aux_row + 4 * j);
+            }
             mbar_wait(&acc_full[slot], acc_ph);
             tc_fence_after();
-            const uint32_t t_main = tmem_base + slot * ACC_COLS + ((uint32_t)lane_base << 16);
-            float acc[BN];
-#pragma unroll
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                uint32_t r[32];
-                tmem_ld_32x32b_x32(t_main + (uint32_t)c0, r);
-                if (SPLIT3) {
-                    uint32_t r2[32];
-                    tmem_ld_32x32b_x32(t_main + (uint32_t)(BN + c0), r2);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) acc[c0 + j] = __uint_as_float(r[j]) + __uint_as_float(r2[j]);
-                } else {
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) acc[c0 + j] = __uint_as_float(r[j]);
-                }
-            }
-            // all TMEM reads of this thread are complete: hand the slot back so the next tile's MMAs can start
-            tc_fence_before();
-            mbar_arrive(&acc_empty[slot]);
-
-            const int64_t m = tc.m0 + lane_base + lane;
+            const uint32_t t_main = tmem_base + slot * ACC_COLS + ((uint32_t)lane_base << 16) + (uint32_t)col0;
             float* Cz = C + (splits > 1 ? (int64_t)tc.z * M * ldc : 0);
-            const bool do_epi = splits == 1;
-            if (m < M) {
-                float* dst = Cz + m * ldc + tc.n0;
-                const bool full_n = tc.n0 + BN <= N;
-                if (full_n && vec_ok && (!do_epi || epi.mode == 0 || (epi.mode == 1 && (bias_vec || !epi.bias)) ||
-                                         (epi.mode == 2 && aux_vec))) {
-                    // fast path: whole row segment in bounds, 128-bit everything
+            float* dst_row = Cz + m * ldc + nbeg;
 #pragma unroll
-                    for (int j = 0; j < BN; j += 4) {
-                        float4 o = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
-                        if (do_epi && epi.mode == 1) {
-                            if (epi.bias) {
-                                const float4 b = __ldg(reinterpret_cast<const float4*>(epi.bias + tc.n0 + j));
-                                o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-                            }
-                            o.x = act_fwd_fast(o.x, epi.act); o.y = act_fwd_fast(o.y, epi.act);
-                            o.z = act_fwd_fast(o.z, epi.act); o.w = act_fwd_fast(o.w, epi.act);
-                        } else if (do_epi && epi.mode == 2) {
-                            const float4 h = *reinterpret_cast<const float4*>(epi.aux + m * epi.ld_aux + tc.n0 + j);
-                            o.x *= act_bwd_from_out(h.x, epi.act); o.y *= act_bwd_from_out(h.y, epi.act);
-                            o.z *= act_bwd_from_out(h.z, epi.act); o.w *= act_bwd_from_out(h.w, epi.act);
-                        }
-                        *reinterpret_cast<float4*>(dst + j) = o;
+            for (int c0 = 0; c0 < CH; c0 += 32) {
+                float acc[32];
+                {
+                    uint32_t r[32];
+                    tmem_ld_32x32b_x32(t_main + (uint32_t)c0, r);
+                    if (SPLIT3) {
+                        uint32_t r2[32];
+                        tmem_ld_32x32b_x32(t_main + (uint32_t)(BN + c0), r2);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(r[j]) + __uint_as_float(r2[j]);
+                    } else {
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(r[j]);
                     }
-                } else {
+                }
+                if (c0 + 32 >= CH) {
+                    // all TMEM reads of this thread are complete: hand the slot back so the next tile's MMAs can start
+                    tc_fence_before();
+                    mbar_arrive(&acc_empty[slot]);
+                }
+                if (c0 > 0 && aux_row) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) auxv[j] = *reinterpret_cast<const float4*>(aux_row + c0 + 4 * j);
+                }
+                if (m < M) {
+                    float* dst = dst_row + c0;
+                    if (fast) {
+                        // whole row segment in bounds, 128-bit everything; mode / activation resolved once per chunk into
+                        // a straight-line specialisation (a per-element switch cost 4x the instructions)
+                        const float* bias_n0 = epi.bias ? bias_base + nbeg + c0 : nullptr;
+                        if (mode == 1) {
+                            switch (epi.act) {
+                                case SFB200_ACT_ELU: write_row<1, SFB200_ACT_ELU, 32>(acc, dst, bias_n0, auxv); break;
+                                case SFB200_ACT_RELU: write_row<1, SFB200_ACT_RELU, 32>(acc, dst, bias_n0, auxv); break;
+                                case SFB200_ACT_TANH: write_row<1, SFB200_ACT_TANH, 32>(acc, dst, bias_n0, auxv); break;
+                                default: write_row<1, SFB200_ACT_NONE, 32>(acc, dst, bias_n0, auxv); break;
+                            }
+                        } else if (mode == 2) {
+                            switch (epi.act) {
+                                case SFB200_ACT_ELU: write_row<2, SFB200_ACT_ELU, 32>(acc, dst, bias_n0, auxv); break;
+                                case SFB200_ACT_RELU: write_row<2, SFB200_ACT_RELU, 32>(acc, dst, bias_n0, auxv); break;
+                                case SFB200_ACT_TANH: write_row<2, SFB200_ACT_TANH, 32>(acc, dst, bias_n0, auxv); break;
+                                default: write_row<0, SFB200_ACT_NONE, 32>(acc, dst, bias_n0, auxv); break;
+                            }
+                        } else {
+                            write_row<0, SFB200_ACT_NONE, 32>(acc, dst, bias_n0, auxv);
+                        }
+                    } else {
 #pragma unroll   // fully unrolled so that acc[] stays in registers (no dynamic indexing)
-                    for (int j = 0; j < BN; ++j) {
-                        const int n = tc.n0 + j;
-                        if (n < N) {
-                            float v = acc[j];
-                            if (do_epi && epi.mode == 1) v = act_fwd_fast(v + (epi.bias ? epi.bias[n] : 0.f), epi.act);
-                            else if (do_epi && epi.mode == 2) v = v * act_bwd_from_out(epi.aux[m * epi.ld_aux + n], epi.act);
-                            dst[j] = v;
+                        for (int j = 0; j < 32; ++j) {
+                            const int n = nbeg + c0 + j;
+                            if (n < N) {
+                                float v = acc[j];
+                                if (mode == 1) v = act_fwd_fast(v + (epi.bias ? epi.bias[n] : 0.f), epi.act);
+                                else if (mode == 2) v = v * act_bwd_from_out(epi.aux[m * epi.ld_aux + n], epi.act);
+                                dst[j] = v;
+                            }
                         }
                     }
                 }
