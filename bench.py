@@ -267,8 +267,7 @@ def run_ours(args):
     e0.record()
     for _ in range(args.steps):
         runner.iteration()
-        if runner.sampler._graph is not None:
-            replay_launches += runner.sampler.kernel_launches_per_rollout
+        replay_launches += runner.sampler.graph_replay_launches
     e1.record()
     barrier()
     timing_on[0] = False
@@ -310,9 +309,9 @@ def run_ours(args):
     # ------------------------------------------------------------------ end-to-end arm (host env, H2D/D2H inside)
     e2e = None
     if not args.no_e2e:
-        r2 = Runner(make_cfg("synthetic_tape_host", args.engine, False))
+        r2 = Runner(make_cfg("synthetic_tape_host", args.engine, not args.no_graph))
         r2.init()
-        for _ in range(max(1, args.warmup)):
+        for _ in range(max(2, args.warmup)):
             r2.iteration()
             r2.learner.fetch_stats()
         barrier()

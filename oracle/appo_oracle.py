@@ -71,6 +71,9 @@ class OracleCfg:
     reward_clip: float = 1000.0
     max_policy_lag: int = 1000
     policy_id: int = 0
+    use_rnn: bool = False      # model/core.py:19-64 (ModelCoreRNN) between encoder and decoder
+    rnn_type: str = "gru"
+    rnn_size: int = 512
 
 
 # --------------------------------------------------------------------------------------
@@ -92,6 +95,9 @@ def dec_b(i: int) -> str:
     return f"decoder.mlp.{2 * i}.bias"
 
 
+RNN_W_IH, RNN_W_HH, RNN_B_IH, RNN_B_HH = (
+    "core.core.weight_ih_l0", "core.core.weight_hh_l0", "core.core.bias_ih_l0", "core.core.bias_hh_l0",
+)
 CRITIC_W, CRITIC_B = "critic_linear.weight", "critic_linear.bias"
 ACTION_W, ACTION_B = (
     "action_parameterization.distribution_linear.weight",
@@ -112,10 +118,19 @@ def param_names(cfg: OracleCfg) -> List[str]:
     names = []
     for i in range(len(cfg.encoder_mlp_layers)):
         names += [enc_w(i), enc_b(i)]
+    if cfg.use_rnn:
+        names += [RNN_W_IH, RNN_W_HH, RNN_B_IH, RNN_B_HH]
     for i in range(len(cfg.decoder_mlp_layers)):
         names += [dec_w(i), dec_b(i)]
     names += [CRITIC_W, CRITIC_B, ACTION_W, ACTION_B]
     return names
+
+
+def rnn_state_size(cfg: OracleCfg) -> int:
+    """model/model_utils.py:11-24 (single layer, shared weights): 1 placeholder without RNN, H for GRU, 2H for LSTM."""
+    if not cfg.use_rnn:
+        return 1
+    return cfg.rnn_size * (2 if cfg.rnn_type == "lstm" else 1)
 
 
 def init_state(cfg: OracleCfg, seed: int = 0) -> Dict[str, Tensor]:
@@ -128,6 +143,14 @@ def init_state(cfg: OracleCfg, seed: int = 0) -> Dict[str, Tensor]:
         st[enc_w(i)] = torch.randn(h, d, generator=g) / math.sqrt(d)
         st[enc_b(i)] = torch.randn(h, generator=g) * 0.01
         d = h
+    if cfg.use_rnn:
+        H, G = cfg.rnn_size, (4 if cfg.rnn_type == "lstm" else 3)
+        k = 1.0 / math.sqrt(H)
+        st[RNN_W_IH] = (torch.rand(G * H, d, generator=g) * 2 - 1) * k
+        st[RNN_W_HH] = (torch.rand(G * H, H, generator=g) * 2 - 1) * k
+        st[RNN_B_IH] = (torch.rand(G * H, generator=g) * 2 - 1) * k
+        st[RNN_B_HH] = (torch.rand(G * H, generator=g) * 2 - 1) * k
+        d = H
     for i, h in enumerate(cfg.decoder_mlp_layers):
         st[dec_w(i)] = torch.randn(h, d, generator=g) / math.sqrt(d)
         st[dec_b(i)] = torch.randn(h, generator=g) * 0.01
@@ -206,16 +229,59 @@ def _act(cfg: OracleCfg, x: Tensor) -> Tensor:
     raise ValueError(cfg.nonlinearity)
 
 
-def mlp_forward(cfg: OracleCfg, st: Dict[str, Tensor], x: Tensor) -> Tuple[Tensor, Tensor]:
-    """normalized obs [B, D] -> (values [B], action_logits [B, A])."""
+def encoder_forward(cfg: OracleCfg, st: Dict[str, Tensor], x: Tensor) -> Tensor:
+    """forward_head (actor_critic.py:160-162): MlpEncoder."""
     h = x
     for i in range(len(cfg.encoder_mlp_layers)):
         h = _act(cfg, torch.nn.functional.linear(h, st[enc_w(i)], st[enc_b(i)]))
+    return h
+
+
+def tail_forward(cfg: OracleCfg, st: Dict[str, Tensor], h: Tensor) -> Tuple[Tensor, Tensor]:
+    """forward_tail (actor_critic.py:168-186): decoder MLP -> critic_linear / distribution_linear."""
     for i in range(len(cfg.decoder_mlp_layers)):
         h = _act(cfg, torch.nn.functional.linear(h, st[dec_w(i)], st[dec_b(i)]))
     values = torch.nn.functional.linear(h, st[CRITIC_W], st[CRITIC_B]).squeeze(-1)
     logits = torch.nn.functional.linear(h, st[ACTION_W], st[ACTION_B])
     return values, logits
+
+
+def rnn_cell(cfg: OracleCfg, st: Dict[str, Tensor], x: Tensor, state: Tensor) -> Tuple[Tensor, Tensor]:
+    """One step of ModelCoreRNN (model/core.py:37-64) written out: torch.nn.GRU / LSTM cell equations, gate order as in
+    the PyTorch weight layout (GRU: r,z,n ; LSTM: i,f,g,o); LSTM state = [h || c] (core.py:51-53).
+    Returns (core_output [B,H], new_state [B, H or 2H])."""
+    H = cfg.rnn_size
+    gi = torch.nn.functional.linear(x, st[RNN_W_IH], st[RNN_B_IH])
+    if cfg.rnn_type == "gru":
+        h = state
+        gh = torch.nn.functional.linear(h, st[RNN_W_HH], st[RNN_B_HH])
+        r = torch.sigmoid(gi[:, :H] + gh[:, :H])
+        z = torch.sigmoid(gi[:, H:2 * H] + gh[:, H:2 * H])
+        n = torch.tanh(gi[:, 2 * H:] + r * gh[:, 2 * H:])
+        h_new = (1 - z) * n + z * h
+        return h_new, h_new
+    h, c = state[:, :H], state[:, H:]
+    g = gi + torch.nn.functional.linear(h, st[RNN_W_HH], st[RNN_B_HH])
+    i_, f_, g_, o_ = torch.sigmoid(g[:, :H]), torch.sigmoid(g[:, H:2 * H]), torch.tanh(g[:, 2 * H:3 * H]), torch.sigmoid(g[:, 3 * H:])
+    c_new = f_ * c + i_ * g_
+    h_new = o_ * torch.tanh(c_new)
+    return h_new, torch.cat([h_new, c_new], dim=1)
+
+
+def model_forward(cfg: OracleCfg, st: Dict[str, Tensor], x: Tensor, rnn_state: Optional[Tensor] = None):
+    """ActorCriticSharedWeights.forward (actor_critic.py:188-195): (values, logits, new_rnn_state)."""
+    h = encoder_forward(cfg, st, x)
+    new_state = rnn_state
+    if cfg.use_rnn:
+        h, new_state = rnn_cell(cfg, st, h, rnn_state)
+    values, logits = tail_forward(cfg, st, h)
+    return values, logits, new_state
+
+
+def mlp_forward(cfg: OracleCfg, st: Dict[str, Tensor], x: Tensor) -> Tuple[Tensor, Tensor]:
+    """normalized obs [B, D] -> (values [B], action_logits [B, A]) for the non-recurrent model."""
+    assert not cfg.use_rnn
+    return tail_forward(cfg, st, encoder_forward(cfg, st, x))
 
 
 # --------------------------------------------------------------------------------------
@@ -258,7 +324,7 @@ def alloc_trajectories(cfg: OracleCfg, num_traj: int) -> Dict[str, Tensor]:
     T, B = cfg.rollout, num_traj
     t: Dict[str, Tensor] = {}
     t["obs"] = torch.full((B, T + 1, cfg.obs_dim), -4242.42)
-    t["rnn_states"] = torch.full((B, T + 1, 1), -4242.42)
+    t["rnn_states"] = torch.full((B, T + 1, rnn_state_size(cfg)), -4242.42)
     t["actions"] = torch.full((B, T, 1), -4242.42)
     t["action_logits"] = torch.full((B, T, cfg.num_actions), -4242.42)
     t["log_prob_actions"] = torch.full((B, T), -4242.42)
@@ -272,17 +338,15 @@ def alloc_trajectories(cfg: OracleCfg, num_traj: int) -> Dict[str, Tensor]:
     return t
 
 
-def policy_step(
-    cfg: OracleCfg, st: Dict[str, Tensor], obs: Tensor, noise_q: Tensor
-) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
-    """inference_worker.py:313-341 body for the non-recurrent categorical model:
+def policy_step(cfg: OracleCfg, st: Dict[str, Tensor], obs: Tensor, noise_q: Tensor, rnn_state: Optional[Tensor] = None):
+    """inference_worker.py:313-341 body for the categorical model:
     normalize (eval mode: no stat update) -> forward -> sample -> log-prob.
-    Returns (actions int64 [N,1], logits [N,A], log_prob [N], values [N])."""
+    Returns (actions int64 [N,1], logits [N,A], log_prob [N], values [N], new_rnn_state)."""
     x = normalize_obs(cfg, st, obs, update_stats=False)
-    values, logits = mlp_forward(cfg, st, x)
+    values, logits, new_state = model_forward(cfg, st, x, rnn_state)
     actions = cat_sample(logits, noise_q)
     log_prob = cat_log_prob(logits, actions)
-    return actions, logits, log_prob, values
+    return actions, logits, log_prob, values, new_state
 
 
 class TapeVecEnv:
@@ -321,14 +385,18 @@ def rollout(
     traj: Dict[str, Tensor],
     noise: Tensor,
     policy_version: int,
+    rnn_state: Optional[Tensor] = None,
 ) -> Tensor:
     """T steps of batched_sampling.py:298-388 + inference_worker.py:313-341 into `traj` (in place).
-    noise: [T, N, A] Exp(1) draws. Returns the obs after the last step (next rollout's first obs)."""
+    noise: [T, N, A] Exp(1) draws. rnn_state [N, S] (S = rnn_state_size) is the runner's last_rnn_state, updated IN
+    PLACE (zeros initially, batched_sampling.py:190). Returns the obs after the last step."""
+    if rnn_state is None:
+        rnn_state = torch.zeros(last_obs.shape[0], rnn_state_size(cfg))
     for t in range(cfg.rollout):
         # generate_policy_request :374-388
         traj["obs"][:, t] = last_obs
-        traj["rnn_states"][:, t] = 0.0
-        actions, logits, log_prob, values = policy_step(cfg, st, last_obs, noise[t])
+        traj["rnn_states"][:, t] = rnn_state
+        actions, logits, log_prob, values, new_state = policy_step(cfg, st, last_obs, noise[t], rnn_state)
         # advance_rollouts part 1 :308-311 (actions stored as float32, SURVEY App.A-1)
         traj["actions"][:, t] = actions.float()
         traj["action_logits"][:, t] = logits
@@ -344,9 +412,11 @@ def rollout(
         traj["dones"][:, t] = dones
         traj["time_outs"][:, t] = truncated
         traj["policy_id"][:, t] = cfg.policy_id
+        # reset next-step hidden states on episode boundaries :332-335
+        rnn_state[:] = new_state * (1.0 - dones.float()).unsqueeze(-1)
     # _finalize_trajectories :289-296
     traj["obs"][:, cfg.rollout] = last_obs
-    traj["rnn_states"][:, cfg.rollout] = 0.0
+    traj["rnn_states"][:, cfg.rollout] = rnn_state
     return last_obs
 
 
@@ -383,7 +453,7 @@ def prepare_batch(cfg: OracleCfg, st: Dict[str, Tensor], batch: Dict[str, Tensor
     buff["normalized_obs"] = nobs
     del buff["obs"]
 
-    next_values, _ = mlp_forward(cfg, st, nobs[:, -1])  # :965-966 (values_only)
+    next_values, _, _ = model_forward(cfg, st, nobs[:, -1], buff["rnn_states"][:, -1])  # :965-966 (values_only)
     buff["values"][:, -1] = next_values  # :967
 
     if cfg.normalize_returns:  # :969-975
@@ -464,7 +534,26 @@ def calculate_losses(cfg: OracleCfg, params: Dict[str, Tensor], mb: Dict[str, Te
     clip_lo = 1.0 / clip_hi  # :546
     valids = mb["valids"]
 
-    values, logits = mlp_forward(cfg, params, mb["normalized_obs"])  # :553,:579,:586
+    head = encoder_forward(cfg, params, mb["normalized_obs"])  # forward_head :553
+    if cfg.use_rnn:
+        # :558-577 + rnn_utils.py:11-158.  The reference packs every run of steps between done-or-invalid boundaries
+        # into a PackedSequence; a segment that starts inside a chunk starts from a ZERO state (rnn_utils.py:143-149,
+        # is_new_episode), a segment at a chunk start from the stored rnn_state.  The same computation as a masked loop:
+        R = cfg.recurrence
+        n = head.shape[0] // R
+        x = head.view(n, R, -1)
+        doi = torch.logical_or(mb["dones"], ~valids).view(n, R).float()  # done_or_invalid :560
+        state = mb["rnn_states"].view(n, R, -1)[:, 0]
+        outs = []
+        for t in range(R):
+            if t > 0:
+                state = state * (1.0 - doi[:, t - 1]).unsqueeze(-1)
+            out, state = rnn_cell(cfg, params, x[:, t], state)
+            outs.append(out)
+        core = torch.stack(outs, 1).reshape(n * R, -1)
+    else:
+        core = head  # ModelCoreIdentity :579
+    values, logits = tail_forward(cfg, params, core)  # :586
     log_prob = cat_log_prob(logits, mb["actions"])  # :588
     ratio = torch.exp(log_prob - mb["log_prob_actions"])  # :589
     ratio = torch.clamp(ratio, 0.05, 20.0)  # :592

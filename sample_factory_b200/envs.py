@@ -83,6 +83,7 @@ class HostTapeVecEnv:
     observation batch host->device and the actions device->host, as it must for any CPU-simulated env."""
 
     is_gpu_env = False
+    static_outputs = True   # step() always returns the same device tensors -> the sampler can graph-capture around it
 
     def __init__(self, tape: np.ndarray, num_actions: int, device: torch.device, term_period: int = 37,
                  trunc_period: int = 11, env_index_offset: int = 0):
@@ -95,13 +96,16 @@ class HostTapeVecEnv:
         self.env_idx = np.arange(self.num_agents, dtype=np.int64) + env_index_offset
         n = self.num_agents
         self.actions_host = torch.empty(n, dtype=torch.int32).pin_memory()
-        self.rew_host = torch.empty(n, dtype=torch.float32).pin_memory()
-        self.term_host = torch.empty(n, dtype=torch.bool).pin_memory()
-        self.trunc_host = torch.empty(n, dtype=torch.bool).pin_memory()
+        # reward / terminated / truncated travel in ONE packed staging buffer (one H2D copy instead of three)
+        self.pack_host = torch.empty(6 * n, dtype=torch.uint8).pin_memory()
+        self.rew_host = self.pack_host[: 4 * n].view(torch.float32)
+        self.term_host = self.pack_host[4 * n: 5 * n].view(torch.bool)
+        self.trunc_host = self.pack_host[5 * n:].view(torch.bool)
         self.obs = torch.empty((n, self.obs_dim), dtype=torch.float32, device=device)
-        self.rew = torch.empty(n, dtype=torch.float32, device=device)
-        self.terminated = torch.empty(n, dtype=torch.bool, device=device)
-        self.truncated = torch.empty(n, dtype=torch.bool, device=device)
+        self.pack = torch.empty(6 * n, dtype=torch.uint8, device=device)
+        self.rew = self.pack[: 4 * n].view(torch.float32)
+        self.terminated = self.pack[4 * n: 5 * n].view(torch.bool)
+        self.truncated = self.pack[5 * n:].view(torch.bool)
         self.h2d_bytes = 0
         self.d2h_bytes = 0
 
@@ -126,8 +130,6 @@ class HostTapeVecEnv:
         self.t += 1
         # H2D: next observation batch + step results
         self.obs.copy_(self.tape[self.t % self.tape_len], non_blocking=True)
-        self.rew.copy_(self.rew_host, non_blocking=True)
-        self.terminated.copy_(self.term_host, non_blocking=True)
-        self.truncated.copy_(self.trunc_host, non_blocking=True)
+        self.pack.copy_(self.pack_host, non_blocking=True)
         self.h2d_bytes += self.obs.numel() * 4 + self.rew.numel() * 4 + 2 * self.num_agents
         return self.obs, self.rew, self.terminated, self.truncated

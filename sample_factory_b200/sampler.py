@@ -61,6 +61,12 @@ class DeviceSampler:
         self.noise: Optional[Tensor] = None  # [T, N, A] explicit Exp(1) noise (parity tests); None -> Philox
         self.use_cuda_graph = use_cuda_graph and getattr(env, "is_gpu_env", False)
         self._graph: Optional[torch.cuda.CUDAGraph] = None
+        # host envs: the env step is a host round trip, but the device work on either side of it is a fixed launch
+        # sequence per rollout step -> one small CUDA graph before and one after every env.step()
+        self.use_step_graphs = (use_cuda_graph and not getattr(env, "is_gpu_env", False)
+                                and getattr(env, "static_outputs", False))
+        self._step_graphs = None
+        self._eager_rollouts = 0
         self.kernel_launches_per_rollout = 0
 
     # ------------------------------------------------------------------------------------------------------------
@@ -98,9 +104,12 @@ class DeviceSampler:
         )
 
     def _env_and_post_step(self, t: int) -> None:
-        cfg, tr = self.cfg, self.traj
         obs, rew, terminated, truncated = self.env.step(self.env_actions)   # batched_sampling.py:316
         self.last_obs = obs
+        self._post_step(t, rew, terminated, truncated)
+
+    def _post_step(self, t: int, rew: Tensor, terminated: Tensor, truncated: Tensor) -> None:
+        cfg, tr = self.cfg, self.traj
         ops.sampler_post_step(rew, terminated, truncated, cfg.reward_scale, cfg.reward_clip, cfg.policy_id,
                               tr["rewards"][:, t], tr["dones"][:, t], tr["time_outs"][:, t], tr["policy_id"][:, t],
                               self.ep_return, self.ep_len, self.ep_min_raw, self.ep_max_raw,
@@ -129,6 +138,9 @@ class DeviceSampler:
         """Collect `rollout` steps for every env into the trajectory buffers (in place)."""
         if self.last_obs is None:
             self.reset()
+        if self.use_step_graphs:
+            self._rollout_step_graphs()
+            return
         if not self.use_cuda_graph:
             self._rollout_eager()
             return
@@ -148,6 +160,45 @@ class DeviceSampler:
             self._graph_launches = self.kernel_launches_per_rollout
         self._graph.replay()
         self.kernel_launches_per_rollout = self._graph_launches
+
+    def _rollout_step_graphs(self) -> None:
+        """Host-env rollout: graph(policy step t) -> env.step (host) -> graph(post step t)."""
+        assert self.noise is None, "explicit noise and CUDA graphs are mutually exclusive"
+        if self._eager_rollouts < 1:       # first rollout eager: warms up every kernel (attributes, module load)
+            self._rollout_eager()
+            self._eager_rollouts += 1
+            return
+        if self._step_graphs is None:
+            env = self.env
+            assert self.last_obs is env.obs, "host env must expose static output buffers (obs/rew/terminated/truncated)"
+            torch.cuda.synchronize()
+            n0 = ops.launch_count()
+            graphs = []
+            for t in range(self.T):
+                gp, gq = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gp):
+                    self._policy_step(t)
+                with torch.cuda.graph(gq):
+                    self._post_step(t, env.rew, env.terminated, env.truncated)
+                graphs.append((gp, gq))
+            self._step_graphs = graphs
+            self._graph_launches = ops.launch_count() - n0
+        for t in range(self.T):
+            gp, gq = self._step_graphs[t]
+            gp.replay()
+            obs, _, _, _ = self.env.step(self.env_actions)
+            assert obs is self.last_obs
+            gq.replay()
+        n0 = ops.launch_count()
+        self._finalize_trajectories()
+        self.kernel_launches_per_rollout = self._graph_launches + (ops.launch_count() - n0)
+
+    @property
+    def graph_replay_launches(self) -> int:
+        """Kernel launches per rollout that happen through graph replay (not seen by the library's launch counter)."""
+        if self._graph is not None or self._step_graphs is not None:
+            return self._graph_launches
+        return 0
 
     def pop_episode_stats(self) -> Dict[str, float]:
         """Aggregate of episodes finished since the last call (host sync; call at reporting time only)."""

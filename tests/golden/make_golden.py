@@ -232,8 +232,10 @@ def run_case(name: str, N: int, T: int, obs_dim: int, A: int, hidden, iters: int
               "reward_scale", "reward_clip", "max_policy_lag", "batch_size", "num_batches_per_epoch", "num_epochs",
               "recurrence", "vtrace_rho", "vtrace_c"]:
         out[f"cfg/{k}"] = np.float64(getattr(cfg, k))
-    for k in ["normalize_input", "normalize_returns", "value_bootstrap", "with_vtrace"]:
+    for k in ["normalize_input", "normalize_returns", "value_bootstrap", "with_vtrace", "use_rnn"]:
         out[f"cfg/{k}"] = np.bool_(getattr(cfg, k))
+    out["cfg/rnn_size"] = np.float64(cfg.rnn_size)
+    out["cfg/rnn_type"] = np.array(cfg.rnn_type)
     path = os.path.join(OUT_DIR, f"{name}.npz")
     np.savez_compressed(path, **out)
     print(f"wrote {path}: {os.path.getsize(path) / 1e6:.2f} MB, losses: {rec_losses[-1]}")
@@ -257,8 +259,22 @@ def kat_action_distribution():
     )
 
 
+_ONLY = set(sys.argv[1:])   # optional: regenerate only the named cases
+
+
+def _selected(fn):
+    def wrapper(name, *a, **k):
+        if _ONLY and name not in _ONLY:
+            return
+        return fn(name, *a, **k)
+    return wrapper
+
+
+run_case = _selected(run_case)
+
 if __name__ == "__main__":
-    kat_action_distribution()
+    if not _ONLY:
+        kat_action_distribution()
     # tiny dims, 2 iterations, invalids + value bootstrap + fixed-KL, 2 epochs x 2 minibatches
     run_case(
         "tiny_gae", N=32, T=8, obs_dim=16, A=8, hidden=[64, 64], iters=2,
@@ -271,6 +287,20 @@ if __name__ == "__main__":
         "tiny_vtrace", N=32, T=8, obs_dim=16, A=8, hidden=[64, 64], iters=2,
         overrides=dict(batch_size=128, num_batches_per_epoch=2, num_epochs=1, with_vtrace=True, recurrence=8,
                        normalize_returns=False),
+        poison=False,
+    )
+    # recurrent cores (model/core.py): GRU (the reference default) and LSTM, BPTT over the whole rollout with
+    # done-or-invalid resets (rnn_utils.py); poisoned data exercises the "invalid" boundaries
+    run_case(
+        "tiny_gru", N=32, T=8, obs_dim=16, A=8, hidden=[64], iters=2,
+        overrides=dict(batch_size=128, num_batches_per_epoch=2, num_epochs=2, use_rnn=True, rnn_type="gru", rnn_size=32,
+                       recurrence=8, value_bootstrap=True),
+        poison=True,
+    )
+    run_case(
+        "tiny_lstm", N=32, T=8, obs_dim=16, A=8, hidden=[64], iters=2,
+        overrides=dict(batch_size=128, num_batches_per_epoch=2, num_epochs=1, use_rnn=True, rnn_type="lstm", rnn_size=32,
+                       recurrence=4),
         poison=False,
     )
     # cfg-2 hyper-parameters and model (300 553 params) at a reduced env count
