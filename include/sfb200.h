@@ -224,13 +224,51 @@ int sfb200_heads_backward(const float* h, int64_t ldh, int64_t rows, int H, int 
 
 int64_t sfb200_linear_backward_workspace_bytes(int64_t M, int N, int K);
 /* backward of y = act(x.W^T + b) given dz = dL/d(pre-activation) [M,N]:
- *   dW[N,K] = dz^T . x ;  (db is produced by the kernel that made dz)
+ *   dW[N,K] = dz^T . x  (skipped if dW == NULL) ;  (db is produced by the kernel that made dz)
  *   if dx != NULL: dx[M,K] = (dz . W) * act_prev'(x)     (x is the previous layer's OUTPUT, act_prev its activation;
  *                                                       pass SFB200_ACT_NONE for the input layer)
  *   if db_prev != NULL: db_prev[k] = sum_i dx[i,k]  (bias gradient of the previous layer) */
 int sfb200_linear_backward(const float* dz, int64_t lddz, const float* x, int64_t ldx, const float* W, int64_t M,
                            int N, int K, int act_prev, float* dW, float* dx, int64_t lddx, float* db_prev,
                            int engine, void* workspace, void* stream);
+
+/* column sums out[n] = sum_m x[m, n] (bias gradients); workspace >= sfb200_colsum_workspace_bytes(N) */
+int64_t sfb200_colsum_workspace_bytes(int N);
+int sfb200_colsum(const float* x, int64_t ldx, int64_t M, int N, float* out, void* workspace, void* stream);
+
+/* ------------------------------------------------------------- recurrent core ---- */
+/* model/core.py:19-64 (ModelCoreRNN: nn.GRU / nn.LSTM, one layer).  The two gate GEMMs gi = x.W_ih^T + b_ih and
+ * gh = h.W_hh^T + b_hh are sfb200_linear_act_forward calls (act NONE); these kernels do the cell math.
+ * GRU (gates r,z,n):  r = s(gi_r+gh_r), z = s(gi_z+gh_z), n = tanh(gi_n + r*gh_n), h' = (1-z)*n + z*h
+ *   h_out  [M,H]   the new state / core output
+ *   h_next [M,H]   optional: h' with rows whose reset_next flag is set zeroed -- the next step's input state
+ *                  (batched_sampling.py:332-335 in the sampler, rnn_utils.py:143-149 in the learner)
+ *   gates  [M,3H]  optional save of (r,z,n) for the backward pass */
+int sfb200_gru_cell_forward(const float* gi, int64_t ldgi, const float* gh, int64_t ldgh, const float* h_in, int64_t ldh,
+                            float* h_out, int64_t ldo, float* h_next, int64_t ldn, const uint8_t* reset_next,
+                            int64_t reset_stride, float* gates, int64_t ldg, int64_t M, int H, void* stream);
+/* backward of one GRU step: dh = dh_out + (reset ? 0 : carry_a + carry_b)  (carry_* = gradient arriving from step t+1
+ * through the state: the GEMM part dgh(t+1).W_hh and the direct part dh(t+1)*z(t+1); `reset` is the flag applied
+ * between t and t+1).  Outputs dgi [M,3H], dgh [M,3H] and dh_direct = dh*z [M,H]. */
+int sfb200_gru_cell_backward(const float* dh_out, int64_t lddo, const float* carry_a, const float* carry_b, int64_t ldc,
+                             const uint8_t* reset, int64_t reset_stride, const float* gates, int64_t ldg, const float* gh,
+                             int64_t ldgh, const float* h_in, int64_t ldh, float* dgi, int64_t lddgi, float* dgh,
+                             int64_t lddgh, float* dh_direct, int64_t lddd, int64_t M, int H, void* stream);
+/* LSTM (gates i,f,g,o over gi+gh), state layout [h || c] of width 2H as in the reference (core.py:51-53):
+ *   c' = f*c + i*g ; h' = o*tanh(c') ; state_out = [h' || c'] ; state_next = state_out with reset rows zeroed ;
+ *   gates [M,4H] optional save of the activated gates */
+int sfb200_lstm_cell_forward(const float* gi, int64_t ldgi, const float* gh, int64_t ldgh, const float* state_in,
+                             int64_t lds, float* state_out, int64_t ldo, float* state_next, int64_t ldn,
+                             const uint8_t* reset_next, int64_t reset_stride, float* gates, int64_t ldg, int64_t M, int H,
+                             void* stream);
+/* backward of one LSTM step; dgates [M,4H] is the gradient of BOTH gi and gh; dc_in [M,H] is carried to step t-1 */
+int sfb200_lstm_cell_backward(const float* dh_out, int64_t lddo, const float* dh_carry, const float* dc_carry, int64_t ldc,
+                              const uint8_t* reset, int64_t reset_stride, const float* gates, int64_t ldg,
+                              const float* state_in, int64_t lds, const float* state_out, int64_t ldo, float* dgates,
+                              int64_t lddg, float* dc_in, int64_t lddc, int64_t M, int H, void* stream);
+/* dst[i,:] = reset[i] ? 0 : src[i,:]   (last_rnn_state = new_rnn_states * (1 - done), batched_sampling.py:332-335) */
+int sfb200_mask_rows(const float* src, int64_t src_stride, float* dst, int64_t dst_stride, const uint8_t* reset,
+                     int64_t reset_stride, int64_t rows, int dim, void* stream);
 
 /* ------------------------------------------------------------- optimizer ---- */
 /* learner.py:782-797: global grad-norm clip (torch clip_grad_norm_: coef = min(max_norm/(norm+1e-6), 1), skipped

@@ -301,7 +301,7 @@ int64_t sfb200_linear_backward_workspace_bytes(int64_t M, int N, int K) {
 int sfb200_linear_backward(const float* dz, int64_t lddz, const float* x, int64_t ldx, const float* W, int64_t M, int N,
                            int K, int act_prev, float* dW, float* dx, int64_t lddx, float* db_prev, int engine,
                            void* workspace, void* stream) {
-    SFB_CHECK_ARG(dz && x && W && dW && workspace && M > 0 && N > 0 && K > 0 && M <= 0x7fffffff,
+    SFB_CHECK_ARG(dz && x && W && (dW || dx) && workspace && M > 0 && N > 0 && K > 0 && M <= 0x7fffffff,
                   "linear_backward: bad arguments");
     SFB_CHECK_ARG(!db_prev || dx, "linear_backward: db_prev needs dx");
     cudaStream_t st = (cudaStream_t)stream;
@@ -319,7 +319,7 @@ int sfb200_linear_backward(const float* dz, int64_t lddz, const float* x, int64_
     }
     // dW[n,k] = sum_m dz[m,n] * x[m,k]   (both operands row-contiguous in the reduced dimension's rows)
     Epilogue none{0, 0, nullptr, nullptr, 0};
-    rc = gemm_simt(false, dz, lddz, false, x, ldx, dW, K, N, K, (int)M, splits, none, ws, st);
+    rc = dW ? gemm_simt(false, dz, lddz, false, x, ldx, dW, K, N, K, (int)M, splits, none, ws, st) : 0;
     if (rc) return rc;
     if (dx) {
         // dx[m,k] = (sum_n dz[m,n] * W[n,k]) * act_prev'(x[m,k])
@@ -329,6 +329,13 @@ int sfb200_linear_backward(const float* dz, int64_t lddz, const float* x, int64_
         if (db_prev) return colsum(dx, lddx, M, K, db_prev, ws_colsum, st);
     }
     return 0;
+}
+
+int64_t sfb200_colsum_workspace_bytes(int N) { return colsum_workspace_floats(N) * (int64_t)sizeof(float); }
+
+int sfb200_colsum(const float* x, int64_t ldx, int64_t M, int N, float* out, void* workspace, void* stream) {
+    SFB_CHECK_ARG(x && out && workspace && M > 0 && N > 0, "colsum: bad arguments");
+    return colsum(x, ldx, M, N, out, (float*)workspace, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -596,7 +596,7 @@ int tc_linear_backward(const float* dz, int64_t lddz, const float* x, int64_t ld
     // dW[n,k] = sum_m dz[m,n] x[m,k]: both operands are stored with the reduced index m as the row -> MN-major
     TcEpilogue none{0, 0, nullptr, nullptr, 0};
     const int splits = choose_splits(N, K, (int)M);
-    int rc = gemm_tc(true, dz, lddz, true, x, ldx, dW, K, N, K, (int)M, splits, none, ws, split3, st);
+    int rc = dW ? gemm_tc(true, dz, lddz, true, x, ldx, dW, K, N, K, (int)M, splits, none, ws, split3, st) : 0;
     if (rc) return rc;
     if (dx) {
         // dx[m,k] = (sum_n dz[m,n] W[n,k]) * act_prev'(x[m,k]): A = dz K-major, B(k, n) = W[n,k] MN-major

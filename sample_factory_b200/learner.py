@@ -21,6 +21,7 @@ from torch import Tensor
 from . import ops
 from .dist_utils import pooled_moments_
 from .model import PolicyModel
+from .rnn_core import RnnCore
 
 
 class KlAdaptiveScheduler:
@@ -124,7 +125,10 @@ class Learner:
             assert not cfg.normalize_returns, "normalize_returns is incompatible with V-trace (arguments.py:129-134)"
         assert cfg.exploration_loss == "entropy", "only the entropy exploration loss is on the device path"
         assert not cfg.shuffle_minibatches, "shuffle_minibatches is not on the device path yet"
-        assert len(spec.hidden) > 0, "the device path needs at least one hidden MLP layer"
+        assert len(spec.hidden) > 0 or spec.use_rnn, "the device path needs at least one hidden layer or an RNN core"
+        if spec.use_rnn:
+            assert cfg.rollout % cfg.recurrence == 0, "rollout must be a multiple of recurrence (learner.py:500)"
+            assert cfg.batch_size % cfg.recurrence == 0
 
         dev = self.device
         f32 = dict(dtype=torch.float32, device=dev)
@@ -163,11 +167,24 @@ class Learner:
         self.grad_norm_log = torch.zeros(n_mb_total, **f32)
         self.dp_partials = torch.zeros(3, dtype=torch.float64, device=dev)
         self.loss_ws = torch.empty(ops.loss_workspace_bytes(max(B, E)) // 8 + 8, dtype=torch.float64, device=dev)
-        H_last = spec.hidden[-1] if spec.hidden else D
-        self.heads_ws = torch.empty(ops.heads_backward_workspace_bytes(H_last, A) // 4 + 4, **f32)
+        self.heads_ws = torch.empty(ops.heads_backward_workspace_bytes(spec.tail_input_size, A) // 4 + 4, **f32)
         lin_ws = 4
         d = D
-        for h in spec.hidden:
+        for h in spec.encoder_mlp_layers:
+            lin_ws = max(lin_ws, ops.linear_backward_workspace_bytes(B, h, d) // 4 + 4)
+            d = h
+        self.rnn: Optional[RnnCore] = None
+        if spec.use_rnn:
+            # recurrent core (model/core.py): BPTT buffers for one minibatch + single-step buffers for the bootstrap value
+            self.rnn = RnnCore(model, engine)
+            self.rnn_bufs = self.rnn.alloc_bptt(B, cfg.recurrence)
+            self.rnn_boot = self.rnn.alloc_step(self.N)
+            self.boot_state_out = torch.empty((self.N, spec.rnn_state_size), **f32)
+            self.d_core = torch.empty((B, spec.rnn_size), **f32)
+            self.rnn_states_flat = torch.empty((E, spec.rnn_state_size), **f32)
+            lin_ws = max(lin_ws, self.rnn.lin_ws_bytes(B, cfg.recurrence, d) // 4 + 4)
+            d = spec.rnn_size
+        for h in spec.decoder_mlp_layers:
             lin_ws = max(lin_ws, ops.linear_backward_workspace_bytes(B, h, d) // 4 + 4)
             d = h
         self.lin_ws = torch.empty(lin_ws, **f32)
@@ -189,10 +206,18 @@ class Learner:
             total = pooled_moments_(bmean[:dim], bvar[:dim], rows, self.pg)
         ops.rms_merge(mean, var, count, bmean[:dim], bvar[:dim], float(total))
 
-    def _forward_hidden(self, x: Tensor, outs: List[Tensor]) -> Tensor:
-        for (W, b), out in zip(self.model.hidden_layers(), outs):
-            ops.linear_act_forward(x, W, b, out[: x.shape[0]], self.act, self.engine)
-            x = out[: x.shape[0]]
+    def _forward_hidden(self, x: Tensor, outs: List[Tensor], rnn_fn=None) -> Tensor:
+        """encoder MLP -> (recurrent core) -> decoder MLP (actor_critic.py:160-170). outs: one buffer per MLP layer."""
+        M = x.shape[0]
+        enc, dec = self.model.encoder_layers(), self.model.decoder_layers()
+        for i, (W, b) in enumerate(enc):
+            ops.linear_act_forward(x, W, b, outs[i][:M], self.act, self.engine)
+            x = outs[i][:M]
+        if self.rnn is not None:
+            x = rnn_fn(x)
+        for j, (W, b) in enumerate(dec):
+            ops.linear_act_forward(x, W, b, outs[len(enc) + j][:M], self.act, self.engine)
+            x = outs[len(enc) + j][:M]
         return x
 
     # ------------------------------------------------------------------------------------------------------------
@@ -219,7 +244,10 @@ class Learner:
         else:
             ops.normalize_obs(obs2d, nobs2d, None, None, spec.obs_subtract_mean, inv_scale)
         # bootstrap value for step T (:965-967): forward on normalized_obs[:, T] in place (strided rows)
-        x = self._forward_hidden(self.normalized_obs[:, T], self.h_boot)
+        boot_rnn = None
+        if self.rnn is not None:
+            boot_rnn = lambda head: self.rnn.step(head, batch["rnn_states"][:, T], self.boot_state_out, self.rnn_boot)
+        x = self._forward_hidden(self.normalized_obs[:, T], self.h_boot, boot_rnn)
         Wv, bv = m.critic
         Wa, ba = m.actor
         ops.heads_forward(x, Wv, bv, Wa, ba, values=batch["values"][:, T], values_stride=batch["values"].stride(0))
@@ -232,6 +260,9 @@ class Learner:
         ops.copy_rows(self.normalized_obs.view(N, (T + 1) * D)[:, : T * D], self.obs_flat_compact.view(N, T * D))
         ops.copy_rows(batch["values"][:, :T], self.values_old)
         self.valids_flat.copy_(batch["valids"][:, :T])
+        if self.rnn is not None:
+            S = spec.rnn_state_size
+            ops.copy_rows(batch["rnn_states"].view(N, (T + 1) * S)[:, : T * S], self.rnn_states_flat.view(N, T * S))
         if spec.normalize_returns and not cfg.with_vtrace:                                          # :1018-1019
             r = self.returns.view(-1, 1)
             self._update_rms(r, m.ret_mean, m.ret_var, m.ret_count, self.rmean, self.rvar)
@@ -256,7 +287,11 @@ class Learner:
         valids = self.valids_flat.view(self.E)[sl]
         v_old = self.values_old.view(self.E)[sl]
         # forward (:553-579)
-        x = self._forward_hidden(x0, self.h)
+        mb_rnn = None
+        if self.rnn is not None:
+            mb_rnn = lambda head: self.rnn.forward_bptt(head, self.rnn_states_flat[sl], batch["dones"].view(self.E)[sl],
+                                                        valids, self.rnn_bufs)
+        x = self._forward_hidden(x0, self.h, mb_rnn)
         Wv, bv = m.critic
         Wa, ba = m.actor
         ops.heads_forward(x, Wv, bv, Wa, ba, values=self.mb_values, values_stride=1, logits=self.mb_logits,
@@ -280,25 +315,45 @@ class Learner:
                              cfg.ppo_clip_ratio, cfg.ppo_clip_value, cfg.exploration_loss_coeff, cfg.value_loss_coeff,
                              cfg.kl_loss_coeff, 1.0, self.dlogits, self.dvalues, self.loss_stats, self.loss_ws)
         self.loss_stats_log[log_idx].copy_(self.loss_stats)
-        # backward through heads and hidden layers
+        # backward: heads -> decoder MLP -> (recurrent core, BPTT) -> encoder MLP
         g = m.grads
-        hidden = m.hidden_layers()
-        hgrads = m.hidden_layer_grads()
-        L = len(hidden)
-        last_in = self.h[L - 1]
-        ops.heads_backward(last_in, Wv, Wa, self.dlogits, self.dvalues, self.act, self.dz[L - 1],
+        none = ops.ACT["none"]
+        enc, dec = m.encoder_layers(), m.decoder_layers()
+        genc, gdec = m.encoder_layers(grads=True), m.decoder_layers(grads=True)
+        Le, Ld = len(enc), len(dec)
+        rnn = self.rnn is not None
+        tail_is_mlp = Ld > 0 or not rnn            # is the tensor feeding the heads an activated MLP output?
+        tail_dz = self.dz[Le + Ld - 1] if tail_is_mlp else self.d_core
+        tail_db = gdec[-1][1] if Ld > 0 else (None if rnn else genc[-1][1])
+        ops.heads_backward(x, Wv, Wa, self.dlogits, self.dvalues, self.act if tail_is_mlp else none, tail_dz,
                            g["critic_linear.weight"].view(-1), g["critic_linear.bias"],
                            g["action_parameterization.distribution_linear.weight"],
-                           g["action_parameterization.distribution_linear.bias"], hgrads[L - 1][1], self.heads_ws)
-        for li in range(L - 1, -1, -1):
-            W, _ = hidden[li]
-            dW, _db = hgrads[li]
-            x_in = self.h[li - 1] if li > 0 else x0
-            if li > 0:
-                ops.linear_backward(self.dz[li], x_in, W, self.act, dW, self.dz[li - 1], hgrads[li - 1][1], self.engine,
-                                    self.lin_ws)
+                           g["action_parameterization.distribution_linear.bias"], tail_db, self.heads_ws)
+        for j in range(Ld - 1, -1, -1):
+            W, dW = dec[j][0], gdec[j][0]
+            if j > 0:
+                x_in, act_prev, dx, dbp = self.h[Le + j - 1], self.act, self.dz[Le + j - 1], gdec[j - 1][1]
+            elif rnn:
+                x_in, act_prev, dx, dbp = self.rnn_bufs["core_out"], none, self.d_core, None
             else:
-                ops.linear_backward(self.dz[li], x_in, W, ops.ACT["none"], dW, None, None, self.engine, self.lin_ws)
+                x_in, act_prev, dx, dbp = self.h[Le - 1], self.act, self.dz[Le - 1], genc[-1][1]
+            ops.linear_backward(self.dz[Le + j], x_in, W, act_prev, dW, dx, dbp, self.engine, self.lin_ws)
+        if rnn:
+            dgi_all = self.rnn.backward_bptt(self.d_core, self.rnn_bufs, self.lin_ws)
+            W_ih = m.rnn_params()[0]
+            dW_ih = m.rnn_params(grads=True)[0]
+            if Le > 0:
+                ops.linear_backward(dgi_all, self.h[Le - 1], W_ih, self.act, dW_ih, self.dz[Le - 1], genc[-1][1],
+                                    self.engine, self.lin_ws)
+            else:
+                ops.linear_backward(dgi_all, x0, W_ih, none, dW_ih, None, None, self.engine, self.lin_ws)
+        for li in range(Le - 1, -1, -1):
+            W, dW = enc[li][0], genc[li][0]
+            if li > 0:
+                ops.linear_backward(self.dz[li], self.h[li - 1], W, self.act, dW, self.dz[li - 1], genc[li - 1][1],
+                                    self.engine, self.lin_ws)
+            else:
+                ops.linear_backward(self.dz[li], x0, W, none, dW, None, None, self.engine, self.lin_ws)
         # gradient all-reduce: ONE NCCL call on the flat buffer; mean over ranks is folded into the sums:
         # each rank's loss already divides by the GLOBAL valid count, so the rank gradients simply add up.
         self._allreduce(m.grad)

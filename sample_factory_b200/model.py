@@ -30,11 +30,34 @@ class ModelSpec:
     normalize_returns: bool = True
     obs_subtract_mean: float = 0.0
     obs_scale: float = 1.0
+    use_rnn: bool = False        # model/core.py: ModelCoreRNN (one layer) between encoder and decoder
+    rnn_type: str = "gru"
+    rnn_size: int = 512
 
     @property
     def hidden(self) -> List[int]:
         # ModelCoreIdentity (use_rnn=False) passes the encoder output straight to the decoder MLP
         return list(self.encoder_mlp_layers) + list(self.decoder_mlp_layers)
+
+    @property
+    def rnn_state_size(self) -> int:
+        """model/model_utils.py:11-24"""
+        if not self.use_rnn:
+            return 1
+        return self.rnn_size * (2 if self.rnn_type == "lstm" else 1)
+
+    @property
+    def rnn_gates(self) -> int:
+        return 4 if self.rnn_type == "lstm" else 3
+
+    @property
+    def tail_input_size(self) -> int:
+        """width of the tensor that feeds critic_linear / distribution_linear"""
+        if self.decoder_mlp_layers:
+            return self.decoder_mlp_layers[-1]
+        if self.use_rnn:
+            return self.rnn_size
+        return self.encoder_mlp_layers[-1]
 
     def param_shapes(self) -> List[Tuple[str, Tuple[int, ...]]]:
         """(reference state_dict key, shape) in nn.Module.parameters() order."""
@@ -44,6 +67,11 @@ class ModelSpec:
             out.append((f"encoder.encoders.obs.mlp_head.{2 * i}.weight", (h, d)))
             out.append((f"encoder.encoders.obs.mlp_head.{2 * i}.bias", (h,)))
             d = h
+        if self.use_rnn:
+            G, H = self.rnn_gates, self.rnn_size
+            out += [("core.core.weight_ih_l0", (G * H, d)), ("core.core.weight_hh_l0", (G * H, H)),
+                    ("core.core.bias_ih_l0", (G * H,)), ("core.core.bias_hh_l0", (G * H,))]
+            d = H
         for i, h in enumerate(self.decoder_mlp_layers):
             out.append((f"decoder.mlp.{2 * i}.weight", (h, d)))
             out.append((f"decoder.mlp.{2 * i}.bias", (h,)))
@@ -102,7 +130,11 @@ class PolicyModel:
         g = torch.Generator(device="cpu").manual_seed(seed)
         for name in self.names:
             p = self.params[name]
-            if name.endswith(".bias"):
+            if name.startswith("core.core."):
+                # RNNs keep the PyTorch default init U(-1/sqrt(H), 1/sqrt(H)) (actor_critic.py:83-88)
+                k = 1.0 / math.sqrt(self.spec.rnn_size)
+                p.copy_((torch.rand(p.shape, generator=g) * 2 - 1) * k)
+            elif name.endswith(".bias"):
                 p.zero_()
             else:
                 w = torch.empty(p.shape, dtype=torch.float32)
@@ -119,6 +151,22 @@ class PolicyModel:
         for i in range(len(self.spec.decoder_mlp_layers)):
             out.append((self.params[f"decoder.mlp.{2 * i}.weight"], self.params[f"decoder.mlp.{2 * i}.bias"]))
         return out
+
+    def encoder_layers(self, grads: bool = False) -> List[Tuple[Tensor, Tensor]]:
+        src = self.grads if grads else self.params
+        return [(src[f"encoder.encoders.obs.mlp_head.{2 * i}.weight"], src[f"encoder.encoders.obs.mlp_head.{2 * i}.bias"])
+                for i in range(len(self.spec.encoder_mlp_layers))]
+
+    def decoder_layers(self, grads: bool = False) -> List[Tuple[Tensor, Tensor]]:
+        src = self.grads if grads else self.params
+        return [(src[f"decoder.mlp.{2 * i}.weight"], src[f"decoder.mlp.{2 * i}.bias"])
+                for i in range(len(self.spec.decoder_mlp_layers))]
+
+    def rnn_params(self, grads: bool = False) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+        """(W_ih [G*H, in], W_hh [G*H, H], b_ih, b_hh) of the one-layer GRU/LSTM core"""
+        src = self.grads if grads else self.params
+        return (src["core.core.weight_ih_l0"], src["core.core.weight_hh_l0"], src["core.core.bias_ih_l0"],
+                src["core.core.bias_hh_l0"])
 
     def hidden_layer_grads(self) -> List[Tuple[Tensor, Tensor]]:
         out = []

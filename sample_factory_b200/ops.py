@@ -255,11 +255,11 @@ def linear_backward_workspace_bytes(M: int, N: int, K: int) -> int:
     return lib().query("sfb200_linear_backward_workspace_bytes", M, N, K)
 
 
-def linear_backward(dz: Tensor, x: Tensor, W: Tensor, act_prev: int, dW: Tensor, dx: Optional[Tensor],
+def linear_backward(dz: Tensor, x: Tensor, W: Tensor, act_prev: int, dW: Optional[Tensor], dx: Optional[Tensor],
                     db_prev: Optional[Tensor], engine: int, workspace: Tensor) -> None:
     M, N = dz.shape
     K = x.shape[1]
-    assert W.shape == (N, K) and W.is_contiguous() and dW.is_contiguous()
+    assert W.shape == (N, K) and W.is_contiguous() and (dW is None or dW.is_contiguous())
     assert workspace.numel() * workspace.element_size() >= linear_backward_workspace_bytes(M, N, K)
     lib().call("sfb200_linear_backward", _p(dz, F32), dz.stride(0), _p(x, F32), x.stride(0), _p(W, F32), M, N, K,
                act_prev, _p(dW, F32), _p(dx, F32), 0 if dx is None else dx.stride(0), _p(db_prev, F32), engine,
@@ -276,3 +276,69 @@ def clip_adam_step(p: Tensor, g: Tensor, m: Tensor, v: Tensor, step: int, lr: fl
     lib().call("sfb200_clip_adam_step", _p(p, F32), _p(g, F32), _p(m, F32), _p(v, F32), p.numel(), step, lr, beta1,
                beta2, eps, max_grad_norm, _p(lr_scale_num, F64), _p(lr_scale_den, F64), _p(grad_norm_out, F32),
                workspace.data_ptr(), _stream())
+
+
+# ------------------------------------------------------------------------------------------------ recurrent core
+def _rs(t: Optional[Tensor]) -> int:
+    return 0 if t is None else (t.stride(0) if t.dim() > 0 else 1)
+
+
+def colsum_workspace_bytes(N: int) -> int:
+    return lib().query("sfb200_colsum_workspace_bytes", N)
+
+
+def colsum(x: Tensor, out: Tensor, workspace: Tensor) -> None:
+    M, N = x.shape
+    assert workspace.numel() * workspace.element_size() >= colsum_workspace_bytes(N)
+    lib().call("sfb200_colsum", _p(x, F32), x.stride(0), M, N, _p(out, F32), workspace.data_ptr(), _stream())
+
+
+def gru_cell_forward(gi: Tensor, gh: Tensor, h_in: Tensor, h_out: Tensor, h_next: Optional[Tensor] = None,
+                     reset_next: Optional[Tensor] = None, gates: Optional[Tensor] = None) -> None:
+    """All arguments are 2-D views with free row strides; reset_next is a 1-D bool view (any stride)."""
+    M, H = h_in.shape
+    lib().call("sfb200_gru_cell_forward", _p(gi, F32), gi.stride(0), _p(gh, F32), gh.stride(0), _p(h_in, F32),
+               h_in.stride(0), _p(h_out, F32), h_out.stride(0), None if h_next is None else h_next.data_ptr(),
+               _rs(h_next), None if reset_next is None else reset_next.data_ptr(), _rs(reset_next),
+               None if gates is None else gates.data_ptr(), _rs(gates), M, H, _stream())
+
+
+def gru_cell_backward(dh_out: Optional[Tensor], carry_a: Optional[Tensor], carry_b: Optional[Tensor],
+                      reset: Optional[Tensor], gates: Tensor, gh: Tensor, h_in: Tensor, dgi: Tensor, dgh: Tensor,
+                      dh_direct: Tensor) -> None:
+    M, H = h_in.shape
+    lib().call("sfb200_gru_cell_backward", None if dh_out is None else dh_out.data_ptr(), _rs(dh_out),
+               None if carry_a is None else carry_a.data_ptr(), None if carry_b is None else carry_b.data_ptr(),
+               _rs(carry_a), None if reset is None else reset.data_ptr(), _rs(reset), _p(gates, F32), gates.stride(0),
+               _p(gh, F32), gh.stride(0), _p(h_in, F32), h_in.stride(0), _p(dgi, F32), dgi.stride(0), _p(dgh, F32),
+               dgh.stride(0), _p(dh_direct, F32), dh_direct.stride(0), M, H, _stream())
+
+
+def lstm_cell_forward(gi: Tensor, gh: Tensor, state_in: Tensor, state_out: Tensor, state_next: Optional[Tensor] = None,
+                      reset_next: Optional[Tensor] = None, gates: Optional[Tensor] = None) -> None:
+    M, H2 = state_in.shape
+    lib().call("sfb200_lstm_cell_forward", _p(gi, F32), gi.stride(0), _p(gh, F32), gh.stride(0), _p(state_in, F32),
+               state_in.stride(0), _p(state_out, F32), state_out.stride(0),
+               None if state_next is None else state_next.data_ptr(), _rs(state_next),
+               None if reset_next is None else reset_next.data_ptr(), _rs(reset_next),
+               None if gates is None else gates.data_ptr(), _rs(gates), M, H2 // 2, _stream())
+
+
+def lstm_cell_backward(dh_out: Optional[Tensor], dh_carry: Optional[Tensor], dc_carry: Optional[Tensor],
+                       reset: Optional[Tensor], gates: Tensor, state_in: Tensor, state_out: Tensor, dgates: Tensor,
+                       dc_in: Tensor) -> None:
+    M, H2 = state_in.shape
+    if dh_carry is not None and dc_carry is not None:
+        assert dh_carry.stride(0) == dc_carry.stride(0)
+    lib().call("sfb200_lstm_cell_backward", None if dh_out is None else dh_out.data_ptr(), _rs(dh_out),
+               None if dh_carry is None else dh_carry.data_ptr(), None if dc_carry is None else dc_carry.data_ptr(),
+               _rs(dh_carry if dh_carry is not None else dc_carry), None if reset is None else reset.data_ptr(), _rs(reset),
+               _p(gates, F32), gates.stride(0), _p(state_in, F32), state_in.stride(0), _p(state_out, F32),
+               state_out.stride(0), _p(dgates, F32), dgates.stride(0), _p(dc_in, F32), dc_in.stride(0), M, H2 // 2,
+               _stream())
+
+
+def mask_rows(src: Tensor, dst: Tensor, reset: Tensor) -> None:
+    rows, dim = src.shape
+    lib().call("sfb200_mask_rows", _p(src, F32), src.stride(0), _p(dst, F32), dst.stride(0), reset.data_ptr(),
+               _rs(reset), rows, dim, _stream())

@@ -24,6 +24,7 @@ from torch import Tensor
 
 from . import ops
 from .model import PolicyModel
+from .rnn_core import RnnCore
 
 
 class DeviceSampler:
@@ -47,6 +48,12 @@ class DeviceSampler:
         self.h = [torch.empty((self.N, h), **f32) for h in spec.hidden]
         self.env_actions = torch.empty(self.N, dtype=torch.int32, device=dev)
         self.last_rnn_state = torch.zeros((self.N, traj["rnn_states"].shape[2]), **f32)
+        self.rnn: Optional[RnnCore] = None
+        if spec.use_rnn:
+            assert traj["rnn_states"].shape[2] == spec.rnn_state_size
+            self.rnn = RnnCore(model, engine)
+            self.rnn_step_bufs = self.rnn.alloc_step(self.N)
+            self.new_rnn_state = torch.zeros((self.N, spec.rnn_state_size), **f32)
         # policy version lives on the device so a captured graph always stamps the current one (inference_worker.py:332)
         self.policy_version = torch.zeros(1, **f32)
         # episode accounting on device (batched_sampling.py:201-204, :215-287)
@@ -85,9 +92,15 @@ class DeviceSampler:
         ops.sampler_pre_step(self.last_obs, tr["obs"][:, t], self.last_rnn_state, tr["rnn_states"][:, t], self.x_norm,
                              mean, var, spec.obs_subtract_mean, inv_scale)
         x = self.x_norm
-        for (W, b), out in zip(m.hidden_layers(), self.h):
-            ops.linear_act_forward(x, W, b, out, self.act, self.engine)
-            x = out
+        enc, dec = m.encoder_layers(), m.decoder_layers()
+        for i, (W, b) in enumerate(enc):
+            ops.linear_act_forward(x, W, b, self.h[i], self.act, self.engine)
+            x = self.h[i]
+        if self.rnn is not None:   # ModelCoreRNN.forward (core.py:37-64), one step
+            x = self.rnn.step(x, self.last_rnn_state, self.new_rnn_state, self.rnn_step_bufs)
+        for j, (W, b) in enumerate(dec):
+            ops.linear_act_forward(x, W, b, self.h[len(enc) + j], self.act, self.engine)
+            x = self.h[len(enc) + j]
         Wv, bv = m.critic
         Wa, ba = m.actor
         noise_t = None if self.noise is None else self.noise[t]
@@ -115,7 +128,10 @@ class DeviceSampler:
                               self.ep_return, self.ep_len, self.ep_min_raw, self.ep_max_raw,
                               cfg.env_frameskip if cfg.summaries_use_frameskip else 1, self.episode_stats,
                               self.step_counter)
-        # non-recurrent core: new_rnn_states == rnn_states (core.py:76-77), times (1-done) stays zero (:334-335)
+        if self.rnn is not None:
+            # last_rnn_state = new_rnn_states * (1 - done)  (batched_sampling.py:332-335); the dones were just written
+            ops.mask_rows(self.new_rnn_state, self.last_rnn_state, tr["dones"][:, t])
+        # non-recurrent core: new_rnn_states == rnn_states (core.py:76-77), times (1-done) stays zero
 
     def advance_rollouts(self, t: int) -> None:
         """One env step for all envs: policy step then env step (reference: inference then advance_rollouts)."""

@@ -91,12 +91,13 @@ class Runner:
         self.env = create_env(cfg.env, cfg, env_config)
         spec = ModelSpec(self.env.obs_dim, self.env.num_actions, list(cfg.encoder_mlp_layers),
                          list(cfg.decoder_mlp_layers), cfg.nonlinearity, cfg.normalize_input, cfg.normalize_returns,
-                         cfg.obs_subtract_mean, cfg.obs_scale)
-        assert not cfg.use_rnn, "the device path is the non-recurrent MLP policy (SURVEY section 8); use --use_rnn=False"
+                         cfg.obs_subtract_mean, cfg.obs_scale, bool(cfg.use_rnn), cfg.rnn_type, cfg.rnn_size)
+        assert cfg.rnn_num_layers == 1, "the device path implements the one-layer recurrent core"
         self.model = PolicyModel(spec, self.device, seed=cfg.seed or 0, policy_init_gain=cfg.policy_init_gain)
         N = self.env.num_agents
         self.engine = select_engine(cfg)
-        self.traj = alloc_trajectory_tensors(spec.obs_dim, spec.num_actions, N, cfg.rollout, self.device)
+        self.traj = alloc_trajectory_tensors(spec.obs_dim, spec.num_actions, N, cfg.rollout, self.device,
+                                             rnn_size=spec.rnn_state_size)
         self.sampler = DeviceSampler(cfg, self.env, self.model, self.traj, engine=self.engine,
                                      use_cuda_graph=bool(getattr(cfg, "cuda_graph", True)),
                                      philox_seed=(cfg.seed or 0) * 1000003 + self.rank)

@@ -21,11 +21,11 @@ def make_cfg(ocfg: O.OracleCfg, **over):
               "ppo_clip_ratio", "ppo_clip_value", "exploration_loss_coeff", "value_loss_coeff", "kl_loss_coeff",
               "max_grad_norm", "learning_rate", "adam_eps", "adam_beta1", "adam_beta2", "normalize_input",
               "normalize_returns", "value_bootstrap", "with_vtrace", "vtrace_rho", "vtrace_c", "reward_scale",
-              "reward_clip", "max_policy_lag", "nonlinearity", "obs_subtract_mean", "obs_scale"]:
+              "reward_clip", "max_policy_lag", "nonlinearity", "obs_subtract_mean", "obs_scale", "use_rnn", "rnn_type",
+              "rnn_size"]:
         setattr(cfg, k, getattr(ocfg, k))
     cfg.encoder_mlp_layers = list(ocfg.encoder_mlp_layers)
     cfg.decoder_mlp_layers = list(ocfg.decoder_mlp_layers)
-    cfg.use_rnn = False
     cfg.async_rl = False
     for k, v in over.items():
         setattr(cfg, k, v)
@@ -44,10 +44,10 @@ def build(ocfg: O.OracleCfg, N: int, state, tape, dev, engine="simt", graph=Fals
     cfg = make_cfg(ocfg)
     spec = ModelSpec(ocfg.obs_dim, ocfg.num_actions, list(ocfg.encoder_mlp_layers), list(ocfg.decoder_mlp_layers),
                      ocfg.nonlinearity, ocfg.normalize_input, ocfg.normalize_returns, ocfg.obs_subtract_mean,
-                     ocfg.obs_scale)
+                     ocfg.obs_scale, ocfg.use_rnn, ocfg.rnn_type, ocfg.rnn_size)
     model = PolicyModel(spec, dev)
     model.load_state_dict(state, strict=False)
-    traj = alloc_trajectory_tensors(ocfg.obs_dim, ocfg.num_actions, N, ocfg.rollout, dev)
+    traj = alloc_trajectory_tensors(ocfg.obs_dim, ocfg.num_actions, N, ocfg.rollout, dev, rnn_size=spec.rnn_state_size)
     env = TapeVecEnv(tape.to(dev).contiguous(), ocfg.num_actions)
     sampler = DeviceSampler(cfg, env, model, traj, engine=ops.ENGINES[engine], use_cuda_graph=graph)
     learner = Learner(cfg, model, N, engine=ops.ENGINES[engine])
@@ -69,8 +69,11 @@ def _need(engine):
         pytest.skip("tcgen05 engine not available")
 
 
+GOLDEN_CASES = ["tiny_gae", "tiny_vtrace", "tiny_gru", "tiny_lstm", "cfg2_small"]
+
+
 @pytest.mark.parametrize("engine", ENGINES)
-@pytest.mark.parametrize("name", ["tiny_gae", "tiny_vtrace", "cfg2_small"])
+@pytest.mark.parametrize("name", GOLDEN_CASES)
 def test_rollout_matches_reference_golden(name, engine):
     """Sampler vs the REFERENCE's own trajectories (same weights, same obs tape, same Exp(1) noise)."""
     _need(engine)
@@ -90,8 +93,9 @@ def test_rollout_matches_reference_golden(name, engine):
         ref = {k: torch.from_numpy(z[f"it{it}/traj/{k}"]) for k in
                ["obs", "actions", "action_logits", "log_prob_actions", "values", "policy_version", "rewards", "dones",
                 "time_outs", "policy_id", "rnn_states"]}
-        for k in ["obs", "rewards", "dones", "time_outs", "rnn_states"]:
+        for k in ["obs", "rewards", "dones", "time_outs"]:
             assert torch.equal(got[k].view(ref[k].shape), ref[k]), k
+        np.testing.assert_allclose(got["rnn_states"].numpy(), ref["rnn_states"].numpy(), atol=TOL)
         if not poisoned:
             assert torch.equal(got["policy_id"], ref["policy_id"])
             assert torch.equal(got["policy_version"], ref["policy_version"])
@@ -104,7 +108,7 @@ def test_rollout_matches_reference_golden(name, engine):
 
 
 @pytest.mark.parametrize("engine", ENGINES)
-@pytest.mark.parametrize("name", ["tiny_gae", "tiny_vtrace", "cfg2_small"])
+@pytest.mark.parametrize("name", GOLDEN_CASES)
 def test_learner_matches_reference_golden(name, engine):
     """Learner.train on the REFERENCE's trajectories: returns / advantages / loss terms / post-Adam weights /
     normalizer statistics against what the reference itself computed."""

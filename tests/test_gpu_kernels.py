@@ -505,6 +505,73 @@ def test_clip_adam_step(dev, n, max_norm):
         np.testing.assert_allclose(vd.cpu().numpy(), v.numpy(), atol=1e-9, rtol=1e-5)
 
 
+# ----------------------------------------------------------------------------------------------- recurrent core
+@pytest.mark.parametrize("rnn_type", ["gru", "lstm"])
+@pytest.mark.parametrize("M,H,IN", [(64, 32, 48), (1024, 512, 512), (333, 96, 20)])
+def test_rnn_cell_forward_backward(dev, rnn_type, M, H, IN):
+    """One recurrent step (cell kernels + the two gate GEMMs) against the oracle's written-out nn.GRU / nn.LSTM cell
+    (oracle.rnn_cell, pinned to the reference's PackedSequence path by the tiny_gru / tiny_lstm goldens) incl. autograd
+    gradients, with a reset mask on the outgoing state and carried gradients from a fictitious next step."""
+    ops = _ops()
+    ocfg = O.OracleCfg(obs_dim=IN, num_actions=4, encoder_mlp_layers=[IN], use_rnn=True, rnn_type=rnn_type, rnn_size=H)
+    st = O.init_state(ocfg, seed=2)
+    G = 4 if rnn_type == "lstm" else 3
+    S = O.rnn_state_size(ocfg)
+    x = torch.randn(M, IN, generator=g(80)).requires_grad_(True)
+    state = (torch.randn(M, S, generator=g(81)) * 0.5).requires_grad_(True)
+    reset = torch.rand(M, generator=g(82)) < 0.3
+    params = {k: st[k].clone().requires_grad_(True) for k in [O.RNN_W_IH, O.RNN_W_HH, O.RNN_B_IH, O.RNN_B_HH]}
+    out, new_state = O.rnn_cell(ocfg, params, x, state)
+    nxt = new_state * (1.0 - reset.float()).unsqueeze(-1)
+    d_out = torch.randn(M, H, generator=g(83))
+    d_next = torch.randn(M, S, generator=g(84))
+    ((out * d_out).sum() + (nxt * d_next).sum()).backward()
+
+    W_ih, W_hh, b_ih, b_hh = (st[k].to(dev) for k in [O.RNN_W_IH, O.RNN_W_HH, O.RNN_B_IH, O.RNN_B_HH])
+    xd, sd = x.detach().to(dev), state.detach().to(dev)
+    gi = torch.empty(M, G * H, device=dev)
+    gh = torch.empty(M, G * H, device=dev)
+    ops.linear_act_forward(xd, W_ih, b_ih, gi, ops.ACT["none"], ops.GEMM_SIMT)
+    ops.linear_act_forward(sd[:, :H], W_hh, b_hh, gh, ops.ACT["none"], ops.GEMM_SIMT)
+    s_out = torch.empty(M, S, device=dev)
+    s_next = torch.empty(M, S, device=dev)
+    gates = torch.empty(M, G * H, device=dev)
+    rd = reset.to(dev)
+    dgi = torch.empty(M, G * H, device=dev)
+    dgh = torch.empty(M, G * H, device=dev)
+    direct = torch.empty(M, H, device=dev)
+    dnd = d_next.to(dev)
+    if rnn_type == "lstm":
+        ops.lstm_cell_forward(gi, gh, sd, s_out, s_next, rd, gates)
+        # carries: gradient wrt next state's h part and c part (already "after the mask" in the oracle graph)
+        ops.lstm_cell_backward(d_out.to(dev), dnd[:, :H].contiguous(), dnd[:, H:].contiguous(), rd, gates, sd, s_out, dgh, direct)
+        dgi = dgh
+    else:
+        ops.gru_cell_forward(gi, gh, sd, s_out, s_next, rd, gates)
+        ops.gru_cell_backward(d_out.to(dev), dnd, None, rd, gates, gh, sd, dgi, dgh, direct)
+    np.testing.assert_allclose(s_out.cpu().numpy(), new_state.detach().numpy(), atol=TOL)
+    np.testing.assert_allclose(s_next.cpu().numpy(), nxt.detach().numpy(), atol=TOL)
+    # gradients: d x = dgi . W_ih ; d state_h = dgh . W_hh + direct ; d state_c (lstm) = direct
+    dx = dgi.cpu().double() @ st[O.RNN_W_IH].double()
+    dh = dgh.cpu().double() @ st[O.RNN_W_HH].double()
+    np.testing.assert_allclose(dx.float().numpy(), x.grad.numpy(), atol=2e-5, rtol=1e-4)
+    if rnn_type == "lstm":
+        np.testing.assert_allclose(dh.float().numpy(), state.grad[:, :H].numpy(), atol=2e-5, rtol=1e-4)
+        np.testing.assert_allclose(direct.cpu().numpy(), state.grad[:, H:].numpy(), atol=2e-5, rtol=1e-4)
+    else:
+        np.testing.assert_allclose((dh + direct.cpu().double()).float().numpy(), state.grad.numpy(), atol=2e-5, rtol=1e-4)
+    np.testing.assert_allclose((dgi.cpu().double().t() @ x.detach().double()).float().numpy(), params[O.RNN_W_IH].grad.numpy(),
+                               atol=2e-4, rtol=1e-4)
+    np.testing.assert_allclose(dgh.cpu().double().sum(0).float().numpy(), params[O.RNN_B_HH].grad.numpy(), atol=2e-4, rtol=1e-4)
+    # mask_rows + colsum helpers
+    masked = torch.empty(M, S, device=dev)
+    ops.mask_rows(s_out, masked, rd)
+    assert torch.equal(masked, s_next)
+    cs = torch.empty(G * H, device=dev)
+    ops.colsum(dgh, cs, torch.empty(ops.colsum_workspace_bytes(G * H) // 4 + 4, device=dev))
+    np.testing.assert_allclose(cs.cpu().numpy(), dgh.cpu().double().sum(0).float().numpy(), atol=1e-4, rtol=1e-4)
+
+
 def test_bad_arguments_raise(dev):
     """Error behaviour: argument violations surface as Python exceptions carrying the library message."""
     ops = _ops()
