@@ -211,6 +211,15 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def _ncu_traffic(key):
+        """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
+        (profiles/traffic.json records the capture it came from); None when no capture is committed."""
+        try:
+            with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "traffic.json")) as f:
+                return json.load(f)[key]["traffic_bytes"]
+        except (OSError, KeyError, ValueError):
+            return None
+
     def max_over_ranks(x: float) -> float:
         if world == 1:
             return x
@@ -290,7 +299,7 @@ def run_ours(args):
         ach = k["work"] / (k["avg_ms"] * 1e-3) / 1e12
         roofline = dict(kernel=f"learner layer-2 forward GEMM [32768x512x512] ({engine_name})", bound="tensor",
                         achieved=ach, peak=peaks["tflops_sustained"], unit="TFLOP/s", frac=ach / peaks["tflops_sustained"],
-                        traffic=None, avg_kernel_ms=k["avg_ms"], launches_timed=k["launches"],
+                        traffic=_ncu_traffic("gemm_fwd_l2"), avg_kernel_ms=k["avg_ms"], launches_timed=k["launches"],
                         peak_source=peaks["source"] + ", bf16 sustained (kernel timed inside a long step)",
                         note="fp32-parity GEMM: 3xTF32 costs 3 tf32 MMAs per product and tf32 peak is half of bf16, so "
                              "the ceiling of this engine is peak/6; the simt engine runs on CUDA cores (no tensor pipe)")
