@@ -235,7 +235,8 @@ class PolicyModel:
             state[i] = dict(step=torch.tensor(float(step)), exp_avg=self.exp_avg[o : o + k].view(shp).clone(),
                             exp_avg_sq=self.exp_avg_sq[o : o + k].view(shp).clone())
         group = dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=0, amsgrad=False, maximize=False, foreach=None,
-                     capturable=False, differentiable=False, fused=None, params=list(range(len(self.names))))
+                     capturable=False, differentiable=False, fused=None, decoupled_weight_decay=False,
+                     params=list(range(len(self.names))))
         return dict(state=state, param_groups=[group])
 
     def load_optimizer_state_dict(self, osd: dict) -> int:

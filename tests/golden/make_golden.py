@@ -70,7 +70,8 @@ class RefTapeEnv(gym.Env):
         pass
 
 
-def run_case(name: str, N: int, T: int, obs_dim: int, A: int, hidden, iters: int, overrides: dict, poison: bool):
+def run_case(name: str, N: int, T: int, obs_dim: int, A: int, hidden, iters: int, overrides: dict, poison: bool,
+             save_checkpoint: bool = False):
     torch.manual_seed(1234)
     np.random.seed(1234)
     tape_len = T * iters + 1
@@ -224,6 +225,16 @@ def run_case(name: str, N: int, T: int, obs_dim: int, A: int, hidden, iters: int
         # hand the buffers back (sync mode: Batcher releases after training, batcher.py:220-267)
         runner.traj_buffer_queue.put(sl)
 
+    if save_checkpoint:
+        # the reference's own checkpoint file after the last iteration (Learner.save, learner.py:323-360): the fixture for
+        # the checkpoint-compatibility tests
+        import shutil
+
+        assert learner.save()
+        files = Learner.get_checkpoints(Learner.checkpoint_dir(cfg, 0))
+        shutil.copy(files[-1], os.path.join(OUT_DIR, f"{name}_checkpoint.pth"))
+        print("checkpoint fixture:", os.path.basename(files[-1]))
+
     meta = dict(N=N, T=T, obs_dim=obs_dim, A=A, hidden=list(hidden), iters=iters, poison=poison, **overrides)
     out["meta"] = np.array(repr(meta))
     # a few flags the oracle needs, straight from the reference cfg object
@@ -280,7 +291,7 @@ if __name__ == "__main__":
         "tiny_gae", N=32, T=8, obs_dim=16, A=8, hidden=[64, 64], iters=2,
         overrides=dict(batch_size=128, num_batches_per_epoch=2, num_epochs=2, value_bootstrap=True,
                        kl_loss_coeff=0.1, reward_scale=0.7, reward_clip=0.5),
-        poison=True,
+        poison=True, save_checkpoint=True,
     )
     # V-trace variant (requires recurrence == rollout, no returns normalisation: arguments.py:129-134,193-194)
     run_case(

@@ -179,3 +179,92 @@ def test_data_parallel_host_logic_gloo_world2(tmp_path):
     for p in procs:
         out, _ = p.communicate(timeout=240)
         assert p.returncode == 0, out
+
+
+# ------------------------------------------------------------------------------------ checkpoint compatibility (8f-2)
+def _tiny_gae_model():
+    from sample_factory_b200.model import ModelSpec, PolicyModel
+    from tests.golden_utils import load_case
+
+    z, meta, ocfg = load_case("tiny_gae")
+    spec = ModelSpec(ocfg.obs_dim, ocfg.num_actions, list(ocfg.encoder_mlp_layers), list(ocfg.decoder_mlp_layers),
+                     ocfg.nonlinearity, ocfg.normalize_input, ocfg.normalize_returns)
+    return z, meta, ocfg, PolicyModel(spec, torch.device("cpu"))
+
+
+def _ckpt_cfg(tmp_path, ocfg):
+    from sample_factory_b200.cfg import default_cfg
+
+    cfg = default_cfg()
+    cfg.train_dir, cfg.experiment = str(tmp_path), "ck"
+    cfg.adam_eps, cfg.adam_beta1, cfg.adam_beta2 = ocfg.adam_eps, ocfg.adam_beta1, ocfg.adam_beta2
+    return cfg
+
+
+def test_loads_checkpoint_written_by_the_reference(tmp_path):
+    """tests/golden/tiny_gae_checkpoint.pth is the file the reference's own Learner.save() (learner.py:323-360) wrote
+    after the last golden iteration: resume from it must restore weights, normaliser state, Adam moments, counters."""
+    import shutil
+
+    from sample_factory_b200.checkpoint import checkpoint_dir, load_checkpoint
+    from tests.golden_utils import GOLDEN_DIR, state_from
+
+    z, meta, ocfg, model = _tiny_gae_model()
+    cfg = _ckpt_cfg(tmp_path, ocfg)
+    shutil.copy(os.path.join(GOLDEN_DIR, "tiny_gae_checkpoint.pth"),
+                os.path.join(checkpoint_dir(cfg, 0), "checkpoint_000000008_512.pth"))
+    info = load_checkpoint(cfg, model, torch.device("cpu"))
+    assert info["train_step"] == 8 and info["env_steps"] == 512 and info["opt_step"] == 8
+    assert info["curr_lr"] == pytest.approx(ocfg.learning_rate)
+    ref_state = state_from(z, f"it{meta['iters'] - 1}/state/")
+    got = model.state_dict()
+    assert set(got.keys()) == set(ref_state.keys())
+    for k, v in ref_state.items():
+        assert got[k].dtype == v.dtype and torch.equal(got[k].view(v.shape), v), k
+    ref_ck = torch.load(os.path.join(GOLDEN_DIR, "tiny_gae_checkpoint.pth"), weights_only=False)
+    osd = model.optimizer_state_dict(info["opt_step"], 1e-4, (0.9, 0.999), 1e-6)
+    for i, st in ref_ck["optimizer"]["state"].items():
+        assert torch.equal(osd["state"][i]["exp_avg"], st["exp_avg"])
+        assert torch.equal(osd["state"][i]["exp_avg_sq"], st["exp_avg_sq"])
+
+
+def test_checkpoint_we_write_has_the_reference_layout(tmp_path):
+    """What the reference's loader does with a checkpoint (learner.py:257-310): torch.load -> actor_critic.load_state_dict
+    (strict) -> optimizer.load_state_dict.  Ours must go through the same calls: same top-level keys / types as the
+    reference's file, same model keys / shapes / dtypes, and torch.optim.Adam must accept the optimizer dict."""
+    from types import SimpleNamespace
+
+    from sample_factory_b200.checkpoint import get_checkpoints, load_checkpoint, save_checkpoint
+    from tests.golden_utils import GOLDEN_DIR, state_from
+
+    z, meta, ocfg, model = _tiny_gae_model()
+    model.load_state_dict(state_from(z, "it0/state/"), strict=True)
+    model.exp_avg.normal_(generator=torch.Generator().manual_seed(0))
+    model.exp_avg_sq.uniform_(generator=torch.Generator().manual_seed(1))
+    cfg = _ckpt_cfg(tmp_path, ocfg)
+    learner = SimpleNamespace(policy_id=0, train_step=12, env_steps=768, opt_step=12, curr_lr=5e-5)
+    path = save_checkpoint(cfg, model, learner)
+    assert os.path.basename(path) == "checkpoint_000000012_768.pth"
+    ours = torch.load(path, weights_only=False)
+    ref = torch.load(os.path.join(GOLDEN_DIR, "tiny_gae_checkpoint.pth"), weights_only=False)
+    assert list(ours.keys()) == list(ref.keys())
+    assert {k: type(v) for k, v in ours.items() if k != "model"} == {k: type(v) for k, v in ref.items() if k != "model"}
+    assert list(ours["model"].keys()) == list(ref["model"].keys())       # same ORDER: nn.Module.load_state_dict is by name,
+    for k, v in ref["model"].items():                                    # optimizer state is by parameter index
+        assert ours["model"][k].shape == v.shape and ours["model"][k].dtype == v.dtype, k
+    assert set(ours["optimizer"]["param_groups"][0].keys()) == set(ref["optimizer"]["param_groups"][0].keys())
+    params = [torch.nn.Parameter(v.clone()) for k, v in ours["model"].items() if "normalizer" not in k]
+    opt = torch.optim.Adam(params, lr=1e-4, betas=(0.9, 0.999), eps=1e-6)
+    opt.load_state_dict(ours["optimizer"])
+    assert opt.param_groups[0]["lr"] == 5e-5 and float(opt.state[params[0]]["step"]) == 12.0
+    # keep_checkpoints pruning (learner.py:353-358) and resume of our own file
+    for step in (13, 14, 15):
+        learner.train_step = learner.opt_step = step
+        save_checkpoint(cfg, model, learner)
+    assert len(get_checkpoints(os.path.dirname(path))) == cfg.keep_checkpoints
+    z2, _, _, model2 = _tiny_gae_model()
+    info = load_checkpoint(cfg, model2, torch.device("cpu"))
+    assert info["train_step"] == 15 and info["opt_step"] == 15 and info["curr_lr"] == 5e-5
+    a, b = model.optimizer_state_dict(15, 0, (0, 0), 0)["state"], model2.optimizer_state_dict(15, 0, (0, 0), 0)["state"]
+    assert torch.equal(model2.flat, model.flat)
+    assert all(torch.equal(a[i]["exp_avg"], b[i]["exp_avg"]) and torch.equal(a[i]["exp_avg_sq"], b[i]["exp_avg_sq"]) for i in a)
