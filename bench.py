@@ -172,11 +172,11 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------------------------------- our arm
-def make_cfg(env_name: str, engine: str, cuda_graph: bool):
+def make_cfg(env_name: str, engine: str, cuda_graph: bool, async_rl: bool = False):
     from sample_factory_b200.cfg import parse_full_cfg, parse_sf_args
 
     argv = [f"--env={env_name}", "--experiment=bench", "--train_dir=/tmp/sfb200_bench", "--restart_behavior=overwrite",
-            "--use_rnn=False", "--async_rl=False", "--serial_mode=True", "--batched_sampling=True", "--num_workers=1",
+            "--use_rnn=False", f"--async_rl={async_rl}", "--serial_mode=True", "--batched_sampling=True", "--num_workers=1",
             "--num_envs_per_worker=1", "--worker_num_splits=1", f"--rollout={ROLLOUT}", f"--batch_size={BATCH}",
             f"--num_batches_per_epoch={N_MINIBATCH}", f"--num_epochs={N_EPOCHS}", "--encoder_mlp_layers", "512", "512",
             "--env_gpu_actions=True", "--env_gpu_observations=True", "--seed=0", f"--gemm_engine={engine}",
@@ -312,8 +312,48 @@ def run_ours(args):
                               frac=ach / peaks["hbm_gbs"], avg_kernel_ms=k["avg_ms"], algorithmic_bytes=k["work"]))
     sampler_launches = runner.sampler.kernel_launches_per_rollout
     learner_launches = runner.learner.kernel_launches
+
+    # sampler-only pass: the rollout's share of the step and its fraction of the HBM roofline (574
+    # algorithmic bytes per env-step -- obs read + trajectory record)
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    s0.record()
+    for _ in range(args.steps):
+        runner.sampler.rollout()
+    s1.record()
+    barrier()
+    rollout_ms = s0.elapsed_time(s1) / args.steps
+    samp_bytes = 574.0 * N_ENVS * ROLLOUT
+    samp_gbs = samp_bytes / (rollout_ms * 1e-3) / 1e9
+    roof_sampler = dict(kernel="sampler rollout (32 policy steps: normalise, 2 GEMMs, heads+sample, env, post-step)",
+                        bound="hbm", achieved=samp_gbs, peak=peaks["hbm_gbs"], unit="GB/s", frac=samp_gbs / peaks["hbm_gbs"],
+                        algorithmic_bytes=samp_bytes, rollout_ms=rollout_ms, share_of_step=rollout_ms / ms_per_step,
+                        note="a 4096-env policy step moves 2.35 MB and 2.45 GFLOP: the rollout is bound by the dependent "
+                             "kernel chain of each step (latency), not by HBM bandwidth")
     del runner
     torch.cuda.empty_cache()
+
+    # ------------------------------------------------------------------ async double-buffered arm (async_rl=True)
+    async_info = None
+    if not args.no_async:
+        arunner = Runner(make_cfg("synthetic_tape", args.engine, not args.no_graph, async_rl=True))
+        arunner.init()
+        for _ in range(args.warmup):
+            arunner.iteration()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        a0.record()
+        for _ in range(args.steps):
+            arunner.iteration()
+        a1.record()
+        barrier()
+        a_ms = max_over_ranks(a0.elapsed_time(a1))
+        async_info = dict(value=world * N_ENVS * ROLLOUT * args.steps / (a_ms / 1e3), unit=UNIT, ms_per_step=a_ms / args.steps,
+                          policy_lag_sgd_steps=N_MINIBATCH * N_EPOCHS,
+                          note="async_rl=True (the reference's default mode): rollout i+1 on a high-priority stream with a "
+                               "weight snapshot while the learner trains on rollout i; same kernels, same work per step")
+        del arunner
+        torch.cuda.empty_cache()
 
     # ------------------------------------------------------------------ end-to-end arm (host env, H2D/D2H inside)
     e2e = None
@@ -361,7 +401,8 @@ def run_ours(args):
                                          "activations 4x64 MB + workspaces) exceeds the 126 MB L2; no explicit flush"),
                    clocks=clock_info, e2e=e2e, gpu_launches=int(gpu_launches),
                    launches_per_step=dict(sampler_rollout=int(sampler_launches), learner_train=int(learner_launches)),
-                   roofline=roofline, roofline_secondary=roof2, cpu_baseline=cpu_baseline)
+                   roofline=roofline, roofline_sampler=roof_sampler, roofline_secondary=roof2, async_rl=async_info,
+                   cpu_baseline=cpu_baseline)
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()
@@ -377,6 +418,7 @@ def main():
     ap.add_argument("--engine", default="auto", choices=["auto", "simt", "3xtf32", "tf32"])
     ap.add_argument("--no-graph", dest="no_graph", action="store_true")
     ap.add_argument("--no-e2e", dest="no_e2e", action="store_true")
+    ap.add_argument("--no-async", dest="no_async", action="store_true")
     ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

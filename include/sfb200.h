@@ -118,13 +118,16 @@ int sfb200_sampler_pre_step(const float* obs, int64_t n_envs, int dim, float* tr
  * per-env ep_return[n], ep_len[n] (int32), ep_min_raw[n], ep_max_raw[n] and, for episodes finishing this step, the
  * accumulators stats[0..4] = {count, sum_return, sum_len, sum_min_raw_reward, sum_max_raw_reward} (doubles) -- the
  * reference's per-episode report (:228-234) aggregated on device, no host sync.  step_counter (optional, device
- * int64) is incremented by one: the sampler's policy-step count, used as the Philox offset of the next step. */
+ * int64) is incremented by one: the sampler's policy-step count, used as the Philox offset of the next step.
+ * fin_return_t / fin_len_t (optional, element [0,t] of [N,T] buffers, same element stride): the per-episode report
+ * itself -- return and length of the episode that finished at this step, NaN / -1 where none did (what the
+ * reference sends as episodic stats messages; consumed by EvalSamplingAPI.eval_stats). */
 int sfb200_sampler_post_step(const float* rew, const uint8_t* terminated, const uint8_t* truncated, int64_t n_envs,
                              float reward_scale, float reward_clip, int32_t policy_id, float* traj_rewards_t,
                              uint8_t* traj_dones_t, uint8_t* traj_time_outs_t, int32_t* traj_policy_id_t,
                              int64_t traj_stride, float* ep_return, int32_t* ep_len, float* ep_min_raw,
                              float* ep_max_raw, int32_t len_increment, double* stats, int64_t* step_counter,
-                             void* stream);
+                             float* fin_return_t, int32_t* fin_len_t, void* stream);
 
 /* strided row copy dst[i*dst_stride + 0..dim) = src[i*src_stride + 0..dim) (_finalize_trajectories :289-296) */
 int sfb200_copy_rows(const float* src, int64_t src_stride, float* dst, int64_t dst_stride, int64_t rows, int dim,

@@ -132,7 +132,7 @@ def parse_sf_args(argv: Optional[List[str]] = None, evaluation: bool = False) ->
         for name, typ, default in [("fps", int, 0), ("eval_env_frameskip", int, None), ("no_render", str2bool, False),
                                    ("save_video", str2bool, False), ("max_num_episodes", int, int(1e9)),
                                    ("max_num_frames", int, int(1e9)), ("eval_deterministic", str2bool, False),
-                                   ("sample_env_episodes", int, 256)]:
+                                   ("sample_env_episodes", int, 256), ("csv_folder_name", str, None)]:
             parser.add_argument(f"--{name}", type=typ, default=default)
     partial_cfg, _ = parser.parse_known_args(argv)
     return parser, partial_cfg

@@ -129,7 +129,8 @@ __global__ void __launch_bounds__(256) post_step_kernel(const float* __restrict_
                                                         float* __restrict__ ep_ret, int32_t* __restrict__ ep_len,
                                                         float* __restrict__ ep_min, float* __restrict__ ep_max,
                                                         int32_t len_inc, double* __restrict__ stats,
-                                                        int64_t* __restrict__ step_counter) {
+                                                        int64_t* __restrict__ step_counter,
+                                                        float* __restrict__ fin_ret, int32_t* __restrict__ fin_len) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (step_counter && i == 0) *step_counter += 1;
     double c = 0.0, s_ret = 0.0, s_len = 0.0, s_min = 0.0, s_max = 0.0;
@@ -148,6 +149,10 @@ __global__ void __launch_bounds__(256) post_step_kernel(const float* __restrict_
             float er = ep_ret[i] + r_raw;
             int32_t el = ep_len[i] + len_inc;
             float mn = fminf(ep_min[i], r_raw), mx = fmaxf(ep_max[i], r_raw);
+            if (fin_ret) {
+                fin_ret[i * stride] = done ? er : __int_as_float(0x7fc00000);
+                fin_len[i * stride] = done ? el : -1;
+            }
             if (done) {
                 c = 1.0; s_ret = er; s_len = el; s_min = mn; s_max = mx;
                 er = 0.f; el = 0; mn = INFINITY; mx = -INFINITY;
@@ -284,7 +289,8 @@ int sfb200_sampler_post_step(const float* rew, const uint8_t* terminated, const 
                              uint8_t* traj_dones_t, uint8_t* traj_time_outs_t, int32_t* traj_policy_id_t,
                              int64_t traj_stride, float* ep_return, int32_t* ep_len, float* ep_min_raw,
                              float* ep_max_raw, int32_t len_increment, double* stats, int64_t* step_counter,
-                             void* stream) {
+                             float* fin_return_t, int32_t* fin_len_t, void* stream) {
+    SFB_CHECK_ARG(!fin_return_t == !fin_len_t, "sampler_post_step: fin_return_t and fin_len_t come together");
     SFB_CHECK_ARG(rew && terminated && truncated && traj_rewards_t && traj_dones_t && traj_time_outs_t &&
                       traj_policy_id_t, "sampler_post_step: NULL argument");
     SFB_CHECK_ARG(!ep_return || (ep_len && ep_min_raw && ep_max_raw), "sampler_post_step: episode arrays incomplete");
@@ -292,7 +298,7 @@ int sfb200_sampler_post_step(const float* rew, const uint8_t* terminated, const 
     post_step_kernel<<<(unsigned)ceil_div(n_envs, 256), 256, 0, (cudaStream_t)stream>>>(
         rew, terminated, truncated, n_envs, reward_scale, reward_clip, policy_id, traj_rewards_t, traj_dones_t,
         traj_time_outs_t, traj_policy_id_t, traj_stride, ep_return, ep_len, ep_min_raw, ep_max_raw, len_increment,
-        ep_return ? stats : nullptr, step_counter);
+        ep_return ? stats : nullptr, step_counter, ep_return ? fin_return_t : nullptr, fin_len_t);
     SFB_LAUNCH_OK();
     return 0;
 }

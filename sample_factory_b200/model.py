@@ -141,6 +141,26 @@ class PolicyModel:
                 torch.nn.init.orthogonal_(w, gain=gain, generator=g)
                 p.copy_(w)
 
+    # ---- inference-side weight snapshot (async_rl: the reference's inference workers hold their own copy of the
+    # weights and refresh it when the learner publishes a new version, model_sharing.py:17-94, inference_worker.py:207-233)
+    def inference_copy(self) -> "PolicyModel":
+        twin = object.__new__(PolicyModel)
+        twin.spec, twin.device = self.spec, self.device
+        twin.numel_padded, twin.num_params, twin.names, twin._slices = self.numel_padded, self.num_params, self.names, self._slices
+        twin.flat = self.flat.clone()
+        twin.grad = twin.exp_avg = twin.exp_avg_sq = None
+        twin.params = {n: twin.flat[o : o + math.prod(shp)].view(shp) for n, (o, shp) in self._slices.items()}
+        twin.grads = {}
+        for k in ("obs_mean", "obs_var", "obs_count", "ret_mean", "ret_var", "ret_count"):
+            setattr(twin, k, getattr(self, k).clone())
+        return twin
+
+    def copy_weights_from(self, other: "PolicyModel") -> None:
+        """Refresh this snapshot from the learner's model (three D2D copies on the current stream)."""
+        self.flat.copy_(other.flat)
+        self.obs_mean.copy_(other.obs_mean)
+        self.obs_var.copy_(other.obs_var)
+
     # ---- layer access ---------------------------------------------------------------------------------------
     def hidden_layers(self) -> List[Tuple[Tensor, Tensor]]:
         """[(W [out,in], b [out]), ...] for encoder then decoder MLP layers."""

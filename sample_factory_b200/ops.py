@@ -144,16 +144,19 @@ def sampler_post_step(rew: Tensor, terminated: Tensor, truncated: Tensor, reward
                       policy_id: int, traj_rewards_t: Tensor, traj_dones_t: Tensor, traj_time_outs_t: Tensor,
                       traj_policy_id_t: Tensor, ep_return: Optional[Tensor], ep_len: Optional[Tensor],
                       ep_min_raw: Optional[Tensor], ep_max_raw: Optional[Tensor], len_increment: int,
-                      stats: Optional[Tensor], step_counter: Optional[Tensor] = None) -> None:
+                      stats: Optional[Tensor], step_counter: Optional[Tensor] = None,
+                      fin_return_t: Optional[Tensor] = None, fin_len_t: Optional[Tensor] = None) -> None:
     n = rew.numel()
     stride = traj_rewards_t.stride(0)
+    assert fin_return_t is None or (fin_return_t.stride(0) == stride and fin_len_t.stride(0) == stride)
     assert traj_dones_t.stride(0) == stride and traj_time_outs_t.stride(0) == stride
     assert traj_policy_id_t.stride(0) == stride
     lib().call("sfb200_sampler_post_step", _p(rew, F32), _p(terminated, U8), _p(truncated, U8), n, reward_scale,
                reward_clip, policy_id, traj_rewards_t.data_ptr(), traj_dones_t.data_ptr(),
                traj_time_outs_t.data_ptr(), traj_policy_id_t.data_ptr(), stride, _p(ep_return, F32), _p(ep_len, I32),
                _p(ep_min_raw, F32), _p(ep_max_raw, F32), len_increment, _p(stats, F64), _p(step_counter, I64),
-               _stream())
+               None if fin_return_t is None else fin_return_t.data_ptr(),
+               None if fin_len_t is None else fin_len_t.data_ptr(), _stream())
 
 
 def copy_rows(src: Tensor, dst: Tensor) -> None:

@@ -29,7 +29,7 @@ from .rnn_core import RnnCore
 
 class DeviceSampler:
     def __init__(self, cfg, env, model: PolicyModel, traj: Dict[str, Tensor], engine: int = ops.GEMM_SIMT,
-                 use_cuda_graph: bool = False, philox_seed: int = 0):
+                 use_cuda_graph: bool = False, philox_seed: int = 0, record_episodes: bool = False):
         self.cfg = cfg
         self.env = env
         self.model = model
@@ -62,6 +62,10 @@ class DeviceSampler:
         self.ep_min_raw = torch.full((self.N,), float("inf"), **f32)
         self.ep_max_raw = torch.full((self.N,), float("-inf"), **f32)
         self.episode_stats = torch.zeros(8, dtype=torch.float64, device=dev)
+        # optional per-episode report (the reference's episodic stats messages, batched_sampling.py:228-234): return /
+        # length of the episode that ended at [n, t], NaN / -1 elsewhere
+        self.fin_return = torch.full((self.N, self.T), float("nan"), **f32) if record_episodes else None
+        self.fin_len = torch.full((self.N, self.T), -1, dtype=torch.int32, device=dev) if record_episodes else None
         self.last_obs: Optional[Tensor] = None
         self.philox_seed = philox_seed
         self.step_counter = torch.zeros(1, dtype=torch.int64, device=dev)  # policy steps taken = Philox offset
@@ -127,7 +131,9 @@ class DeviceSampler:
                               tr["rewards"][:, t], tr["dones"][:, t], tr["time_outs"][:, t], tr["policy_id"][:, t],
                               self.ep_return, self.ep_len, self.ep_min_raw, self.ep_max_raw,
                               cfg.env_frameskip if cfg.summaries_use_frameskip else 1, self.episode_stats,
-                              self.step_counter)
+                              self.step_counter,
+                              None if self.fin_return is None else self.fin_return[:, t],
+                              None if self.fin_len is None else self.fin_len[:, t])
         if self.rnn is not None:
             # last_rnn_state = new_rnn_states * (1 - done)  (batched_sampling.py:332-335); the dones were just written
             ops.mask_rows(self.new_rnn_state, self.last_rnn_state, tr["dones"][:, t])
@@ -215,6 +221,13 @@ class DeviceSampler:
         if self._graph is not None or self._step_graphs is not None:
             return self._graph_launches
         return 0
+
+    def finished_episodes(self):
+        """(returns, lengths) of the episodes that ended during the LAST rollout, in (step, env) order -- host sync."""
+        assert self.fin_return is not None, "construct the sampler with record_episodes=True"
+        ret, ln = self.fin_return.t().cpu().numpy(), self.fin_len.t().cpu().numpy()
+        m = ln >= 0
+        return ret[m], ln[m]
 
     def pop_episode_stats(self) -> Dict[str, float]:
         """Aggregate of episodes finished since the last call (host sync; call at reporting time only)."""

@@ -7,9 +7,13 @@
 The reference's Runner wires rollout workers, inference workers, a batcher and a learner through signal/slot event
 loops across processes (runner.py:626-678).  Here the same components are three objects on ONE GPU stream pair and the
 control loop is ~30 lines: rollout -> train -> (stats, checkpoint), repeated until the env-step / time budget is used.
-Sync mode (async_rl=False) samples and learns back to back on one stream; async mode double-buffers the trajectory
-store and runs the sampler for iteration i+1 on a second stream while the learner consumes iteration i, the sampler
-using a snapshot of the weights (policy lag >= 1, exactly what the reference's async mode gives).
+Sync mode (async_rl=False) samples and learns back to back on one stream.  Async mode (async_rl=True, the reference's
+default: "collect the next batch while the learner trains on the current one", cfg.py:53-61) is a fork-join per
+iteration on two CUDA streams: the sampler (high-priority stream) collects rollout i+1 into its own trajectory set with
+a SNAPSHOT of the weights while the learner trains on rollout i; at the join the learner's stream copies the fresh
+trajectories across (the reference Batcher's copy, batcher.py:170-218; 45 MB D2D) and refreshes the snapshot.  Samples
+are therefore one iteration (num_epochs x num_batches_per_epoch SGD steps) old when they are trained on -- recorded per
+sample in traj["policy_version"] and masked by max_policy_lag exactly as in the reference (learner.py:950-953).
 """
 from __future__ import annotations
 
@@ -63,6 +67,8 @@ class Runner:
         self.msg_handlers: Dict[str, List[Callable]] = {}
         self.fps_history: deque = deque(maxlen=64)
         self.initialized = False
+        self.rollout_hook: Optional[Callable[[int], None]] = None   # called with the rollout index before each rollout
+        self.rollouts_started = 0
 
     # ---- reference-compatible hooks --------------------------------------------------------------------------
     def register_observer(self, observer) -> None:
@@ -98,13 +104,25 @@ class Runner:
         self.engine = select_engine(cfg)
         self.traj = alloc_trajectory_tensors(spec.obs_dim, spec.num_actions, N, cfg.rollout, self.device,
                                              rnn_size=spec.rnn_state_size)
-        self.sampler = DeviceSampler(cfg, self.env, self.model, self.traj, engine=self.engine,
-                                     use_cuda_graph=bool(getattr(cfg, "cuda_graph", True)),
-                                     philox_seed=(cfg.seed or 0) * 1000003 + self.rank)
-        self.learner = Learner(cfg, self.model, N, engine=self.engine)
         if self.world_size > 1:
             # identical replicas: broadcast rank 0's initial weights
             torch.distributed.broadcast(self.model.flat, src=0)
+        self.async_rl = bool(cfg.async_rl)
+        if self.async_rl:
+            # the sampler owns a second trajectory set and a weight snapshot; it runs on its own high-priority stream
+            self.sampler_model = self.model.inference_copy()
+            self.sampler_traj = alloc_trajectory_tensors(spec.obs_dim, spec.num_actions, N, cfg.rollout, self.device,
+                                                         rnn_size=spec.rnn_state_size)
+            self.sampler_stream = torch.cuda.Stream(device=self.device, priority=-1)
+            self.ev_rollout, self.ev_join = torch.cuda.Event(), torch.cuda.Event()
+            self.snapshot_version = 0
+            self.rollouts_in_flight = 0
+        else:
+            self.sampler_model, self.sampler_traj = self.model, self.traj
+        self.sampler = DeviceSampler(cfg, self.env, self.sampler_model, self.sampler_traj, engine=self.engine,
+                                     use_cuda_graph=bool(getattr(cfg, "cuda_graph", True)),
+                                     philox_seed=(cfg.seed or 0) * 1000003 + self.rank)
+        self.learner = Learner(cfg, self.model, N, engine=self.engine)
         if cfg.restart_behavior == "resume":
             ck = load_checkpoint(cfg, self.model, self.device)
             if ck is not None:
@@ -112,6 +130,9 @@ class Runner:
                 self.learner.opt_step = ck["opt_step"]
                 self.learner.curr_lr = ck.get("curr_lr", cfg.learning_rate)
                 self.env_steps = ck["env_steps"]
+                if self.async_rl:
+                    self.sampler_model.copy_weights_from(self.model)
+                    self.snapshot_version = self.learner.train_step
         if self.rank == 0:
             with open(os.path.join(experiment_dir(cfg), "config.json"), "w") as f:
                 json.dump({k: v for k, v in vars(cfg).items() if _jsonable(v)}, f, indent=2)
@@ -119,11 +140,61 @@ class Runner:
         self.initialized = True
         return StatusCode.SUCCESS
 
+    def load_state_dict(self, state_dict, strict: bool = False) -> None:
+        """Replace the policy weights / normaliser state (warm start); the sampler's snapshot follows."""
+        self.model.load_state_dict(state_dict, strict=strict)
+        if self.async_rl:
+            self.sampler_model.copy_weights_from(self.model)
+
+    def _before_rollout(self) -> None:
+        if self.rollout_hook is not None:
+            self.rollout_hook(self.rollouts_started)
+        self.rollouts_started += 1
+
     def iteration(self) -> None:
         """One sampler rollout + one learner update (the unit the FPS counter advances by N*T env steps)."""
+        if self.async_rl:
+            return self._iteration_async()
+        self._before_rollout()
         self.sampler.set_policy_version(self.learner.train_step)
         self.sampler.rollout()
         self.learner.train(self.traj)
+        self.env_steps = self.learner.env_steps
+
+    def _sample_on_side_stream(self) -> None:
+        with torch.cuda.stream(self.sampler_stream):
+            self.sampler_stream.wait_event(self.ev_join)        # snapshot + trajectory hand-off of the last join done
+            self._before_rollout()
+            self.sampler.set_policy_version(self.snapshot_version)
+            self.sampler.rollout()
+            self.ev_rollout.record(self.sampler_stream)
+
+    def _join(self) -> None:
+        """Learner stream: wait for the rollout, take its trajectories (Batcher copy) and publish the new weights."""
+        main = torch.cuda.current_stream()
+        main.wait_event(self.ev_rollout)
+        for k, v in self.sampler_traj.items():
+            self.traj[k].copy_(v, non_blocking=True)
+        self.sampler_model.copy_weights_from(self.model)
+        self.snapshot_version = self.learner.train_step
+        self.ev_join.record(main)
+
+    def _iteration_async(self) -> None:
+        if self.rollouts_in_flight == 0:       # prime the pipeline: the first rollout has nothing to overlap with
+            self.ev_join.record(torch.cuda.current_stream())
+            self._sample_on_side_stream()
+            self._join()
+            self.rollouts_in_flight = 1
+        # fork: the learner trains on rollout i while the sampler collects rollout i+1 with the snapshot taken at the
+        # last join.  A device env's rollout is one graph launch -> enqueue it first; a host env keeps the host busy for
+        # the whole rollout -> enqueue the learner's launches first.
+        if getattr(self.env, "is_gpu_env", False):
+            self._sample_on_side_stream()
+            self.learner.train(self.traj)
+        else:
+            self.learner.train(self.traj)
+            self._sample_on_side_stream()
+        self._join()
         self.env_steps = self.learner.env_steps
 
     def run(self) -> int:

@@ -254,3 +254,58 @@ def test_full_size_properties_and_graph_replay():
         o, shp = modelA._slices[n]
         mask[o:o + int(np.prod(shp))] = False
     assert torch.all(modelA.flat[mask] == 0)
+
+
+def test_async_double_buffered_runner_matches_lagged_oracle(tmp_path):
+    """async_rl=True (train.py): the sampler collects rollout i+1 on its own stream with a weight snapshot while the
+    learner trains on rollout i.  The schedule is deterministic, so the oracle can replay it: rollout r is sampled
+    with the weights published at the join before it (r0, r1 <- W0; r2 <- W after train(0); ...), stamped with that
+    version, and trained on one iteration later (policy lag = 4 SGD steps, inside max_policy_lag)."""
+    import copy
+
+    from sample_factory_b200 import ops
+    from sample_factory_b200.envs import TapeVecEnv, register_env
+    from sample_factory_b200.train import Runner
+
+    dev = torch.device("cuda", 0)
+    N, T, ITERS = 128, 16, 3
+    ocfg = O.OracleCfg(obs_dim=32, num_actions=8, encoder_mlp_layers=[128, 128], rollout=T, recurrence=1,
+                       batch_size=N * T // 4, num_batches_per_epoch=4, num_epochs=1)
+    st0 = O.init_state(ocfg, seed=13)
+    gen = torch.Generator().manual_seed(17)
+    tape = torch.randn((ITERS + 1) * T + 1, N, ocfg.obs_dim, generator=gen)
+    noises = [torch.empty(T, N, ocfg.num_actions).exponential_(generator=gen) for _ in range(ITERS + 1)]
+    register_env("async_tape", lambda n, c, e, render_mode=None: TapeVecEnv(tape.to(dev).contiguous(), ocfg.num_actions))
+    cfg = make_cfg(ocfg, env="async_tape", train_dir=str(tmp_path), experiment="async", cuda_graph=False, seed=0,
+                   gemm_engine="simt", async_rl=True, restart_behavior="overwrite")
+    runner = Runner(cfg)
+    assert runner.init() == 0
+    runner.load_state_dict(st0)
+    runner.rollout_hook = lambda r: setattr(runner.sampler, "noise", noises[r].to(dev))
+
+    olearner = O.OracleLearner(ocfg, copy.deepcopy(st0))
+    oenv = O.TapeVecEnv(tape, ocfg.num_actions)
+    olast = oenv.reset()
+    snap, snap_version = copy.deepcopy(olearner.st), 0
+    pending = O.alloc_trajectories(ocfg, N)
+    olast = O.rollout(ocfg, snap, oenv, olast, pending, noises[0], snap_version)      # priming rollout
+    for it in range(ITERS):
+        runner.iteration()
+        torch.cuda.synchronize()
+        nxt = O.alloc_trajectories(ocfg, N)
+        olast = O.rollout(ocfg, snap, oenv, olast, nxt, noises[it + 1], snap_version)   # overlaps train(it) on the device
+        olearner.train(pending)
+        snap, snap_version = copy.deepcopy(olearner.st), olearner.train_step              # the join
+        # the learner's buffer now holds rollout it+1, sampled with the PREVIOUS snapshot
+        got = {k: v.cpu() for k, v in runner.traj.items()}
+        for k in ["obs", "actions", "rewards", "dones", "policy_version"]:
+            assert torch.equal(got[k], nxt[k]), (it, k)
+        np.testing.assert_allclose(got["action_logits"].numpy(), nxt["action_logits"].numpy(), atol=TOL)
+        sd = runner.model.state_dict()
+        for k in O.param_names(ocfg):
+            np.testing.assert_allclose(sd[k].cpu().numpy(), olearner.st[k].numpy(), atol=TOL, err_msg=f"{it} {k}")
+        assert runner.learner.train_step == olearner.train_step == 4 * (it + 1)
+        pending = nxt
+    assert runner.rollouts_started == ITERS + 1 and runner.env_steps == ITERS * N * T
+    lag = runner.learner.train_step - got["policy_version"].max().item()
+    assert lag == 4.0      # samples in the buffer are one iteration (4 SGD steps) behind the learner
