@@ -20,6 +20,8 @@
 // (dX = dZ.W, dW = dZ^T.X) read the activations in the layout the forward pass wrote them -- no transposed copies.
 // Split-K tiles write raw partial sums to a workspace that the SIMT engine's fixed-order reduce kernel sums.
 #include <cuda.h>
+
+#include <cstdlib>
 #include <cudaTypedefs.h>
 
 #include "common.cuh"
@@ -106,6 +108,29 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
           "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr));
 }
+// D[tmem] (+)= A[tmem] * B[smem desc]: the A operand is read from tensor memory (rows = TMEM lanes, k = 32-bit columns)
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+        "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+        "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------------ descriptors
@@ -211,6 +236,131 @@ __device__ __forceinline__ TileCoord tile_coord(int tile, int tiles_n, int tiles
     const int k_end = (t.k_begin + k_chunk < K) ? t.k_begin + k_chunk : K;
     t.num_kb = (k_end - t.k_begin + TBK - 1) / TBK;
     return t;
+}
+
+struct EpiCtx {
+    int lane_base, lane, col0, mode;
+    bool vec_ok, aux_vec, bias_vec;
+    const float* bias_base;
+};
+
+// Epilogue warps 6..13: warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32); warps 6..9 take columns [0, BN/2) of their
+// lane quadrant, warps 10..13 take [BN/2, BN).  One warp per scheduler was latency-bound (ncu: the epilogue warps were
+// ~100% busy at IPC 0.12 and paced the whole kernel for short-K tiles).  The bias for ALL N columns is staged once per
+// kernel in shared memory (persistent CTA).
+template <int BN>
+__device__ __forceinline__ EpiCtx make_epi_ctx(int warp, int lane, const float* C, int64_t ldc, int N, int splits,
+                                               const TcEpilogue& epi, float* bias_s, int bias_floats) {
+    EpiCtx ec;
+    ec.lane_base = (warp & 3) * 32;
+    ec.lane = lane;
+    ec.col0 = ((warp - 6) >> 2) * (BN / 2);
+    ec.vec_ok = (ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15u) == 0);
+    ec.aux_vec = epi.aux && (epi.ld_aux % 4 == 0) && ((reinterpret_cast<uintptr_t>(epi.aux) & 15u) == 0);
+    const bool bias_smem = epi.bias != nullptr && N <= bias_floats;
+    if (bias_smem) {
+        for (int i = threadIdx.x - 192; i < N; i += 256) bias_s[i] = epi.bias[i];
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+    }
+    ec.bias_base = bias_smem ? bias_s : epi.bias;
+    ec.bias_vec = epi.bias && (bias_smem || ((reinterpret_cast<uintptr_t>(epi.bias) & 15u) == 0));
+    ec.mode = splits == 1 ? epi.mode : 0;
+    return ec;
+}
+
+// One output tile: TMEM accumulator slot (main at column 0, cross terms at column BN) -> registers -> global.
+template <int BN, bool SPLIT3>
+__device__ __forceinline__ void tc_epilogue_tile(uint32_t tmem_slot_addr, uint64_t* acc_full_bar, uint32_t acc_ph,
+                                                 uint64_t* acc_empty_bar, const TileCoord& tc, const EpiCtx& ec,
+                                                 float* __restrict__ C, int64_t ldc, int64_t M, int N, int splits,
+                                                 const TcEpilogue& epi) {
+    constexpr int CH = BN / 2;                      // columns per thread
+    const int lane_base = ec.lane_base, lane = ec.lane, col0 = ec.col0, mode = ec.mode;
+    const bool vec_ok = ec.vec_ok, aux_vec = ec.aux_vec, bias_vec = ec.bias_vec;
+    const float* bias_base = ec.bias_base;
+            const int64_t m = tc.m0 + lane_base + lane;
+            const int nbeg = tc.n0 + col0;
+            const bool fast = (m < M) && (nbeg + CH <= N) && vec_ok &&
+                              (mode == 0 || (mode == 1 && (bias_vec || !epi.bias)) || (mode == 2 && aux_vec));
+            // Processed in 32-column chunks so that the live set (32 accumulators + 32 cross-term temporaries + 8 float4
+            // of aux) fits the 128-register budget of a 448-thread CTA without spilling.
+            // mode 2: the activation-derivative operand of the first chunk is fetched BEFORE the accumulator is ready
+            // (hides its HBM latency behind the main loop of this tile).
+            const float* aux_row = (mode == 2 && fast) ? epi.aux + m * epi.ld_aux + nbeg : nullptr;
+            float4 auxv[8];
+            if (aux_row) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) auxv[j] = *reinterpret_cast<const float4*>(aux_row + 4 * j);
+            }
+            mbar_wait(acc_full_bar, acc_ph);
+            tc_fence_after();
+            const uint32_t t_main = tmem_slot_addr + ((uint32_t)lane_base << 16) + (uint32_t)col0;
+            float* Cz = C + (splits > 1 ? (int64_t)tc.z * M * ldc : 0);
+            float* dst_row = Cz + m * ldc + nbeg;
+#pragma unroll
+            for (int c0 = 0; c0 < CH; c0 += 32) {
+                float acc[32];
+                {
+                    uint32_t r[32];
+                    tmem_ld_32x32b_x32(t_main + (uint32_t)c0, r);
+                    if (SPLIT3) {
+                        uint32_t r2[32];
+                        tmem_ld_32x32b_x32(t_main + (uint32_t)(BN + c0), r2);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(r[j]) + __uint_as_float(r2[j]);
+                    } else {
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(r[j]);
+                    }
+                }
+                if (c0 + 32 >= CH) {
+                    // all TMEM reads of this thread are complete: hand the slot back so the next tile's MMAs can start
+                    tc_fence_before();
+                    mbar_arrive(acc_empty_bar);
+                }
+                if (c0 > 0 && aux_row) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) auxv[j] = *reinterpret_cast<const float4*>(aux_row + c0 + 4 * j);
+                }
+                if (m < M) {
+                    float* dst = dst_row + c0;
+                    if (fast) {
+                        // whole row segment in bounds, 128-bit everything; mode / activation resolved once per chunk into
+                        // a straight-line specialisation (a per-element switch cost 4x the instructions)
+                        const float* bias_n0 = epi.bias ? bias_base + nbeg + c0 : nullptr;
+                        if (mode == 1) {
+                            switch (epi.act) {
+                                case SFB200_ACT_ELU: write_row<1, SFB200_ACT_ELU, 32>(acc, dst, bias_n0, auxv); break;
+                                case SFB200_ACT_RELU: write_row<1, SFB200_ACT_RELU, 32>(acc, dst, bias_n0, auxv); break;
+                                case SFB200_ACT_TANH: write_row<1, SFB200_ACT_TANH, 32>(acc, dst, bias_n0, auxv); break;
+                                default: write_row<1, SFB200_ACT_NONE, 32>(acc, dst, bias_n0, auxv); break;
+                            }
+                        } else if (mode == 2) {
+                            switch (epi.act) {
+                                case SFB200_ACT_ELU: write_row<2, SFB200_ACT_ELU, 32>(acc, dst, bias_n0, auxv); break;
+                                case SFB200_ACT_RELU: write_row<2, SFB200_ACT_RELU, 32>(acc, dst, bias_n0, auxv); break;
+                                case SFB200_ACT_TANH: write_row<2, SFB200_ACT_TANH, 32>(acc, dst, bias_n0, auxv); break;
+                                default: write_row<0, SFB200_ACT_NONE, 32>(acc, dst, bias_n0, auxv); break;
+                            }
+                        } else {
+                            write_row<0, SFB200_ACT_NONE, 32>(acc, dst, bias_n0, auxv);
+                        }
+                    } else {
+#pragma unroll   // fully unrolled so that acc[] stays in registers (no dynamic indexing)
+                        for (int j = 0; j < 32; ++j) {
+                            const int n = nbeg + c0 + j;
+                            if (n < N) {
+                                float v = acc[j];
+                                if (mode == 1) v = act_fwd_fast(v + (epi.bias ? epi.bias[n] : 0.f), epi.act);
+                                else if (mode == 2) v = v * act_bwd_from_out(epi.aux[m * epi.ld_aux + n], epi.act);
+                                dst[j] = v;
+                            }
+                        }
+                    }
+                }
+            }
 }
 
 // ------------------------------------------------------------------------------------------------ the kernel
@@ -366,108 +516,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         // 8 warps: warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32); warps 6..9 take columns [0, BN/2) of their
         // lane quadrant, warps 10..13 take [BN/2, BN).  One warp per scheduler was latency-bound (ncu: the epilogue
         // warps were ~100% busy at IPC 0.12 and paced the whole kernel for short-K tiles).
-        constexpr int CH = BN / 2;                      // columns per thread
-        const int lane_base = (warp & 3) * 32;
-        const int col0 = ((warp - 6) >> 2) * CH;
-        const bool vec_ok = (ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15u) == 0);
-        const bool aux_vec = epi.aux && (epi.ld_aux % 4 == 0) && ((reinterpret_cast<uintptr_t>(epi.aux) & 15u) == 0);
-        // bias for ALL N columns is staged once per kernel in shared memory (persistent CTA)
-        const bool bias_smem = epi.bias != nullptr && N <= S::BIAS_FLOATS;
-        if (bias_smem) {
-            for (int i = threadIdx.x - 192; i < N; i += 256) bias_s[i] = epi.bias[i];
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-        }
-        const float* bias_base = bias_smem ? bias_s : epi.bias;
-        const bool bias_vec = epi.bias && (bias_smem || ((reinterpret_cast<uintptr_t>(epi.bias) & 15u) == 0));
-        const bool do_epi = splits == 1;
-        const int mode = do_epi ? epi.mode : 0;
+        const EpiCtx ec = make_epi_ctx<BN>(warp, lane, C, ldc, N, splits, epi, bias_s, S::BIAS_FLOATS);
         uint32_t tile_iter = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_iter) {
             const TileCoord tc = tile_coord(tile, tiles_n, tiles_per_z, BN, K, k_chunk);
             const uint32_t slot = tile_iter & 1, acc_ph = (tile_iter >> 1) & 1;
-            const int64_t m = tc.m0 + lane_base + lane;
-            const int nbeg = tc.n0 + col0;
-            const bool fast = (m < M) && (nbeg + CH <= N) && vec_ok &&
-                              (mode == 0 || (mode == 1 && (bias_vec || !epi.bias)) || (mode == 2 && aux_vec));
-            // Processed in 32-column chunks so that the live set (32 accumulators + 32 cross-term temporaries + 8 float4
-            // of aux) fits the 128-register budget of a 448-thread CTA without spilling.
-            // mode 2: the activation-derivative operand of the first chunk is fetched BEFORE the accumulator is ready
-            // (hides its HBM latency behind the main loop of this tile).
-            const float* aux_row = (mode == 2 && fast) ? epi.aux + m * epi.ld_aux + nbeg : nullptr;
-            float4 auxv[8];
-            if (aux_row) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) auxv[j] = *reinterpret_cast<const float4*>(aux_row + 4 * j);
-            }
-            mbar_wait(&acc_full[slot], acc_ph);
-            tc_fence_after();
-            const uint32_t t_main = tmem_base + slot * ACC_COLS + ((uint32_t)lane_base << 16) + (uint32_t)col0;
-            float* Cz = C + (splits > 1 ? (int64_t)tc.z * M * ldc : 0);
-            float* dst_row = Cz + m * ldc + nbeg;
-#pragma unroll
-            for (int c0 = 0; c0 < CH; c0 += 32) {
-                float acc[32];
-                {
-                    uint32_t r[32];
-                    tmem_ld_32x32b_x32(t_main + (uint32_t)c0, r);
-                    if (SPLIT3) {
-                        uint32_t r2[32];
-                        tmem_ld_32x32b_x32(t_main + (uint32_t)(BN + c0), r2);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(r[j]) + __uint_as_float(r2[j]);
-                    } else {
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(r[j]);
-                    }
-                }
-                if (c0 + 32 >= CH) {
-                    // all TMEM reads of this thread are complete: hand the slot back so the next tile's MMAs can start
-                    tc_fence_before();
-                    mbar_arrive(&acc_empty[slot]);
-                }
-                if (c0 > 0 && aux_row) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) auxv[j] = *reinterpret_cast<const float4*>(aux_row + c0 + 4 * j);
-                }
-                if (m < M) {
-                    float* dst = dst_row + c0;
-                    if (fast) {
-                        // whole row segment in bounds, 128-bit everything; mode / activation resolved once per chunk into
-                        // a straight-line specialisation (a per-element switch cost 4x the instructions)
-                        const float* bias_n0 = epi.bias ? bias_base + nbeg + c0 : nullptr;
-                        if (mode == 1) {
-                            switch (epi.act) {
-                                case SFB200_ACT_ELU: write_row<1, SFB200_ACT_ELU, 32>(acc, dst, bias_n0, auxv); break;
-                                case SFB200_ACT_RELU: write_row<1, SFB200_ACT_RELU, 32>(acc, dst, bias_n0, auxv); break;
-                                case SFB200_ACT_TANH: write_row<1, SFB200_ACT_TANH, 32>(acc, dst, bias_n0, auxv); break;
-                                default: write_row<1, SFB200_ACT_NONE, 32>(acc, dst, bias_n0, auxv); break;
-                            }
-                        } else if (mode == 2) {
-                            switch (epi.act) {
-                                case SFB200_ACT_ELU: write_row<2, SFB200_ACT_ELU, 32>(acc, dst, bias_n0, auxv); break;
-                                case SFB200_ACT_RELU: write_row<2, SFB200_ACT_RELU, 32>(acc, dst, bias_n0, auxv); break;
-                                case SFB200_ACT_TANH: write_row<2, SFB200_ACT_TANH, 32>(acc, dst, bias_n0, auxv); break;
-                                default: write_row<0, SFB200_ACT_NONE, 32>(acc, dst, bias_n0, auxv); break;
-                            }
-                        } else {
-                            write_row<0, SFB200_ACT_NONE, 32>(acc, dst, bias_n0, auxv);
-                        }
-                    } else {
-#pragma unroll   // fully unrolled so that acc[] stays in registers (no dynamic indexing)
-                        for (int j = 0; j < 32; ++j) {
-                            const int n = nbeg + c0 + j;
-                            if (n < N) {
-                                float v = acc[j];
-                                if (mode == 1) v = act_fwd_fast(v + (epi.bias ? epi.bias[n] : 0.f), epi.act);
-                                else if (mode == 2) v = v * act_bwd_from_out(epi.aux[m * epi.ld_aux + n], epi.act);
-                                dst[j] = v;
-                            }
-                        }
-                    }
-                }
-            }
+            tc_epilogue_tile<BN, SPLIT3>(tmem_base + slot * ACC_COLS, &acc_full[slot], acc_ph, &acc_empty[slot], tc, ec, C, ldc, M,
+                                         N, splits, epi);
         }
     }
     tc_fence_before();
@@ -475,6 +530,192 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ kernel, A in TMEM
+// Variant for a K-major A operand (forward layers, dX).  TMA still stages the raw A tile in shared memory (deep pipeline
+// = HBM/L2 latency hidden), but the four operand warps read it ONCE (each thread owns one of the 128 tile rows = one TMEM
+// lane; the 128B swizzle makes the row-per-thread reads conflict-free), split it in registers and tcgen05.st the hi / lo
+// halves into a TMEM stage; the MMAs take A from TMEM ("TS" form) and only B from shared memory.  Per k-block this
+// removes the two split writes and the three MMA operand reads of A from the shared-memory pipe (224 KB -> 144 KB of
+// smem traffic per k-block: the 3xTF32 main loop was smem-bound).  (Reading A straight from global into registers was
+// tried first and lost: one k-block of register prefetch cannot cover the L2/HBM latency.)
+// The two MMAs of the 3x scheme are issued as  A_hi x [B_hi ; B_lo]  (N = 256: main and cross accumulators are adjacent
+// TMEM columns, B_hi and B_lo adjacent smem tiles) and  A_lo x B_hi  (N = 128 into the cross columns).
+// TMEM budget (512 columns): accumulator [0,256) (single slot), A stages [256, 256 + 64*STAGES).
+constexpr int TA_STAGES = 4;
+constexpr uint32_t TA_ACOL0 = 256;
+
+template <int STAGES>
+struct TaSmem {
+    static constexpr int B_BYTES = 128 * TBK * 4;
+    static constexpr int A_BYTES = TBM * TBK * 4;
+    static constexpr int STAGE_BYTES = 2 * B_BYTES + A_BYTES;   // [B hi | B lo | A raw]
+    static constexpr int NUM_BARS = 3 * STAGES + 2;
+    static constexpr int BIAS_FLOATS = 2048;
+    static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 + 512 + BIAS_FLOATS * 4;
+};
+
+template <bool B_MN, bool SPLIT3>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_ta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                  float* __restrict__ C, int64_t ldc, int64_t M, int N, int K, TcEpilogue epi) {
+    constexpr int BN = 128, STAGES = TA_STAGES;
+    using S = TaSmem<STAGES>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES);
+    uint64_t* full = bars;                  // A and B tiles landed (TMA)
+    uint64_t* conv = bars + STAGES;         // A in TMEM + B split, visible to the tensor core (count 128)
+    uint64_t* empty = bars + 2 * STAGES;    // MMAs of the stage retired: smem B stage and TMEM A stage reusable
+    uint64_t* acc_full = bars + 3 * STAGES;
+    uint64_t* acc_empty = bars + 3 * STAGES + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + S::NUM_BARS);
+    float* bias_s = reinterpret_cast<float*>(smem + STAGES * S::STAGE_BYTES + 512);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_n = (N + BN - 1) / BN;
+    const int total_tiles = tiles_n * (int)((M + TBM - 1) / TBM);
+    const int num_kb = (K + TBK - 1) / TBK;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&conv[s], 128);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(acc_full, 1);
+        mbar_init(acc_empty, 256);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================================================== TMA producer
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const TileCoord tc = tile_coord(tile, tiles_n, total_tiles, BN, K, K);
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
+                    uint8_t* sb = smem + s * S::STAGE_BYTES;
+                    mbar_expect_tx(&full[s], S::B_BYTES + S::A_BYTES);
+                    const int k0 = kb * TBK;
+                    tma_load_2d(sb + 2 * S::B_BYTES, &tmap_a, &full[s], k0, (int)tc.m0);
+                    if (B_MN) {
+                        for (int j = 0; j < BN / 32; ++j) tma_load_2d(sb + j * 4096, &tmap_b, &full[s], tc.n0 + 32 * j, k0);
+                    } else {
+                        tma_load_2d(sb, &tmap_b, &full[s], k0, tc.n0);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================== MMA issuer
+        constexpr uint32_t idesc_wide = make_idesc(false, B_MN, TBM, SPLIT3 ? 2 * BN : BN);
+        constexpr uint32_t idesc_cross = make_idesc(false, B_MN, TBM, BN);
+        constexpr uint32_t B_KSTEP = B_MN ? (1024u >> 4) : (UMMA_K * 4u >> 4);
+        uint32_t it = 0, tile_iter = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_iter) {
+            mbar_wait(acc_empty, (tile_iter & 1) ^ 1);
+            tc_fence_after();
+            for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                const int s = it % STAGES;
+                mbar_wait(&conv[s], (it / STAGES) & 1);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint64_t db_hi = make_smem_desc(smem_u32(smem + s * S::STAGE_BYTES), B_MN);
+                    const uint32_t a_hi = tmem_base + TA_ACOL0 + (uint32_t)s * 64u;
+#pragma unroll
+                    for (int k = 0; k < TBK / UMMA_K; ++k) {
+                        const uint64_t bo = (uint64_t)(k * B_KSTEP);
+                        // [main | cross] (+)= A_hi x [B_hi ; B_lo]   (plain tf32 mode: main (+)= A x B)
+                        umma_tf32_ts(tmem_base, a_hi + k * UMMA_K, db_hi + bo, idesc_wide, (kb | k) != 0);
+                        if (SPLIT3) umma_tf32_ts(tmem_base + BN, a_hi + 32 + k * UMMA_K, db_hi + bo, idesc_cross, 1);
+                    }
+                    umma_commit(&empty[s]);
+                    if (kb == num_kb - 1) umma_commit(acc_full);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp < 6) {
+        // ===================================================== operand warps: A smem -> registers -> TMEM, B split in smem
+        const int ct = threadIdx.x - 64;                       // 0..127
+        const int row = (warp & 3) * 32 + lane;                // tile row == TMEM lane this thread may access
+        const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + TA_ACOL0;
+        const int sw = row & 7;                                // 128B swizzle: 16 B chunk index XOR (row % 8)
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                // full[s] of this phase implies empty[s] of the previous one: the MMAs that read TMEM stage s have retired
+                mbar_wait(&full[s], ph);
+                tc_fence_after();
+                uint8_t* sb = smem + s * S::STAGE_BYTES;
+                const uint4* arow = reinterpret_cast<const uint4*>(sb + 2 * S::B_BYTES + row * 128);
+                uint32_t hi[32], lo[32];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const uint4 q = arow[j ^ sw];
+                    const uint32_t v[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        if (SPLIT3) {
+                            hi[4 * j + e] = v[e] & 0xffffe000u;
+                            lo[4 * j + e] = __float_as_uint(__uint_as_float(v[e]) - __uint_as_float(hi[4 * j + e])) & 0xffffe000u;
+                        } else {
+                            hi[4 * j + e] = v[e];
+                        }
+                    }
+                }
+                tmem_st_32x32b_x32(lane_addr + (uint32_t)s * 64u, hi);
+                if (SPLIT3) {
+                    tmem_st_32x32b_x32(lane_addr + (uint32_t)s * 64u + 32u, lo);
+                    uint4* h4 = reinterpret_cast<uint4*>(sb);
+                    uint4* l4 = reinterpret_cast<uint4*>(sb + S::B_BYTES);
+#pragma unroll 4
+                    for (int i = ct; i < S::B_BYTES / 16; i += 128) {
+                        const uint4 v = h4[i];
+                        uint4 h, l;
+                        h.x = v.x & 0xffffe000u; h.y = v.y & 0xffffe000u; h.z = v.z & 0xffffe000u; h.w = v.w & 0xffffe000u;
+                        l.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x)) & 0xffffe000u;
+                        l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y)) & 0xffffe000u;
+                        l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z)) & 0xffffe000u;
+                        l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w)) & 0xffffe000u;
+                        h4[i] = h;
+                        l4[i] = l;
+                    }
+                }
+                tmem_st_wait();
+                fence_proxy_async_smem();
+                tc_fence_before();
+                mbar_arrive(&conv[s]);
+            }
+        }
+    } else {
+        // ===================================================== epilogue (single accumulator slot)
+        const EpiCtx ec = make_epi_ctx<BN>(warp, lane, C, ldc, N, 1, epi, bias_s, S::BIAS_FLOATS);
+        uint32_t tile_iter = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_iter) {
+            const TileCoord tc = tile_coord(tile, tiles_n, total_tiles, BN, K, K);
+            tc_epilogue_tile<BN, SPLIT3>(tmem_base, acc_full, tile_iter & 1, acc_empty, tc, ec, C, ldc, M, N, 1, epi);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
     }
 }
 
@@ -539,6 +780,33 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, float* C, int
     return 0;
 }
 
+template <bool B_MN, bool SPLIT3>
+static int launch_tc_ta(const CUtensorMap& ta, const CUtensorMap& tb, float* C, int64_t ldc, int64_t M, int N, int K,
+                        const TcEpilogue& epi, cudaStream_t st) {
+    using S = TaSmem<TA_STAGES>;
+    auto kern = gemm_tc_ta_kernel<B_MN, SPLIT3>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        SFB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+        attr_set = true;
+    }
+    const int64_t tiles = ceil_div(N, 128) * ceil_div(M, TBM);
+    const int64_t grid = tiles < sm_count() ? tiles : sm_count();
+    kern<<<(unsigned)grid, TC_THREADS, S::TOTAL, st>>>(ta, tb, C, ldc, M, N, K, epi);
+    SFB_LAUNCH_OK();
+    return 0;
+}
+
+// SFB200_TC_A_IN_TMEM=0 selects the shared-memory-A kernel for every shape (A/B comparison, debugging)
+static bool ta_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("SFB200_TC_A_IN_TMEM");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
+}
+
 // C[M,N] = epi( sum_k A(m,k) B(n,k) ). Returns SFB_TC_UNSUPPORTED when the shape/alignment is not covered.
 static int gemm_tc(bool a_mn, const float* A, int64_t lda, bool b_mn, const float* B, int64_t ldb, float* C, int64_t ldc,
                    int64_t M, int N, int K, int splits, const TcEpilogue& epi, float* ws, bool split3, cudaStream_t st) {
@@ -548,6 +816,18 @@ static int gemm_tc(bool a_mn, const float* A, int64_t lda, bool b_mn, const floa
     const int BN = (N >= 128) ? 128 : 64;
     CUtensorMap ta, tb;
     bool ok;
+    if (!a_mn && BN == 128 && splits == 1 && ta_enabled()) {
+        // K-major A: operand A goes smem -> registers -> TMEM (gemm_tc_ta_kernel)
+        ok = make_tmap(&ta, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, TBK, TBM, false);
+        if (!ok) return SFB_TC_UNSUPPORTED;
+        if (b_mn) ok = make_tmap(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 32, TBK, true);
+        else ok = make_tmap(&tb, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, TBK, 128u, false);
+        if (!ok) return SFB_TC_UNSUPPORTED;
+        if (b_mn) return split3 ? launch_tc_ta<true, true>(ta, tb, C, ldc, M, N, K, epi, st)
+                                : launch_tc_ta<true, false>(ta, tb, C, ldc, M, N, K, epi, st);
+        return split3 ? launch_tc_ta<false, true>(ta, tb, C, ldc, M, N, K, epi, st)
+                      : launch_tc_ta<false, false>(ta, tb, C, ldc, M, N, K, epi, st);
+    }
     if (a_mn) ok = make_tmap(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 32, TBK, true);
     else ok = make_tmap(&ta, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, TBK, TBM, false);
     if (b_mn) ok = ok && make_tmap(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 32, TBK, true);
