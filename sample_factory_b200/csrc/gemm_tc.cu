@@ -557,10 +557,11 @@ struct TaSmem {
     static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 + 512 + BIAS_FLOATS * 4;
 };
 
-template <bool B_MN, bool SPLIT3>
+template <bool A_MN, bool B_MN, bool SPLIT3>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_ta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                  float* __restrict__ C, int64_t ldc, int64_t M, int N, int K, TcEpilogue epi) {
+                  float* __restrict__ C, int64_t ldc, int64_t M, int N, int K, int k_chunk, int splits, TcEpilogue epi,
+                  int raw_hi) {
     constexpr int BN = 128, STAGES = TA_STAGES;
     using S = TaSmem<STAGES>;
     extern __shared__ uint8_t smem_raw[];
@@ -576,8 +577,8 @@ gemm_tc_ta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_n = (N + BN - 1) / BN;
-    const int total_tiles = tiles_n * (int)((M + TBM - 1) / TBM);
-    const int num_kb = (K + TBK - 1) / TBK;
+    const int tiles_per_z = tiles_n * (int)((M + TBM - 1) / TBM);
+    const int total_tiles = tiles_per_z * splits;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
@@ -602,14 +603,19 @@ gemm_tc_ta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         if (lane == 0) {
             uint32_t it = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const TileCoord tc = tile_coord(tile, tiles_n, total_tiles, BN, K, K);
-                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                const TileCoord tc = tile_coord(tile, tiles_n, tiles_per_z, BN, K, k_chunk);
+                for (int kb = 0; kb < tc.num_kb; ++kb, ++it) {
                     const int s = it % STAGES;
                     mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
                     uint8_t* sb = smem + s * S::STAGE_BYTES;
                     mbar_expect_tx(&full[s], S::B_BYTES + S::A_BYTES);
-                    const int k0 = kb * TBK;
-                    tma_load_2d(sb + 2 * S::B_BYTES, &tmap_a, &full[s], k0, (int)tc.m0);
+                    const int k0 = tc.k_begin + kb * TBK;
+                    if (A_MN) {
+                        for (int j = 0; j < TBM / 32; ++j)
+                            tma_load_2d(sb + 2 * S::B_BYTES + j * 4096, &tmap_a, &full[s], (int)tc.m0 + 32 * j, k0);
+                    } else {
+                        tma_load_2d(sb + 2 * S::B_BYTES, &tmap_a, &full[s], k0, (int)tc.m0);
+                    }
                     if (B_MN) {
                         for (int j = 0; j < BN / 32; ++j) tma_load_2d(sb + j * 4096, &tmap_b, &full[s], tc.n0 + 32 * j, k0);
                     } else {
@@ -625,9 +631,10 @@ gemm_tc_ta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         constexpr uint32_t B_KSTEP = B_MN ? (1024u >> 4) : (UMMA_K * 4u >> 4);
         uint32_t it = 0, tile_iter = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_iter) {
+            const TileCoord tc = tile_coord(tile, tiles_n, tiles_per_z, BN, K, k_chunk);
             mbar_wait(acc_empty, (tile_iter & 1) ^ 1);
             tc_fence_after();
-            for (int kb = 0; kb < num_kb; ++kb, ++it) {
+            for (int kb = 0; kb < tc.num_kb; ++kb, ++it) {
                 const int s = it % STAGES;
                 mbar_wait(&conv[s], (it / STAGES) & 1);
                 tc_fence_after();
@@ -642,7 +649,7 @@ gemm_tc_ta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                         if (SPLIT3) umma_tf32_ts(tmem_base + BN, a_hi + 32 + k * UMMA_K, db_hi + bo, idesc_cross, 1);
                     }
                     umma_commit(&empty[s]);
-                    if (kb == num_kb - 1) umma_commit(acc_full);
+                    if (kb == tc.num_kb - 1) umma_commit(acc_full);
                 }
                 __syncwarp();
             }
@@ -655,26 +662,46 @@ gemm_tc_ta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         const int sw = row & 7;                                // 128B swizzle: 16 B chunk index XOR (row % 8)
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            for (int kb = 0; kb < num_kb; ++kb, ++it) {
+            const TileCoord tc = tile_coord(tile, tiles_n, tiles_per_z, BN, K, k_chunk);
+            for (int kb = 0; kb < tc.num_kb; ++kb, ++it) {
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1;
                 // full[s] of this phase implies empty[s] of the previous one: the MMAs that read TMEM stage s have retired
                 mbar_wait(&full[s], ph);
                 tc_fence_after();
                 uint8_t* sb = smem + s * S::STAGE_BYTES;
-                const uint4* arow = reinterpret_cast<const uint4*>(sb + 2 * S::B_BYTES + row * 128);
                 uint32_t hi[32], lo[32];
+                if (A_MN) {
+                    // MN-major tile: box (row/32) of [32 k][32 rows], k-rows 128 B apart, 32 B chunks XOR (k % 4)
+                    // (SWIZZLE_128B_ATOM_32B).  A warp reads one whole 128 B k-row per instruction: conflict-free.
+                    const uint8_t* abox = sb + 2 * S::B_BYTES + (row >> 5) * 4096 + (lane & 7) * 4;
+                    const int chunk = lane >> 3;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const uint4 q = arow[j ^ sw];
-                    const uint32_t v[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
+                    for (int kk = 0; kk < 32; ++kk) {
+                        const uint32_t v = *reinterpret_cast<const uint32_t*>(abox + kk * 128 + ((chunk ^ (kk & 3)) << 5));
                         if (SPLIT3) {
-                            hi[4 * j + e] = v[e] & 0xffffe000u;
-                            lo[4 * j + e] = __float_as_uint(__uint_as_float(v[e]) - __uint_as_float(hi[4 * j + e])) & 0xffffe000u;
+                            const uint32_t h = v & 0xffffe000u;
+                            hi[kk] = raw_hi ? v : h;
+                            lo[kk] = __float_as_uint(__uint_as_float(v) - __uint_as_float(h)) & 0xffffe000u;
                         } else {
-                            hi[4 * j + e] = v[e];
+                            hi[kk] = v;
+                        }
+                    }
+                } else {
+                    const uint4* arow = reinterpret_cast<const uint4*>(sb + 2 * S::B_BYTES + row * 128);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const uint4 q = arow[j ^ sw];
+                        const uint32_t v[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            if (SPLIT3) {
+                                const uint32_t h = v[e] & 0xffffe000u;
+                                hi[4 * j + e] = raw_hi ? v[e] : h;
+                                lo[4 * j + e] = __float_as_uint(__uint_as_float(v[e]) - __uint_as_float(h)) & 0xffffe000u;
+                            } else {
+                                hi[4 * j + e] = v[e];
+                            }
                         }
                     }
                 }
@@ -692,7 +719,7 @@ gemm_tc_ta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                         l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y)) & 0xffffe000u;
                         l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z)) & 0xffffe000u;
                         l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w)) & 0xffffe000u;
-                        h4[i] = h;
+                        if (!raw_hi) h4[i] = h;     // raw_hi: the tensor core truncates the low 13 mantissa bits itself
                         l4[i] = l;
                     }
                 }
@@ -704,11 +731,11 @@ gemm_tc_ta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         }
     } else {
         // ===================================================== epilogue (single accumulator slot)
-        const EpiCtx ec = make_epi_ctx<BN>(warp, lane, C, ldc, N, 1, epi, bias_s, S::BIAS_FLOATS);
+        const EpiCtx ec = make_epi_ctx<BN>(warp, lane, C, ldc, N, splits, epi, bias_s, S::BIAS_FLOATS);
         uint32_t tile_iter = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_iter) {
-            const TileCoord tc = tile_coord(tile, tiles_n, total_tiles, BN, K, K);
-            tc_epilogue_tile<BN, SPLIT3>(tmem_base, acc_full, tile_iter & 1, acc_empty, tc, ec, C, ldc, M, N, 1, epi);
+            const TileCoord tc = tile_coord(tile, tiles_n, tiles_per_z, BN, K, k_chunk);
+            tc_epilogue_tile<BN, SPLIT3>(tmem_base, acc_full, tile_iter & 1, acc_empty, tc, ec, C, ldc, M, N, splits, epi);
         }
     }
     tc_fence_before();
@@ -780,19 +807,32 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, float* C, int
     return 0;
 }
 
-template <bool B_MN, bool SPLIT3>
+// The tensor core reads only the top 19 bits of a tf32 operand (truncation), so the un-masked fp32 value can serve as the
+// "hi" operand and only "lo" has to be written back (measured: bit-identical results, one smem write per element
+// less).  SFB200_TC_RAW_HI=0 restores the explicit mask.
+static bool raw_hi_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("SFB200_TC_RAW_HI");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
+}
+
+template <bool A_MN, bool B_MN, bool SPLIT3>
 static int launch_tc_ta(const CUtensorMap& ta, const CUtensorMap& tb, float* C, int64_t ldc, int64_t M, int N, int K,
-                        const TcEpilogue& epi, cudaStream_t st) {
+                        int k_chunk, int splits, const TcEpilogue& epi, cudaStream_t st) {
     using S = TaSmem<TA_STAGES>;
-    auto kern = gemm_tc_ta_kernel<B_MN, SPLIT3>;
+    auto kern = gemm_tc_ta_kernel<A_MN, B_MN, SPLIT3>;
     static bool attr_set = false;
     if (!attr_set) {
         SFB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
         attr_set = true;
     }
-    const int64_t tiles = ceil_div(N, 128) * ceil_div(M, TBM);
+    const int64_t tiles = ceil_div(N, 128) * ceil_div(M, TBM) * splits;
     const int64_t grid = tiles < sm_count() ? tiles : sm_count();
-    kern<<<(unsigned)grid, TC_THREADS, S::TOTAL, st>>>(ta, tb, C, ldc, M, N, K, epi);
+    kern<<<(unsigned)grid, TC_THREADS, S::TOTAL, st>>>(ta, tb, C, ldc, M, N, K, k_chunk, splits, epi,
+                                                        raw_hi_enabled() ? 1 : 0);
     SFB_LAUNCH_OK();
     return 0;
 }
@@ -816,18 +856,6 @@ static int gemm_tc(bool a_mn, const float* A, int64_t lda, bool b_mn, const floa
     const int BN = (N >= 128) ? 128 : 64;
     CUtensorMap ta, tb;
     bool ok;
-    if (!a_mn && BN == 128 && splits == 1 && ta_enabled()) {
-        // K-major A: operand A goes smem -> registers -> TMEM (gemm_tc_ta_kernel)
-        ok = make_tmap(&ta, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, TBK, TBM, false);
-        if (!ok) return SFB_TC_UNSUPPORTED;
-        if (b_mn) ok = make_tmap(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 32, TBK, true);
-        else ok = make_tmap(&tb, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, TBK, 128u, false);
-        if (!ok) return SFB_TC_UNSUPPORTED;
-        if (b_mn) return split3 ? launch_tc_ta<true, true>(ta, tb, C, ldc, M, N, K, epi, st)
-                                : launch_tc_ta<true, false>(ta, tb, C, ldc, M, N, K, epi, st);
-        return split3 ? launch_tc_ta<false, true>(ta, tb, C, ldc, M, N, K, epi, st)
-                      : launch_tc_ta<false, false>(ta, tb, C, ldc, M, N, K, epi, st);
-    }
     if (a_mn) ok = make_tmap(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 32, TBK, true);
     else ok = make_tmap(&ta, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, TBK, TBM, false);
     if (b_mn) ok = ok && make_tmap(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 32, TBK, true);
@@ -842,6 +870,21 @@ static int gemm_tc(bool a_mn, const float* A, int64_t lda, bool b_mn, const floa
     if (splits > 1 && !ws) return SFB_TC_UNSUPPORTED;
     float* out = splits > 1 ? ws : C;
     const int64_t ld_out = splits > 1 ? N : ldc;
+
+    if (BN == 128 && ta_enabled() && (b_mn || !a_mn)) {
+        // A operand from TMEM (gemm_tc_ta_kernel); (A MN-major, B K-major) is not instantiated (no caller)
+#define SFB_TA(AM, BM_)                                                                                                \
+    (split3 ? launch_tc_ta<AM, BM_, true>(ta, tb, out, ld_out, M, N, K, k_chunk, splits, epi, st)                     \
+            : launch_tc_ta<AM, BM_, false>(ta, tb, out, ld_out, M, N, K, k_chunk, splits, epi, st))
+        int rc_ta;
+        if (!a_mn && !b_mn) rc_ta = SFB_TA(false, false);
+        else if (!a_mn && b_mn) rc_ta = SFB_TA(false, true);
+        else rc_ta = SFB_TA(true, true);
+#undef SFB_TA
+        if (rc_ta) return rc_ta;
+        if (splits > 1) return splitk_reduce(ws, splits, M, N, C, ldc, st);
+        return 0;
+    }
 
 #define SFB_TC(AM, BM_, BNv)                                                                                           \
     (split3 ? launch_tc<AM, BM_, BNv, true>(ta, tb, out, ld_out, M, N, K, k_chunk, splits, epi, st)                   \
