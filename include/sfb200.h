@@ -103,6 +103,26 @@ int sfb200_heads_forward(const float* h, int64_t ldh, int64_t rows, int H, int A
                          int64_t log_prob_stride, const float* policy_version_scalar, float* policy_version_out,
                          int64_t pv_stride, void* stream);
 
+/* The last hidden layer and the heads in ONE pass (same reference sites as sfb200_linear_act_forward +
+ * sfb200_heads_forward): the tcgen05 epilogue forms y = act(x W^T + b) in registers and contracts it at once with
+ * [Wv ; Wa], so y is not re-read by a heads kernel -- and not written at all when y == NULL (the sampler never needs
+ * it).  Two calls:
+ *   P = sfb200_linear_heads_partials(N, A, engine)          0 -> shape/engine not covered: use the two separate calls
+ *   sfb200_linear_act_heads_forward(..., head_partials)      head_partials: P * M * 12 floats of scratch
+ *   sfb200_heads_from_partials(head_partials, P, M, A, ...)  same outputs / sampling semantics as sfb200_heads_forward
+ * The partial sums are combined in a fixed order (deterministic). */
+int sfb200_linear_heads_partials(int N, int A, int engine);
+int sfb200_linear_act_heads_forward(const float* x, int64_t ldx, const float* W, const float* b, float* y, int64_t ldy,
+                                    int64_t M, int N, int K, int act, int engine, const float* Wv, const float* Wa,
+                                    int A, float* head_partials, void* stream);
+int sfb200_heads_from_partials(const float* head_partials, int P, int64_t rows, int A, const float* bv, const float* ba,
+                               float* values, int64_t values_stride, float* logits, int64_t logits_stride,
+                               const float* noise, uint64_t philox_seed, uint64_t philox_offset,
+                               const int64_t* philox_offset_dev, float* actions_f32, int64_t actions_stride,
+                               int32_t* env_actions_i32, float* log_prob, int64_t log_prob_stride,
+                               const float* policy_version_scalar, float* policy_version_out, int64_t pv_stride,
+                               void* stream);
+
 /* ------------------------------------------------------------- sampler steps ---- */
 /* BatchedVectorEnvRunner.generate_policy_request (algo/sampling/batched_sampling.py:374-388) fused with the
  * inference-side normalisation (inference_worker.py:326):  traj_obs[:, t] = obs ; traj_rnn[:, t] = rnn ;
@@ -128,6 +148,21 @@ int sfb200_sampler_post_step(const float* rew, const uint8_t* terminated, const 
                              int64_t traj_stride, float* ep_return, int32_t* ep_len, float* ep_min_raw,
                              float* ep_max_raw, int32_t len_increment, double* stats, int64_t* step_counter,
                              float* fin_return_t, int32_t* fin_len_t, void* stream);
+
+/* sfb200_sampler_post_step for step t and sfb200_sampler_pre_step for step t+1 in ONE launch (both only consume the
+ * env's outputs of step t).  traj_obs_next / traj_rnn_next point at element [0, t+1]; x_norm may be NULL (last step of
+ * the rollout: the observation is only recorded, batched_sampling.py:289-296).  With an RNN core, `rnn` must already
+ * hold the done-masked state for t+1. */
+int sfb200_sampler_post_pre_step(const float* rew, const uint8_t* terminated, const uint8_t* truncated, int64_t n_envs,
+                                 float reward_scale, float reward_clip, int32_t policy_id, float* traj_rewards_t,
+                                 uint8_t* traj_dones_t, uint8_t* traj_time_outs_t, int32_t* traj_policy_id_t,
+                                 int64_t traj_stride, float* ep_return, int32_t* ep_len, float* ep_min_raw,
+                                 float* ep_max_raw, int32_t len_increment, double* stats, int64_t* step_counter,
+                                 float* fin_return_t, int32_t* fin_len_t,
+                                 const float* obs, int dim, float* traj_obs_next, int64_t traj_obs_stride,
+                                 const float* rnn, int rnn_dim, float* traj_rnn_next, int64_t traj_rnn_stride,
+                                 float* x_norm, const double* mean, const double* var, float sub_mean, float inv_scale,
+                                 float eps, float clip, void* stream);
 
 /* strided row copy dst[i*dst_stride + 0..dim) = src[i*src_stride + 0..dim) (_finalize_trajectories :289-296) */
 int sfb200_copy_rows(const float* src, int64_t src_stride, float* dst, int64_t dst_stride, int64_t rows, int dim,

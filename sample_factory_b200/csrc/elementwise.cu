@@ -27,84 +27,96 @@ __device__ __forceinline__ void col_stats(const double* mean, const double* var,
     inv_sigma = __fdiv_rn(1.0f, sigma);
 }
 
-// One kernel serves sfb200_normalize_obs and sfb200_sampler_pre_step: optional second output (raw copy into the
-// trajectory at [.., t]) so obs is read from HBM once.
+// One body serves sfb200_normalize_obs, sfb200_sampler_pre_step and the fused post+pre step: optional second output
+// (raw copy into the trajectory at [.., t]) so obs is read from HBM once.
+struct NormArgs {
+    const float* x; int64_t ldx;
+    float* y; int64_t ldy;
+    float* raw_copy; int64_t ld_copy;
+    int64_t rows; int dim;
+    const double* mean; const double* var;
+    float sub, inv_scale; int do_sub, do_scale; float eps, clip;
+    const float* rnn_src; int rnn_dim; float* rnn_dst; int64_t rnn_dst_stride; int64_t rnn_rows;
+};
+
 template <bool VEC4>
-__global__ void __launch_bounds__(256) normalize_kernel(const float* __restrict__ x, int64_t ldx, float* __restrict__ y,
-                                                        int64_t ldy, float* __restrict__ raw_copy, int64_t ld_copy,
-                                                        int64_t rows, int dim, const double* __restrict__ mean,
-                                                        const double* __restrict__ var, float sub, float inv_scale,
-                                                        int do_sub, int do_scale, float eps, float clip,
-                                                        const float* __restrict__ rnn_src, int rnn_dim,
-                                                        float* __restrict__ rnn_dst, int64_t rnn_dst_stride,
-                                                        int64_t rnn_rows) {
-    const bool do_rms = mean != nullptr;
-    if (rnn_src) {   // sampler pre-step: traj.rnn_states[:, t] <- rnn (tiny; folded in to save a launch)
-        const int64_t tot = rnn_rows * rnn_dim;
-        for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < tot; i += (int64_t)gridDim.x * blockDim.x) {
-            const int64_t r = i / rnn_dim;
-            rnn_dst[r * rnn_dst_stride + (i - r * rnn_dim)] = rnn_src[i];
+__device__ __forceinline__ void normalize_body(const NormArgs& a) {
+    const bool do_rms = a.mean != nullptr;
+    const int64_t tid0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t nthr = (int64_t)gridDim.x * blockDim.x;
+    if (a.rnn_src) {   // sampler pre-step: traj.rnn_states[:, t] <- rnn (tiny; folded in to save a launch)
+        const int64_t tot = a.rnn_rows * a.rnn_dim;
+        for (int64_t i = tid0; i < tot; i += nthr) {
+            const int64_t r = i / a.rnn_dim;
+            a.rnn_dst[r * a.rnn_dst_stride + (i - r * a.rnn_dim)] = a.rnn_src[i];
         }
     }
     if (VEC4) {
-        const int dim4 = dim >> 2;
-        const int64_t total = rows * (int64_t)dim4;
-        for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int dim4 = a.dim >> 2;
+        const int64_t total = a.rows * (int64_t)dim4;
+        for (int64_t i = tid0; i < total; i += nthr) {
             const int64_t r = i / dim4;
             const int c = (int)(i - r * dim4) << 2;
-            const float4 v = *reinterpret_cast<const float4*>(x + r * ldx + c);
-            if (raw_copy) *reinterpret_cast<float4*>(raw_copy + r * ld_copy + c) = v;
-            if (y) {
+            const float4 v = *reinterpret_cast<const float4*>(a.x + r * a.ldx + c);
+            if (a.raw_copy) *reinterpret_cast<float4*>(a.raw_copy + r * a.ld_copy + c) = v;
+            if (a.y) {
                 float in[4] = {v.x, v.y, v.z, v.w};
                 float out[4];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     float mu = 0.f, is = 1.f;
-                    if (do_rms) col_stats(mean, var, c + k, eps, mu, is);
-                    out[k] = norm_one(in[k], sub, inv_scale, do_sub, do_scale, do_rms, mu, is, clip);
+                    if (do_rms) col_stats(a.mean, a.var, c + k, a.eps, mu, is);
+                    out[k] = norm_one(in[k], a.sub, a.inv_scale, a.do_sub, a.do_scale, do_rms, mu, is, a.clip);
                 }
-                *reinterpret_cast<float4*>(y + r * ldy + c) = make_float4(out[0], out[1], out[2], out[3]);
+                *reinterpret_cast<float4*>(a.y + r * a.ldy + c) = make_float4(out[0], out[1], out[2], out[3]);
             }
         }
     } else {
-        const int64_t total = rows * (int64_t)dim;
-        for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-            const int64_t r = i / dim;
-            const int c = (int)(i - r * dim);
-            const float v = x[r * ldx + c];
-            if (raw_copy) raw_copy[r * ld_copy + c] = v;
-            if (y) {
+        const int64_t total = a.rows * (int64_t)a.dim;
+        for (int64_t i = tid0; i < total; i += nthr) {
+            const int64_t r = i / a.dim;
+            const int c = (int)(i - r * a.dim);
+            const float v = a.x[r * a.ldx + c];
+            if (a.raw_copy) a.raw_copy[r * a.ld_copy + c] = v;
+            if (a.y) {
                 float mu = 0.f, is = 1.f;
-                if (do_rms) col_stats(mean, var, c, eps, mu, is);
-                y[r * ldy + c] = norm_one(v, sub, inv_scale, do_sub, do_scale, do_rms, mu, is, clip);
+                if (do_rms) col_stats(a.mean, a.var, c, a.eps, mu, is);
+                a.y[r * a.ldy + c] = norm_one(v, a.sub, a.inv_scale, a.do_sub, a.do_scale, do_rms, mu, is, a.clip);
             }
         }
     }
 }
 
+template <bool VEC4>
+__global__ void __launch_bounds__(256) normalize_kernel(const NormArgs a) { normalize_body<VEC4>(a); }
+
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+static bool make_norm_args(NormArgs& a, const float* x, int64_t ldx, float* y, int64_t ldy, float* raw_copy,
+                           int64_t ld_copy, int64_t rows, int dim, const double* mean, const double* var, float sub_mean,
+                           float inv_scale, float eps, float clip, const float* rnn_src, int rnn_dim, float* rnn_dst,
+                           int64_t rnn_dst_stride) {
+    a = NormArgs{x, ldx, y, ldy, raw_copy, ld_copy, rows, dim, mean, var, sub_mean, inv_scale,
+                 fabsf(sub_mean) > 1e-8f, fabsf(inv_scale - 1.0f) > 1e-8f, eps, clip,
+                 rnn_src, rnn_dim, rnn_dst, rnn_dst_stride, rows};
+    return (dim % 4 == 0) && (ldx % 4 == 0) && aligned16(x) && (!y || ((ldy % 4 == 0) && aligned16(y))) &&
+           (!raw_copy || ((ld_copy % 4 == 0) && aligned16(raw_copy)));
+}
 
 static int launch_normalize(const float* x, int64_t ldx, float* y, int64_t ldy, float* raw_copy, int64_t ld_copy,
                             int64_t rows, int dim, const double* mean, const double* var, float sub_mean,
                             float inv_scale, float eps, float clip, cudaStream_t st, const float* rnn_src = nullptr,
                             int rnn_dim = 0, float* rnn_dst = nullptr, int64_t rnn_dst_stride = 0) {
     if (rows == 0 || dim == 0) return 0;
-    const int do_sub = fabsf(sub_mean) > 1e-8f;
-    const int do_scale = fabsf(inv_scale - 1.0f) > 1e-8f;
-    const bool vec = (dim % 4 == 0) && (ldx % 4 == 0) && aligned16(x) && (!y || ((ldy % 4 == 0) && aligned16(y))) &&
-                     (!raw_copy || ((ld_copy % 4 == 0) && aligned16(raw_copy)));
+    NormArgs a;
+    const bool vec = make_norm_args(a, x, ldx, y, ldy, raw_copy, ld_copy, rows, dim, mean, var, sub_mean, inv_scale, eps,
+                                    clip, rnn_src, rnn_dim, rnn_dst, rnn_dst_stride);
     const int64_t work = vec ? rows * (int64_t)(dim / 4) : rows * (int64_t)dim;
     int64_t blocks = ceil_div(work, 256);
     const int64_t cap = (int64_t)sm_count() * 8;
     if (blocks > cap) blocks = cap;
-    if (vec)
-        normalize_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(x, ldx, y, ldy, raw_copy, ld_copy, rows, dim, mean, var,
-                                                                 sub_mean, inv_scale, do_sub, do_scale, eps, clip, rnn_src,
-                                                                 rnn_dim, rnn_dst, rnn_dst_stride, rows);
-    else
-        normalize_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(x, ldx, y, ldy, raw_copy, ld_copy, rows, dim, mean,
-                                                                  var, sub_mean, inv_scale, do_sub, do_scale, eps, clip, rnn_src,
-                                                                  rnn_dim, rnn_dst, rnn_dst_stride, rows);
+    if (vec) normalize_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(a);
+    else normalize_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(a);
     SFB_LAUNCH_OK();
     return 0;
 }
@@ -121,55 +133,65 @@ __global__ void copy_rows_kernel(const float* __restrict__ src, int64_t ss, floa
 }
 
 // ---- post env step -------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) post_step_kernel(const float* __restrict__ rew, const uint8_t* __restrict__ term,
-                                                        const uint8_t* __restrict__ trunc, int64_t n, float reward_scale,
-                                                        float reward_clip, int32_t policy_id, float* __restrict__ t_rew,
-                                                        uint8_t* __restrict__ t_done, uint8_t* __restrict__ t_to,
-                                                        int32_t* __restrict__ t_pid, int64_t stride,
-                                                        float* __restrict__ ep_ret, int32_t* __restrict__ ep_len,
-                                                        float* __restrict__ ep_min, float* __restrict__ ep_max,
-                                                        int32_t len_inc, double* __restrict__ stats,
-                                                        int64_t* __restrict__ step_counter,
-                                                        float* __restrict__ fin_ret, int32_t* __restrict__ fin_len) {
+struct PostArgs {
+    const float* rew; const uint8_t* term; const uint8_t* trunc; int64_t n;
+    float reward_scale, reward_clip; int32_t policy_id;
+    float* t_rew; uint8_t* t_done; uint8_t* t_to; int32_t* t_pid; int64_t stride;
+    float* ep_ret; int32_t* ep_len; float* ep_min; float* ep_max; int32_t len_inc;
+    double* stats; int64_t* step_counter; float* fin_ret; int32_t* fin_len;
+};
+
+// All threads of the grid must call this (warp reductions inside); thread i < n handles env i.
+__device__ __forceinline__ void post_step_body(const PostArgs& a) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (step_counter && i == 0) *step_counter += 1;
+    if (a.step_counter && i == 0) *a.step_counter += 1;
     double c = 0.0, s_ret = 0.0, s_len = 0.0, s_min = 0.0, s_max = 0.0;
-    if (i < n) {
-        const float r_raw = rew[i];
-        const bool tm = term[i] != 0, tr = trunc[i] != 0;
+    if (i < a.n) {
+        const float r_raw = a.rew[i];
+        const bool tm = a.term[i] != 0, tr = a.trunc[i] != 0;
         const bool done = tm || tr;                                   // batched_sampling.py:317
-        float r = __fmul_rn(r_raw, reward_scale);                       // :209
-        r = clampf(r, -reward_clip, reward_clip);                       // :210
-        t_rew[i * stride] = r;
-        t_done[i * stride] = done ? 1 : 0;
-        t_to[i * stride] = tr ? 1 : 0;                                  // :328
-        t_pid[i * stride] = policy_id;
-        if (ep_ret) {
+        float r = __fmul_rn(r_raw, a.reward_scale);                     // :209
+        r = clampf(r, -a.reward_clip, a.reward_clip);                   // :210
+        a.t_rew[i * a.stride] = r;
+        a.t_done[i * a.stride] = done ? 1 : 0;
+        a.t_to[i * a.stride] = tr ? 1 : 0;                              // :328
+        a.t_pid[i * a.stride] = a.policy_id;
+        if (a.ep_ret) {
             // _process_env_step :215-287 (episode accounting uses the RAW reward, :336 passes rewards_cpu)
-            float er = ep_ret[i] + r_raw;
-            int32_t el = ep_len[i] + len_inc;
-            float mn = fminf(ep_min[i], r_raw), mx = fmaxf(ep_max[i], r_raw);
-            if (fin_ret) {
-                fin_ret[i * stride] = done ? er : __int_as_float(0x7fc00000);
-                fin_len[i * stride] = done ? el : -1;
+            float er = a.ep_ret[i] + r_raw;
+            int32_t el = a.ep_len[i] + a.len_inc;
+            float mn = fminf(a.ep_min[i], r_raw), mx = fmaxf(a.ep_max[i], r_raw);
+            if (a.fin_ret) {
+                a.fin_ret[i * a.stride] = done ? er : __int_as_float(0x7fc00000);
+                a.fin_len[i * a.stride] = done ? el : -1;
             }
             if (done) {
                 c = 1.0; s_ret = er; s_len = el; s_min = mn; s_max = mx;
                 er = 0.f; el = 0; mn = INFINITY; mx = -INFINITY;
             }
-            ep_ret[i] = er; ep_len[i] = el; ep_min[i] = mn; ep_max[i] = mx;
+            a.ep_ret[i] = er; a.ep_len[i] = el; a.ep_min[i] = mn; a.ep_max[i] = mx;
         }
     }
-    if (stats) {
+    if (a.stats) {
         c = warp_sum(c);
         if (c > 0.0) {   // warp-uniform after the reduction
             s_ret = warp_sum(s_ret); s_len = warp_sum(s_len); s_min = warp_sum(s_min); s_max = warp_sum(s_max);
             if ((threadIdx.x & 31) == 0) {
-                atomicAdd(stats + 0, c); atomicAdd(stats + 1, s_ret); atomicAdd(stats + 2, s_len);
-                atomicAdd(stats + 3, s_min); atomicAdd(stats + 4, s_max);
+                atomicAdd(a.stats + 0, c); atomicAdd(a.stats + 1, s_ret); atomicAdd(a.stats + 2, s_len);
+                atomicAdd(a.stats + 3, s_min); atomicAdd(a.stats + 4, s_max);
             }
         }
     }
+}
+
+__global__ void __launch_bounds__(256) post_step_kernel(const PostArgs a) { post_step_body(a); }
+
+// advance_rollouts part 2 of step t fused with generate_policy_request + normalisation of step t+1 (both consume the
+// env's outputs; nothing sits between them on the stream): one launch instead of two per env step.
+template <bool VEC4>
+__global__ void __launch_bounds__(256) post_pre_step_kernel(const PostArgs pa, const NormArgs na) {
+    post_step_body(pa);
+    normalize_body<VEC4>(na);
 }
 
 // ---- synthetic tape env ---------------------------------------------------------------------------------------------
@@ -284,21 +306,72 @@ int sfb200_copy_rows(const float* src, int64_t src_stride, float* dst, int64_t d
     return 0;
 }
 
+static int make_post_args(PostArgs& a, const float* rew, const uint8_t* terminated, const uint8_t* truncated,
+                          int64_t n_envs, float reward_scale, float reward_clip, int32_t policy_id, float* traj_rewards_t,
+                          uint8_t* traj_dones_t, uint8_t* traj_time_outs_t, int32_t* traj_policy_id_t,
+                          int64_t traj_stride, float* ep_return, int32_t* ep_len, float* ep_min_raw, float* ep_max_raw,
+                          int32_t len_increment, double* stats, int64_t* step_counter, float* fin_return_t,
+                          int32_t* fin_len_t) {
+    SFB_CHECK_ARG(!fin_return_t == !fin_len_t, "sampler_post_step: fin_return_t and fin_len_t come together");
+    SFB_CHECK_ARG(rew && terminated && truncated && traj_rewards_t && traj_dones_t && traj_time_outs_t &&
+                      traj_policy_id_t, "sampler_post_step: NULL argument");
+    SFB_CHECK_ARG(!ep_return || (ep_len && ep_min_raw && ep_max_raw), "sampler_post_step: episode arrays incomplete");
+    a = PostArgs{rew, terminated, truncated, n_envs, reward_scale, reward_clip, policy_id, traj_rewards_t, traj_dones_t,
+                 traj_time_outs_t, traj_policy_id_t, traj_stride, ep_return, ep_len, ep_min_raw, ep_max_raw,
+                 len_increment, ep_return ? stats : nullptr, step_counter, ep_return ? fin_return_t : nullptr, fin_len_t};
+    return 0;
+}
+
 int sfb200_sampler_post_step(const float* rew, const uint8_t* terminated, const uint8_t* truncated, int64_t n_envs,
                              float reward_scale, float reward_clip, int32_t policy_id, float* traj_rewards_t,
                              uint8_t* traj_dones_t, uint8_t* traj_time_outs_t, int32_t* traj_policy_id_t,
                              int64_t traj_stride, float* ep_return, int32_t* ep_len, float* ep_min_raw,
                              float* ep_max_raw, int32_t len_increment, double* stats, int64_t* step_counter,
                              float* fin_return_t, int32_t* fin_len_t, void* stream) {
-    SFB_CHECK_ARG(!fin_return_t == !fin_len_t, "sampler_post_step: fin_return_t and fin_len_t come together");
-    SFB_CHECK_ARG(rew && terminated && truncated && traj_rewards_t && traj_dones_t && traj_time_outs_t &&
-                      traj_policy_id_t, "sampler_post_step: NULL argument");
-    SFB_CHECK_ARG(!ep_return || (ep_len && ep_min_raw && ep_max_raw), "sampler_post_step: episode arrays incomplete");
+    PostArgs a;
+    if (int rc = make_post_args(a, rew, terminated, truncated, n_envs, reward_scale, reward_clip, policy_id,
+                                traj_rewards_t, traj_dones_t, traj_time_outs_t, traj_policy_id_t, traj_stride, ep_return,
+                                ep_len, ep_min_raw, ep_max_raw, len_increment, stats, step_counter, fin_return_t,
+                                fin_len_t))
+        return rc;
     if (n_envs == 0) return 0;
-    post_step_kernel<<<(unsigned)ceil_div(n_envs, 256), 256, 0, (cudaStream_t)stream>>>(
-        rew, terminated, truncated, n_envs, reward_scale, reward_clip, policy_id, traj_rewards_t, traj_dones_t,
-        traj_time_outs_t, traj_policy_id_t, traj_stride, ep_return, ep_len, ep_min_raw, ep_max_raw, len_increment,
-        ep_return ? stats : nullptr, step_counter, ep_return ? fin_return_t : nullptr, fin_len_t);
+    post_step_kernel<<<(unsigned)ceil_div(n_envs, 256), 256, 0, (cudaStream_t)stream>>>(a);
+    SFB_LAUNCH_OK();
+    return 0;
+}
+
+int sfb200_sampler_post_pre_step(const float* rew, const uint8_t* terminated, const uint8_t* truncated, int64_t n_envs,
+                                 float reward_scale, float reward_clip, int32_t policy_id, float* traj_rewards_t,
+                                 uint8_t* traj_dones_t, uint8_t* traj_time_outs_t, int32_t* traj_policy_id_t,
+                                 int64_t traj_stride, float* ep_return, int32_t* ep_len, float* ep_min_raw,
+                                 float* ep_max_raw, int32_t len_increment, double* stats, int64_t* step_counter,
+                                 float* fin_return_t, int32_t* fin_len_t,
+                                 const float* obs, int dim, float* traj_obs_next, int64_t traj_obs_stride,
+                                 const float* rnn, int rnn_dim, float* traj_rnn_next, int64_t traj_rnn_stride,
+                                 float* x_norm, const double* mean, const double* var, float sub_mean, float inv_scale,
+                                 float eps, float clip, void* stream) {
+    PostArgs pa;
+    if (int rc = make_post_args(pa, rew, terminated, truncated, n_envs, reward_scale, reward_clip, policy_id,
+                                traj_rewards_t, traj_dones_t, traj_time_outs_t, traj_policy_id_t, traj_stride, ep_return,
+                                ep_len, ep_min_raw, ep_max_raw, len_increment, stats, step_counter, fin_return_t,
+                                fin_len_t))
+        return rc;
+    SFB_CHECK_ARG(obs && traj_obs_next && dim > 0, "sampler_post_pre_step: bad arguments");
+    SFB_CHECK_ARG((mean == nullptr) == (var == nullptr), "sampler_post_pre_step: mean/var must both be set or both NULL");
+    if (n_envs == 0) return 0;
+    const bool with_rnn = rnn && traj_rnn_next && rnn_dim > 0;
+    NormArgs na;
+    const bool vec = make_norm_args(na, obs, dim, x_norm, dim, traj_obs_next, traj_obs_stride, n_envs, dim, mean, var,
+                                    sub_mean, inv_scale, eps, clip, with_rnn ? rnn : nullptr, rnn_dim, traj_rnn_next,
+                                    traj_rnn_stride);
+    const int64_t work = vec ? n_envs * (int64_t)(dim / 4) : n_envs * (int64_t)dim;
+    int64_t blocks = ceil_div(work, 256);
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < ceil_div(n_envs, 256)) blocks = ceil_div(n_envs, 256);   // every env needs its post-step thread
+    cudaStream_t st = (cudaStream_t)stream;
+    if (vec) post_pre_step_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(pa, na);
+    else post_pre_step_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(pa, na);
     SFB_LAUNCH_OK();
     return 0;
 }

@@ -10,6 +10,10 @@ constexpr int SFB_TC_UNSUPPORTED = -1000;   // shape/alignment not handled by th
 // tcgen05 engine (gemm_tc.cu). Return 0, an error code, or SFB_TC_UNSUPPORTED.
 int tc_linear_act_forward(const float* x, int64_t ldx, const float* W, const float* b, float* y, int64_t ldy, int64_t M,
                           int N, int K, int act, int engine, cudaStream_t st);
+int tc_linear_heads_partials(int N, int A, int engine);
+int tc_linear_act_heads_forward(const float* x, int64_t ldx, const float* W, const float* b, float* y, int64_t ldy,
+                                int64_t M, int N, int K, int act, int engine, const float* Wv, const float* Wa, int A,
+                                float* head_part, cudaStream_t st);
 int tc_linear_backward(const float* dz, int64_t lddz, const float* x, int64_t ldx, const float* W, int64_t M, int N,
                        int K, int act_prev, float* dW, float* dx, int64_t lddx, int engine, float* ws, cudaStream_t st);
 

@@ -292,6 +292,22 @@ int sfb200_linear_act_forward(const float* x, int64_t ldx, const float* W, const
     return gemm_simt(true, x, ldx, true, W, K, y, ldy, M, N, K, 1, epi, nullptr, st);
 }
 
+int sfb200_linear_heads_partials(int N, int A, int engine) { return tc_linear_heads_partials(N, A, engine); }
+
+int sfb200_linear_act_heads_forward(const float* x, int64_t ldx, const float* W, const float* b, float* y, int64_t ldy,
+                                    int64_t M, int N, int K, int act, int engine, const float* Wv, const float* Wa,
+                                    int A, float* head_partials, void* stream) {
+    SFB_CHECK_ARG(x && W && b && Wv && Wa && head_partials && M >= 0 && N > 0 && K > 0,
+                  "linear_act_heads_forward: bad arguments");
+    if (M == 0) return 0;
+    int rc = tc_linear_act_heads_forward(x, ldx, W, b, y, ldy, M, N, K, act, engine, Wv, Wa, A, head_partials,
+                                         (cudaStream_t)stream);
+    SFB_CHECK_ARG(rc != SFB_TC_UNSUPPORTED,
+                  "linear_act_heads_forward: shape/engine not covered (N=%d K=%d A=%d engine=%d); "
+                  "sfb200_linear_heads_partials() tells when to use the separate calls", N, K, A, engine);
+    return rc;
+}
+
 int64_t sfb200_linear_backward_workspace_bytes(int64_t M, int N, int K) {
     // split-K slabs for dW [N,K] reduced over M, plus colsum partials for db_prev [K]
     const int splits = choose_splits(N, K, (int)(M > 0x7fffffff ? 0x7fffffff : M));

@@ -108,6 +108,14 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
           "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
 // D[tmem] (+)= A[tmem] * B[smem desc]: the A operand is read from tensor memory (rows = TMEM lanes, k = 32-bit columns)
 __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -164,7 +172,16 @@ struct TcEpilogue {
     const float* bias;
     const float* aux;
     int64_t ld_aux;
+    // fused policy/value heads (mode 1 only): partial dot products of the activated output row with [Wv ; Wa] over this
+    // thread's 64 columns -> head_part[(n_tile*2 + half)][m][kHeadPad]; C may be NULL (output row not stored)
+    const float* head_wv;
+    const float* head_wa;
+    int head_A;
+    float* head_part;
 };
+
+constexpr int kHeadAP = 9;     // value + up to 8 action outputs
+constexpr int kHeadPad = 12;   // floats per (partial, row): three 16 B stores
 
 template <int BN, int STAGES>
 struct TcSmem {
@@ -363,6 +380,81 @@ __device__ __forceinline__ void tc_epilogue_tile(uint32_t tmem_slot_addr, uint64
             }
 }
 
+
+// Epilogue with the policy/value heads folded in (forward layers feeding critic_linear / distribution_linear,
+// actor_critic.py:171-186): y = act(acc + bias) is formed in registers, optionally stored, and immediately contracted
+// with the (A+1) head weight rows staged in shared memory -- the separate heads kernel's re-read of y (4*N bytes per
+// row) disappears, and in the sampler y is not written at all.  16-column chunks keep the live set (16 + 16 accumulator
+// words, 9 partial sums) inside the 128-register budget.
+template <int BN, bool SPLIT3, int ACT>
+__device__ __forceinline__ void tc_epilogue_tile_heads(uint32_t tmem_slot_addr, uint64_t* acc_full_bar, uint32_t acc_ph,
+                                                       uint64_t* acc_empty_bar, const TileCoord& tc, const EpiCtx& ec,
+                                                       float* __restrict__ C, int64_t ldc, int64_t M, int N,
+                                                       const TcEpilogue& epi, const float* __restrict__ headw_s) {
+    constexpr int CH = BN / 2;
+    const int64_t m = tc.m0 + ec.lane_base + ec.lane;
+    const int nbeg = tc.n0 + ec.col0;
+    float hp[kHeadAP];
+#pragma unroll
+    for (int a = 0; a < kHeadAP; ++a) hp[a] = 0.f;
+    mbar_wait(acc_full_bar, acc_ph);
+    tc_fence_after();
+    const uint32_t t_main = tmem_slot_addr + ((uint32_t)ec.lane_base << 16) + (uint32_t)ec.col0;
+    float* dst_row = (C && m < M) ? C + m * ldc + nbeg : nullptr;
+#pragma unroll 1
+    for (int c0 = 0; c0 < CH; c0 += 16) {
+        float o[16];
+        {
+            uint32_t r[16];
+            tmem_ld_32x32b_x16(t_main + (uint32_t)c0, r);
+            if (SPLIT3) {
+                uint32_t r2[16];
+                tmem_ld_32x32b_x16(t_main + (uint32_t)(BN + c0), r2);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) o[j] = __uint_as_float(r[j]) + __uint_as_float(r2[j]);
+            } else {
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) o[j] = __uint_as_float(r[j]);
+            }
+        }
+        if (c0 + 16 >= CH) {
+            tc_fence_before();
+            mbar_arrive(acc_empty_bar);
+        }
+        const float* bias_n0 = ec.bias_base + nbeg + c0;   // staged in shared memory (host guarantees N <= BIAS_FLOATS)
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+            const float4 b = *reinterpret_cast<const float4*>(bias_n0 + j);
+            o[j] = act_fwd_ct<ACT>(o[j] + b.x);
+            o[j + 1] = act_fwd_ct<ACT>(o[j + 1] + b.y);
+            o[j + 2] = act_fwd_ct<ACT>(o[j + 2] + b.z);
+            o[j + 3] = act_fwd_ct<ACT>(o[j + 3] + b.w);
+            if (dst_row) *reinterpret_cast<float4*>(dst_row + c0 + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+        }
+#pragma unroll
+        for (int a = 0; a < kHeadAP; ++a) {
+            const float* w = headw_s + a * N + nbeg + c0;   // warp-uniform address: shared-memory broadcast
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+                const float4 wv = *reinterpret_cast<const float4*>(w + j);
+                hp[a] = fmaf(o[j], wv.x, hp[a]);
+                hp[a] = fmaf(o[j + 1], wv.y, hp[a]);
+                hp[a] = fmaf(o[j + 2], wv.z, hp[a]);
+                hp[a] = fmaf(o[j + 3], wv.w, hp[a]);
+            }
+        }
+    }
+    if (m < M) {
+        const int p = (tc.n0 / BN) * 2 + (ec.col0 ? 1 : 0);
+        float4* dst = reinterpret_cast<float4*>(epi.head_part + ((int64_t)p * M + m) * kHeadPad);
+        dst[0] = make_float4(hp[0], hp[1], hp[2], hp[3]);
+        dst[1] = make_float4(hp[4], hp[5], hp[6], hp[7]);
+        dst[2] = make_float4(hp[8], 0.f, 0.f, 0.f);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ the kernel
 template <bool A_MN, bool B_MN, int BN, int STAGES, bool SPLIT3>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -555,9 +647,11 @@ struct TaSmem {
     static constexpr int NUM_BARS = 3 * STAGES + 2;
     static constexpr int BIAS_FLOATS = 2048;
     static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 + 512 + BIAS_FLOATS * 4;
+    static constexpr int HEADW_FLOATS = kHeadAP * 512;   // fused heads: (A+1) x N weights, N <= 512
+    static constexpr int TOTAL_HEADS = TOTAL + HEADW_FLOATS * 4;
 };
 
-template <bool A_MN, bool B_MN, bool SPLIT3>
+template <bool A_MN, bool B_MN, bool SPLIT3, bool HEADS>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_ta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                   float* __restrict__ C, int64_t ldc, int64_t M, int N, int K, int k_chunk, int splits, TcEpilogue epi,
@@ -731,11 +825,41 @@ gemm_tc_ta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         }
     } else {
         // ===================================================== epilogue (single accumulator slot)
+        float* headw_s = bias_s + S::BIAS_FLOATS;
+        if (HEADS) {
+            // [kHeadAP][N]: row 0 = critic weights, rows 1..A = distribution_linear rows, the rest zero
+            for (int i = threadIdx.x - 192; i < kHeadAP * N; i += 256) {
+                const int a = i / N, n = i - a * N;
+                headw_s[i] = (a == 0) ? epi.head_wv[n] : (a <= epi.head_A ? epi.head_wa[(int64_t)(a - 1) * N + n] : 0.f);
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+        }
         const EpiCtx ec = make_epi_ctx<BN>(warp, lane, C, ldc, N, splits, epi, bias_s, S::BIAS_FLOATS);
         uint32_t tile_iter = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_iter) {
             const TileCoord tc = tile_coord(tile, tiles_n, tiles_per_z, BN, K, k_chunk);
-            tc_epilogue_tile<BN, SPLIT3>(tmem_base, acc_full, tile_iter & 1, acc_empty, tc, ec, C, ldc, M, N, splits, epi);
+            if (HEADS) {
+                switch (epi.act) {
+                    case SFB200_ACT_ELU:
+                        tc_epilogue_tile_heads<BN, SPLIT3, SFB200_ACT_ELU>(tmem_base, acc_full, tile_iter & 1, acc_empty, tc, ec, C,
+                                                                           ldc, M, N, epi, headw_s);
+                        break;
+                    case SFB200_ACT_RELU:
+                        tc_epilogue_tile_heads<BN, SPLIT3, SFB200_ACT_RELU>(tmem_base, acc_full, tile_iter & 1, acc_empty, tc, ec,
+                                                                            C, ldc, M, N, epi, headw_s);
+                        break;
+                    case SFB200_ACT_TANH:
+                        tc_epilogue_tile_heads<BN, SPLIT3, SFB200_ACT_TANH>(tmem_base, acc_full, tile_iter & 1, acc_empty, tc, ec,
+                                                                            C, ldc, M, N, epi, headw_s);
+                        break;
+                    default:
+                        tc_epilogue_tile_heads<BN, SPLIT3, SFB200_ACT_NONE>(tmem_base, acc_full, tile_iter & 1, acc_empty, tc, ec,
+                                                                            C, ldc, M, N, epi, headw_s);
+                        break;
+                }
+            } else {
+                tc_epilogue_tile<BN, SPLIT3>(tmem_base, acc_full, tile_iter & 1, acc_empty, tc, ec, C, ldc, M, N, splits, epi);
+            }
         }
     }
     tc_fence_before();
@@ -819,20 +943,21 @@ static bool raw_hi_enabled() {
     return v == 1;
 }
 
-template <bool A_MN, bool B_MN, bool SPLIT3>
+template <bool A_MN, bool B_MN, bool SPLIT3, bool HEADS = false>
 static int launch_tc_ta(const CUtensorMap& ta, const CUtensorMap& tb, float* C, int64_t ldc, int64_t M, int N, int K,
                         int k_chunk, int splits, const TcEpilogue& epi, cudaStream_t st) {
     using S = TaSmem<TA_STAGES>;
-    auto kern = gemm_tc_ta_kernel<A_MN, B_MN, SPLIT3>;
+    auto kern = gemm_tc_ta_kernel<A_MN, B_MN, SPLIT3, HEADS>;
+    constexpr int SMEM = HEADS ? S::TOTAL_HEADS : S::TOTAL;
     static bool attr_set = false;
     if (!attr_set) {
-        SFB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+        SFB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
         attr_set = true;
     }
     const int64_t tiles = ceil_div(N, 128) * ceil_div(M, TBM) * splits;
     const int64_t grid = tiles < sm_count() ? tiles : sm_count();
-    kern<<<(unsigned)grid, TC_THREADS, S::TOTAL, st>>>(ta, tb, C, ldc, M, N, K, k_chunk, splits, epi,
-                                                        raw_hi_enabled() ? 1 : 0);
+    kern<<<(unsigned)grid, TC_THREADS, SMEM, st>>>(ta, tb, C, ldc, M, N, K, k_chunk, splits, epi,
+                                                    raw_hi_enabled() ? 1 : 0);
     SFB_LAUNCH_OK();
     return 0;
 }
@@ -871,13 +996,17 @@ static int gemm_tc(bool a_mn, const float* A, int64_t lda, bool b_mn, const floa
     float* out = splits > 1 ? ws : C;
     const int64_t ld_out = splits > 1 ? N : ldc;
 
+    if (epi.head_part && !(BN == 128 && ta_enabled() && !a_mn && !b_mn && splits == 1)) return SFB_TC_UNSUPPORTED;
     if (BN == 128 && ta_enabled() && (b_mn || !a_mn)) {
         // A operand from TMEM (gemm_tc_ta_kernel); (A MN-major, B K-major) is not instantiated (no caller)
 #define SFB_TA(AM, BM_)                                                                                                \
     (split3 ? launch_tc_ta<AM, BM_, true>(ta, tb, out, ld_out, M, N, K, k_chunk, splits, epi, st)                     \
             : launch_tc_ta<AM, BM_, false>(ta, tb, out, ld_out, M, N, K, k_chunk, splits, epi, st))
         int rc_ta;
-        if (!a_mn && !b_mn) rc_ta = SFB_TA(false, false);
+        if (epi.head_part) {
+            rc_ta = split3 ? launch_tc_ta<false, false, true, true>(ta, tb, out, ld_out, M, N, K, k_chunk, splits, epi, st)
+                           : launch_tc_ta<false, false, false, true>(ta, tb, out, ld_out, M, N, K, k_chunk, splits, epi, st);
+        } else if (!a_mn && !b_mn) rc_ta = SFB_TA(false, false);
         else if (!a_mn && b_mn) rc_ta = SFB_TA(false, true);
         else rc_ta = SFB_TA(true, true);
 #undef SFB_TA
@@ -911,6 +1040,24 @@ int tc_linear_act_forward(const float* x, int64_t ldx, const float* W, const flo
                           int N, int K, int act, int engine, cudaStream_t st) {
     TcEpilogue epi{1, act, b, nullptr, 0};
     return gemm_tc(false, x, ldx, false, W, K, y, ldy, M, N, K, 1, epi, nullptr, engine == SFB200_GEMM_TC_3XTF32, st);
+}
+
+// Number of head partials the fused forward produces per row for an N-wide layer, or 0 when the fused path does not
+// cover the shape (callers then run the layer and the heads kernel separately).
+int tc_linear_heads_partials(int N, int A, int engine) {
+    if (engine == SFB200_GEMM_SIMT_FP32 || !tc_init() || !ta_enabled()) return 0;
+    if (N % 128 != 0 || N > 512 || A < 1 || A + 1 > kHeadAP) return 0;
+    return 2 * (N / 128);
+}
+
+int tc_linear_act_heads_forward(const float* x, int64_t ldx, const float* W, const float* b, float* y, int64_t ldy,
+                                int64_t M, int N, int K, int act, int engine, const float* Wv, const float* Wa, int A,
+                                float* head_part, cudaStream_t st) {
+    if (tc_linear_heads_partials(N, A, engine) == 0 || !b) return SFB_TC_UNSUPPORTED;
+    if (y && (ldy % 4 != 0 || (reinterpret_cast<uintptr_t>(y) & 15u))) return SFB_TC_UNSUPPORTED;
+    if (reinterpret_cast<uintptr_t>(head_part) & 15u) return SFB_TC_UNSUPPORTED;
+    TcEpilogue epi{1, act, b, nullptr, 0, Wv, Wa, A, head_part};
+    return gemm_tc(false, x, ldx, false, W, K, y, y ? ldy : N, M, N, K, 1, epi, nullptr, engine == SFB200_GEMM_TC_3XTF32, st);
 }
 
 int tc_linear_backward(const float* dz, int64_t lddz, const float* x, int64_t ldx, const float* W, int64_t M, int N, int K,

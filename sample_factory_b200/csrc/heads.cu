@@ -9,6 +9,82 @@ namespace sfb {
 
 constexpr int kHeadsMaxGroups = 512;
 
+
+struct HeadsOut {
+    float* values; int64_t values_stride;
+    float* logits; int64_t logits_stride;
+    float* actions_f32; int64_t actions_stride;
+    int32_t* env_actions;
+    float* log_prob; int64_t log_prob_stride;
+    float* pv_out; int64_t pv_stride;
+};
+
+// Lane a of the warp holds output a of one row (0 = value, 1..A = logits, bias included): store them and, in sampling
+// mode, run CategoricalActionDistribution (action_distributions.py:110-148) on the lanes.
+__device__ __forceinline__ void heads_row_tail(float mine, int lane, int A, int64_t row, const HeadsOut& out,
+                                               const float* __restrict__ noise, uint64_t seed, uint64_t offset, float pv) {
+    if (lane == 0) out.values[row * out.values_stride] = mine;
+    const bool is_logit = lane >= 1 && lane <= A;
+    if (out.logits && is_logit) out.logits[row * out.logits_stride + (lane - 1)] = mine;
+    if (out.actions_f32 == nullptr) return;   // values / logits only (warp-uniform)
+
+    const float x = is_logit ? mine : -INFINITY;
+    const float m = warp_max(x);
+    const float e = is_logit ? expf(x - m) : 0.f;
+    const float s = warp_sum(e);
+    const float p = __fdiv_rn(e, s);                    // softmax :116
+    const float logp = (x - m) - logf(s);               // log_softmax :125
+    float q = 1.f;
+    if (is_logit) {
+        if (noise) q = noise[row * A + (lane - 1)];
+        else {
+            curandStatePhilox4_32_10_t st;
+            curand_init(seed, (unsigned long long)(row * A + (lane - 1)), offset, &st);
+            q = -logf(curand_uniform(&st));             // Exp(1); uniform is in (0, 1]
+            q = fmaxf(q, 1.0e-30f);
+        }
+    }
+    // torch.multinomial(p, 1, True) == argmax(p / q) (first index on ties)
+    float best = is_logit ? __fdiv_rn(p, q) : -INFINITY;
+    int idx = is_logit ? (lane - 1) : 0x7fffffff;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+        if (ob > best || (ob == best && oi < idx)) { best = ob; idx = oi; }
+    }
+    const float lp = __shfl_sync(0xffffffffu, logp, idx + 1);   // log_prob :145-148
+    if (lane == 0) {
+        out.actions_f32[row * out.actions_stride] = (float)idx;
+        if (out.env_actions) out.env_actions[row] = idx;
+        if (out.log_prob) out.log_prob[row * out.log_prob_stride] = lp;
+        if (out.pv_out) out.pv_out[row * out.pv_stride] = pv;
+    }
+}
+
+// Heads from the partial dot products left by the fused GEMM epilogue (gemm_tc.cu, tc_epilogue_tile_heads):
+// part[p][row][kPad], summed over p in fixed order (deterministic).  One warp per row, lane a = output a.
+constexpr int kHeadPartPad = 12;
+__global__ void __launch_bounds__(256) heads_from_partials_kernel(
+    const float* __restrict__ part, int P, int64_t rows, int A, const float* __restrict__ bv, const float* __restrict__ ba,
+    HeadsOut out, const float* __restrict__ noise, uint64_t seed, uint64_t offset_host,
+    const int64_t* __restrict__ offset_dev, const float* __restrict__ pv_scalar) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const float pv = pv_scalar ? *pv_scalar : 0.f;
+    const uint64_t offset = offset_host + (offset_dev ? (uint64_t)*offset_dev : 0ull);
+    const float my_bias = (lane == 0) ? bv[0] : (lane <= A ? ba[lane - 1] : 0.f);
+    for (int64_t row = warp; row < rows; row += nwarps) {
+        float mine = 0.f;
+        if (lane <= A) {
+            for (int p = 0; p < P; ++p) mine += part[((int64_t)p * rows + row) * kHeadPartPad + lane];
+        }
+        mine += my_bias;
+        heads_row_tail(mine, lane, A, row, out, noise, seed, offset, pv);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // forward (+ optional sampling).  One warp handles RPW rows at a time; lane l owns columns l, l+32, ...
 // Wcat (smem): row 0 = Wv, rows 1..A = Wa.  AP = compile-time bound on A+1.
@@ -36,6 +112,8 @@ __global__ void __launch_bounds__(256) heads_forward_kernel(
     const float pv = pv_scalar ? *pv_scalar : 0.f;
     const uint64_t offset = offset_host + (offset_dev ? (uint64_t)*offset_dev : 0ull);
     const float my_bias = (lane == 0) ? bv[0] : (lane <= A ? ba[lane - 1] : 0.f);
+    const HeadsOut out{values, values_stride, logits, logits_stride, actions_f32, actions_stride, env_actions,
+                       log_prob, log_prob_stride, pv_out, pv_stride};
 
     for (int64_t r0 = warp * RPW; r0 < rows; r0 += nwarps * RPW) {
         float acc[RPW][AP];
@@ -96,44 +174,7 @@ __global__ void __launch_bounds__(256) heads_forward_kernel(
                 }
             }
             mine += my_bias;
-            if (lane == 0) values[row * values_stride] = mine;
-            const bool is_logit = lane >= 1 && lane <= A;
-            if (logits && is_logit) logits[row * logits_stride + (lane - 1)] = mine;
-            if (actions_f32 == nullptr) continue;   // values / logits only
-
-            // CategoricalActionDistribution (action_distributions.py:110-148)
-            const float x = is_logit ? mine : -INFINITY;
-            const float m = warp_max(x);
-            const float e = is_logit ? expf(x - m) : 0.f;
-            const float s = warp_sum(e);
-            const float p = __fdiv_rn(e, s);                    // softmax :116
-            const float logp = (x - m) - logf(s);               // log_softmax :125
-            float q = 1.f;
-            if (is_logit) {
-                if (noise) q = noise[row * A + (lane - 1)];
-                else {
-                    curandStatePhilox4_32_10_t st;
-                    curand_init(seed, (unsigned long long)(row * A + (lane - 1)), offset, &st);
-                    q = -logf(curand_uniform(&st));             // Exp(1); uniform is in (0, 1]
-                    q = fmaxf(q, 1.0e-30f);
-                }
-            }
-            // torch.multinomial(p, 1, True) == argmax(p / q) (first index on ties)
-            float best = is_logit ? __fdiv_rn(p, q) : -INFINITY;
-            int idx = is_logit ? (lane - 1) : 0x7fffffff;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-                const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
-                if (ob > best || (ob == best && oi < idx)) { best = ob; idx = oi; }
-            }
-            const float lp = __shfl_sync(0xffffffffu, logp, idx + 1);   // log_prob :145-148
-            if (lane == 0) {
-                actions_f32[row * actions_stride] = (float)idx;
-                if (env_actions) env_actions[row] = idx;
-                if (log_prob) log_prob[row * log_prob_stride] = lp;
-                if (pv_out) pv_out[row * pv_stride] = pv;
-            }
+            heads_row_tail(mine, lane, A, row, out, noise, seed, offset, pv);
         }
     }
 }
@@ -377,6 +418,28 @@ int sfb200_heads_forward(const float* h, int64_t ldh, int64_t rows, int H, int A
     if (vec) SFB_HF(32, 1, true);
     SFB_HF(32, 1, false);
 #undef SFB_HF
+}
+
+int sfb200_heads_from_partials(const float* head_partials, int P, int64_t rows, int A, const float* bv, const float* ba,
+                               float* values, int64_t values_stride, float* logits, int64_t logits_stride,
+                               const float* noise, uint64_t philox_seed, uint64_t philox_offset,
+                               const int64_t* philox_offset_dev, float* actions_f32, int64_t actions_stride,
+                               int32_t* env_actions_i32, float* log_prob, int64_t log_prob_stride,
+                               const float* policy_version_scalar, float* policy_version_out, int64_t pv_stride,
+                               void* stream) {
+    SFB_CHECK_ARG(head_partials && bv && ba && values && rows >= 0 && P >= 1, "heads_from_partials: bad arguments");
+    SFB_CHECK_ARG(A >= 1 && A + 1 <= kHeadPartPad, "heads_from_partials: supports 1 <= A <= %d, got %d", kHeadPartPad - 1, A);
+    if (rows == 0) return 0;
+    const HeadsOut out{values, values_stride, logits, logits_stride, actions_f32, actions_stride, env_actions_i32,
+                       log_prob, log_prob_stride, policy_version_out, pv_stride};
+    int64_t blocks = ceil_div(rows, 8);
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    heads_from_partials_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        head_partials, P, rows, A, bv, ba, out, noise, philox_seed, philox_offset, philox_offset_dev,
+        policy_version_scalar);
+    SFB_LAUNCH_OK();
+    return 0;
 }
 
 int64_t sfb200_heads_backward_workspace_bytes(int H, int A) {

@@ -21,6 +21,7 @@ from torch import Tensor
 from . import ops
 from .dist_utils import pooled_moments_
 from .model import PolicyModel
+from .policy import HeadsPlan, forward_policy
 from .rnn_core import RnnCore
 
 
@@ -188,6 +189,7 @@ class Learner:
             lin_ws = max(lin_ws, ops.linear_backward_workspace_bytes(B, h, d) // 4 + 4)
             d = h
         self.lin_ws = torch.empty(lin_ws, **f32)
+        self.heads_plan = HeadsPlan(model, engine, max(B, self.N))
         self.adam_ws = torch.empty(1024, **f32)
         self.opt_step = 0
         self.kernel_launches = 0
@@ -205,20 +207,6 @@ class Learner:
         if self.world_size > 1:
             total = pooled_moments_(bmean[:dim], bvar[:dim], rows, self.pg)
         ops.rms_merge(mean, var, count, bmean[:dim], bvar[:dim], float(total))
-
-    def _forward_hidden(self, x: Tensor, outs: List[Tensor], rnn_fn=None) -> Tensor:
-        """encoder MLP -> (recurrent core) -> decoder MLP (actor_critic.py:160-170). outs: one buffer per MLP layer."""
-        M = x.shape[0]
-        enc, dec = self.model.encoder_layers(), self.model.decoder_layers()
-        for i, (W, b) in enumerate(enc):
-            ops.linear_act_forward(x, W, b, outs[i][:M], self.act, self.engine)
-            x = outs[i][:M]
-        if self.rnn is not None:
-            x = rnn_fn(x)
-        for j, (W, b) in enumerate(dec):
-            ops.linear_act_forward(x, W, b, outs[len(enc) + j][:M], self.act, self.engine)
-            x = outs[len(enc) + j][:M]
-        return x
 
     # ------------------------------------------------------------------------------------------------------------
     def _prepare_batch(self, batch: Dict[str, Tensor]) -> None:
@@ -247,10 +235,9 @@ class Learner:
         boot_rnn = None
         if self.rnn is not None:
             boot_rnn = lambda head: self.rnn.step(head, batch["rnn_states"][:, T], self.boot_state_out, self.rnn_boot)
-        x = self._forward_hidden(self.normalized_obs[:, T], self.h_boot, boot_rnn)
-        Wv, bv = m.critic
-        Wa, ba = m.actor
-        ops.heads_forward(x, Wv, bv, Wa, ba, values=batch["values"][:, T], values_stride=batch["values"].stride(0))
+        forward_policy(m, self.normalized_obs[:, T], self.h_boot, self.act, self.engine, self.heads_plan,
+                       dict(values=batch["values"][:, T], values_stride=batch["values"].stride(0)), boot_rnn,
+                       store_tail=False)
         # :969-1003 fused
         ops.gae_returns(batch["rewards"], batch["dones"], batch["time_outs"], batch["values"], batch["valids"],
                         cfg.gamma, cfg.gae_lambda, cfg.value_bootstrap,
@@ -291,11 +278,11 @@ class Learner:
         if self.rnn is not None:
             mb_rnn = lambda head: self.rnn.forward_bptt(head, self.rnn_states_flat[sl], batch["dones"].view(self.E)[sl],
                                                         valids, self.rnn_bufs)
-        x = self._forward_hidden(x0, self.h, mb_rnn)
+        x = forward_policy(m, x0, self.h, self.act, self.engine, self.heads_plan,
+                           dict(values=self.mb_values, values_stride=1, logits=self.mb_logits, logits_stride=A), mb_rnn,
+                           store_tail=True)
         Wv, bv = m.critic
         Wa, ba = m.actor
-        ops.heads_forward(x, Wv, bv, Wa, ba, values=self.mb_values, values_stride=1, logits=self.mb_logits,
-                          logits_stride=A)
         if cfg.with_vtrace:                                                                          # :602-640
             ops.action_ratio(self.mb_logits, actions, lp_old, self.ratio)
             ops.vtrace(self.ratio, self.mb_values, batch["rewards"].view(self.E)[sl], batch["dones"].view(self.E)[sl],

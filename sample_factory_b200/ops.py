@@ -126,6 +126,48 @@ def heads_forward(h: Tensor, Wv: Tensor, bv: Tensor, Wa: Tensor, ba: Tensor, val
                None if policy_version_out is None else policy_version_out.data_ptr(), pv_stride, _stream())
 
 
+def linear_heads_partials(N: int, A: int, engine: int) -> int:
+    """Partials per row the fused last-layer + heads forward produces (0: not covered -> use the separate calls)."""
+    return int(lib().query("sfb200_linear_heads_partials", N, A, engine))
+
+
+HEAD_PART_PAD = 12   # floats per (partial, row) in the scratch buffer of the fused last-layer + heads forward
+
+
+def linear_act_heads_forward(x: Tensor, W: Tensor, b: Tensor, out: Optional[Tensor], act: int, engine: int,
+                             Wv: Tensor, Wa: Tensor, head_partials: Tensor) -> None:
+    """out = act(x W^T + b) (not stored when out is None) and head_partials[p, m, :A+1] = partial out . [Wv ; Wa]."""
+    M, K = x.shape
+    N = W.shape[0]
+    A = Wa.shape[0]
+    assert W.shape[1] == K and W.is_contiguous() and Wa.is_contiguous() and Wv.is_contiguous()
+    assert out is None or out.shape == (M, N)
+    P = linear_heads_partials(N, A, engine)
+    assert P > 0 and head_partials.numel() >= P * M * HEAD_PART_PAD and head_partials.is_contiguous()
+    lib().call("sfb200_linear_act_heads_forward", _p(x, F32), x.stride(0), _p(W, F32), _p(b, F32), _p(out, F32),
+               0 if out is None else out.stride(0), M, N, K, act, engine, _p(Wv, F32), _p(Wa, F32), A,
+               _p(head_partials, F32), _stream())
+
+
+def heads_from_partials(head_partials: Tensor, P: int, rows: int, bv: Tensor, ba: Tensor, values: Tensor,
+                        values_stride: int, logits: Optional[Tensor] = None, logits_stride: int = 0,
+                        noise: Optional[Tensor] = None, philox_seed: int = 0, philox_offset: int = 0,
+                        philox_offset_dev: Optional[Tensor] = None, actions_f32: Optional[Tensor] = None,
+                        actions_stride: int = 0, env_actions: Optional[Tensor] = None,
+                        log_prob: Optional[Tensor] = None, log_prob_stride: int = 0,
+                        policy_version_scalar: Optional[Tensor] = None, policy_version_out: Optional[Tensor] = None,
+                        pv_stride: int = 0) -> None:
+    """Second half of the fused path: same outputs / sampling semantics as heads_forward."""
+    A = ba.shape[0]
+    assert noise is None or noise.is_contiguous()
+    lib().call("sfb200_heads_from_partials", _p(head_partials, F32), P, rows, A, _p(bv, F32), _p(ba, F32),
+               values.data_ptr(), values_stride, None if logits is None else logits.data_ptr(), logits_stride,
+               _p(noise, F32), philox_seed, philox_offset, _p(philox_offset_dev, I64),
+               None if actions_f32 is None else actions_f32.data_ptr(), actions_stride, _p(env_actions, I32),
+               None if log_prob is None else log_prob.data_ptr(), log_prob_stride, _p(policy_version_scalar, F32),
+               None if policy_version_out is None else policy_version_out.data_ptr(), pv_stride, _stream())
+
+
 # ------------------------------------------------------------------------------------------------ sampler
 def sampler_pre_step(obs: Tensor, traj_obs_t: Tensor, rnn: Optional[Tensor], traj_rnn_t: Optional[Tensor],
                      x_norm: Optional[Tensor], mean: Optional[Tensor], var: Optional[Tensor], sub_mean: float,
@@ -157,6 +199,37 @@ def sampler_post_step(rew: Tensor, terminated: Tensor, truncated: Tensor, reward
                _p(ep_min_raw, F32), _p(ep_max_raw, F32), len_increment, _p(stats, F64), _p(step_counter, I64),
                None if fin_return_t is None else fin_return_t.data_ptr(),
                None if fin_len_t is None else fin_len_t.data_ptr(), _stream())
+
+
+
+def sampler_post_pre_step(rew: Tensor, terminated: Tensor, truncated: Tensor, reward_scale: float, reward_clip: float,
+                          policy_id: int, traj_rewards_t: Tensor, traj_dones_t: Tensor, traj_time_outs_t: Tensor,
+                          traj_policy_id_t: Tensor, ep_return: Optional[Tensor], ep_len: Optional[Tensor],
+                          ep_min_raw: Optional[Tensor], ep_max_raw: Optional[Tensor], len_increment: int,
+                          stats: Optional[Tensor], step_counter: Optional[Tensor] = None,
+                          fin_return_t: Optional[Tensor] = None, fin_len_t: Optional[Tensor] = None, *,
+                          obs: Tensor, traj_obs_next: Tensor, rnn: Optional[Tensor], traj_rnn_next: Optional[Tensor],
+                          x_norm: Optional[Tensor], mean: Optional[Tensor], var: Optional[Tensor], sub_mean: float,
+                          inv_scale: float, eps: float = 1e-5, clip: float = 5.0) -> None:
+    """sampler_post_step(t) + sampler_pre_step(t+1) in one launch (x_norm None: record the observation only)."""
+    n = rew.numel()
+    stride = traj_rewards_t.stride(0)
+    assert fin_return_t is None or (fin_return_t.stride(0) == stride and fin_len_t.stride(0) == stride)
+    assert traj_dones_t.stride(0) == stride and traj_time_outs_t.stride(0) == stride
+    assert traj_policy_id_t.stride(0) == stride
+    n_obs, dim = obs.shape
+    assert n_obs == n and obs.is_contiguous() and (x_norm is None or x_norm.is_contiguous())
+    rnn_dim = 0 if rnn is None else rnn.shape[1]
+    lib().call("sfb200_sampler_post_pre_step", _p(rew, F32), _p(terminated, U8), _p(truncated, U8), n, reward_scale,
+               reward_clip, policy_id, traj_rewards_t.data_ptr(), traj_dones_t.data_ptr(),
+               traj_time_outs_t.data_ptr(), traj_policy_id_t.data_ptr(), stride, _p(ep_return, F32), _p(ep_len, I32),
+               _p(ep_min_raw, F32), _p(ep_max_raw, F32), len_increment, _p(stats, F64), _p(step_counter, I64),
+               None if fin_return_t is None else fin_return_t.data_ptr(),
+               None if fin_len_t is None else fin_len_t.data_ptr(),
+               _p(obs, F32), dim, traj_obs_next.data_ptr(), traj_obs_next.stride(0), _p(rnn, F32), rnn_dim,
+               None if traj_rnn_next is None else traj_rnn_next.data_ptr(),
+               0 if traj_rnn_next is None else traj_rnn_next.stride(0), _p(x_norm, F32), _p(mean, F64), _p(var, F64),
+               sub_mean, inv_scale, eps, clip, _stream())
 
 
 def copy_rows(src: Tensor, dst: Tensor) -> None:

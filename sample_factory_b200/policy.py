@@ -1,0 +1,66 @@
+"""Forward pass of the actor-critic on the device: encoder MLP -> (recurrent core) -> decoder MLP -> heads
+(reference: ActorCriticSharedWeights.forward_head / forward_core / forward_tail, model/actor_critic.py:160-195).
+
+One function serves the three call sites of the hot path (sampler policy step, learner bootstrap value, learner
+minibatch forward).  When the tensor feeding critic_linear / distribution_linear is the output of an MLP layer and the
+tcgen05 engine covers the shape, that layer and the heads run as ONE GEMM whose epilogue leaves partial head dot
+products (sfb200_linear_act_heads_forward) followed by a tiny finishing kernel (sfb200_heads_from_partials); the
+activated layer output is stored only if the caller needs it (the learner's backward does, the sampler does not).
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, List, Optional
+
+import torch
+from torch import Tensor
+
+from . import ops
+from .model import PolicyModel
+
+
+class HeadsPlan:
+    """Decides once per (model, engine) whether the fused last-layer + heads path applies and owns its scratch."""
+
+    def __init__(self, model: PolicyModel, engine: int, max_rows: int):
+        spec = model.spec
+        self.tail_is_mlp = bool(spec.decoder_mlp_layers) or (not spec.use_rnn and bool(spec.encoder_mlp_layers))
+        self.P = 0
+        self.part: Optional[Tensor] = None
+        if self.tail_is_mlp:
+            self.P = ops.linear_heads_partials(spec.tail_input_size, spec.num_actions, engine)
+        if self.P > 0:
+            self.part = torch.empty(self.P * max_rows * ops.HEAD_PART_PAD, dtype=torch.float32, device=model.device)
+
+
+def forward_policy(model: PolicyModel, x: Tensor, outs: List[Tensor], act: int, engine: int, plan: HeadsPlan,
+                   heads_kwargs: Dict, rnn_fn: Optional[Callable[[Tensor], Tensor]] = None,
+                   store_tail: bool = True) -> Tensor:
+    """x [M, D] (rows may be strided) -> heads outputs described by `heads_kwargs` (the keyword arguments of
+    ops.heads_forward after the weights).  outs: one [>=M, h] buffer per MLP layer.  Returns the tensor that fed the
+    heads (None if it was not stored)."""
+    M = x.shape[0]
+    enc, dec = model.encoder_layers(), model.decoder_layers()
+    Wv, bv = model.critic
+    Wa, ba = model.actor
+    n_mlp = len(enc) + len(dec)
+    fused = plan.P > 0
+    k = 0
+    tail: Optional[Tensor] = x
+    for group, layers in (("enc", enc), ("dec", dec)):
+        if group == "dec" and rnn_fn is not None:
+            tail = rnn_fn(tail)
+        for (W, b) in layers:
+            last = fused and k == n_mlp - 1
+            if last:
+                out = outs[k][:M] if store_tail else None
+                ops.linear_act_heads_forward(tail, W, b, out, act, engine, Wv, Wa, plan.part)
+                tail = out
+            else:
+                ops.linear_act_forward(tail, W, b, outs[k][:M], act, engine)
+                tail = outs[k][:M]
+            k += 1
+    if fused:
+        ops.heads_from_partials(plan.part, plan.P, M, bv, ba, **heads_kwargs)
+    else:
+        ops.heads_forward(tail, Wv, bv, Wa, ba, **heads_kwargs)
+    return tail

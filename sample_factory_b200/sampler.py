@@ -24,6 +24,7 @@ from torch import Tensor
 
 from . import ops
 from .model import PolicyModel
+from .policy import HeadsPlan, forward_policy
 from .rnn_core import RnnCore
 
 
@@ -47,6 +48,7 @@ class DeviceSampler:
         self.x_norm = torch.empty((self.N, spec.obs_dim), **f32)
         self.h = [torch.empty((self.N, h), **f32) for h in spec.hidden]
         self.env_actions = torch.empty(self.N, dtype=torch.int32, device=dev)
+        self.heads_plan = HeadsPlan(model, engine, self.N)
         self.last_rnn_state = torch.zeros((self.N, traj["rnn_states"].shape[2]), **f32)
         self.rnn: Optional[RnnCore] = None
         if spec.use_rnn:
@@ -88,28 +90,22 @@ class DeviceSampler:
     def set_policy_version(self, version: int) -> None:
         self.policy_version.fill_(float(version))
 
-    def _policy_step(self, t: int) -> None:
-        cfg, m, spec, tr = self.cfg, self.model, self.model.spec, self.traj
-        inv_scale = 1.0 / spec.obs_scale
+    def _pre_step(self, t: int) -> None:
+        """generate_policy_request (batched_sampling.py:374-388) + inference-side normalisation for step t."""
+        m, spec, tr = self.model, self.model.spec, self.traj
         mean = m.obs_mean if spec.normalize_input else None
         var = m.obs_var if spec.normalize_input else None
         ops.sampler_pre_step(self.last_obs, tr["obs"][:, t], self.last_rnn_state, tr["rnn_states"][:, t], self.x_norm,
-                             mean, var, spec.obs_subtract_mean, inv_scale)
-        x = self.x_norm
-        enc, dec = m.encoder_layers(), m.decoder_layers()
-        for i, (W, b) in enumerate(enc):
-            ops.linear_act_forward(x, W, b, self.h[i], self.act, self.engine)
-            x = self.h[i]
+                             mean, var, spec.obs_subtract_mean, 1.0 / spec.obs_scale)
+
+    def _policy_step(self, t: int) -> None:
+        """policy forward + sampling on the pre-step's x_norm; outputs go straight into traj[:, t]"""
+        cfg, m, spec, tr = self.cfg, self.model, self.model.spec, self.traj
+        rnn_fn = None
         if self.rnn is not None:   # ModelCoreRNN.forward (core.py:37-64), one step
-            x = self.rnn.step(x, self.last_rnn_state, self.new_rnn_state, self.rnn_step_bufs)
-        for j, (W, b) in enumerate(dec):
-            ops.linear_act_forward(x, W, b, self.h[len(enc) + j], self.act, self.engine)
-            x = self.h[len(enc) + j]
-        Wv, bv = m.critic
-        Wa, ba = m.actor
+            rnn_fn = lambda head: self.rnn.step(head, self.last_rnn_state, self.new_rnn_state, self.rnn_step_bufs)
         noise_t = None if self.noise is None else self.noise[t]
-        ops.heads_forward(
-            x, Wv, bv, Wa, ba,
+        heads_kwargs = dict(
             values=tr["values"][:, t], values_stride=tr["values"].stride(0),
             logits=tr["action_logits"][:, t], logits_stride=tr["action_logits"].stride(0),
             noise=noise_t, philox_seed=self.philox_seed, philox_offset=0, philox_offset_dev=self.step_counter,
@@ -119,6 +115,9 @@ class DeviceSampler:
             policy_version_scalar=self.policy_version,
             policy_version_out=tr["policy_version"][:, t], pv_stride=tr["policy_version"].stride(0),
         )
+        # the sampler never needs the last hidden activation again: with the fused path it is not written to HBM
+        forward_policy(m, self.x_norm, self.h, self.act, self.engine, self.heads_plan, heads_kwargs, rnn_fn,
+                       store_tail=False)
 
     def _env_and_post_step(self, t: int) -> None:
         obs, rew, terminated, truncated = self.env.step(self.env_actions)   # batched_sampling.py:316
@@ -126,18 +125,34 @@ class DeviceSampler:
         self._post_step(t, rew, terminated, truncated)
 
     def _post_step(self, t: int, rew: Tensor, terminated: Tensor, truncated: Tensor) -> None:
-        cfg, tr = self.cfg, self.traj
-        ops.sampler_post_step(rew, terminated, truncated, cfg.reward_scale, cfg.reward_clip, cfg.policy_id,
-                              tr["rewards"][:, t], tr["dones"][:, t], tr["time_outs"][:, t], tr["policy_id"][:, t],
-                              self.ep_return, self.ep_len, self.ep_min_raw, self.ep_max_raw,
-                              cfg.env_frameskip if cfg.summaries_use_frameskip else 1, self.episode_stats,
-                              self.step_counter,
-                              None if self.fin_return is None else self.fin_return[:, t],
-                              None if self.fin_len is None else self.fin_len[:, t])
-        if self.rnn is not None:
-            # last_rnn_state = new_rnn_states * (1 - done)  (batched_sampling.py:332-335); the dones were just written
-            ops.mask_rows(self.new_rnn_state, self.last_rnn_state, tr["dones"][:, t])
-        # non-recurrent core: new_rnn_states == rnn_states (core.py:76-77), times (1-done) stays zero
+        """advance_rollouts part 2 for step t, then the pre-step of t+1 (or, at t = T-1, _finalize_trajectories
+        batched_sampling.py:289-296: obs / rnn state recorded at index T).  Without a recurrent core both halves only
+        consume the env's outputs -> one fused launch."""
+        cfg, m, spec, tr = self.cfg, self.model, self.model.spec, self.traj
+        post_args = (rew, terminated, truncated, cfg.reward_scale, cfg.reward_clip, cfg.policy_id,
+                     tr["rewards"][:, t], tr["dones"][:, t], tr["time_outs"][:, t], tr["policy_id"][:, t],
+                     self.ep_return, self.ep_len, self.ep_min_raw, self.ep_max_raw,
+                     cfg.env_frameskip if cfg.summaries_use_frameskip else 1, self.episode_stats,
+                     self.step_counter,
+                     None if self.fin_return is None else self.fin_return[:, t],
+                     None if self.fin_len is None else self.fin_len[:, t])
+        last = t + 1 == self.T
+        if self.rnn is None:
+            # non-recurrent core: new_rnn_states == rnn_states (core.py:76-77), times (1-done) stays zero
+            mean = m.obs_mean if spec.normalize_input else None
+            var = m.obs_var if spec.normalize_input else None
+            ops.sampler_post_pre_step(*post_args, obs=self.last_obs, traj_obs_next=tr["obs"][:, t + 1],
+                                      rnn=self.last_rnn_state, traj_rnn_next=tr["rnn_states"][:, t + 1],
+                                      x_norm=None if last else self.x_norm, mean=mean, var=var,
+                                      sub_mean=spec.obs_subtract_mean, inv_scale=1.0 / spec.obs_scale)
+            return
+        ops.sampler_post_step(*post_args)
+        # last_rnn_state = new_rnn_states * (1 - done)  (batched_sampling.py:332-335); the dones were just written
+        ops.mask_rows(self.new_rnn_state, self.last_rnn_state, tr["dones"][:, t])
+        if last:
+            self._finalize_trajectories()
+        else:
+            self._pre_step(t + 1)
 
     def advance_rollouts(self, t: int) -> None:
         """One env step for all envs: policy step then env step (reference: inference then advance_rollouts)."""
@@ -151,9 +166,9 @@ class DeviceSampler:
 
     def _rollout_eager(self) -> None:
         n0 = ops.launch_count()
+        self._pre_step(0)
         for t in range(self.T):
             self.advance_rollouts(t)
-        self._finalize_trajectories()
         self.kernel_launches_per_rollout = ops.launch_count() - n0   # counted by the library itself
 
     def rollout(self) -> None:
@@ -199,6 +214,8 @@ class DeviceSampler:
             for t in range(self.T):
                 gp, gq = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
                 with torch.cuda.graph(gp):
+                    if t == 0:
+                        self._pre_step(0)
                     self._policy_step(t)
                 with torch.cuda.graph(gq):
                     self._post_step(t, env.rew, env.terminated, env.truncated)
@@ -211,9 +228,7 @@ class DeviceSampler:
             obs, _, _, _ = self.env.step(self.env_actions)
             assert obs is self.last_obs
             gq.replay()
-        n0 = ops.launch_count()
-        self._finalize_trajectories()
-        self.kernel_launches_per_rollout = self._graph_launches + (ops.launch_count() - n0)
+        self.kernel_launches_per_rollout = self._graph_launches
 
     @property
     def graph_replay_launches(self) -> int:

@@ -582,3 +582,119 @@ def test_bad_arguments_raise(dev):
         ops.heads_forward(x, x[0:1], x[0, :1], torch.zeros(40, 4, device=dev), torch.zeros(40, device=dev), x[:, 0], 4)
     with pytest.raises(RuntimeError):
         ops.normalize_obs(torch.zeros(4, 4), x, None, None)  # CPU tensor: there is no CPU path
+
+
+# ----------------------------------------------------------------------------------------------- fused paths
+@pytest.mark.parametrize("engine_name", ["3xtf32", "tf32"])
+@pytest.mark.parametrize("M,K,N,A,act", [(4096, 512, 512, 8, "elu"), (1000, 64, 256, 5, "tanh"), (333, 96, 128, 1, "relu")])
+def test_linear_heads_fused_matches_separate(dev, engine_name, M, K, N, A, act):
+    """sfb200_linear_act_heads_forward + sfb200_heads_from_partials == sfb200_linear_act_forward + sfb200_heads_forward
+    (same GEMM accumulators -> identical y; head dot products differ only in summation order) and == the oracle."""
+    ops = _ops()
+    engine = {"3xtf32": ops.GEMM_TC_3XTF32, "tf32": ops.GEMM_TC_TF32}[engine_name]
+    P = ops.linear_heads_partials(N, A, engine)
+    assert P == 2 * (N // 128), "fused path must cover these shapes on a B200"
+    x = torch.randn(M, K, generator=g(60))
+    W = torch.randn(N, K, generator=g(61)) / math.sqrt(K)
+    b = torch.randn(N, generator=g(62)) * 0.1
+    Wv = torch.randn(1, N, generator=g(63)) / math.sqrt(N)
+    bv = torch.randn(1, generator=g(64))
+    Wa = torch.randn(A, N, generator=g(65)) / math.sqrt(N)
+    ba = torch.randn(A, generator=g(66)) * 0.1
+    noise = torch.empty(M, A).exponential_(generator=g(67))
+    xd, Wd, bd, Wvd, bvd, Wad, bad, nd = (t.to(dev).contiguous() for t in (x, W, b, Wv, bv, Wa, ba, noise))
+    actc = ops.ACT[act]
+
+    def outs():
+        return dict(values=torch.empty(M, device=dev), logits=torch.empty(M, A, device=dev),
+                    actions=torch.empty(M, device=dev), env_actions=torch.empty(M, dtype=torch.int32, device=dev),
+                    lp=torch.empty(M, device=dev), pv=torch.empty(M, device=dev))
+
+    pvs = torch.full((1,), 7.0, device=dev)
+
+    def kw(o):
+        return dict(values=o["values"], values_stride=1, logits=o["logits"], logits_stride=A, noise=nd,
+                    actions_f32=o["actions"], actions_stride=1, env_actions=o["env_actions"], log_prob=o["lp"],
+                    log_prob_stride=1, policy_version_scalar=pvs, policy_version_out=o["pv"], pv_stride=1)
+
+    # separate
+    y_ref = torch.empty(M, N, device=dev)
+    o1 = outs()
+    ops.linear_act_forward(xd, Wd, bd, y_ref, actc, engine)
+    ops.heads_forward(y_ref, Wvd, bvd, Wad, bad, **kw(o1))
+    # fused, storing y
+    part = torch.full((P * M * ops.HEAD_PART_PAD,), float("nan"), device=dev)
+    y = torch.full((M, N), float("nan"), device=dev)
+    o2 = outs()
+    ops.linear_act_heads_forward(xd, Wd, bd, y, actc, engine, Wvd, Wad, part)
+    ops.heads_from_partials(part, P, M, bvd, bad, **kw(o2))
+    assert torch.equal(y, y_ref)
+    # fused, not storing y (sampler mode)
+    part3 = torch.full_like(part, float("nan"))
+    o3 = outs()
+    ops.linear_act_heads_forward(xd, Wd, bd, None, actc, engine, Wvd, Wad, part3)
+    ops.heads_from_partials(part3, P, M, bvd, bad, **kw(o3))
+    for k in o2:
+        assert torch.equal(o2[k], o3[k]), k
+    assert (o2["values"] - o1["values"]).abs().max().item() < TOL
+    assert (o2["logits"] - o1["logits"]).abs().max().item() < TOL
+    assert (o2["lp"] - o1["lp"]).abs().max().item() < 2 * TOL
+    assert torch.all(o2["pv"] == 7.0)
+    same = (o2["actions"] == o1["actions"]).float().mean().item()
+    assert same >= 0.999, same       # identical up to argmax near-ties moved by 1e-7-level logit differences
+    assert torch.equal(o2["actions"].to(torch.int32), o2["env_actions"])
+    if engine_name == "3xtf32":      # fp32-grade engine: against the oracle (fp32 CPU)
+        h = {"elu": torch.nn.functional.elu, "tanh": torch.tanh, "relu": torch.relu}[act](x @ W.t() + b)
+        v_ref = (h @ Wv.t() + bv).squeeze(1)
+        l_ref = h @ Wa.t() + ba
+        assert (o2["values"].cpu() - v_ref).abs().max().item() < 2 * TOL
+        assert (o2["logits"].cpu() - l_ref).abs().max().item() < 2 * TOL
+        a_ref = torch.argmax(torch.softmax(l_ref, -1) / noise, dim=-1).float()
+        assert (o2["actions"].cpu() == a_ref).float().mean().item() >= 0.999
+
+
+def test_sampler_post_pre_step_fused_matches_separate(dev):
+    """sfb200_sampler_post_pre_step == sfb200_sampler_post_step(t) then sfb200_sampler_pre_step(t+1), bit for bit."""
+    ops = _ops()
+    N, D, T = 1000, 64, 4
+    mean = torch.randn(D, generator=g(70), dtype=torch.float64).to(dev)
+    var = (torch.rand(D, generator=g(71), dtype=torch.float64) + 0.1).to(dev)
+
+    def state():
+        return dict(traj_obs=torch.full((N, T + 1, D), -1.0, device=dev), traj_rnn=torch.full((N, T + 1, 1), -1.0, device=dev),
+                    xn=torch.full((N, D), -2.0, device=dev), rew_t=torch.zeros(N, T, device=dev),
+                    done_t=torch.zeros(N, T, dtype=torch.bool, device=dev), to_t=torch.zeros(N, T, dtype=torch.bool, device=dev),
+                    pid_t=torch.full((N, T), -1, dtype=torch.int32, device=dev), ep_ret=torch.zeros(N, device=dev),
+                    ep_len=torch.zeros(N, dtype=torch.int32, device=dev), ep_min=torch.full((N,), float("inf"), device=dev),
+                    ep_max=torch.full((N,), float("-inf"), device=dev), stats=torch.zeros(8, dtype=torch.float64, device=dev),
+                    counter=torch.zeros(1, dtype=torch.int64, device=dev),
+                    fin_ret=torch.full((N, T), float("nan"), device=dev), fin_len=torch.full((N, T), -1, dtype=torch.int32, device=dev))
+
+    s1, s2 = state(), state()
+    rnn = torch.zeros(N, 1, device=dev)
+    for t in range(T):
+        obs = torch.randn(N, D, generator=g(80 + t)).to(dev)
+        r = torch.randn(N, generator=g(90 + t)).to(dev)
+        tm = (torch.rand(N, generator=g(100 + t)) < 0.1).to(dev)
+        tr = (torch.rand(N, generator=g(110 + t)) < 0.1).to(dev)
+        last = t + 1 == T
+
+        def post_args(s):
+            return (r, tm, tr, 0.7, 0.5, 3, s["rew_t"][:, t], s["done_t"][:, t], s["to_t"][:, t], s["pid_t"][:, t], s["ep_ret"],
+                    s["ep_len"], s["ep_min"], s["ep_max"], 2, s["stats"], s["counter"], s["fin_ret"][:, t], s["fin_len"][:, t])
+
+        ops.sampler_post_step(*post_args(s1))
+        ops.sampler_pre_step(obs, s1["traj_obs"][:, t + 1], rnn, s1["traj_rnn"][:, t + 1], None if last else s1["xn"], mean, var,
+                             0.25, 0.5)
+        ops.sampler_post_pre_step(*post_args(s2), obs=obs, traj_obs_next=s2["traj_obs"][:, t + 1], rnn=rnn,
+                                  traj_rnn_next=s2["traj_rnn"][:, t + 1], x_norm=None if last else s2["xn"], mean=mean,
+                                  var=var, sub_mean=0.25, inv_scale=0.5)
+        for k in s1:
+            a, b = s1[k], s2[k]
+            if k == "stats":      # fp64 atomics: warp order is not fixed
+                assert torch.allclose(a, b, rtol=1e-12, atol=1e-12), (k, t)
+            elif a.dtype.is_floating_point:
+                assert torch.equal(torch.nan_to_num(a, nan=12345.0), torch.nan_to_num(b, nan=12345.0)), (k, t)
+            else:
+                assert torch.equal(a, b), (k, t)
+    assert s2["counter"].item() == T and s2["stats"][0].item() > 0
