@@ -39,10 +39,33 @@ void count_launch();   // every kernel launch of this library is counted (sfb200
     } while (0)
 
 int sm_count();
+bool pdl_enabled();   // SFB200_PDL=0 turns programmatic dependent launch off (api.cu)
+
+// Programmatic dependent launch: kernels launched through launch_pdl() may be made resident while their predecessor on
+// the stream is still running; every such kernel calls pdl_wait() before it touches global memory (the wait returns
+// once the predecessor grid has completed and its writes are visible) and pdl_trigger() to let ITS successor start
+// launching.  Inside the sampler's per-step kernel chain this hides the launch latency of each dependent kernel.
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                     Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // ---------------------------------------------------------------- device helpers
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

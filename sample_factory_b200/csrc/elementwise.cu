@@ -88,7 +88,11 @@ __device__ __forceinline__ void normalize_body(const NormArgs& a) {
 }
 
 template <bool VEC4>
-__global__ void __launch_bounds__(256) normalize_kernel(const NormArgs a) { normalize_body<VEC4>(a); }
+__global__ void __launch_bounds__(256) normalize_kernel(const NormArgs a) {
+    pdl_wait();
+    pdl_trigger();
+    normalize_body<VEC4>(a);
+}
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
@@ -115,8 +119,8 @@ static int launch_normalize(const float* x, int64_t ldx, float* y, int64_t ldy, 
     int64_t blocks = ceil_div(work, 256);
     const int64_t cap = (int64_t)sm_count() * 8;
     if (blocks > cap) blocks = cap;
-    if (vec) normalize_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(a);
-    else normalize_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(a);
+    if (vec) SFB_CUDA_OK(launch_pdl(normalize_kernel<true>, dim3((unsigned)blocks), dim3(256), 0, st, a));
+    else SFB_CUDA_OK(launch_pdl(normalize_kernel<false>, dim3((unsigned)blocks), dim3(256), 0, st, a));
     SFB_LAUNCH_OK();
     return 0;
 }
@@ -190,6 +194,8 @@ __global__ void __launch_bounds__(256) post_step_kernel(const PostArgs a) { post
 // env's outputs; nothing sits between them on the stream): one launch instead of two per env step.
 template <bool VEC4>
 __global__ void __launch_bounds__(256) post_pre_step_kernel(const PostArgs pa, const NormArgs na) {
+    pdl_wait();
+    pdl_trigger();
     post_step_body(pa);
     normalize_body<VEC4>(na);
 }
@@ -201,6 +207,8 @@ __global__ void __launch_bounds__(256) tape_env_kernel(const int32_t* __restrict
                                                        const float* __restrict__ tape, int64_t tape_len, int dim,
                                                        float* __restrict__ obs_out, float* __restrict__ rew,
                                                        uint8_t* __restrict__ term, uint8_t* __restrict__ trunc) {
+    pdl_wait();
+    pdl_trigger();
     const int64_t step = step_counter ? *step_counter : step_host;
     const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
@@ -370,8 +378,8 @@ int sfb200_sampler_post_pre_step(const float* rew, const uint8_t* terminated, co
     if (blocks > cap) blocks = cap;
     if (blocks < ceil_div(n_envs, 256)) blocks = ceil_div(n_envs, 256);   // every env needs its post-step thread
     cudaStream_t st = (cudaStream_t)stream;
-    if (vec) post_pre_step_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(pa, na);
-    else post_pre_step_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(pa, na);
+    if (vec) SFB_CUDA_OK(launch_pdl(post_pre_step_kernel<true>, dim3((unsigned)blocks), dim3(256), 0, st, pa, na));
+    else SFB_CUDA_OK(launch_pdl(post_pre_step_kernel<false>, dim3((unsigned)blocks), dim3(256), 0, st, pa, na));
     SFB_LAUNCH_OK();
     return 0;
 }
@@ -388,9 +396,9 @@ int sfb200_tape_env_step(const int32_t* actions, int64_t n_envs, int num_actions
     if (obs_out) work = n_envs * (int64_t)dim / 4 > work ? n_envs * (int64_t)dim / 4 : work;
     unsigned g = grid_for(work);
     if ((int64_t)g * 256 < n_envs) g = (unsigned)ceil_div(n_envs, 256);
-    tape_env_kernel<<<g, 256, 0, st>>>(actions, n_envs, num_actions, env_index_offset, term_period, trunc_period,
-                                       step_counter, step_host, tape, tape_len, dim, obs_out, rew, terminated,
-                                       truncated);
+    SFB_CUDA_OK(launch_pdl(tape_env_kernel, dim3(g), dim3(256), 0, st, actions, n_envs, num_actions, env_index_offset,
+                           term_period, trunc_period, (const int64_t*)step_counter, step_host, tape, tape_len, dim, obs_out,
+                           rew, terminated, truncated));
     SFB_LAUNCH_OK();
     return 0;
 }

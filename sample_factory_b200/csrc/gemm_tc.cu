@@ -285,6 +285,34 @@ __device__ __forceinline__ EpiCtx make_epi_ctx(int warp, int lane, const float* 
     return ec;
 }
 
+// Whole accumulator row segment of this thread (CH columns, main + cross terms summed) -> registers, then the TMEM slot
+// is handed back at once: all of the epilogue's arithmetic and global traffic overlaps the next tile's main loop (the
+// TMEM-A kernel has a single accumulator slot, so whatever runs before the release is serialised with the MMAs).
+template <int BN, int CH, bool SPLIT3>
+__device__ __forceinline__ void tmem_drain(uint32_t t_main, float (&acc)[CH], uint64_t* acc_full_bar, uint32_t acc_ph,
+                                           uint64_t* acc_empty_bar) {
+    mbar_wait(acc_full_bar, acc_ph);
+    tc_fence_after();
+#pragma unroll
+    for (int c0 = 0; c0 < CH; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld_32x32b_x16(t_main + (uint32_t)c0, r);
+        if (SPLIT3) {
+            uint32_t r2[16];
+            tmem_ld_32x32b_x16(t_main + (uint32_t)(BN + c0), r2);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[c0 + j] = __uint_as_float(r[j]) + __uint_as_float(r2[j]);
+        } else {
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[c0 + j] = __uint_as_float(r[j]);
+        }
+    }
+    tc_fence_before();
+    mbar_arrive(acc_empty_bar);
+}
+
 // One output tile: TMEM accumulator slot (main at column 0, cross terms at column BN) -> registers -> global.
 template <int BN, bool SPLIT3>
 __device__ __forceinline__ void tc_epilogue_tile(uint32_t tmem_slot_addr, uint64_t* acc_full_bar, uint32_t acc_ph,
@@ -295,91 +323,67 @@ __device__ __forceinline__ void tc_epilogue_tile(uint32_t tmem_slot_addr, uint64
     const int lane_base = ec.lane_base, lane = ec.lane, col0 = ec.col0, mode = ec.mode;
     const bool vec_ok = ec.vec_ok, aux_vec = ec.aux_vec, bias_vec = ec.bias_vec;
     const float* bias_base = ec.bias_base;
-            const int64_t m = tc.m0 + lane_base + lane;
-            const int nbeg = tc.n0 + col0;
-            const bool fast = (m < M) && (nbeg + CH <= N) && vec_ok &&
-                              (mode == 0 || (mode == 1 && (bias_vec || !epi.bias)) || (mode == 2 && aux_vec));
-            // Processed in 32-column chunks so that the live set (32 accumulators + 32 cross-term temporaries + 8 float4
-            // of aux) fits the 128-register budget of a 448-thread CTA without spilling.
-            // mode 2: the activation-derivative operand of the first chunk is fetched BEFORE the accumulator is ready
-            // (hides its HBM latency behind the main loop of this tile).
-            const float* aux_row = (mode == 2 && fast) ? epi.aux + m * epi.ld_aux + nbeg : nullptr;
-            float4 auxv[8];
-            if (aux_row) {
+    const int64_t m = tc.m0 + lane_base + lane;
+    const int nbeg = tc.n0 + col0;
+    const bool fast = (m < M) && (nbeg + CH <= N) && vec_ok &&
+                      (mode == 0 || (mode == 1 && (bias_vec || !epi.bias)) || (mode == 2 && aux_vec));
+    // mode 2: the activation-derivative operand of the first 32-column chunk is fetched BEFORE the accumulator is ready
+    // (hides its HBM latency behind the main loop of this tile).
+    const float* aux_row = (mode == 2 && fast) ? epi.aux + m * epi.ld_aux + nbeg : nullptr;
+    float4 auxv[8];
+    if (aux_row) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) auxv[j] = *reinterpret_cast<const float4*>(aux_row + 4 * j);
+        for (int j = 0; j < 8; ++j) auxv[j] = *reinterpret_cast<const float4*>(aux_row + 4 * j);
+    }
+    float acc_all[CH];
+    tmem_drain<BN, CH, SPLIT3>(tmem_slot_addr + ((uint32_t)lane_base << 16) + (uint32_t)col0, acc_all, acc_full_bar, acc_ph,
+                               acc_empty_bar);
+    if (m >= M) return;
+    float* Cz = C + (splits > 1 ? (int64_t)tc.z * M * ldc : 0);
+    float* dst_row = Cz + m * ldc + nbeg;
+#pragma unroll
+    for (int c0 = 0; c0 < CH; c0 += 32) {
+        const float (&acc)[32] = reinterpret_cast<const float (&)[32]>(acc_all[c0]);
+        if (c0 > 0 && aux_row) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) auxv[j] = *reinterpret_cast<const float4*>(aux_row + c0 + 4 * j);
+        }
+        float* dst = dst_row + c0;
+        if (fast) {
+            // whole row segment in bounds, 128-bit everything; mode / activation resolved once per chunk into
+            // a straight-line specialisation (a per-element switch cost 4x the instructions)
+            const float* bias_n0 = epi.bias ? bias_base + nbeg + c0 : nullptr;
+            if (mode == 1) {
+                switch (epi.act) {
+                    case SFB200_ACT_ELU: write_row<1, SFB200_ACT_ELU, 32>(acc, dst, bias_n0, auxv); break;
+                    case SFB200_ACT_RELU: write_row<1, SFB200_ACT_RELU, 32>(acc, dst, bias_n0, auxv); break;
+                    case SFB200_ACT_TANH: write_row<1, SFB200_ACT_TANH, 32>(acc, dst, bias_n0, auxv); break;
+                    default: write_row<1, SFB200_ACT_NONE, 32>(acc, dst, bias_n0, auxv); break;
+                }
+            } else if (mode == 2) {
+                switch (epi.act) {
+                    case SFB200_ACT_ELU: write_row<2, SFB200_ACT_ELU, 32>(acc, dst, bias_n0, auxv); break;
+                    case SFB200_ACT_RELU: write_row<2, SFB200_ACT_RELU, 32>(acc, dst, bias_n0, auxv); break;
+                    case SFB200_ACT_TANH: write_row<2, SFB200_ACT_TANH, 32>(acc, dst, bias_n0, auxv); break;
+                    default: write_row<0, SFB200_ACT_NONE, 32>(acc, dst, bias_n0, auxv); break;
+                }
+            } else {
+                write_row<0, SFB200_ACT_NONE, 32>(acc, dst, bias_n0, auxv);
             }
-            mbar_wait(acc_full_bar, acc_ph);
-            tc_fence_after();
-            const uint32_t t_main = tmem_slot_addr + ((uint32_t)lane_base << 16) + (uint32_t)col0;
-            float* Cz = C + (splits > 1 ? (int64_t)tc.z * M * ldc : 0);
-            float* dst_row = Cz + m * ldc + nbeg;
-#pragma unroll
-            for (int c0 = 0; c0 < CH; c0 += 32) {
-                float acc[32];
-                {
-                    uint32_t r[32];
-                    tmem_ld_32x32b_x32(t_main + (uint32_t)c0, r);
-                    if (SPLIT3) {
-                        uint32_t r2[32];
-                        tmem_ld_32x32b_x32(t_main + (uint32_t)(BN + c0), r2);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(r[j]) + __uint_as_float(r2[j]);
-                    } else {
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(r[j]);
-                    }
-                }
-                if (c0 + 32 >= CH) {
-                    // all TMEM reads of this thread are complete: hand the slot back so the next tile's MMAs can start
-                    tc_fence_before();
-                    mbar_arrive(acc_empty_bar);
-                }
-                if (c0 > 0 && aux_row) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) auxv[j] = *reinterpret_cast<const float4*>(aux_row + c0 + 4 * j);
-                }
-                if (m < M) {
-                    float* dst = dst_row + c0;
-                    if (fast) {
-                        // whole row segment in bounds, 128-bit everything; mode / activation resolved once per chunk into
-                        // a straight-line specialisation (a per-element switch cost 4x the instructions)
-                        const float* bias_n0 = epi.bias ? bias_base + nbeg + c0 : nullptr;
-                        if (mode == 1) {
-                            switch (epi.act) {
-                                case SFB200_ACT_ELU: write_row<1, SFB200_ACT_ELU, 32>(acc, dst, bias_n0, auxv); break;
-                                case SFB200_ACT_RELU: write_row<1, SFB200_ACT_RELU, 32>(acc, dst, bias_n0, auxv); break;
-                                case SFB200_ACT_TANH: write_row<1, SFB200_ACT_TANH, 32>(acc, dst, bias_n0, auxv); break;
-                                default: write_row<1, SFB200_ACT_NONE, 32>(acc, dst, bias_n0, auxv); break;
-                            }
-                        } else if (mode == 2) {
-                            switch (epi.act) {
-                                case SFB200_ACT_ELU: write_row<2, SFB200_ACT_ELU, 32>(acc, dst, bias_n0, auxv); break;
-                                case SFB200_ACT_RELU: write_row<2, SFB200_ACT_RELU, 32>(acc, dst, bias_n0, auxv); break;
-                                case SFB200_ACT_TANH: write_row<2, SFB200_ACT_TANH, 32>(acc, dst, bias_n0, auxv); break;
-                                default: write_row<0, SFB200_ACT_NONE, 32>(acc, dst, bias_n0, auxv); break;
-                            }
-                        } else {
-                            write_row<0, SFB200_ACT_NONE, 32>(acc, dst, bias_n0, auxv);
-                        }
-                    } else {
+        } else {
 #pragma unroll   // fully unrolled so that acc[] stays in registers (no dynamic indexing)
-                        for (int j = 0; j < 32; ++j) {
-                            const int n = nbeg + c0 + j;
-                            if (n < N) {
-                                float v = acc[j];
-                                if (mode == 1) v = act_fwd_fast(v + (epi.bias ? epi.bias[n] : 0.f), epi.act);
-                                else if (mode == 2) v = v * act_bwd_from_out(epi.aux[m * epi.ld_aux + n], epi.act);
-                                dst[j] = v;
-                            }
-                        }
-                    }
+            for (int j = 0; j < 32; ++j) {
+                const int n = nbeg + c0 + j;
+                if (n < N) {
+                    float v = acc[j];
+                    if (mode == 1) v = act_fwd_fast(v + (epi.bias ? epi.bias[n] : 0.f), epi.act);
+                    else if (mode == 2) v = v * act_bwd_from_out(epi.aux[m * epi.ld_aux + n], epi.act);
+                    dst[j] = v;
                 }
             }
+        }
+    }
 }
-
 
 // Epilogue with the policy/value heads folded in (forward layers feeding critic_linear / distribution_linear,
 // actor_critic.py:171-186): y = act(acc + bias) is formed in registers, optionally stored, and immediately contracted
@@ -394,65 +398,43 @@ __device__ __forceinline__ void tc_epilogue_tile_heads(uint32_t tmem_slot_addr, 
     constexpr int CH = BN / 2;
     const int64_t m = tc.m0 + ec.lane_base + ec.lane;
     const int nbeg = tc.n0 + ec.col0;
+    float o[CH];
+    tmem_drain<BN, CH, SPLIT3>(tmem_slot_addr + ((uint32_t)ec.lane_base << 16) + (uint32_t)ec.col0, o, acc_full_bar, acc_ph,
+                               acc_empty_bar);
+    if (m >= M) return;
     float hp[kHeadAP];
 #pragma unroll
     for (int a = 0; a < kHeadAP; ++a) hp[a] = 0.f;
-    mbar_wait(acc_full_bar, acc_ph);
-    tc_fence_after();
-    const uint32_t t_main = tmem_slot_addr + ((uint32_t)ec.lane_base << 16) + (uint32_t)ec.col0;
-    float* dst_row = (C && m < M) ? C + m * ldc + nbeg : nullptr;
-#pragma unroll 1
-    for (int c0 = 0; c0 < CH; c0 += 16) {
-        float o[16];
-        {
-            uint32_t r[16];
-            tmem_ld_32x32b_x16(t_main + (uint32_t)c0, r);
-            if (SPLIT3) {
-                uint32_t r2[16];
-                tmem_ld_32x32b_x16(t_main + (uint32_t)(BN + c0), r2);
-                tmem_ld_wait();
+    float* dst_row = C ? C + m * ldc + nbeg : nullptr;
+    const float* bias_n0 = ec.bias_base + nbeg;   // staged in shared memory (host guarantees N <= BIAS_FLOATS)
 #pragma unroll
-                for (int j = 0; j < 16; ++j) o[j] = __uint_as_float(r[j]) + __uint_as_float(r2[j]);
-            } else {
-                tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 16; ++j) o[j] = __uint_as_float(r[j]);
-            }
-        }
-        if (c0 + 16 >= CH) {
-            tc_fence_before();
-            mbar_arrive(acc_empty_bar);
-        }
-        const float* bias_n0 = ec.bias_base + nbeg + c0;   // staged in shared memory (host guarantees N <= BIAS_FLOATS)
-#pragma unroll
-        for (int j = 0; j < 16; j += 4) {
-            const float4 b = *reinterpret_cast<const float4*>(bias_n0 + j);
-            o[j] = act_fwd_ct<ACT>(o[j] + b.x);
-            o[j + 1] = act_fwd_ct<ACT>(o[j + 1] + b.y);
-            o[j + 2] = act_fwd_ct<ACT>(o[j + 2] + b.z);
-            o[j + 3] = act_fwd_ct<ACT>(o[j + 3] + b.w);
-            if (dst_row) *reinterpret_cast<float4*>(dst_row + c0 + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
-        }
-#pragma unroll
-        for (int a = 0; a < kHeadAP; ++a) {
-            const float* w = headw_s + a * N + nbeg + c0;   // warp-uniform address: shared-memory broadcast
-#pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-                const float4 wv = *reinterpret_cast<const float4*>(w + j);
-                hp[a] = fmaf(o[j], wv.x, hp[a]);
-                hp[a] = fmaf(o[j + 1], wv.y, hp[a]);
-                hp[a] = fmaf(o[j + 2], wv.z, hp[a]);
-                hp[a] = fmaf(o[j + 3], wv.w, hp[a]);
-            }
-        }
+    for (int j = 0; j < CH; j += 4) {
+        const float4 b = *reinterpret_cast<const float4*>(bias_n0 + j);
+        o[j] = act_fwd_ct<ACT>(o[j] + b.x);
+        o[j + 1] = act_fwd_ct<ACT>(o[j + 1] + b.y);
+        o[j + 2] = act_fwd_ct<ACT>(o[j + 2] + b.z);
+        o[j + 3] = act_fwd_ct<ACT>(o[j + 3] + b.w);
+        if (dst_row) *reinterpret_cast<float4*>(dst_row + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
     }
-    if (m < M) {
-        const int p = (tc.n0 / BN) * 2 + (ec.col0 ? 1 : 0);
-        float4* dst = reinterpret_cast<float4*>(epi.head_part + ((int64_t)p * M + m) * kHeadPad);
-        dst[0] = make_float4(hp[0], hp[1], hp[2], hp[3]);
-        dst[1] = make_float4(hp[4], hp[5], hp[6], hp[7]);
-        dst[2] = make_float4(hp[8], 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int a = 0; a < kHeadAP; ++a) {
+        const float* w = headw_s + a * N + nbeg;   // warp-uniform address: shared-memory broadcast
+        float s0 = 0.f, s1 = 0.f;                  // two chains per output: halves the dependent-FMA latency
+#pragma unroll
+        for (int j = 0; j < CH; j += 4) {
+            const float4 wv = *reinterpret_cast<const float4*>(w + j);
+            s0 = fmaf(o[j], wv.x, s0);
+            s1 = fmaf(o[j + 1], wv.y, s1);
+            s0 = fmaf(o[j + 2], wv.z, s0);
+            s1 = fmaf(o[j + 3], wv.w, s1);
+        }
+        hp[a] = s0 + s1;
     }
+    const int p = (tc.n0 / BN) * 2 + (ec.col0 ? 1 : 0);
+    float4* dst = reinterpret_cast<float4*>(epi.head_part + ((int64_t)p * M + m) * kHeadPad);
+    dst[0] = make_float4(hp[0], hp[1], hp[2], hp[3]);
+    dst[1] = make_float4(hp[4], hp[5], hp[6], hp[7]);
+    dst[2] = make_float4(hp[8], 0.f, 0.f, 0.f);
 }
 
 // ------------------------------------------------------------------------------------------------ the kernel
@@ -499,6 +481,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // everything above is CTA-local setup (barriers, TMEM allocation, descriptor prefetch): under programmatic dependent
+    // launch it overlaps the tail of the previous kernel; global memory is only touched after the wait
+    pdl_wait();
+    pdl_trigger();
 
     if (warp == 0) {
         // ===================================================== TMA producer
@@ -691,6 +677,10 @@ gemm_tc_ta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // everything above is CTA-local setup (barriers, TMEM allocation, descriptor prefetch): under programmatic dependent
+    // launch it overlaps the tail of the previous kernel; global memory is only touched after the wait
+    pdl_wait();
+    pdl_trigger();
 
     if (warp == 0) {
         // ===================================================== TMA producer
@@ -926,7 +916,8 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, float* C, int
     }
     const int64_t tiles = ceil_div(N, BN) * ceil_div(M, TBM) * splits;
     const int64_t grid = tiles < sm_count() ? tiles : sm_count();   // persistent: one CTA per SM
-    kern<<<(unsigned)grid, TC_THREADS, S::TOTAL, st>>>(ta, tb, C, ldc, M, N, K, k_chunk, splits, epi);
+    SFB_CUDA_OK(launch_pdl(kern, dim3((unsigned)grid), dim3(TC_THREADS), (size_t)S::TOTAL, st, ta, tb, C, ldc, M, N, K, k_chunk,
+                           splits, epi));
     SFB_LAUNCH_OK();
     return 0;
 }
@@ -956,8 +947,8 @@ static int launch_tc_ta(const CUtensorMap& ta, const CUtensorMap& tb, float* C, 
     }
     const int64_t tiles = ceil_div(N, 128) * ceil_div(M, TBM) * splits;
     const int64_t grid = tiles < sm_count() ? tiles : sm_count();
-    kern<<<(unsigned)grid, TC_THREADS, SMEM, st>>>(ta, tb, C, ldc, M, N, K, k_chunk, splits, epi,
-                                                    raw_hi_enabled() ? 1 : 0);
+    SFB_CUDA_OK(launch_pdl(kern, dim3((unsigned)grid), dim3(TC_THREADS), (size_t)SMEM, st, ta, tb, C, ldc, M, N, K, k_chunk,
+                           splits, epi, raw_hi_enabled() ? 1 : 0));
     SFB_LAUNCH_OK();
     return 0;
 }

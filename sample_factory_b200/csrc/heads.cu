@@ -69,6 +69,8 @@ __global__ void __launch_bounds__(256) heads_from_partials_kernel(
     const float* __restrict__ part, int P, int64_t rows, int A, const float* __restrict__ bv, const float* __restrict__ ba,
     HeadsOut out, const float* __restrict__ noise, uint64_t seed, uint64_t offset_host,
     const int64_t* __restrict__ offset_dev, const float* __restrict__ pv_scalar) {
+    pdl_wait();
+    pdl_trigger();
     const int lane = threadIdx.x & 31;
     const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -99,6 +101,8 @@ __global__ void __launch_bounds__(256) heads_forward_kernel(
     int32_t* __restrict__ env_actions, float* __restrict__ log_prob, int64_t log_prob_stride,
     const float* __restrict__ pv_scalar, float* __restrict__ pv_out, int64_t pv_stride) {
     extern __shared__ float wcat[];   // [(A+1)][H]
+    pdl_wait();
+    pdl_trigger();
     const int n_out = A + 1;
     for (int i = threadIdx.x; !VEC && i < n_out * H; i += blockDim.x) {
         const int a = i / H, j = i - a * H;
@@ -375,9 +379,9 @@ static int launch_heads_forward(const float* h, int64_t ldh, int64_t rows, int H
     int64_t blocks = ceil_div(ceil_div(rows, RPW), 8);
     const int64_t cap = (int64_t)sm_count() * 4;
     if (blocks > cap) blocks = cap;
-    kern<<<(unsigned)blocks, 256, smem, st>>>(h, ldh, rows, H, A, Wv, bv, Wa, ba, values, values_stride, logits,
-                                              logits_stride, noise, seed, offset, offset_dev, actions_f32, actions_stride,
-                                              env_actions, log_prob, log_prob_stride, pv_scalar, pv_out, pv_stride);
+    SFB_CUDA_OK(launch_pdl(kern, dim3((unsigned)blocks), dim3(256), smem, st, h, ldh, rows, H, A, Wv, bv, Wa, ba, values,
+                           values_stride, logits, logits_stride, noise, seed, offset, offset_dev, actions_f32,
+                           actions_stride, env_actions, log_prob, log_prob_stride, pv_scalar, pv_out, pv_stride));
     SFB_LAUNCH_OK();
     return 0;
 }
@@ -435,9 +439,9 @@ int sfb200_heads_from_partials(const float* head_partials, int P, int64_t rows, 
     int64_t blocks = ceil_div(rows, 8);
     const int64_t cap = (int64_t)sm_count() * 8;
     if (blocks > cap) blocks = cap;
-    heads_from_partials_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
-        head_partials, P, rows, A, bv, ba, out, noise, philox_seed, philox_offset, philox_offset_dev,
-        policy_version_scalar);
+    SFB_CUDA_OK(launch_pdl(heads_from_partials_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream,
+                           head_partials, P, rows, A, bv, ba, out, noise, philox_seed, philox_offset, philox_offset_dev,
+                           policy_version_scalar));
     SFB_LAUNCH_OK();
     return 0;
 }

@@ -1,0 +1,13 @@
+#!/bin/bash
+# epilogue drain-first + PDL on the sampler chain: tests, then bench with PDL on / off
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -q -x > gpurun_out/all_tests.log 2>&1; echo "all tests rc=$?"; tail -6 gpurun_out/all_tests.log
+timeout 300 python tools/gemm_bench.py > gpurun_out/gemm_bench.log 2>&1; grep -E "3xtf32" gpurun_out/gemm_bench.log
+timeout 600 python bench.py --no-cpu-baseline > gpurun_out/bench15.json 2> gpurun_out/bench15.err; echo "bench rc=$?"; tail -3 gpurun_out/bench15.err
+SFB200_PDL=0 timeout 600 python bench.py --no-cpu-baseline --no-e2e --no-async > gpurun_out/bench15_nopdl.json 2> gpurun_out/bench15_nopdl.err; echo "bench nopdl rc=$?"; tail -3 gpurun_out/bench15_nopdl.err
+python - <<'PY'
+import json
+for f in ['gpurun_out/bench15.json','gpurun_out/bench15_nopdl.json']:
+    d=json.load(open(f))
+    print(f, {k:d[k] for k in ['value','ms_per_step']}, d['e2e'] and d['e2e']['value'], d['async_rl'] and d['async_rl']['value'], d['roofline']['achieved'], d['roofline']['avg_kernel_ms'], d['roofline_sampler']['rollout_ms'], d['launches_per_step'])
+PY
