@@ -38,7 +38,11 @@ class OracleCfg:
     """The subset of reference flags (cfg/cfg.py) that the hot path reads. Defaults = reference defaults."""
 
     obs_dim: int = 64
-    num_actions: int = 8  # Discrete(n)
+    num_actions: int = 8  # Discrete(n), or the dimension of a Box action space when `continuous`
+    continuous: bool = False           # gym.spaces.Box action space -> ContinuousActionDistribution
+    adaptive_stddev: bool = True       # cfg.py:577: False -> one learned log-stddev vector (mujoco examples)
+    continuous_tanh_scale: float = 0.0  # cfg.py:583 (only read by the non-adaptive parameterization)
+    initial_stddev: float = 1.0        # cfg.py:591
     encoder_mlp_layers: List[int] = field(default_factory=lambda: [512, 512])
     decoder_mlp_layers: List[int] = field(default_factory=list)
     nonlinearity: str = "elu"
@@ -103,6 +107,7 @@ ACTION_W, ACTION_B = (
     "action_parameterization.distribution_linear.weight",
     "action_parameterization.distribution_linear.bias",
 )
+LEARNED_STD = "action_parameterization.learned_stddev"
 OBS_MEAN = "obs_normalizer.running_mean_std.running_mean_std.obs.running_mean"
 OBS_VAR = "obs_normalizer.running_mean_std.running_mean_std.obs.running_var"
 OBS_COUNT = "obs_normalizer.running_mean_std.running_mean_std.obs.count"
@@ -122,8 +127,30 @@ def param_names(cfg: OracleCfg) -> List[str]:
         names += [RNN_W_IH, RNN_W_HH, RNN_B_IH, RNN_B_HH]
     for i in range(len(cfg.decoder_mlp_layers)):
         names += [dec_w(i), dec_b(i)]
-    names += [CRITIC_W, CRITIC_B, ACTION_W, ACTION_B]
+    names += [CRITIC_W, CRITIC_B]
+    if cfg.continuous and not cfg.adaptive_stddev:
+        # ActionParameterizationContinuousNonAdaptiveStddev (action_parameterization.py:42-62): nn.Module.parameters()
+        # yields a module's own parameters before its children's, so learned_stddev precedes distribution_linear.*
+        names += [LEARNED_STD]
+    names += [ACTION_W, ACTION_B]
     return names
+
+
+def num_linear_action_outputs(cfg: OracleCfg) -> int:
+    """rows of distribution_linear: n (Discrete), 2A (Box, adaptive stddev), A (Box, learned stddev)"""
+    if not cfg.continuous:
+        return cfg.num_actions
+    return 2 * cfg.num_actions if cfg.adaptive_stddev else cfg.num_actions
+
+
+def num_action_params(cfg: OracleCfg) -> int:
+    """calc_num_action_parameters (action_distributions.py:33-44): width of `action_logits`"""
+    return 2 * cfg.num_actions if cfg.continuous else cfg.num_actions
+
+
+def action_width(cfg: OracleCfg) -> int:
+    """calc_num_actions (action_distributions.py:16-30): width of `actions`"""
+    return cfg.num_actions if cfg.continuous else 1
 
 
 def rnn_state_size(cfg: OracleCfg) -> int:
@@ -157,8 +184,10 @@ def init_state(cfg: OracleCfg, seed: int = 0) -> Dict[str, Tensor]:
         d = h
     st[CRITIC_W] = torch.randn(1, d, generator=g) / math.sqrt(d)
     st[CRITIC_B] = torch.zeros(1)
-    st[ACTION_W] = torch.randn(cfg.num_actions, d, generator=g) / math.sqrt(d)
-    st[ACTION_B] = torch.zeros(cfg.num_actions)
+    st[ACTION_W] = torch.randn(num_linear_action_outputs(cfg), d, generator=g) / math.sqrt(d)
+    st[ACTION_B] = torch.zeros(num_linear_action_outputs(cfg))
+    if cfg.continuous and not cfg.adaptive_stddev:
+        st[LEARNED_STD] = torch.full((cfg.num_actions,), math.log(cfg.initial_stddev))
     st[OBS_MEAN] = torch.zeros(cfg.obs_dim, dtype=torch.float64)
     st[OBS_VAR] = torch.ones(cfg.obs_dim, dtype=torch.float64)
     st[OBS_COUNT] = torch.ones(1, dtype=torch.float64)
@@ -243,6 +272,12 @@ def tail_forward(cfg: OracleCfg, st: Dict[str, Tensor], h: Tensor) -> Tuple[Tens
         h = _act(cfg, torch.nn.functional.linear(h, st[dec_w(i)], st[dec_b(i)]))
     values = torch.nn.functional.linear(h, st[CRITIC_W], st[CRITIC_B]).squeeze(-1)
     logits = torch.nn.functional.linear(h, st[ACTION_W], st[ACTION_B])
+    if cfg.continuous and not cfg.adaptive_stddev:
+        # ActionParameterizationContinuousNonAdaptiveStddev.forward (action_parameterization.py:64-78)
+        means = logits
+        if cfg.continuous_tanh_scale > 0:
+            means = torch.tanh(means / cfg.continuous_tanh_scale) * cfg.continuous_tanh_scale
+        logits = torch.cat((means, st[LEARNED_STD].repeat(means.shape[0], 1)), dim=1)
     return values, logits
 
 
@@ -317,6 +352,61 @@ def cat_kl(logits_p: Tensor, logits_q: Tensor) -> Tensor:
 
 
 # --------------------------------------------------------------------------------------
+# Diagonal Gaussian distribution (algo/utils/action_distributions.py:290-323 = Independent(Normal(means, std), 1);
+# torch/distributions/normal.py for the arithmetic; SURVEY App.C)
+# --------------------------------------------------------------------------------------
+STDDEV_MIN, STDDEV_MAX = 1e-4, 1e4  # action_distributions.py:291-292
+
+
+def gauss_split(params: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
+    """_init_impl :299-306 -> (means, log_std, clamped stddevs)"""
+    means, log_std = torch.chunk(params, 2, dim=1)
+    return means, log_std, torch.clamp(log_std.exp(), STDDEV_MIN, STDDEV_MAX)
+
+
+def gauss_sample(params: Tensor, eps: Tensor) -> Tensor:
+    """Normal.sample() == torch.normal(mean, std) == eps * std + mean with the product and the sum rounded separately
+    (eps = the N(0,1) draw; an explicit input here, recovered from the reference's generator by make_golden.py)."""
+    means, _, std = gauss_split(params)
+    return eps * std + means
+
+
+def gauss_log_prob(params: Tensor, actions: Tensor) -> Tensor:
+    """Independent(Normal).log_prob: sum over the action dimension of normal.py:84-94"""
+    means, _, std = gauss_split(params)
+    var = std**2
+    lp = -((actions - means) ** 2) / (2 * var) - std.log() - math.log(math.sqrt(2 * math.pi))
+    return lp.sum(-1)
+
+
+def gauss_entropy(params: Tensor) -> Tensor:
+    """normal.py:107-108 summed over the action dimension"""
+    _, _, std = gauss_split(params)
+    return (0.5 + 0.5 * math.log(2 * math.pi) + torch.log(std)).sum(-1)
+
+
+def gauss_kl(params_p: Tensor, params_q: Tensor) -> Tensor:
+    """KL(p || q) of Independent Normals (torch/distributions/kl.py _kl_normal_normal, summed)"""
+    mp, _, sp = gauss_split(params_p)
+    mq, _, sq = gauss_split(params_q)
+    var_ratio = (sp / sq).pow(2)
+    t1 = ((mp - mq) / sq).pow(2)
+    return (0.5 * (var_ratio + t1 - 1 - var_ratio.log())).sum(-1)
+
+
+def dist_log_prob(cfg: OracleCfg, logits: Tensor, actions: Tensor) -> Tensor:
+    return gauss_log_prob(logits, actions.view(logits.shape[0], -1)) if cfg.continuous else cat_log_prob(logits, actions)
+
+
+def dist_entropy(cfg: OracleCfg, logits: Tensor) -> Tensor:
+    return gauss_entropy(logits) if cfg.continuous else cat_entropy(logits)
+
+
+def dist_kl(cfg: OracleCfg, logits_p: Tensor, logits_q: Tensor) -> Tensor:
+    return gauss_kl(logits_p, logits_q) if cfg.continuous else cat_kl(logits_p, logits_q)
+
+
+# --------------------------------------------------------------------------------------
 # Sampler: one policy step + one env step  (inference_worker.py:313-341, batched_sampling.py:298-388)
 # --------------------------------------------------------------------------------------
 def alloc_trajectories(cfg: OracleCfg, num_traj: int) -> Dict[str, Tensor]:
@@ -325,8 +415,8 @@ def alloc_trajectories(cfg: OracleCfg, num_traj: int) -> Dict[str, Tensor]:
     t: Dict[str, Tensor] = {}
     t["obs"] = torch.full((B, T + 1, cfg.obs_dim), -4242.42)
     t["rnn_states"] = torch.full((B, T + 1, rnn_state_size(cfg)), -4242.42)
-    t["actions"] = torch.full((B, T, 1), -4242.42)
-    t["action_logits"] = torch.full((B, T, cfg.num_actions), -4242.42)
+    t["actions"] = torch.full((B, T, action_width(cfg)), -4242.42)
+    t["action_logits"] = torch.full((B, T, num_action_params(cfg)), -4242.42)
     t["log_prob_actions"] = torch.full((B, T), -4242.42)
     t["values"] = torch.full((B, T + 1), -4242.42)
     t["policy_version"] = torch.full((B, T), -4242.42)
@@ -344,8 +434,12 @@ def policy_step(cfg: OracleCfg, st: Dict[str, Tensor], obs: Tensor, noise_q: Ten
     Returns (actions int64 [N,1], logits [N,A], log_prob [N], values [N], new_rnn_state)."""
     x = normalize_obs(cfg, st, obs, update_stats=False)
     values, logits, new_state = model_forward(cfg, st, x, rnn_state)
-    actions = cat_sample(logits, noise_q)
-    log_prob = cat_log_prob(logits, actions)
+    if cfg.continuous:   # noise_q: [N, A] standard-normal draws
+        actions = gauss_sample(logits, noise_q)
+        log_prob = gauss_log_prob(logits, actions)
+    else:
+        actions = cat_sample(logits, noise_q)
+        log_prob = cat_log_prob(logits, actions)
     return actions, logits, log_prob, values, new_state
 
 
@@ -370,7 +464,10 @@ class TapeVecEnv:
     def step(self, actions: Tensor) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
         env = torch.arange(self.num_agents)
         t = self.t
-        rew = actions.view(-1).float() / float(self.num_actions)
+        if actions.is_floating_point():   # Box action space [N, A]: reward = first action component, clipped
+            rew = actions.view(self.num_agents, -1)[:, 0].clamp(-1.0, 1.0)
+        else:
+            rew = actions.view(-1).float() / float(self.num_actions)
         terminated = ((t * 7 + env * 13) % self.term_period) == 0
         truncated = (((t + env) % self.trunc_period) == 0) & ~terminated
         self.t += 1
@@ -403,7 +500,8 @@ def rollout(
         traj["log_prob_actions"][:, t] = log_prob
         traj["values"][:, t] = values
         traj["policy_version"][:, t] = float(policy_version)  # inference_worker.py:332
-        env_actions = actions.to(torch.int32).squeeze(-1)  # preprocess_actions :30-82
+        # preprocess_actions :30-82 (discrete: int32, squeezed; Box: float, as is)
+        env_actions = actions if cfg.continuous else actions.to(torch.int32).squeeze(-1)
         last_obs, rew, terminated, truncated = env.step(env_actions)
         dones = terminated | truncated  # :317
         # _process_rewards :208-213
@@ -554,7 +652,7 @@ def calculate_losses(cfg: OracleCfg, params: Dict[str, Tensor], mb: Dict[str, Te
     else:
         core = head  # ModelCoreIdentity :579
     values, logits = tail_forward(cfg, params, core)  # :586
-    log_prob = cat_log_prob(logits, mb["actions"])  # :588
+    log_prob = dist_log_prob(cfg, logits, mb["actions"])  # :588
     ratio = torch.exp(log_prob - mb["log_prob_actions"])  # :589
     ratio = torch.clamp(ratio, 0.05, 20.0)  # :592
 
@@ -575,10 +673,10 @@ def calculate_losses(cfg: OracleCfg, params: Dict[str, Tensor], mb: Dict[str, Te
     if cfg.exploration_loss_coeff == 0.0:
         exploration_loss = torch.zeros(())
     else:
-        ent = _masked_select(cat_entropy(logits), valids, num_invalids)
+        ent = _masked_select(dist_entropy(cfg, logits), valids, num_invalids)
         exploration_loss = -cfg.exploration_loss_coeff * ent.mean()
     # _kl_loss :461-471 (only part of the loss if coeff != 0; kl_old is always computed for stats :758-768)
-    kl_old = _masked_select(cat_kl(logits, mb["action_logits"]), valids, num_invalids)
+    kl_old = _masked_select(dist_kl(cfg, logits, mb["action_logits"]), valids, num_invalids)
     kl_loss = cfg.kl_loss_coeff * kl_old.mean() if cfg.kl_loss_coeff != 0.0 else torch.zeros(())
     # _value_loss :441-459
     old_values = mb["values"]

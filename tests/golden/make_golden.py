@@ -50,7 +50,7 @@ OUT_DIR = os.path.dirname(os.path.abspath(__file__))
 class RefTapeEnv(gym.Env):
     """Adapter: TapeVecEnv behind the reference's batched-env contract (make_env.py:147-237)."""
 
-    def __init__(self, tape_env: TapeVecEnv):
+    def __init__(self, tape_env: TapeVecEnv, continuous: bool = False):
         self.e = tape_env
         self.num_agents = tape_env.num_agents
         self.is_multiagent = True
@@ -58,12 +58,14 @@ class RefTapeEnv(gym.Env):
             {"obs": gym.spaces.Box(-np.inf, np.inf, (tape_env.obs_dim,), np.float32)}
         )
         self.action_space = gym.spaces.Discrete(tape_env.num_actions)
+        if continuous:   # Box(A) action space -> ContinuousActionDistribution (action_distributions.py:290-323)
+            self.action_space = gym.spaces.Box(-1.0, 1.0, (tape_env.num_actions,), np.float32)
 
     def reset(self, **kw):
         return {"obs": self.e.reset().clone()}, {}
 
     def step(self, actions):
-        obs, rew, term, trunc = self.e.step(torch.as_tensor(actions))  # numpy int32 (batched_sampling.py:62-82)
+        obs, rew, term, trunc = self.e.step(torch.as_tensor(actions))  # numpy int32 / float32 (batched_sampling.py:62-82)
         return {"obs": obs.clone()}, rew, term, trunc, {}
 
     def close(self):
@@ -71,7 +73,7 @@ class RefTapeEnv(gym.Env):
 
 
 def run_case(name: str, N: int, T: int, obs_dim: int, A: int, hidden, iters: int, overrides: dict, poison: bool,
-             save_checkpoint: bool = False):
+             save_checkpoint: bool = False, continuous: bool = False):
     torch.manual_seed(1234)
     np.random.seed(1234)
     tape_len = T * iters + 1
@@ -79,7 +81,7 @@ def run_case(name: str, N: int, T: int, obs_dim: int, A: int, hidden, iters: int
     tape_env = TapeVecEnv(tape, A)
 
     env_name = f"tape_{name}"
-    register_env(env_name, lambda full_env_name, cfg, env_config, render_mode=None: RefTapeEnv(tape_env))
+    register_env(env_name, lambda full_env_name, cfg, env_config, render_mode=None: RefTapeEnv(tape_env, continuous))
 
     cfg = default_cfg(env=env_name, experiment=f"golden_{name}")
     cfg.device = "cpu"
@@ -159,12 +161,20 @@ def run_case(name: str, N: int, T: int, obs_dim: int, A: int, hidden, iters: int
                 rng_before = torch.get_rng_state()
                 policy_outputs = ac(normalized_obs, rnn_states)
                 rng_after = torch.get_rng_state()
-                # recover the Exp(1) noise torch.multinomial consumed (SURVEY App.E) and prove the identity
                 torch.set_rng_state(rng_before)
-                probs = torch.softmax(policy_outputs["action_logits"], -1)
-                q = torch.empty_like(probs).exponential_()
+                if continuous:
+                    # recover the N(0,1) draws Normal.sample() consumed (SURVEY App.C) and prove  a == eps*std + mean
+                    params = policy_outputs["action_logits"]
+                    mu, log_std = torch.chunk(params, 2, dim=1)
+                    std = torch.clamp(log_std.exp(), 1e-4, 1e4)
+                    q = torch.empty_like(mu).normal_()
+                    assert torch.equal(q * std + mu, policy_outputs["actions"]), "normal sample identity"
+                else:
+                    # recover the Exp(1) noise torch.multinomial consumed (SURVEY App.E) and prove the identity
+                    probs = torch.softmax(policy_outputs["action_logits"], -1)
+                    q = torch.empty_like(probs).exponential_()
+                    assert torch.equal(torch.argmax(probs / q, -1), policy_outputs["actions"]), "multinomial identity"
                 torch.set_rng_state(rng_after)
-                assert torch.equal(torch.argmax(probs / q, -1), policy_outputs["actions"]), "multinomial identity"
                 noise_steps.append(q.clone())
                 policy_outputs["policy_version"] = torch.empty([N]).fill_(int(policy_versions[0].item()))
                 # _prepare_policy_outputs_batched :235-269
@@ -235,7 +245,8 @@ def run_case(name: str, N: int, T: int, obs_dim: int, A: int, hidden, iters: int
         shutil.copy(files[-1], os.path.join(OUT_DIR, f"{name}_checkpoint.pth"))
         print("checkpoint fixture:", os.path.basename(files[-1]))
 
-    meta = dict(N=N, T=T, obs_dim=obs_dim, A=A, hidden=list(hidden), iters=iters, poison=poison, **overrides)
+    meta = dict(N=N, T=T, obs_dim=obs_dim, A=A, hidden=list(hidden), iters=iters, poison=poison, continuous=continuous,
+                **overrides)
     out["meta"] = np.array(repr(meta))
     # a few flags the oracle needs, straight from the reference cfg object
     for k in ["gamma", "gae_lambda", "ppo_clip_ratio", "ppo_clip_value", "exploration_loss_coeff", "value_loss_coeff",
@@ -243,7 +254,11 @@ def run_case(name: str, N: int, T: int, obs_dim: int, A: int, hidden, iters: int
               "reward_scale", "reward_clip", "max_policy_lag", "batch_size", "num_batches_per_epoch", "num_epochs",
               "recurrence", "vtrace_rho", "vtrace_c"]:
         out[f"cfg/{k}"] = np.float64(getattr(cfg, k))
-    for k in ["normalize_input", "normalize_returns", "value_bootstrap", "with_vtrace", "use_rnn"]:
+    for k in ["continuous_tanh_scale", "initial_stddev"]:
+        out[f"cfg/{k}"] = np.float64(getattr(cfg, k))
+    out["cfg/nonlinearity"] = np.array(cfg.nonlinearity)
+    out["cfg/continuous"] = np.bool_(continuous)
+    for k in ["normalize_input", "normalize_returns", "value_bootstrap", "with_vtrace", "use_rnn", "adaptive_stddev"]:
         out[f"cfg/{k}"] = np.bool_(getattr(cfg, k))
     out["cfg/rnn_size"] = np.float64(cfg.rnn_size)
     out["cfg/rnn_type"] = np.array(cfg.rnn_type)
@@ -313,6 +328,22 @@ if __name__ == "__main__":
         overrides=dict(batch_size=128, num_batches_per_epoch=2, num_epochs=1, use_rnn=True, rnn_type="lstm", rnn_size=32,
                        recurrence=4),
         poison=False,
+    )
+    # continuous actions (BASELINE cfg-3, mujoco-style flags sf_examples/mujoco/mujoco_params.py:1-38): Box(6) actions,
+    # tanh MLP [64,64], one learned log-stddev vector (adaptive_stddev=False) with tanh-squashed means, fixed-KL loss,
+    # value bootstrap, no entropy bonus; and the default adaptive-stddev parameterization (2A linear outputs)
+    run_case(
+        "tiny_gauss", N=32, T=8, obs_dim=16, A=6, hidden=[64, 64], iters=2,
+        overrides=dict(batch_size=128, num_batches_per_epoch=2, num_epochs=2, nonlinearity="tanh", adaptive_stddev=False,
+                       continuous_tanh_scale=1.5, initial_stddev=0.7, kl_loss_coeff=0.1, value_bootstrap=True,
+                       exploration_loss_coeff=0.0, ppo_clip_ratio=0.2, value_loss_coeff=1.3, max_grad_norm=3.5,
+                       learning_rate=0.00295),
+        poison=True, continuous=True,
+    )
+    run_case(
+        "tiny_gauss_adaptive", N=32, T=8, obs_dim=16, A=6, hidden=[64, 64], iters=2,
+        overrides=dict(batch_size=128, num_batches_per_epoch=2, num_epochs=1, kl_loss_coeff=0.05),
+        poison=False, continuous=True,
     )
     # cfg-2 hyper-parameters and model (300 553 params) at a reduced env count
     run_case(

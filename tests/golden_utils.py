@@ -13,7 +13,7 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 def load_case(name):
     z = np.load(os.path.join(GOLDEN_DIR, f"{name}.npz"), allow_pickle=False)
     meta = ast.literal_eval(str(z["meta"]))
-    c = {k[4:]: z[k].item() for k in z.files if k.startswith("cfg/") and k != "cfg/rnn_type"}
+    c = {k[4:]: z[k].item() for k in z.files if k.startswith("cfg/") and k not in ("cfg/rnn_type", "cfg/nonlinearity")}
     cfg = O.OracleCfg(
         obs_dim=meta["obs_dim"], num_actions=meta["A"], encoder_mlp_layers=list(meta["hidden"]),
         rollout=meta["T"], recurrence=int(c["recurrence"]), batch_size=int(c["batch_size"]),
@@ -28,6 +28,9 @@ def load_case(name):
         reward_scale=c["reward_scale"], reward_clip=c["reward_clip"], max_policy_lag=int(c["max_policy_lag"]),
         use_rnn=bool(c.get("use_rnn", False)), rnn_size=int(c.get("rnn_size", 512)),
         rnn_type=str(z["cfg/rnn_type"]) if "cfg/rnn_type" in z.files else "gru",
+        nonlinearity=str(z["cfg/nonlinearity"]) if "cfg/nonlinearity" in z.files else "elu",
+        continuous=bool(c.get("continuous", False)), adaptive_stddev=bool(c.get("adaptive_stddev", True)),
+        continuous_tanh_scale=float(c.get("continuous_tanh_scale", 0.0)), initial_stddev=float(c.get("initial_stddev", 1.0)),
     )
     return z, meta, cfg
 
