@@ -49,6 +49,14 @@ int sfb200_set_device(int device);
 int sfb200_sm_count(void);
 /* 1 if the tcgen05/TMA GEMM engine is usable in this process (driver entry points resolved), else 0 */
 int sfb200_tc_available(void);
+/* Pre-split weights for the 3xTF32 engine.  register: from now on every tcgen05-3xTF32 GEMM whose WEIGHT operand lies
+ * inside [base, base+n) reads the operand's low tf32 half from `lo` (same offsets) instead of deriving it in shared
+ * memory for every output tile, and sfb200_clip_adam_step on a registered buffer keeps `lo` current.  Any other write
+ * to the weights (checkpoint load, weight copy) must be followed by sfb200_refresh_tf32_lo(base).  With the
+ * environment variable SFB200_CHECK_LO=1 every use verifies the pair on the device and traps on a stale `lo`. */
+int sfb200_register_tf32_lo(const float* base, float* lo, int64_t n);
+int sfb200_unregister_tf32_lo(const float* base);
+int sfb200_refresh_tf32_lo(const float* base, void* stream);
 /* total number of CUDA kernels this library has launched (or recorded into a stream capture) in this process */
 uint64_t sfb200_launch_count(void);
 
@@ -102,6 +110,33 @@ int sfb200_heads_forward(const float* h, int64_t ldh, int64_t rows, int H, int A
                          const int64_t* philox_offset_dev, float* actions_f32, int64_t actions_stride, int32_t* env_actions_i32, float* log_prob,
                          int64_t log_prob_stride, const float* policy_version_scalar, float* policy_version_out,
                          int64_t pv_stride, void* stream);
+
+/* Continuous (Box) action spaces: critic_linear + distribution_linear + ContinuousActionDistribution
+ * (algo/utils/action_distributions.py:290-323 = Independent(Normal(means, clamp(exp(log_std), 1e-4, 1e4)), 1);
+ * model/action_parameterization.py:33-39 when adaptive_stddev -- distribution_linear has 2*act_dim rows [means|log_std]
+ * -- and :42-78 when not -- act_dim rows, means = tanh(z/tanh_scale)*tanh_scale if tanh_scale > 0, log_std = the
+ * learned vector).  params[i] (2*act_dim floats at params + i*params_stride) receives [means | log_std], the layout of
+ * the reference's `action_logits`.  Sampling mode (actions_f32 != NULL): a = eps*std + mean (product and sum rounded
+ * separately = Normal.sample()), eps = noise[i*act_dim + j] or N(0,1) from Philox4x32-10(seed, subsequence i*act_dim+j,
+ * offset); actions_f32[i*actions_stride + j] = env_actions_f32[i*act_dim + j] = a_j; log_prob = sum_j Normal.log_prob.
+ * The _from_partials variant finishes sfb200_linear_act_heads_forward exactly like sfb200_heads_from_partials. */
+int sfb200_heads_forward_continuous(const float* h, int64_t ldh, int64_t rows, int H, int act_dim, int adaptive_stddev,
+                                    const float* Wv, const float* bv, const float* Wa, const float* ba,
+                                    const float* learned_log_std, float tanh_scale, float* values,
+                                    int64_t values_stride, float* params, int64_t params_stride, const float* noise,
+                                    uint64_t philox_seed, uint64_t philox_offset, const int64_t* philox_offset_dev,
+                                    float* actions_f32, int64_t actions_stride, float* env_actions_f32, float* log_prob,
+                                    int64_t log_prob_stride, const float* policy_version_scalar,
+                                    float* policy_version_out, int64_t pv_stride, void* stream);
+int sfb200_heads_from_partials_continuous(const float* head_partials, int P, int64_t rows, int act_dim,
+                                          int adaptive_stddev, const float* bv, const float* ba,
+                                          const float* learned_log_std, float tanh_scale, float* values,
+                                          int64_t values_stride, float* params, int64_t params_stride,
+                                          const float* noise, uint64_t philox_seed, uint64_t philox_offset,
+                                          const int64_t* philox_offset_dev, float* actions_f32, int64_t actions_stride,
+                                          float* env_actions_f32, float* log_prob, int64_t log_prob_stride,
+                                          const float* policy_version_scalar, float* policy_version_out,
+                                          int64_t pv_stride, void* stream);
 
 /* The last hidden layer and the heads in ONE pass (same reference sites as sfb200_linear_act_forward +
  * sfb200_heads_forward): the tcgen05 epilogue forms y = act(x W^T + b) in registers and contracts it at once with
@@ -249,6 +284,21 @@ int sfb200_ppo_loss_fwd_bwd(const float* logits, const float* values, int A, con
                             float clip_ratio, float clip_value, float exploration_coeff, float value_coeff,
                             float kl_coeff, float grad_scale, float* dlogits, float* dvalues, double* stats,
                             void* workspace, void* stream);
+
+/* The same for a Box action space (ContinuousActionDistribution, action_distributions.py:290-323): params / params_old
+ * rows are [means | log_std] (2*act_dim floats, the `action_logits` layout), actions_f32 rows act_dim floats.
+ * adaptive_stddev: dlogits [B, 2*act_dim] = [d means | d log_std]; otherwise dlogits [B, act_dim] = d(pre-tanh means)
+ * and dlogstd [B, act_dim], whose column sum is the gradient of the learned log-stddev vector
+ * (action_parameterization.py:56-62). */
+int sfb200_action_ratio_continuous(const float* params, int act_dim, const float* actions_f32, const float* log_prob_old,
+                                   int64_t batch, float* ratio, void* stream);
+int sfb200_ppo_loss_fwd_bwd_continuous(const float* params, const float* values, int act_dim, int adaptive_stddev,
+                                       float tanh_scale, const float* actions_f32, const float* log_prob_old,
+                                       const float* values_old, const float* adv, const float* targets,
+                                       const uint8_t* valids, const float* params_old, int64_t batch, float clip_ratio,
+                                       float clip_value, float exploration_coeff, float value_coeff, float kl_coeff,
+                                       float grad_scale, float* dlogits, float* dlogstd, float* dvalues, double* stats,
+                                       void* workspace, void* stream);
 
 /* ------------------------------------------------------------- learner: backward ---- */
 int64_t sfb200_heads_backward_workspace_bytes(int H, int A);

@@ -39,6 +39,13 @@ void count_launch();   // every kernel launch of this library is counted (sfb200
     } while (0)
 
 int sm_count();
+// Registered "tf32 low halves" of weight buffers (api.cu): for a pointer range [p, p+count) inside a registered buffer,
+// the matching range of lo = ((w - (w & ~0x1fff)) & ~0x1fff) words, else NULL.  The 3xTF32 GEMM then takes the weight
+// operand's lo tile straight from HBM/L2 by TMA instead of splitting it in shared memory for every tile.
+const float* tf32_lo_lookup(const float* p, int64_t count);
+float* tf32_lo_lookup_mut(float* p, int64_t count);
+int tf32_lo_check(const float* w, const float* lo, int64_t count, cudaStream_t st);   // SFB200_CHECK_LO=1: trap if stale
+bool tf32_lo_check_enabled();
 bool pdl_enabled();   // SFB200_PDL=0 turns programmatic dependent launch off (api.cu)
 
 // Programmatic dependent launch: kernels launched through launch_pdl() may be made resident while their predecessor on
@@ -104,6 +111,13 @@ __device__ __forceinline__ float act_bwd_from_out(float h, int act) {
         case SFB200_ACT_TANH: return 1.f - h * h;
         default: return 1.f;
     }
+}
+
+// the 3xTF32 operand split: hi = w with the 13 low mantissa bits cleared (what the tensor core reads of w), lo = the
+// tf32-representable part of the remainder
+__device__ __forceinline__ uint32_t tf32_lo_bits(uint32_t w) {
+    const uint32_t h = w & 0xffffe000u;
+    return __float_as_uint(__uint_as_float(w) - __uint_as_float(h)) & 0xffffe000u;
 }
 
 __device__ __forceinline__ float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }

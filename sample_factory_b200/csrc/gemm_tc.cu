@@ -637,11 +637,14 @@ struct TaSmem {
     static constexpr int TOTAL_HEADS = TOTAL + HEADW_FLOATS * 4;
 };
 
-template <bool A_MN, bool B_MN, bool SPLIT3, bool HEADS>
+// BLO: the B operand is a registered weight buffer whose low tf32 halves sit in a second array (tmap_b_lo): TMA fills the
+// B_hi (raw weights; the tensor core ignores the 13 low mantissa bits) and B_lo tiles directly and the operand warps do
+// no shared-memory work for B at all.
+template <bool A_MN, bool B_MN, bool SPLIT3, bool HEADS, bool BLO>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_ta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                  float* __restrict__ C, int64_t ldc, int64_t M, int N, int K, int k_chunk, int splits, TcEpilogue epi,
-                  int raw_hi) {
+                  const __grid_constant__ CUtensorMap tmap_b_lo, float* __restrict__ C, int64_t ldc, int64_t M, int N,
+                  int K, int k_chunk, int splits, TcEpilogue epi, int raw_hi) {
     constexpr int BN = 128, STAGES = TA_STAGES;
     using S = TaSmem<STAGES>;
     extern __shared__ uint8_t smem_raw[];
@@ -663,6 +666,7 @@ gemm_tc_ta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
+        if (BLO) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b_lo) : "memory");
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&conv[s], 128);
@@ -692,7 +696,7 @@ gemm_tc_ta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                     const int s = it % STAGES;
                     mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
                     uint8_t* sb = smem + s * S::STAGE_BYTES;
-                    mbar_expect_tx(&full[s], S::B_BYTES + S::A_BYTES);
+                    mbar_expect_tx(&full[s], (BLO ? 2 : 1) * S::B_BYTES + S::A_BYTES);
                     const int k0 = tc.k_begin + kb * TBK;
                     if (A_MN) {
                         for (int j = 0; j < TBM / 32; ++j)
@@ -702,8 +706,12 @@ gemm_tc_ta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                     }
                     if (B_MN) {
                         for (int j = 0; j < BN / 32; ++j) tma_load_2d(sb + j * 4096, &tmap_b, &full[s], tc.n0 + 32 * j, k0);
+                        if (BLO)
+                            for (int j = 0; j < BN / 32; ++j)
+                                tma_load_2d(sb + S::B_BYTES + j * 4096, &tmap_b_lo, &full[s], tc.n0 + 32 * j, k0);
                     } else {
                         tma_load_2d(sb, &tmap_b, &full[s], k0, tc.n0);
+                        if (BLO) tma_load_2d(sb + S::B_BYTES, &tmap_b_lo, &full[s], k0, tc.n0);
                     }
                 }
             }
@@ -720,6 +728,7 @@ gemm_tc_ta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             tc_fence_after();
             for (int kb = 0; kb < tc.num_kb; ++kb, ++it) {
                 const int s = it % STAGES;
+                if (BLO) mbar_wait(&full[s], (it / STAGES) & 1);   // B tiles come straight from TMA: observe their barrier here too
                 mbar_wait(&conv[s], (it / STAGES) & 1);
                 tc_fence_after();
                 if (lane == 0) {
@@ -790,8 +799,8 @@ gemm_tc_ta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                     }
                 }
                 tmem_st_32x32b_x32(lane_addr + (uint32_t)s * 64u, hi);
-                if (SPLIT3) {
-                    tmem_st_32x32b_x32(lane_addr + (uint32_t)s * 64u + 32u, lo);
+                if (SPLIT3) tmem_st_32x32b_x32(lane_addr + (uint32_t)s * 64u + 32u, lo);
+                if (SPLIT3 && !BLO) {
                     uint4* h4 = reinterpret_cast<uint4*>(sb);
                     uint4* l4 = reinterpret_cast<uint4*>(sb + S::B_BYTES);
 #pragma unroll 4
@@ -808,7 +817,7 @@ gemm_tc_ta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                     }
                 }
                 tmem_st_wait();
-                fence_proxy_async_smem();
+                if (!BLO) fence_proxy_async_smem();   // (BLO: these warps wrote nothing to shared memory)
                 tc_fence_before();
                 mbar_arrive(&conv[s]);
             }
@@ -934,11 +943,11 @@ static bool raw_hi_enabled() {
     return v == 1;
 }
 
-template <bool A_MN, bool B_MN, bool SPLIT3, bool HEADS = false>
+template <bool A_MN, bool B_MN, bool SPLIT3, bool HEADS = false, bool BLO = false>
 static int launch_tc_ta(const CUtensorMap& ta, const CUtensorMap& tb, float* C, int64_t ldc, int64_t M, int N, int K,
-                        int k_chunk, int splits, const TcEpilogue& epi, cudaStream_t st) {
+                        int k_chunk, int splits, const TcEpilogue& epi, cudaStream_t st, const CUtensorMap* tb_lo = nullptr) {
     using S = TaSmem<TA_STAGES>;
-    auto kern = gemm_tc_ta_kernel<A_MN, B_MN, SPLIT3, HEADS>;
+    auto kern = gemm_tc_ta_kernel<A_MN, B_MN, SPLIT3, HEADS, BLO>;
     constexpr int SMEM = HEADS ? S::TOTAL_HEADS : S::TOTAL;
     static bool attr_set = false;
     if (!attr_set) {
@@ -947,10 +956,20 @@ static int launch_tc_ta(const CUtensorMap& ta, const CUtensorMap& tb, float* C, 
     }
     const int64_t tiles = ceil_div(N, 128) * ceil_div(M, TBM) * splits;
     const int64_t grid = tiles < sm_count() ? tiles : sm_count();
-    SFB_CUDA_OK(launch_pdl(kern, dim3((unsigned)grid), dim3(TC_THREADS), (size_t)SMEM, st, ta, tb, C, ldc, M, N, K, k_chunk,
-                           splits, epi, raw_hi_enabled() ? 1 : 0));
+    SFB_CUDA_OK(launch_pdl(kern, dim3((unsigned)grid), dim3(TC_THREADS), (size_t)SMEM, st, ta, tb, tb_lo ? *tb_lo : tb, C, ldc, M,
+                           N, K, k_chunk, splits, epi, raw_hi_enabled() ? 1 : 0));
     SFB_LAUNCH_OK();
     return 0;
+}
+
+// SFB200_TC_B_LO=0 ignores registered tf32-lo buffers (A/B comparison)
+static bool blo_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("SFB200_TC_B_LO");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
 }
 
 // SFB200_TC_A_IN_TMEM=0 selects the shared-memory-A kernel for every shape (A/B comparison, debugging)
@@ -990,6 +1009,27 @@ static int gemm_tc(bool a_mn, const float* A, int64_t lda, bool b_mn, const floa
     if (epi.head_part && !(BN == 128 && ta_enabled() && !a_mn && !b_mn && splits == 1)) return SFB_TC_UNSUPPORTED;
     if (BN == 128 && ta_enabled() && (b_mn || !a_mn)) {
         // A operand from TMEM (gemm_tc_ta_kernel); (A MN-major, B K-major) is not instantiated (no caller)
+        // weight operand with a registered tf32-lo twin (forward layers and dX: B is the weight matrix)
+        const int64_t b_extent = b_mn ? (int64_t)(K - 1) * ldb + N : (int64_t)(N - 1) * ldb + K;
+        const float* B_lo = (split3 && !a_mn && raw_hi_enabled() && blo_enabled()) ? tf32_lo_lookup(B, b_extent) : nullptr;
+        if (B_lo) {
+            CUtensorMap tb_lo;
+            bool ok_lo;
+            if (b_mn) ok_lo = make_tmap(&tb_lo, B_lo, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 32, TBK, true);
+            else ok_lo = make_tmap(&tb_lo, B_lo, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, TBK, 128, false);
+            if (!ok_lo) return SFB_TC_UNSUPPORTED;
+            if (tf32_lo_check_enabled()) {
+                int rcc = tf32_lo_check(B, B_lo, b_extent, st);
+                if (rcc) return rcc;
+            }
+            int rc_lo;
+            if (epi.head_part) rc_lo = launch_tc_ta<false, false, true, true, true>(ta, tb, out, ld_out, M, N, K, k_chunk, splits, epi, st, &tb_lo);
+            else if (!b_mn) rc_lo = launch_tc_ta<false, false, true, false, true>(ta, tb, out, ld_out, M, N, K, k_chunk, splits, epi, st, &tb_lo);
+            else rc_lo = launch_tc_ta<false, true, true, false, true>(ta, tb, out, ld_out, M, N, K, k_chunk, splits, epi, st, &tb_lo);
+            if (rc_lo) return rc_lo;
+            if (splits > 1) return splitk_reduce(ws, splits, M, N, C, ldc, st);
+            return 0;
+        }
 #define SFB_TA(AM, BM_)                                                                                                \
     (split3 ? launch_tc_ta<AM, BM_, true>(ta, tb, out, ld_out, M, N, K, k_chunk, splits, epi, st)                     \
             : launch_tc_ta<AM, BM_, false>(ta, tb, out, ld_out, M, N, K, k_chunk, splits, epi, st))

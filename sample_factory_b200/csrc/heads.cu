@@ -17,13 +17,70 @@ struct HeadsOut {
     int32_t* env_actions;
     float* log_prob; int64_t log_prob_stride;
     float* pv_out; int64_t pv_stride;
+    // continuous (diagonal Gaussian) action space: dist 0 = categorical, 1 = Gaussian with state-dependent log-stddev
+    // (the linear layer has 2*act_dim rows), 2 = Gaussian with one learned log-stddev vector (act_dim rows)
+    int dist; int act_dim; const float* learned_log_std; float tanh_scale; float* env_actions_f32;
 };
+
+constexpr float kStddevMin = 1e-4f, kStddevMax = 1e4f;   // action_distributions.py:291-292
+constexpr float kHalfLog2Pi = 0.91893853320467274178f;   // log(sqrt(2 pi))
+
+// ContinuousActionDistribution (action_distributions.py:290-323) on the lanes: lane j in 1..act_dim owns action
+// dimension j-1.  Stored `logits` are the distribution parameters [means | log_std] (2*act_dim floats) exactly as the
+// reference's action_parameterization returns them (tanh-scaled means and the repeated learned vector when
+// adaptive_stddev=False, action_parameterization.py:64-78).
+__device__ __forceinline__ void gaussian_row_tail(float mine, int lane, int64_t row, const HeadsOut& out,
+                                                  const float* __restrict__ noise, uint64_t seed, uint64_t offset,
+                                                  float pv) {
+    const int Ad = out.act_dim;
+    const bool is_dim = lane >= 1 && lane <= Ad;
+    float mean = mine, log_std;
+    if (out.dist == 1) {
+        const int src = lane + Ad;
+        log_std = __shfl_sync(0xffffffffu, mine, src < 32 ? src : 31);
+    } else {
+        log_std = is_dim ? out.learned_log_std[lane - 1] : 0.f;
+        if (out.tanh_scale > 0.f) mean = tanhf(__fdiv_rn(mine, out.tanh_scale)) * out.tanh_scale;
+    }
+    if (out.logits && is_dim) {
+        out.logits[row * out.logits_stride + (lane - 1)] = mean;
+        out.logits[row * out.logits_stride + Ad + (lane - 1)] = log_std;
+    }
+    if (out.actions_f32 == nullptr) return;   // values / distribution parameters only (warp-uniform)
+    const float sd = clampf(expf(log_std), kStddevMin, kStddevMax);
+    float eps = 0.f;
+    if (is_dim) {
+        if (noise) eps = noise[row * Ad + (lane - 1)];
+        else {
+            curandStatePhilox4_32_10_t st;
+            curand_init(seed, (unsigned long long)(row * Ad + (lane - 1)), offset, &st);
+            eps = curand_normal(&st);
+        }
+    }
+    // Normal.sample(): eps * std + mean, product and sum rounded separately (SURVEY App.C)
+    const float a = __fadd_rn(__fmul_rn(eps, sd), mean);
+    const float d = a - mean;
+    const float lpj = is_dim ? (-(d * d) / (2.f * (sd * sd)) - logf(sd) - kHalfLog2Pi) : 0.f;   // normal.py:84-94
+    const float lp = warp_sum(lpj);                                                              // Independent(.., 1)
+    if (is_dim) {
+        out.actions_f32[row * out.actions_stride + (lane - 1)] = a;
+        if (out.env_actions_f32) out.env_actions_f32[row * Ad + (lane - 1)] = a;
+    }
+    if (lane == 0) {
+        if (out.log_prob) out.log_prob[row * out.log_prob_stride] = lp;
+        if (out.pv_out) out.pv_out[row * out.pv_stride] = pv;
+    }
+}
 
 // Lane a of the warp holds output a of one row (0 = value, 1..A = logits, bias included): store them and, in sampling
 // mode, run CategoricalActionDistribution (action_distributions.py:110-148) on the lanes.
 __device__ __forceinline__ void heads_row_tail(float mine, int lane, int A, int64_t row, const HeadsOut& out,
                                                const float* __restrict__ noise, uint64_t seed, uint64_t offset, float pv) {
     if (lane == 0) out.values[row * out.values_stride] = mine;
+    if (out.dist != 0) {
+        gaussian_row_tail(mine, lane, row, out, noise, seed, offset, pv);
+        return;
+    }
     const bool is_logit = lane >= 1 && lane <= A;
     if (out.logits && is_logit) out.logits[row * out.logits_stride + (lane - 1)] = mine;
     if (out.actions_f32 == nullptr) return;   // values / logits only (warp-uniform)
@@ -94,12 +151,9 @@ __global__ void __launch_bounds__(256) heads_from_partials_kernel(
 template <int AP, int RPW, bool VEC>
 __global__ void __launch_bounds__(256) heads_forward_kernel(
     const float* __restrict__ h, int64_t ldh, int64_t rows, int H, int A, const float* __restrict__ Wv,
-    const float* __restrict__ bv, const float* __restrict__ Wa, const float* __restrict__ ba, float* __restrict__ values,
-    int64_t values_stride, float* __restrict__ logits, int64_t logits_stride, const float* __restrict__ noise,
-    uint64_t seed, uint64_t offset_host, const int64_t* __restrict__ offset_dev, float* __restrict__ actions_f32,
-    int64_t actions_stride,
-    int32_t* __restrict__ env_actions, float* __restrict__ log_prob, int64_t log_prob_stride,
-    const float* __restrict__ pv_scalar, float* __restrict__ pv_out, int64_t pv_stride) {
+    const float* __restrict__ bv, const float* __restrict__ Wa, const float* __restrict__ ba, const HeadsOut out,
+    const float* __restrict__ noise, uint64_t seed, uint64_t offset_host, const int64_t* __restrict__ offset_dev,
+    const float* __restrict__ pv_scalar) {
     extern __shared__ float wcat[];   // [(A+1)][H]
     pdl_wait();
     pdl_trigger();
@@ -116,8 +170,6 @@ __global__ void __launch_bounds__(256) heads_forward_kernel(
     const float pv = pv_scalar ? *pv_scalar : 0.f;
     const uint64_t offset = offset_host + (offset_dev ? (uint64_t)*offset_dev : 0ull);
     const float my_bias = (lane == 0) ? bv[0] : (lane <= A ? ba[lane - 1] : 0.f);
-    const HeadsOut out{values, values_stride, logits, logits_stride, actions_f32, actions_stride, env_actions,
-                       log_prob, log_prob_stride, pv_out, pv_stride};
 
     for (int64_t r0 = warp * RPW; r0 < rows; r0 += nwarps * RPW) {
         float acc[RPW][AP];
@@ -368,46 +420,32 @@ __global__ void heads_backward_reduce_kernel(const float* __restrict__ part, int
 
 template <int AP, int RPW, bool VEC>
 static int launch_heads_forward(const float* h, int64_t ldh, int64_t rows, int H, int A, const float* Wv,
-                                const float* bv, const float* Wa, const float* ba, float* values, int64_t values_stride,
-                                float* logits, int64_t logits_stride, const float* noise, uint64_t seed, uint64_t offset,
-                                const int64_t* offset_dev, float* actions_f32, int64_t actions_stride, int32_t* env_actions, float* log_prob,
-                                int64_t log_prob_stride, const float* pv_scalar, float* pv_out, int64_t pv_stride,
-                                cudaStream_t st) {
+                                const float* bv, const float* Wa, const float* ba, const HeadsOut& out,
+                                const float* noise, uint64_t seed, uint64_t offset, const int64_t* offset_dev,
+                                const float* pv_scalar, cudaStream_t st) {
     const size_t smem = VEC ? 0 : (size_t)(A + 1) * H * sizeof(float);
     auto kern = heads_forward_kernel<AP, RPW, VEC>;
     if (smem > 48 * 1024) SFB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int64_t blocks = ceil_div(ceil_div(rows, RPW), 8);
     const int64_t cap = (int64_t)sm_count() * 4;
     if (blocks > cap) blocks = cap;
-    SFB_CUDA_OK(launch_pdl(kern, dim3((unsigned)blocks), dim3(256), smem, st, h, ldh, rows, H, A, Wv, bv, Wa, ba, values,
-                           values_stride, logits, logits_stride, noise, seed, offset, offset_dev, actions_f32,
-                           actions_stride, env_actions, log_prob, log_prob_stride, pv_scalar, pv_out, pv_stride));
+    SFB_CUDA_OK(launch_pdl(kern, dim3((unsigned)blocks), dim3(256), smem, st, h, ldh, rows, H, A, Wv, bv, Wa, ba, out, noise,
+                           seed, offset, offset_dev, pv_scalar));
     SFB_LAUNCH_OK();
     return 0;
 }
 
-}  // namespace sfb
-
-using namespace sfb;
-
-extern "C" {
-
-int sfb200_heads_forward(const float* h, int64_t ldh, int64_t rows, int H, int A, const float* Wv, const float* bv,
-                         const float* Wa, const float* ba, float* values, int64_t values_stride, float* logits,
-                         int64_t logits_stride, const float* noise, uint64_t philox_seed, uint64_t philox_offset,
-                         const int64_t* philox_offset_dev, float* actions_f32, int64_t actions_stride, int32_t* env_actions_i32, float* log_prob,
-                         int64_t log_prob_stride, const float* policy_version_scalar, float* policy_version_out,
-                         int64_t pv_stride, void* stream) {
-    SFB_CHECK_ARG(h && Wv && bv && Wa && ba && values && rows >= 0 && H > 0, "heads_forward: bad arguments");
-    SFB_CHECK_ARG(A >= 1 && A <= 31, "heads_forward: supports 1 <= A <= 31 discrete actions, got %d", A);
+// A = rows of distribution_linear (n for Discrete(n); 2*act_dim or act_dim for a Box action space)
+static int heads_forward_impl(const float* h, int64_t ldh, int64_t rows, int H, int A, const float* Wv, const float* bv,
+                              const float* Wa, const float* ba, const HeadsOut& out, const float* noise, uint64_t seed,
+                              uint64_t offset, const int64_t* offset_dev, const float* pv_scalar, cudaStream_t st) {
+    SFB_CHECK_ARG(h && Wv && bv && Wa && ba && out.values && rows >= 0 && H > 0, "heads_forward: bad arguments");
+    SFB_CHECK_ARG(A >= 1 && A <= 31, "heads_forward: supports 1 <= distribution_linear rows <= 31, got %d", A);
     SFB_CHECK_ARG((size_t)(A + 1) * H * sizeof(float) <= 200 * 1024, "heads_forward: (A+1)*H too large for smem");
     if (rows == 0) return 0;
-    cudaStream_t st = (cudaStream_t)stream;
 #define SFB_HF(AP, RPW, VEC)                                                                                          \
-    return launch_heads_forward<AP, RPW, VEC>(h, ldh, rows, H, A, Wv, bv, Wa, ba, values, values_stride, logits,       \
-                                              logits_stride, noise, philox_seed, philox_offset, philox_offset_dev,     \
-                                              actions_f32, actions_stride, env_actions_i32, log_prob, log_prob_stride, \
-                                              policy_version_scalar, policy_version_out, pv_stride, st)
+    return launch_heads_forward<AP, RPW, VEC>(h, ldh, rows, H, A, Wv, bv, Wa, ba, out, noise, seed, offset, offset_dev, \
+                                              pv_scalar, st)
     auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
     const bool vec = (H % 4 == 0) && (ldh % 4 == 0) && al16(h) && al16(Wv) && al16(Wa);
     if (A + 1 <= 9) {
@@ -424,6 +462,52 @@ int sfb200_heads_forward(const float* h, int64_t ldh, int64_t rows, int H, int A
 #undef SFB_HF
 }
 
+static int heads_from_partials_impl(const float* head_partials, int P, int64_t rows, int A, const float* bv,
+                                    const float* ba, const HeadsOut& out, const float* noise, uint64_t seed,
+                                    uint64_t offset, const int64_t* offset_dev, const float* pv_scalar, cudaStream_t st) {
+    SFB_CHECK_ARG(head_partials && bv && ba && out.values && rows >= 0 && P >= 1, "heads_from_partials: bad arguments");
+    SFB_CHECK_ARG(A >= 1 && A + 1 <= kHeadPartPad, "heads_from_partials: supports 1 <= A <= %d, got %d", kHeadPartPad - 1, A);
+    if (rows == 0) return 0;
+    int64_t blocks = ceil_div(rows, 8);
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    SFB_CUDA_OK(launch_pdl(heads_from_partials_kernel, dim3((unsigned)blocks), dim3(256), 0, st, head_partials, P, rows, A, bv,
+                           ba, out, noise, seed, offset, offset_dev, pv_scalar));
+    SFB_LAUNCH_OK();
+    return 0;
+}
+
+static int make_gaussian_out(HeadsOut& out, int act_dim, int adaptive_stddev, const float* learned_log_std,
+                             float tanh_scale, float* values, int64_t values_stride, float* params,
+                             int64_t params_stride, float* actions_f32, int64_t actions_stride, float* env_actions_f32,
+                             float* log_prob, int64_t log_prob_stride, float* pv_out, int64_t pv_stride) {
+    SFB_CHECK_ARG(act_dim >= 1 && (adaptive_stddev ? 2 * act_dim : act_dim) <= 31,
+                  "heads (continuous): act_dim %d needs more than 31 distribution_linear rows", act_dim);
+    SFB_CHECK_ARG(adaptive_stddev || learned_log_std, "heads (continuous): learned_log_std is required when adaptive_stddev=0");
+    out = HeadsOut{values, values_stride, params, params_stride, actions_f32, actions_stride, nullptr, log_prob,
+                   log_prob_stride, pv_out, pv_stride, adaptive_stddev ? 1 : 2, act_dim, learned_log_std, tanh_scale,
+                   env_actions_f32};
+    return 0;
+}
+
+}  // namespace sfb
+
+using namespace sfb;
+
+extern "C" {
+
+int sfb200_heads_forward(const float* h, int64_t ldh, int64_t rows, int H, int A, const float* Wv, const float* bv,
+                         const float* Wa, const float* ba, float* values, int64_t values_stride, float* logits,
+                         int64_t logits_stride, const float* noise, uint64_t philox_seed, uint64_t philox_offset,
+                         const int64_t* philox_offset_dev, float* actions_f32, int64_t actions_stride, int32_t* env_actions_i32, float* log_prob,
+                         int64_t log_prob_stride, const float* policy_version_scalar, float* policy_version_out,
+                         int64_t pv_stride, void* stream) {
+    const HeadsOut out{values, values_stride, logits, logits_stride, actions_f32, actions_stride, env_actions_i32,
+                       log_prob, log_prob_stride, policy_version_out, pv_stride, 0, 0, nullptr, 0.f, nullptr};
+    return heads_forward_impl(h, ldh, rows, H, A, Wv, bv, Wa, ba, out, noise, philox_seed, philox_offset,
+                              philox_offset_dev, policy_version_scalar, (cudaStream_t)stream);
+}
+
 int sfb200_heads_from_partials(const float* head_partials, int P, int64_t rows, int A, const float* bv, const float* ba,
                                float* values, int64_t values_stride, float* logits, int64_t logits_stride,
                                const float* noise, uint64_t philox_seed, uint64_t philox_offset,
@@ -431,19 +515,46 @@ int sfb200_heads_from_partials(const float* head_partials, int P, int64_t rows, 
                                int32_t* env_actions_i32, float* log_prob, int64_t log_prob_stride,
                                const float* policy_version_scalar, float* policy_version_out, int64_t pv_stride,
                                void* stream) {
-    SFB_CHECK_ARG(head_partials && bv && ba && values && rows >= 0 && P >= 1, "heads_from_partials: bad arguments");
-    SFB_CHECK_ARG(A >= 1 && A + 1 <= kHeadPartPad, "heads_from_partials: supports 1 <= A <= %d, got %d", kHeadPartPad - 1, A);
-    if (rows == 0) return 0;
     const HeadsOut out{values, values_stride, logits, logits_stride, actions_f32, actions_stride, env_actions_i32,
-                       log_prob, log_prob_stride, policy_version_out, pv_stride};
-    int64_t blocks = ceil_div(rows, 8);
-    const int64_t cap = (int64_t)sm_count() * 8;
-    if (blocks > cap) blocks = cap;
-    SFB_CUDA_OK(launch_pdl(heads_from_partials_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream,
-                           head_partials, P, rows, A, bv, ba, out, noise, philox_seed, philox_offset, philox_offset_dev,
-                           policy_version_scalar));
-    SFB_LAUNCH_OK();
-    return 0;
+                       log_prob, log_prob_stride, policy_version_out, pv_stride, 0, 0, nullptr, 0.f, nullptr};
+    return heads_from_partials_impl(head_partials, P, rows, A, bv, ba, out, noise, philox_seed, philox_offset,
+                                    philox_offset_dev, policy_version_scalar, (cudaStream_t)stream);
+}
+
+int sfb200_heads_forward_continuous(const float* h, int64_t ldh, int64_t rows, int H, int act_dim, int adaptive_stddev,
+                                    const float* Wv, const float* bv, const float* Wa, const float* ba,
+                                    const float* learned_log_std, float tanh_scale, float* values,
+                                    int64_t values_stride, float* params, int64_t params_stride, const float* noise,
+                                    uint64_t philox_seed, uint64_t philox_offset, const int64_t* philox_offset_dev,
+                                    float* actions_f32, int64_t actions_stride, float* env_actions_f32, float* log_prob,
+                                    int64_t log_prob_stride, const float* policy_version_scalar,
+                                    float* policy_version_out, int64_t pv_stride, void* stream) {
+    HeadsOut out;
+    if (int rc = make_gaussian_out(out, act_dim, adaptive_stddev, learned_log_std, tanh_scale, values, values_stride, params,
+                                   params_stride, actions_f32, actions_stride, env_actions_f32, log_prob, log_prob_stride,
+                                   policy_version_out, pv_stride))
+        return rc;
+    return heads_forward_impl(h, ldh, rows, H, adaptive_stddev ? 2 * act_dim : act_dim, Wv, bv, Wa, ba, out, noise,
+                              philox_seed, philox_offset, philox_offset_dev, policy_version_scalar, (cudaStream_t)stream);
+}
+
+int sfb200_heads_from_partials_continuous(const float* head_partials, int P, int64_t rows, int act_dim,
+                                          int adaptive_stddev, const float* bv, const float* ba,
+                                          const float* learned_log_std, float tanh_scale, float* values,
+                                          int64_t values_stride, float* params, int64_t params_stride,
+                                          const float* noise, uint64_t philox_seed, uint64_t philox_offset,
+                                          const int64_t* philox_offset_dev, float* actions_f32, int64_t actions_stride,
+                                          float* env_actions_f32, float* log_prob, int64_t log_prob_stride,
+                                          const float* policy_version_scalar, float* policy_version_out,
+                                          int64_t pv_stride, void* stream) {
+    HeadsOut out;
+    if (int rc = make_gaussian_out(out, act_dim, adaptive_stddev, learned_log_std, tanh_scale, values, values_stride, params,
+                                   params_stride, actions_f32, actions_stride, env_actions_f32, log_prob, log_prob_stride,
+                                   policy_version_out, pv_stride))
+        return rc;
+    return heads_from_partials_impl(head_partials, P, rows, adaptive_stddev ? 2 * act_dim : act_dim, bv, ba, out, noise,
+                                    philox_seed, philox_offset, philox_offset_dev, policy_version_scalar,
+                                    (cudaStream_t)stream);
 }
 
 int64_t sfb200_heads_backward_workspace_bytes(int H, int A) {

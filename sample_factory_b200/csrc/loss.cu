@@ -6,6 +6,8 @@
 namespace sfb {
 
 constexpr int kLossMaxBlocks = 1024;
+constexpr float kStdMin = 1e-4f, kStdMax = 1e4f;          // action_distributions.py:291-292
+constexpr float kHalfLog2PiL = 0.91893853320467274178f;   // log(sqrt(2 pi))
 constexpr int kNumPart = 12;
 // partial-sum slots
 enum { P_PL = 0, P_VL, P_ENT, P_KL, P_KLMAX, P_RDEV, P_RMIN, P_RMAX, P_CLIPPED, P_VSUM, P_COUNT, P_UNUSED };
@@ -142,6 +144,61 @@ __global__ void adv_stats_from_partials_kernel(const double* __restrict__ dp, do
 }
 
 // ---- the loss ---------------------------------------------------------------------------------------------------------
+// distribution-independent pieces shared by the categorical and the Gaussian kernels
+struct PpoAcc {
+    double s_pl = 0, s_vl = 0, s_ent = 0, s_kl = 0, s_rdev = 0, s_clip = 0, s_v = 0, s_cnt = 0;
+    double m_kl = -INFINITY, m_rmin = -INFINITY /* holds -min */, m_rmax = -INFINITY;
+};
+
+// _policy_loss :431-439 given log_prob of the stored action under the new distribution.  Returns d(loss)/d(log_prob).
+__device__ __forceinline__ float ppo_policy_terms(float lp, float lp_old, float adv, float adv_mean, float adv_std,
+                                                  float clip_lo, float clip_hi, float w, PpoAcc& acc) {
+    const float ratio_raw = expf(lp - lp_old);                          // :589
+    const float ratio = clampf(ratio_raw, 0.05f, 20.0f);                // :592
+    const float advn = __fdiv_rn(__fsub_rn(adv, adv_mean), adv_std);    // :647
+    const float rc = clampf(ratio, clip_lo, clip_hi);
+    const float s1 = ratio * advn, s2 = rc * advn;
+    acc.s_pl = fminf(s1, s2);
+    const bool in_window = ratio >= clip_lo && ratio <= clip_hi;
+    const float g_ratio = (in_window || s1 < s2) ? -advn : 0.f;         // d(-min)/d ratio (ties split evenly)
+    const float dratio_dlp = (ratio_raw >= 0.05f && ratio_raw <= 20.0f) ? ratio_raw : 0.f;
+    // summaries :843-923
+    acc.s_rdev = fabsf(1.f - ratio);
+    acc.m_rmin = -(double)ratio;
+    acc.m_rmax = ratio;
+    acc.s_clip = (ratio < clip_lo ? 1.0 : 0.0) + (ratio > clip_hi ? 1.0 : 0.0);
+    return w * g_ratio * dratio_dlp;
+}
+
+// _value_loss :441-459.  Returns d(loss)/d(value).
+__device__ __forceinline__ float ppo_value_terms(float v, float vo, float R, float clip_value, float w, float c_val,
+                                                 PpoAcc& acc) {
+    const float diff = v - vo;
+    const float vc = vo + clampf(diff, -clip_value, clip_value);
+    const float l1 = (v - R) * (v - R), l2 = (vc - R) * (vc - R);
+    acc.s_vl = fmaxf(l1, l2);
+    const bool inside = diff >= -clip_value && diff <= clip_value;
+    const float g1 = 2.f * (v - R), g2 = inside ? 2.f * (vc - R) : 0.f;
+    const float gv = (l1 > l2) ? g1 : ((l2 > l1) ? g2 : 0.5f * (g1 + g2));
+    return w * c_val * gv;
+}
+
+__device__ __forceinline__ void ppo_store_partials(const PpoAcc& a, double* __restrict__ part, double* sm) {
+    double* my = part + (int64_t)blockIdx.x * kNumPart;
+    double t;
+    t = block_sum(a.s_pl, sm);   if (threadIdx.x == 0) my[P_PL] = t;
+    t = block_sum(a.s_vl, sm);   if (threadIdx.x == 0) my[P_VL] = t;
+    t = block_sum(a.s_ent, sm);  if (threadIdx.x == 0) my[P_ENT] = t;
+    t = block_sum(a.s_kl, sm);   if (threadIdx.x == 0) my[P_KL] = t;
+    t = block_max(a.m_kl, sm);   if (threadIdx.x == 0) my[P_KLMAX] = t;
+    t = block_sum(a.s_rdev, sm); if (threadIdx.x == 0) my[P_RDEV] = t;
+    t = block_max(a.m_rmin, sm); if (threadIdx.x == 0) my[P_RMIN] = t;
+    t = block_max(a.m_rmax, sm); if (threadIdx.x == 0) my[P_RMAX] = t;
+    t = block_sum(a.s_clip, sm); if (threadIdx.x == 0) my[P_CLIPPED] = t;
+    t = block_sum(a.s_v, sm);    if (threadIdx.x == 0) my[P_VSUM] = t;
+    t = block_sum(a.s_cnt, sm);  if (threadIdx.x == 0) my[P_COUNT] = t;
+}
+
 template <int AMAX>
 __global__ void __launch_bounds__(256) ppo_loss_kernel(
     const float* __restrict__ logits, const float* __restrict__ values, int A, const float* __restrict__ actions,
@@ -156,19 +213,17 @@ __global__ void __launch_bounds__(256) ppo_loss_kernel(
     const float adv_mean = (float)stats[SFB200_LS_ADV_MEAN];
     const float adv_std = fmaxf((float)stats[SFB200_LS_ADV_STD], 1e-7f);   // clamp_min :647
     const float w = n_valid > 0.0 ? (float)((double)grad_scale / n_valid) : 0.f;
-
-    double s_pl = 0, s_vl = 0, s_ent = 0, s_kl = 0, s_rdev = 0, s_clip = 0, s_v = 0, s_cnt = 0;
-    double m_kl = -INFINITY, m_rmin = -INFINITY /* holds -min */, m_rmax = -INFINITY;
+    PpoAcc acc;
 
     if (i < batch) {
         const float v = values[i];
-        s_v = v;
+        acc.s_v = v;
         float dl[AMAX];
 #pragma unroll
         for (int a = 0; a < AMAX; ++a) dl[a] = 0.f;
         float dv = 0.f;
         if (valids[i]) {
-            s_cnt = 1.0;
+            acc.s_cnt = 1.0;
             float l[AMAX], p[AMAX], logp[AMAX];
             load_row<AMAX>(logits + i * A, A, l);
             row_softmax<AMAX>(l, A, p, logp);
@@ -177,23 +232,13 @@ __global__ void __launch_bounds__(256) ppo_loss_kernel(
 #pragma unroll
             for (int a = 0; a < AMAX; ++a)
                 if (a < A && a == act) lp = logp[a];
-            const float ratio_raw = expf(lp - lp_old[i]);                       // :589
-            const float ratio = clampf(ratio_raw, 0.05f, 20.0f);                // :592
-            const float advn = __fdiv_rn(__fsub_rn(adv[i], adv_mean), adv_std); // :647
-            // _policy_loss :431-439
-            const float rc = clampf(ratio, clip_lo, clip_hi);
-            const float s1 = ratio * advn, s2 = rc * advn;
-            s_pl = fminf(s1, s2);
-            const bool in_window = ratio >= clip_lo && ratio <= clip_hi;
-            const float g_ratio = (in_window || s1 < s2) ? -advn : 0.f;         // d(-min)/d ratio (ties split evenly)
-            const float dratio_dlp = (ratio_raw >= 0.05f && ratio_raw <= 20.0f) ? ratio_raw : 0.f;
-            const float g_lp = w * g_ratio * dratio_dlp;
+            const float g_lp = ppo_policy_terms(lp, lp_old[i], adv[i], adv_mean, adv_std, clip_lo, clip_hi, w, acc);
             // entropy :150-152, :473-477
             float H = 0.f;
 #pragma unroll
             for (int a = 0; a < AMAX; ++a)
                 if (a < A) H -= logp[a] * p[a];
-            s_ent = H;
+            acc.s_ent = H;
             // KL(new || old) :154-158
             float kl = 0.f;
             float lq[AMAX];
@@ -204,8 +249,8 @@ __global__ void __launch_bounds__(256) ppo_loss_kernel(
 #pragma unroll
                 for (int a = 0; a < AMAX; ++a)
                     if (a < A) kl += p[a] * (logp[a] - lq[a]);
-                s_kl = kl;
-                m_kl = kl;
+                acc.s_kl = kl;
+                acc.m_kl = kl;
             }
             const float we = w * c_ent, wk = (logits_old ? w * c_kl : 0.f);
 #pragma unroll
@@ -217,38 +262,134 @@ __global__ void __launch_bounds__(256) ppo_loss_kernel(
                     dl[a] = g;
                 }
             }
-            // _value_loss :441-459
-            const float vo = v_old[i], R = targets[i];
-            const float diff = v - vo;
-            const float vc = vo + clampf(diff, -clip_value, clip_value);
-            const float l1 = (v - R) * (v - R), l2 = (vc - R) * (vc - R);
-            s_vl = fmaxf(l1, l2);
-            const bool inside = diff >= -clip_value && diff <= clip_value;
-            const float g1 = 2.f * (v - R), g2 = inside ? 2.f * (vc - R) : 0.f;
-            const float gv = (l1 > l2) ? g1 : ((l2 > l1) ? g2 : 0.5f * (g1 + g2));
-            dv = w * c_val * gv;
-            // summaries :843-923
-            s_rdev = fabsf(1.f - ratio);
-            m_rmin = -(double)ratio;
-            m_rmax = ratio;
-            s_clip = (ratio < clip_lo ? 1.0 : 0.0) + (ratio > clip_hi ? 1.0 : 0.0);
+            dv = ppo_value_terms(v, v_old[i], targets[i], clip_value, w, c_val, acc);
         }
         store_row<AMAX>(dlogits + i * A, A, dl);
         dvalues[i] = dv;
     }
-    double* my = part + (int64_t)blockIdx.x * kNumPart;
-    double t;
-    t = block_sum(s_pl, sm);   if (threadIdx.x == 0) my[P_PL] = t;
-    t = block_sum(s_vl, sm);   if (threadIdx.x == 0) my[P_VL] = t;
-    t = block_sum(s_ent, sm);  if (threadIdx.x == 0) my[P_ENT] = t;
-    t = block_sum(s_kl, sm);   if (threadIdx.x == 0) my[P_KL] = t;
-    t = block_max(m_kl, sm);   if (threadIdx.x == 0) my[P_KLMAX] = t;
-    t = block_sum(s_rdev, sm); if (threadIdx.x == 0) my[P_RDEV] = t;
-    t = block_max(m_rmin, sm); if (threadIdx.x == 0) my[P_RMIN] = t;
-    t = block_max(m_rmax, sm); if (threadIdx.x == 0) my[P_RMAX] = t;
-    t = block_sum(s_clip, sm); if (threadIdx.x == 0) my[P_CLIPPED] = t;
-    t = block_sum(s_v, sm);    if (threadIdx.x == 0) my[P_VSUM] = t;
-    t = block_sum(s_cnt, sm);  if (threadIdx.x == 0) my[P_COUNT] = t;
+    ppo_store_partials(acc, part, sm);
+}
+
+// Diagonal Gaussian policy (ContinuousActionDistribution, action_distributions.py:290-323; torch Normal / kl formulas):
+// params rows are [means | log_std] (2*Ad floats, the layout of `action_logits`), actions rows Ad floats.
+//   log_prob = sum_j -(a-m)^2 / (2 sd^2) - log sd - log sqrt(2 pi),  sd = clamp(exp(log_std), 1e-4, 1e4)
+//   entropy  = sum_j 0.5 + 0.5 log(2 pi) + log sd
+//   KL(new || old) = sum_j 0.5 (r + t - 1 - log r),  r = (sd/sd_old)^2,  t = ((m - m_old)/sd_old)^2
+// Gradients go to the distribution_linear outputs: adaptive stddev -> dlogits [B, 2*Ad] = [d means | d log_std];
+// learned stddev -> dlogits [B, Ad] = d means * (1 - (m/tanh_scale)^2) (tanh-squashed means) and dlogstd [B, Ad], which
+// the caller column-sums into the learned vector's gradient.  The clamp passes gradient inside [1e-4, 1e4] only.
+template <int AH>
+__device__ __forceinline__ void gauss_load(const float* __restrict__ row, int Ad, float (&m)[AH], float (&s)[AH]) {
+#pragma unroll
+    for (int j = 0; j < AH; ++j)
+        if (j < Ad) { m[j] = row[j]; s[j] = row[Ad + j]; }
+}
+
+template <int AH>
+__global__ void __launch_bounds__(256) ppo_loss_gauss_kernel(
+    const float* __restrict__ params, const float* __restrict__ values, int Ad, int adaptive, float tanh_scale,
+    const float* __restrict__ actions, const float* __restrict__ lp_old, const float* __restrict__ v_old,
+    const float* __restrict__ adv, const float* __restrict__ targets, const uint8_t* __restrict__ valids,
+    const float* __restrict__ params_old, int64_t batch, float clip_lo, float clip_hi, float clip_value, float c_ent,
+    float c_val, float c_kl, float grad_scale, float* __restrict__ dlogits, float* __restrict__ dlogstd,
+    float* __restrict__ dvalues, const double* __restrict__ stats, double* __restrict__ part) {
+    __shared__ double sm[8];
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const double n_valid = stats[SFB200_LS_NUM_VALID];
+    const float adv_mean = (float)stats[SFB200_LS_ADV_MEAN];
+    const float adv_std = fmaxf((float)stats[SFB200_LS_ADV_STD], 1e-7f);
+    const float w = n_valid > 0.0 ? (float)((double)grad_scale / n_valid) : 0.f;
+    PpoAcc acc;
+
+    if (i < batch) {
+        const float v = values[i];
+        acc.s_v = v;
+        float dm[AH], ds[AH];
+#pragma unroll
+        for (int j = 0; j < AH; ++j) { dm[j] = 0.f; ds[j] = 0.f; }
+        float dv = 0.f;
+        if (valids[i]) {
+            acc.s_cnt = 1.0;
+            float m[AH], s[AH], sd[AH], dlt[AH];
+            gauss_load<AH>(params + i * 2 * Ad, Ad, m, s);
+            float lp = 0.f, H = 0.f;
+#pragma unroll
+            for (int j = 0; j < AH; ++j) {
+                if (j < Ad) {
+                    sd[j] = clampf(expf(s[j]), kStdMin, kStdMax);
+                    dlt[j] = actions[i * Ad + j] - m[j];
+                    const float lsd = logf(sd[j]);
+                    lp += -(dlt[j] * dlt[j]) / (2.f * (sd[j] * sd[j])) - lsd - kHalfLog2PiL;
+                    H += 0.5f + kHalfLog2PiL + lsd;     // 0.5 + 0.5 log(2 pi) + log sd
+                }
+            }
+            const float g_lp = ppo_policy_terms(lp, lp_old[i], adv[i], adv_mean, adv_std, clip_lo, clip_hi, w, acc);
+            acc.s_ent = H;
+            const float we = w * c_ent, wk = (params_old ? w * c_kl : 0.f);
+            float mo[AH], so[AH];
+            float kl = 0.f;
+            if (params_old) gauss_load<AH>(params_old + i * 2 * Ad, Ad, mo, so);
+#pragma unroll
+            for (int j = 0; j < AH; ++j) {
+                if (j < Ad) {
+                    const float ex = expf(s[j]);
+                    const float in_range = (ex >= kStdMin && ex <= kStdMax) ? 1.f : 0.f;
+                    const float inv_var = 1.f / (sd[j] * sd[j]);
+                    float gm = g_lp * dlt[j] * inv_var;
+                    float gs = g_lp * (dlt[j] * dlt[j] * inv_var - 1.f) - we;
+                    if (params_old) {
+                        const float sdo = clampf(expf(so[j]), kStdMin, kStdMax);
+                        const float q = sd[j] / sdo, r = q * q;
+                        const float dq = (m[j] - mo[j]) / sdo;
+                        kl += 0.5f * (r + dq * dq - 1.f - logf(r));
+                        gm += wk * dq / sdo;
+                        gs += wk * (r - 1.f);
+                    }
+                    gs *= in_range;
+                    if (!adaptive && tanh_scale > 0.f) {
+                        const float tq = m[j] / tanh_scale;      // m = tanh(z/ts)*ts -> dm/dz = 1 - tanh^2
+                        gm *= (1.f - tq * tq);
+                    }
+                    dm[j] = gm;
+                    ds[j] = gs;
+                }
+            }
+            if (params_old) { acc.s_kl = kl; acc.m_kl = kl; }
+            dv = ppo_value_terms(v, v_old[i], targets[i], clip_value, w, c_val, acc);
+        }
+        float* drow = dlogits + i * (adaptive ? 2 * Ad : Ad);
+#pragma unroll
+        for (int j = 0; j < AH; ++j) {
+            if (j < Ad) {
+                drow[j] = dm[j];
+                if (adaptive) drow[Ad + j] = ds[j];
+                else dlogstd[i * Ad + j] = ds[j];
+            }
+        }
+        dvalues[i] = dv;
+    }
+    ppo_store_partials(acc, part, sm);
+}
+
+template <int AH>
+__global__ void __launch_bounds__(256) action_ratio_gauss_kernel(const float* __restrict__ params, int Ad,
+                                                                 const float* __restrict__ actions,
+                                                                 const float* __restrict__ lp_old, int64_t batch,
+                                                                 float* __restrict__ ratio) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= batch) return;
+    float m[AH], s[AH];
+    gauss_load<AH>(params + i * 2 * Ad, Ad, m, s);
+    float lp = 0.f;
+#pragma unroll
+    for (int j = 0; j < AH; ++j) {
+        if (j < Ad) {
+            const float sd = clampf(expf(s[j]), kStdMin, kStdMax);
+            const float d = actions[i * Ad + j] - m[j];
+            lp += -(d * d) / (2.f * (sd * sd)) - logf(sd) - kHalfLog2PiL;
+        }
+    }
+    ratio[i] = clampf(expf(lp - lp_old[i]), 0.05f, 20.0f);
 }
 
 __global__ void __launch_bounds__(256) ppo_loss_finalize_kernel(const double* __restrict__ part, int nblocks,
@@ -363,6 +504,51 @@ int sfb200_ppo_loss_fwd_bwd(const float* logits, const float* values, int A, con
     else if (A <= 16) SFB_PL(16);
     else SFB_PL(32);
 #undef SFB_PL
+    SFB_LAUNCH_OK();
+    ppo_loss_finalize_kernel<<<1, 256, 0, st>>>(part, (int)g, batch, exploration_coeff, value_coeff, kl_coeff, stats);
+    SFB_LAUNCH_OK();
+    return 0;
+}
+
+int sfb200_action_ratio_continuous(const float* params, int act_dim, const float* actions_f32, const float* log_prob_old,
+                                   int64_t batch, float* ratio, void* stream) {
+    SFB_CHECK_ARG(params && actions_f32 && log_prob_old && ratio && batch >= 0, "action_ratio_continuous: bad arguments");
+    SFB_CHECK_ARG(act_dim >= 1 && act_dim <= 32, "action_ratio_continuous: supports 1 <= act_dim <= 32");
+    if (batch == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned g = (unsigned)ceil_div(batch, 256);
+    if (act_dim <= 8) action_ratio_gauss_kernel<8><<<g, 256, 0, st>>>(params, act_dim, actions_f32, log_prob_old, batch, ratio);
+    else if (act_dim <= 16) action_ratio_gauss_kernel<16><<<g, 256, 0, st>>>(params, act_dim, actions_f32, log_prob_old, batch, ratio);
+    else action_ratio_gauss_kernel<32><<<g, 256, 0, st>>>(params, act_dim, actions_f32, log_prob_old, batch, ratio);
+    SFB_LAUNCH_OK();
+    return 0;
+}
+
+int sfb200_ppo_loss_fwd_bwd_continuous(const float* params, const float* values, int act_dim, int adaptive_stddev,
+                                       float tanh_scale, const float* actions_f32, const float* log_prob_old,
+                                       const float* values_old, const float* adv, const float* targets,
+                                       const uint8_t* valids, const float* params_old, int64_t batch, float clip_ratio,
+                                       float clip_value, float exploration_coeff, float value_coeff, float kl_coeff,
+                                       float grad_scale, float* dlogits, float* dlogstd, float* dvalues, double* stats,
+                                       void* workspace, void* stream) {
+    SFB_CHECK_ARG(params && values && actions_f32 && log_prob_old && values_old && adv && targets && valids && dlogits &&
+                      dvalues && stats && workspace && batch > 0, "ppo_loss_fwd_bwd_continuous: bad arguments");
+    SFB_CHECK_ARG(act_dim >= 1 && act_dim <= 32, "ppo_loss_fwd_bwd_continuous: supports 1 <= act_dim <= 32");
+    SFB_CHECK_ARG(adaptive_stddev || dlogstd, "ppo_loss_fwd_bwd_continuous: dlogstd is required when adaptive_stddev=0");
+    cudaStream_t st = (cudaStream_t)stream;
+    const float clip_hi = 1.0f + clip_ratio;
+    const float clip_lo = 1.0f / clip_hi;
+    const unsigned g = (unsigned)ceil_div(batch, 256);
+    double* part = (double*)workspace;
+#define SFB_PG(AHV)                                                                                                      \
+    ppo_loss_gauss_kernel<AHV><<<g, 256, 0, st>>>(params, values, act_dim, adaptive_stddev, tanh_scale, actions_f32,      \
+                                                  log_prob_old, values_old, adv, targets, valids, params_old, batch,      \
+                                                  clip_lo, clip_hi, clip_value, exploration_coeff, value_coeff, kl_coeff, \
+                                                  grad_scale, dlogits, dlogstd, dvalues, stats, part)
+    if (act_dim <= 8) SFB_PG(8);
+    else if (act_dim <= 16) SFB_PG(16);
+    else SFB_PG(32);
+#undef SFB_PG
     SFB_LAUNCH_OK();
     ppo_loss_finalize_kernel<<<1, 256, 0, st>>>(part, (int)g, batch, exploration_coeff, value_coeff, kl_coeff, stats);
     SFB_LAUNCH_OK();

@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(256) clip_adam_kernel(float* __restrict__ p, c
                                                         float eps, float max_norm, const double* __restrict__ part,
                                                         int nparts, const double* __restrict__ lr_num,
                                                         const double* __restrict__ lr_den,
-                                                        float* __restrict__ grad_norm_out) {
+                                                        float* __restrict__ grad_norm_out, float* __restrict__ p_lo) {
     __shared__ float s_coef;
     __shared__ float s_step;
     if (threadIdx.x < 32) {
@@ -59,7 +59,9 @@ __global__ void __launch_bounds__(256) clip_adam_kernel(float* __restrict__ p, c
         mi = mi + omb1 * (gi - mi);                        // exp_avg.lerp_(grad, 1-beta1)
         vi = vi * beta2 + (omb2 * gi) * gi;                // exp_avg_sq.mul_(b2).addcmul_(g, g, value=1-b2)
         const float denom = __fdiv_rn(__fsqrt_rn(vi), bc2_sqrt) + eps;
-        p[i] = p[i] - step_size * __fdiv_rn(mi, denom);    // param.addcdiv_(exp_avg, denom, value=-step_size)
+        const float pn = p[i] - step_size * __fdiv_rn(mi, denom);   // param.addcdiv_(exp_avg, denom, value=-step_size)
+        p[i] = pn;
+        if (p_lo) p_lo[i] = __uint_as_float(tf32_lo_bits(__float_as_uint(pn)));   // registered tf32 low half stays current
         m[i] = mi;
         v[i] = vi;
     }
@@ -89,7 +91,7 @@ int sfb200_clip_adam_step(float* p, float* g, float* m, float* v, int64_t n, int
     if (blocks > cap) blocks = cap;
     clip_adam_kernel<<<(unsigned)blocks, 256, 0, st>>>(p, g, m, v, n, lr, bc1, (float)sqrt(bc2), (float)(1.0 - beta1),
                                                        (float)beta2, (float)(1.0 - beta2), (float)eps, (float)max_grad_norm, part, (int)nb,
-                                                       lr_scale_num, lr_scale_den, grad_norm_out);
+                                                       lr_scale_num, lr_scale_den, grad_norm_out, tf32_lo_lookup_mut(p, n));
     SFB_LAUNCH_OK();
     return 0;
 }

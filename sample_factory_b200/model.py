@@ -124,6 +124,32 @@ class PolicyModel:
         self.ret_count = torch.ones(1, dtype=torch.float64, device=device)
 
         self._init_weights(seed, policy_init_gain)
+        self._register_lo()
+
+    # ---- tf32 low halves of the weights (3xTF32 engine: the weight operand's lo tile is loaded, not recomputed) -----
+    def _register_lo(self) -> None:
+        self.flat_lo = None
+        if self.flat.is_cuda:
+            from . import ops
+
+            self.flat_lo = torch.empty_like(self.flat)
+            ops.register_tf32_lo(self.flat, self.flat_lo)
+
+    def weights_changed(self) -> None:
+        """Call after writing `flat` / `params[...]` by anything other than the Adam kernel (which keeps lo current)."""
+        if self.flat_lo is not None:
+            from . import ops
+
+            ops.refresh_tf32_lo(self.flat)
+
+    def __del__(self):
+        try:
+            if getattr(self, "flat_lo", None) is not None:
+                from . import ops
+
+                ops.unregister_tf32_lo(self.flat)
+        except Exception:
+            pass
 
     def _init_weights(self, seed: int, gain: float) -> None:
         """ActorCritic.initialize_weights (actor_critic.py:73-96): bias 0, orthogonal(gain) on Linear weights."""
@@ -153,11 +179,16 @@ class PolicyModel:
         twin.grads = {}
         for k in ("obs_mean", "obs_var", "obs_count", "ret_mean", "ret_var", "ret_count"):
             setattr(twin, k, getattr(self, k).clone())
+        twin._register_lo()
         return twin
 
     def copy_weights_from(self, other: "PolicyModel") -> None:
         """Refresh this snapshot from the learner's model (three D2D copies on the current stream)."""
         self.flat.copy_(other.flat)
+        if self.flat_lo is not None and other.flat_lo is not None:
+            self.flat_lo.copy_(other.flat_lo)
+        else:
+            self.weights_changed()
         self.obs_mean.copy_(other.obs_mean)
         self.obs_var.copy_(other.obs_var)
 
@@ -241,6 +272,7 @@ class PolicyModel:
                 self.ret_count.copy_(v.to(self.device).view(1))
             elif strict:
                 raise KeyError(f"unexpected key in state_dict: {k}")
+        self.weights_changed()
         if strict:
             missing = known - set(sd.keys())
             if missing:

@@ -126,6 +126,22 @@ def heads_forward(h: Tensor, Wv: Tensor, bv: Tensor, Wa: Tensor, ba: Tensor, val
                None if policy_version_out is None else policy_version_out.data_ptr(), pv_stride, _stream())
 
 
+def register_tf32_lo(base: Tensor, lo: Tensor) -> None:
+    """Pair a flat weight buffer with its tf32 low-half twin (see include/sfb200.h) and fill the twin."""
+    assert base.is_contiguous() and lo.is_contiguous() and base.numel() == lo.numel()
+    lib().call("sfb200_register_tf32_lo", _p(base, F32), _p(lo, F32), base.numel())
+    refresh_tf32_lo(base)
+
+
+def unregister_tf32_lo(base: Tensor) -> None:
+    lib().call("sfb200_unregister_tf32_lo", _p(base, F32))
+
+
+def refresh_tf32_lo(base: Tensor) -> None:
+    """Recompute the registered low halves after the weights were written by anything but clip_adam_step."""
+    lib().call("sfb200_refresh_tf32_lo", _p(base, F32), _stream())
+
+
 def linear_heads_partials(N: int, A: int, engine: int) -> int:
     """Partials per row the fused last-layer + heads forward produces (0: not covered -> use the separate calls)."""
     return int(lib().query("sfb200_linear_heads_partials", N, A, engine))

@@ -107,6 +107,7 @@ class Runner:
         if self.world_size > 1:
             # identical replicas: broadcast rank 0's initial weights
             torch.distributed.broadcast(self.model.flat, src=0)
+            self.model.weights_changed()
         self.async_rl = bool(cfg.async_rl)
         if self.async_rl:
             # the sampler owns a second trajectory set and a weight snapshot; it runs on its own high-priority stream

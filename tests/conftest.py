@@ -3,6 +3,9 @@ import sys
 
 import pytest
 
+# every use of a registered tf32-lo weight twin is verified on the device during the tests (include/sfb200.h)
+os.environ.setdefault("SFB200_CHECK_LO", "1")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

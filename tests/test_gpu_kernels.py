@@ -698,3 +698,43 @@ def test_sampler_post_pre_step_fused_matches_separate(dev):
             else:
                 assert torch.equal(a, b), (k, t)
     assert s2["counter"].item() == T and s2["stats"][0].item() > 0
+
+
+def test_presplit_weight_lo_matches_inline_split(dev):
+    """A GEMM whose weight operand lies in a buffer registered with sfb200_register_tf32_lo (lo tile loaded by TMA) is
+    bit-identical to the same GEMM on an unregistered copy (lo derived in shared memory); Adam keeps lo current."""
+    ops = _ops()
+    M, K, N = 4096, 512, 512
+    eng = ops.GEMM_TC_3XTF32
+    flat = (torch.randn(N * K + N, generator=g(120)) / math.sqrt(K)).to(dev)
+    lo = torch.empty_like(flat)
+    ops.register_tf32_lo(flat, lo)
+    try:
+        W, b = flat[: N * K].view(N, K), flat[N * K:]
+        W2, b2 = W.clone(), b.clone()
+        x = torch.randn(M, K, generator=g(121)).to(dev)
+        y1, y2 = torch.empty(M, N, device=dev), torch.empty(M, N, device=dev)
+        ops.linear_act_forward(x, W, b, y1, ops.ACT["elu"], eng)
+        ops.linear_act_forward(x, W2, b2, y2, ops.ACT["elu"], eng)
+        assert torch.equal(y1, y2)
+        ref = torch.nn.functional.elu(x.double() @ W.double().t() + b.double()).float()
+        assert (y1 - ref).abs().max().item() < 2e-5
+        dz = torch.randn(M, N, generator=g(122)).to(dev)
+        ws = torch.empty(ops.linear_backward_workspace_bytes(M, N, K) // 4 + 4, device=dev)
+        dW1, dW2 = torch.empty(N, K, device=dev), torch.empty(N, K, device=dev)
+        dx1, dx2 = torch.empty(M, K, device=dev), torch.empty(M, K, device=dev)
+        ops.linear_backward(dz, x, W, ops.ACT["elu"], dW1, dx1, None, eng, ws)
+        ops.linear_backward(dz, x, W2, ops.ACT["elu"], dW2, dx2, None, eng, ws)
+        assert torch.equal(dx1, dx2) and torch.equal(dW1, dW2)
+        # Adam on the registered buffer refreshes lo in the same kernel
+        grad = torch.randn_like(flat) * 0.01
+        m, v = torch.zeros_like(flat), torch.zeros_like(flat)
+        ops.clip_adam_step(flat, grad, m, v, 1, 1e-3, 0.9, 0.999, 1e-6, 4.0, None, None, None,
+                           torch.empty(1024, device=dev))
+        lo_adam = lo.clone()
+        ops.refresh_tf32_lo(flat)
+        assert torch.equal(lo_adam, lo)
+        hi = (flat.view(torch.int32) & -8192).view(torch.float32)
+        assert torch.equal(lo, ((flat - hi).view(torch.int32) & -8192).view(torch.float32))
+    finally:
+        ops.unregister_tf32_lo(flat)
