@@ -213,6 +213,11 @@ int sfb200_tape_env_step(const int32_t* actions, int64_t n_envs, int num_actions
                          int term_period, int trunc_period, int64_t* step_counter, int64_t step_host,
                          const float* tape, int64_t tape_len, int dim, float* obs_out, float* rew,
                          uint8_t* terminated, uint8_t* truncated, void* stream);
+/* the same env with a Box(act_dim) action space: reward = clamp(actions[:, 0], -1, 1) */
+int sfb200_tape_env_step_continuous(const float* actions_f32, int act_dim, int64_t n_envs, int64_t env_index_offset,
+                                    int term_period, int trunc_period, int64_t* step_counter, int64_t step_host,
+                                    const float* tape, int64_t tape_len, int dim, float* obs_out, float* rew,
+                                    uint8_t* terminated, uint8_t* truncated, void* stream);
 
 /* ------------------------------------------------------------- learner: batch prep ---- */
 /* learner.py:950-955: valids[:, :T] = (policy_id == this_policy) & (train_step - policy_version < max_lag);

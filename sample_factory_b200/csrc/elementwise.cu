@@ -201,7 +201,9 @@ __global__ void __launch_bounds__(256) post_pre_step_kernel(const PostArgs pa, c
 }
 
 // ---- synthetic tape env ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) tape_env_kernel(const int32_t* __restrict__ actions, int64_t n, int num_actions,
+__global__ void __launch_bounds__(256) tape_env_kernel(const int32_t* __restrict__ actions,
+                                                       const float* __restrict__ actions_f32, int act_dim, int64_t n,
+                                                       int num_actions,
                                                        int64_t env_off, int term_period, int trunc_period,
                                                        const int64_t* __restrict__ step_counter, int64_t step_host,
                                                        const float* __restrict__ tape, int64_t tape_len, int dim,
@@ -214,7 +216,8 @@ __global__ void __launch_bounds__(256) tape_env_kernel(const int32_t* __restrict
     const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
     if (tid < n) {
         const int64_t env = env_off + tid;
-        rew[tid] = (float)actions[tid] / (float)num_actions;
+        // Discrete: action / n ; Box: first action component clipped to [-1, 1] (same rules as the oracle's env)
+        rew[tid] = actions_f32 ? clampf(actions_f32[tid * act_dim], -1.f, 1.f) : (float)actions[tid] / (float)num_actions;
         const bool tm = ((step * 7 + env * 13) % term_period) == 0;
         const bool tr = (((step + env) % trunc_period) == 0) && !tm;
         term[tid] = tm; trunc[tid] = tr;
@@ -384,11 +387,11 @@ int sfb200_sampler_post_pre_step(const float* rew, const uint8_t* terminated, co
     return 0;
 }
 
-int sfb200_tape_env_step(const int32_t* actions, int64_t n_envs, int num_actions, int64_t env_index_offset,
-                         int term_period, int trunc_period, int64_t* step_counter, int64_t step_host, const float* tape,
-                         int64_t tape_len, int dim, float* obs_out, float* rew, uint8_t* terminated,
-                         uint8_t* truncated, void* stream) {
-    SFB_CHECK_ARG(actions && rew && terminated && truncated && n_envs > 0 && num_actions > 0 && term_period > 0 &&
+static int tape_env_step_impl(const int32_t* actions, const float* actions_f32, int act_dim, int64_t n_envs,
+                              int num_actions, int64_t env_index_offset, int term_period, int trunc_period,
+                              int64_t* step_counter, int64_t step_host, const float* tape, int64_t tape_len, int dim,
+                              float* obs_out, float* rew, uint8_t* terminated, uint8_t* truncated, void* stream) {
+    SFB_CHECK_ARG((actions || (actions_f32 && act_dim > 0)) && rew && terminated && truncated && n_envs > 0 && num_actions > 0 && term_period > 0 &&
                       trunc_period > 0, "tape_env_step: bad arguments");
     SFB_CHECK_ARG(!obs_out || (tape && tape_len > 0 && dim > 0), "tape_env_step: obs_out needs a tape");
     cudaStream_t st = (cudaStream_t)stream;
@@ -396,11 +399,27 @@ int sfb200_tape_env_step(const int32_t* actions, int64_t n_envs, int num_actions
     if (obs_out) work = n_envs * (int64_t)dim / 4 > work ? n_envs * (int64_t)dim / 4 : work;
     unsigned g = grid_for(work);
     if ((int64_t)g * 256 < n_envs) g = (unsigned)ceil_div(n_envs, 256);
-    SFB_CUDA_OK(launch_pdl(tape_env_kernel, dim3(g), dim3(256), 0, st, actions, n_envs, num_actions, env_index_offset,
+    SFB_CUDA_OK(launch_pdl(tape_env_kernel, dim3(g), dim3(256), 0, st, actions, actions_f32, act_dim, n_envs, num_actions, env_index_offset,
                            term_period, trunc_period, (const int64_t*)step_counter, step_host, tape, tape_len, dim, obs_out,
                            rew, terminated, truncated));
     SFB_LAUNCH_OK();
     return 0;
+}
+
+int sfb200_tape_env_step(const int32_t* actions, int64_t n_envs, int num_actions, int64_t env_index_offset,
+                         int term_period, int trunc_period, int64_t* step_counter, int64_t step_host, const float* tape,
+                         int64_t tape_len, int dim, float* obs_out, float* rew, uint8_t* terminated,
+                         uint8_t* truncated, void* stream) {
+    return tape_env_step_impl(actions, nullptr, 0, n_envs, num_actions, env_index_offset, term_period, trunc_period,
+                              step_counter, step_host, tape, tape_len, dim, obs_out, rew, terminated, truncated, stream);
+}
+
+int sfb200_tape_env_step_continuous(const float* actions_f32, int act_dim, int64_t n_envs, int64_t env_index_offset,
+                                    int term_period, int trunc_period, int64_t* step_counter, int64_t step_host,
+                                    const float* tape, int64_t tape_len, int dim, float* obs_out, float* rew,
+                                    uint8_t* terminated, uint8_t* truncated, void* stream) {
+    return tape_env_step_impl(nullptr, actions_f32, act_dim, n_envs, 1, env_index_offset, term_period, trunc_period,
+                              step_counter, step_host, tape, tape_len, dim, obs_out, rew, terminated, truncated, stream);
 }
 
 int sfb200_compute_valids(const int32_t* policy_id, const float* policy_version, int64_t n_traj, int T,

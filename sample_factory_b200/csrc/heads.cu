@@ -568,7 +568,7 @@ int sfb200_heads_backward(const float* h, int64_t ldh, int64_t rows, int H, int 
                   "heads_backward: bad arguments");
     SFB_CHECK_ARG(A >= 1 && A <= 31, "heads_backward: supports 1 <= A <= 31, got %d", A);
     cudaStream_t st = (cudaStream_t)stream;
-    int64_t groups = (int64_t)sm_count() * 2;
+    int64_t groups = (int64_t)sm_count() * 2;   // (3 blocks/SM with deeper unrolling measured 33 % slower: 97 vs 73 us)
     if (groups > kHeadsMaxGroups) groups = kHeadsMaxGroups;
     int64_t rpg = ceil_div(rows, groups);
     rpg = ceil_div(rpg, kHbTile) * kHbTile;

@@ -52,9 +52,12 @@ class TapeVecEnv:
     is_gpu_env = True
 
     def __init__(self, tape: Tensor, num_actions: int, term_period: int = 37, trunc_period: int = 11,
-                 env_index_offset: int = 0):
+                 env_index_offset: int = 0, continuous: bool = False):
         assert tape.is_cuda and tape.dtype == torch.float32 and tape.dim() == 3 and tape.is_contiguous()
         self.tape = tape
+        # continuous: Box(num_actions) action space, actions arrive as float32 [num_agents, num_actions] and
+        # reward = clamp(actions[:, 0], -1, 1); otherwise Discrete(num_actions), int32 [num_agents]
+        self.continuous = continuous
         self.tape_len, self.num_agents, self.obs_dim = tape.shape
         self.num_actions = num_actions
         self.term_period, self.trunc_period = term_period, trunc_period
@@ -73,8 +76,13 @@ class TapeVecEnv:
         return self.obs
 
     def step(self, actions: Tensor) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
-        ops.tape_env_step(actions, self.num_actions, self.env_index_offset, self.term_period, self.trunc_period,
-                          self.step_counter, 0, self.tape, self.obs, self.rew, self.terminated, self.truncated)
+        if self.continuous:
+            ops.tape_env_step_continuous(actions, self.env_index_offset, self.term_period, self.trunc_period,
+                                         self.step_counter, 0, self.tape, self.obs, self.rew, self.terminated,
+                                         self.truncated)
+        else:
+            ops.tape_env_step(actions, self.num_actions, self.env_index_offset, self.term_period, self.trunc_period,
+                              self.step_counter, 0, self.tape, self.obs, self.rew, self.terminated, self.truncated)
         return self.obs, self.rew, self.terminated, self.truncated
 
 

@@ -125,6 +125,8 @@ class Learner:
             assert cfg.recurrence == cfg.rollout and cfg.recurrence > 1, "V-trace requires recurrence == rollout > 1"
             assert not cfg.normalize_returns, "normalize_returns is incompatible with V-trace (arguments.py:129-134)"
         assert cfg.exploration_loss == "entropy", "only the entropy exploration loss is on the device path"
+        assert not (spec.continuous and spec.adaptive_stddev and spec.continuous_tanh_scale > 0), (
+            "continuous_tanh_scale is only read by the non-adaptive parameterization (action_parameterization.py:33-78)")
         assert not cfg.shuffle_minibatches, "shuffle_minibatches is not on the device path yet"
         assert len(spec.hidden) > 0 or spec.use_rnn, "the device path needs at least one hidden layer or an RNN core"
         if spec.use_rnn:
@@ -133,7 +135,9 @@ class Learner:
 
         dev = self.device
         f32 = dict(dtype=torch.float32, device=dev)
-        D, A = spec.obs_dim, spec.num_actions
+        D = spec.obs_dim
+        A = spec.num_action_params           # width of action_logits: n logits, or [means | log_std] for a Box space
+        A_lin = spec.num_linear_action_outputs   # rows of distribution_linear
         B = cfg.batch_size
         self.E = E
         # batch-prep buffers
@@ -157,7 +161,12 @@ class Learner:
         self.dz = [torch.empty((B, h), **f32) for h in spec.hidden]
         self.mb_values = torch.empty(B, **f32)
         self.mb_logits = torch.empty((B, A), **f32)
-        self.dlogits = torch.empty((B, A), **f32)
+        self.dlogits = torch.empty((B, A_lin), **f32)
+        # learned log-stddev vector (continuous, adaptive_stddev=False): per-sample gradient, column-summed per minibatch
+        self.dlogstd = self.colsum_ws = None
+        if spec.continuous and not spec.adaptive_stddev:
+            self.dlogstd = torch.empty((B, spec.num_actions), **f32)
+            self.colsum_ws = torch.empty(ops.colsum_workspace_bytes(spec.num_actions) // 4 + 4, **f32)
         self.dvalues = torch.empty(B, **f32)
         self.ratio = torch.empty(B, **f32)
         self.vs = torch.empty(B, **f32)
@@ -168,7 +177,7 @@ class Learner:
         self.grad_norm_log = torch.zeros(n_mb_total, **f32)
         self.dp_partials = torch.zeros(3, dtype=torch.float64, device=dev)
         self.loss_ws = torch.empty(ops.loss_workspace_bytes(max(B, E)) // 8 + 8, dtype=torch.float64, device=dev)
-        self.heads_ws = torch.empty(ops.heads_backward_workspace_bytes(spec.tail_input_size, A) // 4 + 4, **f32)
+        self.heads_ws = torch.empty(ops.heads_backward_workspace_bytes(spec.tail_input_size, A_lin) // 4 + 4, **f32)
         lin_ws = 4
         d = D
         for h in spec.encoder_mlp_layers:
@@ -266,9 +275,11 @@ class Learner:
         cfg, m, spec = self.cfg, self.model, self.model.spec
         B = cfg.batch_size
         sl = slice(b * B, (b + 1) * B)                                                               # :521
-        A = spec.num_actions
+        A = spec.num_action_params
         x0 = self.obs_flat_compact[sl]
-        actions = batch["actions"].view(self.E)[sl]
+        actions = batch["actions"].view(self.E, spec.action_width)[sl]
+        if not spec.continuous:
+            actions = actions.view(-1)
         lp_old = batch["log_prob_actions"].view(self.E)[sl]
         logits_old = batch["action_logits"].view(self.E, A)[sl]
         valids = self.valids_flat.view(self.E)[sl]
@@ -284,7 +295,10 @@ class Learner:
         Wv, bv = m.critic
         Wa, ba = m.actor
         if cfg.with_vtrace:                                                                          # :602-640
-            ops.action_ratio(self.mb_logits, actions, lp_old, self.ratio)
+            if spec.continuous:
+                ops.action_ratio_continuous(self.mb_logits, actions, lp_old, self.ratio)
+            else:
+                ops.action_ratio(self.mb_logits, actions, lp_old, self.ratio)
             ops.vtrace(self.ratio, self.mb_values, batch["rewards"].view(self.E)[sl], batch["dones"].view(self.E)[sl],
                        cfg.recurrence, cfg.gamma, cfg.vtrace_rho, cfg.vtrace_c, self.vs, self.vt_adv)
             adv, targets = self.vt_adv, self.vs
@@ -298,9 +312,18 @@ class Learner:
         else:
             ops.adv_stats(adv, valids, self.loss_stats, None, self.loss_ws)
         # losses forward + backward (:651-657, :779)
-        ops.ppo_loss_fwd_bwd(self.mb_logits, self.mb_values, actions, lp_old, v_old, adv, targets, valids, logits_old,
-                             cfg.ppo_clip_ratio, cfg.ppo_clip_value, cfg.exploration_loss_coeff, cfg.value_loss_coeff,
-                             cfg.kl_loss_coeff, 1.0, self.dlogits, self.dvalues, self.loss_stats, self.loss_ws)
+        if spec.continuous:
+            ops.ppo_loss_fwd_bwd_continuous(self.mb_logits, self.mb_values, spec.adaptive_stddev, spec.continuous_tanh_scale,
+                                            actions, lp_old, v_old, adv, targets, valids, logits_old, cfg.ppo_clip_ratio,
+                                            cfg.ppo_clip_value, cfg.exploration_loss_coeff, cfg.value_loss_coeff,
+                                            cfg.kl_loss_coeff, 1.0, self.dlogits, self.dlogstd, self.dvalues,
+                                            self.loss_stats, self.loss_ws)
+            if self.dlogstd is not None:   # gradient of the learned log-stddev vector = column sum over the minibatch
+                ops.colsum(self.dlogstd, m.grads["action_parameterization.learned_stddev"], self.colsum_ws)
+        else:
+            ops.ppo_loss_fwd_bwd(self.mb_logits, self.mb_values, actions, lp_old, v_old, adv, targets, valids, logits_old,
+                                 cfg.ppo_clip_ratio, cfg.ppo_clip_value, cfg.exploration_loss_coeff, cfg.value_loss_coeff,
+                                 cfg.kl_loss_coeff, 1.0, self.dlogits, self.dvalues, self.loss_stats, self.loss_ws)
         self.loss_stats_log[log_idx].copy_(self.loss_stats)
         # backward: heads -> decoder MLP -> (recurrent core, BPTT) -> encoder MLP
         g = m.grads

@@ -33,6 +33,40 @@ class ModelSpec:
     use_rnn: bool = False        # model/core.py: ModelCoreRNN (one layer) between encoder and decoder
     rnn_type: str = "gru"
     rnn_size: int = 512
+    # Box action space (action_distributions.py:290-323): num_actions is then the action DIMENSION
+    continuous: bool = False
+    adaptive_stddev: bool = True        # cfg.py:577; False -> one learned log-stddev vector (action_parameterization.py:42)
+    continuous_tanh_scale: float = 0.0  # cfg.py:583
+    initial_stddev: float = 1.0         # cfg.py:591
+
+    @classmethod
+    def from_cfg(cls, cfg, env) -> "ModelSpec":
+        """The model the reference would build for this cfg / env (model/actor_critic.py:136-158, create_actor_critic):
+        Discrete(n) envs expose `num_actions = n`; Box(A) envs expose `continuous = True` and `num_actions = A`."""
+        return cls(env.obs_dim, env.num_actions, list(cfg.encoder_mlp_layers), list(cfg.decoder_mlp_layers),
+                   cfg.nonlinearity, cfg.normalize_input, cfg.normalize_returns, cfg.obs_subtract_mean, cfg.obs_scale,
+                   bool(cfg.use_rnn), cfg.rnn_type, cfg.rnn_size,
+                   continuous=bool(getattr(env, "continuous", False)),
+                   adaptive_stddev=bool(getattr(cfg, "adaptive_stddev", True)),
+                   continuous_tanh_scale=float(getattr(cfg, "continuous_tanh_scale", 0.0)),
+                   initial_stddev=float(getattr(cfg, "initial_stddev", 1.0)))
+
+    @property
+    def num_linear_action_outputs(self) -> int:
+        """rows of distribution_linear"""
+        if not self.continuous:
+            return self.num_actions
+        return 2 * self.num_actions if self.adaptive_stddev else self.num_actions
+
+    @property
+    def num_action_params(self) -> int:
+        """calc_num_action_parameters (action_distributions.py:33-44): width of `action_logits`"""
+        return 2 * self.num_actions if self.continuous else self.num_actions
+
+    @property
+    def action_width(self) -> int:
+        """calc_num_actions (:16-30): width of `actions`"""
+        return self.num_actions if self.continuous else 1
 
     @property
     def hidden(self) -> List[int]:
@@ -78,8 +112,11 @@ class ModelSpec:
             d = h
         out.append(("critic_linear.weight", (1, d)))
         out.append(("critic_linear.bias", (1,)))
-        out.append(("action_parameterization.distribution_linear.weight", (self.num_actions, d)))
-        out.append(("action_parameterization.distribution_linear.bias", (self.num_actions,)))
+        if self.continuous and not self.adaptive_stddev:
+            # a module's own parameters precede its children's in nn.Module.parameters()
+            out.append(("action_parameterization.learned_stddev", (self.num_actions,)))
+        out.append(("action_parameterization.distribution_linear.weight", (self.num_linear_action_outputs, d)))
+        out.append(("action_parameterization.distribution_linear.bias", (self.num_linear_action_outputs,)))
         return out
 
 
@@ -156,7 +193,9 @@ class PolicyModel:
         g = torch.Generator(device="cpu").manual_seed(seed)
         for name in self.names:
             p = self.params[name]
-            if name.startswith("core.core."):
+            if name == "action_parameterization.learned_stddev":
+                p.fill_(math.log(self.spec.initial_stddev))   # action_parameterization.py:59-61
+            elif name.startswith("core.core."):
                 # RNNs keep the PyTorch default init U(-1/sqrt(H), 1/sqrt(H)) (actor_critic.py:83-88)
                 k = 1.0 / math.sqrt(self.spec.rnn_size)
                 p.copy_((torch.rand(p.shape, generator=g) * 2 - 1) * k)
@@ -227,6 +266,17 @@ class PolicyModel:
         for i in range(len(self.spec.decoder_mlp_layers)):
             out.append((self.grads[f"decoder.mlp.{2 * i}.weight"], self.grads[f"decoder.mlp.{2 * i}.bias"]))
         return out
+
+    @property
+    def learned_log_std(self):
+        """the learned log-stddev vector (None unless continuous with adaptive_stddev=False)"""
+        return self.params.get("action_parameterization.learned_stddev")
+
+    def dist_kwargs(self) -> Dict:
+        """distribution description for the continuous heads / loss ops"""
+        sp = self.spec
+        return dict(act_dim=sp.num_actions, adaptive_stddev=sp.adaptive_stddev, learned_log_std=self.learned_log_std,
+                    tanh_scale=sp.continuous_tanh_scale)
 
     @property
     def critic(self) -> Tuple[Tensor, Tensor]:

@@ -126,6 +126,54 @@ def heads_forward(h: Tensor, Wv: Tensor, bv: Tensor, Wa: Tensor, ba: Tensor, val
                None if policy_version_out is None else policy_version_out.data_ptr(), pv_stride, _stream())
 
 
+def _cont_tail_args(values, values_stride, params, params_stride, noise, philox_seed, philox_offset, philox_offset_dev,
+                    actions_f32, actions_stride, env_actions, log_prob, log_prob_stride, policy_version_scalar,
+                    policy_version_out, pv_stride):
+    assert noise is None or noise.is_contiguous()
+    assert env_actions is None or (env_actions.dtype == F32 and env_actions.is_contiguous())
+    return (values.data_ptr(), values_stride, None if params is None else params.data_ptr(), params_stride,
+            _p(noise, F32), philox_seed, philox_offset, _p(philox_offset_dev, I64),
+            None if actions_f32 is None else actions_f32.data_ptr(), actions_stride, _p(env_actions, F32),
+            None if log_prob is None else log_prob.data_ptr(), log_prob_stride, _p(policy_version_scalar, F32),
+            None if policy_version_out is None else policy_version_out.data_ptr(), pv_stride, _stream())
+
+
+def heads_forward_continuous(h: Tensor, Wv: Tensor, bv: Tensor, Wa: Tensor, ba: Tensor, act_dim: int,
+                             adaptive_stddev: bool, learned_log_std: Optional[Tensor], tanh_scale: float, values: Tensor,
+                             values_stride: int, logits: Optional[Tensor] = None, logits_stride: int = 0,
+                             noise: Optional[Tensor] = None, philox_seed: int = 0, philox_offset: int = 0,
+                             philox_offset_dev: Optional[Tensor] = None, actions_f32: Optional[Tensor] = None,
+                             actions_stride: int = 0, env_actions: Optional[Tensor] = None,
+                             log_prob: Optional[Tensor] = None, log_prob_stride: int = 0,
+                             policy_version_scalar: Optional[Tensor] = None, policy_version_out: Optional[Tensor] = None,
+                             pv_stride: int = 0) -> None:
+    """Box action space: `logits` receives the distribution parameters [means | log_std] (2*act_dim per row), actions
+    are float vectors; `env_actions` is a dense float32 [rows, act_dim] copy for the env."""
+    rows, H = h.shape
+    assert Wa.shape[0] == (2 * act_dim if adaptive_stddev else act_dim) and Wa.is_contiguous() and Wv.is_contiguous()
+    lib().call("sfb200_heads_forward_continuous", _p(h, F32), h.stride(0), rows, H, act_dim, int(adaptive_stddev),
+               _p(Wv, F32), _p(bv, F32), _p(Wa, F32), _p(ba, F32), _p(learned_log_std, F32), float(tanh_scale),
+               *_cont_tail_args(values, values_stride, logits, logits_stride, noise, philox_seed, philox_offset,
+                                philox_offset_dev, actions_f32, actions_stride, env_actions, log_prob, log_prob_stride,
+                                policy_version_scalar, policy_version_out, pv_stride))
+
+
+def heads_from_partials_continuous(head_partials: Tensor, P: int, rows: int, bv: Tensor, ba: Tensor, act_dim: int,
+                                   adaptive_stddev: bool, learned_log_std: Optional[Tensor], tanh_scale: float,
+                                   values: Tensor, values_stride: int, logits: Optional[Tensor] = None,
+                                   logits_stride: int = 0, noise: Optional[Tensor] = None, philox_seed: int = 0,
+                                   philox_offset: int = 0, philox_offset_dev: Optional[Tensor] = None,
+                                   actions_f32: Optional[Tensor] = None, actions_stride: int = 0,
+                                   env_actions: Optional[Tensor] = None, log_prob: Optional[Tensor] = None,
+                                   log_prob_stride: int = 0, policy_version_scalar: Optional[Tensor] = None,
+                                   policy_version_out: Optional[Tensor] = None, pv_stride: int = 0) -> None:
+    lib().call("sfb200_heads_from_partials_continuous", _p(head_partials, F32), P, rows, act_dim, int(adaptive_stddev),
+               _p(bv, F32), _p(ba, F32), _p(learned_log_std, F32), float(tanh_scale),
+               *_cont_tail_args(values, values_stride, logits, logits_stride, noise, philox_seed, philox_offset,
+                                philox_offset_dev, actions_f32, actions_stride, env_actions, log_prob, log_prob_stride,
+                                policy_version_scalar, policy_version_out, pv_stride))
+
+
 def register_tf32_lo(base: Tensor, lo: Tensor) -> None:
     """Pair a flat weight buffer with its tf32 low-half twin (see include/sfb200.h) and fill the twin."""
     assert base.is_contiguous() and lo.is_contiguous() and base.numel() == lo.numel()
@@ -263,6 +311,17 @@ def tape_env_step(actions: Tensor, num_actions: int, env_index_offset: int, term
                _p(terminated, U8), _p(truncated, U8), _stream())
 
 
+def tape_env_step_continuous(actions_f32: Tensor, env_index_offset: int, term_period: int, trunc_period: int,
+                             step_counter: Optional[Tensor], step_host: int, tape: Optional[Tensor],
+                             obs_out: Optional[Tensor], rew: Tensor, terminated: Tensor, truncated: Tensor) -> None:
+    n, act_dim = actions_f32.shape
+    assert actions_f32.is_contiguous()
+    tape_len, dim = (tape.shape[0], tape.shape[2]) if tape is not None else (0, 0)
+    lib().call("sfb200_tape_env_step_continuous", _p(actions_f32, F32), act_dim, n, env_index_offset, term_period,
+               trunc_period, _p(step_counter, I64), step_host, _p(tape, F32), tape_len, dim, _p(obs_out, F32),
+               _p(rew, F32), _p(terminated, U8), _p(truncated, U8), _stream())
+
+
 # ------------------------------------------------------------------------------------------------ learner: prep
 def compute_valids(policy_id: Tensor, policy_version: Tensor, this_policy: int, train_step: int, max_policy_lag: int,
                    valids: Tensor) -> None:
@@ -326,6 +385,34 @@ def ppo_loss_fwd_bwd(logits: Tensor, values: Tensor, actions_f32: Tensor, log_pr
                _p(log_prob_old, F32), _p(values_old, F32), _p(adv, F32), _p(targets, F32), _p(valids, U8),
                _p(logits_old, F32), B, clip_ratio, clip_value, exploration_coeff, value_coeff, kl_coeff, grad_scale,
                _p(dlogits, F32), _p(dvalues, F32), _p(stats, F64), workspace.data_ptr(), _stream())
+
+
+def action_ratio_continuous(params: Tensor, actions_f32: Tensor, log_prob_old: Tensor, ratio: Tensor) -> None:
+    B, A2 = params.shape
+    assert params.is_contiguous() and actions_f32.is_contiguous()
+    lib().call("sfb200_action_ratio_continuous", _p(params, F32), A2 // 2, _p(actions_f32, F32), _p(log_prob_old, F32),
+               B, _p(ratio, F32), _stream())
+
+
+def ppo_loss_fwd_bwd_continuous(params: Tensor, values: Tensor, adaptive_stddev: bool, tanh_scale: float,
+                                actions_f32: Tensor, log_prob_old: Tensor, values_old: Tensor, adv: Tensor,
+                                targets: Tensor, valids: Tensor, params_old: Optional[Tensor], clip_ratio: float,
+                                clip_value: float, exploration_coeff: float, value_coeff: float, kl_coeff: float,
+                                grad_scale: float, dlogits: Tensor, dlogstd: Optional[Tensor], dvalues: Tensor,
+                                stats: Tensor, workspace: Tensor) -> None:
+    """params / params_old [B, 2*Ad] = [means | log_std]; actions [B, Ad]; dlogits [B, 2*Ad] (adaptive) or [B, Ad]
+    plus dlogstd [B, Ad] (learned stddev)."""
+    B, A2 = params.shape
+    Ad = A2 // 2
+    assert params.is_contiguous() and dlogits.is_contiguous() and actions_f32.is_contiguous()
+    assert dlogits.shape == (B, A2 if adaptive_stddev else Ad)
+    assert params_old is None or params_old.is_contiguous()
+    assert workspace.numel() * workspace.element_size() >= loss_workspace_bytes(B)
+    lib().call("sfb200_ppo_loss_fwd_bwd_continuous", _p(params, F32), _p(values, F32), Ad, int(adaptive_stddev),
+               float(tanh_scale), _p(actions_f32, F32), _p(log_prob_old, F32), _p(values_old, F32), _p(adv, F32),
+               _p(targets, F32), _p(valids, U8), _p(params_old, F32), B, clip_ratio, clip_value, exploration_coeff,
+               value_coeff, kl_coeff, grad_scale, _p(dlogits, F32), _p(dlogstd, F32), _p(dvalues, F32), _p(stats, F64),
+               workspace.data_ptr(), _stream())
 
 
 # ------------------------------------------------------------------------------------------------ learner: backward

@@ -27,7 +27,7 @@ class HeadsPlan:
         self.P = 0
         self.part: Optional[Tensor] = None
         if self.tail_is_mlp:
-            self.P = ops.linear_heads_partials(spec.tail_input_size, spec.num_actions, engine)
+            self.P = ops.linear_heads_partials(spec.tail_input_size, spec.num_linear_action_outputs, engine)
         if self.P > 0:
             self.part = torch.empty(self.P * max_rows * ops.HEAD_PART_PAD, dtype=torch.float32, device=model.device)
 
@@ -59,7 +59,13 @@ def forward_policy(model: PolicyModel, x: Tensor, outs: List[Tensor], act: int, 
                 ops.linear_act_forward(tail, W, b, outs[k][:M], act, engine)
                 tail = outs[k][:M]
             k += 1
-    if fused:
+    if model.spec.continuous:   # Box action space: Gaussian heads (action_distributions.py:290-323)
+        dk = model.dist_kwargs()
+        if fused:
+            ops.heads_from_partials_continuous(plan.part, plan.P, M, bv, ba, **dk, **heads_kwargs)
+        else:
+            ops.heads_forward_continuous(tail, Wv, bv, Wa, ba, **dk, **heads_kwargs)
+    elif fused:
         ops.heads_from_partials(plan.part, plan.P, M, bv, ba, **heads_kwargs)
     else:
         ops.heads_forward(tail, Wv, bv, Wa, ba, **heads_kwargs)

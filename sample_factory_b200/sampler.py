@@ -47,7 +47,12 @@ class DeviceSampler:
         # per-step scratch (never reallocated)
         self.x_norm = torch.empty((self.N, spec.obs_dim), **f32)
         self.h = [torch.empty((self.N, h), **f32) for h in spec.hidden]
-        self.env_actions = torch.empty(self.N, dtype=torch.int32, device=dev)
+        # what env.step() receives (preprocess_actions, batched_sampling.py:30-82): int32 [N] for Discrete, float32 [N, A]
+        # for a Box action space
+        if spec.continuous:
+            self.env_actions = torch.empty((self.N, spec.num_actions), dtype=torch.float32, device=dev)
+        else:
+            self.env_actions = torch.empty(self.N, dtype=torch.int32, device=dev)
         self.heads_plan = HeadsPlan(model, engine, self.N)
         self.last_rnn_state = torch.zeros((self.N, traj["rnn_states"].shape[2]), **f32)
         self.rnn: Optional[RnnCore] = None

@@ -25,7 +25,7 @@ from .cfg import preprocess_cfg
 from .envs import create_env
 from .model import ModelSpec, PolicyModel
 from .sampler import DeviceSampler
-from .trajectory import alloc_trajectory_tensors
+from .trajectory import alloc_for_spec
 
 
 class StatusCode:
@@ -56,9 +56,7 @@ def samples_per_trajectory(traj: Dict[str, Tensor]) -> int:
 
 
 def _model_spec(cfg, env) -> ModelSpec:
-    return ModelSpec(env.obs_dim, env.num_actions, list(cfg.encoder_mlp_layers), list(cfg.decoder_mlp_layers),
-                     cfg.nonlinearity, cfg.normalize_input, cfg.normalize_returns, cfg.obs_subtract_mean, cfg.obs_scale,
-                     bool(cfg.use_rnn), cfg.rnn_type, cfg.rnn_size)
+    return ModelSpec.from_cfg(cfg, env)
 
 
 class _DeviceSamplingLoop:
@@ -81,8 +79,7 @@ class _DeviceSamplingLoop:
                                                                  policy_init_gain=cfg.policy_init_gain)
         engine = ops.ENGINES[getattr(cfg, "gemm_engine", "auto")] if getattr(cfg, "gemm_engine", "auto") != "auto" else (
             ops.GEMM_TC_3XTF32 if ops.tc_available() else ops.GEMM_SIMT)
-        self.traj = alloc_trajectory_tensors(spec.obs_dim, spec.num_actions, self.env.num_agents, cfg.rollout, self.device,
-                                             rnn_size=spec.rnn_state_size)
+        self.traj = alloc_for_spec(spec, self.env.num_agents, cfg.rollout, self.device)
         self.sampler = DeviceSampler(cfg, self.env, self.model, self.traj, engine=engine,
                                      use_cuda_graph=bool(getattr(cfg, "cuda_graph", True)),
                                      philox_seed=(cfg.seed or 0) * 1000003, record_episodes=record_episodes)

@@ -33,7 +33,7 @@ from .envs import create_env
 from .learner import Learner
 from .model import ModelSpec, PolicyModel
 from .sampler import DeviceSampler
-from .trajectory import alloc_trajectory_tensors
+from .trajectory import alloc_for_spec
 
 
 class StatusCode:
@@ -95,15 +95,12 @@ class Runner:
             raise ValueError("invalid configuration (see cfg.verify_cfg)")
         env_config = dict(worker_index=self.rank, vector_index=0, env_id=self.rank)
         self.env = create_env(cfg.env, cfg, env_config)
-        spec = ModelSpec(self.env.obs_dim, self.env.num_actions, list(cfg.encoder_mlp_layers),
-                         list(cfg.decoder_mlp_layers), cfg.nonlinearity, cfg.normalize_input, cfg.normalize_returns,
-                         cfg.obs_subtract_mean, cfg.obs_scale, bool(cfg.use_rnn), cfg.rnn_type, cfg.rnn_size)
+        spec = ModelSpec.from_cfg(cfg, self.env)
         assert cfg.rnn_num_layers == 1, "the device path implements the one-layer recurrent core"
         self.model = PolicyModel(spec, self.device, seed=cfg.seed or 0, policy_init_gain=cfg.policy_init_gain)
         N = self.env.num_agents
         self.engine = select_engine(cfg)
-        self.traj = alloc_trajectory_tensors(spec.obs_dim, spec.num_actions, N, cfg.rollout, self.device,
-                                             rnn_size=spec.rnn_state_size)
+        self.traj = alloc_for_spec(spec, N, cfg.rollout, self.device)
         if self.world_size > 1:
             # identical replicas: broadcast rank 0's initial weights
             torch.distributed.broadcast(self.model.flat, src=0)
@@ -112,8 +109,7 @@ class Runner:
         if self.async_rl:
             # the sampler owns a second trajectory set and a weight snapshot; it runs on its own high-priority stream
             self.sampler_model = self.model.inference_copy()
-            self.sampler_traj = alloc_trajectory_tensors(spec.obs_dim, spec.num_actions, N, cfg.rollout, self.device,
-                                                         rnn_size=spec.rnn_state_size)
+            self.sampler_traj = alloc_for_spec(spec, N, cfg.rollout, self.device)
             self.sampler_stream = torch.cuda.Stream(device=self.device, priority=-1)
             self.ev_rollout, self.ev_join = torch.cuda.Event(), torch.cuda.Event()
             self.snapshot_version = 0

@@ -37,6 +37,13 @@ def alloc_trajectory_tensors(obs_dim: int, num_action_params: int, num_traj: int
     return t
 
 
+def alloc_for_spec(spec, num_traj: int, rollout: int, device) -> Dict[str, Tensor]:
+    """Trajectory set for a ModelSpec: `actions` is [.., 1] for Discrete and [.., A] for Box(A); `action_logits` holds the
+    distribution parameters (n logits, or 2A = [means | log_std]) -- shared_buffers.py:67-76 policy_output_shapes."""
+    return alloc_trajectory_tensors(spec.obs_dim, spec.num_action_params, num_traj, rollout, device,
+                                    rnn_size=spec.rnn_state_size, num_actions=spec.action_width)
+
+
 def trajectory_bytes_per_env_step(obs_dim: int, num_action_params: int, rnn_size: int = 1) -> int:
     """Algorithmic sampler traffic per env step: obs read + the trajectory record written."""
     write = obs_dim * 4 + rnn_size * 4 + 4 + num_action_params * 4 + 4 + 4 + 4 + 4 + 1 + 1 + 4

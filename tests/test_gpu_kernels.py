@@ -738,3 +738,137 @@ def test_presplit_weight_lo_matches_inline_split(dev):
         assert torch.equal(lo, ((flat - hi).view(torch.int32) & -8192).view(torch.float32))
     finally:
         ops.unregister_tf32_lo(flat)
+
+
+# ----------------------------------------------------------------------------------------------- continuous actions
+@pytest.mark.parametrize("adaptive,tanh_scale", [(True, 0.0), (False, 0.0), (False, 1.5)])
+@pytest.mark.parametrize("rows,H,Ad", [(300, 64, 6), (4096, 512, 8), (37, 48, 1)])
+def test_heads_forward_continuous(dev, rows, H, Ad, adaptive, tanh_scale):
+    """sfb200_heads_forward_continuous vs the oracle's ContinuousActionDistribution restatement (pinned to the reference
+    by the tiny_gauss goldens): distribution parameters, sampled actions, log-probs."""
+    ops = _ops()
+    ocfg = O.OracleCfg(obs_dim=H, num_actions=Ad, encoder_mlp_layers=[], continuous=True, adaptive_stddev=adaptive,
+                       continuous_tanh_scale=tanh_scale)
+    n_lin = O.num_linear_action_outputs(ocfg)
+    h = torch.randn(rows, H, generator=g(130))
+    st = {O.CRITIC_W: torch.randn(1, H, generator=g(131)) / math.sqrt(H), O.CRITIC_B: torch.randn(1, generator=g(132)),
+          O.ACTION_W: torch.randn(n_lin, H, generator=g(133)) / math.sqrt(H), O.ACTION_B: torch.randn(n_lin, generator=g(134)) * 0.3,
+          O.LEARNED_STD: torch.randn(Ad, generator=g(135)) * 0.5}
+    eps = torch.randn(rows, Ad, generator=g(136))
+    v_ref, params_ref = O.tail_forward(ocfg, st, h)
+    a_ref = O.gauss_sample(params_ref, eps)
+    lp_ref = O.gauss_log_prob(params_ref, a_ref)
+
+    d = {k: v.to(dev).contiguous() for k, v in st.items()}
+    values = torch.empty(rows, device=dev)
+    params = torch.full((rows, 2 * Ad), float("nan"), device=dev)
+    actions = torch.empty(rows, Ad, device=dev)
+    env_actions = torch.empty(rows, Ad, device=dev)
+    lp = torch.empty(rows, device=dev)
+    pv = torch.empty(rows, device=dev)
+    ops.heads_forward_continuous(h.to(dev), d[O.CRITIC_W], d[O.CRITIC_B], d[O.ACTION_W], d[O.ACTION_B], Ad, adaptive,
+                                 None if adaptive else d[O.LEARNED_STD], tanh_scale, values, 1, params, 2 * Ad,
+                                 eps.to(dev), 0, 0, None, actions, Ad, env_actions, lp, 1,
+                                 torch.full((1,), 3.0, device=dev), pv, 1)
+    assert (values.cpu() - v_ref).abs().max().item() < TOL
+    assert (params.cpu() - params_ref).abs().max().item() < TOL
+    if not adaptive:
+        assert torch.equal(params.cpu()[:, Ad:], st[O.LEARNED_STD].repeat(rows, 1))
+    # a = eps*std + mean: std = exp(log_std) carries the 1e-6 RELATIVE difference of log_std, so compare relatively
+    np.testing.assert_allclose(actions.cpu().numpy(), a_ref.numpy(), atol=2e-5, rtol=5e-5)
+    assert torch.equal(actions, env_actions) and torch.all(pv == 3.0)
+    # log-prob of the device's own action under the device's own parameters, evaluated by the oracle formula
+    lp_self = O.gauss_log_prob(params.cpu(), actions.cpu())
+    assert (lp.cpu() - lp_self).abs().max().item() < 2e-5
+    assert (lp.cpu() - lp_ref).abs().max().item() < 1e-3   # (a - mean)/std amplifies 1e-6 differences for small std
+    # parameters-only mode (learner minibatch forward) and the Philox path (statistics only)
+    params2 = torch.empty_like(params)
+    ops.heads_forward_continuous(h.to(dev), d[O.CRITIC_W], d[O.CRITIC_B], d[O.ACTION_W], d[O.ACTION_B], Ad, adaptive,
+                                 None if adaptive else d[O.LEARNED_STD], tanh_scale, values, 1, params2, 2 * Ad)
+    assert torch.equal(params2, params)
+    if rows >= 4096:
+        ops.heads_forward_continuous(h.to(dev), d[O.CRITIC_W], d[O.CRITIC_B], d[O.ACTION_W], d[O.ACTION_B], Ad, adaptive,
+                                     None if adaptive else d[O.LEARNED_STD], tanh_scale, values, 1, params2, 2 * Ad,
+                                     None, 1234, 0, None, actions, Ad, env_actions, lp, 1)
+        mu, _, sd = O.gauss_split(params.cpu())
+        zs = (actions.cpu() - mu) / sd
+        assert abs(zs.mean().item()) < 0.02 and abs(zs.std().item() - 1.0) < 0.02
+
+
+@pytest.mark.parametrize("B,Ad,adaptive,tanh_scale,frac_invalid,kl_coeff",
+                         [(64, 6, True, 0.0, 0.0, 0.0), (1000, 6, False, 1.5, 0.2, 0.1), (4096, 8, False, 0.0, 0.0, 0.1),
+                          (777, 3, True, 0.0, 0.3, 0.5), (513, 12, False, 2.0, 0.1, 0.2)])
+def test_ppo_loss_fwd_bwd_continuous(dev, B, Ad, adaptive, tanh_scale, frac_invalid, kl_coeff):
+    """Gaussian PPO loss forward + backward vs autograd through the oracle's distribution formulas; the leaves are the
+    distribution_linear outputs z (and the learned log-stddev vector when adaptive_stddev=False)."""
+    ops = _ops()
+    cfg = O.OracleCfg(num_actions=Ad, kl_loss_coeff=kl_coeff, ppo_clip_ratio=0.2, ppo_clip_value=0.2, continuous=True,
+                      exploration_loss_coeff=0.003)
+    n_lin = 2 * Ad if adaptive else Ad
+    z = (torch.randn(B, n_lin, generator=g(140)) * 0.8).requires_grad_(True)
+    learned = (torch.randn(Ad, generator=g(141)) * 0.4).requires_grad_(True)
+    if adaptive:
+        z.data[:, Ad:] *= 0.5
+        z.data[0, Ad] = -12.0     # std clamp (1e-4) active: zero gradient through the clamp
+        z.data[1, Ad] = 11.0      # std clamp (1e4) active
+
+    def params_of(zz, ll):
+        if adaptive:
+            return zz
+        means = torch.tanh(zz / tanh_scale) * tanh_scale if tanh_scale > 0 else zz
+        return torch.cat((means, ll.repeat(B, 1)), dim=1)
+
+    params = params_of(z, learned)
+    values = torch.randn(B, generator=g(142)).requires_grad_(True)
+    params_old = params.detach() + torch.randn(B, 2 * Ad, generator=g(143)) * 0.2
+    actions = O.gauss_sample(params_old, torch.randn(B, Ad, generator=g(144)))
+    lp_old = O.gauss_log_prob(params_old, actions) + torch.randn(B, generator=g(145)) * 0.05
+    v_old = values.detach() + torch.randn(B, generator=g(146)) * 0.3
+    adv = torch.randn(B, generator=g(147)) * 2 + 0.5
+    targets = torch.randn(B, generator=g(148))
+    valids = torch.rand(B, generator=g(149)) >= frac_invalid
+    num_invalids = int((~valids).sum())
+
+    clip_hi = 1.0 + cfg.ppo_clip_ratio
+    clip_lo = 1.0 / clip_hi
+    lp = O.gauss_log_prob(params, actions)
+    ratio = torch.clamp(torch.exp(lp - lp_old), 0.05, 20.0)
+    adv_std, adv_mean = torch.std_mean(O._masked_select(adv, valids, num_invalids))
+    advn = (adv - adv_mean) / torch.clamp_min(adv_std, 1e-7)
+    pl = -O._masked_select(torch.min(ratio * advn, torch.clamp(ratio, clip_lo, clip_hi) * advn), valids, num_invalids).mean()
+    ent = O._masked_select(O.gauss_entropy(params), valids, num_invalids)
+    el = -cfg.exploration_loss_coeff * ent.mean()
+    kl_old = O._masked_select(O.gauss_kl(params, params_old), valids, num_invalids)
+    kl = cfg.kl_loss_coeff * kl_old.mean()
+    vc = v_old + torch.clamp(values - v_old, -cfg.ppo_clip_value, cfg.ppo_clip_value)
+    vl = O._masked_select(torch.max((values - targets) ** 2, (vc - targets) ** 2), valids, num_invalids).mean() * cfg.value_loss_coeff
+    total = pl + el + kl + vl
+    total.backward()
+
+    stats = torch.zeros(ops.LS_SIZE, dtype=torch.float64, device=dev)
+    ws = torch.empty(ops.loss_workspace_bytes(B) // 8 + 8, dtype=torch.float64, device=dev)
+    dl = torch.empty(B, n_lin, device=dev)
+    dls = None if adaptive else torch.empty(B, Ad, device=dev)
+    dv = torch.empty(B, device=dev)
+    ops.adv_stats(adv.to(dev), valids.to(dev), stats, None, ws)
+    ops.ppo_loss_fwd_bwd_continuous(params.detach().to(dev).contiguous(), values.detach().to(dev), adaptive, tanh_scale,
+                                    actions.to(dev).contiguous(), lp_old.to(dev), v_old.to(dev), adv.to(dev), targets.to(dev),
+                                    valids.to(dev), params_old.to(dev).contiguous(), cfg.ppo_clip_ratio, cfg.ppo_clip_value,
+                                    cfg.exploration_loss_coeff, cfg.value_loss_coeff, cfg.kl_loss_coeff, 1.0, dl, dls, dv,
+                                    stats, ws)
+    s = stats.cpu()
+    LS = ops.LS
+    for key, ref in [("policy_loss", pl), ("value_loss", vl), ("exploration_loss", el), ("kl_loss", kl),
+                     ("kl_old_mean", kl_old.mean()), ("kl_old_max", kl_old.max()), ("total_loss", total)]:
+        assert abs(s[LS[key]].item() - float(ref)) < TOL + 1e-5 * abs(float(ref)), (key, s[LS[key]].item(), float(ref))
+    np.testing.assert_allclose(dl.cpu().numpy(), z.grad.numpy(), atol=2e-7, rtol=5e-4)
+    np.testing.assert_allclose(dv.cpu().numpy(), values.grad.numpy(), atol=1e-7, rtol=2e-4)
+    if not adaptive:
+        np.testing.assert_allclose(dls.cpu().sum(0).numpy(), learned.grad.numpy(), atol=1e-6, rtol=5e-4)
+    else:
+        assert dl[0, Ad].item() == 0.0 and dl[1, Ad].item() == 0.0    # clamped stddev passes no gradient
+    assert torch.all(dl.cpu()[~valids] == 0) and torch.all(dv.cpu()[~valids] == 0)
+    # V-trace pre-pass
+    out = torch.empty(B, device=dev)
+    ops.action_ratio_continuous(params.detach().to(dev).contiguous(), actions.to(dev).contiguous(), lp_old.to(dev), out)
+    np.testing.assert_allclose(out.cpu().numpy(), ratio.detach().numpy(), rtol=2e-5, atol=1e-6)
