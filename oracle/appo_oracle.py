@@ -75,6 +75,10 @@ class OracleCfg:
     reward_clip: float = 1000.0
     max_policy_lag: int = 1000
     policy_id: int = 0
+    # image observations: obs_shape = (C, H, W) selects the ConvEncoder (model/encoder.py:88-145), obs_dim = C*H*W
+    obs_shape: Optional[Tuple[int, int, int]] = None
+    encoder_conv_architecture: str = "convnet_atari"                       # cfg.py:506-517
+    encoder_conv_mlp_layers: List[int] = field(default_factory=lambda: [512])   # cfg.py:520-526
     use_rnn: bool = False      # model/core.py:19-64 (ModelCoreRNN) between encoder and decoder
     rnn_type: str = "gru"
     rnn_size: int = 512
@@ -83,6 +87,39 @@ class OracleCfg:
 # --------------------------------------------------------------------------------------
 # Parameter naming = reference state_dict keys (model/actor_critic.py:136-158, encoder.py:72-84)
 # --------------------------------------------------------------------------------------
+CONV_ARCH = {  # model/encoder.py:127-134: (out_channels, kernel, stride) per Conv2d, input channels chain from obs
+    "convnet_simple": [(32, 8, 4), (64, 4, 2), (128, 3, 2)],
+    "convnet_impala": [(16, 8, 4), (32, 4, 2)],
+    "convnet_atari": [(32, 8, 4), (64, 4, 2), (64, 3, 1)],
+}
+
+
+def conv_w(i: int) -> str:
+    return f"encoder.encoders.obs.enc.conv_head.{2 * i}.weight"   # Sequential(Conv2d, act, Conv2d, act, ...)
+
+
+def conv_b(i: int) -> str:
+    return f"encoder.encoders.obs.enc.conv_head.{2 * i}.bias"
+
+
+def conv_fc_w(i: int) -> str:
+    return f"encoder.encoders.obs.enc.mlp_layers.{2 * i}.weight"
+
+
+def conv_fc_b(i: int) -> str:
+    return f"encoder.encoders.obs.enc.mlp_layers.{2 * i}.bias"
+
+
+def conv_out_shapes(cfg: "OracleCfg") -> List[Tuple[int, int, int]]:
+    """(C, H, W) after every conv layer (no padding: out = (in - k) // s + 1)"""
+    c, h, w = cfg.obs_shape
+    out = []
+    for (co, k, s_) in CONV_ARCH[cfg.encoder_conv_architecture]:
+        h, w = (h - k) // s_ + 1, (w - k) // s_ + 1
+        out.append((co, h, w))
+    return out
+
+
 def enc_w(i: int) -> str:
     return f"encoder.encoders.obs.mlp_head.{2 * i}.weight"
 
@@ -121,8 +158,14 @@ RET_MEAN, RET_VAR, RET_COUNT = (
 def param_names(cfg: OracleCfg) -> List[str]:
     """Trainable parameter order == nn.Module.parameters() order of the reference model."""
     names = []
-    for i in range(len(cfg.encoder_mlp_layers)):
-        names += [enc_w(i), enc_b(i)]
+    if cfg.obs_shape is not None:
+        for i in range(len(CONV_ARCH[cfg.encoder_conv_architecture])):
+            names += [conv_w(i), conv_b(i)]
+        for i in range(len(cfg.encoder_conv_mlp_layers)):
+            names += [conv_fc_w(i), conv_fc_b(i)]
+    else:
+        for i in range(len(cfg.encoder_mlp_layers)):
+            names += [enc_w(i), enc_b(i)]
     if cfg.use_rnn:
         names += [RNN_W_IH, RNN_W_HH, RNN_B_IH, RNN_B_HH]
     for i in range(len(cfg.decoder_mlp_layers)):
@@ -166,10 +209,23 @@ def init_state(cfg: OracleCfg, seed: int = 0) -> Dict[str, Tensor]:
     g = torch.Generator().manual_seed(seed)
     st: Dict[str, Tensor] = {}
     d = cfg.obs_dim
-    for i, h in enumerate(cfg.encoder_mlp_layers):
-        st[enc_w(i)] = torch.randn(h, d, generator=g) / math.sqrt(d)
-        st[enc_b(i)] = torch.randn(h, generator=g) * 0.01
-        d = h
+    if cfg.obs_shape is not None:
+        ci = cfg.obs_shape[0]
+        for i, (co, k, _s) in enumerate(CONV_ARCH[cfg.encoder_conv_architecture]):
+            st[conv_w(i)] = torch.randn(co, ci, k, k, generator=g) / math.sqrt(ci * k * k)
+            st[conv_b(i)] = torch.randn(co, generator=g) * 0.01
+            ci = co
+        c_, h_, w_ = conv_out_shapes(cfg)[-1]
+        d = c_ * h_ * w_
+        for i, h in enumerate(cfg.encoder_conv_mlp_layers):
+            st[conv_fc_w(i)] = torch.randn(h, d, generator=g) / math.sqrt(d)
+            st[conv_fc_b(i)] = torch.randn(h, generator=g) * 0.01
+            d = h
+    else:
+        for i, h in enumerate(cfg.encoder_mlp_layers):
+            st[enc_w(i)] = torch.randn(h, d, generator=g) / math.sqrt(d)
+            st[enc_b(i)] = torch.randn(h, generator=g) * 0.01
+            d = h
     if cfg.use_rnn:
         H, G = cfg.rnn_size, (4 if cfg.rnn_type == "lstm" else 3)
         k = 1.0 / math.sqrt(H)
@@ -259,7 +315,16 @@ def _act(cfg: OracleCfg, x: Tensor) -> Tensor:
 
 
 def encoder_forward(cfg: OracleCfg, st: Dict[str, Tensor], x: Tensor) -> Tensor:
-    """forward_head (actor_critic.py:160-162): MlpEncoder."""
+    """forward_head (actor_critic.py:160-162): MlpEncoder, or ConvEncoder (encoder.py:88-118) for image observations
+    (x arrives as flat [B, C*H*W] rows in CHW order, the layout of the trajectory buffers)."""
+    if cfg.obs_shape is not None:
+        h = x.view(x.shape[0], *cfg.obs_shape)
+        for i, (_co, _k, s_) in enumerate(CONV_ARCH[cfg.encoder_conv_architecture]):
+            h = _act(cfg, torch.nn.functional.conv2d(h, st[conv_w(i)], st[conv_b(i)], stride=s_))
+        h = h.contiguous().view(h.shape[0], -1)   # :115 (C, H, W) flatten order
+        for i in range(len(cfg.encoder_conv_mlp_layers)):
+            h = _act(cfg, torch.nn.functional.linear(h, st[conv_fc_w(i)], st[conv_fc_b(i)]))
+        return h
     h = x
     for i in range(len(cfg.encoder_mlp_layers)):
         h = _act(cfg, torch.nn.functional.linear(h, st[enc_w(i)], st[enc_b(i)]))
@@ -413,7 +478,10 @@ def alloc_trajectories(cfg: OracleCfg, num_traj: int) -> Dict[str, Tensor]:
     """shared_buffers.py:79-117 layout (single 'obs' key, rnn placeholder size 1 -- model_utils.py:11-24)."""
     T, B = cfg.rollout, num_traj
     t: Dict[str, Tensor] = {}
-    t["obs"] = torch.full((B, T + 1, cfg.obs_dim), -4242.42)
+    if cfg.obs_shape is not None:   # image observations keep the env's dtype (uint8), shared_buffers.py:88-96
+        t["obs"] = torch.zeros((B, T + 1, cfg.obs_dim), dtype=torch.uint8)
+    else:
+        t["obs"] = torch.full((B, T + 1, cfg.obs_dim), -4242.42)
     t["rnn_states"] = torch.full((B, T + 1, rnn_state_size(cfg)), -4242.42)
     t["actions"] = torch.full((B, T, action_width(cfg)), -4242.42)
     t["action_logits"] = torch.full((B, T, num_action_params(cfg)), -4242.42)

@@ -216,24 +216,51 @@ __device__ __forceinline__ float act_bwd_ct(float h) {
     return 1.f;
 }
 
+// 256-bit global accesses (sm_100 LDG/STG.256): a lane of the epilogue owns a whole row segment, so a warp-wide 128-bit
+// store touches 32 different 128 B lines with half a sector each -- every 32 B sector was written twice (ncu: 2x the
+// ideal sector count on the store path, the limiter of the short-K layers).  One 32 B store per lane = one full sector.
+__device__ __forceinline__ void st_global_v8(float* p, float a0, float a1, float a2, float a3, float a4, float a5, float a6,
+                                             float a7) {
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(a0), "f"(a1), "f"(a2), "f"(a3), "f"(a4),
+                 "f"(a5), "f"(a6), "f"(a7)
+                 : "memory");
+}
+__device__ __forceinline__ void ld_global_v8(const float* p, float4& lo, float4& hi) {
+    asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(lo.x), "=f"(lo.y), "=f"(lo.z), "=f"(lo.w), "=f"(hi.x), "=f"(hi.y), "=f"(hi.z), "=f"(hi.w)
+                 : "l"(p));
+}
+
 // one output row segment (BN columns, fully in bounds, 16 B aligned) with the epilogue resolved at compile time
 template <int MODE, int ACT, int BN>
 __device__ __forceinline__ void write_row(const float (&acc)[BN], float* __restrict__ dst, const float* bias_n0,
-                                          const float4 (&auxv)[BN / 4]) {
+                                          const float4 (&auxv)[BN / 4], bool v8) {
 #pragma unroll
-    for (int j = 0; j < BN; j += 4) {
-        float4 o = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
-        if (MODE == 1) {
-            if (bias_n0) {
-                const float4 b = *reinterpret_cast<const float4*>(bias_n0 + j);   // shared (staged) or global
-                o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+    for (int j = 0; j < BN; j += 8) {
+        float4 o[2];
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+            const int jj = j + 4 * hf;
+            o[hf] = make_float4(acc[jj], acc[jj + 1], acc[jj + 2], acc[jj + 3]);
+            if (MODE == 1) {
+                if (bias_n0) {
+                    const float4 b = *reinterpret_cast<const float4*>(bias_n0 + jj);   // shared (staged) or global
+                    o[hf].x += b.x; o[hf].y += b.y; o[hf].z += b.z; o[hf].w += b.w;
+                }
+                o[hf].x = act_fwd_ct<ACT>(o[hf].x); o[hf].y = act_fwd_ct<ACT>(o[hf].y);
+                o[hf].z = act_fwd_ct<ACT>(o[hf].z); o[hf].w = act_fwd_ct<ACT>(o[hf].w);
+            } else if (MODE == 2) {
+                const float4 h = auxv[jj / 4];
+                o[hf].x *= act_bwd_ct<ACT>(h.x); o[hf].y *= act_bwd_ct<ACT>(h.y);
+                o[hf].z *= act_bwd_ct<ACT>(h.z); o[hf].w *= act_bwd_ct<ACT>(h.w);
             }
-            o.x = act_fwd_ct<ACT>(o.x); o.y = act_fwd_ct<ACT>(o.y); o.z = act_fwd_ct<ACT>(o.z); o.w = act_fwd_ct<ACT>(o.w);
-        } else if (MODE == 2) {
-            const float4 h = auxv[j / 4];
-            o.x *= act_bwd_ct<ACT>(h.x); o.y *= act_bwd_ct<ACT>(h.y); o.z *= act_bwd_ct<ACT>(h.z); o.w *= act_bwd_ct<ACT>(h.w);
         }
-        *reinterpret_cast<float4*>(dst + j) = o;
+        if (v8) {
+            st_global_v8(dst + j, o[0].x, o[0].y, o[0].z, o[0].w, o[1].x, o[1].y, o[1].z, o[1].w);
+        } else {
+            *reinterpret_cast<float4*>(dst + j) = o[0];
+            *reinterpret_cast<float4*>(dst + j + 4) = o[1];
+        }
     }
 }
 
@@ -257,7 +284,7 @@ __device__ __forceinline__ TileCoord tile_coord(int tile, int tiles_n, int tiles
 
 struct EpiCtx {
     int lane_base, lane, col0, mode;
-    bool vec_ok, aux_vec, bias_vec;
+    bool vec_ok, aux_vec, bias_vec, st_v8, aux_v8;
     const float* bias_base;
 };
 
@@ -274,6 +301,8 @@ __device__ __forceinline__ EpiCtx make_epi_ctx(int warp, int lane, const float* 
     ec.col0 = ((warp - 6) >> 2) * (BN / 2);
     ec.vec_ok = (ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15u) == 0);
     ec.aux_vec = epi.aux && (epi.ld_aux % 4 == 0) && ((reinterpret_cast<uintptr_t>(epi.aux) & 15u) == 0);
+    ec.st_v8 = (ldc % 8 == 0) && ((reinterpret_cast<uintptr_t>(C) & 31u) == 0);
+    ec.aux_v8 = epi.aux && (epi.ld_aux % 8 == 0) && ((reinterpret_cast<uintptr_t>(epi.aux) & 31u) == 0);
     const bool bias_smem = epi.bias != nullptr && N <= bias_floats;
     if (bias_smem) {
         for (int i = threadIdx.x - 192; i < N; i += 256) bias_s[i] = epi.bias[i];
@@ -331,9 +360,15 @@ __device__ __forceinline__ void tc_epilogue_tile(uint32_t tmem_slot_addr, uint64
     // (hides its HBM latency behind the main loop of this tile).
     const float* aux_row = (mode == 2 && fast) ? epi.aux + m * epi.ld_aux + nbeg : nullptr;
     float4 auxv[8];
+    const bool aux_v8 = ec.aux_v8, st_v8 = ec.st_v8 && splits == 1;
     if (aux_row) {
+        if (aux_v8) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) auxv[j] = *reinterpret_cast<const float4*>(aux_row + 4 * j);
+            for (int j = 0; j < 8; j += 2) ld_global_v8(aux_row + 4 * j, auxv[j], auxv[j + 1]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) auxv[j] = *reinterpret_cast<const float4*>(aux_row + 4 * j);
+        }
     }
     float acc_all[CH];
     tmem_drain<BN, CH, SPLIT3>(tmem_slot_addr + ((uint32_t)lane_base << 16) + (uint32_t)col0, acc_all, acc_full_bar, acc_ph,
@@ -345,8 +380,13 @@ __device__ __forceinline__ void tc_epilogue_tile(uint32_t tmem_slot_addr, uint64
     for (int c0 = 0; c0 < CH; c0 += 32) {
         const float (&acc)[32] = reinterpret_cast<const float (&)[32]>(acc_all[c0]);
         if (c0 > 0 && aux_row) {
+            if (aux_v8) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) auxv[j] = *reinterpret_cast<const float4*>(aux_row + c0 + 4 * j);
+                for (int j = 0; j < 8; j += 2) ld_global_v8(aux_row + c0 + 4 * j, auxv[j], auxv[j + 1]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) auxv[j] = *reinterpret_cast<const float4*>(aux_row + c0 + 4 * j);
+            }
         }
         float* dst = dst_row + c0;
         if (fast) {
@@ -355,20 +395,20 @@ __device__ __forceinline__ void tc_epilogue_tile(uint32_t tmem_slot_addr, uint64
             const float* bias_n0 = epi.bias ? bias_base + nbeg + c0 : nullptr;
             if (mode == 1) {
                 switch (epi.act) {
-                    case SFB200_ACT_ELU: write_row<1, SFB200_ACT_ELU, 32>(acc, dst, bias_n0, auxv); break;
-                    case SFB200_ACT_RELU: write_row<1, SFB200_ACT_RELU, 32>(acc, dst, bias_n0, auxv); break;
-                    case SFB200_ACT_TANH: write_row<1, SFB200_ACT_TANH, 32>(acc, dst, bias_n0, auxv); break;
-                    default: write_row<1, SFB200_ACT_NONE, 32>(acc, dst, bias_n0, auxv); break;
+                    case SFB200_ACT_ELU: write_row<1, SFB200_ACT_ELU, 32>(acc, dst, bias_n0, auxv, st_v8); break;
+                    case SFB200_ACT_RELU: write_row<1, SFB200_ACT_RELU, 32>(acc, dst, bias_n0, auxv, st_v8); break;
+                    case SFB200_ACT_TANH: write_row<1, SFB200_ACT_TANH, 32>(acc, dst, bias_n0, auxv, st_v8); break;
+                    default: write_row<1, SFB200_ACT_NONE, 32>(acc, dst, bias_n0, auxv, st_v8); break;
                 }
             } else if (mode == 2) {
                 switch (epi.act) {
-                    case SFB200_ACT_ELU: write_row<2, SFB200_ACT_ELU, 32>(acc, dst, bias_n0, auxv); break;
-                    case SFB200_ACT_RELU: write_row<2, SFB200_ACT_RELU, 32>(acc, dst, bias_n0, auxv); break;
-                    case SFB200_ACT_TANH: write_row<2, SFB200_ACT_TANH, 32>(acc, dst, bias_n0, auxv); break;
-                    default: write_row<0, SFB200_ACT_NONE, 32>(acc, dst, bias_n0, auxv); break;
+                    case SFB200_ACT_ELU: write_row<2, SFB200_ACT_ELU, 32>(acc, dst, bias_n0, auxv, st_v8); break;
+                    case SFB200_ACT_RELU: write_row<2, SFB200_ACT_RELU, 32>(acc, dst, bias_n0, auxv, st_v8); break;
+                    case SFB200_ACT_TANH: write_row<2, SFB200_ACT_TANH, 32>(acc, dst, bias_n0, auxv, st_v8); break;
+                    default: write_row<0, SFB200_ACT_NONE, 32>(acc, dst, bias_n0, auxv, st_v8); break;
                 }
             } else {
-                write_row<0, SFB200_ACT_NONE, 32>(acc, dst, bias_n0, auxv);
+                write_row<0, SFB200_ACT_NONE, 32>(acc, dst, bias_n0, auxv, st_v8);
             }
         } else {
 #pragma unroll   // fully unrolled so that acc[] stays in registers (no dynamic indexing)
@@ -408,13 +448,23 @@ __device__ __forceinline__ void tc_epilogue_tile_heads(uint32_t tmem_slot_addr, 
     float* dst_row = C ? C + m * ldc + nbeg : nullptr;
     const float* bias_n0 = ec.bias_base + nbeg;   // staged in shared memory (host guarantees N <= BIAS_FLOATS)
 #pragma unroll
-    for (int j = 0; j < CH; j += 4) {
-        const float4 b = *reinterpret_cast<const float4*>(bias_n0 + j);
-        o[j] = act_fwd_ct<ACT>(o[j] + b.x);
-        o[j + 1] = act_fwd_ct<ACT>(o[j + 1] + b.y);
-        o[j + 2] = act_fwd_ct<ACT>(o[j + 2] + b.z);
-        o[j + 3] = act_fwd_ct<ACT>(o[j + 3] + b.w);
-        if (dst_row) *reinterpret_cast<float4*>(dst_row + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+    for (int j = 0; j < CH; j += 8) {
+#pragma unroll
+        for (int jj = j; jj < j + 8; jj += 4) {
+            const float4 b = *reinterpret_cast<const float4*>(bias_n0 + jj);
+            o[jj] = act_fwd_ct<ACT>(o[jj] + b.x);
+            o[jj + 1] = act_fwd_ct<ACT>(o[jj + 1] + b.y);
+            o[jj + 2] = act_fwd_ct<ACT>(o[jj + 2] + b.z);
+            o[jj + 3] = act_fwd_ct<ACT>(o[jj + 3] + b.w);
+        }
+        if (dst_row) {
+            if (ec.st_v8) {
+                st_global_v8(dst_row + j, o[j], o[j + 1], o[j + 2], o[j + 3], o[j + 4], o[j + 5], o[j + 6], o[j + 7]);
+            } else {
+                *reinterpret_cast<float4*>(dst_row + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+                *reinterpret_cast<float4*>(dst_row + j + 4) = make_float4(o[j + 4], o[j + 5], o[j + 6], o[j + 7]);
+            }
+        }
     }
 #pragma unroll
     for (int a = 0; a < kHeadAP; ++a) {

@@ -7,7 +7,7 @@
 
 namespace sfb {
 
-constexpr int kHeadsMaxGroups = 512;
+constexpr int kHeadsMaxGroups = 1024;
 
 
 struct HeadsOut {
@@ -311,10 +311,12 @@ __global__ void __launch_bounds__(256) heads_backward_kernel(
     if (tid < n_out) my_part[(int64_t)(A + 2) * H + tid] = acc_g;
 }
 
-// Vectorised variant (H % 4 == 0, H/4 divides 256): a thread owns 4 consecutive columns (128-bit loads/stores) and
-// every RPB-th row of the group; row-lane partials are combined through shared memory at the end.
-template <int AP>
-__global__ void __launch_bounds__(256) heads_backward_vec4_kernel(
+// Vectorised variant: a thread owns VW (4 or 2) consecutive columns (128- / 64-bit loads and stores) and every RPB-th
+// row of the group; row-lane partials are combined through shared memory at the end.  VW = 2 halves the per-thread
+// register state (weights + 9 weight-gradient accumulators per column), which lets four blocks reside per SM with eight
+// row loads in flight per thread: this kernel is HBM-latency bound (reads h, writes dz: 8*H bytes per row).
+template <int AP, int VW, int UNROLL, int MINB>
+__global__ void __launch_bounds__(256, MINB) heads_backward_vec_kernel(
     const float* __restrict__ h, int64_t ldh, int64_t rows, int H, int A, const float* __restrict__ Wv,
     const float* __restrict__ Wa, const float* __restrict__ dlogits, const float* __restrict__ dvalues, int act,
     float* __restrict__ dz, int64_t lddz, float* __restrict__ part, int64_t rows_per_group) {
@@ -322,22 +324,26 @@ __global__ void __launch_bounds__(256) heads_backward_vec4_kernel(
     extern __shared__ float red_s[];   // [(A+2)][H] cross-row-lane reduction
     const int n_out = A + 1;
     const int tid = threadIdx.x;
-    const int TPR = H >> 2, RPB = 256 / TPR;
-    const int c4 = tid % TPR, rl = tid / TPR;
-    const int j = c4 << 2;
+    const int TPR = H / VW, RPB = 256 / TPR;
+    const int cv = tid % TPR, rl = tid / TPR;
+    const int j = cv * VW;
     const int64_t r_begin = blockIdx.x * rows_per_group;
     const int64_t r_end = (r_begin + rows_per_group < rows) ? r_begin + rows_per_group : rows;
     const int64_t part_stride = (int64_t)(A + 2) * H + n_out;
     float* my_part = part + blockIdx.x * part_stride;
 
-    float4 w[AP], accw[AP];
+    float w[AP][VW], accw[AP][VW];
 #pragma unroll
     for (int a = 0; a < AP; ++a) {
-        accw[a] = make_float4(0.f, 0.f, 0.f, 0.f);
-        w[a] = (a < n_out) ? *reinterpret_cast<const float4*>((a == 0 ? Wv : Wa + (int64_t)(a - 1) * H) + j)
-                           : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int c = 0; c < VW; ++c) {
+            accw[a][c] = 0.f;
+            w[a][c] = (a < n_out) ? (a == 0 ? Wv[j + c] : Wa[(int64_t)(a - 1) * H + j + c]) : 0.f;
+        }
     }
-    float4 acc_db = make_float4(0.f, 0.f, 0.f, 0.f);
+    float acc_db[VW];
+#pragma unroll
+    for (int c = 0; c < VW; ++c) acc_db[c] = 0.f;
     float acc_g = 0.f;
     for (int64_t b0 = r_begin; b0 < r_end; b0 += kHbTile) {
         const int nb = (int)((r_end - b0 < kHbTile) ? (r_end - b0) : kHbTile);
@@ -351,25 +357,38 @@ __global__ void __launch_bounds__(256) heads_backward_vec4_kernel(
         __syncthreads();
         if (tid < n_out)
             for (int bb = 0; bb < nb; ++bb) acc_g += g_s[bb][tid];
-#pragma unroll 4
+#pragma unroll UNROLL
         for (int bb = rl; bb < nb; bb += RPB) {
-            const float4 hv = *reinterpret_cast<const float4*>(h + (b0 + bb) * ldh + j);
-            float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+            float hv[VW];
+            if (VW == 4) {
+                const float4 q = *reinterpret_cast<const float4*>(h + (b0 + bb) * ldh + j);
+                hv[0] = q.x; hv[1] = q.y; hv[VW - 2] = q.z; hv[VW - 1] = q.w;
+            } else {
+                const float2 q = *reinterpret_cast<const float2*>(h + (b0 + bb) * ldh + j);
+                hv[0] = q.x; hv[1] = q.y;
+            }
+            float sacc[VW];
+#pragma unroll
+            for (int c = 0; c < VW; ++c) sacc[c] = 0.f;
 #pragma unroll
             for (int a = 0; a < AP; ++a) {
                 if (a < n_out) {
                     const float g = g_s[bb][a];
-                    s.x = fmaf(g, w[a].x, s.x); s.y = fmaf(g, w[a].y, s.y);
-                    s.z = fmaf(g, w[a].z, s.z); s.w = fmaf(g, w[a].w, s.w);
-                    accw[a].x = fmaf(g, hv.x, accw[a].x); accw[a].y = fmaf(g, hv.y, accw[a].y);
-                    accw[a].z = fmaf(g, hv.z, accw[a].z); accw[a].w = fmaf(g, hv.w, accw[a].w);
+#pragma unroll
+                    for (int c = 0; c < VW; ++c) {
+                        sacc[c] = fmaf(g, w[a][c], sacc[c]);
+                        accw[a][c] = fmaf(g, hv[c], accw[a][c]);
+                    }
                 }
             }
-            float4 d;
-            d.x = s.x * act_bwd_from_out(hv.x, act); d.y = s.y * act_bwd_from_out(hv.y, act);
-            d.z = s.z * act_bwd_from_out(hv.z, act); d.w = s.w * act_bwd_from_out(hv.w, act);
-            *reinterpret_cast<float4*>(dz + (b0 + bb) * lddz + j) = d;
-            acc_db.x += d.x; acc_db.y += d.y; acc_db.z += d.z; acc_db.w += d.w;
+            float d[VW];
+#pragma unroll
+            for (int c = 0; c < VW; ++c) {
+                d[c] = sacc[c] * act_bwd_from_out(hv[c], act);
+                acc_db[c] += d[c];
+            }
+            if (VW == 4) *reinterpret_cast<float4*>(dz + (b0 + bb) * lddz + j) = make_float4(d[0], d[1], d[VW - 2], d[VW - 1]);
+            else *reinterpret_cast<float2*>(dz + (b0 + bb) * lddz + j) = make_float2(d[0], d[1]);
         }
     }
     // combine the RPB row lanes (fixed order -> deterministic)
@@ -379,16 +398,20 @@ __global__ void __launch_bounds__(256) heads_backward_vec4_kernel(
 #pragma unroll
             for (int a = 0; a < AP; ++a) {
                 if (a < n_out) {
-                    float4* dst = reinterpret_cast<float4*>(red_s + a * H + j);
-                    float4 v = accw[a];
-                    if (r > 0) { const float4 o = *dst; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
-                    *dst = v;
+#pragma unroll
+                    for (int c = 0; c < VW; ++c) {
+                        float v = accw[a][c];
+                        if (r > 0) v += red_s[a * H + j + c];
+                        red_s[a * H + j + c] = v;
+                    }
                 }
             }
-            float4* dst = reinterpret_cast<float4*>(red_s + n_out * H + j);
-            float4 v = acc_db;
-            if (r > 0) { const float4 o = *dst; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
-            *dst = v;
+#pragma unroll
+            for (int c = 0; c < VW; ++c) {
+                float v = acc_db[c];
+                if (r > 0) v += red_s[n_out * H + j + c];
+                red_s[n_out * H + j + c] = v;
+            }
         }
     }
     __syncthreads();
@@ -568,19 +591,25 @@ int sfb200_heads_backward(const float* h, int64_t ldh, int64_t rows, int H, int 
                   "heads_backward: bad arguments");
     SFB_CHECK_ARG(A >= 1 && A <= 31, "heads_backward: supports 1 <= A <= 31, got %d", A);
     cudaStream_t st = (cudaStream_t)stream;
-    int64_t groups = (int64_t)sm_count() * 2;   // (3 blocks/SM with deeper unrolling measured 33 % slower: 97 vs 73 us)
+    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+    const size_t red_bytes = (size_t)(A + 2) * H * sizeof(float);
+    const bool vec_common = (ldh % 4 == 0) && (lddz % 4 == 0) && al16(h) && al16(dz) && al16(Wv) && al16(Wa) &&
+                            red_bytes <= 40 * 1024 && A + 1 <= 9;
+    // two columns per thread (64 registers, 4 blocks per SM) when a row fills a whole block, else four
+    const bool vec2 = vec_common && (H % 2 == 0) && (H / 2 <= 256) && (256 % (H / 2) == 0) && rows >= 16384;
+    const bool vec4 = vec_common && (H % 4 == 0) && (H / 4 <= 256) && (256 % (H / 4) == 0);
+    int64_t groups = (int64_t)sm_count() * (vec2 ? 4 : 2);
     if (groups > kHeadsMaxGroups) groups = kHeadsMaxGroups;
     int64_t rpg = ceil_div(rows, groups);
     rpg = ceil_div(rpg, kHbTile) * kHbTile;
     groups = ceil_div(rows, rpg);
     float* part = (float*)workspace;
-    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
-    const size_t red_bytes = (size_t)(A + 2) * H * sizeof(float);
-    const bool vec4 = (H % 4 == 0) && (H / 4 <= 256) && (256 % (H / 4) == 0) && (ldh % 4 == 0) && (lddz % 4 == 0) &&
-                      al16(h) && al16(dz) && al16(Wv) && al16(Wa) && red_bytes <= 40 * 1024 && A + 1 <= 9;
-    if (vec4)
-        heads_backward_vec4_kernel<9><<<(unsigned)groups, 256, red_bytes, st>>>(h, ldh, rows, H, A, Wv, Wa, dlogits,
-                                                                               dvalues, act, dz, lddz, part, rpg);
+    if (vec2)
+        heads_backward_vec_kernel<9, 2, 8, 4><<<(unsigned)groups, 256, red_bytes, st>>>(h, ldh, rows, H, A, Wv, Wa, dlogits,
+                                                                                        dvalues, act, dz, lddz, part, rpg);
+    else if (vec4)
+        heads_backward_vec_kernel<9, 4, 4, 2><<<(unsigned)groups, 256, red_bytes, st>>>(h, ldh, rows, H, A, Wv, Wa, dlogits,
+                                                                                        dvalues, act, dz, lddz, part, rpg);
     else if (A + 1 <= 9)
         heads_backward_kernel<9><<<(unsigned)groups, 256, 0, st>>>(h, ldh, rows, H, A, Wv, Wa, dlogits, dvalues, act, dz,
                                                                    lddz, part, rpg);

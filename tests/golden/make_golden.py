@@ -50,38 +50,48 @@ OUT_DIR = os.path.dirname(os.path.abspath(__file__))
 class RefTapeEnv(gym.Env):
     """Adapter: TapeVecEnv behind the reference's batched-env contract (make_env.py:147-237)."""
 
-    def __init__(self, tape_env: TapeVecEnv, continuous: bool = False):
+    def __init__(self, tape_env: TapeVecEnv, continuous: bool = False, obs_shape=None):
         self.e = tape_env
+        self.obs_shape = obs_shape
         self.num_agents = tape_env.num_agents
         self.is_multiagent = True
         self.observation_space = gym.spaces.Dict(
             {"obs": gym.spaces.Box(-np.inf, np.inf, (tape_env.obs_dim,), np.float32)}
         )
         self.action_space = gym.spaces.Discrete(tape_env.num_actions)
+        if obs_shape is not None:   # uint8 image observations (C, H, W) -> ConvEncoder (model/encoder.py:88-145)
+            self.observation_space = gym.spaces.Dict({"obs": gym.spaces.Box(0, 255, tuple(obs_shape), np.uint8)})
         if continuous:   # Box(A) action space -> ContinuousActionDistribution (action_distributions.py:290-323)
             self.action_space = gym.spaces.Box(-1.0, 1.0, (tape_env.num_actions,), np.float32)
 
+    def _obs(self, o):
+        return o.clone() if self.obs_shape is None else o.view(self.num_agents, *self.obs_shape).clone()
+
     def reset(self, **kw):
-        return {"obs": self.e.reset().clone()}, {}
+        return {"obs": self._obs(self.e.reset())}, {}
 
     def step(self, actions):
         obs, rew, term, trunc = self.e.step(torch.as_tensor(actions))  # numpy int32 / float32 (batched_sampling.py:62-82)
-        return {"obs": obs.clone()}, rew, term, trunc, {}
+        return {"obs": self._obs(obs)}, rew, term, trunc, {}
 
     def close(self):
         pass
 
 
 def run_case(name: str, N: int, T: int, obs_dim: int, A: int, hidden, iters: int, overrides: dict, poison: bool,
-             save_checkpoint: bool = False, continuous: bool = False):
+             save_checkpoint: bool = False, continuous: bool = False, obs_shape=None):
     torch.manual_seed(1234)
     np.random.seed(1234)
     tape_len = T * iters + 1
-    tape = torch.randn(tape_len, N, obs_dim) * 1.5 + 0.3
+    if obs_shape is not None:
+        assert obs_dim == int(np.prod(obs_shape))
+        tape = torch.randint(0, 256, (tape_len, N, obs_dim), dtype=torch.uint8)
+    else:
+        tape = torch.randn(tape_len, N, obs_dim) * 1.5 + 0.3
     tape_env = TapeVecEnv(tape, A)
 
     env_name = f"tape_{name}"
-    register_env(env_name, lambda full_env_name, cfg, env_config, render_mode=None: RefTapeEnv(tape_env, continuous))
+    register_env(env_name, lambda full_env_name, cfg, env_config, render_mode=None: RefTapeEnv(tape_env, continuous, obs_shape))
 
     cfg = default_cfg(env=env_name, experiment=f"golden_{name}")
     cfg.device = "cpu"
@@ -201,7 +211,7 @@ def run_case(name: str, N: int, T: int, obs_dim: int, A: int, hidden, iters: int
         for k in ["actions", "action_logits", "log_prob_actions", "values", "policy_version", "rewards", "dones",
                   "time_outs", "policy_id", "rnn_states"]:
             pre[k] = batch[k].clone().numpy()
-        pre["obs"] = batch["obs"]["obs"].clone().numpy()
+        pre["obs"] = batch["obs"]["obs"].clone().numpy().reshape(N, T + 1, -1)
         for k, v in pre.items():
             out[f"it{it}/traj/{k}"] = v
         out[f"it{it}/noise"] = torch.stack(noise_steps).numpy()
@@ -246,7 +256,7 @@ def run_case(name: str, N: int, T: int, obs_dim: int, A: int, hidden, iters: int
         print("checkpoint fixture:", os.path.basename(files[-1]))
 
     meta = dict(N=N, T=T, obs_dim=obs_dim, A=A, hidden=list(hidden), iters=iters, poison=poison, continuous=continuous,
-                **overrides)
+                obs_shape=None if obs_shape is None else tuple(obs_shape), **overrides)
     out["meta"] = np.array(repr(meta))
     # a few flags the oracle needs, straight from the reference cfg object
     for k in ["gamma", "gae_lambda", "ppo_clip_ratio", "ppo_clip_value", "exploration_loss_coeff", "value_loss_coeff",
@@ -254,9 +264,11 @@ def run_case(name: str, N: int, T: int, obs_dim: int, A: int, hidden, iters: int
               "reward_scale", "reward_clip", "max_policy_lag", "batch_size", "num_batches_per_epoch", "num_epochs",
               "recurrence", "vtrace_rho", "vtrace_c"]:
         out[f"cfg/{k}"] = np.float64(getattr(cfg, k))
-    for k in ["continuous_tanh_scale", "initial_stddev"]:
+    for k in ["continuous_tanh_scale", "initial_stddev", "obs_scale", "obs_subtract_mean"]:
         out[f"cfg/{k}"] = np.float64(getattr(cfg, k))
     out["cfg/nonlinearity"] = np.array(cfg.nonlinearity)
+    out["cfg/encoder_conv_architecture"] = np.array(cfg.encoder_conv_architecture)
+    out["cfg/encoder_conv_mlp_layers"] = np.array(list(cfg.encoder_conv_mlp_layers), dtype=np.int64)
     out["cfg/continuous"] = np.bool_(continuous)
     for k in ["normalize_input", "normalize_returns", "value_bootstrap", "with_vtrace", "use_rnn", "adaptive_stddev"]:
         out[f"cfg/{k}"] = np.bool_(getattr(cfg, k))
@@ -344,6 +356,16 @@ if __name__ == "__main__":
         "tiny_gauss_adaptive", N=32, T=8, obs_dim=16, A=6, hidden=[64, 64], iters=2,
         overrides=dict(batch_size=128, num_batches_per_epoch=2, num_epochs=1, kl_loss_coeff=0.05),
         poison=False, continuous=True,
+    )
+    # image observations (BASELINE cfg-4, atari-style flags sf_examples/atari/atari_params.py:1-45): uint8 [4, 44, 44]
+    # frames, convnet_atari (32@8s4, 64@4s2, 64@3s1) + FC 128, ReLU, obs_scale=255, per-pixel input normalisation,
+    # 2 epochs x 2 minibatches, small grad-norm clip
+    run_case(
+        "tiny_conv", N=8, T=8, obs_dim=4 * 44 * 44, A=6, hidden=[], iters=2,
+        overrides=dict(batch_size=32, num_batches_per_epoch=2, num_epochs=2, nonlinearity="relu", obs_scale=255.0,
+                       encoder_conv_architecture="convnet_atari", encoder_conv_mlp_layers=[128],
+                       exploration_loss_coeff=0.01, max_grad_norm=0.5, adam_eps=1e-5, ppo_clip_ratio=0.1),
+        poison=True, obs_shape=(4, 44, 44),
     )
     # cfg-2 hyper-parameters and model (300 553 params) at a reduced env count
     run_case(

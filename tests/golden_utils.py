@@ -13,7 +13,8 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 def load_case(name):
     z = np.load(os.path.join(GOLDEN_DIR, f"{name}.npz"), allow_pickle=False)
     meta = ast.literal_eval(str(z["meta"]))
-    c = {k[4:]: z[k].item() for k in z.files if k.startswith("cfg/") and k not in ("cfg/rnn_type", "cfg/nonlinearity")}
+    _arrays = ("cfg/rnn_type", "cfg/nonlinearity", "cfg/encoder_conv_architecture", "cfg/encoder_conv_mlp_layers")
+    c = {k[4:]: z[k].item() for k in z.files if k.startswith("cfg/") and k not in _arrays}
     cfg = O.OracleCfg(
         obs_dim=meta["obs_dim"], num_actions=meta["A"], encoder_mlp_layers=list(meta["hidden"]),
         rollout=meta["T"], recurrence=int(c["recurrence"]), batch_size=int(c["batch_size"]),
@@ -31,13 +32,23 @@ def load_case(name):
         nonlinearity=str(z["cfg/nonlinearity"]) if "cfg/nonlinearity" in z.files else "elu",
         continuous=bool(c.get("continuous", False)), adaptive_stddev=bool(c.get("adaptive_stddev", True)),
         continuous_tanh_scale=float(c.get("continuous_tanh_scale", 0.0)), initial_stddev=float(c.get("initial_stddev", 1.0)),
+        obs_scale=float(c.get("obs_scale", 1.0)), obs_subtract_mean=float(c.get("obs_subtract_mean", 0.0)),
+        obs_shape=tuple(meta["obs_shape"]) if meta.get("obs_shape") else None,
+        encoder_conv_architecture=(str(z["cfg/encoder_conv_architecture"]) if "cfg/encoder_conv_architecture" in z.files
+                                   else "convnet_atari"),
+        encoder_conv_mlp_layers=([int(v) for v in z["cfg/encoder_conv_mlp_layers"]] if "cfg/encoder_conv_mlp_layers" in z.files
+                                 else [512]),
     )
     return z, meta, cfg
 
 
 def state_from(z, prefix):
     """prefix 'init/' or 'it0/state/' -> dict of torch tensors keyed by reference state_dict names."""
-    return {k[len(prefix):]: torch.from_numpy(z[k].copy()) for k in z.files if k.startswith(prefix)}
+    st = {k[len(prefix):]: torch.from_numpy(z[k].copy()) for k in z.files if k.startswith(prefix)}
+    for k in (O.OBS_MEAN, O.OBS_VAR):   # image observations: per-pixel statistics [C,H,W] -> flat, like the obs rows
+        if k in st and st[k].dim() > 1:
+            st[k] = st[k].reshape(-1)
+    return st
 
 
 def traj_from(z, it, cfg):
