@@ -305,6 +305,41 @@ int sfb200_ppo_loss_fwd_bwd_continuous(const float* params, const float* values,
                                        float grad_scale, float* dlogits, float* dlogstd, float* dvalues, double* stats,
                                        void* workspace, void* stream);
 
+/* uint8 observations (image envs: the reference converts with .float() before sub-mean / scale / running-mean-std,
+ * utils/normalize.py:40-67): the same three entry points reading uint8 rows; the raw copy into the trajectory stays
+ * uint8 (shared_buffers.py:88-96 keeps the observation space's dtype). */
+int sfb200_normalize_obs_u8(const uint8_t* x, int64_t ldx, float* y, int64_t ldy, int64_t rows, int dim,
+                            const double* mean, const double* var, float sub_mean, float inv_scale, float eps,
+                            float clip, void* stream);
+int sfb200_sampler_pre_step_u8(const uint8_t* obs, int64_t n_envs, int dim, uint8_t* traj_obs_t, int64_t traj_obs_stride,
+                               const float* rnn, int rnn_dim, float* traj_rnn_t, int64_t traj_rnn_stride, float* x_norm,
+                               const double* mean, const double* var, float sub_mean, float inv_scale, float eps,
+                               float clip, void* stream);
+int sfb200_sampler_post_pre_step_u8(const float* rew, const uint8_t* terminated, const uint8_t* truncated, int64_t n_envs,
+                                    float reward_scale, float reward_clip, int32_t policy_id, float* traj_rewards_t,
+                                    uint8_t* traj_dones_t, uint8_t* traj_time_outs_t, int32_t* traj_policy_id_t,
+                                    int64_t traj_stride, float* ep_return, int32_t* ep_len, float* ep_min_raw,
+                                    float* ep_max_raw, int32_t len_increment, double* stats, int64_t* step_counter,
+                                    float* fin_return_t, int32_t* fin_len_t,
+                                    const uint8_t* obs, int dim, uint8_t* traj_obs_next, int64_t traj_obs_stride,
+                                    const float* rnn, int rnn_dim, float* traj_rnn_next, int64_t traj_rnn_stride,
+                                    float* x_norm, const double* mean, const double* var, float sub_mean,
+                                    float inv_scale, float eps, float clip, void* stream);
+
+/* ------------------------------------------------------------- convolutional encoder ---- */
+/* ConvEncoderImpl (model/encoder.py:88-118): Conv2d without padding = im2col + sfb200_linear_act_forward.
+ *   col[(b,oh,ow), (ci,kh,kw)] = x[b, ci, oh*stride+kh, ow*stride+kw]      (column order == Conv2d weight flatten)
+ * x is NCHW [B,C,H,W] (in_nchw = 1: the normalised observation) or NHWC [B,H,W,C] (the previous layer's GEMM output);
+ * col is [B*OH*OW, C*kernel*kernel] with OH = (H-kernel)/stride+1. */
+int sfb200_im2col(const float* x, int in_nchw, int64_t B, int C, int H, int W, int kernel, int stride, float* col,
+                  void* stream);
+/* backward of im2col fused with the activation derivative of the layer that produced x_act (NHWC, activated):
+ *   dx[b,ih,iw,ci] = act'(x_act[b,ih,iw,ci]) * sum_{windows covering (ih,iw)} dcol[(b,oh,ow), (ci,kh,kw)]   (gather) */
+int sfb200_col2im_act_backward(const float* dcol, const float* x_act, int64_t B, int C, int H, int W, int kernel,
+                               int stride, int act, float* dx, void* stream);
+/* [B, P, C] <-> [B, C, P]: NHWC rows of the last conv layer <-> the (C,H,W) flatten order of encoder.py:115 */
+int sfb200_permute_bpc(const float* src, float* dst, int64_t B, int P, int C, int to_channel_major, void* stream);
+
 /* ------------------------------------------------------------- learner: backward ---- */
 int64_t sfb200_heads_backward_workspace_bytes(int H, int A);
 /* backward of critic_linear + distribution_linear fused with the activation derivative of the layer that produced h:

@@ -30,16 +30,16 @@ __device__ __forceinline__ void col_stats(const double* mean, const double* var,
 // One body serves sfb200_normalize_obs, sfb200_sampler_pre_step and the fused post+pre step: optional second output
 // (raw copy into the trajectory at [.., t]) so obs is read from HBM once.
 struct NormArgs {
-    const float* x; int64_t ldx;
-    float* y; int64_t ldy;
-    float* raw_copy; int64_t ld_copy;
+    const void* x; int64_t ldx;          // float32, or uint8 when the kernel is instantiated with U8 (image observations:
+    float* y; int64_t ldy;               // the reference converts with .float() first, normalize.py:40-46)
+    void* raw_copy; int64_t ld_copy;     // same element type as x
     int64_t rows; int dim;
     const double* mean; const double* var;
     float sub, inv_scale; int do_sub, do_scale; float eps, clip;
     const float* rnn_src; int rnn_dim; float* rnn_dst; int64_t rnn_dst_stride; int64_t rnn_rows;
 };
 
-template <bool VEC4>
+template <bool VEC4, bool U8>
 __device__ __forceinline__ void normalize_body(const NormArgs& a) {
     const bool do_rms = a.mean != nullptr;
     const int64_t tid0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -51,16 +51,27 @@ __device__ __forceinline__ void normalize_body(const NormArgs& a) {
             a.rnn_dst[r * a.rnn_dst_stride + (i - r * a.rnn_dim)] = a.rnn_src[i];
         }
     }
+    const float* xf = reinterpret_cast<const float*>(a.x);
+    const uint8_t* xb = reinterpret_cast<const uint8_t*>(a.x);
+    float* cf = reinterpret_cast<float*>(a.raw_copy);
+    uint8_t* cb = reinterpret_cast<uint8_t*>(a.raw_copy);
     if (VEC4) {
         const int dim4 = a.dim >> 2;
         const int64_t total = a.rows * (int64_t)dim4;
         for (int64_t i = tid0; i < total; i += nthr) {
             const int64_t r = i / dim4;
             const int c = (int)(i - r * dim4) << 2;
-            const float4 v = *reinterpret_cast<const float4*>(a.x + r * a.ldx + c);
-            if (a.raw_copy) *reinterpret_cast<float4*>(a.raw_copy + r * a.ld_copy + c) = v;
+            float in[4];
+            if (U8) {
+                const uchar4 v = *reinterpret_cast<const uchar4*>(xb + r * a.ldx + c);
+                if (a.raw_copy) *reinterpret_cast<uchar4*>(cb + r * a.ld_copy + c) = v;
+                in[0] = (float)v.x; in[1] = (float)v.y; in[2] = (float)v.z; in[3] = (float)v.w;
+            } else {
+                const float4 v = *reinterpret_cast<const float4*>(xf + r * a.ldx + c);
+                if (a.raw_copy) *reinterpret_cast<float4*>(cf + r * a.ld_copy + c) = v;
+                in[0] = v.x; in[1] = v.y; in[2] = v.z; in[3] = v.w;
+            }
             if (a.y) {
-                float in[4] = {v.x, v.y, v.z, v.w};
                 float out[4];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
@@ -76,8 +87,15 @@ __device__ __forceinline__ void normalize_body(const NormArgs& a) {
         for (int64_t i = tid0; i < total; i += nthr) {
             const int64_t r = i / a.dim;
             const int c = (int)(i - r * a.dim);
-            const float v = a.x[r * a.ldx + c];
-            if (a.raw_copy) a.raw_copy[r * a.ld_copy + c] = v;
+            float v;
+            if (U8) {
+                const uint8_t b = xb[r * a.ldx + c];
+                if (a.raw_copy) cb[r * a.ld_copy + c] = b;
+                v = (float)b;
+            } else {
+                v = xf[r * a.ldx + c];
+                if (a.raw_copy) cf[r * a.ld_copy + c] = v;
+            }
             if (a.y) {
                 float mu = 0.f, is = 1.f;
                 if (do_rms) col_stats(a.mean, a.var, c, a.eps, mu, is);
@@ -87,40 +105,48 @@ __device__ __forceinline__ void normalize_body(const NormArgs& a) {
     }
 }
 
-template <bool VEC4>
+template <bool VEC4, bool U8>
 __global__ void __launch_bounds__(256) normalize_kernel(const NormArgs a) {
     pdl_wait();
     pdl_trigger();
-    normalize_body<VEC4>(a);
+    normalize_body<VEC4, U8>(a);
 }
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-static bool make_norm_args(NormArgs& a, const float* x, int64_t ldx, float* y, int64_t ldy, float* raw_copy,
+static bool make_norm_args(NormArgs& a, const void* x, int64_t ldx, float* y, int64_t ldy, void* raw_copy,
                            int64_t ld_copy, int64_t rows, int dim, const double* mean, const double* var, float sub_mean,
                            float inv_scale, float eps, float clip, const float* rnn_src, int rnn_dim, float* rnn_dst,
-                           int64_t rnn_dst_stride) {
+                           int64_t rnn_dst_stride, bool u8 = false) {
     a = NormArgs{x, ldx, y, ldy, raw_copy, ld_copy, rows, dim, mean, var, sub_mean, inv_scale,
                  fabsf(sub_mean) > 1e-8f, fabsf(inv_scale - 1.0f) > 1e-8f, eps, clip,
                  rnn_src, rnn_dim, rnn_dst, rnn_dst_stride, rows};
-    return (dim % 4 == 0) && (ldx % 4 == 0) && aligned16(x) && (!y || ((ldy % 4 == 0) && aligned16(y))) &&
-           (!raw_copy || ((ld_copy % 4 == 0) && aligned16(raw_copy)));
+    const uintptr_t in_mask = u8 ? 3u : 15u;   // uchar4 vs float4 accesses on the input / raw-copy side
+    return (dim % 4 == 0) && (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & in_mask) == 0) &&
+           (!y || ((ldy % 4 == 0) && aligned16(y))) &&
+           (!raw_copy || ((ld_copy % 4 == 0) && ((reinterpret_cast<uintptr_t>(raw_copy) & in_mask) == 0)));
 }
 
-static int launch_normalize(const float* x, int64_t ldx, float* y, int64_t ldy, float* raw_copy, int64_t ld_copy,
+static int launch_normalize(const void* x, int64_t ldx, float* y, int64_t ldy, void* raw_copy, int64_t ld_copy,
                             int64_t rows, int dim, const double* mean, const double* var, float sub_mean,
                             float inv_scale, float eps, float clip, cudaStream_t st, const float* rnn_src = nullptr,
-                            int rnn_dim = 0, float* rnn_dst = nullptr, int64_t rnn_dst_stride = 0) {
+                            int rnn_dim = 0, float* rnn_dst = nullptr, int64_t rnn_dst_stride = 0, bool u8 = false) {
     if (rows == 0 || dim == 0) return 0;
     NormArgs a;
     const bool vec = make_norm_args(a, x, ldx, y, ldy, raw_copy, ld_copy, rows, dim, mean, var, sub_mean, inv_scale, eps,
-                                    clip, rnn_src, rnn_dim, rnn_dst, rnn_dst_stride);
+                                    clip, rnn_src, rnn_dim, rnn_dst, rnn_dst_stride, u8);
     const int64_t work = vec ? rows * (int64_t)(dim / 4) : rows * (int64_t)dim;
     int64_t blocks = ceil_div(work, 256);
     const int64_t cap = (int64_t)sm_count() * 8;
     if (blocks > cap) blocks = cap;
-    if (vec) SFB_CUDA_OK(launch_pdl(normalize_kernel<true>, dim3((unsigned)blocks), dim3(256), 0, st, a));
-    else SFB_CUDA_OK(launch_pdl(normalize_kernel<false>, dim3((unsigned)blocks), dim3(256), 0, st, a));
+    const dim3 g((unsigned)blocks), b(256);
+    if (u8) {
+        if (vec) SFB_CUDA_OK(launch_pdl(normalize_kernel<true, true>, g, b, 0, st, a));
+        else SFB_CUDA_OK(launch_pdl(normalize_kernel<false, true>, g, b, 0, st, a));
+    } else {
+        if (vec) SFB_CUDA_OK(launch_pdl(normalize_kernel<true, false>, g, b, 0, st, a));
+        else SFB_CUDA_OK(launch_pdl(normalize_kernel<false, false>, g, b, 0, st, a));
+    }
     SFB_LAUNCH_OK();
     return 0;
 }
@@ -192,12 +218,12 @@ __global__ void __launch_bounds__(256) post_step_kernel(const PostArgs a) { post
 
 // advance_rollouts part 2 of step t fused with generate_policy_request + normalisation of step t+1 (both consume the
 // env's outputs; nothing sits between them on the stream): one launch instead of two per env step.
-template <bool VEC4>
+template <bool VEC4, bool U8>
 __global__ void __launch_bounds__(256) post_pre_step_kernel(const PostArgs pa, const NormArgs na) {
     pdl_wait();
     pdl_trigger();
     post_step_body(pa);
-    normalize_body<VEC4>(na);
+    normalize_body<VEC4, U8>(na);
 }
 
 // ---- synthetic tape env ---------------------------------------------------------------------------------------------
@@ -289,23 +315,51 @@ using namespace sfb;
 
 extern "C" {
 
-int sfb200_normalize_obs(const float* x, int64_t ldx, float* y, int64_t ldy, int64_t rows, int dim, const double* mean,
-                         const double* var, float sub_mean, float inv_scale, float eps, float clip, void* stream) {
+static int normalize_obs_impl(const void* x, bool u8, int64_t ldx, float* y, int64_t ldy, int64_t rows, int dim,
+                              const double* mean, const double* var, float sub_mean, float inv_scale, float eps,
+                              float clip, void* stream) {
     SFB_CHECK_ARG(x && y && rows >= 0 && dim > 0, "normalize_obs: bad arguments");
     SFB_CHECK_ARG((mean == nullptr) == (var == nullptr), "normalize_obs: mean/var must both be set or both NULL");
     return launch_normalize(x, ldx, y, ldy, nullptr, 0, rows, dim, mean, var, sub_mean, inv_scale, eps, clip,
-                            (cudaStream_t)stream);
+                            (cudaStream_t)stream, nullptr, 0, nullptr, 0, u8);
+}
+
+int sfb200_normalize_obs(const float* x, int64_t ldx, float* y, int64_t ldy, int64_t rows, int dim, const double* mean,
+                         const double* var, float sub_mean, float inv_scale, float eps, float clip, void* stream) {
+    return normalize_obs_impl(x, false, ldx, y, ldy, rows, dim, mean, var, sub_mean, inv_scale, eps, clip, stream);
+}
+
+int sfb200_normalize_obs_u8(const uint8_t* x, int64_t ldx, float* y, int64_t ldy, int64_t rows, int dim,
+                            const double* mean, const double* var, float sub_mean, float inv_scale, float eps,
+                            float clip, void* stream) {
+    return normalize_obs_impl(x, true, ldx, y, ldy, rows, dim, mean, var, sub_mean, inv_scale, eps, clip, stream);
+}
+
+static int sampler_pre_step_impl(const void* obs, bool u8, int64_t n_envs, int dim, void* traj_obs_t,
+                                 int64_t traj_obs_stride, const float* rnn, int rnn_dim, float* traj_rnn_t,
+                                 int64_t traj_rnn_stride, float* x_norm, const double* mean, const double* var,
+                                 float sub_mean, float inv_scale, float eps, float clip, void* stream) {
+    SFB_CHECK_ARG(obs && traj_obs_t && n_envs >= 0 && dim > 0, "sampler_pre_step: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool with_rnn = rnn && traj_rnn_t && rnn_dim > 0;
+    return launch_normalize(obs, dim, x_norm, dim, traj_obs_t, traj_obs_stride, n_envs, dim, mean, var, sub_mean,
+                            inv_scale, eps, clip, st, with_rnn ? rnn : nullptr, rnn_dim, traj_rnn_t, traj_rnn_stride, u8);
 }
 
 int sfb200_sampler_pre_step(const float* obs, int64_t n_envs, int dim, float* traj_obs_t, int64_t traj_obs_stride,
                             const float* rnn, int rnn_dim, float* traj_rnn_t, int64_t traj_rnn_stride, float* x_norm,
                             const double* mean, const double* var, float sub_mean, float inv_scale, float eps,
                             float clip, void* stream) {
-    SFB_CHECK_ARG(obs && traj_obs_t && n_envs >= 0 && dim > 0, "sampler_pre_step: bad arguments");
-    cudaStream_t st = (cudaStream_t)stream;
-    const bool with_rnn = rnn && traj_rnn_t && rnn_dim > 0;
-    return launch_normalize(obs, dim, x_norm, dim, traj_obs_t, traj_obs_stride, n_envs, dim, mean, var, sub_mean,
-                            inv_scale, eps, clip, st, with_rnn ? rnn : nullptr, rnn_dim, traj_rnn_t, traj_rnn_stride);
+    return sampler_pre_step_impl(obs, false, n_envs, dim, traj_obs_t, traj_obs_stride, rnn, rnn_dim, traj_rnn_t,
+                                 traj_rnn_stride, x_norm, mean, var, sub_mean, inv_scale, eps, clip, stream);
+}
+
+int sfb200_sampler_pre_step_u8(const uint8_t* obs, int64_t n_envs, int dim, uint8_t* traj_obs_t, int64_t traj_obs_stride,
+                               const float* rnn, int rnn_dim, float* traj_rnn_t, int64_t traj_rnn_stride, float* x_norm,
+                               const double* mean, const double* var, float sub_mean, float inv_scale, float eps,
+                               float clip, void* stream) {
+    return sampler_pre_step_impl(obs, true, n_envs, dim, traj_obs_t, traj_obs_stride, rnn, rnn_dim, traj_rnn_t,
+                                 traj_rnn_stride, x_norm, mean, var, sub_mean, inv_scale, eps, clip, stream);
 }
 
 int sfb200_copy_rows(const float* src, int64_t src_stride, float* dst, int64_t dst_stride, int64_t rows, int dim,
@@ -351,13 +405,13 @@ int sfb200_sampler_post_step(const float* rew, const uint8_t* terminated, const 
     return 0;
 }
 
-int sfb200_sampler_post_pre_step(const float* rew, const uint8_t* terminated, const uint8_t* truncated, int64_t n_envs,
+static int sampler_post_pre_step_impl(bool u8, const float* rew, const uint8_t* terminated, const uint8_t* truncated, int64_t n_envs,
                                  float reward_scale, float reward_clip, int32_t policy_id, float* traj_rewards_t,
                                  uint8_t* traj_dones_t, uint8_t* traj_time_outs_t, int32_t* traj_policy_id_t,
                                  int64_t traj_stride, float* ep_return, int32_t* ep_len, float* ep_min_raw,
                                  float* ep_max_raw, int32_t len_increment, double* stats, int64_t* step_counter,
                                  float* fin_return_t, int32_t* fin_len_t,
-                                 const float* obs, int dim, float* traj_obs_next, int64_t traj_obs_stride,
+                                 const void* obs, int dim, void* traj_obs_next, int64_t traj_obs_stride,
                                  const float* rnn, int rnn_dim, float* traj_rnn_next, int64_t traj_rnn_stride,
                                  float* x_norm, const double* mean, const double* var, float sub_mean, float inv_scale,
                                  float eps, float clip, void* stream) {
@@ -374,18 +428,57 @@ int sfb200_sampler_post_pre_step(const float* rew, const uint8_t* terminated, co
     NormArgs na;
     const bool vec = make_norm_args(na, obs, dim, x_norm, dim, traj_obs_next, traj_obs_stride, n_envs, dim, mean, var,
                                     sub_mean, inv_scale, eps, clip, with_rnn ? rnn : nullptr, rnn_dim, traj_rnn_next,
-                                    traj_rnn_stride);
+                                    traj_rnn_stride, u8);
     const int64_t work = vec ? n_envs * (int64_t)(dim / 4) : n_envs * (int64_t)dim;
     int64_t blocks = ceil_div(work, 256);
     const int64_t cap = (int64_t)sm_count() * 8;
     if (blocks > cap) blocks = cap;
     if (blocks < ceil_div(n_envs, 256)) blocks = ceil_div(n_envs, 256);   // every env needs its post-step thread
     cudaStream_t st = (cudaStream_t)stream;
-    if (vec) SFB_CUDA_OK(launch_pdl(post_pre_step_kernel<true>, dim3((unsigned)blocks), dim3(256), 0, st, pa, na));
-    else SFB_CUDA_OK(launch_pdl(post_pre_step_kernel<false>, dim3((unsigned)blocks), dim3(256), 0, st, pa, na));
+    const dim3 g((unsigned)blocks), b(256);
+    if (u8) {
+        if (vec) SFB_CUDA_OK(launch_pdl(post_pre_step_kernel<true, true>, g, b, 0, st, pa, na));
+        else SFB_CUDA_OK(launch_pdl(post_pre_step_kernel<false, true>, g, b, 0, st, pa, na));
+    } else {
+        if (vec) SFB_CUDA_OK(launch_pdl(post_pre_step_kernel<true, false>, g, b, 0, st, pa, na));
+        else SFB_CUDA_OK(launch_pdl(post_pre_step_kernel<false, false>, g, b, 0, st, pa, na));
+    }
     SFB_LAUNCH_OK();
     return 0;
 }
+
+#define SFB_POST_PRE_ARGS                                                                                                  \
+    rew, terminated, truncated, n_envs, reward_scale, reward_clip, policy_id, traj_rewards_t, traj_dones_t,              \
+        traj_time_outs_t, traj_policy_id_t, traj_stride, ep_return, ep_len, ep_min_raw, ep_max_raw, len_increment, stats, \
+        step_counter, fin_return_t, fin_len_t, obs, dim, traj_obs_next, traj_obs_stride, rnn, rnn_dim, traj_rnn_next,     \
+        traj_rnn_stride, x_norm, mean, var, sub_mean, inv_scale, eps, clip, stream
+
+int sfb200_sampler_post_pre_step(const float* rew, const uint8_t* terminated, const uint8_t* truncated, int64_t n_envs,
+                                 float reward_scale, float reward_clip, int32_t policy_id, float* traj_rewards_t,
+                                 uint8_t* traj_dones_t, uint8_t* traj_time_outs_t, int32_t* traj_policy_id_t,
+                                 int64_t traj_stride, float* ep_return, int32_t* ep_len, float* ep_min_raw,
+                                 float* ep_max_raw, int32_t len_increment, double* stats, int64_t* step_counter,
+                                 float* fin_return_t, int32_t* fin_len_t,
+                                 const float* obs, int dim, float* traj_obs_next, int64_t traj_obs_stride,
+                                 const float* rnn, int rnn_dim, float* traj_rnn_next, int64_t traj_rnn_stride,
+                                 float* x_norm, const double* mean, const double* var, float sub_mean, float inv_scale,
+                                 float eps, float clip, void* stream) {
+    return sampler_post_pre_step_impl(false, SFB_POST_PRE_ARGS);
+}
+
+int sfb200_sampler_post_pre_step_u8(const float* rew, const uint8_t* terminated, const uint8_t* truncated, int64_t n_envs,
+                                    float reward_scale, float reward_clip, int32_t policy_id, float* traj_rewards_t,
+                                    uint8_t* traj_dones_t, uint8_t* traj_time_outs_t, int32_t* traj_policy_id_t,
+                                    int64_t traj_stride, float* ep_return, int32_t* ep_len, float* ep_min_raw,
+                                    float* ep_max_raw, int32_t len_increment, double* stats, int64_t* step_counter,
+                                    float* fin_return_t, int32_t* fin_len_t,
+                                    const uint8_t* obs, int dim, uint8_t* traj_obs_next, int64_t traj_obs_stride,
+                                    const float* rnn, int rnn_dim, float* traj_rnn_next, int64_t traj_rnn_stride,
+                                    float* x_norm, const double* mean, const double* var, float sub_mean,
+                                    float inv_scale, float eps, float clip, void* stream) {
+    return sampler_post_pre_step_impl(true, SFB_POST_PRE_ARGS);
+}
+#undef SFB_POST_PRE_ARGS
 
 static int tape_env_step_impl(const int32_t* actions, const float* actions_f32, int act_dim, int64_t n_envs,
                               int num_actions, int64_t env_index_offset, int term_period, int trunc_period,

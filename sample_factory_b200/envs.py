@@ -52,9 +52,15 @@ class TapeVecEnv:
     is_gpu_env = True
 
     def __init__(self, tape: Tensor, num_actions: int, term_period: int = 37, trunc_period: int = 11,
-                 env_index_offset: int = 0, continuous: bool = False):
-        assert tape.is_cuda and tape.dtype == torch.float32 and tape.dim() == 3 and tape.is_contiguous()
+                 env_index_offset: int = 0, continuous: bool = False, obs_shape=None):
+        assert tape.is_cuda and tape.dim() == 3 and tape.is_contiguous()
+        assert tape.dtype in (torch.float32, torch.uint8)
         self.tape = tape
+        # image observations: uint8 tape rows of C*H*W bytes with obs_shape = (C, H, W) -> the model builds a ConvEncoder
+        self.obs_uint8 = tape.dtype == torch.uint8
+        self.obs_shape = None if obs_shape is None else tuple(obs_shape)
+        assert self.obs_shape is None or int(np.prod(self.obs_shape)) == tape.shape[2]
+        assert not self.obs_uint8 or tape.shape[2] % 16 == 0, "uint8 observation rows must be a multiple of 16 bytes"
         # continuous: Box(num_actions) action space, actions arrive as float32 [num_agents, num_actions] and
         # reward = clamp(actions[:, 0], -1, 1); otherwise Discrete(num_actions), int32 [num_agents]
         self.continuous = continuous
@@ -65,10 +71,13 @@ class TapeVecEnv:
         dev = tape.device
         # device-side so CUDA graphs can replay: [0] = env step, [1] = block ticket used to advance it in-kernel
         self.step_counter = torch.zeros(2, dtype=torch.int64, device=dev)
-        self.obs = torch.empty((self.num_agents, self.obs_dim), dtype=torch.float32, device=dev)
+        self.obs = torch.empty((self.num_agents, self.obs_dim), dtype=tape.dtype, device=dev)
         self.rew = torch.empty(self.num_agents, dtype=torch.float32, device=dev)
         self.terminated = torch.empty(self.num_agents, dtype=torch.bool, device=dev)
         self.truncated = torch.empty(self.num_agents, dtype=torch.bool, device=dev)
+        # the env kernel copies observation rows as 32-bit words: uint8 rows are handed over as float32 views
+        self._tape_w = tape.view(torch.float32) if self.obs_uint8 else tape
+        self._obs_w = self.obs.view(torch.float32) if self.obs_uint8 else self.obs
 
     def reset(self) -> Tensor:
         self.step_counter.zero_()
@@ -78,11 +87,11 @@ class TapeVecEnv:
     def step(self, actions: Tensor) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
         if self.continuous:
             ops.tape_env_step_continuous(actions, self.env_index_offset, self.term_period, self.trunc_period,
-                                         self.step_counter, 0, self.tape, self.obs, self.rew, self.terminated,
+                                         self.step_counter, 0, self._tape_w, self._obs_w, self.rew, self.terminated,
                                          self.truncated)
         else:
             ops.tape_env_step(actions, self.num_actions, self.env_index_offset, self.term_period, self.trunc_period,
-                              self.step_counter, 0, self.tape, self.obs, self.rew, self.terminated, self.truncated)
+                              self.step_counter, 0, self._tape_w, self._obs_w, self.rew, self.terminated, self.truncated)
         return self.obs, self.rew, self.terminated, self.truncated
 
 

@@ -1,0 +1,108 @@
+"""Adapter from ordinary (CPU, single-agent, gymnasium-API) environments to the batched contract the device sampler
+drives -- the role of the reference's make_env_func_batched stack (algo/utils/make_env.py:89-237:
+BatchedMultiAgentWrapper auto-reset, SequentialVectorizeWrapper :240-335, BatchedVecEnv tensor conversion) and of
+preprocess_actions (batched_sampling.py:30-82).  This is what lets an sf_examples-style `make_env_func` that returns a
+plain `gym.Env` (BASELINE.json config 1: CartPole-v1, 64 envs) run on the device engine unmodified:
+
+    register_env("CartPole-v1", lambda name, cfg, env_config, render_mode=None:
+                 BatchedHostEnv(lambda i: gym.make(name), num_envs=64, device=...))
+
+Per step: actions D2H (one sync: a host simulator cannot start without them), a Python loop over the envs with
+auto-reset, results staged in pinned buffers, one H2D copy of the observation batch and one of the packed
+reward / terminated / truncated record.  The output tensors are static (the sampler captures its per-step kernels in
+CUDA graphs around env.step).  Duck-typed on the gymnasium API (reset(seed=...) -> (obs, info);
+step(a) -> (obs, reward, terminated, truncated, info)); gymnasium itself is not imported.
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Tuple
+
+import numpy as np
+import torch
+from torch import Tensor
+
+
+def _space_info(space) -> Tuple[bool, int]:
+    """(continuous, n) from a gymnasium-like action space: Discrete(n) -> (False, n); Box(shape=(A,)) -> (True, A)"""
+    if hasattr(space, "n"):
+        return False, int(space.n)
+    shape = tuple(getattr(space, "shape", ()))
+    if len(shape) != 1:
+        raise NotImplementedError("Non-trivial shape Box action spaces not currently supported. Try to flatten the space.")
+    return True, int(shape[0])
+
+
+class BatchedHostEnv:
+    is_gpu_env = False
+    static_outputs = True
+
+    def __init__(self, make_env: Callable[[int], object], num_envs: int, device: torch.device, seed: Optional[int] = None):
+        self.envs: List = [make_env(i) for i in range(num_envs)]
+        self.num_agents = num_envs
+        self.device = device
+        e0 = self.envs[0]
+        obs_space = e0.observation_space
+        shape = tuple(obs_space.shape)
+        self.obs_uint8 = np.dtype(getattr(obs_space, "dtype", np.float32)) == np.uint8
+        self.obs_shape = shape if len(shape) == 3 else None       # (C, H, W) image observations -> ConvEncoder
+        self.obs_dim = int(np.prod(shape))
+        self.continuous, self.num_actions = _space_info(e0.action_space)
+        self._seed = seed
+        self._seeded = False
+        n = num_envs
+        odt = torch.uint8 if self.obs_uint8 else torch.float32
+        self.obs_host = torch.empty((n, self.obs_dim), dtype=odt).pin_memory()
+        self.obs = torch.empty((n, self.obs_dim), dtype=odt, device=device)
+        adt, ashape = (torch.float32, (n, self.num_actions)) if self.continuous else (torch.int32, (n,))
+        self.actions_host = torch.empty(ashape, dtype=adt).pin_memory()
+        # reward / terminated / truncated travel in ONE packed staging buffer (one H2D copy instead of three)
+        self.pack_host = torch.empty(6 * n, dtype=torch.uint8).pin_memory()
+        self.rew_host = self.pack_host[: 4 * n].view(torch.float32)
+        self.term_host = self.pack_host[4 * n: 5 * n].view(torch.bool)
+        self.trunc_host = self.pack_host[5 * n:].view(torch.bool)
+        self.pack = torch.empty(6 * n, dtype=torch.uint8, device=device)
+        self.rew = self.pack[: 4 * n].view(torch.float32)
+        self.terminated = self.pack[4 * n: 5 * n].view(torch.bool)
+        self.truncated = self.pack[5 * n:].view(torch.bool)
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+        self.episode_infos: List[dict] = []   # infos of finished episodes since the last pop (batched_sampling.py:228-270)
+
+    def _put_obs(self, i: int, obs) -> None:
+        self.obs_host[i].copy_(torch.as_tensor(np.asarray(obs)).reshape(-1))
+
+    def reset(self) -> Tensor:
+        for i, e in enumerate(self.envs):
+            kw = {}
+            if self._seed is not None and not self._seeded:
+                kw["seed"] = self._seed + i        # per-env seed = global env id (batched_sampling.py:177)
+            obs, _info = e.reset(**kw)
+            self._put_obs(i, obs)
+        self._seeded = True
+        self.obs.copy_(self.obs_host, non_blocking=True)
+        self.h2d_bytes += self.obs_host.numel() * self.obs_host.element_size()
+        return self.obs
+
+    def step(self, actions: Tensor) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+        self.actions_host.copy_(actions, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        self.d2h_bytes += self.actions_host.numel() * self.actions_host.element_size()
+        a = self.actions_host.numpy()
+        rew, term, trunc = self.rew_host.numpy(), self.term_host.numpy(), self.trunc_host.numpy()
+        for i, e in enumerate(self.envs):
+            obs, r, tm, tr, info = e.step(a[i] if self.continuous else int(a[i]))
+            rew[i], term[i], trunc[i] = r, bool(tm), bool(tr)
+            if tm or tr:                             # BatchedMultiAgentWrapper auto-reset (make_env.py:89-94)
+                if info:
+                    self.episode_infos.append(info)
+                obs, _ = e.reset()
+            self._put_obs(i, obs)
+        self.obs.copy_(self.obs_host, non_blocking=True)
+        self.pack.copy_(self.pack_host, non_blocking=True)
+        self.h2d_bytes += self.obs_host.numel() * self.obs_host.element_size() + self.pack_host.numel()
+        return self.obs, self.rew, self.terminated, self.truncated
+
+    def close(self) -> None:
+        for e in self.envs:
+            if hasattr(e, "close"):
+                e.close()

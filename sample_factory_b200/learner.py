@@ -129,6 +129,9 @@ class Learner:
             "continuous_tanh_scale is only read by the non-adaptive parameterization (action_parameterization.py:33-78)")
         assert not cfg.shuffle_minibatches, "shuffle_minibatches is not on the device path yet"
         assert len(spec.hidden) > 0 or spec.use_rnn, "the device path needs at least one hidden layer or an RNN core"
+        assert spec.obs_shape is None or len(spec.fc_encoder_layers) > 0, (
+            "ConvEncoder on the device path needs at least one fully connected layer after the conv head "
+            "(encoder_conv_mlp_layers, reference default [512])")
         if spec.use_rnn:
             assert cfg.rollout % cfg.recurrence == 0, "rollout must be a multiple of recurrence (learner.py:500)"
             assert cfg.batch_size % cfg.recurrence == 0
@@ -179,8 +182,8 @@ class Learner:
         self.loss_ws = torch.empty(ops.loss_workspace_bytes(max(B, E)) // 8 + 8, dtype=torch.float64, device=dev)
         self.heads_ws = torch.empty(ops.heads_backward_workspace_bytes(spec.tail_input_size, A_lin) // 4 + 4, **f32)
         lin_ws = 4
-        d = D
-        for h in spec.encoder_mlp_layers:
+        d = spec.fc_encoder_input
+        for h in spec.fc_encoder_layers:
             lin_ws = max(lin_ws, ops.linear_backward_workspace_bytes(B, h, d) // 4 + 4)
             d = h
         self.rnn: Optional[RnnCore] = None
@@ -198,7 +201,9 @@ class Learner:
             lin_ws = max(lin_ws, ops.linear_backward_workspace_bytes(B, h, d) // 4 + 4)
             d = h
         self.lin_ws = torch.empty(lin_ws, **f32)
-        self.heads_plan = HeadsPlan(model, engine, max(B, self.N))
+        self.heads_plan = HeadsPlan(model, engine, max(B, self.N), need_backward=True)
+        # image observations: gradient w.r.t. the conv head's output (pre-activation of its last layer, (C,H,W) order)
+        self.dfeat = torch.empty((B, spec.conv_out_size), **f32) if spec.obs_shape is not None else None
         self.adam_ws = torch.empty(1024, **f32)
         self.opt_step = 0
         self.kernel_launches = 0
@@ -229,7 +234,7 @@ class Learner:
         inv_scale = 1.0 / spec.obs_scale
         if spec.normalize_input:                                                                     # :961, :925-941
             src = obs2d
-            if abs(spec.obs_subtract_mean) > 1e-8 or abs(spec.obs_scale - 1.0) > 1e-8:
+            if abs(spec.obs_subtract_mean) > 1e-8 or abs(spec.obs_scale - 1.0) > 1e-8 or obs2d.dtype != torch.float32:
                 # stats are taken AFTER sub-mean / scaling (normalize.py:62-67): stage the scaled obs first
                 ops.normalize_obs(obs2d, nobs2d, None, None, spec.obs_subtract_mean, inv_scale)
                 src = nobs2d
@@ -362,6 +367,12 @@ class Learner:
             if li > 0:
                 ops.linear_backward(self.dz[li], self.h[li - 1], W, self.act, dW, self.dz[li - 1], genc[li - 1][1],
                                     self.engine, self.lin_ws)
+            elif self.heads_plan.conv is not None:
+                # first fully connected layer of a ConvEncoder: its input is the conv head's activated output
+                conv = self.heads_plan.conv
+                ops.linear_backward(self.dz[li], conv.feat[: x0.shape[0]], W, self.act, dW, self.dfeat, None, self.engine,
+                                    self.lin_ws)
+                conv.backward(self.dfeat)
             else:
                 ops.linear_backward(self.dz[li], x0, W, none, dW, None, None, self.engine, self.lin_ws)
         # gradient all-reduce: ONE NCCL call on the flat buffer; mean over ranks is folded into the sums:

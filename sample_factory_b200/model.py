@@ -10,7 +10,7 @@ from __future__ import annotations
 
 import math
 from dataclasses import dataclass, field
-from typing import Dict, List, Tuple
+from typing import Dict, List, Optional, Tuple
 
 import torch
 from torch import Tensor
@@ -38,14 +38,63 @@ class ModelSpec:
     adaptive_stddev: bool = True        # cfg.py:577; False -> one learned log-stddev vector (action_parameterization.py:42)
     continuous_tanh_scale: float = 0.0  # cfg.py:583
     initial_stddev: float = 1.0         # cfg.py:591
+    # image observations: obs_shape = (C, H, W) selects the ConvEncoder (model/encoder.py:88-145); obs_dim = C*H*W and the
+    # fully connected layers after the conv head (encoder_conv_mlp_layers) take the place of encoder_mlp_layers
+    obs_shape: Optional[Tuple[int, int, int]] = None
+    encoder_conv_architecture: str = "convnet_atari"
+    encoder_conv_mlp_layers: List[int] = field(default_factory=lambda: [512])
+    obs_uint8: bool = False              # dtype of the observation rows in the trajectory buffers
+
+    CONV_ARCH = {  # model/encoder.py:127-134: (out_channels, kernel, stride); no padding
+        "convnet_simple": [(32, 8, 4), (64, 4, 2), (128, 3, 2)],
+        "convnet_impala": [(16, 8, 4), (32, 4, 2)],
+        "convnet_atari": [(32, 8, 4), (64, 4, 2), (64, 3, 1)],
+    }
+
+    @property
+    def conv_layers(self) -> List[Tuple[int, int, int, int, int, int, int, int]]:
+        """[(C_in, H_in, W_in, C_out, kernel, stride, H_out, W_out)] of the conv head ([] for vector observations)"""
+        if self.obs_shape is None:
+            return []
+        c, h, w = self.obs_shape
+        out = []
+        for (co, k, s) in self.CONV_ARCH[self.encoder_conv_architecture]:
+            ho, wo = (h - k) // s + 1, (w - k) // s + 1
+            out.append((c, h, w, co, k, s, ho, wo))
+            c, h, w = co, ho, wo
+        return out
+
+    @property
+    def conv_out_size(self) -> int:
+        c, _, _, co, _, _, ho, wo = self.conv_layers[-1]
+        return co * ho * wo
+
+    @property
+    def fc_encoder_layers(self) -> List[int]:
+        """widths of the fully connected encoder layers (after the conv head for image observations)"""
+        return list(self.encoder_conv_mlp_layers) if self.obs_shape is not None else list(self.encoder_mlp_layers)
+
+    @property
+    def fc_encoder_input(self) -> int:
+        return self.conv_out_size if self.obs_shape is not None else self.obs_dim
+
+    def fc_encoder_name(self, i: int, what: str) -> str:
+        if self.obs_shape is not None:
+            return f"encoder.encoders.obs.enc.mlp_layers.{2 * i}.{what}"
+        return f"encoder.encoders.obs.mlp_head.{2 * i}.{what}"
 
     @classmethod
     def from_cfg(cls, cfg, env) -> "ModelSpec":
         """The model the reference would build for this cfg / env (model/actor_critic.py:136-158, create_actor_critic):
         Discrete(n) envs expose `num_actions = n`; Box(A) envs expose `continuous = True` and `num_actions = A`."""
+        obs_shape = getattr(env, "obs_shape", None)   # (C, H, W) image observations -> ConvEncoder (encoder.py:218-227)
         return cls(env.obs_dim, env.num_actions, list(cfg.encoder_mlp_layers), list(cfg.decoder_mlp_layers),
                    cfg.nonlinearity, cfg.normalize_input, cfg.normalize_returns, cfg.obs_subtract_mean, cfg.obs_scale,
                    bool(cfg.use_rnn), cfg.rnn_type, cfg.rnn_size,
+                   obs_shape=None if obs_shape is None else tuple(obs_shape),
+                   encoder_conv_architecture=getattr(cfg, "encoder_conv_architecture", "convnet_atari"),
+                   encoder_conv_mlp_layers=list(getattr(cfg, "encoder_conv_mlp_layers", [512])),
+                   obs_uint8=bool(getattr(env, "obs_uint8", False)),
                    continuous=bool(getattr(env, "continuous", False)),
                    adaptive_stddev=bool(getattr(cfg, "adaptive_stddev", True)),
                    continuous_tanh_scale=float(getattr(cfg, "continuous_tanh_scale", 0.0)),
@@ -71,7 +120,7 @@ class ModelSpec:
     @property
     def hidden(self) -> List[int]:
         # ModelCoreIdentity (use_rnn=False) passes the encoder output straight to the decoder MLP
-        return list(self.encoder_mlp_layers) + list(self.decoder_mlp_layers)
+        return self.fc_encoder_layers + list(self.decoder_mlp_layers)
 
     @property
     def rnn_state_size(self) -> int:
@@ -91,15 +140,18 @@ class ModelSpec:
             return self.decoder_mlp_layers[-1]
         if self.use_rnn:
             return self.rnn_size
-        return self.encoder_mlp_layers[-1]
+        return self.fc_encoder_layers[-1]
 
     def param_shapes(self) -> List[Tuple[str, Tuple[int, ...]]]:
         """(reference state_dict key, shape) in nn.Module.parameters() order."""
         out = []
-        d = self.obs_dim
-        for i, h in enumerate(self.encoder_mlp_layers):
-            out.append((f"encoder.encoders.obs.mlp_head.{2 * i}.weight", (h, d)))
-            out.append((f"encoder.encoders.obs.mlp_head.{2 * i}.bias", (h,)))
+        for i, (ci, _h, _w, co, k, _s, _ho, _wo) in enumerate(self.conv_layers):
+            out.append((f"encoder.encoders.obs.enc.conv_head.{2 * i}.weight", (co, ci, k, k)))
+            out.append((f"encoder.encoders.obs.enc.conv_head.{2 * i}.bias", (co,)))
+        d = self.fc_encoder_input
+        for i, h in enumerate(self.fc_encoder_layers):
+            out.append((self.fc_encoder_name(i, "weight"), (h, d)))
+            out.append((self.fc_encoder_name(i, "bias"), (h,)))
             d = h
         if self.use_rnn:
             G, H = self.rnn_gates, self.rnn_size
@@ -234,18 +286,20 @@ class PolicyModel:
     # ---- layer access ---------------------------------------------------------------------------------------
     def hidden_layers(self) -> List[Tuple[Tensor, Tensor]]:
         """[(W [out,in], b [out]), ...] for encoder then decoder MLP layers."""
-        out = []
-        for i in range(len(self.spec.encoder_mlp_layers)):
-            out.append((self.params[f"encoder.encoders.obs.mlp_head.{2 * i}.weight"],
-                        self.params[f"encoder.encoders.obs.mlp_head.{2 * i}.bias"]))
-        for i in range(len(self.spec.decoder_mlp_layers)):
-            out.append((self.params[f"decoder.mlp.{2 * i}.weight"], self.params[f"decoder.mlp.{2 * i}.bias"]))
-        return out
+        return self.encoder_layers() + self.decoder_layers()
 
     def encoder_layers(self, grads: bool = False) -> List[Tuple[Tensor, Tensor]]:
+        """the fully connected encoder layers (MlpEncoder, or the layers after the conv head of a ConvEncoder)"""
         src = self.grads if grads else self.params
-        return [(src[f"encoder.encoders.obs.mlp_head.{2 * i}.weight"], src[f"encoder.encoders.obs.mlp_head.{2 * i}.bias"])
-                for i in range(len(self.spec.encoder_mlp_layers))]
+        sp = self.spec
+        return [(src[sp.fc_encoder_name(i, "weight")], src[sp.fc_encoder_name(i, "bias")])
+                for i in range(len(sp.fc_encoder_layers))]
+
+    def conv_params(self, grads: bool = False) -> List[Tuple[Tensor, Tensor]]:
+        """[(W [C_out, C_in, k, k], b [C_out])] of the conv head"""
+        src = self.grads if grads else self.params
+        return [(src[f"encoder.encoders.obs.enc.conv_head.{2 * i}.weight"], src[f"encoder.encoders.obs.enc.conv_head.{2 * i}.bias"])
+                for i in range(len(self.spec.conv_layers))]
 
     def decoder_layers(self, grads: bool = False) -> List[Tuple[Tensor, Tensor]]:
         src = self.grads if grads else self.params
@@ -259,13 +313,7 @@ class PolicyModel:
                 src["core.core.bias_hh_l0"])
 
     def hidden_layer_grads(self) -> List[Tuple[Tensor, Tensor]]:
-        out = []
-        for i in range(len(self.spec.encoder_mlp_layers)):
-            out.append((self.grads[f"encoder.encoders.obs.mlp_head.{2 * i}.weight"],
-                        self.grads[f"encoder.encoders.obs.mlp_head.{2 * i}.bias"]))
-        for i in range(len(self.spec.decoder_mlp_layers)):
-            out.append((self.grads[f"decoder.mlp.{2 * i}.weight"], self.grads[f"decoder.mlp.{2 * i}.bias"]))
-        return out
+        return self.encoder_layers(grads=True) + self.decoder_layers(grads=True)
 
     @property
     def learned_log_std(self):
@@ -291,8 +339,9 @@ class PolicyModel:
     def state_dict(self) -> Dict[str, Tensor]:
         sd: Dict[str, Tensor] = {}
         if self.spec.normalize_input:
-            sd[OBS_NORM_PREFIX + "running_mean"] = self.obs_mean.clone()
-            sd[OBS_NORM_PREFIX + "running_var"] = self.obs_var.clone()
+            shp = self.spec.obs_shape if self.spec.obs_shape is not None else (self.spec.obs_dim,)
+            sd[OBS_NORM_PREFIX + "running_mean"] = self.obs_mean.clone().view(shp)   # reference shape = obs space shape
+            sd[OBS_NORM_PREFIX + "running_var"] = self.obs_var.clone().view(shp)
             sd[OBS_NORM_PREFIX + "count"] = self.obs_count.clone()
         if self.spec.normalize_returns:
             sd[RET_NORM_PREFIX + "running_mean"] = self.ret_mean.clone()
@@ -309,9 +358,9 @@ class PolicyModel:
             if k in known:
                 self.params[k].copy_(v.to(self.device, torch.float32).view(self.params[k].shape))
             elif k == OBS_NORM_PREFIX + "running_mean":
-                self.obs_mean.copy_(v.to(self.device))
+                self.obs_mean.copy_(v.to(self.device).reshape(-1))     # image observations: [C,H,W] statistics, flat here
             elif k == OBS_NORM_PREFIX + "running_var":
-                self.obs_var.copy_(v.to(self.device))
+                self.obs_var.copy_(v.to(self.device).reshape(-1))
             elif k == OBS_NORM_PREFIX + "count":
                 self.obs_count.copy_(v.to(self.device).view(1))
             elif k == RET_NORM_PREFIX + "running_mean":

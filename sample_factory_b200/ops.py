@@ -50,6 +50,14 @@ def _p(t: Optional[Tensor], dtype=None) -> Optional[int]:
 
 
 F32, F64, U8, I32, I64 = torch.float32, torch.float64, torch.bool, torch.int32, torch.int64
+BYTE = torch.uint8   # image observations
+
+
+def _obs_entry(name: str, obs: Tensor):
+    """(entry point, dtype) for an observation tensor: uint8 rows go to the *_u8 twin of the entry point"""
+    if obs.dtype == BYTE:
+        return name + "_u8", BYTE
+    return name, F32
 
 
 def sm_count() -> int:
@@ -70,7 +78,8 @@ def normalize_obs(x: Tensor, out: Tensor, mean: Optional[Tensor], var: Optional[
                   inv_scale: float = 1.0, eps: float = 1e-5, clip: float = 5.0) -> Tensor:
     """x, out: [rows, dim] (row strides free). utils/normalize.py:51-70."""
     rows, dim = x.shape
-    lib().call("sfb200_normalize_obs", _p(x, F32), x.stride(0), _p(out, F32), out.stride(0), rows, dim,
+    entry, dt = _obs_entry("sfb200_normalize_obs", x)
+    lib().call(entry, _p(x, dt), x.stride(0), _p(out, F32), out.stride(0), rows, dim,
                _p(mean, F64), _p(var, F64), sub_mean, inv_scale, eps, clip, _stream())
     return out
 
@@ -174,6 +183,27 @@ def heads_from_partials_continuous(head_partials: Tensor, P: int, rows: int, bv:
                                 policy_version_scalar, policy_version_out, pv_stride))
 
 
+# ------------------------------------------------------------------------------------------------ conv encoder
+def im2col(x: Tensor, in_nchw: bool, B: int, C: int, H: int, W: int, kernel: int, stride: int, col: Tensor) -> None:
+    """x: [B, C*H*W] rows in (C,H,W) order (in_nchw) or [B*H*W, C] NHWC rows; col: [B*OH*OW, C*kernel*kernel]"""
+    assert x.is_contiguous() and col.is_contiguous()
+    lib().call("sfb200_im2col", _p(x, F32), int(in_nchw), B, C, H, W, kernel, stride, _p(col, F32), _stream())
+
+
+def col2im_act_backward(dcol: Tensor, x_act: Tensor, B: int, C: int, H: int, W: int, kernel: int, stride: int, act: int,
+                        dx: Tensor) -> None:
+    """dx [B*H*W, C] (NHWC) = col2im(dcol) * act'(x_act)"""
+    assert dcol.is_contiguous() and x_act.is_contiguous() and dx.is_contiguous()
+    lib().call("sfb200_col2im_act_backward", _p(dcol, F32), _p(x_act, F32), B, C, H, W, kernel, stride, act, _p(dx, F32),
+               _stream())
+
+
+def permute_bpc(src: Tensor, dst: Tensor, B: int, P: int, C: int, to_channel_major: bool) -> None:
+    """[B, P, C] -> [B, C, P] (to_channel_major) or back"""
+    assert src.is_contiguous() and dst.is_contiguous()
+    lib().call("sfb200_permute_bpc", _p(src, F32), _p(dst, F32), B, P, C, int(to_channel_major), _stream())
+
+
 def register_tf32_lo(base: Tensor, lo: Tensor) -> None:
     """Pair a flat weight buffer with its tf32 low-half twin (see include/sfb200.h) and fill the twin."""
     assert base.is_contiguous() and lo.is_contiguous() and base.numel() == lo.numel()
@@ -240,7 +270,9 @@ def sampler_pre_step(obs: Tensor, traj_obs_t: Tensor, rnn: Optional[Tensor], tra
     n, dim = obs.shape
     assert obs.is_contiguous() and (x_norm is None or x_norm.is_contiguous())
     rnn_dim = 0 if rnn is None else rnn.shape[1]
-    lib().call("sfb200_sampler_pre_step", _p(obs, F32), n, dim, traj_obs_t.data_ptr(), traj_obs_t.stride(0),
+    entry, dt = _obs_entry("sfb200_sampler_pre_step", obs)
+    assert traj_obs_t.dtype == obs.dtype
+    lib().call(entry, _p(obs, dt), n, dim, traj_obs_t.data_ptr(), traj_obs_t.stride(0),
                _p(rnn, F32), rnn_dim, None if traj_rnn_t is None else traj_rnn_t.data_ptr(),
                0 if traj_rnn_t is None else traj_rnn_t.stride(0), _p(x_norm, F32), _p(mean, F64), _p(var, F64),
                sub_mean, inv_scale, eps, clip, _stream())
@@ -284,13 +316,15 @@ def sampler_post_pre_step(rew: Tensor, terminated: Tensor, truncated: Tensor, re
     n_obs, dim = obs.shape
     assert n_obs == n and obs.is_contiguous() and (x_norm is None or x_norm.is_contiguous())
     rnn_dim = 0 if rnn is None else rnn.shape[1]
-    lib().call("sfb200_sampler_post_pre_step", _p(rew, F32), _p(terminated, U8), _p(truncated, U8), n, reward_scale,
+    entry, dt = _obs_entry("sfb200_sampler_post_pre_step", obs)
+    assert traj_obs_next.dtype == obs.dtype
+    lib().call(entry, _p(rew, F32), _p(terminated, U8), _p(truncated, U8), n, reward_scale,
                reward_clip, policy_id, traj_rewards_t.data_ptr(), traj_dones_t.data_ptr(),
                traj_time_outs_t.data_ptr(), traj_policy_id_t.data_ptr(), stride, _p(ep_return, F32), _p(ep_len, I32),
                _p(ep_min_raw, F32), _p(ep_max_raw, F32), len_increment, _p(stats, F64), _p(step_counter, I64),
                None if fin_return_t is None else fin_return_t.data_ptr(),
                None if fin_len_t is None else fin_len_t.data_ptr(),
-               _p(obs, F32), dim, traj_obs_next.data_ptr(), traj_obs_next.stride(0), _p(rnn, F32), rnn_dim,
+               _p(obs, dt), dim, traj_obs_next.data_ptr(), traj_obs_next.stride(0), _p(rnn, F32), rnn_dim,
                None if traj_rnn_next is None else traj_rnn_next.data_ptr(),
                0 if traj_rnn_next is None else traj_rnn_next.stride(0), _p(x_norm, F32), _p(mean, F64), _p(var, F64),
                sub_mean, inv_scale, eps, clip, _stream())

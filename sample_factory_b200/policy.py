@@ -19,11 +19,17 @@ from .model import PolicyModel
 
 
 class HeadsPlan:
-    """Decides once per (model, engine) whether the fused last-layer + heads path applies and owns its scratch."""
+    """Per call-site forward plan: decides once per (model, engine) whether the fused last-layer + heads path applies,
+    owns its scratch, and owns the conv head's buffers for image observations."""
 
-    def __init__(self, model: PolicyModel, engine: int, max_rows: int):
+    def __init__(self, model: PolicyModel, engine: int, max_rows: int, need_backward: bool = False):
         spec = model.spec
-        self.tail_is_mlp = bool(spec.decoder_mlp_layers) or (not spec.use_rnn and bool(spec.encoder_mlp_layers))
+        self.conv = None
+        if spec.obs_shape is not None:
+            from .conv_encoder import ConvHead
+
+            self.conv = ConvHead(model, engine, max_rows, need_backward)
+        self.tail_is_mlp = bool(spec.decoder_mlp_layers) or (not spec.use_rnn and bool(spec.fc_encoder_layers))
         self.P = 0
         self.part: Optional[Tensor] = None
         if self.tail_is_mlp:
@@ -39,6 +45,8 @@ def forward_policy(model: PolicyModel, x: Tensor, outs: List[Tensor], act: int, 
     ops.heads_forward after the weights).  outs: one [>=M, h] buffer per MLP layer.  Returns the tensor that fed the
     heads (None if it was not stored)."""
     M = x.shape[0]
+    if plan.conv is not None:        # ConvEncoder: conv head first, its fully connected layers are `enc` below
+        x = plan.conv.forward(x)
     enc, dec = model.encoder_layers(), model.decoder_layers()
     Wv, bv = model.critic
     Wa, ba = model.actor

@@ -41,6 +41,7 @@ class DeviceSampler:
         self.T = cfg.rollout
         spec = model.spec
         assert traj["obs"].shape == (self.N, self.T + 1, spec.obs_dim)
+        assert (traj["obs"].dtype == torch.uint8) == spec.obs_uint8
         self.act = ops.ACT[spec.nonlinearity]
         dev = self.device
         f32 = dict(dtype=torch.float32, device=dev)
@@ -166,7 +167,10 @@ class DeviceSampler:
 
     def _finalize_trajectories(self) -> None:
         tr = self.traj
-        ops.copy_rows(self.last_obs, tr["obs"][:, self.T])                       # batched_sampling.py:292
+        if self.last_obs.dtype == torch.float32:
+            ops.copy_rows(self.last_obs, tr["obs"][:, self.T])                   # batched_sampling.py:292
+        else:
+            tr["obs"][:, self.T].copy_(self.last_obs)                            # uint8 frames (recurrent path only)
         ops.copy_rows(self.last_rnn_state, tr["rnn_states"][:, self.T])          # :293
 
     def _rollout_eager(self) -> None:

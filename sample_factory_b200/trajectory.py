@@ -18,11 +18,14 @@ MAGIC_INT = 43  # algo/utils/misc.py:20
 
 
 def alloc_trajectory_tensors(obs_dim: int, num_action_params: int, num_traj: int, rollout: int, device,
-                             rnn_size: int = 1, num_actions: int = 1) -> Dict[str, Tensor]:
+                             rnn_size: int = 1, num_actions: int = 1, obs_uint8: bool = False) -> Dict[str, Tensor]:
     T, B = rollout, num_traj
     f32 = dict(dtype=torch.float32, device=device)
     t: Dict[str, Tensor] = {}
-    t["obs"] = torch.full((B, T + 1, obs_dim), MAGIC_FLOAT, **f32)
+    if obs_uint8:   # image observations keep the observation space's dtype (shared_buffers.py:88-96)
+        t["obs"] = torch.full((B, T + 1, obs_dim), MAGIC_INT, dtype=torch.uint8, device=device)
+    else:
+        t["obs"] = torch.full((B, T + 1, obs_dim), MAGIC_FLOAT, **f32)
     t["rnn_states"] = torch.full((B, T + 1, rnn_size), MAGIC_FLOAT, **f32)
     t["actions"] = torch.full((B, T, num_actions), MAGIC_FLOAT, **f32)
     t["action_logits"] = torch.full((B, T, num_action_params), MAGIC_FLOAT, **f32)
@@ -41,7 +44,8 @@ def alloc_for_spec(spec, num_traj: int, rollout: int, device) -> Dict[str, Tenso
     """Trajectory set for a ModelSpec: `actions` is [.., 1] for Discrete and [.., A] for Box(A); `action_logits` holds the
     distribution parameters (n logits, or 2A = [means | log_std]) -- shared_buffers.py:67-76 policy_output_shapes."""
     return alloc_trajectory_tensors(spec.obs_dim, spec.num_action_params, num_traj, rollout, device,
-                                    rnn_size=spec.rnn_state_size, num_actions=spec.action_width)
+                                    rnn_size=spec.rnn_state_size, num_actions=spec.action_width,
+                                    obs_uint8=spec.obs_uint8)
 
 
 def trajectory_bytes_per_env_step(obs_dim: int, num_action_params: int, rnn_size: int = 1) -> int:

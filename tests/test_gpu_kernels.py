@@ -872,3 +872,82 @@ def test_ppo_loss_fwd_bwd_continuous(dev, B, Ad, adaptive, tanh_scale, frac_inva
     out = torch.empty(B, device=dev)
     ops.action_ratio_continuous(params.detach().to(dev).contiguous(), actions.to(dev).contiguous(), lp_old.to(dev), out)
     np.testing.assert_allclose(out.cpu().numpy(), ratio.detach().numpy(), rtol=2e-5, atol=1e-6)
+
+
+# ----------------------------------------------------------------------------------------------- conv encoder
+@pytest.mark.parametrize("engine_name", ["simt", "3xtf32"])
+@pytest.mark.parametrize("B,shape,arch", [(5, (4, 44, 44), "convnet_atari"), (3, (4, 84, 84), "convnet_atari"),
+                                          (4, (3, 36, 36), "convnet_simple"), (6, (1, 30, 30), "convnet_impala")])
+def test_conv_head_forward_backward(dev, B, shape, arch, engine_name):
+    """ConvHead (im2col + GEMM engine + col2im) vs torch.nn.functional.conv2d + autograd on the CPU (the arithmetic the
+    reference's ConvEncoderImpl executes, model/encoder.py:88-118): features, conv weight / bias gradients."""
+    ops = _ops()
+    if engine_name != "simt" and not ops.tc_available():
+        pytest.skip("tcgen05 engine not available")
+    from sample_factory_b200.conv_encoder import ConvHead
+    from sample_factory_b200.model import ModelSpec, PolicyModel
+
+    ocfg = O.OracleCfg(obs_dim=int(np.prod(shape)), num_actions=4, obs_shape=shape, encoder_conv_architecture=arch,
+                       encoder_conv_mlp_layers=[32], nonlinearity="relu")
+    st = O.init_state(ocfg, seed=5)
+    spec = ModelSpec(ocfg.obs_dim, 4, nonlinearity="relu", obs_shape=shape, encoder_conv_architecture=arch,
+                     encoder_conv_mlp_layers=[32])
+    model = PolicyModel(spec, dev)
+    model.load_state_dict(st, strict=False)
+    head = ConvHead(model, ops.ENGINES[engine_name], B + 2, need_backward=True)
+    x = torch.randn(B, ocfg.obs_dim, generator=g(150))
+    # CPU reference with autograd
+    params = {k: st[k].clone().requires_grad_(True) for k in st if "conv_head" in k}
+    hcpu = x.view(B, *shape)
+    for i, (_co, _k, s_) in enumerate(O.CONV_ARCH[arch]):
+        hcpu = torch.relu(torch.nn.functional.conv2d(hcpu, params[O.conv_w(i)], params[O.conv_b(i)], stride=s_))
+    feat_ref = hcpu.reshape(B, -1)
+    gfeat = torch.randn(feat_ref.shape, generator=g(151))
+    feat_ref.backward(gfeat)
+
+    feat = head.forward(x.to(dev))
+    tol = 2e-5
+    assert (feat.cpu() - feat_ref.detach()).abs().max().item() < tol
+    # the backward takes the gradient w.r.t. the PRE-activation of the last conv layer
+    dpre = (gfeat * (feat_ref.detach() > 0).float()).to(dev).contiguous()
+    model.grad.zero_()
+    head.backward(dpre)
+    for i in range(len(O.CONV_ARCH[arch])):
+        gW, gb = model.conv_params(grads=True)[i]
+        ref_w, ref_b = params[O.conv_w(i)].grad, params[O.conv_b(i)].grad
+        scale = max(1.0, ref_w.abs().max().item())
+        assert (gW.cpu() - ref_w).abs().max().item() < 5e-5 * scale, i
+        assert (gb.cpu() - ref_b).abs().max().item() < 5e-5 * max(1.0, ref_b.abs().max().item()), i
+
+
+def test_normalize_obs_uint8(dev):
+    """uint8 observation rows: .float() -> scale -> running-mean-std (utils/normalize.py:40-67), bit-exact"""
+    ops = _ops()
+    rows, dim = 77, 4 * 12 * 12
+    x = torch.randint(0, 256, (rows, dim), generator=g(160), dtype=torch.uint8)
+    mean = torch.rand(dim, generator=g(161), dtype=torch.float64)
+    var = torch.rand(dim, generator=g(162), dtype=torch.float64) * 0.1 + 0.01
+    ref = x.float().mul_(1.0 / 255.0)
+    staged = torch.empty(rows, dim, device=dev)
+    ops.normalize_obs(x.to(dev), staged, None, None, 0.0, 1.0 / 255.0)
+    assert torch.equal(staged.cpu(), ref)
+    # IEEE restatement of running_mean_std.py:96-110 in numpy float32 (every op correctly rounded).  torch's CPU sqrt is
+    # NOT correctly rounded (vectorised approximation: ~1 % of inputs are 1 ulp off), so the torch oracle is matched to
+    # 1 ulp while the numpy pipeline -- which is what torch computes on a CUDA device -- is matched bit for bit.
+    f = np.float32
+    sig = np.sqrt((var.numpy().astype(f) + f(1e-5)).astype(f))
+    ieee = ((ref.numpy() - mean.numpy().astype(f)).astype(f) * (f(1) / sig).astype(f)).astype(f).clip(-5, 5)
+    O.rms_normalize_(ref, mean, var)
+    out = torch.empty(rows, dim, device=dev)
+    ops.normalize_obs(x.to(dev), out, mean.to(dev), var.to(dev), 0.0, 1.0 / 255.0)
+    assert np.array_equal(out.cpu().numpy(), ieee)
+    np.testing.assert_allclose(out.cpu().numpy(), ref.numpy(), rtol=2.5e-7, atol=1e-7)
+    ref = torch.from_numpy(ieee)
+    # sampler pre-step: raw uint8 copy into the trajectory + normalised float row
+    T = 3
+    traj = torch.zeros((rows, T + 1, dim), dtype=torch.uint8, device=dev)
+    traj_rnn = torch.zeros((rows, T + 1, 1), device=dev)
+    xn = torch.empty(rows, dim, device=dev)
+    ops.sampler_pre_step(x.to(dev), traj[:, 1], torch.zeros(rows, 1, device=dev), traj_rnn[:, 1], xn, mean.to(dev),
+                         var.to(dev), 0.0, 1.0 / 255.0)
+    assert torch.equal(traj[:, 1].cpu(), x) and torch.all(traj[:, 0] == 0) and torch.equal(xn.cpu(), ref)
