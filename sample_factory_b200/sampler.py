@@ -261,3 +261,101 @@ class DeviceSampler:
         if n <= 0:
             return dict(episodes=0)
         return dict(episodes=int(n), reward=s[1] / n, len=s[2] / n, min_raw_reward=s[3] / n, max_raw_reward=s[4] / n)
+
+
+class SplitSampler:
+    """The reference's double-buffered sampling (cfg.worker_num_splits, rollout_worker.py:97-143, "while one group of
+    envs waits for actions the other one is stepping"): the env instances of a worker are split into groups that advance
+    independently.  Here every group is a DeviceSampler over its own env instance and its own ROW RANGE of the shared
+    trajectory buffers, and the groups' per-step kernel chains run concurrently on separate CUDA streams (fork / join
+    captured into ONE graph).  A 4096-env policy step is latency-bound (five dependent kernels moving 2 MB), so two
+    2048-env chains in flight use the idle SMs instead of waiting on each other."""
+
+    def __init__(self, cfg, envs: List, model: PolicyModel, traj: Dict[str, Tensor], engine: int = ops.GEMM_SIMT,
+                 use_cuda_graph: bool = False, philox_seed: int = 0, record_episodes: bool = False):
+        assert len(envs) >= 2
+        self.cfg, self.model, self.traj = cfg, model, traj
+        self.subs: List[DeviceSampler] = []
+        lo = 0
+        for s, env in enumerate(envs):
+            n = env.num_agents
+            view = {k: v[lo: lo + n] for k, v in traj.items()}
+            self.subs.append(DeviceSampler(cfg, env, model, view, engine=engine, use_cuda_graph=False,
+                                           philox_seed=philox_seed + 7919 * s, record_episodes=record_episodes))
+            lo += n
+        self.N, self.T = lo, cfg.rollout
+        assert traj["obs"].shape[0] == self.N
+        self.env = envs[0]
+        self.side_streams = [torch.cuda.Stream(device=model.device) for _ in envs[1:]]
+        self.use_cuda_graph = use_cuda_graph and all(getattr(e, "is_gpu_env", False) for e in envs)
+        self._graph: Optional[torch.cuda.CUDAGraph] = None
+        self._graph_launches = 0
+        self.kernel_launches_per_rollout = 0
+
+    # ---- the DeviceSampler surface the runner / bench use ------------------------------------------------------
+    def reset(self) -> None:
+        for s in self.subs:
+            s.reset()
+
+    def set_policy_version(self, version: int) -> None:
+        for s in self.subs:
+            s.set_policy_version(version)
+
+    @property
+    def noise(self):
+        return None
+
+    @noise.setter
+    def noise(self, value: Optional[Tensor]) -> None:
+        """[T, N, A] explicit sampling noise (parity tests), cut into the groups' row ranges"""
+        lo = 0
+        for s in self.subs:
+            s.noise = None if value is None else value[:, lo: lo + s.N].contiguous()
+            lo += s.N
+
+    def _rollout_all(self) -> None:
+        main = torch.cuda.current_stream()
+        n0 = ops.launch_count()
+        for sub, st in zip(self.subs[1:], self.side_streams):      # fork
+            st.wait_stream(main)
+            with torch.cuda.stream(st):
+                sub._rollout_eager()
+        self.subs[0]._rollout_eager()
+        for st in self.side_streams:                               # join
+            main.wait_stream(st)
+        self.kernel_launches_per_rollout = ops.launch_count() - n0
+
+    def rollout(self) -> None:
+        if any(s.last_obs is None for s in self.subs):
+            self.reset()
+        if not self.use_cuda_graph:
+            self._rollout_all()
+            return
+        if self._graph is None:
+            assert all(s.noise is None for s in self.subs), "explicit noise and CUDA graphs are mutually exclusive"
+            torch.cuda.synchronize()
+            warm = torch.cuda.Stream()
+            warm.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(warm):
+                self._rollout_all()            # warm-up (kernel attributes, module load) outside the capture
+            torch.cuda.current_stream().wait_stream(warm)
+            torch.cuda.synchronize()
+            self._graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph):
+                self._rollout_all()
+            self._graph_launches = self.kernel_launches_per_rollout
+        self._graph.replay()
+        self.kernel_launches_per_rollout = self._graph_launches
+
+    @property
+    def graph_replay_launches(self) -> int:
+        return self._graph_launches if self._graph is not None else 0
+
+    def pop_episode_stats(self) -> Dict[str, float]:
+        tot = torch.stack([s.episode_stats for s in self.subs]).sum(0).cpu().tolist()
+        for s in self.subs:
+            s.episode_stats.zero_()
+        n = tot[0]
+        if n <= 0:
+            return dict(episodes=0)
+        return dict(episodes=int(n), reward=tot[1] / n, len=tot[2] / n, min_raw_reward=tot[3] / n, max_raw_reward=tot[4] / n)

@@ -32,7 +32,7 @@ from .dist_utils import init_from_env
 from .envs import create_env
 from .learner import Learner
 from .model import ModelSpec, PolicyModel
-from .sampler import DeviceSampler
+from .sampler import DeviceSampler, SplitSampler
 from .trajectory import alloc_for_spec
 
 
@@ -93,12 +93,20 @@ class Runner:
             torch.manual_seed(cfg.seed + self.rank)
         if not preprocess_cfg(cfg):
             raise ValueError("invalid configuration (see cfg.verify_cfg)")
-        env_config = dict(worker_index=self.rank, vector_index=0, env_id=self.rank)
-        self.env = create_env(cfg.env, cfg, env_config)
+        # env instances: one batched env, or -- the reference's double-buffered sampling, rollout_worker.py:97-143 --
+        # worker_num_splits groups of num_envs_per_worker / worker_num_splits env instances each (one instance per group
+        # on this path), created with the reference's env_config (batched_sampling.py:166-174)
+        n_splits = int(cfg.worker_num_splits) if (cfg.batched_sampling and cfg.worker_num_splits > 1 and
+                                                   cfg.num_envs_per_worker == cfg.worker_num_splits) else 1
+        self.envs = []
+        for s_ in range(n_splits):
+            env_config = dict(worker_index=self.rank, vector_index=s_, env_id=self.rank * n_splits + s_)
+            self.envs.append(create_env(cfg.env, cfg, env_config))
+        self.env = self.envs[0]
         spec = ModelSpec.from_cfg(cfg, self.env)
         assert cfg.rnn_num_layers == 1, "the device path implements the one-layer recurrent core"
         self.model = PolicyModel(spec, self.device, seed=cfg.seed or 0, policy_init_gain=cfg.policy_init_gain)
-        N = self.env.num_agents
+        N = sum(e.num_agents for e in self.envs)
         self.engine = select_engine(cfg)
         self.traj = alloc_for_spec(spec, N, cfg.rollout, self.device)
         if self.world_size > 1:
@@ -116,9 +124,12 @@ class Runner:
             self.rollouts_in_flight = 0
         else:
             self.sampler_model, self.sampler_traj = self.model, self.traj
-        self.sampler = DeviceSampler(cfg, self.env, self.sampler_model, self.sampler_traj, engine=self.engine,
-                                     use_cuda_graph=bool(getattr(cfg, "cuda_graph", True)),
-                                     philox_seed=(cfg.seed or 0) * 1000003 + self.rank)
+        sampler_kw = dict(engine=self.engine, use_cuda_graph=bool(getattr(cfg, "cuda_graph", True)),
+                          philox_seed=(cfg.seed or 0) * 1000003 + self.rank)
+        if n_splits > 1:
+            self.sampler = SplitSampler(cfg, self.envs, self.sampler_model, self.sampler_traj, **sampler_kw)
+        else:
+            self.sampler = DeviceSampler(cfg, self.env, self.sampler_model, self.sampler_traj, **sampler_kw)
         self.learner = Learner(cfg, self.model, N, engine=self.engine)
         if cfg.restart_behavior == "resume":
             ck = load_checkpoint(cfg, self.model, self.device)

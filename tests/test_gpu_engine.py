@@ -326,3 +326,60 @@ def test_async_double_buffered_runner_matches_lagged_oracle(tmp_path):
     assert runner.rollouts_started == ITERS + 1 and runner.env_steps == ITERS * N * T
     lag = runner.learner.train_step - got["policy_version"].max().item()
     assert lag == 4.0      # samples in the buffer are one iteration (4 SGD steps) behind the learner
+
+
+def test_split_sampler_matches_single_sampler():
+    """worker_num_splits = 2 (two env groups on two streams, one graph) fills the trajectory buffers exactly like one
+    sampler over all envs: same weights, same tape, same explicit noise -> identical trajectories (eager), and the
+    graph-captured fork/join rollout reproduces the eager one with Philox noise."""
+    from sample_factory_b200 import ops
+    from sample_factory_b200.envs import TapeVecEnv
+    from sample_factory_b200.sampler import DeviceSampler, SplitSampler
+
+    dev = torch.device("cuda", 0)
+    N, T = 256, 8
+    ocfg = O.OracleCfg(rollout=T, recurrence=1, batch_size=N * T, num_batches_per_epoch=1, encoder_mlp_layers=[128, 128])
+    st0 = O.init_state(ocfg, seed=8)
+    tape = (torch.randn(2 * T + 1, N, ocfg.obs_dim, generator=torch.Generator().manual_seed(5)) * 1.1).to(dev)
+    cfg, model, traj, env, sampler, _ = build(ocfg, N, st0, tape.cpu(), dev, engine="3xtf32" if ops.tc_available() else "simt")
+    eng = sampler.engine
+    noise = torch.empty(T, N, ocfg.num_actions).exponential_(generator=torch.Generator().manual_seed(9)).to(dev)
+    sampler.reset()
+    sampler.noise = noise
+    sampler.rollout()
+    ref = {k: v.clone() for k, v in traj.items()}
+    for v in traj.values():
+        v.zero_()
+    h = N // 2
+    envs = [TapeVecEnv(tape[:, :h].contiguous(), ocfg.num_actions, env_index_offset=0),
+            TapeVecEnv(tape[:, h:].contiguous(), ocfg.num_actions, env_index_offset=h)]
+    split = SplitSampler(cfg, envs, model, traj, engine=eng, use_cuda_graph=False)
+    split.reset()
+    split.noise = noise
+    split.rollout()
+    torch.cuda.synchronize()
+    for k in ref:
+        if k == "valids":
+            continue
+        if k == "values":      # column T (bootstrap value) belongs to the learner
+            assert torch.equal(traj[k][:, :T], ref[k][:, :T]), k
+            continue
+        assert torch.equal(traj[k], ref[k]), k
+    # graph-captured fork / join: replays are deterministic functions of (weights, tape, Philox counters)
+    def run(use_graph):
+        es = [TapeVecEnv(tape[:, :h].contiguous(), ocfg.num_actions, env_index_offset=0),
+              TapeVecEnv(tape[:, h:].contiguous(), ocfg.num_actions, env_index_offset=h)]
+        sp = SplitSampler(cfg, es, model, traj, engine=eng, use_cuda_graph=use_graph, philox_seed=3)
+        sp.reset()
+        outs = []
+        for _ in range(3):
+            sp.rollout()
+            torch.cuda.synchronize()
+            outs.append({k: traj[k].clone() for k in ("actions", "values", "rewards", "dones", "obs")})
+        return outs, sp
+    eager, _ = run(False)
+    graphed, sp = run(True)
+    assert sp.graph_replay_launches > 0
+    for a, b in zip(eager, graphed):
+        for k in a:
+            assert torch.equal(a[k], b[k]), k
