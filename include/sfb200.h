@@ -281,14 +281,16 @@ int sfb200_adv_stats_finalize(const double* dp_partials, double* stats, void* st
  *           targets (returns or vs), valids, logits_old [B,A]
  *   uses stats[NUM_VALID, ADV_MEAN, ADV_STD] (from sfb200_adv_stats) for the per-minibatch advantage normalisation
  *   outputs: dlogits [B,A], dvalues [B] = d(total loss)/d(.) ; stats[POLICY_LOSS .. TOTAL_LOSS]
+ * exploration_loss: 0 = entropy bonus (learner.py:473-477), 1 = symmetric KL to the uniform prior (:479-486,
+ * action_distributions.py:168-177; stats[EXPLORATION_LOSS] = +coeff * min(mean, 30)).
  * All means are over valid entries only (algo/utils/torch_utils.py:50-55).  grad_scale multiplies every gradient
  * (1/world_size under data parallelism). */
 int sfb200_ppo_loss_fwd_bwd(const float* logits, const float* values, int A, const float* actions_f32,
                             const float* log_prob_old, const float* values_old, const float* adv,
                             const float* targets, const uint8_t* valids, const float* logits_old, int64_t batch,
-                            float clip_ratio, float clip_value, float exploration_coeff, float value_coeff,
-                            float kl_coeff, float grad_scale, float* dlogits, float* dvalues, double* stats,
-                            void* workspace, void* stream);
+                            float clip_ratio, float clip_value, float exploration_coeff, int exploration_loss,
+                            float value_coeff, float kl_coeff, float grad_scale, float* dlogits, float* dvalues,
+                            double* stats, void* workspace, void* stream);
 
 /* The same for a Box action space (ContinuousActionDistribution, action_distributions.py:290-323): params / params_old
  * rows are [means | log_std] (2*act_dim floats, the `action_logits` layout), actions_f32 rows act_dim floats.

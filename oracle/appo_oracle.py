@@ -56,6 +56,7 @@ class OracleCfg:
     ppo_clip_ratio: float = 0.1
     ppo_clip_value: float = 1.0
     exploration_loss_coeff: float = 0.003
+    exploration_loss: str = "entropy"   # or "symmetric_kl" (learner.py:181-186, categorical distributions only)
     value_loss_coeff: float = 0.5
     kl_loss_coeff: float = 0.0
     max_grad_norm: float = 4.0
@@ -411,6 +412,14 @@ def cat_entropy(logits: Tensor) -> Tensor:
     return -(cat_log_probs(logits) * cat_probs(logits)).sum(-1)
 
 
+def cat_symmetric_kl_with_uniform_prior(logits: Tensor) -> Tensor:
+    """:168-177"""
+    probs, log_probs = cat_probs(logits), cat_log_probs(logits)
+    u = 1 / logits.shape[-1]
+    log_u = math.log(u)
+    return 0.5 * ((probs * (log_probs - log_u)).sum(-1) + (u * (log_u - log_probs)).sum(-1))
+
+
 def cat_kl(logits_p: Tensor, logits_q: Tensor) -> Tensor:
     """KL(p || q), :154-158,179-180"""
     return (cat_probs(logits_p) * (cat_log_probs(logits_p) - cat_log_probs(logits_q))).sum(-1)
@@ -740,6 +749,12 @@ def calculate_losses(cfg: OracleCfg, params: Dict[str, Tensor], mb: Dict[str, Te
     # _entropy_exploration_loss :473-477
     if cfg.exploration_loss_coeff == 0.0:
         exploration_loss = torch.zeros(())
+    elif cfg.exploration_loss == "symmetric_kl":   # _symmetric_kl_exploration_loss :479-486
+        assert not cfg.continuous
+        kl_prior = _masked_select(cat_symmetric_kl_with_uniform_prior(logits), valids, num_invalids).mean()
+        if not torch.isfinite(kl_prior):
+            kl_prior = torch.zeros(kl_prior.shape)
+        exploration_loss = cfg.exploration_loss_coeff * torch.clamp(kl_prior, max=30)
     else:
         ent = _masked_select(dist_entropy(cfg, logits), valids, num_invalids)
         exploration_loss = -cfg.exploration_loss_coeff * ent.mean()

@@ -271,6 +271,12 @@ int colsum(const float* X, int64_t ldx, int64_t M, int N, float* out, float* ws,
     return 0;
 }
 
+int colsum_reduce(const float* part, int64_t groups, int N, float* out, cudaStream_t st) {
+    colsum_reduce_kernel<<<(unsigned)ceil_div((int64_t)N * 32, 256), 256, 0, st>>>(part, (int)groups, N, out);
+    SFB_LAUNCH_OK();
+    return 0;
+}
+
 int64_t colsum_workspace_floats(int N) { return (int64_t)kColsumMaxGroups * N; }
 
 }  // namespace sfb
@@ -311,7 +317,10 @@ int sfb200_linear_act_heads_forward(const float* x, int64_t ldx, const float* W,
 int64_t sfb200_linear_backward_workspace_bytes(int64_t M, int N, int K) {
     // split-K slabs for dW [N,K] reduced over M, plus colsum partials for db_prev [K]
     const int splits = choose_splits(N, K, (int)(M > 0x7fffffff ? 0x7fffffff : M));
-    return ((int64_t)splits * N * K + colsum_workspace_floats(K)) * (int64_t)sizeof(float);
+    // colsum partials: kColsumMaxGroups rows for the standalone kernel, M/32 rows when the dX GEMM's epilogue writes them
+    int64_t cs_rows = M / 32 + 1;
+    if (cs_rows < kColsumMaxGroups) cs_rows = kColsumMaxGroups;
+    return ((int64_t)splits * N * K + cs_rows * K) * (int64_t)sizeof(float);
 }
 
 int sfb200_linear_backward(const float* dz, int64_t lddz, const float* x, int64_t ldx, const float* W, int64_t M, int N,
@@ -326,9 +335,12 @@ int sfb200_linear_backward(const float* dz, int64_t lddz, const float* x, int64_
     float* ws_colsum = ws + (int64_t)splits * N * K;
     int rc;
     if (engine != SFB200_GEMM_SIMT_FP32) {
-        rc = tc_linear_backward(dz, lddz, x, ldx, W, M, N, K, act_prev, dW, dx, lddx, engine, ws, st);
+        int fused = 0;
+        rc = tc_linear_backward(dz, lddz, x, ldx, W, M, N, K, act_prev, dW, dx, lddx, engine, ws, st,
+                                db_prev ? ws_colsum : nullptr, &fused);
         if (rc == 0 || rc != SFB_TC_UNSUPPORTED) {
             if (rc) return rc;
+            if (db_prev && fused) return colsum_reduce(ws_colsum, M / 32, K, db_prev, st);
             if (db_prev) return colsum(dx, lddx, M, K, db_prev, ws_colsum, st);
             return 0;
         }

@@ -178,6 +178,9 @@ struct TcEpilogue {
     const float* head_wa;
     int head_A;
     float* head_part;
+    // fused column sums of the OUTPUT (bias gradient of the previous layer = sum over rows of dX): one partial row per
+    // (128-row tile, 32-row warp quadrant) -> colsum_part[(m_tile*4 + quadrant)][N]; requires M % 128 == 0, N % 128 == 0
+    float* colsum_part;
 };
 
 constexpr int kHeadAP = 9;     // value + up to 8 action outputs
@@ -233,7 +236,7 @@ __device__ __forceinline__ void ld_global_v8(const float* p, float4& lo, float4&
 
 // one output row segment (BN columns, fully in bounds, 16 B aligned) with the epilogue resolved at compile time
 template <int MODE, int ACT, int BN>
-__device__ __forceinline__ void write_row(const float (&acc)[BN], float* __restrict__ dst, const float* bias_n0,
+__device__ __forceinline__ void write_row(float (&acc)[BN], float* __restrict__ dst, const float* bias_n0,
                                           const float4 (&auxv)[BN / 4], bool v8) {
 #pragma unroll
     for (int j = 0; j < BN; j += 8) {
@@ -261,7 +264,26 @@ __device__ __forceinline__ void write_row(const float (&acc)[BN], float* __restr
             *reinterpret_cast<float4*>(dst + j) = o[0];
             *reinterpret_cast<float4*>(dst + j + 4) = o[1];
         }
+        // keep the final values: the fused column-sum reduction reads them
+        acc[j] = o[0].x; acc[j + 1] = o[0].y; acc[j + 2] = o[0].z; acc[j + 3] = o[0].w;
+        acc[j + 4] = o[1].x; acc[j + 5] = o[1].y; acc[j + 6] = o[1].z; acc[j + 7] = o[1].w;
     }
+}
+
+// Sum 32 per-lane values over the 32 lanes of the warp so that lane j ends up with the total of v[j]: a transposing
+// butterfly, 16 + 8 + 4 + 2 + 1 = 31 shuffles instead of 32 x 5.  (Fixed order -> deterministic.)
+__device__ __forceinline__ float warp_transpose_sum32(float (&v)[32], int lane) {
+#pragma unroll
+    for (int half = 16; half >= 1; half >>= 1) {
+        const bool upper = (lane & half) != 0;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+            const float send = upper ? v[i] : v[i + half];
+            const float keep = upper ? v[i + half] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+        }
+    }
+    return v[0];
 }
 
 struct TileCoord {
@@ -378,7 +400,7 @@ __device__ __forceinline__ void tc_epilogue_tile(uint32_t tmem_slot_addr, uint64
     float* dst_row = Cz + m * ldc + nbeg;
 #pragma unroll
     for (int c0 = 0; c0 < CH; c0 += 32) {
-        const float (&acc)[32] = reinterpret_cast<const float (&)[32]>(acc_all[c0]);
+        float (&acc)[32] = reinterpret_cast<float (&)[32]>(acc_all[c0]);
         if (c0 > 0 && aux_row) {
             if (aux_v8) {
 #pragma unroll
@@ -409,6 +431,10 @@ __device__ __forceinline__ void tc_epilogue_tile(uint32_t tmem_slot_addr, uint64
                 }
             } else {
                 write_row<0, SFB200_ACT_NONE, 32>(acc, dst, bias_n0, auxv, st_v8);
+            }
+            if (epi.colsum_part) {   // (host guarantees full tiles: every lane of the warp is here)
+                const float cs = warp_transpose_sum32(acc, lane);
+                epi.colsum_part[((tc.m0 >> 5) + (lane_base >> 5)) * (int64_t)N + nbeg + c0 + lane] = cs;
             }
         } else {
 #pragma unroll   // fully unrolled so that acc[] stays in registers (no dynamic indexing)
@@ -690,6 +716,8 @@ struct TaSmem {
 // BLO: the B operand is a registered weight buffer whose low tf32 halves sit in a second array (tmap_b_lo): TMA fills the
 // B_hi (raw weights; the tensor core ignores the 13 low mantissa bits) and B_lo tiles directly and the operand warps do
 // no shared-memory work for B at all.
+// (Tried and dropped: two extra warps taking over the B-tile split of the dW-type GEMM so that A and B work of a stage
+// proceed in parallel -- 230.6 vs 232.4 us for dW + dX at M=32768, N=K=512, i.e. the B split is not what paces that GEMM.)
 template <bool A_MN, bool B_MN, bool SPLIT3, bool HEADS, bool BLO>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_ta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -1142,7 +1170,8 @@ int tc_linear_act_heads_forward(const float* x, int64_t ldx, const float* W, con
 }
 
 int tc_linear_backward(const float* dz, int64_t lddz, const float* x, int64_t ldx, const float* W, int64_t M, int N, int K,
-                       int act_prev, float* dW, float* dx, int64_t lddx, int engine, float* ws, cudaStream_t st) {
+                       int act_prev, float* dW, float* dx, int64_t lddx, int engine, float* ws, cudaStream_t st,
+                       float* colsum_part, int* colsum_fused) {
     const bool split3 = engine == SFB200_GEMM_TC_3XTF32;
     // dW[n,k] = sum_m dz[m,n] x[m,k]: both operands are stored with the reduced index m as the row -> MN-major
     TcEpilogue none{0, 0, nullptr, nullptr, 0};
@@ -1152,6 +1181,12 @@ int tc_linear_backward(const float* dz, int64_t lddz, const float* x, int64_t ld
     if (dx) {
         // dx[m,k] = (sum_n dz[m,n] W[n,k]) * act_prev'(x[m,k]): A = dz K-major, B(k, n) = W[n,k] MN-major
         TcEpilogue e{act_prev == SFB200_ACT_NONE ? 0 : 2, act_prev, nullptr, x, ldx};
+        // db_prev = column sums of dx, folded into this GEMM's epilogue when every tile is full (TMEM-A kernel, BN = 128)
+        const bool fuse_cs = colsum_part && M % 128 == 0 && K % 128 == 0 && ta_enabled() && lddx % 4 == 0 &&
+                             (act_prev == SFB200_ACT_NONE || (ldx % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15u) == 0)) &&
+                             (reinterpret_cast<uintptr_t>(dx) & 15u) == 0;
+        if (fuse_cs) e.colsum_part = colsum_part;
+        if (colsum_fused) *colsum_fused = fuse_cs ? 1 : 0;
         rc = gemm_tc(false, dz, lddz, true, W, K, dx, lddx, M, K, N, 1, e, nullptr, split3, st);
         if (rc) return rc;
     }

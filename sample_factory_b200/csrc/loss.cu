@@ -10,7 +10,7 @@ constexpr float kStdMin = 1e-4f, kStdMax = 1e4f;          // action_distribution
 constexpr float kHalfLog2PiL = 0.91893853320467274178f;   // log(sqrt(2 pi))
 constexpr int kNumPart = 12;
 // partial-sum slots
-enum { P_PL = 0, P_VL, P_ENT, P_KL, P_KLMAX, P_RDEV, P_RMIN, P_RMAX, P_CLIPPED, P_VSUM, P_COUNT, P_UNUSED };
+enum { P_PL = 0, P_VL, P_ENT, P_KL, P_KLMAX, P_RDEV, P_RMIN, P_RMAX, P_CLIPPED, P_VSUM, P_COUNT, P_SKL };
 
 template <int AMAX>
 __device__ __forceinline__ void load_row(const float* __restrict__ p, int A, float (&out)[AMAX]) {
@@ -146,7 +146,7 @@ __global__ void adv_stats_from_partials_kernel(const double* __restrict__ dp, do
 // ---- the loss ---------------------------------------------------------------------------------------------------------
 // distribution-independent pieces shared by the categorical and the Gaussian kernels
 struct PpoAcc {
-    double s_pl = 0, s_vl = 0, s_ent = 0, s_kl = 0, s_rdev = 0, s_clip = 0, s_v = 0, s_cnt = 0;
+    double s_pl = 0, s_vl = 0, s_ent = 0, s_kl = 0, s_rdev = 0, s_clip = 0, s_v = 0, s_cnt = 0, s_skl = 0;
     double m_kl = -INFINITY, m_rmin = -INFINITY /* holds -min */, m_rmax = -INFINITY;
 };
 
@@ -197,6 +197,7 @@ __device__ __forceinline__ void ppo_store_partials(const PpoAcc& a, double* __re
     t = block_sum(a.s_clip, sm); if (threadIdx.x == 0) my[P_CLIPPED] = t;
     t = block_sum(a.s_v, sm);    if (threadIdx.x == 0) my[P_VSUM] = t;
     t = block_sum(a.s_cnt, sm);  if (threadIdx.x == 0) my[P_COUNT] = t;
+    t = block_sum(a.s_skl, sm);  if (threadIdx.x == 0) my[P_SKL] = t;
 }
 
 template <int AMAX>
@@ -204,7 +205,7 @@ __global__ void __launch_bounds__(256) ppo_loss_kernel(
     const float* __restrict__ logits, const float* __restrict__ values, int A, const float* __restrict__ actions,
     const float* __restrict__ lp_old, const float* __restrict__ v_old, const float* __restrict__ adv,
     const float* __restrict__ targets, const uint8_t* __restrict__ valids, const float* __restrict__ logits_old,
-    int64_t batch, float clip_lo, float clip_hi, float clip_value, float c_ent, float c_val, float c_kl,
+    int64_t batch, float clip_lo, float clip_hi, float clip_value, float c_ent, int expl_mode, float c_val, float c_kl,
     float grad_scale, float* __restrict__ dlogits, float* __restrict__ dvalues, const double* __restrict__ stats,
     double* __restrict__ part) {
     __shared__ double sm[8];
@@ -239,6 +240,16 @@ __global__ void __launch_bounds__(256) ppo_loss_kernel(
             for (int a = 0; a < AMAX; ++a)
                 if (a < A) H -= logp[a] * p[a];
             acc.s_ent = H;
+            // symmetric KL to the uniform prior (action_distributions.py:168-177), the alternative exploration loss
+            // (learner.py:479-486):  0.5 * (sum_a p_a (logp_a - log u) + sum_a u (log u - logp_a)),  u = 1/A
+            const float u = 1.f / (float)A, log_u = -logf((float)A);
+            float S1 = 0.f, S2 = 0.f;
+            if (expl_mode == 1) {
+#pragma unroll
+                for (int a = 0; a < AMAX; ++a)
+                    if (a < A) { S1 += p[a] * (logp[a] - log_u); S2 += u * (log_u - logp[a]); }
+                acc.s_skl = 0.5f * (S1 + S2);
+            }
             // KL(new || old) :154-158
             float kl = 0.f;
             float lq[AMAX];
@@ -257,7 +268,8 @@ __global__ void __launch_bounds__(256) ppo_loss_kernel(
             for (int a = 0; a < AMAX; ++a) {
                 if (a < A) {
                     float g = g_lp * ((a == act ? 1.f : 0.f) - p[a]);
-                    g += we * p[a] * (logp[a] + H);
+                    if (expl_mode == 1) g += we * 0.5f * (p[a] * ((logp[a] - log_u) - S1) + p[a] - u);   // +c * d skl / d l_a
+                    else g += we * p[a] * (logp[a] + H);                                                    // -c * d H / d l_a
                     if (logits_old) g += wk * p[a] * ((logp[a] - lq[a]) - kl);
                     dl[a] = g;
                 }
@@ -393,8 +405,8 @@ __global__ void __launch_bounds__(256) action_ratio_gauss_kernel(const float* __
 }
 
 __global__ void __launch_bounds__(256) ppo_loss_finalize_kernel(const double* __restrict__ part, int nblocks,
-                                                                int64_t batch, float c_ent, float c_val, float c_kl,
-                                                                double* __restrict__ stats) {
+                                                                int64_t batch, float c_ent, int expl_mode, float c_val,
+                                                                float c_kl, double* __restrict__ stats) {
     __shared__ double sm[8];
     double acc[kNumPart];
 #pragma unroll
@@ -417,7 +429,14 @@ __global__ void __launch_bounds__(256) ppo_loss_finalize_kernel(const double* __
         const double inv = n > 0.0 ? 1.0 / n : 0.0;
         const double pl = -acc[P_PL] * inv;
         const double vl = (double)c_val * acc[P_VL] * inv;
-        const double el = -(double)c_ent * acc[P_ENT] * inv;
+        // entropy bonus :473-477, or +coeff * min(mean symmetric KL, 30) :479-486 (the gradient assumes the clamp inactive:
+        // a mean symmetric KL above 30 needs probabilities below e^-60)
+        double el = -(double)c_ent * acc[P_ENT] * inv;
+        if (expl_mode == 1) {
+            double skl = acc[P_SKL] * inv;
+            if (!isfinite(skl)) skl = 0.0;
+            el = (double)c_ent * (skl < 30.0 ? skl : 30.0);
+        }
         const double kl = (double)c_kl * acc[P_KL] * inv;
         stats[SFB200_LS_POLICY_LOSS] = pl;
         stats[SFB200_LS_VALUE_LOSS] = vl;
@@ -485,9 +504,10 @@ int sfb200_adv_stats_finalize(const double* dp_partials, double* stats, void* st
 int sfb200_ppo_loss_fwd_bwd(const float* logits, const float* values, int A, const float* actions_f32,
                             const float* log_prob_old, const float* values_old, const float* adv, const float* targets,
                             const uint8_t* valids, const float* logits_old, int64_t batch, float clip_ratio,
-                            float clip_value, float exploration_coeff, float value_coeff, float kl_coeff,
-                            float grad_scale, float* dlogits, float* dvalues, double* stats, void* workspace,
-                            void* stream) {
+                            float clip_value, float exploration_coeff, int exploration_loss, float value_coeff,
+                            float kl_coeff, float grad_scale, float* dlogits, float* dvalues, double* stats,
+                            void* workspace, void* stream) {
+    SFB_CHECK_ARG(exploration_loss == 0 || exploration_loss == 1, "ppo_loss_fwd_bwd: exploration_loss must be 0 (entropy) or 1 (symmetric_kl)");
     SFB_CHECK_ARG(logits && values && actions_f32 && log_prob_old && values_old && adv && targets && valids && dlogits &&
                       dvalues && stats && workspace && batch > 0, "ppo_loss_fwd_bwd: bad arguments");
     SFB_CHECK_ARG(A >= 1 && A <= 32, "ppo_loss_fwd_bwd: supports 1 <= A <= 32");
@@ -499,13 +519,14 @@ int sfb200_ppo_loss_fwd_bwd(const float* logits, const float* values, int A, con
 #define SFB_PL(AM)                                                                                                   \
     ppo_loss_kernel<AM><<<g, 256, 0, st>>>(logits, values, A, actions_f32, log_prob_old, values_old, adv, targets,    \
                                            valids, logits_old, batch, clip_lo, clip_hi, clip_value, exploration_coeff, \
-                                           value_coeff, kl_coeff, grad_scale, dlogits, dvalues, stats, part)
+                                           exploration_loss, value_coeff, kl_coeff, grad_scale, dlogits, dvalues, stats, part)
     if (A <= 8) SFB_PL(8);
     else if (A <= 16) SFB_PL(16);
     else SFB_PL(32);
 #undef SFB_PL
     SFB_LAUNCH_OK();
-    ppo_loss_finalize_kernel<<<1, 256, 0, st>>>(part, (int)g, batch, exploration_coeff, value_coeff, kl_coeff, stats);
+    ppo_loss_finalize_kernel<<<1, 256, 0, st>>>(part, (int)g, batch, exploration_coeff, exploration_loss, value_coeff, kl_coeff,
+                                                stats);
     SFB_LAUNCH_OK();
     return 0;
 }
@@ -550,7 +571,7 @@ int sfb200_ppo_loss_fwd_bwd_continuous(const float* params, const float* values,
     else SFB_PG(32);
 #undef SFB_PG
     SFB_LAUNCH_OK();
-    ppo_loss_finalize_kernel<<<1, 256, 0, st>>>(part, (int)g, batch, exploration_coeff, value_coeff, kl_coeff, stats);
+    ppo_loss_finalize_kernel<<<1, 256, 0, st>>>(part, (int)g, batch, exploration_coeff, 0, value_coeff, kl_coeff, stats);
     SFB_LAUNCH_OK();
     return 0;
 }

@@ -124,7 +124,10 @@ class Learner:
         if cfg.with_vtrace:
             assert cfg.recurrence == cfg.rollout and cfg.recurrence > 1, "V-trace requires recurrence == rollout > 1"
             assert not cfg.normalize_returns, "normalize_returns is incompatible with V-trace (arguments.py:129-134)"
-        assert cfg.exploration_loss == "entropy", "only the entropy exploration loss is on the device path"
+        assert cfg.exploration_loss in ("entropy", "symmetric_kl"), f"{cfg.exploration_loss} not supported!"   # learner.py:186
+        assert cfg.exploration_loss == "entropy" or not spec.continuous, (
+            "symmetric_kl is defined for categorical distributions only (ContinuousActionDistribution has no "
+            "symmetric_kl_with_uniform_prior in the reference either)")
         assert not (spec.continuous and spec.adaptive_stddev and spec.continuous_tanh_scale > 0), (
             "continuous_tanh_scale is only read by the non-adaptive parameterization (action_parameterization.py:33-78)")
         assert not cfg.shuffle_minibatches, "shuffle_minibatches is not on the device path yet"
@@ -328,7 +331,8 @@ class Learner:
         else:
             ops.ppo_loss_fwd_bwd(self.mb_logits, self.mb_values, actions, lp_old, v_old, adv, targets, valids, logits_old,
                                  cfg.ppo_clip_ratio, cfg.ppo_clip_value, cfg.exploration_loss_coeff, cfg.value_loss_coeff,
-                                 cfg.kl_loss_coeff, 1.0, self.dlogits, self.dvalues, self.loss_stats, self.loss_ws)
+                                 cfg.kl_loss_coeff, 1.0, self.dlogits, self.dvalues, self.loss_stats, self.loss_ws,
+                                 exploration_loss=cfg.exploration_loss)
         self.loss_stats_log[log_idx].copy_(self.loss_stats)
         # backward: heads -> decoder MLP -> (recurrent core, BPTT) -> encoder MLP
         g = m.grads

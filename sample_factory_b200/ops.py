@@ -411,13 +411,15 @@ def adv_stats_finalize(dp_partials: Tensor, stats: Tensor) -> None:
 def ppo_loss_fwd_bwd(logits: Tensor, values: Tensor, actions_f32: Tensor, log_prob_old: Tensor, values_old: Tensor,
                      adv: Tensor, targets: Tensor, valids: Tensor, logits_old: Optional[Tensor], clip_ratio: float,
                      clip_value: float, exploration_coeff: float, value_coeff: float, kl_coeff: float,
-                     grad_scale: float, dlogits: Tensor, dvalues: Tensor, stats: Tensor, workspace: Tensor) -> None:
+                     grad_scale: float, dlogits: Tensor, dvalues: Tensor, stats: Tensor, workspace: Tensor,
+                     exploration_loss: str = "entropy") -> None:
     B, A = logits.shape
     assert logits.is_contiguous() and dlogits.is_contiguous()
     assert workspace.numel() * workspace.element_size() >= loss_workspace_bytes(B)
     lib().call("sfb200_ppo_loss_fwd_bwd", _p(logits, F32), _p(values, F32), A, _p(actions_f32, F32),
                _p(log_prob_old, F32), _p(values_old, F32), _p(adv, F32), _p(targets, F32), _p(valids, U8),
-               _p(logits_old, F32), B, clip_ratio, clip_value, exploration_coeff, value_coeff, kl_coeff, grad_scale,
+               _p(logits_old, F32), B, clip_ratio, clip_value, exploration_coeff,
+               {"entropy": 0, "symmetric_kl": 1}[exploration_loss], value_coeff, kl_coeff, grad_scale,
                _p(dlogits, F32), _p(dvalues, F32), _p(stats, F64), workspace.data_ptr(), _stream())
 
 

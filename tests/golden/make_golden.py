@@ -267,6 +267,7 @@ def run_case(name: str, N: int, T: int, obs_dim: int, A: int, hidden, iters: int
     for k in ["continuous_tanh_scale", "initial_stddev", "obs_scale", "obs_subtract_mean"]:
         out[f"cfg/{k}"] = np.float64(getattr(cfg, k))
     out["cfg/nonlinearity"] = np.array(cfg.nonlinearity)
+    out["cfg/exploration_loss"] = np.array(cfg.exploration_loss)
     out["cfg/encoder_conv_architecture"] = np.array(cfg.encoder_conv_architecture)
     out["cfg/encoder_conv_mlp_layers"] = np.array(list(cfg.encoder_conv_mlp_layers), dtype=np.int64)
     out["cfg/continuous"] = np.bool_(continuous)
@@ -366,6 +367,13 @@ if __name__ == "__main__":
                        encoder_conv_architecture="convnet_atari", encoder_conv_mlp_layers=[128],
                        exploration_loss_coeff=0.01, max_grad_norm=0.5, adam_eps=1e-5, ppo_clip_ratio=0.1),
         poison=True, obs_shape=(4, 44, 44),
+    )
+    # symmetric-KL-to-uniform exploration loss (learner.py:479-486) instead of the entropy bonus
+    run_case(
+        "tiny_symkl", N=32, T=8, obs_dim=16, A=5, hidden=[64, 64], iters=2,
+        overrides=dict(batch_size=128, num_batches_per_epoch=2, num_epochs=1, exploration_loss="symmetric_kl",
+                       exploration_loss_coeff=0.01),
+        poison=True,
     )
     # cfg-2 hyper-parameters and model (300 553 params) at a reduced env count
     run_case(

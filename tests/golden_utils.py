@@ -13,7 +13,8 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 def load_case(name):
     z = np.load(os.path.join(GOLDEN_DIR, f"{name}.npz"), allow_pickle=False)
     meta = ast.literal_eval(str(z["meta"]))
-    _arrays = ("cfg/rnn_type", "cfg/nonlinearity", "cfg/encoder_conv_architecture", "cfg/encoder_conv_mlp_layers")
+    _arrays = ("cfg/rnn_type", "cfg/nonlinearity", "cfg/encoder_conv_architecture", "cfg/encoder_conv_mlp_layers",
+               "cfg/exploration_loss")
     c = {k[4:]: z[k].item() for k in z.files if k.startswith("cfg/") and k not in _arrays}
     cfg = O.OracleCfg(
         obs_dim=meta["obs_dim"], num_actions=meta["A"], encoder_mlp_layers=list(meta["hidden"]),
@@ -32,6 +33,7 @@ def load_case(name):
         nonlinearity=str(z["cfg/nonlinearity"]) if "cfg/nonlinearity" in z.files else "elu",
         continuous=bool(c.get("continuous", False)), adaptive_stddev=bool(c.get("adaptive_stddev", True)),
         continuous_tanh_scale=float(c.get("continuous_tanh_scale", 0.0)), initial_stddev=float(c.get("initial_stddev", 1.0)),
+        exploration_loss=str(z["cfg/exploration_loss"]) if "cfg/exploration_loss" in z.files else "entropy",
         obs_scale=float(c.get("obs_scale", 1.0)), obs_subtract_mean=float(c.get("obs_subtract_mean", 0.0)),
         obs_shape=tuple(meta["obs_shape"]) if meta.get("obs_shape") else None,
         encoder_conv_architecture=(str(z["cfg/encoder_conv_architecture"]) if "cfg/encoder_conv_architecture" in z.files

@@ -151,7 +151,8 @@ def test_linear_forward_strided_input(dev):
 
 
 @pytest.mark.parametrize("M,N,K,act_prev", [(64, 8, 4, "elu"), (1000, 70, 37, "elu"), (4096, 512, 512, "elu"),
-                                            (2048, 512, 64, "none"), (777, 130, 260, "tanh")])
+                                            (2048, 512, 64, "none"), (777, 130, 260, "tanh"), (4096, 256, 256, "none"),
+                                            (8192, 128, 384, "relu")])
 @pytest.mark.parametrize("engine", ["simt", "3xtf32"])
 def test_linear_backward(dev, M, N, K, act_prev, engine):
     ops = _ops()
@@ -169,6 +170,8 @@ def test_linear_backward(dev, M, N, K, act_prev, engine):
         d = torch.where(pre > 0, torch.ones_like(pre), torch.exp(pre)).double()
     elif act_prev == "tanh":
         d = (1 - torch.tanh(pre) ** 2).double()
+    elif act_prev == "relu":
+        d = (pre > 0).double()
     else:
         d = torch.ones_like(pre).double()
     dx_ref = (dxl * d).float()
@@ -408,11 +411,13 @@ def test_vtrace(dev, n, R):
 
 
 # ----------------------------------------------------------------------------------------------- loss
+@pytest.mark.parametrize("expl", ["entropy", "symmetric_kl"])
 @pytest.mark.parametrize("B,A,frac_invalid,kl_coeff", [(64, 8, 0.0, 0.0), (1000, 8, 0.2, 0.1), (32768, 8, 0.0, 0.0),
                                                        (777, 3, 0.3, 0.5), (513, 17, 0.1, 0.2)])
-def test_ppo_loss_fwd_bwd(dev, B, A, frac_invalid, kl_coeff):
+def test_ppo_loss_fwd_bwd(dev, B, A, frac_invalid, kl_coeff, expl):
     ops = _ops()
-    cfg = O.OracleCfg(num_actions=A, kl_loss_coeff=kl_coeff, ppo_clip_ratio=0.1, ppo_clip_value=0.2)
+    cfg = O.OracleCfg(num_actions=A, kl_loss_coeff=kl_coeff, ppo_clip_ratio=0.1, ppo_clip_value=0.2, exploration_loss=expl,
+                      exploration_loss_coeff=0.003 if expl == "entropy" else 0.02)
     logits = (torch.randn(B, A, generator=g(39)) * 1.5).requires_grad_(True)
     values = torch.randn(B, generator=g(40)).requires_grad_(True)
     logits_old = logits.detach() + torch.randn(B, A, generator=g(41)) * 0.3
@@ -432,8 +437,12 @@ def test_ppo_loss_fwd_bwd(dev, B, A, frac_invalid, kl_coeff):
     adv_std, adv_mean = torch.std_mean(O._masked_select(adv, valids, num_invalids))
     advn = (adv - adv_mean) / torch.clamp_min(adv_std, 1e-7)
     pl = -O._masked_select(torch.min(ratio * advn, torch.clamp(ratio, clip_lo, clip_hi) * advn), valids, num_invalids).mean()
-    ent = O._masked_select(O.cat_entropy(logits), valids, num_invalids)
-    el = -cfg.exploration_loss_coeff * ent.mean()
+    if expl == "entropy":
+        ent = O._masked_select(O.cat_entropy(logits), valids, num_invalids)
+        el = -cfg.exploration_loss_coeff * ent.mean()
+    else:   # learner.py:479-486
+        skl = O._masked_select(O.cat_symmetric_kl_with_uniform_prior(logits), valids, num_invalids).mean()
+        el = cfg.exploration_loss_coeff * torch.clamp(skl, max=30)
     kl_old = O._masked_select(O.cat_kl(logits, logits_old), valids, num_invalids)
     kl = cfg.kl_loss_coeff * kl_old.mean()
     vc = v_old + torch.clamp(values - v_old, -cfg.ppo_clip_value, cfg.ppo_clip_value)
@@ -449,7 +458,7 @@ def test_ppo_loss_fwd_bwd(dev, B, A, frac_invalid, kl_coeff):
     ops.ppo_loss_fwd_bwd(logits.detach().to(dev), values.detach().to(dev), actions.view(-1).to(dev), lp_old.to(dev),
                          v_old.to(dev), adv.to(dev), targets.to(dev), valids.to(dev), logits_old.to(dev),
                          cfg.ppo_clip_ratio, cfg.ppo_clip_value, cfg.exploration_loss_coeff, cfg.value_loss_coeff,
-                         cfg.kl_loss_coeff, 1.0, dl, dv, stats, ws)
+                         cfg.kl_loss_coeff, 1.0, dl, dv, stats, ws, exploration_loss=expl)
     s = stats.cpu()
     LS = ops.LS
     assert int(s[LS["num_valid"]]) == B - num_invalids
