@@ -111,6 +111,25 @@ int sfb200_heads_forward(const float* h, int64_t ldh, int64_t rows, int H, int A
                          int64_t log_prob_stride, const float* policy_version_scalar, float* policy_version_out,
                          int64_t pv_stride, void* stream);
 
+/* sfb200_heads_forward / sfb200_heads_from_partials for a Tuple of Discretes: every head softmaxes and samples over its own
+ * logit segment (noise rows hold the heads' Exp(1) draws side by side, A floats); actions_f32[i*actions_stride + k] and
+ * env_actions_i32[i*K + k] receive head k's index, log_prob the sum of the heads' log-probs. */
+int sfb200_heads_forward_tuple(const float* h, int64_t ldh, int64_t rows, int H, int A, int num_heads,
+                               const int32_t* head_sizes_host, const float* Wv, const float* bv, const float* Wa,
+                               const float* ba, float* values, int64_t values_stride, float* logits,
+                               int64_t logits_stride, const float* noise, uint64_t philox_seed, uint64_t philox_offset,
+                               const int64_t* philox_offset_dev, float* actions_f32, int64_t actions_stride,
+                               int32_t* env_actions_i32, float* log_prob, int64_t log_prob_stride,
+                               const float* policy_version_scalar, float* policy_version_out, int64_t pv_stride,
+                               void* stream);
+int sfb200_heads_from_partials_tuple(const float* head_partials, int P, int64_t rows, int A, int num_heads,
+                                     const int32_t* head_sizes_host, const float* bv, const float* ba, float* values,
+                                     int64_t values_stride, float* logits, int64_t logits_stride, const float* noise,
+                                     uint64_t philox_seed, uint64_t philox_offset, const int64_t* philox_offset_dev,
+                                     float* actions_f32, int64_t actions_stride, int32_t* env_actions_i32,
+                                     float* log_prob, int64_t log_prob_stride, const float* policy_version_scalar,
+                                     float* policy_version_out, int64_t pv_stride, void* stream);
+
 /* Continuous (Box) action spaces: critic_linear + distribution_linear + ContinuousActionDistribution
  * (algo/utils/action_distributions.py:290-323 = Independent(Normal(means, clamp(exp(log_std), 1e-4, 1e4)), 1);
  * model/action_parameterization.py:33-39 when adaptive_stddev -- distribution_linear has 2*act_dim rows [means|log_std]
@@ -292,6 +311,20 @@ int sfb200_ppo_loss_fwd_bwd(const float* logits, const float* values, int A, con
                             float value_coeff, float kl_coeff, float grad_scale, float* dlogits, float* dvalues,
                             double* stats, void* workspace, void* stream);
 
+/* Tuple(Discrete(n_0), ..., Discrete(n_{K-1})) action spaces (TupleActionDistribution, action_distributions.py:197-286):
+ * K <= 8 independent categorical heads over consecutive segments of the A = sum n_k logits (head_sizes_host: K int32 on
+ * the HOST).  actions_f32 rows hold K floats (one index per head), log-prob / entropy / KL are sums over the heads. */
+int sfb200_action_ratio_tuple(const float* logits, int A, int num_heads, const int32_t* head_sizes_host,
+                              const float* actions_f32, const float* log_prob_old, int64_t batch, float* ratio,
+                              void* stream);
+int sfb200_ppo_loss_fwd_bwd_tuple(const float* logits, const float* values, int A, int num_heads,
+                                  const int32_t* head_sizes_host, const float* actions_f32, const float* log_prob_old,
+                                  const float* values_old, const float* adv, const float* targets, const uint8_t* valids,
+                                  const float* logits_old, int64_t batch, float clip_ratio, float clip_value,
+                                  float exploration_coeff, int exploration_loss, float value_coeff, float kl_coeff,
+                                  float grad_scale, float* dlogits, float* dvalues, double* stats, void* workspace,
+                                  void* stream);
+
 /* The same for a Box action space (ContinuousActionDistribution, action_distributions.py:290-323): params / params_old
  * rows are [means | log_std] (2*act_dim floats, the `action_logits` layout), actions_f32 rows act_dim floats.
  * adaptive_stddev: dlogits [B, 2*act_dim] = [d means | d log_std]; otherwise dlogits [B, act_dim] = d(pre-tanh means)
@@ -411,6 +444,19 @@ int sfb200_mask_rows(const float* src, int64_t src_stride, float* dst, int64_t d
 int sfb200_clip_adam_step(float* p, float* g, float* m, float* v, int64_t n, int64_t step, double lr, double beta1,
                           double beta2, double eps, double max_grad_norm, const double* lr_scale_num,
                           const double* lr_scale_den, float* grad_norm_out, void* workspace, void* stream);
+
+/* The reference's other optimizer, cfg.optimizer = "lamb" (algo/utils/optimizers.py:13-175 as the learner constructs it,
+ * learner.py:228-243: bias correction, weight_decay 1e-4, min_trust 0.01, no look-ahead), after the same global grad-norm
+ * clip and valid-fraction lr scaling as sfb200_clip_adam_step.  The flat buffers are described per tensor by
+ * seg_offsets / seg_numel (device int64[num_tensors]; padding between tensors is never touched) because the trust ratio
+ *   clamp(min(|p_t|, 10) / |u_t|, min_trust, 1/min_trust),  u = m_hat / (sqrt(v_hat) + eps) + weight_decay * p
+ * is per parameter tensor.  g is overwritten with u.  `step` starts at 1. */
+int64_t sfb200_lamb_workspace_bytes(int num_tensors, int64_t max_numel);
+int sfb200_clip_lamb_step(float* p, float* g, float* m, float* v, int64_t n, const int64_t* seg_offsets,
+                          const int64_t* seg_numel, int num_tensors, int64_t max_numel, int64_t step, double lr,
+                          double beta1, double beta2, double eps, double weight_decay, double min_trust,
+                          double max_grad_norm, const double* lr_scale_num, const double* lr_scale_den,
+                          float* grad_norm_out, void* workspace, void* stream);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

@@ -39,6 +39,9 @@ class OracleCfg:
 
     obs_dim: int = 64
     num_actions: int = 8  # Discrete(n), or the dimension of a Box action space when `continuous`
+    # gym.spaces.Tuple(Discrete(n_0), Discrete(n_1), ...) -> TupleActionDistribution (action_distributions.py:197-286):
+    # independent categorical heads over consecutive logit segments; num_actions is then sum(n_k)
+    action_segments: Optional[List[int]] = None
     continuous: bool = False           # gym.spaces.Box action space -> ContinuousActionDistribution
     adaptive_stddev: bool = True       # cfg.py:577: False -> one learned log-stddev vector (mujoco examples)
     continuous_tanh_scale: float = 0.0  # cfg.py:583 (only read by the non-adaptive parameterization)
@@ -57,6 +60,7 @@ class OracleCfg:
     ppo_clip_value: float = 1.0
     exploration_loss_coeff: float = 0.003
     exploration_loss: str = "entropy"   # or "symmetric_kl" (learner.py:181-186, categorical distributions only)
+    optimizer: str = "adam"             # or "lamb" (learner.py:228-243, algo/utils/optimizers.py)
     value_loss_coeff: float = 0.5
     kl_loss_coeff: float = 0.0
     max_grad_norm: float = 4.0
@@ -194,6 +198,8 @@ def num_action_params(cfg: OracleCfg) -> int:
 
 def action_width(cfg: OracleCfg) -> int:
     """calc_num_actions (action_distributions.py:16-30): width of `actions`"""
+    if cfg.action_segments:
+        return len(cfg.action_segments)
     return cfg.num_actions if cfg.continuous else 1
 
 
@@ -468,16 +474,43 @@ def gauss_kl(params_p: Tensor, params_q: Tensor) -> Tensor:
     return (0.5 * (var_ratio + t1 - 1 - var_ratio.log())).sum(-1)
 
 
+# Tuple of independent categorical heads (action_distributions.py:197-286): everything is a sum over the heads
+def tuple_split(cfg: OracleCfg, logits: Tensor):
+    return torch.split(logits, list(cfg.action_segments), dim=1)
+
+
+def tuple_sample(cfg: OracleCfg, logits: Tensor, noise_q: Tensor) -> Tensor:
+    """:243-252: each head samples on its own; noise_q [N, sum n_k] holds the heads' Exp(1) draws side by side"""
+    return torch.cat([cat_sample(l, q) for l, q in zip(tuple_split(cfg, logits), tuple_split(cfg, noise_q))], dim=1)
+
+
+def tuple_log_prob(cfg: OracleCfg, logits: Tensor, actions: Tensor) -> Tensor:
+    acts = actions.view(logits.shape[0], -1)
+    return sum(cat_log_prob(l, acts[:, k]) for k, l in enumerate(tuple_split(cfg, logits)))
+
+
 def dist_log_prob(cfg: OracleCfg, logits: Tensor, actions: Tensor) -> Tensor:
+    if cfg.action_segments:
+        return tuple_log_prob(cfg, logits, actions)
     return gauss_log_prob(logits, actions.view(logits.shape[0], -1)) if cfg.continuous else cat_log_prob(logits, actions)
 
 
 def dist_entropy(cfg: OracleCfg, logits: Tensor) -> Tensor:
+    if cfg.action_segments:
+        return sum(cat_entropy(l) for l in tuple_split(cfg, logits))
     return gauss_entropy(logits) if cfg.continuous else cat_entropy(logits)
 
 
 def dist_kl(cfg: OracleCfg, logits_p: Tensor, logits_q: Tensor) -> Tensor:
+    if cfg.action_segments:
+        return sum(cat_kl(lp, lq) for lp, lq in zip(tuple_split(cfg, logits_p), tuple_split(cfg, logits_q)))
     return gauss_kl(logits_p, logits_q) if cfg.continuous else cat_kl(logits_p, logits_q)
+
+
+def dist_symmetric_kl(cfg: OracleCfg, logits: Tensor) -> Tensor:
+    if cfg.action_segments:
+        return sum(cat_symmetric_kl_with_uniform_prior(l) for l in tuple_split(cfg, logits))
+    return cat_symmetric_kl_with_uniform_prior(logits)
 
 
 # --------------------------------------------------------------------------------------
@@ -511,7 +544,10 @@ def policy_step(cfg: OracleCfg, st: Dict[str, Tensor], obs: Tensor, noise_q: Ten
     Returns (actions int64 [N,1], logits [N,A], log_prob [N], values [N], new_rnn_state)."""
     x = normalize_obs(cfg, st, obs, update_stats=False)
     values, logits, new_state = model_forward(cfg, st, x, rnn_state)
-    if cfg.continuous:   # noise_q: [N, A] standard-normal draws
+    if cfg.action_segments:
+        actions = tuple_sample(cfg, logits, noise_q)
+        log_prob = tuple_log_prob(cfg, logits, actions)
+    elif cfg.continuous:   # noise_q: [N, A] standard-normal draws
         actions = gauss_sample(logits, noise_q)
         log_prob = gauss_log_prob(logits, actions)
     else:
@@ -543,8 +579,8 @@ class TapeVecEnv:
         t = self.t
         if actions.is_floating_point():   # Box action space [N, A]: reward = first action component, clipped
             rew = actions.view(self.num_agents, -1)[:, 0].clamp(-1.0, 1.0)
-        else:
-            rew = actions.view(-1).float() / float(self.num_actions)
+        else:                             # Discrete, or Tuple of Discretes [N, K]: first component / num_actions
+            rew = actions.view(self.num_agents, -1)[:, 0].float() / float(self.num_actions)
         terminated = ((t * 7 + env * 13) % self.term_period) == 0
         truncated = (((t + env) % self.trunc_period) == 0) & ~terminated
         self.t += 1
@@ -578,7 +614,12 @@ def rollout(
         traj["values"][:, t] = values
         traj["policy_version"][:, t] = float(policy_version)  # inference_worker.py:332
         # preprocess_actions :30-82 (discrete: int32, squeezed; Box: float, as is)
-        env_actions = actions if cfg.continuous else actions.to(torch.int32).squeeze(-1)
+        if cfg.continuous:
+            env_actions = actions
+        elif cfg.action_segments:
+            env_actions = actions.to(torch.int32)          # [N, K]: one index per head
+        else:
+            env_actions = actions.to(torch.int32).squeeze(-1)
         last_obs, rew, terminated, truncated = env.step(env_actions)
         dones = terminated | truncated  # :317
         # _process_rewards :208-213
@@ -751,7 +792,7 @@ def calculate_losses(cfg: OracleCfg, params: Dict[str, Tensor], mb: Dict[str, Te
         exploration_loss = torch.zeros(())
     elif cfg.exploration_loss == "symmetric_kl":   # _symmetric_kl_exploration_loss :479-486
         assert not cfg.continuous
-        kl_prior = _masked_select(cat_symmetric_kl_with_uniform_prior(logits), valids, num_invalids).mean()
+        kl_prior = _masked_select(dist_symmetric_kl(cfg, logits), valids, num_invalids).mean()
         if not torch.isfinite(kl_prior):
             kl_prior = torch.zeros(kl_prior.shape)
         exploration_loss = cfg.exploration_loss_coeff * torch.clamp(kl_prior, max=30)
@@ -808,6 +849,27 @@ def adam_step(p: Tensor, g: Tensor, m: Tensor, v: Tensor, step: int, lr: float, 
     p.addcdiv_(m, denom, value=-step_size)
 
 
+LAMB_WEIGHT_DECAY, LAMB_MIN_TRUST = 1e-4, 0.01   # optimizers.py:22-23 defaults (the learner passes lr, betas, eps only)
+
+
+def lamb_step(p: Tensor, g: Tensor, m: Tensor, v: Tensor, step: int, lr: float, b1: float, b2: float, eps: float):
+    """algo/utils/optimizers.py:58-134 (list-params path, bias correction on, no look-ahead); `step` starts at 1."""
+    m.mul_(b1).add_(g, alpha=(1 - b1))
+    v.mul_(b2).addcmul_(g, g, value=(1 - b2))
+    mh = m.clone().mul_(1 / (1 - b1**step))
+    vh = v.sqrt().mul_(1 / math.sqrt(1 - b2**step))
+    adam_step = mh.div_(vh.add_(eps))
+    adam_step.add_(p, alpha=LAMB_WEIGHT_DECAY)
+    weight_norm = torch.norm(p).item()
+    step_norm = torch.norm(adam_step).item()
+    if weight_norm == 0 or step_norm == 0:
+        trust_ratio = 1
+    else:
+        trust_ratio = min(weight_norm, 10.0) / step_norm
+        trust_ratio = min(max(trust_ratio, LAMB_MIN_TRUST), 1.0 / LAMB_MIN_TRUST)
+    p.add_(adam_step, alpha=-lr * trust_ratio)
+
+
 class OracleLearner:
     """State holder mirroring algo/learning/learner.py:125-255 for the path's numerics."""
 
@@ -852,7 +914,7 @@ class OracleLearner:
                 self.opt_step += 1
                 with torch.no_grad():
                     for k, g in zip(self.names, grads):
-                        adam_step(
+                        (lamb_step if cfg.optimizer == "lamb" else adam_step)(
                             self.st[k], g, self.m[k], self.v[k], self.opt_step, lr,
                             cfg.adam_beta1, cfg.adam_beta2, cfg.adam_eps,
                         )

@@ -20,6 +20,9 @@ struct HeadsOut {
     // continuous (diagonal Gaussian) action space: dist 0 = categorical, 1 = Gaussian with state-dependent log-stddev
     // (the linear layer has 2*act_dim rows), 2 = Gaussian with one learned log-stddev vector (act_dim rows)
     int dist; int act_dim; const float* learned_log_std; float tanh_scale; float* env_actions_f32;
+    // Tuple(Discrete(n_0), ..., Discrete(n_{K-1})) action space (action_distributions.py:197-286): K independent
+    // categorical heads over consecutive logit segments; num_seg <= 1 means one plain categorical
+    int num_seg; int seg_len[8];
 };
 
 constexpr float kStddevMin = 1e-4f, kStddevMax = 1e4f;   // action_distributions.py:291-292
@@ -72,6 +75,9 @@ __device__ __forceinline__ void gaussian_row_tail(float mine, int lane, int64_t 
     }
 }
 
+__device__ __forceinline__ void tuple_row_tail(float mine, int lane, int A, int64_t row, const HeadsOut& out,
+                                               const float* __restrict__ noise, uint64_t seed, uint64_t offset, float pv);
+
 // Lane a of the warp holds output a of one row (0 = value, 1..A = logits, bias included): store them and, in sampling
 // mode, run CategoricalActionDistribution (action_distributions.py:110-148) on the lanes.
 __device__ __forceinline__ void heads_row_tail(float mine, int lane, int A, int64_t row, const HeadsOut& out,
@@ -84,6 +90,10 @@ __device__ __forceinline__ void heads_row_tail(float mine, int lane, int A, int6
     const bool is_logit = lane >= 1 && lane <= A;
     if (out.logits && is_logit) out.logits[row * out.logits_stride + (lane - 1)] = mine;
     if (out.actions_f32 == nullptr) return;   // values / logits only (warp-uniform)
+    if (out.num_seg > 1) {
+        tuple_row_tail(mine, lane, A, row, out, noise, seed, offset, pv);
+        return;
+    }
 
     const float x = is_logit ? mine : -INFINITY;
     const float m = warp_max(x);
@@ -115,6 +125,53 @@ __device__ __forceinline__ void heads_row_tail(float mine, int lane, int A, int6
         out.actions_f32[row * out.actions_stride] = (float)idx;
         if (out.env_actions) out.env_actions[row] = idx;
         if (out.log_prob) out.log_prob[row * out.log_prob_stride] = lp;
+        if (out.pv_out) out.pv_out[row * out.pv_stride] = pv;
+    }
+}
+
+// TupleActionDistribution on the lanes: every head runs the categorical recipe on its own lane range; actions_f32 gets K
+// floats per row (one index per head), env_actions K int32, log_prob the sum over the heads (:231-241).
+__device__ __forceinline__ void tuple_row_tail(float mine, int lane, int A, int64_t row, const HeadsOut& out,
+                                               const float* __restrict__ noise, uint64_t seed, uint64_t offset, float pv) {
+    const bool is_logit = lane >= 1 && lane <= A;
+    float q = 1.f;
+    if (is_logit) {
+        if (noise) q = noise[row * A + (lane - 1)];
+        else {
+            curandStatePhilox4_32_10_t st;
+            curand_init(seed, (unsigned long long)(row * A + (lane - 1)), offset, &st);
+            q = fmaxf(-logf(curand_uniform(&st)), 1.0e-30f);
+        }
+    }
+    float lp_total = 0.f;
+    int start = 0;
+    const int K = out.num_seg;
+    for (int k = 0; k < K; ++k) {
+        const int n = out.seg_len[k];
+        const bool in_seg = (lane - 1) >= start && (lane - 1) < start + n;
+        const float x = in_seg ? mine : -INFINITY;
+        const float m = warp_max(x);
+        const float e = in_seg ? expf(x - m) : 0.f;
+        const float s = warp_sum(e);
+        const float p = __fdiv_rn(e, s);
+        const float logp = (x - m) - logf(s);
+        float best = in_seg ? __fdiv_rn(p, q) : -INFINITY;
+        int idx = in_seg ? (lane - 1 - start) : 0x7fffffff;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+            if (ob > best || (ob == best && oi < idx)) { best = ob; idx = oi; }
+        }
+        lp_total += __shfl_sync(0xffffffffu, logp, start + idx + 1);
+        if (lane == 0) {
+            out.actions_f32[row * out.actions_stride + k] = (float)idx;
+            if (out.env_actions) out.env_actions[row * K + k] = idx;
+        }
+        start += n;
+    }
+    if (lane == 0) {
+        if (out.log_prob) out.log_prob[row * out.log_prob_stride] = lp_total;
         if (out.pv_out) out.pv_out[row * out.pv_stride] = pv;
     }
 }
@@ -540,6 +597,48 @@ int sfb200_heads_from_partials(const float* head_partials, int P, int64_t rows, 
                                void* stream) {
     const HeadsOut out{values, values_stride, logits, logits_stride, actions_f32, actions_stride, env_actions_i32,
                        log_prob, log_prob_stride, policy_version_out, pv_stride, 0, 0, nullptr, 0.f, nullptr};
+    return heads_from_partials_impl(head_partials, P, rows, A, bv, ba, out, noise, philox_seed, philox_offset,
+                                    philox_offset_dev, policy_version_scalar, (cudaStream_t)stream);
+}
+
+static int make_tuple_out(HeadsOut& out, int A, int num_seg, const int32_t* seg_lens) {
+    SFB_CHECK_ARG(num_seg >= 1 && num_seg <= 8 && seg_lens, "heads (tuple): 1 <= number of heads <= 8");
+    int tot = 0;
+    for (int k = 0; k < num_seg; ++k) {
+        SFB_CHECK_ARG(seg_lens[k] >= 1, "heads (tuple): empty head");
+        out.seg_len[k] = seg_lens[k];
+        tot += seg_lens[k];
+    }
+    SFB_CHECK_ARG(tot == A, "heads (tuple): the heads' sizes sum to %d but distribution_linear has %d rows", tot, A);
+    out.num_seg = num_seg;
+    return 0;
+}
+
+int sfb200_heads_forward_tuple(const float* h, int64_t ldh, int64_t rows, int H, int A, int num_heads,
+                               const int32_t* head_sizes_host, const float* Wv, const float* bv, const float* Wa,
+                               const float* ba, float* values, int64_t values_stride, float* logits,
+                               int64_t logits_stride, const float* noise, uint64_t philox_seed, uint64_t philox_offset,
+                               const int64_t* philox_offset_dev, float* actions_f32, int64_t actions_stride,
+                               int32_t* env_actions_i32, float* log_prob, int64_t log_prob_stride,
+                               const float* policy_version_scalar, float* policy_version_out, int64_t pv_stride,
+                               void* stream) {
+    HeadsOut out{values, values_stride, logits, logits_stride, actions_f32, actions_stride, env_actions_i32,
+                 log_prob, log_prob_stride, policy_version_out, pv_stride, 0, 0, nullptr, 0.f, nullptr};
+    if (int rc = make_tuple_out(out, A, num_heads, head_sizes_host)) return rc;
+    return heads_forward_impl(h, ldh, rows, H, A, Wv, bv, Wa, ba, out, noise, philox_seed, philox_offset,
+                              philox_offset_dev, policy_version_scalar, (cudaStream_t)stream);
+}
+
+int sfb200_heads_from_partials_tuple(const float* head_partials, int P, int64_t rows, int A, int num_heads,
+                                     const int32_t* head_sizes_host, const float* bv, const float* ba, float* values,
+                                     int64_t values_stride, float* logits, int64_t logits_stride, const float* noise,
+                                     uint64_t philox_seed, uint64_t philox_offset, const int64_t* philox_offset_dev,
+                                     float* actions_f32, int64_t actions_stride, int32_t* env_actions_i32,
+                                     float* log_prob, int64_t log_prob_stride, const float* policy_version_scalar,
+                                     float* policy_version_out, int64_t pv_stride, void* stream) {
+    HeadsOut out{values, values_stride, logits, logits_stride, actions_f32, actions_stride, env_actions_i32,
+                 log_prob, log_prob_stride, policy_version_out, pv_stride, 0, 0, nullptr, 0.f, nullptr};
+    if (int rc = make_tuple_out(out, A, num_heads, head_sizes_host)) return rc;
     return heads_from_partials_impl(head_partials, P, rows, A, bv, ba, out, noise, philox_seed, philox_offset,
                                     philox_offset_dev, policy_version_scalar, (cudaStream_t)stream);
 }

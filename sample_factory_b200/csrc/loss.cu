@@ -282,6 +282,152 @@ __global__ void __launch_bounds__(256) ppo_loss_kernel(
     ppo_store_partials(acc, part, sm);
 }
 
+
+// Tuple of independent categorical heads (TupleActionDistribution, action_distributions.py:197-286): log-prob, entropy,
+// KL and the symmetric KL are sums over the heads; every head normalises over its own logit segment.
+struct Segs {
+    int n;
+    int len[8];
+};
+
+template <int AMAX>
+__device__ __forceinline__ void row_softmax_segs(const float (&l)[AMAX], const Segs& sg, float (&p)[AMAX],
+                                                 float (&logp)[AMAX]) {
+    int start = 0;
+    for (int k = 0; k < sg.n; ++k) {
+        const int end = start + sg.len[k];
+        float m = -INFINITY;
+#pragma unroll
+        for (int a = 0; a < AMAX; ++a)
+            if (a >= start && a < end) m = fmaxf(m, l[a]);
+        float s = 0.f;
+#pragma unroll
+        for (int a = 0; a < AMAX; ++a)
+            if (a >= start && a < end) { p[a] = expf(l[a] - m); s += p[a]; }
+        const float logs = logf(s);
+#pragma unroll
+        for (int a = 0; a < AMAX; ++a)
+            if (a >= start && a < end) { logp[a] = (l[a] - m) - logs; p[a] = __fdiv_rn(p[a], s); }
+        start = end;
+    }
+}
+
+template <int AMAX>
+__global__ void __launch_bounds__(256) ppo_loss_tuple_kernel(
+    const float* __restrict__ logits, const float* __restrict__ values, int A, Segs sg, const float* __restrict__ actions,
+    const float* __restrict__ lp_old, const float* __restrict__ v_old, const float* __restrict__ adv,
+    const float* __restrict__ targets, const uint8_t* __restrict__ valids, const float* __restrict__ logits_old,
+    int64_t batch, float clip_lo, float clip_hi, float clip_value, float c_ent, int expl_mode, float c_val, float c_kl,
+    float grad_scale, float* __restrict__ dlogits, float* __restrict__ dvalues, const double* __restrict__ stats,
+    double* __restrict__ part) {
+    __shared__ double sm[8];
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const double n_valid = stats[SFB200_LS_NUM_VALID];
+    const float adv_mean = (float)stats[SFB200_LS_ADV_MEAN];
+    const float adv_std = fmaxf((float)stats[SFB200_LS_ADV_STD], 1e-7f);
+    const float w = n_valid > 0.0 ? (float)((double)grad_scale / n_valid) : 0.f;
+    PpoAcc acc;
+
+    if (i < batch) {
+        const float v = values[i];
+        acc.s_v = v;
+        float dl[AMAX];
+#pragma unroll
+        for (int a = 0; a < AMAX; ++a) dl[a] = 0.f;
+        float dv = 0.f;
+        if (valids[i]) {
+            acc.s_cnt = 1.0;
+            float l[AMAX], p[AMAX], logp[AMAX], lq[AMAX];
+            load_row<AMAX>(logits + i * A, A, l);
+            row_softmax_segs<AMAX>(l, sg, p, logp);
+            if (logits_old) {
+                float lo[AMAX], po[AMAX];
+                load_row<AMAX>(logits_old + i * A, A, lo);
+                row_softmax_segs<AMAX>(lo, sg, po, lq);
+            }
+            // per-head terms
+            float lp = 0.f, Htot = 0.f, kltot = 0.f, skltot = 0.f;
+            float segH[8], segKL[8], segS1[8];
+            int act_idx[8];
+            int start = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                segH[k] = 0.f; segKL[k] = 0.f; segS1[k] = 0.f; act_idx[k] = -1;
+                if (k < sg.n) {
+                    const int n = sg.len[k], end = start + n;
+                    act_idx[k] = start + (int)actions[i * sg.n + k];
+                    const float u = 1.f / (float)n, log_u = -logf((float)n);
+                    float S2 = 0.f;
+#pragma unroll
+                    for (int a = 0; a < AMAX; ++a) {
+                        if (a >= start && a < end) {
+                            if (a == act_idx[k]) lp += logp[a];
+                            segH[k] -= logp[a] * p[a];
+                            if (logits_old) segKL[k] += p[a] * (logp[a] - lq[a]);
+                            segS1[k] += p[a] * (logp[a] - log_u);
+                            S2 += u * (log_u - logp[a]);
+                        }
+                    }
+                    Htot += segH[k];
+                    kltot += segKL[k];
+                    skltot += 0.5f * (segS1[k] + S2);
+                    start = end;
+                }
+            }
+            const float g_lp = ppo_policy_terms(lp, lp_old[i], adv[i], adv_mean, adv_std, clip_lo, clip_hi, w, acc);
+            acc.s_ent = Htot;
+            if (expl_mode == 1) acc.s_skl = skltot;
+            if (logits_old) { acc.s_kl = kltot; acc.m_kl = kltot; }
+            const float we = w * c_ent, wk = (logits_old ? w * c_kl : 0.f);
+            start = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if (k < sg.n) {
+                    const int n = sg.len[k], end = start + n;
+                    const float u = 1.f / (float)n, log_u = -logf((float)n);
+#pragma unroll
+                    for (int a = 0; a < AMAX; ++a) {
+                        if (a >= start && a < end) {
+                            float g = g_lp * ((a == act_idx[k] ? 1.f : 0.f) - p[a]);
+                            if (expl_mode == 1) g += we * 0.5f * (p[a] * ((logp[a] - log_u) - segS1[k]) + p[a] - u);
+                            else g += we * p[a] * (logp[a] + segH[k]);
+                            if (logits_old) g += wk * p[a] * ((logp[a] - lq[a]) - segKL[k]);
+                            dl[a] = g;
+                        }
+                    }
+                    start = end;
+                }
+            }
+            dv = ppo_value_terms(v, v_old[i], targets[i], clip_value, w, c_val, acc);
+        }
+        store_row<AMAX>(dlogits + i * A, A, dl);
+        dvalues[i] = dv;
+    }
+    ppo_store_partials(acc, part, sm);
+}
+
+template <int AMAX>
+__global__ void __launch_bounds__(256) action_ratio_tuple_kernel(const float* __restrict__ logits, int A, Segs sg,
+                                                                 const float* __restrict__ actions,
+                                                                 const float* __restrict__ lp_old, int64_t batch,
+                                                                 float* __restrict__ ratio) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= batch) return;
+    float l[AMAX], p[AMAX], logp[AMAX];
+    load_row<AMAX>(logits + i * A, A, l);
+    row_softmax_segs<AMAX>(l, sg, p, logp);
+    float lp = 0.f;
+    int start = 0;
+    for (int k = 0; k < sg.n; ++k) {
+        const int idx = start + (int)actions[i * sg.n + k];
+#pragma unroll
+        for (int a = 0; a < AMAX; ++a)
+            if (a == idx) lp += logp[a];
+        start += sg.len[k];
+    }
+    ratio[i] = clampf(expf(lp - lp_old[i]), 0.05f, 20.0f);
+}
+
 // Diagonal Gaussian policy (ContinuousActionDistribution, action_distributions.py:290-323; torch Normal / kl formulas):
 // params rows are [means | log_std] (2*Ad floats, the layout of `action_logits`), actions rows Ad floats.
 //   log_prob = sum_j -(a-m)^2 / (2 sd^2) - log sd - log sqrt(2 pi),  sd = clamp(exp(log_std), 1e-4, 1e4)
@@ -524,6 +670,65 @@ int sfb200_ppo_loss_fwd_bwd(const float* logits, const float* values, int A, con
     else if (A <= 16) SFB_PL(16);
     else SFB_PL(32);
 #undef SFB_PL
+    SFB_LAUNCH_OK();
+    ppo_loss_finalize_kernel<<<1, 256, 0, st>>>(part, (int)g, batch, exploration_coeff, exploration_loss, value_coeff, kl_coeff,
+                                                stats);
+    SFB_LAUNCH_OK();
+    return 0;
+}
+
+static int make_segs(Segs& sg, int A, int num_heads, const int32_t* head_sizes) {
+    SFB_CHECK_ARG(num_heads >= 1 && num_heads <= 8 && head_sizes, "tuple action space: 1 <= number of heads <= 8");
+    int tot = 0;
+    sg.n = num_heads;
+    for (int k = 0; k < 8; ++k) sg.len[k] = k < num_heads ? head_sizes[k] : 0;
+    for (int k = 0; k < num_heads; ++k) tot += head_sizes[k];
+    SFB_CHECK_ARG(tot == A && A <= 32, "tuple action space: head sizes must sum to A = %d (<= 32), got %d", A, tot);
+    return 0;
+}
+
+int sfb200_action_ratio_tuple(const float* logits, int A, int num_heads, const int32_t* head_sizes_host,
+                              const float* actions_f32, const float* log_prob_old, int64_t batch, float* ratio,
+                              void* stream) {
+    SFB_CHECK_ARG(logits && actions_f32 && log_prob_old && ratio && batch >= 0, "action_ratio_tuple: bad arguments");
+    Segs sg;
+    if (int rc = make_segs(sg, A, num_heads, head_sizes_host)) return rc;
+    if (batch == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned g = (unsigned)ceil_div(batch, 256);
+    if (A <= 8) action_ratio_tuple_kernel<8><<<g, 256, 0, st>>>(logits, A, sg, actions_f32, log_prob_old, batch, ratio);
+    else if (A <= 16) action_ratio_tuple_kernel<16><<<g, 256, 0, st>>>(logits, A, sg, actions_f32, log_prob_old, batch, ratio);
+    else action_ratio_tuple_kernel<32><<<g, 256, 0, st>>>(logits, A, sg, actions_f32, log_prob_old, batch, ratio);
+    SFB_LAUNCH_OK();
+    return 0;
+}
+
+int sfb200_ppo_loss_fwd_bwd_tuple(const float* logits, const float* values, int A, int num_heads,
+                                  const int32_t* head_sizes_host, const float* actions_f32, const float* log_prob_old,
+                                  const float* values_old, const float* adv, const float* targets, const uint8_t* valids,
+                                  const float* logits_old, int64_t batch, float clip_ratio, float clip_value,
+                                  float exploration_coeff, int exploration_loss, float value_coeff, float kl_coeff,
+                                  float grad_scale, float* dlogits, float* dvalues, double* stats, void* workspace,
+                                  void* stream) {
+    SFB_CHECK_ARG(logits && values && actions_f32 && log_prob_old && values_old && adv && targets && valids && dlogits &&
+                      dvalues && stats && workspace && batch > 0, "ppo_loss_fwd_bwd_tuple: bad arguments");
+    SFB_CHECK_ARG(exploration_loss == 0 || exploration_loss == 1, "ppo_loss_fwd_bwd_tuple: exploration_loss must be 0 or 1");
+    Segs sg;
+    if (int rc = make_segs(sg, A, num_heads, head_sizes_host)) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const float clip_hi = 1.0f + clip_ratio;
+    const float clip_lo = 1.0f / clip_hi;
+    const unsigned g = (unsigned)ceil_div(batch, 256);
+    double* part = (double*)workspace;
+#define SFB_PT(AM)                                                                                                       \
+    ppo_loss_tuple_kernel<AM><<<g, 256, 0, st>>>(logits, values, A, sg, actions_f32, log_prob_old, values_old, adv,       \
+                                                 targets, valids, logits_old, batch, clip_lo, clip_hi, clip_value,        \
+                                                 exploration_coeff, exploration_loss, value_coeff, kl_coeff, grad_scale,  \
+                                                 dlogits, dvalues, stats, part)
+    if (A <= 8) SFB_PT(8);
+    else if (A <= 16) SFB_PT(16);
+    else SFB_PT(32);
+#undef SFB_PT
     SFB_LAUNCH_OK();
     ppo_loss_finalize_kernel<<<1, 256, 0, st>>>(part, (int)g, batch, exploration_coeff, exploration_loss, value_coeff, kl_coeff,
                                                 stats);

@@ -208,6 +208,15 @@ class Learner:
         # image observations: gradient w.r.t. the conv head's output (pre-activation of its last layer, (C,H,W) order)
         self.dfeat = torch.empty((B, spec.conv_out_size), **f32) if spec.obs_shape is not None else None
         self.adam_ws = torch.empty(1024, **f32)
+        assert cfg.optimizer in ("adam", "lamb"), f"Unknown optimizer {cfg.optimizer}"    # learner.py:228-230
+        if cfg.optimizer == "lamb":
+            # per-tensor view of the flat buffers for the trust ratios (algo/utils/optimizers.py:101-134)
+            segs = [model._slices[n] for n in model.names]
+            numels = [math.prod(shp) for _, shp in segs]
+            self.lamb_off = torch.tensor([o for o, _ in segs], dtype=torch.int64, device=dev)
+            self.lamb_numel = torch.tensor(numels, dtype=torch.int64, device=dev)
+            self.lamb_max = max(numels)
+            self.lamb_ws = torch.empty(ops.lamb_workspace_bytes(len(segs), self.lamb_max) // 4 + 4, **f32)
         self.opt_step = 0
         self.kernel_launches = 0
 
@@ -384,9 +393,15 @@ class Learner:
         self._allreduce(m.grad)
         # :781-797 clip + Adam (+ lr scaling by the valid fraction, on device)
         self.opt_step += 1
-        ops.clip_adam_step(m.flat, m.grad, m.exp_avg, m.exp_avg_sq, self.opt_step, self.curr_lr, cfg.adam_beta1,
-                           cfg.adam_beta2, cfg.adam_eps, cfg.max_grad_norm, self.num_valid_dev, self.exp_size_total_dev(),
-                           self.grad_norm_log[log_idx : log_idx + 1], self.adam_ws)
+        if cfg.optimizer == "lamb":
+            ops.clip_lamb_step(m.flat, m.grad, m.exp_avg, m.exp_avg_sq, self.lamb_off, self.lamb_numel, self.lamb_max,
+                               self.opt_step, self.curr_lr, cfg.adam_beta1, cfg.adam_beta2, cfg.adam_eps, 1e-4, 0.01,
+                               cfg.max_grad_norm, self.num_valid_dev, self.exp_size_total_dev(),
+                               self.grad_norm_log[log_idx : log_idx + 1], self.lamb_ws)
+        else:
+            ops.clip_adam_step(m.flat, m.grad, m.exp_avg, m.exp_avg_sq, self.opt_step, self.curr_lr, cfg.adam_beta1,
+                               cfg.adam_beta2, cfg.adam_eps, cfg.max_grad_norm, self.num_valid_dev,
+                               self.exp_size_total_dev(), self.grad_norm_log[log_idx : log_idx + 1], self.adam_ws)
         self.train_step += 1                                                                         # :388-392
 
     def exp_size_total_dev(self) -> Tensor:

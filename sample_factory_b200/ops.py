@@ -493,6 +493,24 @@ def clip_adam_step(p: Tensor, g: Tensor, m: Tensor, v: Tensor, step: int, lr: fl
                workspace.data_ptr(), _stream())
 
 
+def lamb_workspace_bytes(num_tensors: int, max_numel: int) -> int:
+    return lib().query("sfb200_lamb_workspace_bytes", num_tensors, max_numel)
+
+
+def clip_lamb_step(p: Tensor, g: Tensor, m: Tensor, v: Tensor, seg_offsets: Tensor, seg_numel: Tensor, max_numel: int,
+                   step: int, lr: float, beta1: float, beta2: float, eps: float, weight_decay: float, min_trust: float,
+                   max_grad_norm: float, lr_scale_num: Optional[Tensor], lr_scale_den: Optional[Tensor],
+                   grad_norm_out: Optional[Tensor], workspace: Tensor) -> None:
+    """LAMB on the flat buffers; seg_offsets / seg_numel: int64 device tensors, one entry per parameter tensor"""
+    for t in (p, g, m, v):
+        assert t.is_contiguous() and t.dim() == 1
+    T = seg_offsets.numel()
+    assert seg_numel.numel() == T and workspace.numel() * workspace.element_size() >= lamb_workspace_bytes(T, max_numel)
+    lib().call("sfb200_clip_lamb_step", _p(p, F32), _p(g, F32), _p(m, F32), _p(v, F32), p.numel(), _p(seg_offsets, I64),
+               _p(seg_numel, I64), T, max_numel, step, lr, beta1, beta2, eps, weight_decay, min_trust, max_grad_norm,
+               _p(lr_scale_num, F64), _p(lr_scale_den, F64), _p(grad_norm_out, F32), workspace.data_ptr(), _stream())
+
+
 # ------------------------------------------------------------------------------------------------ recurrent core
 def _rs(t: Optional[Tensor]) -> int:
     return 0 if t is None else (t.stride(0) if t.dim() > 0 else 1)

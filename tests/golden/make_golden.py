@@ -50,9 +50,10 @@ OUT_DIR = os.path.dirname(os.path.abspath(__file__))
 class RefTapeEnv(gym.Env):
     """Adapter: TapeVecEnv behind the reference's batched-env contract (make_env.py:147-237)."""
 
-    def __init__(self, tape_env: TapeVecEnv, continuous: bool = False, obs_shape=None):
+    def __init__(self, tape_env: TapeVecEnv, continuous: bool = False, obs_shape=None, action_segments=None):
         self.e = tape_env
         self.obs_shape = obs_shape
+        self.action_segments = action_segments
         self.num_agents = tape_env.num_agents
         self.is_multiagent = True
         self.observation_space = gym.spaces.Dict(
@@ -61,6 +62,8 @@ class RefTapeEnv(gym.Env):
         self.action_space = gym.spaces.Discrete(tape_env.num_actions)
         if obs_shape is not None:   # uint8 image observations (C, H, W) -> ConvEncoder (model/encoder.py:88-145)
             self.observation_space = gym.spaces.Dict({"obs": gym.spaces.Box(0, 255, tuple(obs_shape), np.uint8)})
+        if action_segments:   # Tuple of Discretes -> TupleActionDistribution (action_distributions.py:197-286)
+            self.action_space = gym.spaces.Tuple([gym.spaces.Discrete(n) for n in action_segments])
         if continuous:   # Box(A) action space -> ContinuousActionDistribution (action_distributions.py:290-323)
             self.action_space = gym.spaces.Box(-1.0, 1.0, (tape_env.num_actions,), np.float32)
 
@@ -71,6 +74,10 @@ class RefTapeEnv(gym.Env):
         return {"obs": self._obs(self.e.reset())}, {}
 
     def step(self, actions):
+        if self.action_segments and isinstance(actions, (list, tuple)):
+            # (a Tuple space with non-discrete members gets a LIST of per-head arrays, batched_sampling.py:44-56; an
+            # all-discrete Tuple -- the case here -- gets one int32 [N, K] array, :40-41)
+            actions = np.stack([np.asarray(a) for a in actions], axis=1)
         obs, rew, term, trunc = self.e.step(torch.as_tensor(actions))  # numpy int32 / float32 (batched_sampling.py:62-82)
         return {"obs": self._obs(obs)}, rew, term, trunc, {}
 
@@ -79,7 +86,7 @@ class RefTapeEnv(gym.Env):
 
 
 def run_case(name: str, N: int, T: int, obs_dim: int, A: int, hidden, iters: int, overrides: dict, poison: bool,
-             save_checkpoint: bool = False, continuous: bool = False, obs_shape=None):
+             save_checkpoint: bool = False, continuous: bool = False, obs_shape=None, action_segments=None):
     torch.manual_seed(1234)
     np.random.seed(1234)
     tape_len = T * iters + 1
@@ -91,7 +98,7 @@ def run_case(name: str, N: int, T: int, obs_dim: int, A: int, hidden, iters: int
     tape_env = TapeVecEnv(tape, A)
 
     env_name = f"tape_{name}"
-    register_env(env_name, lambda full_env_name, cfg, env_config, render_mode=None: RefTapeEnv(tape_env, continuous, obs_shape))
+    register_env(env_name, lambda full_env_name, cfg, env_config, render_mode=None: RefTapeEnv(tape_env, continuous, obs_shape, action_segments))
 
     cfg = default_cfg(env=env_name, experiment=f"golden_{name}")
     cfg.device = "cpu"
@@ -172,7 +179,16 @@ def run_case(name: str, N: int, T: int, obs_dim: int, A: int, hidden, iters: int
                 policy_outputs = ac(normalized_obs, rnn_states)
                 rng_after = torch.get_rng_state()
                 torch.set_rng_state(rng_before)
-                if continuous:
+                if action_segments:
+                    # every head draws its own multinomial, in order (action_distributions.py:243-252)
+                    qs = []
+                    for k, lk in enumerate(torch.split(policy_outputs["action_logits"], list(action_segments), dim=1)):
+                        pk = torch.softmax(lk, -1)
+                        qk = torch.empty_like(pk).exponential_()
+                        assert torch.equal(torch.argmax(pk / qk, -1), policy_outputs["actions"][:, k]), "multinomial identity"
+                        qs.append(qk)
+                    q = torch.cat(qs, dim=1)
+                elif continuous:
                     # recover the N(0,1) draws Normal.sample() consumed (SURVEY App.C) and prove  a == eps*std + mean
                     params = policy_outputs["action_logits"]
                     mu, log_std = torch.chunk(params, 2, dim=1)
@@ -256,7 +272,8 @@ def run_case(name: str, N: int, T: int, obs_dim: int, A: int, hidden, iters: int
         print("checkpoint fixture:", os.path.basename(files[-1]))
 
     meta = dict(N=N, T=T, obs_dim=obs_dim, A=A, hidden=list(hidden), iters=iters, poison=poison, continuous=continuous,
-                obs_shape=None if obs_shape is None else tuple(obs_shape), **overrides)
+                obs_shape=None if obs_shape is None else tuple(obs_shape),
+                action_segments=None if action_segments is None else list(action_segments), **overrides)
     out["meta"] = np.array(repr(meta))
     # a few flags the oracle needs, straight from the reference cfg object
     for k in ["gamma", "gae_lambda", "ppo_clip_ratio", "ppo_clip_value", "exploration_loss_coeff", "value_loss_coeff",
@@ -268,6 +285,7 @@ def run_case(name: str, N: int, T: int, obs_dim: int, A: int, hidden, iters: int
         out[f"cfg/{k}"] = np.float64(getattr(cfg, k))
     out["cfg/nonlinearity"] = np.array(cfg.nonlinearity)
     out["cfg/exploration_loss"] = np.array(cfg.exploration_loss)
+    out["cfg/optimizer"] = np.array(cfg.optimizer)
     out["cfg/encoder_conv_architecture"] = np.array(cfg.encoder_conv_architecture)
     out["cfg/encoder_conv_mlp_layers"] = np.array(list(cfg.encoder_conv_mlp_layers), dtype=np.int64)
     out["cfg/continuous"] = np.bool_(continuous)
@@ -373,6 +391,18 @@ if __name__ == "__main__":
         "tiny_symkl", N=32, T=8, obs_dim=16, A=5, hidden=[64, 64], iters=2,
         overrides=dict(batch_size=128, num_batches_per_epoch=2, num_epochs=1, exploration_loss="symmetric_kl",
                        exploration_loss_coeff=0.01),
+        poison=True,
+    )
+    # Tuple(Discrete(3), Discrete(2), Discrete(4)) action space: three independent categorical heads over 9 logits
+    run_case(
+        "tiny_tuple", N=32, T=8, obs_dim=16, A=9, hidden=[64, 64], iters=2,
+        overrides=dict(batch_size=128, num_batches_per_epoch=2, num_epochs=1, kl_loss_coeff=0.05),
+        poison=True, action_segments=[3, 2, 4],
+    )
+    # LAMB optimizer (algo/utils/optimizers.py) instead of Adam: per-tensor trust ratios, weight decay 1e-4
+    run_case(
+        "tiny_lamb", N=32, T=8, obs_dim=16, A=8, hidden=[64, 64], iters=2,
+        overrides=dict(batch_size=128, num_batches_per_epoch=2, num_epochs=2, optimizer="lamb", learning_rate=3e-3),
         poison=True,
     )
     # cfg-2 hyper-parameters and model (300 553 params) at a reduced env count

@@ -14,7 +14,7 @@ def load_case(name):
     z = np.load(os.path.join(GOLDEN_DIR, f"{name}.npz"), allow_pickle=False)
     meta = ast.literal_eval(str(z["meta"]))
     _arrays = ("cfg/rnn_type", "cfg/nonlinearity", "cfg/encoder_conv_architecture", "cfg/encoder_conv_mlp_layers",
-               "cfg/exploration_loss")
+               "cfg/exploration_loss", "cfg/optimizer")
     c = {k[4:]: z[k].item() for k in z.files if k.startswith("cfg/") and k not in _arrays}
     cfg = O.OracleCfg(
         obs_dim=meta["obs_dim"], num_actions=meta["A"], encoder_mlp_layers=list(meta["hidden"]),
@@ -34,8 +34,10 @@ def load_case(name):
         continuous=bool(c.get("continuous", False)), adaptive_stddev=bool(c.get("adaptive_stddev", True)),
         continuous_tanh_scale=float(c.get("continuous_tanh_scale", 0.0)), initial_stddev=float(c.get("initial_stddev", 1.0)),
         exploration_loss=str(z["cfg/exploration_loss"]) if "cfg/exploration_loss" in z.files else "entropy",
+        optimizer=str(z["cfg/optimizer"]) if "cfg/optimizer" in z.files else "adam",
         obs_scale=float(c.get("obs_scale", 1.0)), obs_subtract_mean=float(c.get("obs_subtract_mean", 0.0)),
         obs_shape=tuple(meta["obs_shape"]) if meta.get("obs_shape") else None,
+        action_segments=list(meta["action_segments"]) if meta.get("action_segments") else None,
         encoder_conv_architecture=(str(z["cfg/encoder_conv_architecture"]) if "cfg/encoder_conv_architecture" in z.files
                                    else "convnet_atari"),
         encoder_conv_mlp_layers=([int(v) for v in z["cfg/encoder_conv_mlp_layers"]] if "cfg/encoder_conv_mlp_layers" in z.files

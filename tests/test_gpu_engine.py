@@ -22,7 +22,7 @@ def make_cfg(ocfg: O.OracleCfg, **over):
               "max_grad_norm", "learning_rate", "adam_eps", "adam_beta1", "adam_beta2", "normalize_input",
               "normalize_returns", "value_bootstrap", "with_vtrace", "vtrace_rho", "vtrace_c", "reward_scale",
               "reward_clip", "max_policy_lag", "nonlinearity", "obs_subtract_mean", "obs_scale", "use_rnn", "rnn_type",
-              "rnn_size", "adaptive_stddev", "continuous_tanh_scale", "initial_stddev", "exploration_loss"]:
+              "rnn_size", "adaptive_stddev", "continuous_tanh_scale", "initial_stddev", "exploration_loss", "optimizer"]:
         setattr(cfg, k, getattr(ocfg, k))
     cfg.encoder_mlp_layers = list(ocfg.encoder_mlp_layers)
     cfg.decoder_mlp_layers = list(ocfg.decoder_mlp_layers)
@@ -75,7 +75,7 @@ def _need(engine):
         pytest.skip("tcgen05 engine not available")
 
 
-GOLDEN_CASES = ["tiny_gae", "tiny_vtrace", "tiny_gru", "tiny_lstm", "cfg2_small", "tiny_gauss", "tiny_gauss_adaptive", "tiny_conv", "tiny_symkl"]
+GOLDEN_CASES = ["tiny_gae", "tiny_vtrace", "tiny_gru", "tiny_lstm", "cfg2_small", "tiny_gauss", "tiny_gauss_adaptive", "tiny_conv", "tiny_symkl", "tiny_lamb"]
 
 
 @pytest.mark.parametrize("engine", ENGINES)

@@ -960,3 +960,51 @@ def test_normalize_obs_uint8(dev):
     ops.sampler_pre_step(x.to(dev), traj[:, 1], torch.zeros(rows, 1, device=dev), traj_rnn[:, 1], xn, mean.to(dev),
                          var.to(dev), 0.0, 1.0 / 255.0)
     assert torch.equal(traj[:, 1].cpu(), x) and torch.all(traj[:, 0] == 0) and torch.equal(xn.cpu(), ref)
+
+
+def test_clip_lamb_step(dev):
+    """sfb200_clip_lamb_step vs the oracle's restatement of algo/utils/optimizers.py (pinned by the tiny_lamb golden):
+    three steps on a padded flat buffer with tensors of very different norms (trust ratio clamped at both ends)."""
+    ops = _ops()
+    shapes = [(64, 16), (64,), (5, 64), (5,), (1, 64), (1,)]
+    numels = [int(np.prod(sh)) for sh in shapes]
+    offs, off = [], 0
+    for n in numels:
+        offs.append(off)
+        off += (n + 63) // 64 * 64
+    total = off
+    scales = [1.0, 1e-4, 30.0, 0.0, 0.5, 2.0]     # |p| = 0 -> trust 1 ; |p| large -> min(|p|, 10) ; tiny |p| -> min_trust
+    ps = [torch.randn(n, generator=g(170 + i)) * sc for i, (n, sc) in enumerate(zip(numels, scales))]
+    ms = [torch.zeros(n) for n in numels]
+    vs = [torch.zeros(n) for n in numels]
+    flat = torch.zeros(total)
+    for p_, o, n in zip(ps, offs, numels):
+        flat[o: o + n] = p_
+    pd = flat.to(dev)
+    md, vd = torch.zeros(total, device=dev), torch.zeros(total, device=dev)
+    seg_off = torch.tensor(offs, dtype=torch.int64, device=dev)
+    seg_n = torch.tensor(numels, dtype=torch.int64, device=dev)
+    ws = torch.empty(ops.lamb_workspace_bytes(len(shapes), max(numels)) // 4 + 4, device=dev)
+    gn = torch.zeros(1, device=dev)
+    lr, b1, b2, eps, max_norm = 3e-3, 0.9, 0.999, 1e-6, 0.7
+    for step in range(1, 4):
+        gs = [torch.randn(n, generator=g(180 + 10 * step + i)) * 0.3 for i, n in enumerate(numels)]
+        gflat = torch.zeros(total)
+        for g_, o, n in zip(gs, offs, numels):
+            gflat[o: o + n] = g_
+        gd = gflat.to(dev)
+        ops.clip_lamb_step(pd, gd, md, vd, seg_off, seg_n, max(numels), step, lr, b1, b2, eps, 1e-4, 0.01, max_norm, None,
+                           None, gn, ws)
+        gl = [x.clone() for x in gs]
+        total_norm = O.clip_grad_norm_(gl, max_norm)
+        assert abs(gn.item() - float(total_norm)) < 1e-5 * max(1.0, float(total_norm))
+        for p_, g_, m_, v_ in zip(ps, gl, ms, vs):
+            O.lamb_step(p_, g_, m_, v_, step, lr, b1, b2, eps)
+        got = pd.cpu()
+        for p_, o, n in zip(ps, offs, numels):
+            np.testing.assert_allclose(got[o: o + n].numpy(), p_.numpy(), atol=2e-6, rtol=2e-5)
+    # padding between the tensors is never touched
+    mask = torch.ones(total, dtype=torch.bool)
+    for o, n in zip(offs, numels):
+        mask[o: o + n] = False
+    assert torch.all(pd.cpu()[mask] == 0) and torch.all(md.cpu()[mask] == 0)
