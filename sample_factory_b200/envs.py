@@ -52,7 +52,7 @@ class TapeVecEnv:
     is_gpu_env = True
 
     def __init__(self, tape: Tensor, num_actions: int, term_period: int = 37, trunc_period: int = 11,
-                 env_index_offset: int = 0, continuous: bool = False, obs_shape=None):
+                 env_index_offset: int = 0, continuous: bool = False, obs_shape=None, action_segments=None):
         assert tape.is_cuda and tape.dim() == 3 and tape.is_contiguous()
         assert tape.dtype in (torch.float32, torch.uint8)
         self.tape = tape
@@ -64,6 +64,9 @@ class TapeVecEnv:
         # continuous: Box(num_actions) action space, actions arrive as float32 [num_agents, num_actions] and
         # reward = clamp(actions[:, 0], -1, 1); otherwise Discrete(num_actions), int32 [num_agents]
         self.continuous = continuous
+        # Tuple(Discrete(n_0), ...) action space: actions arrive as int32 [num_agents, K]; reward = actions[:, 0] / num_actions
+        # with num_actions = sum(n_k) (same rule as the oracle's env)
+        self.action_segments = None if action_segments is None else list(action_segments)
         self.tape_len, self.num_agents, self.obs_dim = tape.shape
         self.num_actions = num_actions
         self.term_period, self.trunc_period = term_period, trunc_period
@@ -78,6 +81,7 @@ class TapeVecEnv:
         # the env kernel copies observation rows as 32-bit words: uint8 rows are handed over as float32 views
         self._tape_w = tape.view(torch.float32) if self.obs_uint8 else tape
         self._obs_w = self.obs.view(torch.float32) if self.obs_uint8 else self.obs
+        self._a0 = torch.empty(self.num_agents, dtype=torch.int32, device=dev) if self.action_segments else None
 
     def reset(self) -> Tensor:
         self.step_counter.zero_()
@@ -90,6 +94,9 @@ class TapeVecEnv:
                                          self.step_counter, 0, self._tape_w, self._obs_w, self.rew, self.terminated,
                                          self.truncated)
         else:
+            if self.action_segments:
+                self._a0.copy_(actions[:, 0])      # first head's index (a strided gather; this env is test scaffolding)
+                actions = self._a0
             ops.tape_env_step(actions, self.num_actions, self.env_index_offset, self.term_period, self.trunc_period,
                               self.step_counter, 0, self._tape_w, self._obs_w, self.rew, self.terminated, self.truncated)
         return self.obs, self.rew, self.terminated, self.truncated

@@ -295,7 +295,7 @@ class Learner:
         A = spec.num_action_params
         x0 = self.obs_flat_compact[sl]
         actions = batch["actions"].view(self.E, spec.action_width)[sl]
-        if not spec.continuous:
+        if not spec.continuous and not spec.action_segments:
             actions = actions.view(-1)
         lp_old = batch["log_prob_actions"].view(self.E)[sl]
         logits_old = batch["action_logits"].view(self.E, A)[sl]
@@ -312,7 +312,9 @@ class Learner:
         Wv, bv = m.critic
         Wa, ba = m.actor
         if cfg.with_vtrace:                                                                          # :602-640
-            if spec.continuous:
+            if spec.action_segments:
+                ops.action_ratio_tuple(self.mb_logits, spec.action_segments, actions, lp_old, self.ratio)
+            elif spec.continuous:
                 ops.action_ratio_continuous(self.mb_logits, actions, lp_old, self.ratio)
             else:
                 ops.action_ratio(self.mb_logits, actions, lp_old, self.ratio)
@@ -329,7 +331,13 @@ class Learner:
         else:
             ops.adv_stats(adv, valids, self.loss_stats, None, self.loss_ws)
         # losses forward + backward (:651-657, :779)
-        if spec.continuous:
+        if spec.action_segments:
+            ops.ppo_loss_fwd_bwd_tuple(self.mb_logits, self.mb_values, spec.action_segments, actions, lp_old, v_old, adv,
+                                       targets, valids, logits_old, cfg.ppo_clip_ratio, cfg.ppo_clip_value,
+                                       cfg.exploration_loss_coeff, cfg.value_loss_coeff, cfg.kl_loss_coeff, 1.0,
+                                       self.dlogits, self.dvalues, self.loss_stats, self.loss_ws,
+                                       exploration_loss=cfg.exploration_loss)
+        elif spec.continuous:
             ops.ppo_loss_fwd_bwd_continuous(self.mb_logits, self.mb_values, spec.adaptive_stddev, spec.continuous_tanh_scale,
                                             actions, lp_old, v_old, adv, targets, valids, logits_old, cfg.ppo_clip_ratio,
                                             cfg.ppo_clip_value, cfg.exploration_loss_coeff, cfg.value_loss_coeff,

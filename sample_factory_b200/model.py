@@ -38,6 +38,9 @@ class ModelSpec:
     adaptive_stddev: bool = True        # cfg.py:577; False -> one learned log-stddev vector (action_parameterization.py:42)
     continuous_tanh_scale: float = 0.0  # cfg.py:583
     initial_stddev: float = 1.0         # cfg.py:591
+    # Tuple(Discrete(n_0), ..., Discrete(n_{K-1})) action space (action_distributions.py:197-286): the heads' sizes;
+    # num_actions is then sum(n_k) (the number of logits)
+    action_segments: Optional[List[int]] = None
     # image observations: obs_shape = (C, H, W) selects the ConvEncoder (model/encoder.py:88-145); obs_dim = C*H*W and the
     # fully connected layers after the conv head (encoder_conv_mlp_layers) take the place of encoder_mlp_layers
     obs_shape: Optional[Tuple[int, int, int]] = None
@@ -95,6 +98,7 @@ class ModelSpec:
                    encoder_conv_architecture=getattr(cfg, "encoder_conv_architecture", "convnet_atari"),
                    encoder_conv_mlp_layers=list(getattr(cfg, "encoder_conv_mlp_layers", [512])),
                    obs_uint8=bool(getattr(env, "obs_uint8", False)),
+                   action_segments=(list(env.action_segments) if getattr(env, "action_segments", None) else None),
                    continuous=bool(getattr(env, "continuous", False)),
                    adaptive_stddev=bool(getattr(cfg, "adaptive_stddev", True)),
                    continuous_tanh_scale=float(getattr(cfg, "continuous_tanh_scale", 0.0)),
@@ -115,6 +119,8 @@ class ModelSpec:
     @property
     def action_width(self) -> int:
         """calc_num_actions (:16-30): width of `actions`"""
+        if self.action_segments:
+            return len(self.action_segments)
         return self.num_actions if self.continuous else 1
 
     @property

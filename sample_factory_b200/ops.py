@@ -135,6 +135,58 @@ def heads_forward(h: Tensor, Wv: Tensor, bv: Tensor, Wa: Tensor, ba: Tensor, val
                None if policy_version_out is None else policy_version_out.data_ptr(), pv_stride, _stream())
 
 
+def _seg_array(head_sizes):
+    import ctypes
+
+    return (ctypes.c_int32 * len(head_sizes))(*[int(n) for n in head_sizes])
+
+
+def _cat_tail_args(values, values_stride, logits, logits_stride, noise, philox_seed, philox_offset, philox_offset_dev,
+                   actions_f32, actions_stride, env_actions, log_prob, log_prob_stride, policy_version_scalar,
+                   policy_version_out, pv_stride):
+    assert noise is None or noise.is_contiguous()
+    return (values.data_ptr(), values_stride, None if logits is None else logits.data_ptr(), logits_stride,
+            _p(noise, F32), philox_seed, philox_offset, _p(philox_offset_dev, I64),
+            None if actions_f32 is None else actions_f32.data_ptr(), actions_stride, _p(env_actions, I32),
+            None if log_prob is None else log_prob.data_ptr(), log_prob_stride, _p(policy_version_scalar, F32),
+            None if policy_version_out is None else policy_version_out.data_ptr(), pv_stride, _stream())
+
+
+def heads_forward_tuple(h: Tensor, Wv: Tensor, bv: Tensor, Wa: Tensor, ba: Tensor, head_sizes, values: Tensor,
+                        values_stride: int, logits: Optional[Tensor] = None, logits_stride: int = 0,
+                        noise: Optional[Tensor] = None, philox_seed: int = 0, philox_offset: int = 0,
+                        philox_offset_dev: Optional[Tensor] = None, actions_f32: Optional[Tensor] = None,
+                        actions_stride: int = 0, env_actions: Optional[Tensor] = None,
+                        log_prob: Optional[Tensor] = None, log_prob_stride: int = 0,
+                        policy_version_scalar: Optional[Tensor] = None, policy_version_out: Optional[Tensor] = None,
+                        pv_stride: int = 0) -> None:
+    """Tuple(Discrete(n_0), ...) action space: `actions_f32` rows hold one index per head, env_actions int32 [rows, K]"""
+    rows, H = h.shape
+    A = Wa.shape[0]
+    assert Wa.is_contiguous() and Wv.is_contiguous() and sum(head_sizes) == A
+    lib().call("sfb200_heads_forward_tuple", _p(h, F32), h.stride(0), rows, H, A, len(head_sizes), _seg_array(head_sizes),
+               _p(Wv, F32), _p(bv, F32), _p(Wa, F32), _p(ba, F32),
+               *_cat_tail_args(values, values_stride, logits, logits_stride, noise, philox_seed, philox_offset,
+                               philox_offset_dev, actions_f32, actions_stride, env_actions, log_prob, log_prob_stride,
+                               policy_version_scalar, policy_version_out, pv_stride))
+
+
+def heads_from_partials_tuple(head_partials: Tensor, P: int, rows: int, bv: Tensor, ba: Tensor, head_sizes,
+                              values: Tensor, values_stride: int, logits: Optional[Tensor] = None,
+                              logits_stride: int = 0, noise: Optional[Tensor] = None, philox_seed: int = 0,
+                              philox_offset: int = 0, philox_offset_dev: Optional[Tensor] = None,
+                              actions_f32: Optional[Tensor] = None, actions_stride: int = 0,
+                              env_actions: Optional[Tensor] = None, log_prob: Optional[Tensor] = None,
+                              log_prob_stride: int = 0, policy_version_scalar: Optional[Tensor] = None,
+                              policy_version_out: Optional[Tensor] = None, pv_stride: int = 0) -> None:
+    A = ba.shape[0]
+    lib().call("sfb200_heads_from_partials_tuple", _p(head_partials, F32), P, rows, A, len(head_sizes),
+               _seg_array(head_sizes), _p(bv, F32), _p(ba, F32),
+               *_cat_tail_args(values, values_stride, logits, logits_stride, noise, philox_seed, philox_offset,
+                               philox_offset_dev, actions_f32, actions_stride, env_actions, log_prob, log_prob_stride,
+                               policy_version_scalar, policy_version_out, pv_stride))
+
+
 def _cont_tail_args(values, values_stride, params, params_stride, noise, philox_seed, philox_offset, philox_offset_dev,
                     actions_f32, actions_stride, env_actions, log_prob, log_prob_stride, policy_version_scalar,
                     policy_version_out, pv_stride):
@@ -419,6 +471,30 @@ def ppo_loss_fwd_bwd(logits: Tensor, values: Tensor, actions_f32: Tensor, log_pr
     lib().call("sfb200_ppo_loss_fwd_bwd", _p(logits, F32), _p(values, F32), A, _p(actions_f32, F32),
                _p(log_prob_old, F32), _p(values_old, F32), _p(adv, F32), _p(targets, F32), _p(valids, U8),
                _p(logits_old, F32), B, clip_ratio, clip_value, exploration_coeff,
+               {"entropy": 0, "symmetric_kl": 1}[exploration_loss], value_coeff, kl_coeff, grad_scale,
+               _p(dlogits, F32), _p(dvalues, F32), _p(stats, F64), workspace.data_ptr(), _stream())
+
+
+def action_ratio_tuple(logits: Tensor, head_sizes, actions_f32: Tensor, log_prob_old: Tensor, ratio: Tensor) -> None:
+    B, A = logits.shape
+    assert logits.is_contiguous() and actions_f32.is_contiguous()
+    lib().call("sfb200_action_ratio_tuple", _p(logits, F32), A, len(head_sizes), _seg_array(head_sizes),
+               _p(actions_f32, F32), _p(log_prob_old, F32), B, _p(ratio, F32), _stream())
+
+
+def ppo_loss_fwd_bwd_tuple(logits: Tensor, values: Tensor, head_sizes, actions_f32: Tensor, log_prob_old: Tensor,
+                           values_old: Tensor, adv: Tensor, targets: Tensor, valids: Tensor,
+                           logits_old: Optional[Tensor], clip_ratio: float, clip_value: float,
+                           exploration_coeff: float, value_coeff: float, kl_coeff: float, grad_scale: float,
+                           dlogits: Tensor, dvalues: Tensor, stats: Tensor, workspace: Tensor,
+                           exploration_loss: str = "entropy") -> None:
+    """Tuple of Discretes: actions_f32 [B, K] (one index per head), logits / logits_old / dlogits [B, sum n_k]"""
+    B, A = logits.shape
+    assert logits.is_contiguous() and dlogits.is_contiguous() and actions_f32.is_contiguous()
+    assert workspace.numel() * workspace.element_size() >= loss_workspace_bytes(B)
+    lib().call("sfb200_ppo_loss_fwd_bwd_tuple", _p(logits, F32), _p(values, F32), A, len(head_sizes),
+               _seg_array(head_sizes), _p(actions_f32, F32), _p(log_prob_old, F32), _p(values_old, F32), _p(adv, F32),
+               _p(targets, F32), _p(valids, U8), _p(logits_old, F32), B, clip_ratio, clip_value, exploration_coeff,
                {"entropy": 0, "symmetric_kl": 1}[exploration_loss], value_coeff, kl_coeff, grad_scale,
                _p(dlogits, F32), _p(dvalues, F32), _p(stats, F64), workspace.data_ptr(), _stream())
 

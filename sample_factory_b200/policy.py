@@ -73,6 +73,11 @@ def forward_policy(model: PolicyModel, x: Tensor, outs: List[Tensor], act: int, 
             ops.heads_from_partials_continuous(plan.part, plan.P, M, bv, ba, **dk, **heads_kwargs)
         else:
             ops.heads_forward_continuous(tail, Wv, bv, Wa, ba, **dk, **heads_kwargs)
+    elif model.spec.action_segments:   # Tuple of Discretes: independent categorical heads (action_distributions.py:197-286)
+        if fused:
+            ops.heads_from_partials_tuple(plan.part, plan.P, M, bv, ba, model.spec.action_segments, **heads_kwargs)
+        else:
+            ops.heads_forward_tuple(tail, Wv, bv, Wa, ba, model.spec.action_segments, **heads_kwargs)
     elif fused:
         ops.heads_from_partials(plan.part, plan.P, M, bv, ba, **heads_kwargs)
     else:

@@ -52,6 +52,8 @@ class DeviceSampler:
         # for a Box action space
         if spec.continuous:
             self.env_actions = torch.empty((self.N, spec.num_actions), dtype=torch.float32, device=dev)
+        elif spec.action_segments:      # Tuple of Discretes: int32 [N, K] (batched_sampling.py:40-41)
+            self.env_actions = torch.empty((self.N, len(spec.action_segments)), dtype=torch.int32, device=dev)
         else:
             self.env_actions = torch.empty(self.N, dtype=torch.int32, device=dev)
         self.heads_plan = HeadsPlan(model, engine, self.N)

@@ -50,11 +50,13 @@ def build(ocfg: O.OracleCfg, N: int, state, tape, dev, engine="simt", graph=Fals
                      adaptive_stddev=ocfg.adaptive_stddev, continuous_tanh_scale=ocfg.continuous_tanh_scale,
                      initial_stddev=ocfg.initial_stddev, obs_shape=ocfg.obs_shape,
                      encoder_conv_architecture=ocfg.encoder_conv_architecture,
-                     encoder_conv_mlp_layers=list(ocfg.encoder_conv_mlp_layers), obs_uint8=tape.dtype == torch.uint8)
+                     encoder_conv_mlp_layers=list(ocfg.encoder_conv_mlp_layers), obs_uint8=tape.dtype == torch.uint8,
+                     action_segments=ocfg.action_segments)
     model = PolicyModel(spec, dev)
     model.load_state_dict(state, strict=False)
     traj = alloc_for_spec(spec, N, ocfg.rollout, dev)
-    env = TapeVecEnv(tape.to(dev).contiguous(), ocfg.num_actions, continuous=ocfg.continuous, obs_shape=ocfg.obs_shape)
+    env = TapeVecEnv(tape.to(dev).contiguous(), ocfg.num_actions, continuous=ocfg.continuous, obs_shape=ocfg.obs_shape,
+                     action_segments=ocfg.action_segments)
     sampler = DeviceSampler(cfg, env, model, traj, engine=ops.ENGINES[engine], use_cuda_graph=graph)
     learner = Learner(cfg, model, N, engine=ops.ENGINES[engine])
     return cfg, model, traj, env, sampler, learner
@@ -75,7 +77,7 @@ def _need(engine):
         pytest.skip("tcgen05 engine not available")
 
 
-GOLDEN_CASES = ["tiny_gae", "tiny_vtrace", "tiny_gru", "tiny_lstm", "cfg2_small", "tiny_gauss", "tiny_gauss_adaptive", "tiny_conv", "tiny_symkl", "tiny_lamb"]
+GOLDEN_CASES = ["tiny_gae", "tiny_vtrace", "tiny_gru", "tiny_lstm", "cfg2_small", "tiny_gauss", "tiny_gauss_adaptive", "tiny_conv", "tiny_symkl", "tiny_lamb", "tiny_tuple"]
 
 
 @pytest.mark.parametrize("engine", ENGINES)

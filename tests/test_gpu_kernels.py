@@ -1008,3 +1008,93 @@ def test_clip_lamb_step(dev):
     for o, n in zip(offs, numels):
         mask[o: o + n] = False
     assert torch.all(pd.cpu()[mask] == 0) and torch.all(md.cpu()[mask] == 0)
+
+
+# ----------------------------------------------------------------------------------------------- tuple action spaces
+@pytest.mark.parametrize("expl", ["entropy", "symmetric_kl"])
+@pytest.mark.parametrize("B,segs,frac_invalid,kl_coeff", [(64, [3, 2, 4], 0.0, 0.0), (1000, [8], 0.2, 0.1),
+                                                          (4096, [3, 3, 3, 3, 3, 3, 3, 3], 0.1, 0.3), (513, [17, 2, 5], 0.3, 0.2)])
+def test_ppo_loss_fwd_bwd_tuple(dev, B, segs, frac_invalid, kl_coeff, expl):
+    """Tuple-of-Discretes PPO loss forward + backward vs autograd through the oracle's TupleActionDistribution formulas"""
+    ops = _ops()
+    A = sum(segs)
+    cfg = O.OracleCfg(num_actions=A, action_segments=list(segs), kl_loss_coeff=kl_coeff, ppo_clip_ratio=0.1,
+                      ppo_clip_value=0.2, exploration_loss=expl, exploration_loss_coeff=0.003 if expl == "entropy" else 0.02)
+    logits = (torch.randn(B, A, generator=g(190)) * 1.5).requires_grad_(True)
+    values = torch.randn(B, generator=g(191)).requires_grad_(True)
+    logits_old = logits.detach() + torch.randn(B, A, generator=g(192)) * 0.3
+    noise = torch.empty(B, A).exponential_(generator=g(193))
+    actions = O.tuple_sample(cfg, logits_old, noise).float()
+    lp_old = O.tuple_log_prob(cfg, logits_old, actions) + torch.randn(B, generator=g(194)) * 0.05
+    v_old = values.detach() + torch.randn(B, generator=g(195)) * 0.3
+    adv = torch.randn(B, generator=g(196)) * 2 + 0.5
+    targets = torch.randn(B, generator=g(197))
+    valids = torch.rand(B, generator=g(198)) >= frac_invalid
+    num_invalids = int((~valids).sum())
+
+    clip_hi = 1.0 + cfg.ppo_clip_ratio
+    clip_lo = 1.0 / clip_hi
+    lp = O.dist_log_prob(cfg, logits, actions)
+    ratio = torch.clamp(torch.exp(lp - lp_old), 0.05, 20.0)
+    adv_std, adv_mean = torch.std_mean(O._masked_select(adv, valids, num_invalids))
+    advn = (adv - adv_mean) / torch.clamp_min(adv_std, 1e-7)
+    pl = -O._masked_select(torch.min(ratio * advn, torch.clamp(ratio, clip_lo, clip_hi) * advn), valids, num_invalids).mean()
+    if expl == "entropy":
+        el = -cfg.exploration_loss_coeff * O._masked_select(O.dist_entropy(cfg, logits), valids, num_invalids).mean()
+    else:
+        el = cfg.exploration_loss_coeff * torch.clamp(
+            O._masked_select(O.dist_symmetric_kl(cfg, logits), valids, num_invalids).mean(), max=30)
+    kl_old = O._masked_select(O.dist_kl(cfg, logits, logits_old), valids, num_invalids)
+    kl = cfg.kl_loss_coeff * kl_old.mean()
+    vc = v_old + torch.clamp(values - v_old, -cfg.ppo_clip_value, cfg.ppo_clip_value)
+    vl = O._masked_select(torch.max((values - targets) ** 2, (vc - targets) ** 2), valids, num_invalids).mean() * cfg.value_loss_coeff
+    total = pl + el + kl + vl
+    total.backward()
+
+    stats = torch.zeros(ops.LS_SIZE, dtype=torch.float64, device=dev)
+    ws = torch.empty(ops.loss_workspace_bytes(B) // 8 + 8, dtype=torch.float64, device=dev)
+    dl = torch.empty(B, A, device=dev)
+    dv = torch.empty(B, device=dev)
+    ops.adv_stats(adv.to(dev), valids.to(dev), stats, None, ws)
+    ops.ppo_loss_fwd_bwd_tuple(logits.detach().to(dev), values.detach().to(dev), segs, actions.to(dev).contiguous(),
+                               lp_old.to(dev), v_old.to(dev), adv.to(dev), targets.to(dev), valids.to(dev),
+                               logits_old.to(dev), cfg.ppo_clip_ratio, cfg.ppo_clip_value, cfg.exploration_loss_coeff,
+                               cfg.value_loss_coeff, cfg.kl_loss_coeff, 1.0, dl, dv, stats, ws, exploration_loss=expl)
+    s = stats.cpu()
+    LS = ops.LS
+    for key, ref in [("policy_loss", pl), ("value_loss", vl), ("exploration_loss", el), ("kl_loss", kl),
+                     ("kl_old_mean", kl_old.mean()), ("total_loss", total)]:
+        assert abs(s[LS[key]].item() - float(ref)) < TOL, (key, s[LS[key]].item(), float(ref))
+    np.testing.assert_allclose(dl.cpu().numpy(), logits.grad.numpy(), atol=1e-7, rtol=3e-4)
+    np.testing.assert_allclose(dv.cpu().numpy(), values.grad.numpy(), atol=1e-7, rtol=2e-4)
+    assert torch.all(dl.cpu()[~valids] == 0)
+    out = torch.empty(B, device=dev)
+    ops.action_ratio_tuple(logits.detach().to(dev), segs, actions.to(dev).contiguous(), lp_old.to(dev), out)
+    np.testing.assert_allclose(out.cpu().numpy(), ratio.detach().numpy(), rtol=3e-6, atol=1e-6)
+
+
+def test_heads_forward_tuple(dev):
+    """Tuple heads: per-head sampling / log-prob sums vs the oracle, both the dot-product kernel and the from-partials one"""
+    ops = _ops()
+    rows, H, segs = 777, 96, [3, 2, 4]
+    A = sum(segs)
+    cfg = O.OracleCfg(num_actions=A, action_segments=segs)
+    h = torch.randn(rows, H, generator=g(200))
+    Wv = torch.randn(1, H, generator=g(201)) / math.sqrt(H)
+    bv = torch.randn(1, generator=g(202))
+    Wa = torch.randn(A, H, generator=g(203)) / math.sqrt(H) * 2
+    ba = torch.randn(A, generator=g(204)) * 0.1
+    noise = torch.empty(rows, A).exponential_(generator=g(205))
+    logits_ref = torch.nn.functional.linear(h, Wa, ba)
+    a_ref = O.tuple_sample(cfg, logits_ref, noise)
+    lp_ref = O.tuple_log_prob(cfg, logits_ref, a_ref.float())
+    values = torch.empty(rows, device=dev)
+    logits = torch.empty(rows, A, device=dev)
+    actions = torch.empty(rows, len(segs), device=dev)
+    env_actions = torch.empty(rows, len(segs), dtype=torch.int32, device=dev)
+    lp = torch.empty(rows, device=dev)
+    ops.heads_forward_tuple(h.to(dev), Wv.to(dev), bv.to(dev), Wa.to(dev), ba.to(dev), segs, values, 1, logits, A,
+                            noise.to(dev), 0, 0, None, actions, len(segs), env_actions, lp, 1)
+    assert (logits.cpu() - logits_ref).abs().max().item() < TOL
+    assert torch.equal(actions.cpu().long(), a_ref) and torch.equal(env_actions.cpu().long(), a_ref)
+    assert (lp.cpu() - lp_ref).abs().max().item() < 2 * TOL
