@@ -172,7 +172,8 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------------------------------- our arm
-def make_cfg(env_name: str, engine: str, cuda_graph: bool, async_rl: bool = False, splits: int = 1):
+def make_cfg(env_name: str, engine: str, cuda_graph: bool, async_rl: bool = False, splits: int = 1,
+             learner_graph: bool = False):
     from sample_factory_b200.cfg import parse_full_cfg, parse_sf_args
 
     argv = [f"--env={env_name}", "--experiment=bench", "--train_dir=/tmp/sfb200_bench", "--restart_behavior=overwrite",
@@ -180,7 +181,7 @@ def make_cfg(env_name: str, engine: str, cuda_graph: bool, async_rl: bool = Fals
             f"--num_envs_per_worker={splits}", f"--worker_num_splits={splits}", f"--rollout={ROLLOUT}", f"--batch_size={BATCH}",
             f"--num_batches_per_epoch={N_MINIBATCH}", f"--num_epochs={N_EPOCHS}", "--encoder_mlp_layers", "512", "512",
             "--env_gpu_actions=True", "--env_gpu_observations=True", "--seed=0", f"--gemm_engine={engine}",
-            f"--cuda_graph={cuda_graph}", "--save_every_sec=1000000000"]
+            f"--cuda_graph={cuda_graph}", f"--learner_cuda_graph={learner_graph}", "--save_every_sec=1000000000"]
     parser, _ = parse_sf_args(argv)
     return parse_full_cfg(parser, argv)
 
@@ -372,29 +373,41 @@ def run_ours(args):
     # ------------------------------------------------------------------ end-to-end arm (host env, H2D/D2H inside)
     e2e = None
     if not args.no_e2e:
-        r2 = Runner(make_cfg("synthetic_tape_host", args.engine, not args.no_graph))
-        r2.init()
-        for _ in range(max(2, args.warmup)):
-            r2.iteration()
-            r2.learner.fetch_stats()
-        barrier()
-        env = r2.env
-        h0, d0 = env.h2d_bytes, env.d2h_bytes
-        stats_bytes = 0
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            r2.iteration()
-            st = r2.learner.fetch_stats()            # D2H read of the step's result (loss terms)
-            stats_bytes += (len(st) - 2) * 8
-        barrier()
-        dt = max_over_ranks(time.perf_counter() - t0)
-        e2e = dict(value=world * N_ENVS * ROLLOUT * args.steps / dt, unit=UNIT,
-                   h2d_bytes_per_step=(env.h2d_bytes - h0) // args.steps,
-                   d2h_bytes_per_step=(env.d2h_bytes - d0 + stats_bytes) // args.steps,
-                   ms_per_step=1e3 * dt / args.steps,
-                   api="sample_factory_b200.train.Runner.iteration() with a HOST env (numpy simulator, pinned staging): "
-                       "obs H2D + actions D2H every env step, loss stats D2H every iteration")
-        del r2
+        def run_e2e(async_rl: bool):
+            # the host is the bottleneck of this arm (it steps the envs): the learner's ~90 launches are replayed as one graph
+            r2 = Runner(make_cfg("synthetic_tape_host", args.engine, not args.no_graph, async_rl=async_rl,
+                                 learner_graph=not args.no_graph))
+            r2.init()
+            for _ in range(max(3, args.warmup)):
+                r2.iteration()
+                r2.learner.fetch_stats()
+            barrier()
+            env = r2.env
+            h0, d0 = env.h2d_bytes, env.d2h_bytes
+            stats_bytes = 0
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                r2.iteration()
+                st = r2.learner.fetch_stats()            # D2H read of the step's result (loss terms)
+                stats_bytes += 8 * sum(1 for v in st.values() if isinstance(v, float))
+            barrier()
+            dt = max_over_ranks(time.perf_counter() - t0)
+            out = dict(value=world * N_ENVS * ROLLOUT * args.steps / dt, unit=UNIT,
+                       h2d_bytes_per_step=(env.h2d_bytes - h0) // args.steps,
+                       d2h_bytes_per_step=(env.d2h_bytes - d0 + stats_bytes) // args.steps,
+                       ms_per_step=1e3 * dt / args.steps)
+            del r2
+            torch.cuda.empty_cache()
+            return out
+
+        e2e = run_e2e(False)
+        e2e["api"] = ("sample_factory_b200.train.Runner.iteration() with a HOST env (numpy simulator, pinned staging): "
+                      "obs H2D + actions D2H every env step, loss stats D2H every iteration; learner_cuda_graph=True")
+        if not args.no_async:
+            ea = run_e2e(True)
+            e2e["async_rl"] = dict(value=ea["value"], ms_per_step=ea["ms_per_step"],
+                                   note="same arm with async_rl=True (the reference's default): the learner's graph runs "
+                                        "on the GPU while the host steps the envs of the next rollout")
 
     cpu_baseline = None
     if world == 1 and rank == 0 and not args.no_cpu_baseline:

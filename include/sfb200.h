@@ -244,6 +244,10 @@ int sfb200_tape_env_step_continuous(const float* actions_f32, int act_dim, int64
 int sfb200_compute_valids(const int32_t* policy_id, const float* policy_version, int64_t n_traj, int T,
                           int32_t this_policy, float train_step, float max_policy_lag, uint8_t* valids,
                           void* stream);
+/* the same with the train-step counter read from device memory (a CUDA-graph-captured learner replays the launch) */
+int sfb200_compute_valids_dev(const int32_t* policy_id, const float* policy_version, int64_t n_traj, int T,
+                              int32_t this_policy, const int64_t* train_step_dev, float max_policy_lag, uint8_t* valids,
+                              void* stream);
 
 /* learner.py:969-1003 fused, warp-scan over the time axis (algo/utils/rl_utils.py:51-94):
  *   dv = normalize_returns ? clamp(values, +-5)*sigma + mu : values            (:969-978)
@@ -444,6 +448,14 @@ int sfb200_mask_rows(const float* src, int64_t src_stride, float* dst, int64_t d
 int sfb200_clip_adam_step(float* p, float* g, float* m, float* v, int64_t n, int64_t step, double lr, double beta1,
                           double beta2, double eps, double max_grad_norm, const double* lr_scale_num,
                           const double* lr_scale_den, float* grad_norm_out, void* workspace, void* stream);
+/* Graph-replayable variant: the number of optimizer steps ALREADY taken and the learning rate are read from device
+ * memory (bias corrections 1 - beta^(steps_done+1) are formed in the kernel, in double like the host path);
+ * sfb200_advance_counters(a, b) adds 1 to up to two device counters (optimizer step, policy version) afterwards. */
+int sfb200_clip_adam_step_dev(float* p, float* g, float* m, float* v, int64_t n, const int64_t* steps_done_dev,
+                              const double* lr_dev, double beta1, double beta2, double eps, double max_grad_norm,
+                              const double* lr_scale_num, const double* lr_scale_den, float* grad_norm_out,
+                              void* workspace, void* stream);
+int sfb200_advance_counters(int64_t* a, int64_t* b, void* stream);
 
 /* The reference's other optimizer, cfg.optimizer = "lamb" (algo/utils/optimizers.py:13-175 as the learner constructs it,
  * learner.py:228-243: bias correction, weight_decay 1e-4, min_trust 0.01, no look-ahead), after the same global grad-norm

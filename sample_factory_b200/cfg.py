@@ -106,6 +106,9 @@ _F = [
     # engine-specific additions
     ("gemm_engine", str, "auto", None, ["auto", "simt", "3xtf32", "tf32"]),
     ("cuda_graph", str2bool, True, None, None),
+    # replay Learner.train() as one CUDA graph (constant lr schedule, one epoch, Adam, single process); removes the host's
+    # ~90 kernel launches per iteration -- matters when the host is busy stepping CPU envs
+    ("learner_cuda_graph", str2bool, False, None, None),
 ]
 
 

@@ -275,7 +275,9 @@ __global__ void __launch_bounds__(256) tape_env_kernel(const int32_t* __restrict
 
 // ---- valids ----------------------------------------------------------------------------------------------------------
 __global__ void valids_kernel(const int32_t* __restrict__ pid, const float* __restrict__ pver, int64_t n_traj, int T,
-                              int32_t this_policy, float train_step, float max_lag, uint8_t* __restrict__ valids) {
+                              int32_t this_policy, float train_step_host, const int64_t* __restrict__ train_step_dev,
+                              float max_lag, uint8_t* __restrict__ valids) {
+    const float train_step = train_step_dev ? (float)train_step_dev[0] : train_step_host;
     const int64_t total = n_traj * (int64_t)(T + 1);
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t r = i / (T + 1);
@@ -515,15 +517,30 @@ int sfb200_tape_env_step_continuous(const float* actions_f32, int act_dim, int64
                               step_counter, step_host, tape, tape_len, dim, obs_out, rew, terminated, truncated, stream);
 }
 
-int sfb200_compute_valids(const int32_t* policy_id, const float* policy_version, int64_t n_traj, int T,
-                          int32_t this_policy, float train_step, float max_policy_lag, uint8_t* valids, void* stream) {
+static int compute_valids_impl(const int32_t* policy_id, const float* policy_version, int64_t n_traj, int T,
+                               int32_t this_policy, float train_step, const int64_t* train_step_dev,
+                               float max_policy_lag, uint8_t* valids, void* stream) {
     SFB_CHECK_ARG(policy_id && policy_version && valids && n_traj >= 0 && T > 0, "compute_valids: bad arguments");
     if (n_traj == 0) return 0;
     valids_kernel<<<grid_for(n_traj * (T + 1)), 256, 0, (cudaStream_t)stream>>>(policy_id, policy_version, n_traj, T,
-                                                                                  this_policy, train_step,
+                                                                                  this_policy, train_step, train_step_dev,
                                                                                   max_policy_lag, valids);
     SFB_LAUNCH_OK();
     return 0;
+}
+
+int sfb200_compute_valids(const int32_t* policy_id, const float* policy_version, int64_t n_traj, int T,
+                          int32_t this_policy, float train_step, float max_policy_lag, uint8_t* valids, void* stream) {
+    return compute_valids_impl(policy_id, policy_version, n_traj, T, this_policy, train_step, nullptr, max_policy_lag,
+                               valids, stream);
+}
+
+int sfb200_compute_valids_dev(const int32_t* policy_id, const float* policy_version, int64_t n_traj, int T,
+                              int32_t this_policy, const int64_t* train_step_dev, float max_policy_lag, uint8_t* valids,
+                              void* stream) {
+    SFB_CHECK_ARG(train_step_dev, "compute_valids_dev: the device train-step counter is required");
+    return compute_valids_impl(policy_id, policy_version, n_traj, T, this_policy, 0.f, train_step_dev, max_policy_lag,
+                               valids, stream);
 }
 
 int sfb200_rms_apply_scalar(float* x, int64_t n, const double* mean, const double* var, float eps, float clip,

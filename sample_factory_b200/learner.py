@@ -219,6 +219,17 @@ class Learner:
             self.lamb_ws = torch.empty(ops.lamb_workspace_bytes(len(segs), self.lamb_max) // 4 + 4, **f32)
         self.opt_step = 0
         self.kernel_launches = 0
+        # CUDA-graph replay of the whole train() (cfg.learner_cuda_graph): possible when nothing in it depends on host
+        # state -- constant lr schedule, one epoch (no early-stopping read-back), Adam, single process.  The step
+        # counters and the learning rate then live in device memory (read by the *_dev entry points).
+        self.use_graph = (bool(getattr(cfg, "learner_cuda_graph", False)) and cfg.lr_schedule == "constant" and
+                          cfg.num_epochs == 1 and cfg.optimizer == "adam" and self.world_size == 1)
+        self.counters_dev = torch.zeros(2, dtype=torch.int64, device=dev)     # [optimizer steps taken, train_step]
+        self.lr_dev = torch.full((1,), float(cfg.learning_rate), dtype=torch.float64, device=dev)
+        self._graph: Optional[torch.cuda.CUDAGraph] = None
+        self._graph_batch_ptrs = None
+        self._graph_calls = 0
+        self._graph_launches = 0
 
     # ------------------------------------------------------------------------------------------------------------
     def _allreduce(self, t: Tensor) -> None:
@@ -239,8 +250,12 @@ class Learner:
         """learner.py:943-1034 (sync mode: operates on the trajectory buffers in place like the reference)."""
         cfg, m, spec = self.cfg, self.model, self.model.spec
         N, T, D = self.N, self.T, spec.obs_dim
-        ops.compute_valids(batch["policy_id"], batch["policy_version"], self.policy_id, self.train_step,
-                           cfg.max_policy_lag, batch["valids"])                                     # :950-955
+        if self.use_graph:
+            ops.compute_valids_dev(batch["policy_id"], batch["policy_version"], self.policy_id, self.counters_dev[1:2],
+                                   cfg.max_policy_lag, batch["valids"])
+        else:
+            ops.compute_valids(batch["policy_id"], batch["policy_version"], self.policy_id, self.train_step,
+                               cfg.max_policy_lag, batch["valids"])                                 # :950-955
         obs2d = batch["obs"].view(N * (T + 1), D)
         nobs2d = self.normalized_obs.view(N * (T + 1), D)
         inv_scale = 1.0 / spec.obs_scale
@@ -406,6 +421,11 @@ class Learner:
                                self.opt_step, self.curr_lr, cfg.adam_beta1, cfg.adam_beta2, cfg.adam_eps, 1e-4, 0.01,
                                cfg.max_grad_norm, self.num_valid_dev, self.exp_size_total_dev(),
                                self.grad_norm_log[log_idx : log_idx + 1], self.lamb_ws)
+        elif self.use_graph:
+            ops.clip_adam_step_dev(m.flat, m.grad, m.exp_avg, m.exp_avg_sq, self.counters_dev[0:1], self.lr_dev,
+                                   cfg.adam_beta1, cfg.adam_beta2, cfg.adam_eps, cfg.max_grad_norm, self.num_valid_dev,
+                                   self.exp_size_total_dev(), self.grad_norm_log[log_idx : log_idx + 1], self.adam_ws)
+            ops.advance_counters(self.counters_dev[0:1], self.counters_dev[1:2])
         else:
             ops.clip_adam_step(m.flat, m.grad, m.exp_avg, m.exp_avg_sq, self.opt_step, self.curr_lr, cfg.adam_beta1,
                                cfg.adam_beta2, cfg.adam_eps, cfg.max_grad_norm, self.num_valid_dev,
@@ -421,6 +441,9 @@ class Learner:
     def train(self, batch: Dict[str, Tensor]) -> Dict[str, float]:
         """learner.py:1036-1067. `batch` is the trajectory dict (reference layout) on this learner's device."""
         cfg = self.cfg
+        self._last_batch = batch
+        if self.use_graph:
+            return self._train_graphed(batch)
         launches0 = ops.launch_count()
         self._prepare_batch(batch)
         recent_kls: List[float] = []
@@ -453,6 +476,50 @@ class Learner:
         self.env_steps += self.E * self.world_size * (cfg.env_frameskip if cfg.summaries_use_frameskip else 1)
         return dict(env_steps=self.env_steps, train_step=self.train_step)
 
+    def _train_body(self, batch: Dict[str, Tensor]) -> None:
+        """one epoch of minibatch steps with no host dependence (the graph-capturable form of train())"""
+        self._prepare_batch(batch)
+        for b in range(self.cfg.num_batches_per_epoch):
+            self._minibatch_step(batch, b, b)
+
+    def _train_graphed(self, batch: Dict[str, Tensor]) -> Dict[str, float]:
+        """train() as ONE graph launch: the first call runs eagerly (kernel attributes, allocator warm-up), the second
+        captures, later calls replay.  Host mirrors of the counters advance alongside the device ones."""
+        cfg = self.cfg
+        nmb = cfg.num_batches_per_epoch
+        ptrs = tuple(v.data_ptr() for v in batch.values())
+        if self._graph is not None and ptrs != self._graph_batch_ptrs:
+            self._graph = None                      # different trajectory buffers: capture again
+            self._graph_calls = 1
+        # the device counters / lr follow the host values whenever these were changed from outside (checkpoint resume)
+        self.counters_dev.copy_(torch.tensor([self.opt_step, self.train_step], dtype=torch.int64), non_blocking=True)
+        self.lr_dev.fill_(float(self.curr_lr))
+        opt0, train0 = self.opt_step, self.train_step
+        if self._graph_calls == 0:
+            n0 = ops.launch_count()
+            self._train_body(batch)
+            self._graph_launches = ops.launch_count() - n0
+        else:
+            if self._graph is None:
+                torch.cuda.synchronize()
+                self._graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self._graph):
+                    self._train_body(batch)
+                self._graph_batch_ptrs = ptrs
+            self._graph.replay()
+        self._graph_calls += 1
+        # _minibatch_step advanced the host mirrors during eager / capture passes only: set them explicitly
+        self.opt_step, self.train_step = opt0 + nmb, train0 + nmb
+        self.num_minibatches_done = nmb
+        self.kernel_launches = self._graph_launches
+        self.env_steps += self.E * self.world_size * (cfg.env_frameskip if cfg.summaries_use_frameskip else 1)
+        return dict(env_steps=self.env_steps, train_step=self.train_step)
+
+    @property
+    def graph_replay_launches(self) -> int:
+        """kernel launches of the last train() that happened through graph replay (not seen by the launch counter)"""
+        return self._graph_launches if (self.use_graph and self._graph is not None and self._graph_calls > 2) else 0
+
     def fetch_stats(self) -> Dict[str, float]:
         """Loss summaries of the LAST minibatch of the last train() (learner.py:843-923 keys). Host sync."""
         n = getattr(self, "num_minibatches_done", 0)
@@ -463,6 +530,15 @@ class Learner:
         out["grad_norm"] = float(self.grad_norm_log[n - 1].item())
         out["lr"] = self.curr_lr
         out["loss"] = out["total_loss"]
+        out["adam_max_second_moment"] = float(self.model.exp_avg_sq.max().item())            # learner.py:908-913
+        b = getattr(self, "_last_batch", None)
+        if b is not None:   # policy lag of the last minibatch (learner.py:915-918)
+            sl = slice((n - 1) * self.cfg.batch_size, n * self.cfg.batch_size)
+            own = b["policy_id"].view(self.E)[sl] == self.policy_id
+            vd = (float(self.train_step - 1) - b["policy_version"].view(self.E)[sl])[own]
+            if vd.numel() > 0:
+                out["version_diff_avg"], out["version_diff_min"], out["version_diff_max"] = (
+                    float(vd.mean().item()), float(vd.min().item()), float(vd.max().item()))
         return out
 
     def minibatch_log(self) -> Tensor:

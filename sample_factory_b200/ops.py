@@ -587,6 +587,33 @@ def clip_lamb_step(p: Tensor, g: Tensor, m: Tensor, v: Tensor, seg_offsets: Tens
                _p(lr_scale_num, F64), _p(lr_scale_den, F64), _p(grad_norm_out, F32), workspace.data_ptr(), _stream())
 
 
+def compute_valids_dev(policy_id: Tensor, policy_version: Tensor, this_policy: int, train_step_dev: Tensor,
+                       max_policy_lag: int, valids: Tensor) -> None:
+    """compute_valids with the train-step counter in device memory (int64[1])"""
+    n_traj, T = policy_id.shape
+    assert policy_id.is_contiguous() and policy_version.is_contiguous() and valids.is_contiguous()
+    assert valids.shape == (n_traj, T + 1)
+    lib().call("sfb200_compute_valids_dev", _p(policy_id, I32), _p(policy_version, F32), n_traj, T, this_policy,
+               _p(train_step_dev, I64), float(max_policy_lag), _p(valids, U8), _stream())
+
+
+def clip_adam_step_dev(p: Tensor, g: Tensor, m: Tensor, v: Tensor, steps_done_dev: Tensor, lr_dev: Tensor, beta1: float,
+                       beta2: float, eps: float, max_grad_norm: float, lr_scale_num: Optional[Tensor],
+                       lr_scale_den: Optional[Tensor], grad_norm_out: Optional[Tensor], workspace: Tensor) -> None:
+    """clip_adam_step with the step counter (int64[1], steps already taken) and the learning rate (float64[1]) in device
+    memory -- every argument is then static, so the launch can be replayed from a CUDA graph"""
+    for t in (p, g, m, v):
+        assert t.is_contiguous() and t.dim() == 1
+    assert workspace.numel() * workspace.element_size() >= 4096
+    lib().call("sfb200_clip_adam_step_dev", _p(p, F32), _p(g, F32), _p(m, F32), _p(v, F32), p.numel(),
+               _p(steps_done_dev, I64), _p(lr_dev, F64), beta1, beta2, eps, max_grad_norm, _p(lr_scale_num, F64),
+               _p(lr_scale_den, F64), _p(grad_norm_out, F32), workspace.data_ptr(), _stream())
+
+
+def advance_counters(a: Optional[Tensor], b: Optional[Tensor]) -> None:
+    lib().call("sfb200_advance_counters", _p(a, I64), _p(b, I64), _stream())
+
+
 # ------------------------------------------------------------------------------------------------ recurrent core
 def _rs(t: Optional[Tensor]) -> int:
     return 0 if t is None else (t.stride(0) if t.dim() > 0 else 1)

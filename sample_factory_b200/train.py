@@ -63,6 +63,8 @@ class Runner:
         self.env_steps = 0
         self.total_train_seconds = 0.0
         self.policy_avg_stats: Dict[str, List[deque]] = {}
+        self.policy_lag: List[Dict[str, float]] = [dict()]     # runner.py:132,289: version_diff_{min,avg,max} per policy
+        self.writers: Dict[int, object] = {}                   # runner.py: tensorboard writers (none: tensorboardX is absent)
         self.observers: List = []
         self.msg_handlers: Dict[str, List[Callable]] = {}
         self.fps_history: deque = deque(maxlen=64)
@@ -222,6 +224,11 @@ class Runner:
                     self.fps_history.append(fps)
                     ep = self.sampler.pop_episode_stats()
                     st = self.learner.fetch_stats()
+                    for key in ("version_diff_min", "version_diff_avg", "version_diff_max"):
+                        if key in st:
+                            self.policy_lag[0][key] = st[key]
+                    for key, val in ep.items():                    # runner.py:296-308 running episodic statistics
+                        self.policy_avg_stats.setdefault(key, [deque(maxlen=cfg.stats_avg)])[0].append(val)
                     for h in self.msg_handlers.get("episodic", []):
                         h(self, ep, 0)
                     if self.rank == 0:

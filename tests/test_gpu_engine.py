@@ -387,3 +387,41 @@ def test_split_sampler_matches_single_sampler():
     for a, b in zip(eager[1:], graphed):
         for k in a:
             assert torch.equal(a[k], b[k]), k
+
+
+def test_graphed_learner_matches_eager():
+    """cfg.learner_cuda_graph: Learner.train() replayed as ONE CUDA graph (device-resident step counters / lr) produces the
+    same parameters, Adam moments and loss statistics as the launch-by-launch learner, iteration after iteration."""
+    from sample_factory_b200 import ops
+
+    dev = torch.device("cuda", 0)
+    N, T = 128, 8
+    ocfg = O.OracleCfg(rollout=T, recurrence=1, batch_size=N * T // 2, num_batches_per_epoch=2, encoder_mlp_layers=[128, 128])
+    st0 = O.init_state(ocfg, seed=2)
+    tape = torch.randn(6 * T + 1, N, ocfg.obs_dim, generator=torch.Generator().manual_seed(3))
+    eng = "3xtf32" if ops.tc_available() else "simt"
+    cfgA, modelA, trajA, envA, samplerA, learnerA = build(ocfg, N, st0, tape, dev, engine=eng)
+    cfgB, modelB, trajB, envB, samplerB, _ = build(ocfg, N, st0, tape, dev, engine=eng)
+    from sample_factory_b200.learner import Learner
+
+    cfgB.learner_cuda_graph = True
+    learnerB = Learner(cfgB, modelB, N, engine=ops.ENGINES[eng])
+    assert learnerB.use_graph and not learnerA.use_graph
+    samplerA.reset()
+    for it in range(5):
+        noise = torch.empty(T, N, ocfg.num_actions).exponential_(generator=torch.Generator().manual_seed(20 + it)).to(dev)
+        samplerA.noise = noise
+        samplerA.set_policy_version(learnerA.train_step)
+        samplerA.rollout()
+        for k in trajA:
+            trajB[k].copy_(trajA[k])
+        learnerA.train(trajA)
+        learnerB.train(trajB)
+        torch.cuda.synchronize()
+        assert learnerA.train_step == learnerB.train_step == 2 * (it + 1)
+        assert torch.equal(modelA.flat, modelB.flat), it
+        assert torch.equal(modelA.exp_avg_sq, modelB.exp_avg_sq) and torch.equal(modelA.obs_mean, modelB.obs_mean)
+        assert torch.equal(learnerA.minibatch_log(), learnerB.minibatch_log())
+        sa, sb = learnerA.fetch_stats(), learnerB.fetch_stats()
+        assert sa["grad_norm"] == sb["grad_norm"] and sa["loss"] == sb["loss"]
+    assert learnerB.graph_replay_launches > 0 and learnerB.kernel_launches == learnerA.kernel_launches + 2  # + advance_counters
