@@ -182,6 +182,10 @@ class Learner:
         self.loss_stats_log = torch.zeros((n_mb_total, ops.LS_SIZE), dtype=torch.float64, device=dev)
         self.grad_norm_log = torch.zeros(n_mb_total, **f32)
         self.dp_partials = torch.zeros(3, dtype=torch.float64, device=dev)
+        # GAE mode: the advantages are final after _prepare_batch, so the per-minibatch (count, sum, sumsq) of ALL minibatches
+        # are taken there and made global with ONE all-reduce (instead of one per SGD step); row b serves minibatch b of
+        # every epoch.  (V-trace advantages depend on the current policy: they keep the per-step path.)
+        self.mb_partials = torch.zeros((cfg.num_batches_per_epoch, 3), dtype=torch.float64, device=dev)
         self.loss_ws = torch.empty(ops.loss_workspace_bytes(max(B, E)) // 8 + 8, dtype=torch.float64, device=dev)
         self.heads_ws = torch.empty(ops.heads_backward_workspace_bytes(spec.tail_input_size, A_lin) // 4 + 4, **f32)
         lin_ws = 4
@@ -296,11 +300,21 @@ class Learner:
             self._update_rms(r, m.ret_mean, m.ret_var, m.ret_count, self.rmean, self.rvar)
             ops.rms_apply_scalar(self.returns.view(-1), m.ret_mean, m.ret_var, denormalize=False)
         # :1021 num_invalids, kept on the device (lr scaling :788-794 happens inside the Adam kernel)
-        ops.adv_stats(self.advantages.view(-1), self.valids_flat.view(-1), self.batch_stats, None, self.loss_ws)
-        nv = self.batch_stats[ops.LS["num_valid"] : ops.LS["num_valid"] + 1]
-        if self.world_size > 1:
-            self._allreduce(nv)
-        self.num_valid_dev.copy_(nv)
+        if cfg.with_vtrace:
+            ops.adv_stats(self.advantages.view(-1), self.valids_flat.view(-1), self.batch_stats, None, self.loss_ws)
+            nv = self.batch_stats[ops.LS["num_valid"] : ops.LS["num_valid"] + 1]
+            if self.world_size > 1:
+                self._allreduce(nv)
+            self.num_valid_dev.copy_(nv)
+        else:
+            B = cfg.batch_size
+            adv_flat, val_flat = self.advantages.view(self.E), self.valids_flat.view(self.E)
+            for b in range(cfg.num_batches_per_epoch):
+                ops.adv_stats(adv_flat[b * B : (b + 1) * B], val_flat[b * B : (b + 1) * B], self.batch_stats,
+                              self.mb_partials[b], self.loss_ws)
+            if self.world_size > 1:
+                self._allreduce(self.mb_partials)
+            torch.sum(self.mb_partials[:, 0], dim=0, keepdim=True, out=self.num_valid_dev)   # global valid count
 
     # ------------------------------------------------------------------------------------------------------------
     def _minibatch_step(self, batch: Dict[str, Tensor], b: int, log_idx: int) -> None:
@@ -339,7 +353,9 @@ class Learner:
         else:
             adv, targets = self.advantages.view(self.E)[sl], self.returns.view(self.E)[sl]            # :643-644
         # :646-647 advantage statistics (global under data parallelism)
-        if self.world_size > 1:
+        if not cfg.with_vtrace:
+            ops.adv_stats_finalize(self.mb_partials[b], self.loss_stats)       # partials taken in _prepare_batch
+        elif self.world_size > 1:
             ops.adv_stats(adv, valids, self.loss_stats, self.dp_partials, self.loss_ws)
             self._allreduce(self.dp_partials)
             ops.adv_stats_finalize(self.dp_partials, self.loss_stats)
