@@ -61,6 +61,9 @@ class OracleCfg:
     exploration_loss_coeff: float = 0.003
     exploration_loss: str = "entropy"   # or "symmetric_kl" (learner.py:181-186, categorical distributions only)
     optimizer: str = "adam"             # or "lamb" (learner.py:228-243, algo/utils/optimizers.py)
+    # False -> ActorCriticSeparateWeights (model/actor_critic.py:198-322): an actor tower feeding distribution_linear and a
+    # critic tower feeding critic_linear (MLP encoders / decoders only in this restatement; rnn placeholder state size 2)
+    actor_critic_share_weights: bool = True
     value_loss_coeff: float = 0.5
     kl_loss_coeff: float = 0.0
     max_grad_norm: float = 4.0
@@ -125,20 +128,20 @@ def conv_out_shapes(cfg: "OracleCfg") -> List[Tuple[int, int, int]]:
     return out
 
 
-def enc_w(i: int) -> str:
-    return f"encoder.encoders.obs.mlp_head.{2 * i}.weight"
+def enc_w(i: int, tower: str = "") -> str:
+    return f"{tower}encoder.encoders.obs.mlp_head.{2 * i}.weight"
 
 
-def enc_b(i: int) -> str:
-    return f"encoder.encoders.obs.mlp_head.{2 * i}.bias"
+def enc_b(i: int, tower: str = "") -> str:
+    return f"{tower}encoder.encoders.obs.mlp_head.{2 * i}.bias"
 
 
-def dec_w(i: int) -> str:
-    return f"decoder.mlp.{2 * i}.weight"
+def dec_w(i: int, tower: str = "") -> str:
+    return f"{tower}decoder.mlp.{2 * i}.weight"
 
 
-def dec_b(i: int) -> str:
-    return f"decoder.mlp.{2 * i}.bias"
+def dec_b(i: int, tower: str = "") -> str:
+    return f"{tower}decoder.mlp.{2 * i}.bias"
 
 
 RNN_W_IH, RNN_W_HH, RNN_B_IH, RNN_B_HH = (
@@ -163,6 +166,20 @@ RET_MEAN, RET_VAR, RET_COUNT = (
 def param_names(cfg: OracleCfg) -> List[str]:
     """Trainable parameter order == nn.Module.parameters() order of the reference model."""
     names = []
+    if not cfg.actor_critic_share_weights:
+        # module registration order of ActorCriticSeparateWeights.__init__ (actor_critic.py:208-225)
+        assert cfg.obs_shape is None and not cfg.use_rnn
+        for tw in ("actor_", "critic_"):
+            for i in range(len(cfg.encoder_mlp_layers)):
+                names += [enc_w(i, tw), enc_b(i, tw)]
+        for tw in ("actor_", "critic_"):
+            for i in range(len(cfg.decoder_mlp_layers)):
+                names += [dec_w(i, tw), dec_b(i, tw)]
+        names += [CRITIC_W, CRITIC_B]
+        if cfg.continuous and not cfg.adaptive_stddev:
+            names += [LEARNED_STD]
+        names += [ACTION_W, ACTION_B]
+        return names
     if cfg.obs_shape is not None:
         for i in range(len(CONV_ARCH[cfg.encoder_conv_architecture])):
             names += [conv_w(i), conv_b(i)]
@@ -204,9 +221,10 @@ def action_width(cfg: OracleCfg) -> int:
 
 
 def rnn_state_size(cfg: OracleCfg) -> int:
-    """model/model_utils.py:11-24 (single layer, shared weights): 1 placeholder without RNN, H for GRU, 2H for LSTM."""
+    """model/model_utils.py:11-24 (single layer): 1 placeholder without RNN, H for GRU, 2H for LSTM; doubled when actor and
+    critic have separate weights."""
     if not cfg.use_rnn:
-        return 1
+        return 1 if cfg.actor_critic_share_weights else 2
     return cfg.rnn_size * (2 if cfg.rnn_type == "lstm" else 1)
 
 
@@ -216,7 +234,18 @@ def init_state(cfg: OracleCfg, seed: int = 0) -> Dict[str, Tensor]:
     g = torch.Generator().manual_seed(seed)
     st: Dict[str, Tensor] = {}
     d = cfg.obs_dim
-    if cfg.obs_shape is not None:
+    if not cfg.actor_critic_share_weights:
+        for tw in ("actor_", "critic_"):
+            d = cfg.obs_dim
+            for i, h in enumerate(cfg.encoder_mlp_layers):
+                st[enc_w(i, tw)] = torch.randn(h, d, generator=g) / math.sqrt(d)
+                st[enc_b(i, tw)] = torch.randn(h, generator=g) * 0.01
+                d = h
+            for i, h in enumerate(cfg.decoder_mlp_layers):
+                st[dec_w(i, tw)] = torch.randn(h, d, generator=g) / math.sqrt(d)
+                st[dec_b(i, tw)] = torch.randn(h, generator=g) * 0.01
+                d = h
+    elif cfg.obs_shape is not None:
         ci = cfg.obs_shape[0]
         for i, (co, k, _s) in enumerate(CONV_ARCH[cfg.encoder_conv_architecture]):
             st[conv_w(i)] = torch.randn(co, ci, k, k, generator=g) / math.sqrt(ci * k * k)
@@ -241,10 +270,11 @@ def init_state(cfg: OracleCfg, seed: int = 0) -> Dict[str, Tensor]:
         st[RNN_B_IH] = (torch.rand(G * H, generator=g) * 2 - 1) * k
         st[RNN_B_HH] = (torch.rand(G * H, generator=g) * 2 - 1) * k
         d = H
-    for i, h in enumerate(cfg.decoder_mlp_layers):
-        st[dec_w(i)] = torch.randn(h, d, generator=g) / math.sqrt(d)
-        st[dec_b(i)] = torch.randn(h, generator=g) * 0.01
-        d = h
+    if cfg.actor_critic_share_weights:
+        for i, h in enumerate(cfg.decoder_mlp_layers):
+            st[dec_w(i)] = torch.randn(h, d, generator=g) / math.sqrt(d)
+            st[dec_b(i)] = torch.randn(h, generator=g) * 0.01
+            d = h
     st[CRITIC_W] = torch.randn(1, d, generator=g) / math.sqrt(d)
     st[CRITIC_B] = torch.zeros(1)
     st[ACTION_W] = torch.randn(num_linear_action_outputs(cfg), d, generator=g) / math.sqrt(d)
@@ -375,8 +405,33 @@ def rnn_cell(cfg: OracleCfg, st: Dict[str, Tensor], x: Tensor, state: Tensor) ->
     return h_new, torch.cat([h_new, c_new], dim=1)
 
 
+def _tower(cfg: OracleCfg, st: Dict[str, Tensor], x: Tensor, tw: str) -> Tensor:
+    h = x
+    for i in range(len(cfg.encoder_mlp_layers)):
+        h = _act(cfg, torch.nn.functional.linear(h, st[enc_w(i, tw)], st[enc_b(i, tw)]))
+    for i in range(len(cfg.decoder_mlp_layers)):
+        h = _act(cfg, torch.nn.functional.linear(h, st[dec_w(i, tw)], st[dec_b(i, tw)]))
+    return h
+
+
+def separate_forward(cfg: OracleCfg, st: Dict[str, Tensor], x: Tensor) -> Tuple[Tensor, Tensor]:
+    """ActorCriticSeparateWeights.forward (actor_critic.py:283-318) without recurrent cores: the critic tower feeds
+    critic_linear, the actor tower feeds the action parameterization."""
+    values = torch.nn.functional.linear(_tower(cfg, st, x, "critic_"), st[CRITIC_W], st[CRITIC_B]).squeeze(-1)
+    logits = torch.nn.functional.linear(_tower(cfg, st, x, "actor_"), st[ACTION_W], st[ACTION_B])
+    if cfg.continuous and not cfg.adaptive_stddev:
+        means = logits
+        if cfg.continuous_tanh_scale > 0:
+            means = torch.tanh(means / cfg.continuous_tanh_scale) * cfg.continuous_tanh_scale
+        logits = torch.cat((means, st[LEARNED_STD].repeat(means.shape[0], 1)), dim=1)
+    return values, logits
+
+
 def model_forward(cfg: OracleCfg, st: Dict[str, Tensor], x: Tensor, rnn_state: Optional[Tensor] = None):
     """ActorCriticSharedWeights.forward (actor_critic.py:188-195): (values, logits, new_rnn_state)."""
+    if not cfg.actor_critic_share_weights:
+        values, logits = separate_forward(cfg, st, x)
+        return values, logits, rnn_state
     h = encoder_forward(cfg, st, x)
     new_state = rnn_state
     if cfg.use_rnn:
@@ -750,8 +805,13 @@ def calculate_losses(cfg: OracleCfg, params: Dict[str, Tensor], mb: Dict[str, Te
     clip_lo = 1.0 / clip_hi  # :546
     valids = mb["valids"]
 
-    head = encoder_forward(cfg, params, mb["normalized_obs"])  # forward_head :553
-    if cfg.use_rnn:
+    if not cfg.actor_critic_share_weights:
+        head = None
+    else:
+        head = encoder_forward(cfg, params, mb["normalized_obs"])  # forward_head :553
+    if head is None:
+        core = None
+    elif cfg.use_rnn:
         # :558-577 + rnn_utils.py:11-158.  The reference packs every run of steps between done-or-invalid boundaries
         # into a PackedSequence; a segment that starts inside a chunk starts from a ZERO state (rnn_utils.py:143-149,
         # is_new_episode), a segment at a chunk start from the stored rnn_state.  The same computation as a masked loop:
@@ -769,7 +829,10 @@ def calculate_losses(cfg: OracleCfg, params: Dict[str, Tensor], mb: Dict[str, Te
         core = torch.stack(outs, 1).reshape(n * R, -1)
     else:
         core = head  # ModelCoreIdentity :579
-    values, logits = tail_forward(cfg, params, core)  # :586
+    if core is None:
+        values, logits = separate_forward(cfg, params, mb["normalized_obs"])
+    else:
+        values, logits = tail_forward(cfg, params, core)  # :586
     log_prob = dist_log_prob(cfg, logits, mb["actions"])  # :588
     ratio = torch.exp(log_prob - mb["log_prob_actions"])  # :589
     ratio = torch.clamp(ratio, 0.05, 20.0)  # :592

@@ -272,6 +272,7 @@ def run_case(name: str, N: int, T: int, obs_dim: int, A: int, hidden, iters: int
         print("checkpoint fixture:", os.path.basename(files[-1]))
 
     meta = dict(N=N, T=T, obs_dim=obs_dim, A=A, hidden=list(hidden), iters=iters, poison=poison, continuous=continuous,
+                decoder=list(cfg.decoder_mlp_layers),
                 obs_shape=None if obs_shape is None else tuple(obs_shape),
                 action_segments=None if action_segments is None else list(action_segments), **overrides)
     out["meta"] = np.array(repr(meta))
@@ -289,7 +290,8 @@ def run_case(name: str, N: int, T: int, obs_dim: int, A: int, hidden, iters: int
     out["cfg/encoder_conv_architecture"] = np.array(cfg.encoder_conv_architecture)
     out["cfg/encoder_conv_mlp_layers"] = np.array(list(cfg.encoder_conv_mlp_layers), dtype=np.int64)
     out["cfg/continuous"] = np.bool_(continuous)
-    for k in ["normalize_input", "normalize_returns", "value_bootstrap", "with_vtrace", "use_rnn", "adaptive_stddev"]:
+    for k in ["normalize_input", "normalize_returns", "value_bootstrap", "with_vtrace", "use_rnn", "adaptive_stddev",
+              "actor_critic_share_weights"]:
         out[f"cfg/{k}"] = np.bool_(getattr(cfg, k))
     out["cfg/rnn_size"] = np.float64(cfg.rnn_size)
     out["cfg/rnn_type"] = np.array(cfg.rnn_type)
@@ -398,6 +400,13 @@ if __name__ == "__main__":
         "tiny_tuple", N=32, T=8, obs_dim=16, A=9, hidden=[64, 64], iters=2,
         overrides=dict(batch_size=128, num_batches_per_epoch=2, num_epochs=1, kl_loss_coeff=0.05),
         poison=True, action_segments=[3, 2, 4],
+    )
+    # separate actor / critic towers (ActorCriticSeparateWeights, model/actor_critic.py:198-322), with decoder MLPs
+    run_case(
+        "tiny_separate", N=32, T=8, obs_dim=16, A=8, hidden=[64, 48], iters=2,
+        overrides=dict(batch_size=128, num_batches_per_epoch=2, num_epochs=2, actor_critic_share_weights=False,
+                       decoder_mlp_layers=[32], value_bootstrap=True),
+        poison=True,
     )
     # LAMB optimizer (algo/utils/optimizers.py) instead of Adam: per-tensor trust ratios, weight decay 1e-4
     run_case(

@@ -18,6 +18,8 @@ def load_case(name):
     c = {k[4:]: z[k].item() for k in z.files if k.startswith("cfg/") and k not in _arrays}
     cfg = O.OracleCfg(
         obs_dim=meta["obs_dim"], num_actions=meta["A"], encoder_mlp_layers=list(meta["hidden"]),
+        decoder_mlp_layers=list(meta.get("decoder", [])),
+        actor_critic_share_weights=bool(c.get("actor_critic_share_weights", True)),
         rollout=meta["T"], recurrence=int(c["recurrence"]), batch_size=int(c["batch_size"]),
         num_batches_per_epoch=int(c["num_batches_per_epoch"]), num_epochs=int(c["num_epochs"]),
         gamma=c["gamma"], gae_lambda=c["gae_lambda"], ppo_clip_ratio=c["ppo_clip_ratio"],
