@@ -187,7 +187,8 @@ class Learner:
         # every epoch.  (V-trace advantages depend on the current policy: they keep the per-step path.)
         self.mb_partials = torch.zeros((cfg.num_batches_per_epoch, 3), dtype=torch.float64, device=dev)
         self.loss_ws = torch.empty(ops.loss_workspace_bytes(max(B, E)) // 8 + 8, dtype=torch.float64, device=dev)
-        self.heads_ws = torch.empty(ops.heads_backward_workspace_bytes(spec.tail_input_size, A_lin) // 4 + 4, **f32)
+        tail_w = spec.tail_input_size * (1 if spec.share_weights else 2)     # separate weights: [actor tail | critic tail]
+        self.heads_ws = torch.empty(ops.heads_backward_workspace_bytes(tail_w, A_lin) // 4 + 4, **f32)
         lin_ws = 4
         d = spec.fc_encoder_input
         for h in spec.fc_encoder_layers:
@@ -382,6 +383,37 @@ class Learner:
                                  cfg.kl_loss_coeff, 1.0, self.dlogits, self.dvalues, self.loss_stats, self.loss_ws,
                                  exploration_loss=cfg.exploration_loss)
         self.loss_stats_log[log_idx].copy_(self.loss_stats)
+        if self.heads_plan.separate:
+            self._backward_separate(x0)
+        else:
+            self._backward_shared(batch, x, x0, sl, valids)
+        # gradient all-reduce: ONE NCCL call on the flat buffer (SURVEY 8e); mean over ranks is folded into the sums:
+        # each rank's loss already divides by the GLOBAL valid count, so the rank gradients simply add up.
+        self._allreduce(m.grad)
+        # :781-797 clip + Adam (+ lr scaling by the valid fraction, on device)
+        self.opt_step += 1
+        if cfg.optimizer == "lamb":
+            ops.clip_lamb_step(m.flat, m.grad, m.exp_avg, m.exp_avg_sq, self.lamb_off, self.lamb_numel, self.lamb_max,
+                               self.opt_step, self.curr_lr, cfg.adam_beta1, cfg.adam_beta2, cfg.adam_eps, 1e-4, 0.01,
+                               cfg.max_grad_norm, self.num_valid_dev, self.exp_size_total_dev(),
+                               self.grad_norm_log[log_idx : log_idx + 1], self.lamb_ws)
+        elif self.use_graph:
+            ops.clip_adam_step_dev(m.flat, m.grad, m.exp_avg, m.exp_avg_sq, self.counters_dev[0:1], self.lr_dev,
+                                   cfg.adam_beta1, cfg.adam_beta2, cfg.adam_eps, cfg.max_grad_norm, self.num_valid_dev,
+                                   self.exp_size_total_dev(), self.grad_norm_log[log_idx : log_idx + 1], self.adam_ws)
+            ops.advance_counters(self.counters_dev[0:1], self.counters_dev[1:2])
+        else:
+            ops.clip_adam_step(m.flat, m.grad, m.exp_avg, m.exp_avg_sq, self.opt_step, self.curr_lr, cfg.adam_beta1,
+                               cfg.adam_beta2, cfg.adam_eps, cfg.max_grad_norm, self.num_valid_dev,
+                               self.exp_size_total_dev(), self.grad_norm_log[log_idx : log_idx + 1], self.adam_ws)
+        m.refresh_cat_heads()        # separate actor / critic weights: re-embed the updated head weights (no-op otherwise)
+        self.train_step += 1                                                                         # :388-392
+
+    def _backward_shared(self, batch: Dict[str, Tensor], x: Tensor, x0: Tensor, sl: slice, valids: Tensor) -> None:
+        """explicit backward pass of the shared-weights model (the reference's loss.backward(), learner.py:779)"""
+        cfg, m, spec = self.cfg, self.model, self.model.spec
+        Wv, bv = m.critic
+        Wa, ba = m.actor
         # backward: heads -> decoder MLP -> (recurrent core, BPTT) -> encoder MLP
         g = m.grads
         none = ops.ACT["none"]
@@ -427,26 +459,34 @@ class Learner:
                 conv.backward(self.dfeat)
             else:
                 ops.linear_backward(self.dz[li], x0, W, none, dW, None, None, self.engine, self.lin_ws)
-        # gradient all-reduce: ONE NCCL call on the flat buffer (SURVEY 8e); mean over ranks is folded into the sums:
-        # each rank's loss already divides by the GLOBAL valid count, so the rank gradients simply add up.
-        self._allreduce(m.grad)
-        # :781-797 clip + Adam (+ lr scaling by the valid fraction, on device)
-        self.opt_step += 1
-        if cfg.optimizer == "lamb":
-            ops.clip_lamb_step(m.flat, m.grad, m.exp_avg, m.exp_avg_sq, self.lamb_off, self.lamb_numel, self.lamb_max,
-                               self.opt_step, self.curr_lr, cfg.adam_beta1, cfg.adam_beta2, cfg.adam_eps, 1e-4, 0.01,
-                               cfg.max_grad_norm, self.num_valid_dev, self.exp_size_total_dev(),
-                               self.grad_norm_log[log_idx : log_idx + 1], self.lamb_ws)
-        elif self.use_graph:
-            ops.clip_adam_step_dev(m.flat, m.grad, m.exp_avg, m.exp_avg_sq, self.counters_dev[0:1], self.lr_dev,
-                                   cfg.adam_beta1, cfg.adam_beta2, cfg.adam_eps, cfg.max_grad_norm, self.num_valid_dev,
-                                   self.exp_size_total_dev(), self.grad_norm_log[log_idx : log_idx + 1], self.adam_ws)
-            ops.advance_counters(self.counters_dev[0:1], self.counters_dev[1:2])
-        else:
-            ops.clip_adam_step(m.flat, m.grad, m.exp_avg, m.exp_avg_sq, self.opt_step, self.curr_lr, cfg.adam_beta1,
-                               cfg.adam_beta2, cfg.adam_eps, cfg.max_grad_norm, self.num_valid_dev,
-                               self.exp_size_total_dev(), self.grad_norm_log[log_idx : log_idx + 1], self.adam_ws)
-        self.train_step += 1                                                                         # :388-392
+
+    def _backward_separate(self, x0: Tensor) -> None:
+        """backward of ActorCriticSeparateWeights: one heads-backward over the concatenated tail [B, 2H] (zero-padded head
+        weights route d(logits) into the actor half and d(value) into the critic half), then each tower's MLP chain."""
+        m, spec, plan = self.model, self.model.spec, self.heads_plan
+        B = x0.shape[0]
+        H = spec.tail_input_size
+        g = m.grads
+        none = ops.ACT["none"]
+        ops.heads_backward(plan.tail_cat[:B], m.Wv_cat, m.Wa_cat, self.dlogits, self.dvalues, self.act, plan.dz_cat[:B],
+                           plan.gWv_cat.view(-1), g["critic_linear.bias"], plan.gWa_cat,
+                           g["action_parameterization.distribution_linear.bias"], plan.db_cat, self.heads_ws)
+        g["critic_linear.weight"].copy_(plan.gWv_cat[:, H:])                                   # (the padded halves are not
+        g["action_parameterization.distribution_linear.weight"].copy_(plan.gWa_cat[:, :H])     #  parameters: dropped)
+        for tw, col in (("actor_", 0), ("critic_", H)):
+            layers, glayers = m.tower_layers(tw), m.tower_layers(tw, grads=True)
+            L = len(layers)
+            glayers[L - 1][1].copy_(plan.db_cat[col: col + H])      # bias gradient of the tower's last layer
+            dz = plan.dz_cat[:B, col: col + H]
+            for k in range(L - 1, -1, -1):
+                W, dW = layers[k][0], glayers[k][0]
+                if k > 0:
+                    dx = plan.tower_dz[tw][k - 1][:B]
+                    ops.linear_backward(dz, plan.tower_h[tw][k - 1][:B], W, self.act, dW, dx, glayers[k - 1][1], self.engine,
+                                        self.lin_ws)
+                    dz = dx
+                else:
+                    ops.linear_backward(dz, x0, W, none, dW, None, None, self.engine, self.lin_ws)
 
     def exp_size_total_dev(self) -> Tensor:
         if not hasattr(self, "_exp_total"):

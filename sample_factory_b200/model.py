@@ -47,6 +47,9 @@ class ModelSpec:
     encoder_conv_architecture: str = "convnet_atari"
     encoder_conv_mlp_layers: List[int] = field(default_factory=lambda: [512])
     obs_uint8: bool = False              # dtype of the observation rows in the trajectory buffers
+    # False -> ActorCriticSeparateWeights (model/actor_critic.py:198-322): an actor tower (encoder + decoder MLP) feeding
+    # distribution_linear and a critic tower feeding critic_linear; vector observations, no recurrent core on this path
+    share_weights: bool = True
 
     CONV_ARCH = {  # model/encoder.py:127-134: (out_channels, kernel, stride); no padding
         "convnet_simple": [(32, 8, 4), (64, 4, 2), (128, 3, 2)],
@@ -98,6 +101,7 @@ class ModelSpec:
                    encoder_conv_architecture=getattr(cfg, "encoder_conv_architecture", "convnet_atari"),
                    encoder_conv_mlp_layers=list(getattr(cfg, "encoder_conv_mlp_layers", [512])),
                    obs_uint8=bool(getattr(env, "obs_uint8", False)),
+                   share_weights=bool(getattr(cfg, "actor_critic_share_weights", True)),
                    action_segments=(list(env.action_segments) if getattr(env, "action_segments", None) else None),
                    continuous=bool(getattr(env, "continuous", False)),
                    adaptive_stddev=bool(getattr(cfg, "adaptive_stddev", True)),
@@ -132,7 +136,7 @@ class ModelSpec:
     def rnn_state_size(self) -> int:
         """model/model_utils.py:11-24"""
         if not self.use_rnn:
-            return 1
+            return 1 if self.share_weights else 2       # "actor and critic need separate states" (model_utils.py:20-22)
         return self.rnn_size * (2 if self.rnn_type == "lstm" else 1)
 
     @property
@@ -143,7 +147,7 @@ class ModelSpec:
     def tail_input_size(self) -> int:
         """width of the tensor that feeds critic_linear / distribution_linear"""
         if self.decoder_mlp_layers:
-            return self.decoder_mlp_layers[-1]
+            return self.decoder_mlp_layers[-1]     # (separate weights: the width of ONE tower's tail)
         if self.use_rnn:
             return self.rnn_size
         return self.fc_encoder_layers[-1]
@@ -151,6 +155,29 @@ class ModelSpec:
     def param_shapes(self) -> List[Tuple[str, Tuple[int, ...]]]:
         """(reference state_dict key, shape) in nn.Module.parameters() order."""
         out = []
+        if not self.share_weights:
+            # registration order of ActorCriticSeparateWeights.__init__ (actor_critic.py:208-225)
+            assert self.obs_shape is None and not self.use_rnn, "separate actor / critic weights: MLP towers only"
+            for tw in ("actor_", "critic_"):
+                d = self.obs_dim
+                for i, h in enumerate(self.encoder_mlp_layers):
+                    out.append((f"{tw}encoder.encoders.obs.mlp_head.{2 * i}.weight", (h, d)))
+                    out.append((f"{tw}encoder.encoders.obs.mlp_head.{2 * i}.bias", (h,)))
+                    d = h
+            d_enc = d
+            for tw in ("actor_", "critic_"):
+                d = d_enc
+                for i, h in enumerate(self.decoder_mlp_layers):
+                    out.append((f"{tw}decoder.mlp.{2 * i}.weight", (h, d)))
+                    out.append((f"{tw}decoder.mlp.{2 * i}.bias", (h,)))
+                    d = h
+            out.append(("critic_linear.weight", (1, d)))
+            out.append(("critic_linear.bias", (1,)))
+            if self.continuous and not self.adaptive_stddev:
+                out.append(("action_parameterization.learned_stddev", (self.num_actions,)))
+            out.append(("action_parameterization.distribution_linear.weight", (self.num_linear_action_outputs, d)))
+            out.append(("action_parameterization.distribution_linear.bias", (self.num_linear_action_outputs,)))
+            return out
         for i, (ci, _h, _w, co, k, _s, _ho, _wo) in enumerate(self.conv_layers):
             out.append((f"encoder.encoders.obs.enc.conv_head.{2 * i}.weight", (co, ci, k, k)))
             out.append((f"encoder.encoders.obs.enc.conv_head.{2 * i}.bias", (co,)))
@@ -220,6 +247,7 @@ class PolicyModel:
 
         self._init_weights(seed, policy_init_gain)
         self._register_lo()
+        self.refresh_cat_heads()
 
     # ---- tf32 low halves of the weights (3xTF32 engine: the weight operand's lo tile is loaded, not recomputed) -----
     def _register_lo(self) -> None:
@@ -236,6 +264,7 @@ class PolicyModel:
             from . import ops
 
             ops.refresh_tf32_lo(self.flat)
+        self.refresh_cat_heads()
 
     def __del__(self):
         try:
@@ -277,6 +306,7 @@ class PolicyModel:
         for k in ("obs_mean", "obs_var", "obs_count", "ret_mean", "ret_var", "ret_count"):
             setattr(twin, k, getattr(self, k).clone())
         twin._register_lo()
+        twin.refresh_cat_heads()
         return twin
 
     def copy_weights_from(self, other: "PolicyModel") -> None:
@@ -284,6 +314,7 @@ class PolicyModel:
         self.flat.copy_(other.flat)
         if self.flat_lo is not None and other.flat_lo is not None:
             self.flat_lo.copy_(other.flat_lo)
+            self.refresh_cat_heads()
         else:
             self.weights_changed()
         self.obs_mean.copy_(other.obs_mean)
@@ -300,6 +331,28 @@ class PolicyModel:
         sp = self.spec
         return [(src[sp.fc_encoder_name(i, "weight")], src[sp.fc_encoder_name(i, "bias")])
                 for i in range(len(sp.fc_encoder_layers))]
+
+    def tower_layers(self, tower: str, grads: bool = False) -> List[Tuple[Tensor, Tensor]]:
+        """separate actor / critic weights: [(W, b)] of one tower ("actor_" / "critic_"), encoder then decoder MLP"""
+        src = self.grads if grads else self.params
+        out = [(src[f"{tower}encoder.encoders.obs.mlp_head.{2 * i}.weight"], src[f"{tower}encoder.encoders.obs.mlp_head.{2 * i}.bias"])
+               for i in range(len(self.spec.encoder_mlp_layers))]
+        out += [(src[f"{tower}decoder.mlp.{2 * i}.weight"], src[f"{tower}decoder.mlp.{2 * i}.bias"])
+                for i in range(len(self.spec.decoder_mlp_layers))]
+        return out
+
+    def refresh_cat_heads(self) -> None:
+        """separate weights: the heads kernels read ONE tail [M, 2H] = [actor tail | critic tail]; critic_linear and
+        distribution_linear are embedded in zero-padded [., 2H] matrices (value <- critic half, logits <- actor half)."""
+        if self.spec.share_weights:
+            return
+        H = self.spec.tail_input_size
+        if not hasattr(self, "Wv_cat"):
+            A = self.spec.num_linear_action_outputs
+            self.Wv_cat = torch.zeros((1, 2 * H), dtype=torch.float32, device=self.device)
+            self.Wa_cat = torch.zeros((A, 2 * H), dtype=torch.float32, device=self.device)
+        self.Wv_cat[:, H:].copy_(self.params["critic_linear.weight"])
+        self.Wa_cat[:, :H].copy_(self.params["action_parameterization.distribution_linear.weight"])
 
     def conv_params(self, grads: bool = False) -> List[Tuple[Tensor, Tensor]]:
         """[(W [C_out, C_in, k, k], b [C_out])] of the conv head"""

@@ -30,7 +30,24 @@ class HeadsPlan:
 
             self.conv = ConvHead(model, engine, max_rows, need_backward)
         self.tail_is_mlp = bool(spec.decoder_mlp_layers) or (not spec.use_rnn and bool(spec.fc_encoder_layers))
+        # separate actor / critic weights: per-tower activations and ONE concatenated tail [rows, 2H] = [actor | critic]
+        self.separate = not spec.share_weights
+        if self.separate:
+            f32 = dict(dtype=torch.float32, device=model.device)
+            widths, H = spec.hidden, spec.tail_input_size
+            assert len(widths) > 0, "separate actor / critic weights need at least one MLP layer per tower"
+            self.tower_h = {tw: [torch.empty((max_rows, w), **f32) for w in widths[:-1]] for tw in ("actor_", "critic_")}
+            self.tail_cat = torch.empty((max_rows, 2 * H), **f32)
+            if need_backward:
+                A = spec.num_linear_action_outputs
+                self.tower_dz = {tw: [torch.empty((max_rows, w), **f32) for w in widths[:-1]] for tw in ("actor_", "critic_")}
+                self.dz_cat = torch.empty((max_rows, 2 * H), **f32)
+                self.gWv_cat = torch.empty((1, 2 * H), **f32)
+                self.gWa_cat = torch.empty((A, 2 * H), **f32)
+                self.db_cat = torch.empty(2 * H, **f32)
         self.P = 0
+        if self.separate:
+            return
         self.part: Optional[Tensor] = None
         if self.tail_is_mlp:
             self.P = ops.linear_heads_partials(spec.tail_input_size, spec.num_linear_action_outputs, engine)
@@ -45,6 +62,8 @@ def forward_policy(model: PolicyModel, x: Tensor, outs: List[Tensor], act: int, 
     ops.heads_forward after the weights).  outs: one [>=M, h] buffer per MLP layer.  Returns the tensor that fed the
     heads (None if it was not stored)."""
     M = x.shape[0]
+    if plan.separate:
+        return _forward_separate(model, x, act, engine, plan, heads_kwargs)
     if plan.conv is not None:        # ConvEncoder: conv head first, its fully connected layers are `enc` below
         x = plan.conv.forward(x)
     enc, dec = model.encoder_layers(), model.decoder_layers()
@@ -67,6 +86,32 @@ def forward_policy(model: PolicyModel, x: Tensor, outs: List[Tensor], act: int, 
                 ops.linear_act_forward(tail, W, b, outs[k][:M], act, engine)
                 tail = outs[k][:M]
             k += 1
+    _heads(model, tail, Wv, bv, Wa, ba, fused, plan, M, heads_kwargs)
+    return tail
+
+
+def _forward_separate(model: PolicyModel, x: Tensor, act: int, engine: int, plan: HeadsPlan, heads_kwargs: Dict) -> Tensor:
+    """ActorCriticSeparateWeights (model/actor_critic.py:283-318): two MLP towers on the same normalised observation; the
+    towers' last layers write the two halves of one [M, 2H] tail, and the heads read it through zero-padded weights
+    (PolicyModel.refresh_cat_heads), so value = critic half . Wv and logits = actor half . Wa^T."""
+    M = x.shape[0]
+    H = model.spec.tail_input_size
+    for tw, col in (("actor_", 0), ("critic_", H)):
+        t = x
+        layers = model.tower_layers(tw)
+        for k, (W, b) in enumerate(layers):
+            out = plan.tail_cat[:M, col: col + H] if k == len(layers) - 1 else plan.tower_h[tw][k][:M]
+            ops.linear_act_forward(t, W, b, out, act, engine)
+            t = out
+    _, bv = model.critic
+    _, ba = model.actor
+    tail = plan.tail_cat[:M]
+    _heads(model, tail, model.Wv_cat, bv, model.Wa_cat, ba, False, plan, M, heads_kwargs)
+    return tail
+
+
+def _heads(model: PolicyModel, tail: Tensor, Wv: Tensor, bv: Tensor, Wa: Tensor, ba: Tensor, fused: bool, plan: HeadsPlan,
+           M: int, heads_kwargs: Dict) -> None:
     if model.spec.continuous:   # Box action space: Gaussian heads (action_distributions.py:290-323)
         dk = model.dist_kwargs()
         if fused:
@@ -82,4 +127,3 @@ def forward_policy(model: PolicyModel, x: Tensor, outs: List[Tensor], act: int, 
         ops.heads_from_partials(plan.part, plan.P, M, bv, ba, **heads_kwargs)
     else:
         ops.heads_forward(tail, Wv, bv, Wa, ba, **heads_kwargs)
-    return tail

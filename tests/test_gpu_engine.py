@@ -22,7 +22,7 @@ def make_cfg(ocfg: O.OracleCfg, **over):
               "max_grad_norm", "learning_rate", "adam_eps", "adam_beta1", "adam_beta2", "normalize_input",
               "normalize_returns", "value_bootstrap", "with_vtrace", "vtrace_rho", "vtrace_c", "reward_scale",
               "reward_clip", "max_policy_lag", "nonlinearity", "obs_subtract_mean", "obs_scale", "use_rnn", "rnn_type",
-              "rnn_size", "adaptive_stddev", "continuous_tanh_scale", "initial_stddev", "exploration_loss", "optimizer"]:
+              "rnn_size", "adaptive_stddev", "continuous_tanh_scale", "initial_stddev", "exploration_loss", "optimizer", "actor_critic_share_weights"]:
         setattr(cfg, k, getattr(ocfg, k))
     cfg.encoder_mlp_layers = list(ocfg.encoder_mlp_layers)
     cfg.decoder_mlp_layers = list(ocfg.decoder_mlp_layers)
@@ -51,7 +51,7 @@ def build(ocfg: O.OracleCfg, N: int, state, tape, dev, engine="simt", graph=Fals
                      initial_stddev=ocfg.initial_stddev, obs_shape=ocfg.obs_shape,
                      encoder_conv_architecture=ocfg.encoder_conv_architecture,
                      encoder_conv_mlp_layers=list(ocfg.encoder_conv_mlp_layers), obs_uint8=tape.dtype == torch.uint8,
-                     action_segments=ocfg.action_segments)
+                     action_segments=ocfg.action_segments, share_weights=ocfg.actor_critic_share_weights)
     model = PolicyModel(spec, dev)
     model.load_state_dict(state, strict=False)
     traj = alloc_for_spec(spec, N, ocfg.rollout, dev)
@@ -77,7 +77,7 @@ def _need(engine):
         pytest.skip("tcgen05 engine not available")
 
 
-GOLDEN_CASES = ["tiny_gae", "tiny_vtrace", "tiny_gru", "tiny_lstm", "cfg2_small", "tiny_gauss", "tiny_gauss_adaptive", "tiny_conv", "tiny_symkl", "tiny_lamb", "tiny_tuple"]
+GOLDEN_CASES = ["tiny_gae", "tiny_vtrace", "tiny_gru", "tiny_lstm", "cfg2_small", "tiny_gauss", "tiny_gauss_adaptive", "tiny_conv", "tiny_symkl", "tiny_lamb", "tiny_tuple", "tiny_separate"]
 
 
 @pytest.mark.parametrize("engine", ENGINES)
