@@ -44,6 +44,39 @@ def global_env_registry() -> Dict[str, Callable]:
     return _ENV_REGISTRY
 
 
+class TrainingInfoInterface:
+    """envs/env_utils.py:117-129: envs that implement curricula receive the training progress at the end of every rollout
+    (batched_sampling.py:351-354); `training_info` is guaranteed to contain 'approx_total_training_steps'."""
+
+    def __init__(self):
+        self.training_info: Dict[str, object] = dict()
+
+    def set_training_info(self, training_info):
+        self.training_info = training_info
+
+
+class RewardShapingInterface:
+    """envs/env_utils.py:74-90 (used by the reference's PBT to mutate reward shaping; the device runner only forwards a
+    scheme the caller put into Runner.training_info['reward_shaping'])."""
+
+    def get_default_reward_shaping(self):
+        raise NotImplementedError
+
+    def set_reward_shaping(self, reward_shaping, agent_idx) -> None:
+        raise NotImplementedError
+
+
+def set_training_info(env, training_info) -> None:
+    """forward the training info (and an optional reward-shaping scheme) to an env that implements the interfaces"""
+    if training_info is None:
+        return
+    shaping = training_info.get("reward_shaping") if isinstance(training_info, dict) else None
+    if shaping is not None and hasattr(env, "set_reward_shaping"):
+        env.set_reward_shaping(shaping, slice(0, env.num_agents))
+    if hasattr(env, "set_training_info"):
+        env.set_training_info(training_info)
+
+
 class TapeVecEnv:
     """GPU-resident synthetic vector env.  obs_t = tape[t % L] (pre-generated N(0,1)-like tape in HBM),
     reward = action / num_actions, terminated / truncated = fixed integer rules of (step, env).

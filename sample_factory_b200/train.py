@@ -29,7 +29,7 @@ from . import ops
 from .cfg import preprocess_cfg
 from .checkpoint import load_checkpoint, save_checkpoint
 from .dist_utils import init_from_env
-from .envs import create_env
+from .envs import create_env, set_training_info
 from .learner import Learner
 from .model import ModelSpec, PolicyModel
 from .sampler import DeviceSampler, SplitSampler
@@ -70,6 +70,8 @@ class Runner:
         self.fps_history: deque = deque(maxlen=64)
         self.initialized = False
         self.rollout_hook: Optional[Callable[[int], None]] = None   # called with the rollout index before each rollout
+        # what the reference's runner publishes to the rollout workers (runner.py training_info / batched_sampling.py:351-354)
+        self.training_info: Dict[str, object] = dict(approx_total_training_steps=0)
         self.rollouts_started = 0
 
     # ---- reference-compatible hooks --------------------------------------------------------------------------
@@ -160,6 +162,9 @@ class Runner:
         if self.rollout_hook is not None:
             self.rollout_hook(self.rollouts_started)
         self.rollouts_started += 1
+        self.training_info["approx_total_training_steps"] = self.env_steps
+        for e in self.envs:                                    # TrainingInfoInterface / RewardShapingInterface envs
+            set_training_info(e, self.training_info)
 
     def iteration(self) -> None:
         """One sampler rollout + one learner update (the unit the FPS counter advances by N*T env steps)."""

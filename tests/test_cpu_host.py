@@ -268,3 +268,28 @@ def test_checkpoint_we_write_has_the_reference_layout(tmp_path):
     a, b = model.optimizer_state_dict(15, 0, (0, 0), 0)["state"], model2.optimizer_state_dict(15, 0, (0, 0), 0)["state"]
     assert torch.equal(model2.flat, model.flat)
     assert all(torch.equal(a[i]["exp_avg"], b[i]["exp_avg"]) and torch.equal(a[i]["exp_avg_sq"], b[i]["exp_avg_sq"]) for i in a)
+
+
+def test_training_info_interface_plumbing():
+    """envs/env_utils.py:74-133: TrainingInfoInterface / RewardShapingInterface envs get the runner's training info"""
+    from sample_factory_b200.envs import RewardShapingInterface, TrainingInfoInterface, set_training_info
+
+    class Env(TrainingInfoInterface, RewardShapingInterface):
+        num_agents = 5
+
+        def __init__(self):
+            TrainingInfoInterface.__init__(self)
+            self.shaping = None
+
+        def get_default_reward_shaping(self):
+            return dict(kill=1.0)
+
+        def set_reward_shaping(self, reward_shaping, agent_idx):
+            self.shaping = (reward_shaping, agent_idx)
+
+    e = Env()
+    set_training_info(e, dict(approx_total_training_steps=123))
+    assert e.training_info["approx_total_training_steps"] == 123 and e.shaping is None
+    set_training_info(e, dict(approx_total_training_steps=456, reward_shaping=dict(kill=2.0)))
+    assert e.training_info["approx_total_training_steps"] == 456 and e.shaping == (dict(kill=2.0), slice(0, 5))
+    set_training_info(object(), dict(approx_total_training_steps=1))     # envs without the interfaces are left alone
