@@ -589,7 +589,8 @@ class Learner:
         out["adam_max_second_moment"] = float(self.model.exp_avg_sq.max().item())            # learner.py:908-913
         b = getattr(self, "_last_batch", None)
         if b is not None:   # policy lag of the last minibatch (learner.py:915-918)
-            sl = slice((n - 1) * self.cfg.batch_size, n * self.cfg.batch_size)
+            bi = (n - 1) % self.cfg.num_batches_per_epoch          # position of the last minibatch inside its epoch
+            sl = slice(bi * self.cfg.batch_size, (bi + 1) * self.cfg.batch_size)
             own = b["policy_id"].view(self.E)[sl] == self.policy_id
             vd = (float(self.train_step - 1) - b["policy_version"].view(self.E)[sl])[own]
             if vd.numel() > 0:
