@@ -177,6 +177,22 @@ int sfb200_heads_from_partials(const float* head_partials, int P, int64_t rows, 
                                const float* policy_version_scalar, float* policy_version_out, int64_t pv_stride,
                                void* stream);
 
+/* The same fused layer, finishing the heads INSIDE the GEMM kernel (no second launch): the n-tile CTAs of every 128-row
+ * block count themselves in finish_counters[M/128] (int32, zero before the first call, left at zero); the CTA that arrives
+ * last sums the partials of its rows in fixed order and runs the distribution tail.  dist_kind: 0 = Discrete(A),
+ * 1 = Tuple of Discretes (num_heads, head_sizes_host), 2 = Box(act_dim) (adaptive_stddev, learned_log_std, tanh_scale;
+ * A = 2*act_dim or act_dim).  env_actions: int32 [M] / [M, num_heads], or float32 [M, act_dim] for dist_kind 2.  The other
+ * outputs are those of sfb200_heads_forward / _tuple / _continuous. */
+int sfb200_linear_act_heads_forward_fused(
+    const float* x, int64_t ldx, const float* W, const float* b, float* y, int64_t ldy, int64_t M, int N, int K, int act,
+    int engine, const float* Wv, const float* bv, const float* Wa, const float* ba, int A, float* head_partials,
+    int32_t* finish_counters, int dist_kind, int act_dim, int adaptive_stddev, const float* learned_log_std,
+    float tanh_scale, int num_heads, const int32_t* head_sizes_host, float* values, int64_t values_stride, float* logits,
+    int64_t logits_stride, const float* noise, uint64_t philox_seed, uint64_t philox_offset,
+    const int64_t* philox_offset_dev, float* actions_f32, int64_t actions_stride, void* env_actions, float* log_prob,
+    int64_t log_prob_stride, const float* policy_version_scalar, float* policy_version_out, int64_t pv_stride,
+    void* stream);
+
 /* ------------------------------------------------------------- sampler steps ---- */
 /* BatchedVectorEnvRunner.generate_policy_request (algo/sampling/batched_sampling.py:374-388) fused with the
  * inference-side normalisation (inference_worker.py:326):  traj_obs[:, t] = obs ; traj_rnn[:, t] = rnn ;

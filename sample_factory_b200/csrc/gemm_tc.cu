@@ -26,6 +26,7 @@
 
 #include "common.cuh"
 #include "gemm.h"
+#include "heads_tail.cuh"
 
 namespace sfb {
 
@@ -181,6 +182,11 @@ struct TcEpilogue {
     // fused column sums of the OUTPUT (bias gradient of the previous layer = sum over rows of dX): one partial row per
     // (128-row tile, 32-row warp quadrant) -> colsum_part[(m_tile*4 + quadrant)][N]; requires M % 128 == 0, N % 128 == 0
     float* colsum_part;
+    // finish the heads inside this kernel: the n-tile CTAs of a 128-row block count themselves in fin_counters[m_block];
+    // the one that arrives last sums the partials of its rows and runs the distribution tail (sampling, log-prob, ...) --
+    // the separate finishing launch disappears.  fin_counters: M/128 zero-initialised ints, left at zero again.
+    int* fin_counters;
+    HeadsFinish fin;
 };
 
 constexpr int kHeadAP = 9;     // value + up to 8 action outputs
@@ -467,7 +473,7 @@ __device__ __forceinline__ void tc_epilogue_tile_heads(uint32_t tmem_slot_addr, 
     float o[CH];
     tmem_drain<BN, CH, SPLIT3>(tmem_slot_addr + ((uint32_t)ec.lane_base << 16) + (uint32_t)ec.col0, o, acc_full_bar, acc_ph,
                                acc_empty_bar);
-    if (m >= M) return;
+    if (m >= M) return;   // (the caller's named barriers come after this function: every thread still reaches them)
     float hp[kHeadAP];
 #pragma unroll
     for (int a = 0; a < kHeadAP; ++a) hp[a] = 0.f;
@@ -934,6 +940,25 @@ gemm_tc_ta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                                                                             C, ldc, M, N, epi, headw_s);
                         break;
                 }
+                if (epi.fin_counters) {
+                    // last-arriving n-tile CTA of this 128-row block finishes the heads (threadFenceReduction pattern)
+                    volatile int* s_last = reinterpret_cast<volatile int*>(tmem_slot + 4);
+                    const int mb = (int)(tc.m0 / TBM);
+                    __threadfence();
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    if (threadIdx.x == 192) *s_last = (atomicAdd(&epi.fin_counters[mb], 1) == tiles_n - 1) ? 1 : 0;
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    if (*s_last) {
+                        __threadfence();
+                        const float pv = epi.fin.pv_scalar ? *epi.fin.pv_scalar : 0.f;
+                        const uint64_t offset = epi.fin.offset_host + (epi.fin.offset_dev ? (uint64_t)*epi.fin.offset_dev : 0ull);
+                        for (int r = warp - 6; r < TBM; r += 8) {
+                            const int64_t row = tc.m0 + r;
+                            if (row < M) heads_finish_row(epi.head_part, 2 * tiles_n, M, row, lane, epi.fin, pv, offset);
+                        }
+                        if (threadIdx.x == 192) epi.fin_counters[mb] = 0;
+                    }
+                }
             } else {
                 tc_epilogue_tile<BN, SPLIT3>(tmem_base, acc_full, tile_iter & 1, acc_empty, tc, ec, C, ldc, M, N, splits, epi);
             }
@@ -1161,11 +1186,15 @@ int tc_linear_heads_partials(int N, int A, int engine) {
 
 int tc_linear_act_heads_forward(const float* x, int64_t ldx, const float* W, const float* b, float* y, int64_t ldy,
                                 int64_t M, int N, int K, int act, int engine, const float* Wv, const float* Wa, int A,
-                                float* head_part, cudaStream_t st) {
+                                float* head_part, cudaStream_t st, const HeadsFinish* fin, int* fin_counters) {
     if (tc_linear_heads_partials(N, A, engine) == 0 || !b) return SFB_TC_UNSUPPORTED;
     if (y && (ldy % 4 != 0 || (reinterpret_cast<uintptr_t>(y) & 15u))) return SFB_TC_UNSUPPORTED;
     if (reinterpret_cast<uintptr_t>(head_part) & 15u) return SFB_TC_UNSUPPORTED;
     TcEpilogue epi{1, act, b, nullptr, 0, Wv, Wa, A, head_part};
+    if (fin && fin_counters) {
+        epi.fin = *fin;
+        epi.fin_counters = fin_counters;
+    }
     return gemm_tc(false, x, ldx, false, W, K, y, y ? ldy : N, M, N, K, 1, epi, nullptr, engine == SFB200_GEMM_TC_3XTF32, st);
 }
 

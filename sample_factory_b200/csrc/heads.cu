@@ -1,204 +1,26 @@
 // Policy/value heads: critic_linear + distribution_linear (N = 1 + A output columns, far too narrow for a
 // tensor-core tile) fused with the categorical distribution math, forward and backward.  Both kernels stream h once
 // (HBM-bound: 4*H bytes per row read, backward also writes 4*H).
-#include <curand_kernel.h>
-
-#include "common.cuh"
+#include "gemm.h"
+#include "heads_tail.cuh"
 
 namespace sfb {
 
 constexpr int kHeadsMaxGroups = 1024;
 
 
-struct HeadsOut {
-    float* values; int64_t values_stride;
-    float* logits; int64_t logits_stride;
-    float* actions_f32; int64_t actions_stride;
-    int32_t* env_actions;
-    float* log_prob; int64_t log_prob_stride;
-    float* pv_out; int64_t pv_stride;
-    // continuous (diagonal Gaussian) action space: dist 0 = categorical, 1 = Gaussian with state-dependent log-stddev
-    // (the linear layer has 2*act_dim rows), 2 = Gaussian with one learned log-stddev vector (act_dim rows)
-    int dist; int act_dim; const float* learned_log_std; float tanh_scale; float* env_actions_f32;
-    // Tuple(Discrete(n_0), ..., Discrete(n_{K-1})) action space (action_distributions.py:197-286): K independent
-    // categorical heads over consecutive logit segments; num_seg <= 1 means one plain categorical
-    int num_seg; int seg_len[8];
-};
-
-constexpr float kStddevMin = 1e-4f, kStddevMax = 1e4f;   // action_distributions.py:291-292
-constexpr float kHalfLog2Pi = 0.91893853320467274178f;   // log(sqrt(2 pi))
-
-// ContinuousActionDistribution (action_distributions.py:290-323) on the lanes: lane j in 1..act_dim owns action
-// dimension j-1.  Stored `logits` are the distribution parameters [means | log_std] (2*act_dim floats) exactly as the
-// reference's action_parameterization returns them (tanh-scaled means and the repeated learned vector when
-// adaptive_stddev=False, action_parameterization.py:64-78).
-__device__ __forceinline__ void gaussian_row_tail(float mine, int lane, int64_t row, const HeadsOut& out,
-                                                  const float* __restrict__ noise, uint64_t seed, uint64_t offset,
-                                                  float pv) {
-    const int Ad = out.act_dim;
-    const bool is_dim = lane >= 1 && lane <= Ad;
-    float mean = mine, log_std;
-    if (out.dist == 1) {
-        const int src = lane + Ad;
-        log_std = __shfl_sync(0xffffffffu, mine, src < 32 ? src : 31);
-    } else {
-        log_std = is_dim ? out.learned_log_std[lane - 1] : 0.f;
-        if (out.tanh_scale > 0.f) mean = tanhf(__fdiv_rn(mine, out.tanh_scale)) * out.tanh_scale;
-    }
-    if (out.logits && is_dim) {
-        out.logits[row * out.logits_stride + (lane - 1)] = mean;
-        out.logits[row * out.logits_stride + Ad + (lane - 1)] = log_std;
-    }
-    if (out.actions_f32 == nullptr) return;   // values / distribution parameters only (warp-uniform)
-    const float sd = clampf(expf(log_std), kStddevMin, kStddevMax);
-    float eps = 0.f;
-    if (is_dim) {
-        if (noise) eps = noise[row * Ad + (lane - 1)];
-        else {
-            curandStatePhilox4_32_10_t st;
-            curand_init(seed, (unsigned long long)(row * Ad + (lane - 1)), offset, &st);
-            eps = curand_normal(&st);
-        }
-    }
-    // Normal.sample(): eps * std + mean, product and sum rounded separately (SURVEY App.C)
-    const float a = __fadd_rn(__fmul_rn(eps, sd), mean);
-    const float d = a - mean;
-    const float lpj = is_dim ? (-(d * d) / (2.f * (sd * sd)) - logf(sd) - kHalfLog2Pi) : 0.f;   // normal.py:84-94
-    const float lp = warp_sum(lpj);                                                              // Independent(.., 1)
-    if (is_dim) {
-        out.actions_f32[row * out.actions_stride + (lane - 1)] = a;
-        if (out.env_actions_f32) out.env_actions_f32[row * Ad + (lane - 1)] = a;
-    }
-    if (lane == 0) {
-        if (out.log_prob) out.log_prob[row * out.log_prob_stride] = lp;
-        if (out.pv_out) out.pv_out[row * out.pv_stride] = pv;
-    }
-}
-
-__device__ __forceinline__ void tuple_row_tail(float mine, int lane, int A, int64_t row, const HeadsOut& out,
-                                               const float* __restrict__ noise, uint64_t seed, uint64_t offset, float pv);
-
-// Lane a of the warp holds output a of one row (0 = value, 1..A = logits, bias included): store them and, in sampling
-// mode, run CategoricalActionDistribution (action_distributions.py:110-148) on the lanes.
-__device__ __forceinline__ void heads_row_tail(float mine, int lane, int A, int64_t row, const HeadsOut& out,
-                                               const float* __restrict__ noise, uint64_t seed, uint64_t offset, float pv) {
-    if (lane == 0) out.values[row * out.values_stride] = mine;
-    if (out.dist != 0) {
-        gaussian_row_tail(mine, lane, row, out, noise, seed, offset, pv);
-        return;
-    }
-    const bool is_logit = lane >= 1 && lane <= A;
-    if (out.logits && is_logit) out.logits[row * out.logits_stride + (lane - 1)] = mine;
-    if (out.actions_f32 == nullptr) return;   // values / logits only (warp-uniform)
-    if (out.num_seg > 1) {
-        tuple_row_tail(mine, lane, A, row, out, noise, seed, offset, pv);
-        return;
-    }
-
-    const float x = is_logit ? mine : -INFINITY;
-    const float m = warp_max(x);
-    const float e = is_logit ? expf(x - m) : 0.f;
-    const float s = warp_sum(e);
-    const float p = __fdiv_rn(e, s);                    // softmax :116
-    const float logp = (x - m) - logf(s);               // log_softmax :125
-    float q = 1.f;
-    if (is_logit) {
-        if (noise) q = noise[row * A + (lane - 1)];
-        else {
-            curandStatePhilox4_32_10_t st;
-            curand_init(seed, (unsigned long long)(row * A + (lane - 1)), offset, &st);
-            q = -logf(curand_uniform(&st));             // Exp(1); uniform is in (0, 1]
-            q = fmaxf(q, 1.0e-30f);
-        }
-    }
-    // torch.multinomial(p, 1, True) == argmax(p / q) (first index on ties)
-    float best = is_logit ? __fdiv_rn(p, q) : -INFINITY;
-    int idx = is_logit ? (lane - 1) : 0x7fffffff;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
-        if (ob > best || (ob == best && oi < idx)) { best = ob; idx = oi; }
-    }
-    const float lp = __shfl_sync(0xffffffffu, logp, idx + 1);   // log_prob :145-148
-    if (lane == 0) {
-        out.actions_f32[row * out.actions_stride] = (float)idx;
-        if (out.env_actions) out.env_actions[row] = idx;
-        if (out.log_prob) out.log_prob[row * out.log_prob_stride] = lp;
-        if (out.pv_out) out.pv_out[row * out.pv_stride] = pv;
-    }
-}
-
-// TupleActionDistribution on the lanes: every head runs the categorical recipe on its own lane range; actions_f32 gets K
-// floats per row (one index per head), env_actions K int32, log_prob the sum over the heads (:231-241).
-__device__ __forceinline__ void tuple_row_tail(float mine, int lane, int A, int64_t row, const HeadsOut& out,
-                                               const float* __restrict__ noise, uint64_t seed, uint64_t offset, float pv) {
-    const bool is_logit = lane >= 1 && lane <= A;
-    float q = 1.f;
-    if (is_logit) {
-        if (noise) q = noise[row * A + (lane - 1)];
-        else {
-            curandStatePhilox4_32_10_t st;
-            curand_init(seed, (unsigned long long)(row * A + (lane - 1)), offset, &st);
-            q = fmaxf(-logf(curand_uniform(&st)), 1.0e-30f);
-        }
-    }
-    float lp_total = 0.f;
-    int start = 0;
-    const int K = out.num_seg;
-    for (int k = 0; k < K; ++k) {
-        const int n = out.seg_len[k];
-        const bool in_seg = (lane - 1) >= start && (lane - 1) < start + n;
-        const float x = in_seg ? mine : -INFINITY;
-        const float m = warp_max(x);
-        const float e = in_seg ? expf(x - m) : 0.f;
-        const float s = warp_sum(e);
-        const float p = __fdiv_rn(e, s);
-        const float logp = (x - m) - logf(s);
-        float best = in_seg ? __fdiv_rn(p, q) : -INFINITY;
-        int idx = in_seg ? (lane - 1 - start) : 0x7fffffff;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
-            if (ob > best || (ob == best && oi < idx)) { best = ob; idx = oi; }
-        }
-        lp_total += __shfl_sync(0xffffffffu, logp, start + idx + 1);
-        if (lane == 0) {
-            out.actions_f32[row * out.actions_stride + k] = (float)idx;
-            if (out.env_actions) out.env_actions[row * K + k] = idx;
-        }
-        start += n;
-    }
-    if (lane == 0) {
-        if (out.log_prob) out.log_prob[row * out.log_prob_stride] = lp_total;
-        if (out.pv_out) out.pv_out[row * out.pv_stride] = pv;
-    }
-}
-
 // Heads from the partial dot products left by the fused GEMM epilogue (gemm_tc.cu, tc_epilogue_tile_heads):
 // part[p][row][kPad], summed over p in fixed order (deterministic).  One warp per row, lane a = output a.
-constexpr int kHeadPartPad = 12;
-__global__ void __launch_bounds__(256) heads_from_partials_kernel(
-    const float* __restrict__ part, int P, int64_t rows, int A, const float* __restrict__ bv, const float* __restrict__ ba,
-    HeadsOut out, const float* __restrict__ noise, uint64_t seed, uint64_t offset_host,
-    const int64_t* __restrict__ offset_dev, const float* __restrict__ pv_scalar) {
+__global__ void __launch_bounds__(256) heads_from_partials_kernel(const float* __restrict__ part, int P, int64_t rows,
+                                                                  const HeadsFinish f) {
     pdl_wait();
     pdl_trigger();
     const int lane = threadIdx.x & 31;
     const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    const float pv = pv_scalar ? *pv_scalar : 0.f;
-    const uint64_t offset = offset_host + (offset_dev ? (uint64_t)*offset_dev : 0ull);
-    const float my_bias = (lane == 0) ? bv[0] : (lane <= A ? ba[lane - 1] : 0.f);
-    for (int64_t row = warp; row < rows; row += nwarps) {
-        float mine = 0.f;
-        if (lane <= A) {
-            for (int p = 0; p < P; ++p) mine += part[((int64_t)p * rows + row) * kHeadPartPad + lane];
-        }
-        mine += my_bias;
-        heads_row_tail(mine, lane, A, row, out, noise, seed, offset, pv);
-    }
+    const float pv = f.pv_scalar ? *f.pv_scalar : 0.f;
+    const uint64_t offset = f.offset_host + (f.offset_dev ? (uint64_t)*f.offset_dev : 0ull);
+    for (int64_t row = warp; row < rows; row += nwarps) heads_finish_row(part, P, rows, row, lane, f, pv, offset);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -551,8 +373,8 @@ static int heads_from_partials_impl(const float* head_partials, int P, int64_t r
     int64_t blocks = ceil_div(rows, 8);
     const int64_t cap = (int64_t)sm_count() * 8;
     if (blocks > cap) blocks = cap;
-    SFB_CUDA_OK(launch_pdl(heads_from_partials_kernel, dim3((unsigned)blocks), dim3(256), 0, st, head_partials, P, rows, A, bv,
-                           ba, out, noise, seed, offset, offset_dev, pv_scalar));
+    const HeadsFinish fin{out, bv, ba, noise, seed, offset, offset_dev, pv_scalar, A};
+    SFB_CUDA_OK(launch_pdl(heads_from_partials_kernel, dim3((unsigned)blocks), dim3(256), 0, st, head_partials, P, rows, fin));
     SFB_LAUNCH_OK();
     return 0;
 }
@@ -641,6 +463,41 @@ int sfb200_heads_from_partials_tuple(const float* head_partials, int P, int64_t 
     if (int rc = make_tuple_out(out, A, num_heads, head_sizes_host)) return rc;
     return heads_from_partials_impl(head_partials, P, rows, A, bv, ba, out, noise, philox_seed, philox_offset,
                                     philox_offset_dev, policy_version_scalar, (cudaStream_t)stream);
+}
+
+int sfb200_linear_act_heads_forward_fused(
+    const float* x, int64_t ldx, const float* W, const float* b, float* y, int64_t ldy, int64_t M, int N, int K, int act,
+    int engine, const float* Wv, const float* bv, const float* Wa, const float* ba, int A, float* head_partials,
+    int32_t* finish_counters, int dist_kind, int act_dim, int adaptive_stddev, const float* learned_log_std,
+    float tanh_scale, int num_heads, const int32_t* head_sizes_host, float* values, int64_t values_stride, float* logits,
+    int64_t logits_stride, const float* noise, uint64_t philox_seed, uint64_t philox_offset,
+    const int64_t* philox_offset_dev, float* actions_f32, int64_t actions_stride, void* env_actions, float* log_prob,
+    int64_t log_prob_stride, const float* policy_version_scalar, float* policy_version_out, int64_t pv_stride,
+    void* stream) {
+    SFB_CHECK_ARG(x && W && b && Wv && bv && Wa && ba && head_partials && finish_counters && values && M >= 0 && N > 0 && K > 0,
+                  "linear_act_heads_forward_fused: bad arguments");
+    SFB_CHECK_ARG(dist_kind >= 0 && dist_kind <= 2, "linear_act_heads_forward_fused: dist_kind 0 categorical, 1 tuple, 2 Gaussian");
+    if (M == 0) return 0;
+    HeadsOut out{values, values_stride, logits, logits_stride, actions_f32, actions_stride, nullptr, log_prob,
+                 log_prob_stride, policy_version_out, pv_stride, 0, 0, nullptr, 0.f, nullptr};
+    if (dist_kind == 2) {
+        if (int rc = make_gaussian_out(out, act_dim, adaptive_stddev, learned_log_std, tanh_scale, values, values_stride, logits,
+                                       logits_stride, actions_f32, actions_stride, (float*)env_actions, log_prob,
+                                       log_prob_stride, policy_version_out, pv_stride))
+            return rc;
+        SFB_CHECK_ARG(A == (adaptive_stddev ? 2 * act_dim : act_dim), "linear_act_heads_forward_fused: A does not match act_dim");
+    } else {
+        out.env_actions = (int32_t*)env_actions;
+        if (dist_kind == 1)
+            if (int rc = make_tuple_out(out, A, num_heads, head_sizes_host)) return rc;
+    }
+    const HeadsFinish fin{out, bv, ba, noise, philox_seed, philox_offset, philox_offset_dev, policy_version_scalar, A};
+    int rc = tc_linear_act_heads_forward(x, ldx, W, b, y, ldy, M, N, K, act, engine, Wv, Wa, A, head_partials,
+                                         (cudaStream_t)stream, &fin, finish_counters);
+    SFB_CHECK_ARG(rc != SFB_TC_UNSUPPORTED,
+                  "linear_act_heads_forward_fused: shape/engine not covered (N=%d K=%d A=%d engine=%d); "
+                  "sfb200_linear_heads_partials() tells when to use the separate calls", N, K, A, engine);
+    return rc;
 }
 
 int sfb200_heads_forward_continuous(const float* h, int64_t ldh, int64_t rows, int H, int act_dim, int adaptive_stddev,

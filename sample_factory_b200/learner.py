@@ -497,7 +497,6 @@ class Learner:
     def train(self, batch: Dict[str, Tensor]) -> Dict[str, float]:
         """learner.py:1036-1067. `batch` is the trajectory dict (reference layout) on this learner's device."""
         cfg = self.cfg
-        self._last_batch = batch
         if self.use_graph:
             return self._train_graphed(batch)
         launches0 = ops.launch_count()
@@ -528,6 +527,7 @@ class Learner:
                     break
                 prev_epoch_actor_loss = new_loss
         self.num_minibatches_done = log_idx
+        self._snapshot_policy_lag(batch, log_idx)
         self.kernel_launches = ops.launch_count() - launches0   # counted by the library itself
         self.env_steps += self.E * self.world_size * (cfg.env_frameskip if cfg.summaries_use_frameskip else 1)
         return dict(env_steps=self.env_steps, train_step=self.train_step)
@@ -567,6 +567,7 @@ class Learner:
         # _minibatch_step advanced the host mirrors during eager / capture passes only: set them explicitly
         self.opt_step, self.train_step = opt0 + nmb, train0 + nmb
         self.num_minibatches_done = nmb
+        self._snapshot_policy_lag(batch, nmb)
         self.kernel_launches = self._graph_launches
         self.env_steps += self.E * self.world_size * (cfg.env_frameskip if cfg.summaries_use_frameskip else 1)
         return dict(env_steps=self.env_steps, train_step=self.train_step)
@@ -575,6 +576,14 @@ class Learner:
     def graph_replay_launches(self) -> int:
         """kernel launches of the last train() that happened through graph replay (not seen by the launch counter)"""
         return self._graph_launches if (self.use_graph and self._graph is not None and self._graph_calls > 2) else 0
+
+    def _snapshot_policy_lag(self, batch: Dict[str, Tensor], n: int) -> None:
+        """Keep the last minibatch's policy versions: the caller may overwrite the trajectory set (async join) before
+        fetch_stats() is asked for the policy lag."""
+        bi = (n - 1) % self.cfg.num_batches_per_epoch          # position of the last minibatch inside its epoch
+        sl = slice(bi * self.cfg.batch_size, (bi + 1) * self.cfg.batch_size)
+        self._lag = (batch["policy_version"].view(self.E)[sl].clone(), batch["policy_id"].view(self.E)[sl].clone(),
+                     self.train_step - 1)
 
     def fetch_stats(self) -> Dict[str, float]:
         """Loss summaries of the LAST minibatch of the last train() (learner.py:843-923 keys). Host sync."""
@@ -587,12 +596,10 @@ class Learner:
         out["lr"] = self.curr_lr
         out["loss"] = out["total_loss"]
         out["adam_max_second_moment"] = float(self.model.exp_avg_sq.max().item())            # learner.py:908-913
-        b = getattr(self, "_last_batch", None)
-        if b is not None:   # policy lag of the last minibatch (learner.py:915-918)
-            bi = (n - 1) % self.cfg.num_batches_per_epoch          # position of the last minibatch inside its epoch
-            sl = slice(bi * self.cfg.batch_size, (bi + 1) * self.cfg.batch_size)
-            own = b["policy_id"].view(self.E)[sl] == self.policy_id
-            vd = (float(self.train_step - 1) - b["policy_version"].view(self.E)[sl])[own]
+        lag = getattr(self, "_lag", None)
+        if lag is not None:   # policy lag of the last minibatch (learner.py:915-918)
+            pv, pid, version = lag
+            vd = (float(version) - pv)[pid == self.policy_id]
             if vd.numel() > 0:
                 out["version_diff_avg"], out["version_diff_min"], out["version_diff_max"] = (
                     float(vd.mean().item()), float(vd.min().item()), float(vd.max().item()))

@@ -295,6 +295,43 @@ def linear_act_heads_forward(x: Tensor, W: Tensor, b: Tensor, out: Optional[Tens
                _p(head_partials, F32), _stream())
 
 
+def linear_act_heads_forward_fused(x: Tensor, W: Tensor, b: Tensor, out: Optional[Tensor], act: int, engine: int,
+                                   Wv: Tensor, bv: Tensor, Wa: Tensor, ba: Tensor, head_partials: Tensor,
+                                   finish_counters: Tensor, values: Tensor, values_stride: int,
+                                   logits: Optional[Tensor] = None, logits_stride: int = 0,
+                                   noise: Optional[Tensor] = None, philox_seed: int = 0, philox_offset: int = 0,
+                                   philox_offset_dev: Optional[Tensor] = None, actions_f32: Optional[Tensor] = None,
+                                   actions_stride: int = 0, env_actions: Optional[Tensor] = None,
+                                   log_prob: Optional[Tensor] = None, log_prob_stride: int = 0,
+                                   policy_version_scalar: Optional[Tensor] = None,
+                                   policy_version_out: Optional[Tensor] = None, pv_stride: int = 0, *,
+                                   head_sizes=None, act_dim: int = 0, adaptive_stddev: bool = True,
+                                   learned_log_std: Optional[Tensor] = None, tanh_scale: float = 0.0,
+                                   continuous: bool = False) -> None:
+    """Last hidden layer + heads + distribution tail in ONE launch (the last-arriving n-tile CTA of every 128-row block
+    finishes the heads).  finish_counters: int32 [ceil(M/128)] zeros, owned by the caller."""
+    M, K = x.shape
+    N = W.shape[0]
+    A = Wa.shape[0]
+    assert W.shape[1] == K and W.is_contiguous() and Wa.is_contiguous() and Wv.is_contiguous()
+    assert out is None or out.shape == (M, N)
+    P = linear_heads_partials(N, A, engine)
+    assert P > 0 and head_partials.numel() >= P * M * HEAD_PART_PAD and head_partials.is_contiguous()
+    assert finish_counters.dtype == I32 and finish_counters.numel() * 128 >= M
+    assert noise is None or noise.is_contiguous()
+    kind = 2 if continuous else (1 if head_sizes else 0)
+    env_ptr = None if env_actions is None else _p(env_actions, F32 if continuous else I32)
+    lib().call("sfb200_linear_act_heads_forward_fused", _p(x, F32), x.stride(0), _p(W, F32), _p(b, F32), _p(out, F32),
+               0 if out is None else out.stride(0), M, N, K, act, engine, _p(Wv, F32), _p(bv, F32), _p(Wa, F32), _p(ba, F32),
+               A, _p(head_partials, F32), _p(finish_counters, I32), kind, act_dim, int(adaptive_stddev),
+               _p(learned_log_std, F32), float(tanh_scale), len(head_sizes) if head_sizes else 0,
+               _seg_array(head_sizes) if head_sizes else None, values.data_ptr(), values_stride,
+               None if logits is None else logits.data_ptr(), logits_stride, _p(noise, F32), philox_seed, philox_offset,
+               _p(philox_offset_dev, I64), None if actions_f32 is None else actions_f32.data_ptr(), actions_stride, env_ptr,
+               None if log_prob is None else log_prob.data_ptr(), log_prob_stride, _p(policy_version_scalar, F32),
+               None if policy_version_out is None else policy_version_out.data_ptr(), pv_stride, _stream())
+
+
 def heads_from_partials(head_partials: Tensor, P: int, rows: int, bv: Tensor, ba: Tensor, values: Tensor,
                         values_stride: int, logits: Optional[Tensor] = None, logits_stride: int = 0,
                         noise: Optional[Tensor] = None, philox_seed: int = 0, philox_offset: int = 0,

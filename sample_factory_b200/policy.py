@@ -53,6 +53,14 @@ class HeadsPlan:
             self.P = ops.linear_heads_partials(spec.tail_input_size, spec.num_linear_action_outputs, engine)
         if self.P > 0:
             self.part = torch.empty(self.P * max_rows * ops.HEAD_PART_PAD, dtype=torch.float32, device=model.device)
+            # optional: the GEMM finishes the heads itself (last-arriving CTA per 128-row block; these are its arrival
+            # counters).  Measured on B200 (profiles/r01_l_heads_finish_in_gemm.md): one launch less per policy step but
+            # the finishing CTA walks its 128 rows 16 deep per warp -> +25 us per step (28.0M vs 37.3M env-steps/s), so
+            # the separate, fully parallel heads_from_partials launch stays the default.
+            self.counters = torch.zeros((max_rows + 127) // 128, dtype=torch.int32, device=model.device)
+            import os
+
+            self.finish_in_gemm = os.environ.get("SFB200_HEADS_FINISH_IN_GEMM", "0") == "1"
 
 
 def forward_policy(model: PolicyModel, x: Tensor, outs: List[Tensor], act: int, engine: int, plan: HeadsPlan,
@@ -78,6 +86,14 @@ def forward_policy(model: PolicyModel, x: Tensor, outs: List[Tensor], act: int, 
             tail = rnn_fn(tail)
         for (W, b) in layers:
             last = fused and k == n_mlp - 1
+            if last and plan.finish_in_gemm:
+                out = outs[k][:M] if store_tail else None
+                sp = model.spec
+                dk = model.dist_kwargs() if sp.continuous else {}
+                ops.linear_act_heads_forward_fused(tail, W, b, out, act, engine, Wv, bv, Wa, ba, plan.part, plan.counters,
+                                                   **heads_kwargs, head_sizes=sp.action_segments, continuous=sp.continuous,
+                                                   **dk)
+                return out
             if last:
                 out = outs[k][:M] if store_tail else None
                 ops.linear_act_heads_forward(tail, W, b, out, act, engine, Wv, Wa, plan.part)

@@ -645,6 +645,18 @@ def test_linear_heads_fused_matches_separate(dev, engine_name, M, K, N, A, act):
     ops.heads_from_partials(part3, P, M, bvd, bad, **kw(o3))
     for k in o2:
         assert torch.equal(o2[k], o3[k]), k
+    # heads finished inside the GEMM kernel (last-arriving CTA of every 128-row block): identical to the two-launch path
+    counters = torch.zeros((M + 127) // 128, dtype=torch.int32, device=dev)
+    for rep in range(2):          # twice: the arrival counters must be left at zero
+        part4 = torch.full_like(part, float("nan"))
+        o4 = outs()
+        y4 = torch.full((M, N), float("nan"), device=dev)
+        ops.linear_act_heads_forward_fused(xd, Wd, bd, y4 if rep == 0 else None, actc, engine, Wvd, bvd, Wad, bad, part4,
+                                           counters, **kw(o4))
+        for k in o2:
+            assert torch.equal(o2[k], o4[k]), (k, rep)
+        assert rep == 1 or torch.equal(y4, y_ref)
+        assert torch.all(counters == 0)
     assert (o2["values"] - o1["values"]).abs().max().item() < TOL
     assert (o2["logits"] - o1["logits"]).abs().max().item() < TOL
     assert (o2["lp"] - o1["lp"]).abs().max().item() < 2 * TOL
