@@ -92,6 +92,18 @@ int sfb200_rms_apply_scalar(float* x, int64_t n, const double* mean, const doubl
 int sfb200_linear_act_forward(const float* x, int64_t ldx, const float* W, const float* b, float* y, int64_t ldy,
                               int64_t M, int N, int K, int act, int engine, void* stream);
 
+/* Sampling mode of the calling host thread, picked up by every heads entry below that samples actions (the
+ * `action_mask=` argument of ActorCritic.forward, model/actor_critic.py:189-195, filled from the observation dict's
+ * "action_mask" entry, algo/sampling/inference_worker.py:324-331; and enjoy.py:165-171 `eval_deterministic`).
+ *   action_mask        uint8 [rows, mask_row_stride] on the device or NULL; 0 = action not allowed.  Plain Discrete
+ *                      spaces only: p = masked_softmax(logits, mask), log_prob = masked_log_softmax(logits, mask)_a,
+ *                      rows that allow nothing sample from a uniform 1e-6 vector (action_distributions.py:84-95,
+ *                      135-143); the stored action_logits stay the raw logits.  The pointer is read at launch time
+ *                      (a captured CUDA graph keeps reading the same buffer).
+ *   deterministic      != 0: the action is argmax(p) (first index on ties) / the Gaussian mean, no noise is consumed.
+ * Stays in force until changed; (NULL, 0, 0) is the default. */
+int sfb200_set_sampling_mode(const uint8_t* action_mask, int64_t mask_row_stride, int deterministic);
+
 /* critic_linear + distribution_linear + CategoricalActionDistribution (model/actor_critic.py:171-186,
  * model/action_parameterization.py:33-39, algo/utils/action_distributions.py:110-148):
  *   values[i]  = h[i] . Wv + bv                                   (written at values[i * values_stride])

@@ -42,6 +42,7 @@ class OracleCfg:
     # gym.spaces.Tuple(Discrete(n_0), Discrete(n_1), ...) -> TupleActionDistribution (action_distributions.py:197-286):
     # independent categorical heads over consecutive logit segments; num_actions is then sum(n_k)
     action_segments: Optional[List[int]] = None
+    action_mask: bool = False   # the env's obs dict carries an "action_mask" entry (inference_worker.py:324-331)
     continuous: bool = False           # gym.spaces.Box action space -> ContinuousActionDistribution
     adaptive_stddev: bool = True       # cfg.py:577: False -> one learned log-stddev vector (mujoco examples)
     continuous_tanh_scale: float = 0.0  # cfg.py:583 (only read by the non-adaptive parameterization)
@@ -468,6 +469,30 @@ def cat_log_prob(logits: Tensor, actions: Tensor) -> Tensor:
     return torch.gather(cat_log_probs(logits), -1, actions.long().view(-1, 1)).view(-1)
 
 
+def masked_cat_probs(logits: Tensor, mask: Tensor) -> Tensor:
+    """masked_softmax :84-90: invalid logits pushed down by 1e9, softmax, times mask, renormalised with +1e-13"""
+    p = torch.softmax(logits + (mask == 0) * -1e9, dim=-1)
+    p = p * mask
+    return p / (p.sum(dim=-1, keepdim=True) + 1e-13)
+
+
+def masked_cat_log_probs(logits: Tensor, mask: Tensor) -> Tensor:
+    """masked_log_softmax :93-95"""
+    return torch.log_softmax(logits + (mask == 0) * -1e9, dim=-1)
+
+
+def masked_cat_sample(logits: Tensor, mask: Tensor, noise_q: Tensor) -> Tensor:
+    """sample() with an action mask :135-143: rows whose probabilities are all zero fall back to 1e-6 everywhere"""
+    p = masked_cat_probs(logits, mask)
+    all_zero = (p.sum(dim=-1) == 0).unsqueeze(-1)
+    p = torch.where(all_zero, torch.full_like(p, 1e-6), p)
+    return torch.argmax(p / noise_q, dim=-1, keepdim=True)
+
+
+def masked_cat_log_prob(logits: Tensor, mask: Tensor, actions: Tensor) -> Tensor:
+    return torch.gather(masked_cat_log_probs(logits, mask), -1, actions.long().view(-1, 1)).view(-1)
+
+
 def cat_entropy(logits: Tensor) -> Tensor:
     """:150-152"""
     return -(cat_log_probs(logits) * cat_probs(logits)).sum(-1)
@@ -593,12 +618,19 @@ def alloc_trajectories(cfg: OracleCfg, num_traj: int) -> Dict[str, Tensor]:
     return t
 
 
-def policy_step(cfg: OracleCfg, st: Dict[str, Tensor], obs: Tensor, noise_q: Tensor, rnn_state: Optional[Tensor] = None):
+def policy_step(cfg: OracleCfg, st: Dict[str, Tensor], obs: Tensor, noise_q: Tensor, rnn_state: Optional[Tensor] = None,
+                action_mask: Optional[Tensor] = None):
     """inference_worker.py:313-341 body for the categorical model:
     normalize (eval mode: no stat update) -> forward -> sample -> log-prob.
-    Returns (actions int64 [N,1], logits [N,A], log_prob [N], values [N], new_rnn_state)."""
+    `action_mask` [N, A] (0 = action not allowed) is the obs dict's "action_mask" entry (:324-331); the stored logits
+    stay the raw ones.  Returns (actions int64 [N,1], logits [N,A], log_prob [N], values [N], new_rnn_state)."""
     x = normalize_obs(cfg, st, obs, update_stats=False)
     values, logits, new_state = model_forward(cfg, st, x, rnn_state)
+    if action_mask is not None:
+        assert not cfg.action_segments and not cfg.continuous, "action masks: plain Discrete action spaces only"
+        actions = masked_cat_sample(logits, action_mask, noise_q)
+        log_prob = masked_cat_log_prob(logits, action_mask, actions)
+        return actions, logits, log_prob, values, new_state
     if cfg.action_segments:
         actions = tuple_sample(cfg, logits, noise_q)
         log_prob = tuple_log_prob(cfg, logits, actions)
@@ -618,12 +650,19 @@ class TapeVecEnv:
     obs_t is read from a pre-generated tape (independent of actions, so oracle and GPU rollouts stay aligned),
     reward = action / num_actions, terminated / truncated follow fixed integer rules of (global step, env)."""
 
-    def __init__(self, tape: Tensor, num_actions: int, term_period: int = 37, trunc_period: int = 11):
+    def __init__(self, tape: Tensor, num_actions: int, term_period: int = 37, trunc_period: int = 11,
+                 with_action_mask: bool = False):
         self.tape = tape  # [L, N, D]
         self.L, self.num_agents, self.obs_dim = tape.shape
         self.num_actions = num_actions
         self.term_period, self.trunc_period = term_period, trunc_period
+        self.with_action_mask = with_action_mask
         self.t = 0
+
+    def action_mask(self) -> Tensor:
+        """int64 [N, A] mask that goes with the CURRENT observation (obs dict key "action_mask"): a fixed integer rule of
+        (step, env, action); every 29th (step + env) row allows nothing (the reference's all-zero fallback)."""
+        return tape_action_mask(self.t, torch.arange(self.num_agents), self.num_actions)
 
     def reset(self) -> Tensor:
         self.t = 0
@@ -640,6 +679,14 @@ class TapeVecEnv:
         truncated = (((t + env) % self.trunc_period) == 0) & ~terminated
         self.t += 1
         return self.tape[self.t % self.L], rew, terminated, truncated
+
+
+def tape_action_mask(t: int, env: Tensor, num_actions: int) -> Tensor:
+    a = torch.arange(num_actions).view(1, -1)
+    e = env.view(-1, 1)
+    allowed = (((t * 3 + e * 5 + a * 7) % 3) == 0) | (a == (t + e) % num_actions)
+    allowed = allowed & (((t + e) % 29) != 0)
+    return allowed.to(torch.int64)
 
 
 def rollout(
@@ -661,7 +708,8 @@ def rollout(
         # generate_policy_request :374-388
         traj["obs"][:, t] = last_obs
         traj["rnn_states"][:, t] = rnn_state
-        actions, logits, log_prob, values, new_state = policy_step(cfg, st, last_obs, noise[t], rnn_state)
+        mask = env.action_mask() if getattr(env, "with_action_mask", False) else None
+        actions, logits, log_prob, values, new_state = policy_step(cfg, st, last_obs, noise[t], rnn_state, mask)
         # advance_rollouts part 1 :308-311 (actions stored as float32, SURVEY App.A-1)
         traj["actions"][:, t] = actions.float()
         traj["action_logits"][:, t] = logits

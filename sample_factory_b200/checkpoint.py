@@ -56,9 +56,11 @@ def _cpu(osd: dict) -> dict:
     return osd
 
 
-def load_checkpoint(cfg, model, device) -> Optional[dict]:
-    d = checkpoint_dir(cfg, 0)
-    files = get_checkpoints(d)
+def load_checkpoint(cfg, model, device, kind: str = "latest", policy_id: int = 0) -> Optional[dict]:
+    """Learner.load_from_checkpoint (learner.py:257-310) / enjoy.load_state_dict (enjoy.py:92-100): newest
+    `checkpoint_*` file, or newest `best_*` file for kind="best"."""
+    d = checkpoint_dir(cfg, policy_id)
+    files = get_checkpoints(d, dict(latest="checkpoint", best="best")[kind] + "_*")
     if not files:
         return None
     ck = torch.load(files[-1], map_location="cpu", weights_only=False)

@@ -320,6 +320,25 @@ __global__ void heads_backward_reduce_kernel(const float* __restrict__ part, int
     }
 }
 
+// sampling mode of the calling host thread (sfb200_set_sampling_mode), read by every heads entry that samples actions
+static thread_local const uint8_t* g_action_mask = nullptr;
+static thread_local int64_t g_mask_stride = 0;
+static thread_local int g_deterministic = 0;
+
+static int apply_sampling_mode(HeadsOut& out, int A) {
+    if (out.actions_f32 == nullptr) return 0;     // values / distribution parameters only: nothing is sampled
+    out.deterministic = g_deterministic;
+    if (g_action_mask) {
+        SFB_CHECK_ARG(out.dist == 0 && out.num_seg <= 1,
+                      "action masks are supported for a plain Discrete action space only (the reference indexes a Tuple's "
+                      "mask by head along the batch axis, action_distributions.py:224)");
+        SFB_CHECK_ARG(g_mask_stride >= A, "action mask: row stride %lld < %d actions", (long long)g_mask_stride, A);
+        out.action_mask = g_action_mask;
+        out.mask_stride = g_mask_stride;
+    }
+    return 0;
+}
+
 template <int AP, int RPW, bool VEC>
 static int launch_heads_forward(const float* h, int64_t ldh, int64_t rows, int H, int A, const float* Wv,
                                 const float* bv, const float* Wa, const float* ba, const HeadsOut& out,
@@ -339,8 +358,10 @@ static int launch_heads_forward(const float* h, int64_t ldh, int64_t rows, int H
 
 // A = rows of distribution_linear (n for Discrete(n); 2*act_dim or act_dim for a Box action space)
 static int heads_forward_impl(const float* h, int64_t ldh, int64_t rows, int H, int A, const float* Wv, const float* bv,
-                              const float* Wa, const float* ba, const HeadsOut& out, const float* noise, uint64_t seed,
+                              const float* Wa, const float* ba, const HeadsOut& out_in, const float* noise, uint64_t seed,
                               uint64_t offset, const int64_t* offset_dev, const float* pv_scalar, cudaStream_t st) {
+    HeadsOut out = out_in;
+    if (int rc = apply_sampling_mode(out, A)) return rc;
     SFB_CHECK_ARG(h && Wv && bv && Wa && ba && out.values && rows >= 0 && H > 0, "heads_forward: bad arguments");
     SFB_CHECK_ARG(A >= 1 && A <= 31, "heads_forward: supports 1 <= distribution_linear rows <= 31, got %d", A);
     SFB_CHECK_ARG((size_t)(A + 1) * H * sizeof(float) <= 200 * 1024, "heads_forward: (A+1)*H too large for smem");
@@ -365,8 +386,10 @@ static int heads_forward_impl(const float* h, int64_t ldh, int64_t rows, int H, 
 }
 
 static int heads_from_partials_impl(const float* head_partials, int P, int64_t rows, int A, const float* bv,
-                                    const float* ba, const HeadsOut& out, const float* noise, uint64_t seed,
+                                    const float* ba, const HeadsOut& out_in, const float* noise, uint64_t seed,
                                     uint64_t offset, const int64_t* offset_dev, const float* pv_scalar, cudaStream_t st) {
+    HeadsOut out = out_in;
+    if (int rc = apply_sampling_mode(out, A)) return rc;
     SFB_CHECK_ARG(head_partials && bv && ba && out.values && rows >= 0 && P >= 1, "heads_from_partials: bad arguments");
     SFB_CHECK_ARG(A >= 1 && A + 1 <= kHeadPartPad, "heads_from_partials: supports 1 <= A <= %d, got %d", kHeadPartPad - 1, A);
     if (rows == 0) return 0;
@@ -397,6 +420,14 @@ static int make_gaussian_out(HeadsOut& out, int act_dim, int adaptive_stddev, co
 using namespace sfb;
 
 extern "C" {
+
+int sfb200_set_sampling_mode(const uint8_t* action_mask, int64_t mask_row_stride, int deterministic) {
+    SFB_CHECK_ARG(action_mask == nullptr || mask_row_stride >= 1, "set_sampling_mode: bad mask stride");
+    g_action_mask = action_mask;
+    g_mask_stride = action_mask ? mask_row_stride : 0;
+    g_deterministic = deterministic ? 1 : 0;
+    return 0;
+}
 
 int sfb200_heads_forward(const float* h, int64_t ldh, int64_t rows, int H, int A, const float* Wv, const float* bv,
                          const float* Wa, const float* ba, float* values, int64_t values_stride, float* logits,
@@ -491,6 +522,7 @@ int sfb200_linear_act_heads_forward_fused(
         if (dist_kind == 1)
             if (int rc = make_tuple_out(out, A, num_heads, head_sizes_host)) return rc;
     }
+    if (int rc = apply_sampling_mode(out, A)) return rc;
     const HeadsFinish fin{out, bv, ba, noise, philox_seed, philox_offset, philox_offset_dev, policy_version_scalar, A};
     int rc = tc_linear_act_heads_forward(x, ldx, W, b, y, ldy, M, N, K, act, engine, Wv, Wa, A, head_partials,
                                          (cudaStream_t)stream, &fin, finish_counters);

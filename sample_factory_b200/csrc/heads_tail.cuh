@@ -20,6 +20,10 @@ struct HeadsOut {
     // Tuple(Discrete(n_0), ..., Discrete(n_{K-1})) action space (action_distributions.py:197-286): K independent
     // categorical heads over consecutive logit segments; num_seg <= 1 means one plain categorical
     int num_seg; int seg_len[8];
+    // sampling mode (sfb200_set_sampling_mode): action_mask[row * mask_stride + a] == 0 forbids action a of a plain
+    // Discrete space (masked_softmax / masked_log_softmax, action_distributions.py:84-95); deterministic = argmax of the
+    // probabilities / the Gaussian means instead of a draw (enjoy.py:165-171 eval_deterministic)
+    const uint8_t* action_mask = nullptr; int64_t mask_stride = 0; int deterministic = 0;
 };
 
 constexpr float kStddevMin = 1e-4f, kStddevMax = 1e4f;   // action_distributions.py:291-292
@@ -49,7 +53,7 @@ __device__ __forceinline__ void gaussian_row_tail(float mine, int lane, int64_t 
     if (out.actions_f32 == nullptr) return;   // values / distribution parameters only (warp-uniform)
     const float sd = clampf(expf(log_std), kStddevMin, kStddevMax);
     float eps = 0.f;
-    if (is_dim) {
+    if (is_dim && !out.deterministic) {
         if (noise) eps = noise[row * Ad + (lane - 1)];
         else {
             curandStatePhilox4_32_10_t st;
@@ -92,14 +96,22 @@ __device__ __forceinline__ void heads_row_tail(float mine, int lane, int A, int6
         return;
     }
 
-    const float x = is_logit ? mine : -INFINITY;
+    const bool masked = out.action_mask != nullptr;
+    const float mk = (masked && is_logit && out.action_mask[row * out.mask_stride + (lane - 1)] != 0) ? 1.f : 0.f;
+    // masked_softmax / masked_log_softmax :84-95: a forbidden logit gets -1e9 added (an allowed one -0.0: unchanged)
+    const float x = is_logit ? ((masked && mk == 0.f) ? __fadd_rn(mine, -1.0e9f) : mine) : -INFINITY;
     const float m = warp_max(x);
     const float e = is_logit ? expf(x - m) : 0.f;
     const float s = warp_sum(e);
-    const float p = __fdiv_rn(e, s);                    // softmax :116
+    float p = __fdiv_rn(e, s);                          // softmax :116
     const float logp = (x - m) - logf(s);               // log_softmax :125
+    if (masked) {
+        p = __fmul_rn(p, mk);                                              // :88
+        p = __fdiv_rn(p, __fadd_rn(warp_sum(p), 1.0e-13f));                // :89
+        if (__ballot_sync(0xffffffffu, p > 0.f) == 0u) p = 1.0e-6f;        // :137-140 nothing allowed: uniform fallback
+    }
     float q = 1.f;
-    if (is_logit) {
+    if (is_logit && !out.deterministic) {
         if (noise) q = noise[row * A + (lane - 1)];
         else {
             curandStatePhilox4_32_10_t st;
@@ -132,7 +144,7 @@ __device__ __forceinline__ void tuple_row_tail(float mine, int lane, int A, int6
                                                const float* __restrict__ noise, uint64_t seed, uint64_t offset, float pv) {
     const bool is_logit = lane >= 1 && lane <= A;
     float q = 1.f;
-    if (is_logit) {
+    if (is_logit && !out.deterministic) {
         if (noise) q = noise[row * A + (lane - 1)];
         else {
             curandStatePhilox4_32_10_t st;

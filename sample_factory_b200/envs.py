@@ -85,7 +85,8 @@ class TapeVecEnv:
     is_gpu_env = True
 
     def __init__(self, tape: Tensor, num_actions: int, term_period: int = 37, trunc_period: int = 11,
-                 env_index_offset: int = 0, continuous: bool = False, obs_shape=None, action_segments=None):
+                 env_index_offset: int = 0, continuous: bool = False, obs_shape=None, action_segments=None,
+                 with_action_mask: bool = False):
         assert tape.is_cuda and tape.dim() == 3 and tape.is_contiguous()
         assert tape.dtype in (torch.float32, torch.uint8)
         self.tape = tape
@@ -115,11 +116,27 @@ class TapeVecEnv:
         self._tape_w = tape.view(torch.float32) if self.obs_uint8 else tape
         self._obs_w = self.obs.view(torch.float32) if self.obs_uint8 else self.obs
         self._a0 = torch.empty(self.num_agents, dtype=torch.int32, device=dev) if self.action_segments else None
+        # with_action_mask: observations come as the reference's dict {"obs", "action_mask"}; the mask is the oracle env's
+        # integer rule of (step, env, action), computed from the device-side step counter (graph-replay safe)
+        self.with_action_mask = with_action_mask
+        if with_action_mask:
+            e = (torch.arange(self.num_agents, device=dev, dtype=torch.int64) + env_index_offset).view(-1, 1)
+            a = torch.arange(num_actions, device=dev, dtype=torch.int64).view(1, -1)
+            self._mask_e, self._mask_a, self._mask_ea = e, a, e * 5 + a * 7
+            self.action_mask = torch.empty((self.num_agents, num_actions), dtype=torch.bool, device=dev)
+
+    def _obs_out(self):
+        if not self.with_action_mask:
+            return self.obs
+        t = self.step_counter[0]
+        allowed = (((t * 3 + self._mask_ea) % 3) == 0) | (self._mask_a == (t + self._mask_e) % self.num_actions)
+        torch.logical_and(allowed, ((t + self._mask_e) % 29) != 0, out=self.action_mask)
+        return {"obs": self.obs, "action_mask": self.action_mask}
 
     def reset(self) -> Tensor:
         self.step_counter.zero_()
         self.obs.copy_(self.tape[0])
-        return self.obs
+        return self._obs_out()
 
     def step(self, actions: Tensor) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
         if self.continuous:
@@ -132,7 +149,7 @@ class TapeVecEnv:
                 actions = self._a0
             ops.tape_env_step(actions, self.num_actions, self.env_index_offset, self.term_period, self.trunc_period,
                               self.step_counter, 0, self._tape_w, self._obs_w, self.rew, self.terminated, self.truncated)
-        return self.obs, self.rew, self.terminated, self.truncated
+        return self._obs_out(), self.rew, self.terminated, self.truncated
 
 
 class HostTapeVecEnv:

@@ -135,6 +135,15 @@ def heads_forward(h: Tensor, Wv: Tensor, bv: Tensor, Wa: Tensor, ba: Tensor, val
                None if policy_version_out is None else policy_version_out.data_ptr(), pv_stride, _stream())
 
 
+def set_sampling_mode(action_mask: Optional[Tensor] = None, deterministic: bool = False) -> None:
+    """action_mask: bool / uint8 [rows, A] on the device (0 = action not allowed) or None; see sfb200_set_sampling_mode"""
+    if action_mask is not None:
+        assert action_mask.dtype in (torch.bool, torch.uint8) and action_mask.dim() == 2 and action_mask.stride(1) == 1
+        lib().call("sfb200_set_sampling_mode", action_mask.data_ptr(), action_mask.stride(0), int(deterministic))
+    else:
+        lib().call("sfb200_set_sampling_mode", None, 0, int(deterministic))
+
+
 def _seg_array(head_sizes):
     import ctypes
 

@@ -30,9 +30,14 @@ from .rnn_core import RnnCore
 
 class DeviceSampler:
     def __init__(self, cfg, env, model: PolicyModel, traj: Dict[str, Tensor], engine: int = ops.GEMM_SIMT,
-                 use_cuda_graph: bool = False, philox_seed: int = 0, record_episodes: bool = False):
+                 use_cuda_graph: bool = False, philox_seed: int = 0, record_episodes: bool = False,
+                 deterministic: bool = False):
         self.cfg = cfg
         self.env = env
+        # argmax / mean actions instead of draws (enjoy.py:165-171 eval_deterministic)
+        self.deterministic = deterministic
+        # obs dict entry "action_mask" (inference_worker.py:324-331): kept in a static bool [N, A] buffer the heads read
+        self.action_mask: Optional[Tensor] = None
         self.model = model
         self.traj = traj
         self.engine = engine
@@ -91,8 +96,23 @@ class DeviceSampler:
         self.kernel_launches_per_rollout = 0
 
     # ------------------------------------------------------------------------------------------------------------
+    def _take_obs(self, obs):
+        """Envs may return the observation tensor or the reference's obs dict {"obs": ..., "action_mask": [N, A]}; the
+        mask (any dtype, 0 = not allowed) is popped like the inference worker does and never reaches the model."""
+        if not isinstance(obs, dict):
+            return obs
+        mask = obs.get("action_mask")
+        if mask is not None:
+            spec = self.model.spec
+            if spec.continuous or spec.action_segments:
+                raise NotImplementedError("action masks are supported for plain Discrete action spaces only")
+            if self.action_mask is None:
+                self.action_mask = torch.empty((self.N, spec.num_actions), dtype=torch.bool, device=self.device)
+            torch.ne(mask.view(self.N, spec.num_actions), 0, out=self.action_mask)
+        return obs["obs"]
+
     def reset(self) -> None:
-        self.last_obs = self.env.reset()
+        self.last_obs = self._take_obs(self.env.reset())
         self.last_rnn_state.zero_()
 
     def set_policy_version(self, version: int) -> None:
@@ -124,12 +144,19 @@ class DeviceSampler:
             policy_version_out=tr["policy_version"][:, t], pv_stride=tr["policy_version"].stride(0),
         )
         # the sampler never needs the last hidden activation again: with the fused path it is not written to HBM
-        forward_policy(m, self.x_norm, self.h, self.act, self.engine, self.heads_plan, heads_kwargs, rnn_fn,
-                       store_tail=False)
+        special = self.action_mask is not None or self.deterministic
+        if special:
+            ops.set_sampling_mode(self.action_mask, self.deterministic)
+        try:
+            forward_policy(m, self.x_norm, self.h, self.act, self.engine, self.heads_plan, heads_kwargs, rnn_fn,
+                           store_tail=False)
+        finally:
+            if special:
+                ops.set_sampling_mode(None, False)
 
     def _env_and_post_step(self, t: int) -> None:
         obs, rew, terminated, truncated = self.env.step(self.env_actions)   # batched_sampling.py:316
-        self.last_obs = obs
+        self.last_obs = self._take_obs(obs)
         self._post_step(t, rew, terminated, truncated)
 
     def _post_step(self, t: int, rew: Tensor, terminated: Tensor, truncated: Tensor) -> None:
@@ -237,7 +264,7 @@ class DeviceSampler:
             gp, gq = self._step_graphs[t]
             gp.replay()
             obs, _, _, _ = self.env.step(self.env_actions)
-            assert obs is self.last_obs
+            assert self._take_obs(obs) is self.last_obs
             gq.replay()
         self.kernel_launches_per_rollout = self._graph_launches
 

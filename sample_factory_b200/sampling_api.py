@@ -62,7 +62,8 @@ def _model_spec(cfg, env) -> ModelSpec:
 class _DeviceSamplingLoop:
     """What SamplingLoop (evaluation_sampling_api.py:31-231) owns: env, trajectory buffers, the policy, the sampler."""
 
-    def __init__(self, cfg, env_info: Optional[EnvInfo], model: Optional[PolicyModel], record_episodes: bool):
+    def __init__(self, cfg, env_info: Optional[EnvInfo], model: Optional[PolicyModel], record_episodes: bool,
+                 deterministic: bool = False):
         if not torch.cuda.is_available():
             raise RuntimeError("sample_factory_b200 needs a CUDA device (B200); there is no CPU execution path")
         self.cfg = cfg
@@ -82,7 +83,8 @@ class _DeviceSamplingLoop:
         self.traj = alloc_for_spec(spec, self.env.num_agents, cfg.rollout, self.device)
         self.sampler = DeviceSampler(cfg, self.env, self.model, self.traj, engine=engine,
                                      use_cuda_graph=bool(getattr(cfg, "cuda_graph", True)),
-                                     philox_seed=(cfg.seed or 0) * 1000003, record_episodes=record_episodes)
+                                     philox_seed=(cfg.seed or 0) * 1000003, record_episodes=record_episodes,
+                                     deterministic=deterministic)
         self.stopped = False
         self.started = False
         self.status = StatusCode.SUCCESS

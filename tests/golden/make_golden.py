@@ -66,12 +66,19 @@ class RefTapeEnv(gym.Env):
             self.action_space = gym.spaces.Tuple([gym.spaces.Discrete(n) for n in action_segments])
         if continuous:   # Box(A) action space -> ContinuousActionDistribution (action_distributions.py:290-323)
             self.action_space = gym.spaces.Box(-1.0, 1.0, (tape_env.num_actions,), np.float32)
+        if tape_env.with_action_mask:   # obs dict entry the inference worker pops (inference_worker.py:324-331)
+            self.observation_space = gym.spaces.Dict({
+                "obs": self.observation_space["obs"],
+                "action_mask": gym.spaces.Box(0, 1, (tape_env.num_actions,), np.int8)})
 
     def _obs(self, o):
-        return o.clone() if self.obs_shape is None else o.view(self.num_agents, *self.obs_shape).clone()
+        o = o.clone() if self.obs_shape is None else o.view(self.num_agents, *self.obs_shape).clone()
+        if self.e.with_action_mask:
+            return {"obs": o, "action_mask": self.e.action_mask().to(torch.int8)}
+        return {"obs": o}
 
     def reset(self, **kw):
-        return {"obs": self._obs(self.e.reset())}, {}
+        return self._obs(self.e.reset()), {}
 
     def step(self, actions):
         if self.action_segments and isinstance(actions, (list, tuple)):
@@ -79,14 +86,15 @@ class RefTapeEnv(gym.Env):
             # all-discrete Tuple -- the case here -- gets one int32 [N, K] array, :40-41)
             actions = np.stack([np.asarray(a) for a in actions], axis=1)
         obs, rew, term, trunc = self.e.step(torch.as_tensor(actions))  # numpy int32 / float32 (batched_sampling.py:62-82)
-        return {"obs": self._obs(obs)}, rew, term, trunc, {}
+        return self._obs(obs), rew, term, trunc, {}
 
     def close(self):
         pass
 
 
 def run_case(name: str, N: int, T: int, obs_dim: int, A: int, hidden, iters: int, overrides: dict, poison: bool,
-             save_checkpoint: bool = False, continuous: bool = False, obs_shape=None, action_segments=None):
+             save_checkpoint: bool = False, continuous: bool = False, obs_shape=None, action_segments=None,
+             action_mask: bool = False):
     torch.manual_seed(1234)
     np.random.seed(1234)
     tape_len = T * iters + 1
@@ -95,7 +103,7 @@ def run_case(name: str, N: int, T: int, obs_dim: int, A: int, hidden, iters: int
         tape = torch.randint(0, 256, (tape_len, N, obs_dim), dtype=torch.uint8)
     else:
         tape = torch.randn(tape_len, N, obs_dim) * 1.5 + 0.3
-    tape_env = TapeVecEnv(tape, A)
+    tape_env = TapeVecEnv(tape, A, with_action_mask=action_mask)
 
     env_name = f"tape_{name}"
     register_env(env_name, lambda full_env_name, cfg, env_config, render_mode=None: RefTapeEnv(tape_env, continuous, obs_shape, action_segments))
@@ -174,9 +182,10 @@ def run_case(name: str, N: int, T: int, obs_dim: int, A: int, hidden, iters: int
                 rnn_states = runner.traj_tensors["rnn_states"][traj_slice, step]
                 if ac.training:
                     ac.eval()
+                mask = obs.pop("action_mask") if "action_mask" in obs else None          # inference_worker.py:324-326
                 normalized_obs = prepare_and_normalize_obs(ac, obs)
                 rng_before = torch.get_rng_state()
-                policy_outputs = ac(normalized_obs, rnn_states)
+                policy_outputs = ac(normalized_obs, rnn_states, action_mask=mask)
                 rng_after = torch.get_rng_state()
                 torch.set_rng_state(rng_before)
                 if action_segments:
@@ -195,6 +204,15 @@ def run_case(name: str, N: int, T: int, obs_dim: int, A: int, hidden, iters: int
                     std = torch.clamp(log_std.exp(), 1e-4, 1e4)
                     q = torch.empty_like(mu).normal_()
                     assert torch.equal(q * std + mu, policy_outputs["actions"]), "normal sample identity"
+                elif mask is not None:
+                    # masked categorical (action_distributions.py:84-95,135-143): same identity on the masked probabilities
+                    from sample_factory.algo.utils.action_distributions import masked_softmax
+
+                    probs = masked_softmax(policy_outputs["action_logits"], mask)
+                    probs = torch.where((probs.sum(-1) == 0).unsqueeze(-1), torch.full_like(probs, 1e-6), probs)
+                    q = torch.empty_like(probs).exponential_()
+                    assert torch.equal(torch.argmax(probs / q, -1), policy_outputs["actions"]), "multinomial identity"
+                    assert bool((mask.gather(1, policy_outputs["actions"].view(-1, 1)).view(-1) | (mask.sum(-1) == 0)).all())
                 else:
                     # recover the Exp(1) noise torch.multinomial consumed (SURVEY App.E) and prove the identity
                     probs = torch.softmax(policy_outputs["action_logits"], -1)
@@ -274,7 +292,8 @@ def run_case(name: str, N: int, T: int, obs_dim: int, A: int, hidden, iters: int
     meta = dict(N=N, T=T, obs_dim=obs_dim, A=A, hidden=list(hidden), iters=iters, poison=poison, continuous=continuous,
                 decoder=list(cfg.decoder_mlp_layers),
                 obs_shape=None if obs_shape is None else tuple(obs_shape),
-                action_segments=None if action_segments is None else list(action_segments), **overrides)
+                action_segments=None if action_segments is None else list(action_segments), action_mask=action_mask,
+                **overrides)
     out["meta"] = np.array(repr(meta))
     # a few flags the oracle needs, straight from the reference cfg object
     for k in ["gamma", "gae_lambda", "ppo_clip_ratio", "ppo_clip_value", "exploration_loss_coeff", "value_loss_coeff",
@@ -413,6 +432,13 @@ if __name__ == "__main__":
         "tiny_lamb", N=32, T=8, obs_dim=16, A=8, hidden=[64, 64], iters=2,
         overrides=dict(batch_size=128, num_batches_per_epoch=2, num_epochs=2, optimizer="lamb", learning_rate=3e-3),
         poison=True,
+    )
+    # action masks (obs dict key "action_mask", inference_worker.py:324-331 -> masked_softmax / masked_log_softmax,
+    # action_distributions.py:84-95): masked sampling in the rollout; the learner ignores the mask, like the reference
+    run_case(
+        "tiny_mask", N=64, T=8, obs_dim=16, A=7, hidden=[64, 64], iters=2,
+        overrides=dict(batch_size=256, num_batches_per_epoch=2, num_epochs=2),
+        poison=True, action_mask=True,
     )
     # cfg-2 hyper-parameters and model (300 553 params) at a reduced env count
     run_case(

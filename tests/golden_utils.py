@@ -40,6 +40,7 @@ def load_case(name):
         obs_scale=float(c.get("obs_scale", 1.0)), obs_subtract_mean=float(c.get("obs_subtract_mean", 0.0)),
         obs_shape=tuple(meta["obs_shape"]) if meta.get("obs_shape") else None,
         action_segments=list(meta["action_segments"]) if meta.get("action_segments") else None,
+        action_mask=bool(meta.get("action_mask", False)),
         encoder_conv_architecture=(str(z["cfg/encoder_conv_architecture"]) if "cfg/encoder_conv_architecture" in z.files
                                    else "convnet_atari"),
         encoder_conv_mlp_layers=([int(v) for v in z["cfg/encoder_conv_mlp_layers"]] if "cfg/encoder_conv_mlp_layers" in z.files

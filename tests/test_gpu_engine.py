@@ -56,7 +56,7 @@ def build(ocfg: O.OracleCfg, N: int, state, tape, dev, engine="simt", graph=Fals
     model.load_state_dict(state, strict=False)
     traj = alloc_for_spec(spec, N, ocfg.rollout, dev)
     env = TapeVecEnv(tape.to(dev).contiguous(), ocfg.num_actions, continuous=ocfg.continuous, obs_shape=ocfg.obs_shape,
-                     action_segments=ocfg.action_segments)
+                     action_segments=ocfg.action_segments, with_action_mask=ocfg.action_mask)
     sampler = DeviceSampler(cfg, env, model, traj, engine=ops.ENGINES[engine], use_cuda_graph=graph)
     learner = Learner(cfg, model, N, engine=ops.ENGINES[engine])
     return cfg, model, traj, env, sampler, learner
@@ -77,7 +77,7 @@ def _need(engine):
         pytest.skip("tcgen05 engine not available")
 
 
-GOLDEN_CASES = ["tiny_gae", "tiny_vtrace", "tiny_gru", "tiny_lstm", "cfg2_small", "tiny_gauss", "tiny_gauss_adaptive", "tiny_conv", "tiny_symkl", "tiny_lamb", "tiny_tuple", "tiny_separate"]
+GOLDEN_CASES = ["tiny_gae", "tiny_vtrace", "tiny_gru", "tiny_lstm", "cfg2_small", "tiny_gauss", "tiny_gauss_adaptive", "tiny_conv", "tiny_symkl", "tiny_lamb", "tiny_tuple", "tiny_separate", "tiny_mask"]
 
 
 @pytest.mark.parametrize("engine", ENGINES)
@@ -273,6 +273,51 @@ def test_full_size_properties_and_graph_replay():
         o, shp = modelA._slices[n]
         mask[o:o + int(np.prod(shp))] = False
     assert torch.all(modelA.flat[mask] == 0)
+
+
+def test_action_mask_graph_replay_and_mask_respected():
+    """Action-mask env (obs dict) under the production path: in-kernel Philox noise, CUDA-graph replay == eager, every
+    sampled action is allowed by the mask of its step (rows that allow nothing excepted), and the fused GEMM + heads path
+    (hidden 128) honours the mask too."""
+    dev = torch.device("cuda", 0)
+    N, T = 512, 16
+    ocfg = O.OracleCfg(obs_dim=32, num_actions=8, encoder_mlp_layers=[128, 128], rollout=T, recurrence=1,
+                       batch_size=N * T // 2, num_batches_per_epoch=2, action_mask=True)
+    st0 = O.init_state(ocfg, seed=6)
+    tape = torch.randn(3 * T + 1, N, ocfg.obs_dim, generator=torch.Generator().manual_seed(13))
+    engine = "3xtf32" if _tc() else "simt"
+    _, _, trajA, envA, samplerA, _ = build(ocfg, N, st0, tape, dev, engine=engine, graph=False)
+    _, _, trajB, envB, samplerB, _ = build(ocfg, N, st0, tape, dev, engine=engine, graph=True)
+    for s in (samplerA, samplerB):
+        s.reset()
+        s.rollout()
+    for s in (samplerA, samplerB):
+        s.reset()
+        s.step_counter.zero_()
+        s.rollout()
+    torch.cuda.synchronize()
+    for k in trajA:
+        assert torch.equal(trajA[k], trajB[k]), f"graph replay differs from eager for {k}"
+    a = trajB["actions"][:, :, 0].cpu().long()
+    env_idx = torch.arange(N)
+    some_allowed = torch.zeros(N, T, dtype=torch.bool)
+    for t in range(T):
+        m = O.tape_action_mask(t, env_idx, ocfg.num_actions)
+        some_allowed[:, t] = m.sum(1) > 0
+        ok = m.gather(1, a[:, t:t + 1]).view(-1).bool() | ~some_allowed[:, t]
+        assert bool(ok.all()), f"forbidden action sampled at step {t}"
+    assert int(some_allowed.sum()) > 0.9 * N * T and not bool(some_allowed.all())
+    # log-probs are the masked ones: exp(lp) sums over allowed actions only -> lp >= unmasked log-softmax of the action
+    lg = trajB["action_logits"].cpu()
+    lp_unmasked = torch.log_softmax(lg, -1).gather(2, a.unsqueeze(-1)).squeeze(-1)
+    assert bool((trajB["log_prob_actions"].cpu() >= lp_unmasked - 1e-5)[some_allowed].all())
+    np.testing.assert_allclose(trajB["log_prob_actions"].cpu()[~some_allowed].numpy(), -np.log(ocfg.num_actions), atol=1e-6)
+
+
+def _tc():
+    from sample_factory_b200 import ops
+
+    return ops.tc_available()
 
 
 def test_async_double_buffered_runner_matches_lagged_oracle(tmp_path):

@@ -222,6 +222,96 @@ def test_heads_forward_and_sampling(dev, rows, H, A):
     assert torch.all(pv[:, t] == 7.0) and torch.all(pv[:, 0] == 0) and torch.all(values[:, 0] == 0)
 
 
+@pytest.mark.parametrize("rows,H,A", [(257, 64, 7), (4096, 128, 8), (100, 96, 31)])
+def test_heads_action_mask_and_deterministic(dev, rows, H, A):
+    """masked_softmax / masked_log_softmax sampling (action_distributions.py:84-95,135-143) incl. rows that allow nothing,
+    and deterministic (argmax) actions (enjoy.py:165-171), through both heads entry points."""
+    ops = _ops()
+    h = torch.randn(rows, H, generator=g(113))
+    Wv = torch.randn(1, H, generator=g(114)) / math.sqrt(H)
+    bv = torch.randn(1, generator=g(115))
+    Wa = torch.randn(A, H, generator=g(116)) / math.sqrt(H) * 2
+    ba = torch.randn(A, generator=g(117)) * 0.1
+    noise = torch.empty(rows, A).exponential_(generator=g(118))
+    mask = (torch.rand(rows, A, generator=g(119)) < 0.4)
+    mask[::13] = False                       # nothing allowed -> the reference's uniform 1e-6 fallback
+    mask[1::13] = True                       # everything allowed
+    values = torch.zeros(rows, device=dev)
+    logits = torch.zeros(rows, A, device=dev)
+    actions = torch.zeros(rows, 1, device=dev)
+    logp = torch.zeros(rows, device=dev)
+    env_actions = torch.zeros(rows, dtype=torch.int32, device=dev)
+    args = (h.to(dev), Wv.to(dev), bv.to(dev), Wa.to(dev), ba.to(dev), values, 1, logits, A, noise.to(dev), 0, 0, None,
+            actions, 1, env_actions, logp, 1)
+    mask_dev = mask.to(dev)
+
+    def partials_call(noise_dev):
+        # the same tail behind heads_from_partials: one "partial" holding the finished dot products, zero biases
+        part = torch.zeros(rows, ops.HEAD_PART_PAD, device=dev)
+        part[:, 0] = values
+        part[:, 1:A + 1] = logits
+        ops.heads_from_partials(part.view(-1), 1, rows, torch.zeros(1, device=dev), torch.zeros(A, device=dev), values, 1,
+                                None, 0, noise_dev, 0, 0, None, actions, 1, env_actions, logp, 1)
+
+    try:
+        ops.set_sampling_mode(mask_dev, False)
+        ops.heads_forward(*args)
+        dl = logits.cpu()
+        m64 = mask.to(torch.int64)
+        a_ref = O.masked_cat_sample(dl, m64, noise)
+        lp_ref = O.masked_cat_log_prob(dl, m64, a_ref)
+        assert torch.equal(env_actions.cpu().long(), a_ref.view(-1)), "masked action indices must be bit-exact"
+        allowed = mask.gather(1, a_ref) | ~mask.any(1, keepdim=True)
+        assert bool(allowed.all())
+        np.testing.assert_allclose(logp.cpu().numpy(), lp_ref.numpy(), atol=2e-6, rtol=1e-6)
+        if A + 1 <= ops.HEAD_PART_PAD:
+            env_actions.zero_(); logp.zero_()
+            partials_call(noise.to(dev))
+            assert torch.equal(env_actions.cpu().long(), a_ref.view(-1))
+            np.testing.assert_allclose(logp.cpu().numpy(), lp_ref.numpy(), atol=2e-6, rtol=1e-6)
+        # deterministic + mask: argmax of the masked probabilities; no noise consumed (Philox path would otherwise run)
+        ops.set_sampling_mode(mask_dev, True)
+        ops.heads_forward(*args[:9], None, 0, 0, None, *args[13:])
+        p = O.masked_cat_probs(dl, m64)
+        p = torch.where((p.sum(-1) == 0).unsqueeze(-1), torch.full_like(p, 1e-6), p)
+        assert torch.equal(env_actions.cpu().long(), torch.argmax(p, -1))
+        # deterministic, no mask
+        ops.set_sampling_mode(None, True)
+        ops.heads_forward(*args[:9], None, 0, 0, None, *args[13:])
+        assert torch.equal(env_actions.cpu().long(), torch.argmax(O.cat_probs(dl), -1))
+        np.testing.assert_allclose(logp.cpu().numpy(), O.cat_log_probs(dl).max(-1).values.numpy(), atol=2e-6)
+    finally:
+        ops.set_sampling_mode(None, False)
+    # back to the default: plain sampling again
+    ops.heads_forward(*args)
+    assert torch.equal(env_actions.cpu().long(), O.cat_sample(logits.cpu(), noise).view(-1))
+
+
+def test_heads_deterministic_continuous_and_mask_errors(dev):
+    ops = _ops()
+    rows, H, Ad = 300, 64, 5
+    h = torch.randn(rows, H, generator=g(120)).to(dev)
+    Wv = (torch.randn(1, H, generator=g(121)) / 8).to(dev)
+    Wa = (torch.randn(2 * Ad, H, generator=g(122)) / 8).to(dev)
+    bv, ba = torch.zeros(1, device=dev), torch.zeros(2 * Ad, device=dev)
+    values = torch.zeros(rows, device=dev)
+    params = torch.zeros(rows, 2 * Ad, device=dev)
+    actions = torch.zeros(rows, Ad, device=dev)
+    logp = torch.zeros(rows, device=dev)
+    call = lambda: ops.heads_forward_continuous(h, Wv, bv, Wa, ba, Ad, True, None, 0.0, values, 1, params, 2 * Ad, None, 3, 0,
+                                                None, actions, Ad, None, logp, 1)
+    try:
+        ops.set_sampling_mode(None, True)
+        call()
+        assert torch.equal(actions, params[:, :Ad]), "deterministic Gaussian actions are the means"
+        np.testing.assert_allclose(logp.cpu().numpy(), O.gauss_log_prob(params.cpu(), actions.cpu()).numpy(), atol=1e-5, rtol=1e-5)
+        ops.set_sampling_mode(torch.ones(rows, 2 * Ad, dtype=torch.bool, device=dev), False)
+        with pytest.raises(Exception, match="plain Discrete"):
+            call()
+    finally:
+        ops.set_sampling_mode(None, False)
+
+
 def test_heads_philox_sampling_distribution(dev):
     """Production path: in-kernel Philox Exp(1) noise. Empirical action frequencies must match softmax(logits)."""
     ops = _ops()
@@ -579,6 +669,71 @@ def test_rnn_cell_forward_backward(dev, rnn_type, M, H, IN):
     cs = torch.empty(G * H, device=dev)
     ops.colsum(dgh, cs, torch.empty(ops.colsum_workspace_bytes(G * H) // 4 + 4, device=dev))
     np.testing.assert_allclose(cs.cpu().numpy(), dgh.cpu().double().sum(0).float().numpy(), atol=1e-4, rtol=1e-4)
+
+
+@pytest.mark.parametrize("engine_name", ["simt", "3xtf32"])
+@pytest.mark.parametrize("rnn_type", ["gru", "lstm"])
+@pytest.mark.parametrize("random_dones", [True, False])
+@pytest.mark.parametrize("T,N,D", [(5, 1, 1), (5, 64, 10), (27, 1, 42), (27, 64, 10), (37, 64, 42)])
+def test_bptt_matches_loopy_torch_rnn(dev, T, N, D, random_dones, rnn_type, engine_name):
+    """The reference's own recurrent-core check (tests/algo/test_rnn.py:10-75: T in {5,27,37}, N in {1,64}, D in {1,10,42},
+    dones every 7th step or random) against the device BPTT: a step-by-step torch nn.GRU / nn.LSTM loop that zeroes the
+    state after a done is the ground truth for the forward outputs AND, through autograd, for every gradient."""
+    ops = _ops()
+    from sample_factory_b200.model import ModelSpec, PolicyModel
+    from sample_factory_b200.rnn_core import RnnCore
+
+    if engine_name != "simt" and not ops.tc_available():
+        pytest.skip("tcgen05 engine not available")
+    engine = ops.ENGINES[engine_name]
+    gen = g(1000 + T * 131 + N * 7 + D)
+    rnn = (torch.nn.GRU if rnn_type == "gru" else torch.nn.LSTM)(D, D, 1)
+    B = N * T
+    if random_dones:
+        dones = torch.randint(0, 2, (B,), generator=gen).bool()
+    else:
+        dones = torch.zeros(B, dtype=torch.bool)
+        dones[1::7] = True
+    S = D if rnn_type == "gru" else 2 * D
+    states = torch.rand(B, S, generator=gen)
+    x = torch.randn(B, D, generator=gen, requires_grad=True)
+    d_core = torch.randn(B, D, generator=gen)
+
+    # loopy ground truth, env-major rows c*T + t (tests/algo/test_rnn.py:37-45)
+    h = states[::T, :D].unsqueeze(0).contiguous()
+    c = states[::T, D:].unsqueeze(0).contiguous() if rnn_type == "lstm" else None
+    outs = []
+    for t in range(T):
+        if rnn_type == "gru":
+            out, h = rnn(x[t::T].view(1, N, D), h)
+        else:
+            out, (h, c) = rnn(x[t::T].view(1, N, D), (h, c))
+            c = c * (1 - dones[t::T].float().view(1, N, 1))
+        outs.append(out.view(N, D))
+        h = h * (1 - dones[t::T].float().view(1, N, 1))
+    loopy = torch.stack(outs, dim=1).view(B, D)
+    (loopy * d_core).sum().backward()
+
+    spec = ModelSpec(D, 3, [D], [], "elu", False, False, use_rnn=True, rnn_type=rnn_type, rnn_size=D)
+    model = PolicyModel(spec, dev)
+    sd = {f"core.core.{k}": v.detach().clone() for k, v in rnn.state_dict().items()}
+    model.load_state_dict(sd, strict=False)
+    core = RnnCore(model, engine)
+    b = core.alloc_bptt(B, T)
+    valids = torch.ones(B, dtype=torch.bool, device=dev)
+    got = core.forward_bptt(x.detach().to(dev), states.to(dev), dones.to(dev), valids, b)
+    np.testing.assert_allclose(got.cpu().numpy(), loopy.detach().numpy(), atol=4e-6)      # the reference test's tolerance
+
+    model.grad.zero_()
+    lin_ws = torch.empty(core.lin_ws_bytes(B, T, D) // 4 + 4, device=dev)
+    dgi = core.backward_bptt(d_core.to(dev), b, lin_ws).cpu().double()
+    W_ih = rnn.weight_ih_l0.detach().double()
+    np.testing.assert_allclose((dgi @ W_ih).float().numpy(), x.grad.numpy(), atol=2e-5, rtol=1e-4)
+    np.testing.assert_allclose((dgi.t() @ x.detach().double()).float().numpy(), rnn.weight_ih_l0.grad.numpy(), atol=1e-4, rtol=1e-4)
+    _, dW_hh, db_ih, db_hh = model.rnn_params(grads=True)
+    np.testing.assert_allclose(dW_hh.cpu().numpy(), rnn.weight_hh_l0.grad.numpy(), atol=1e-4, rtol=1e-4)
+    np.testing.assert_allclose(db_ih.cpu().numpy(), rnn.bias_ih_l0.grad.numpy(), atol=1e-4, rtol=1e-4)
+    np.testing.assert_allclose(db_hh.cpu().numpy(), rnn.bias_hh_l0.grad.numpy(), atol=1e-4, rtol=1e-4)
 
 
 def test_bad_arguments_raise(dev):

@@ -131,3 +131,59 @@ def test_eval_sampling_api_episode_stats_and_checkpoint(tmp_path):
     assert do_eval(cfg) == 0
     lines = open(os.path.join(str(tmp_path), "api", "eval_p0.csv")).read().strip().split("\n")
     assert lines[0] == ",reward,len,episode_number" and len(lines) - 1 >= 100
+
+
+def test_enjoy_deterministic_matches_oracle(tmp_path):
+    """enjoy(cfg) (reference enjoy.py:103-295): saved config + latest checkpoint, eval_deterministic argmax actions, mean
+    reward over the first max_num_episodes finished episodes -- against an oracle rollout with unit noise
+    (argmax(p / 1) = argmax(p))."""
+    import json
+    from types import SimpleNamespace
+
+    from sample_factory_b200 import ops
+    from sample_factory_b200.checkpoint import save_checkpoint
+    from sample_factory_b200.enjoy import enjoy
+    from sample_factory_b200.model import ModelSpec, PolicyModel
+
+    dev = torch.device("cuda", 0)
+    N, T = 48, 8
+    ocfg = O.OracleCfg(obs_dim=12, num_actions=5, encoder_mlp_layers=[32, 32], rollout=T)
+    st = O.init_state(ocfg, seed=11)
+    tape = torch.randn(40, N, ocfg.obs_dim, generator=torch.Generator().manual_seed(4)) * 2
+    _register("api_tape_enjoy", tape, ocfg.num_actions, dev)
+    cfg = _cfg(ocfg, "api_tape_enjoy", tmp_path)
+    os.makedirs(os.path.join(str(tmp_path), "api"), exist_ok=True)
+    with pytest.raises(Exception, match="Could not load saved parameters"):
+        enjoy(cfg)
+    saved = {k: v for k, v in vars(cfg).items() if isinstance(v, (int, float, str, bool, list, type(None)))}
+    with open(os.path.join(str(tmp_path), "api", "config.json"), "w") as f:
+        json.dump(saved, f)
+    with pytest.raises(RuntimeError, match="Could not load checkpoint"):
+        enjoy(cfg)
+    ops.bind_device(dev)
+    model = PolicyModel(ModelSpec(ocfg.obs_dim, ocfg.num_actions, [32, 32], [], ocfg.nonlinearity, True, True), dev)
+    model.load_state_dict(st, strict=False)
+    save_checkpoint(cfg, model, SimpleNamespace(policy_id=0, train_step=5, env_steps=100, opt_step=5, curr_lr=1e-4))
+
+    max_ep = 70
+    cfg.cli_args = dict(eval_deterministic=True, max_num_episodes=max_ep)     # explicitly passed flags override the file
+    cfg.eval_deterministic, cfg.max_num_episodes = True, max_ep
+    status, avg = enjoy(cfg)
+    assert status == 0
+
+    oenv = O.TapeVecEnv(tape, ocfg.num_actions)
+    olast = oenv.reset()
+    ep_ret, ep_len = np.zeros(N, dtype=np.float32), np.zeros(N, dtype=np.int64)
+    want_ret, want_len = [], []
+    ones = torch.ones(T, N, ocfg.num_actions)
+    while len(want_ret) < max_ep:
+        otraj = O.alloc_trajectories(ocfg, N)
+        olast = O.rollout(ocfg, st, oenv, olast, otraj, ones, 5)
+        raw = (otraj["actions"][:, :, 0] / ocfg.num_actions).numpy()
+        _episodes_from_traj(raw, otraj["dones"].numpy(), ep_ret, ep_len, want_ret, want_len)
+    np.testing.assert_allclose(avg, float(np.mean(want_ret[:max_ep])), rtol=1e-5, atol=1e-6)
+    # sampling (non-deterministic) mode gives a different answer on the same checkpoint
+    cfg.cli_args = dict(eval_deterministic=False, max_num_episodes=max_ep)
+    cfg.eval_deterministic = False
+    status2, avg2 = enjoy(cfg)
+    assert status2 == 0 and np.isfinite(avg2) and abs(avg2 - avg) > 1e-4
