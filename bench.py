@@ -313,8 +313,7 @@ def run_ours(args):
     if "gemm_fwd_l2" in kern:
         k = kern["gemm_fwd_l2"]
         ach = k["work"] / (k["avg_ms"] * 1e-3) / 1e12
-        roofline = dict(kernel=f"learner layer-2 forward GEMM [32768x512x512] + heads (partials in the epilogue, finished by the "
-                               f"last CTA of each row block) ({engine_name})", bound="tensor",
+        roofline = dict(kernel=f"learner layer-2 forward GEMM [32768x512x512] + fused heads epilogue ({engine_name})", bound="tensor",
                         achieved=ach, peak=peaks["tflops_sustained"], unit="TFLOP/s", frac=ach / peaks["tflops_sustained"],
                         traffic=_ncu_traffic("gemm_fwd_l2"), avg_kernel_ms=k["avg_ms"], launches_timed=k["launches"],
                         peak_source=peaks["source"] + ", bf16 sustained (kernel timed inside a long step)",

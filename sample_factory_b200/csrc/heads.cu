@@ -298,6 +298,122 @@ __global__ void __launch_bounds__(256, MINB) heads_backward_vec_kernel(
     if (tid < n_out) my_part[(int64_t)(A + 2) * H + tid] = acc_g;
 }
 
+// Software-pipelined variant for the learner-sized case (two columns per thread): the compiler keeps ONE row load in
+// flight per thread in the kernel above (load -> 36 FMAs -> store, serially: 8 KB in flight per SM ~ 2 TB/s), so here the
+// row loads run U rows ahead of the arithmetic through a register queue with static slots.  Row k of a thread is
+// r_begin + rl + k*RPB; a staged coefficient tile covers kHbTile/RPB consecutive k, which must be a multiple of U.
+// FULL: A + 1 == AP, so the per-output guards fold away.
+template <int AP, int U, int MINB, bool FULL>
+__global__ void __launch_bounds__(256, MINB) heads_backward_pipe_kernel(
+    const float* __restrict__ h, int64_t ldh, int64_t rows, int H, int A, const float* __restrict__ Wv,
+    const float* __restrict__ Wa, const float* __restrict__ dlogits, const float* __restrict__ dvalues, int act,
+    float* __restrict__ dz, int64_t lddz, float* __restrict__ part, int64_t rows_per_group) {
+    constexpr int VW = 2;
+    __shared__ float g_s[kHbTile][AP];
+    extern __shared__ float red_s[];   // [(A+2)][H] cross-row-lane reduction
+    const int n_out = FULL ? AP : A + 1;
+    const int tid = threadIdx.x;
+    const int TPR = H / VW, RPB = 256 / TPR;
+    const int cv = tid % TPR, rl = tid / TPR;
+    const int j = cv * VW;
+    const int64_t r_begin = blockIdx.x * rows_per_group;
+    const int64_t r_end = (r_begin + rows_per_group < rows) ? r_begin + rows_per_group : rows;
+    const int64_t part_stride = (int64_t)(A + 2) * H + n_out;
+    float* my_part = part + blockIdx.x * part_stride;
+
+    float w[AP][VW], accw[AP][VW];
+#pragma unroll
+    for (int a = 0; a < AP; ++a) {
+#pragma unroll
+        for (int c = 0; c < VW; ++c) {
+            accw[a][c] = 0.f;
+            w[a][c] = (FULL || a < n_out) ? (a == 0 ? Wv[j + c] : Wa[(int64_t)(a - 1) * H + j + c]) : 0.f;
+        }
+    }
+    float acc_db[VW] = {0.f, 0.f};
+    float acc_g = 0.f;
+    const int kpt = kHbTile / RPB;                                              // k per coefficient tile
+    const int K = (int)((r_end - r_begin - rl + RPB - 1) / RPB);                // rows of this thread (may be <= 0)
+    const float* hp = h + (r_begin + rl) * ldh + j;
+    float* dzp = dz + (r_begin + rl) * lddz + j;
+    const int64_t hstep = (int64_t)RPB * ldh, dstep = (int64_t)RPB * lddz;
+    float2 q[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) q[u] = (u < K) ? __ldg(reinterpret_cast<const float2*>(hp + u * hstep)) : make_float2(0.f, 0.f);
+
+    int k0 = 0;
+    for (int64_t b0 = r_begin; b0 < r_end; b0 += kHbTile, k0 += kpt) {
+        const int nb = (int)((r_end - b0 < kHbTile) ? (r_end - b0) : kHbTile);
+        __syncthreads();
+        for (int i = tid; i < kHbTile * n_out; i += 256) {
+            const int bb = i / n_out, a = i - bb * n_out;
+            float v = 0.f;
+            if (bb < nb) v = (a == 0) ? dvalues[b0 + bb] : dlogits[(b0 + bb) * A + (a - 1)];
+            g_s[bb][a] = v;
+        }
+        __syncthreads();
+        if (tid < n_out)
+            for (int bb = 0; bb < nb; ++bb) acc_g += g_s[bb][tid];
+        for (int kk = 0; kk < kpt; kk += U) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int k = k0 + kk + u;
+                if (k < K) {
+                    const float2 hq = q[u];
+                    if (k + U < K) q[u] = __ldg(reinterpret_cast<const float2*>(hp + (int64_t)(k + U) * hstep));
+                    const int bb = rl + (kk + u) * RPB;
+                    const float hv[VW] = {hq.x, hq.y};
+                    float sacc[VW] = {0.f, 0.f};
+#pragma unroll
+                    for (int a = 0; a < AP; ++a) {
+                        if (FULL || a < n_out) {
+                            const float g = g_s[bb][a];
+#pragma unroll
+                            for (int c = 0; c < VW; ++c) {
+                                sacc[c] = fmaf(g, w[a][c], sacc[c]);
+                                accw[a][c] = fmaf(g, hv[c], accw[a][c]);
+                            }
+                        }
+                    }
+                    float d[VW];
+#pragma unroll
+                    for (int c = 0; c < VW; ++c) {
+                        d[c] = sacc[c] * act_bwd_from_out(hv[c], act);
+                        acc_db[c] += d[c];
+                    }
+                    *reinterpret_cast<float2*>(dzp + (int64_t)k * dstep) = make_float2(d[0], d[1]);
+                }
+            }
+        }
+    }
+    // combine the RPB row lanes (fixed order -> deterministic)
+    for (int r = 0; r < RPB; ++r) {
+        __syncthreads();
+        if (rl == r) {
+#pragma unroll
+            for (int a = 0; a < AP; ++a) {
+                if (FULL || a < n_out) {
+#pragma unroll
+                    for (int c = 0; c < VW; ++c) {
+                        float v = accw[a][c];
+                        if (r > 0) v += red_s[a * H + j + c];
+                        red_s[a * H + j + c] = v;
+                    }
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < VW; ++c) {
+                float v = acc_db[c];
+                if (r > 0) v += red_s[n_out * H + j + c];
+                red_s[n_out * H + j + c] = v;
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < (A + 2) * H; i += 256) my_part[i] = red_s[i];
+    if (tid < n_out) my_part[(int64_t)(A + 2) * H + tid] = acc_g;
+}
+
 __global__ void heads_backward_reduce_kernel(const float* __restrict__ part, int groups, int H, int A,
                                              float* __restrict__ dWv, float* __restrict__ dbv, float* __restrict__ dWa,
                                              float* __restrict__ dba, float* __restrict__ db_prev) {
@@ -586,13 +702,22 @@ int sfb200_heads_backward(const float* h, int64_t ldh, int64_t rows, int H, int 
     // two columns per thread (64 registers, 4 blocks per SM) when a row fills a whole block, else four
     const bool vec2 = vec_common && (H % 2 == 0) && (H / 2 <= 256) && (256 % (H / 2) == 0) && rows >= 16384;
     const bool vec4 = vec_common && (H % 4 == 0) && (H / 4 <= 256) && (256 % (H / 4) == 0);
-    int64_t groups = (int64_t)sm_count() * (vec2 ? 4 : 2);
+    // pipelined row loads (see heads_backward_pipe_kernel): rows per thread and tile must be a multiple of the queue depth
+    static const int hb_pipe = [] { const char* e = getenv("SFB200_HB_PIPE"); return e ? atoi(e) : 1; }();
+    const bool pipe = vec2 && hb_pipe && (kHbTile / (256 / (H / 2))) % 8 == 0;
+    int64_t groups = (int64_t)sm_count() * (pipe ? 3 : (vec2 ? 4 : 2));
     if (groups > kHeadsMaxGroups) groups = kHeadsMaxGroups;
     int64_t rpg = ceil_div(rows, groups);
-    rpg = ceil_div(rpg, kHbTile) * kHbTile;
+    if (!pipe) rpg = ceil_div(rpg, kHbTile) * kHbTile;     // (the pipelined kernel fills exactly one wave instead)
     groups = ceil_div(rows, rpg);
     float* part = (float*)workspace;
-    if (vec2)
+    if (pipe && A + 1 == 9)
+        heads_backward_pipe_kernel<9, 8, 3, true><<<(unsigned)groups, 256, red_bytes, st>>>(h, ldh, rows, H, A, Wv, Wa, dlogits,
+                                                                                            dvalues, act, dz, lddz, part, rpg);
+    else if (pipe)
+        heads_backward_pipe_kernel<9, 8, 3, false><<<(unsigned)groups, 256, red_bytes, st>>>(h, ldh, rows, H, A, Wv, Wa, dlogits,
+                                                                                             dvalues, act, dz, lddz, part, rpg);
+    else if (vec2)
         heads_backward_vec_kernel<9, 2, 8, 4><<<(unsigned)groups, 256, red_bytes, st>>>(h, ldh, rows, H, A, Wv, Wa, dlogits,
                                                                                         dvalues, act, dz, lddz, part, rpg);
     else if (vec4)

@@ -338,6 +338,7 @@ def test_heads_philox_sampling_distribution(dev):
 
 
 @pytest.mark.parametrize("rows,H,A,act", [(64, 64, 8, "elu"), (32768, 512, 8, "elu"), (1000, 96, 3, "relu"),
+                                          (20011, 256, 8, "relu"), (16500, 128, 5, "tanh"), (16384, 512, 2, "elu"),
                                           (555, 300, 17, "tanh")])
 def test_heads_backward(dev, rows, H, A, act):
     ops = _ops()

@@ -152,6 +152,7 @@ def test_enjoy_deterministic_matches_oracle(tmp_path):
     tape = torch.randn(40, N, ocfg.obs_dim, generator=torch.Generator().manual_seed(4)) * 2
     _register("api_tape_enjoy", tape, ocfg.num_actions, dev)
     cfg = _cfg(ocfg, "api_tape_enjoy", tmp_path)
+    cfg.cli_args = {}          # (default_cfg records algo / env / experiment as "passed on the command line")
     os.makedirs(os.path.join(str(tmp_path), "api"), exist_ok=True)
     with pytest.raises(Exception, match="Could not load saved parameters"):
         enjoy(cfg)
