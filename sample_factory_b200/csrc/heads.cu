@@ -298,20 +298,64 @@ __global__ void __launch_bounds__(256, MINB) heads_backward_vec_kernel(
     if (tid < n_out) my_part[(int64_t)(A + 2) * H + tid] = acc_g;
 }
 
-// Software-pipelined variant for the learner-sized case (two columns per thread): the compiler keeps ONE row load in
-// flight per thread in the kernel above (load -> 36 FMAs -> store, serially: 8 KB in flight per SM ~ 2 TB/s), so here the
-// row loads run U rows ahead of the arithmetic through a register queue with static slots.  Row k of a thread is
-// r_begin + rl + k*RPB; a staged coefficient tile covers kHbTile/RPB consecutive k, which must be a multiple of U.
-// FULL: A + 1 == AP, so the per-output guards fold away.
-template <int AP, int U, int MINB, bool FULL>
+// Software-pipelined variant for the learner-sized case (two columns per thread).  Two things bound the kernel above
+// (ncu, profiles/r01_m_ncu_heads_backward.md): the compiler keeps ONE row load in flight per thread (load -> 36 FMAs ->
+// store, serially: ~2 TB/s), and once that is fixed, instruction issue (123 instructions per row and warp, 2/3 of them
+// address arithmetic, guards and scalar shared-memory loads).  Here the row loads run U rows ahead of the arithmetic
+// through a register queue with static slots, all pointers advance by increments, full batches run unguarded, the
+// coefficients of a row come as three 128-bit shared loads, and the activation is a template parameter.
+// Row k of a thread is r_begin + rl + k*RPB; a staged coefficient tile covers kpt = kHbTile/RPB consecutive k, a
+// multiple of U.
+constexpr int kHbGP = 20;   // floats per staged coefficient row: 9 duplicated pairs (g, g) + padding to 5 x 16 bytes
+
+// packed fp32 pairs (sm_100 FFMA2: two IEEE fma.rn per instruction -- same results as the scalar form, half the issue slots)
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ float2 unpack2(uint64_t v) {
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+    return r;
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
+// one row of the pipelined kernel: hq = the thread's two h values, gp = the row's duplicated coefficient pairs in smem.
+// All nine outputs are always computed (unused ones have zero coefficients and zero weights and are never written).
+template <int ACT>
+__device__ __forceinline__ void hb_row(const uint64_t hq, const float* __restrict__ gp, const uint64_t (&w)[9],
+                                       uint64_t (&accw)[9], float (&acc_db)[2], float* __restrict__ dzk) {
+    const ulonglong2* g2 = reinterpret_cast<const ulonglong2*>(gp);
+    const ulonglong2 p0 = g2[0], p1 = g2[1], p2 = g2[2], p3 = g2[3];
+    const uint64_t p8 = *reinterpret_cast<const uint64_t*>(gp + 16);
+    const uint64_t g[9] = {p0.x, p0.y, p1.x, p1.y, p2.x, p2.y, p3.x, p3.y, p8};
+    uint64_t sacc = 0ull;    // (+0.f, +0.f)
+#pragma unroll
+    for (int a = 0; a < 9; ++a) {
+        sacc = fma2(g[a], w[a], sacc);
+        accw[a] = fma2(g[a], hq, accw[a]);
+    }
+    const float2 hv = unpack2(hq), sv = unpack2(sacc);
+    const float d0 = sv.x * act_bwd_from_out(hv.x, ACT), d1 = sv.y * act_bwd_from_out(hv.y, ACT);
+    acc_db[0] += d0;
+    acc_db[1] += d1;
+    *reinterpret_cast<float2*>(dzk) = make_float2(d0, d1);
+}
+
+template <int U, int MINB, int ACT>
 __global__ void __launch_bounds__(256, MINB) heads_backward_pipe_kernel(
     const float* __restrict__ h, int64_t ldh, int64_t rows, int H, int A, const float* __restrict__ Wv,
-    const float* __restrict__ Wa, const float* __restrict__ dlogits, const float* __restrict__ dvalues, int act,
+    const float* __restrict__ Wa, const float* __restrict__ dlogits, const float* __restrict__ dvalues,
     float* __restrict__ dz, int64_t lddz, float* __restrict__ part, int64_t rows_per_group) {
-    constexpr int VW = 2;
-    __shared__ float g_s[kHbTile][AP];
+    constexpr int VW = 2, AP = 9;
+    __shared__ __align__(16) float g_s[kHbTile][kHbGP];
     extern __shared__ float red_s[];   // [(A+2)][H] cross-row-lane reduction
-    const int n_out = FULL ? AP : A + 1;
+    const int n_out = A + 1;
     const int tid = threadIdx.x;
     const int TPR = H / VW, RPB = 256 / TPR;
     const int cv = tid % TPR, rl = tid / TPR;
@@ -321,67 +365,61 @@ __global__ void __launch_bounds__(256, MINB) heads_backward_pipe_kernel(
     const int64_t part_stride = (int64_t)(A + 2) * H + n_out;
     float* my_part = part + blockIdx.x * part_stride;
 
-    float w[AP][VW], accw[AP][VW];
+    uint64_t w[AP], accw[AP];
 #pragma unroll
     for (int a = 0; a < AP; ++a) {
-#pragma unroll
-        for (int c = 0; c < VW; ++c) {
-            accw[a][c] = 0.f;
-            w[a][c] = (FULL || a < n_out) ? (a == 0 ? Wv[j + c] : Wa[(int64_t)(a - 1) * H + j + c]) : 0.f;
-        }
+        accw[a] = 0ull;
+        const float* src = (a == 0) ? Wv : Wa + (int64_t)(a - 1) * H;
+        w[a] = (a < n_out) ? pack2(src[j], src[j + 1]) : 0ull;
     }
     float acc_db[VW] = {0.f, 0.f};
     float acc_g = 0.f;
     const int kpt = kHbTile / RPB;                                              // k per coefficient tile
     const int K = (int)((r_end - r_begin - rl + RPB - 1) / RPB);                // rows of this thread (may be <= 0)
-    const float* hp = h + (r_begin + rl) * ldh + j;
-    float* dzp = dz + (r_begin + rl) * lddz + j;
     const int64_t hstep = (int64_t)RPB * ldh, dstep = (int64_t)RPB * lddz;
-    float2 q[U];
+    const float* hnext = h + (r_begin + rl) * ldh + j;                          // next row to prefetch
+    float* dzk = dz + (r_begin + rl) * lddz + j;                                // next row to write
+    uint64_t q[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) q[u] = (u < K) ? __ldg(reinterpret_cast<const float2*>(hp + u * hstep)) : make_float2(0.f, 0.f);
+    for (int u = 0; u < U; ++u) {
+        q[u] = (u < K) ? __ldg(reinterpret_cast<const unsigned long long*>(hnext)) : 0ull;
+        hnext += hstep;
+    }
 
-    int k0 = 0;
-    for (int64_t b0 = r_begin; b0 < r_end; b0 += kHbTile, k0 += kpt) {
+    // (staging one 32-row coefficient tile at a time keeps the resident blocks out of phase; staging a whole row group up
+    //  front, with or without L2 prefetches further ahead, measured slower: 54-60 vs 50 us, profiles/r01_m_ncu_heads_backward.md)
+    int k = 0;
+    for (int64_t b0 = r_begin; b0 < r_end; b0 += kHbTile) {
         const int nb = (int)((r_end - b0 < kHbTile) ? (r_end - b0) : kHbTile);
         __syncthreads();
-        for (int i = tid; i < kHbTile * n_out; i += 256) {
-            const int bb = i / n_out, a = i - bb * n_out;
+        for (int i = tid; i < kHbTile * (kHbGP / 2); i += 256) {
+            const int bb = i / (kHbGP / 2), a = i - bb * (kHbGP / 2);
             float v = 0.f;
-            if (bb < nb) v = (a == 0) ? dvalues[b0 + bb] : dlogits[(b0 + bb) * A + (a - 1)];
-            g_s[bb][a] = v;
+            if (bb < nb && a < n_out) v = (a == 0) ? dvalues[b0 + bb] : dlogits[(b0 + bb) * A + (a - 1)];
+            *reinterpret_cast<float2*>(&g_s[bb][2 * a]) = make_float2(v, v);
         }
         __syncthreads();
         if (tid < n_out)
-            for (int bb = 0; bb < nb; ++bb) acc_g += g_s[bb][tid];
-        for (int kk = 0; kk < kpt; kk += U) {
+            for (int bb = 0; bb < nb; ++bb) acc_g += g_s[bb][2 * tid];
+        const float* gp = &g_s[rl][0];
+        for (int kk = 0; kk < kpt; kk += U, k += U) {
+            if (k + 2 * U <= K) {          // a full batch whose prefetches are all in range: no guards
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int k = k0 + kk + u;
-                if (k < K) {
-                    const float2 hq = q[u];
-                    if (k + U < K) q[u] = __ldg(reinterpret_cast<const float2*>(hp + (int64_t)(k + U) * hstep));
-                    const int bb = rl + (kk + u) * RPB;
-                    const float hv[VW] = {hq.x, hq.y};
-                    float sacc[VW] = {0.f, 0.f};
+                for (int u = 0; u < U; ++u) {
+                    const uint64_t hq = q[u];
+                    q[u] = __ldg(reinterpret_cast<const unsigned long long*>(hnext));
+                    hb_row<ACT>(hq, gp, w, accw, acc_db, dzk);
+                    hnext += hstep; dzk += dstep; gp += RPB * kHbGP;
+                }
+            } else {
 #pragma unroll
-                    for (int a = 0; a < AP; ++a) {
-                        if (FULL || a < n_out) {
-                            const float g = g_s[bb][a];
-#pragma unroll
-                            for (int c = 0; c < VW; ++c) {
-                                sacc[c] = fmaf(g, w[a][c], sacc[c]);
-                                accw[a][c] = fmaf(g, hv[c], accw[a][c]);
-                            }
-                        }
+                for (int u = 0; u < U; ++u) {
+                    if (k + u < K) {
+                        const uint64_t hq = q[u];
+                        if (k + u + U < K) q[u] = __ldg(reinterpret_cast<const unsigned long long*>(hnext));
+                        hb_row<ACT>(hq, gp, w, accw, acc_db, dzk);
                     }
-                    float d[VW];
-#pragma unroll
-                    for (int c = 0; c < VW; ++c) {
-                        d[c] = sacc[c] * act_bwd_from_out(hv[c], act);
-                        acc_db[c] += d[c];
-                    }
-                    *reinterpret_cast<float2*>(dzp + (int64_t)k * dstep) = make_float2(d[0], d[1]);
+                    hnext += hstep; dzk += dstep; gp += RPB * kHbGP;
                 }
             }
         }
@@ -392,13 +430,11 @@ __global__ void __launch_bounds__(256, MINB) heads_backward_pipe_kernel(
         if (rl == r) {
 #pragma unroll
             for (int a = 0; a < AP; ++a) {
-                if (FULL || a < n_out) {
-#pragma unroll
-                    for (int c = 0; c < VW; ++c) {
-                        float v = accw[a][c];
-                        if (r > 0) v += red_s[a * H + j + c];
-                        red_s[a * H + j + c] = v;
-                    }
+                if (a < n_out) {
+                    float2 v = unpack2(accw[a]);
+                    if (r > 0) { v.x += red_s[a * H + j]; v.y += red_s[a * H + j + 1]; }
+                    red_s[a * H + j] = v.x;
+                    red_s[a * H + j + 1] = v.y;
                 }
             }
 #pragma unroll
@@ -412,6 +448,22 @@ __global__ void __launch_bounds__(256, MINB) heads_backward_pipe_kernel(
     __syncthreads();
     for (int i = tid; i < (A + 2) * H; i += 256) my_part[i] = red_s[i];
     if (tid < n_out) my_part[(int64_t)(A + 2) * H + tid] = acc_g;
+}
+
+static void launch_heads_backward_pipe(int act, unsigned groups, size_t red_bytes, cudaStream_t st, const float* h,
+                                       int64_t ldh, int64_t rows, int H, int A, const float* Wv, const float* Wa,
+                                       const float* dlogits, const float* dvalues, float* dz, int64_t lddz, float* part,
+                                       int64_t rpg) {
+#define SFB_HBP(ACT)                                                                                                      \
+    heads_backward_pipe_kernel<8, 3, ACT><<<groups, 256, red_bytes, st>>>(h, ldh, rows, H, A, Wv, Wa, dlogits, dvalues, dz,  \
+                                                                          lddz, part, rpg)
+    switch (act) {
+        case SFB200_ACT_ELU: SFB_HBP(SFB200_ACT_ELU); break;
+        case SFB200_ACT_RELU: SFB_HBP(SFB200_ACT_RELU); break;
+        case SFB200_ACT_TANH: SFB_HBP(SFB200_ACT_TANH); break;
+        default: SFB_HBP(SFB200_ACT_NONE); break;
+    }
+#undef SFB_HBP
 }
 
 __global__ void heads_backward_reduce_kernel(const float* __restrict__ part, int groups, int H, int A,
@@ -711,12 +763,9 @@ int sfb200_heads_backward(const float* h, int64_t ldh, int64_t rows, int H, int 
     if (!pipe) rpg = ceil_div(rpg, kHbTile) * kHbTile;     // (the pipelined kernel fills exactly one wave instead)
     groups = ceil_div(rows, rpg);
     float* part = (float*)workspace;
-    if (pipe && A + 1 == 9)
-        heads_backward_pipe_kernel<9, 8, 3, true><<<(unsigned)groups, 256, red_bytes, st>>>(h, ldh, rows, H, A, Wv, Wa, dlogits,
-                                                                                            dvalues, act, dz, lddz, part, rpg);
-    else if (pipe)
-        heads_backward_pipe_kernel<9, 8, 3, false><<<(unsigned)groups, 256, red_bytes, st>>>(h, ldh, rows, H, A, Wv, Wa, dlogits,
-                                                                                             dvalues, act, dz, lddz, part, rpg);
+    if (pipe)
+        launch_heads_backward_pipe(act, (unsigned)groups, red_bytes, st, h, ldh, rows, H, A, Wv, Wa, dlogits, dvalues, dz, lddz,
+                                   part, rpg);
     else if (vec2)
         heads_backward_vec_kernel<9, 2, 8, 4><<<(unsigned)groups, 256, red_bytes, st>>>(h, ldh, rows, H, A, Wv, Wa, dlogits,
                                                                                         dvalues, act, dz, lddz, part, rpg);
