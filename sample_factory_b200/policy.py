@@ -9,6 +9,7 @@ activated layer output is stored only if the caller needs it (the learner's back
 """
 from __future__ import annotations
 
+import os
 from typing import Callable, Dict, List, Optional
 
 import torch
@@ -58,8 +59,6 @@ class HeadsPlan:
             # the finishing CTA walks its 128 rows 16 deep per warp -> +25 us per step (28.0M vs 37.3M env-steps/s), so
             # the separate, fully parallel heads_from_partials launch stays the default.
             self.counters = torch.zeros((max_rows + 127) // 128, dtype=torch.int32, device=model.device)
-            import os
-
             self.finish_in_gemm = os.environ.get("SFB200_HEADS_FINISH_IN_GEMM", "0") == "1"
 
 

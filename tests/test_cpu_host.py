@@ -293,3 +293,29 @@ def test_training_info_interface_plumbing():
     set_training_info(e, dict(approx_total_training_steps=456, reward_shaping=dict(kill=2.0)))
     assert e.training_info["approx_total_training_steps"] == 456 and e.shaping == (dict(kill=2.0), slice(0, 5))
     set_training_info(object(), dict(approx_total_training_steps=1))     # envs without the interfaces are left alone
+
+
+def test_enjoy_load_from_checkpoint_cli_overrides(tmp_path):
+    """cfg/arguments.py:227-260 semantics of enjoy's config loading: the saved file wins over defaults, explicitly passed
+    flags win over the file, parameters the file does not know are taken from the current cfg; a missing file raises."""
+    import json
+
+    from sample_factory_b200.cfg import parse_full_cfg, parse_sf_args
+    from sample_factory_b200.enjoy import cfg_file, load_from_checkpoint
+
+    argv = ["--env=my_env", "--experiment=exp1", f"--train_dir={tmp_path}", "--eval_deterministic=True", "--rollout=16"]
+    parser, _ = parse_sf_args(argv, evaluation=True)
+    cfg = parse_full_cfg(parser, argv)
+    assert cfg.cli_args["rollout"] == 16 and "gamma" not in cfg.cli_args
+    with pytest.raises(Exception, match="Could not load saved parameters"):
+        load_from_checkpoint(cfg)
+    os.makedirs(os.path.dirname(cfg_file(cfg)), exist_ok=True)
+    saved = dict(env="my_env", experiment="exp1", train_dir=str(tmp_path), rollout=64, gamma=0.9, batch_size=4096,
+                 encoder_mlp_layers=[64, 64])
+    with open(cfg_file(cfg), "w") as f:
+        json.dump(saved, f)
+    loaded = load_from_checkpoint(cfg)
+    assert loaded.rollout == 16                      # passed on the command line: overrides the file
+    assert loaded.gamma == 0.9 and loaded.batch_size == 4096 and loaded.encoder_mlp_layers == [64, 64]   # from the file
+    assert loaded.eval_deterministic is True         # not in the file: from the current cfg
+    assert loaded.max_num_episodes == cfg.max_num_episodes
