@@ -238,7 +238,8 @@ def run_ours(args):
         return float(t.item())
 
     # ------------------------------------------------------------------ device-resident arm ("value")
-    runner = Runner(make_cfg("synthetic_tape", args.engine, not args.no_graph, splits=args.splits))
+    runner = Runner(make_cfg("synthetic_tape", args.engine, not args.no_graph, splits=args.splits,
+                             learner_graph=args.learner_graph and not args.no_graph))
     runner.init()
     engine_name = {0: "simt-fp32", 1: "tcgen05-3xTF32", 2: "tcgen05-TF32"}[runner.engine]
 
@@ -292,13 +293,22 @@ def run_ours(args):
     e0.record()
     for _ in range(args.steps):
         runner.iteration()
-        replay_launches += runner.sampler.graph_replay_launches
+        replay_launches += runner.sampler.graph_replay_launches + runner.learner.graph_replay_launches
     e1.record()
     barrier()
     timing_on[0] = False
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     clock_info = clocks.stop()
     gpu_launches = (ops.launch_count() - launches0) + replay_launches
+    if runner.learner.use_graph:
+        # the learner was replayed as a graph: per-kernel CUDA events need eager launches -> three more (untimed for the
+        # headline) iterations with the same kernels launched one by one
+        runner.learner.use_graph = False
+        timing_on[0] = True
+        for _ in range(3):
+            runner.iteration()
+        barrier()
+        timing_on[0] = False
     ms_per_step = ms_total / args.steps
     value = world * N_ENVS * ROLLOUT * args.steps / (ms_total / 1e3)
 
@@ -449,6 +459,9 @@ def main():
                          "(measured at 4096 envs: 1.29 ms per rollout with 2 or 4 groups vs 1.32 ms with 1 -- a policy step is "
                          "a chain of one-wave kernels, so halving the rows per kernel does not shorten it)")
     ap.add_argument("--no-graph", dest="no_graph", action="store_true")
+    ap.add_argument("--learner-graph", dest="learner_graph", action="store_true",
+                    help="replay Learner.train() as one CUDA graph in the device-resident arm too (experiment: the per-kernel "
+                         "roofline timings need eager launches, so they are absent from this arm's line)")
     ap.add_argument("--no-e2e", dest="no_e2e", action="store_true")
     ap.add_argument("--no-async", dest="no_async", action="store_true")
     ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
