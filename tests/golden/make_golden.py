@@ -337,6 +337,28 @@ def kat_action_distribution():
     )
 
 
+def kat_masked_categorical():
+    """Masked categorical in the style of the reference's tests/algo/test_action_distributions.py:22-43 (Discrete sizes,
+    batch sizes, integer masks incl. rows that allow nothing), evaluated with the reference's own class."""
+    from sample_factory.algo.utils.action_distributions import CategoricalActionDistribution
+
+    gen = torch.Generator().manual_seed(99)
+    out = {}
+    for i, (n, b) in enumerate([(3, 1), (5, 128), (16, 512), (31, 64)]):
+        logits = torch.randn(b, n, generator=gen) * 3
+        mask = (torch.rand(b, n, generator=gen) < 0.5).to(torch.int64)
+        if b > 4:
+            mask[::9] = 0
+            mask[1::9] = 1
+        d = CategoricalActionDistribution(logits, mask)
+        out[f"c{i}/logits"], out[f"c{i}/mask"] = logits.numpy(), mask.numpy()
+        out[f"c{i}/probs"], out[f"c{i}/log_probs"] = d.probs.numpy(), d.log_probs.numpy()
+        out[f"c{i}/entropy"] = d.entropy().numpy()
+        a = torch.argmax(d.probs, -1, keepdim=True)
+        out[f"c{i}/argmax"], out[f"c{i}/log_prob_argmax"] = a.numpy(), d.log_prob(a).numpy()
+    np.savez_compressed(os.path.join(OUT_DIR, "kat_masked_categorical.npz"), **out)
+
+
 _ONLY = set(sys.argv[1:])   # optional: regenerate only the named cases
 
 
@@ -353,6 +375,8 @@ run_case = _selected(run_case)
 if __name__ == "__main__":
     if not _ONLY:
         kat_action_distribution()
+    if not _ONLY or "kat_masked_categorical" in _ONLY:
+        kat_masked_categorical()
     # tiny dims, 2 iterations, invalids + value bootstrap + fixed-KL, 2 epochs x 2 minibatches
     run_case(
         "tiny_gae", N=32, T=8, obs_dim=16, A=8, hidden=[64, 64], iters=2,
