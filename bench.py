@@ -239,7 +239,7 @@ def run_ours(args):
 
     # ------------------------------------------------------------------ device-resident arm ("value")
     runner = Runner(make_cfg("synthetic_tape", args.engine, not args.no_graph, splits=args.splits,
-                             learner_graph=args.learner_graph and not args.no_graph))
+                             learner_graph=not (args.no_learner_graph or args.no_graph)))
     runner.init()
     engine_name = {0: "simt-fp32", 1: "tcgen05-3xTF32", 2: "tcgen05-TF32"}[runner.engine]
 
@@ -362,7 +362,8 @@ def run_ours(args):
     # ------------------------------------------------------------------ async double-buffered arm (async_rl=True)
     async_info = None
     if not args.no_async:
-        arunner = Runner(make_cfg("synthetic_tape", args.engine, not args.no_graph, async_rl=True, splits=args.splits))
+        arunner = Runner(make_cfg("synthetic_tape", args.engine, not args.no_graph, async_rl=True, splits=args.splits,
+                                  learner_graph=not (args.no_learner_graph or args.no_graph)))
         arunner.init()
         for _ in range(args.warmup):
             arunner.iteration()
@@ -434,7 +435,8 @@ def run_ours(args):
                    data="synthetic",
                    config=dict(workload=WORKLOAD, envs_per_gpu=N_ENVS, rollout=ROLLOUT, global_batch=BATCH * N_MINIBATCH * world,
                                parallelism=f"dp{world} (env shards, 1 grad all-reduce per SGD step)", gemm_engine=engine_name,
-                               cuda_graph_rollout=not args.no_graph, worker_num_splits=args.splits,
+                               cuda_graph_rollout=not args.no_graph,
+                               cuda_graph_learner=not (args.no_learner_graph or args.no_graph), worker_num_splits=args.splits,
                                l2_policy="per-step working set (trajectories 45 MB + obs tape 101 MB + learner "
                                          "activations 4x64 MB + workspaces) exceeds the 126 MB L2; no explicit flush"),
                    clocks=clock_info, e2e=e2e, gpu_launches=int(gpu_launches),
@@ -459,9 +461,10 @@ def main():
                          "(measured at 4096 envs: 1.29 ms per rollout with 2 or 4 groups vs 1.32 ms with 1 -- a policy step is "
                          "a chain of one-wave kernels, so halving the rows per kernel does not shorten it)")
     ap.add_argument("--no-graph", dest="no_graph", action="store_true")
-    ap.add_argument("--learner-graph", dest="learner_graph", action="store_true",
-                    help="replay Learner.train() as one CUDA graph in the device-resident arm too (experiment: the per-kernel "
-                         "roofline timings need eager launches, so they are absent from this arm's line)")
+    ap.add_argument("--no-learner-graph", dest="no_learner_graph", action="store_true",
+                    help="launch the learner's kernels one by one instead of replaying Learner.train() as one CUDA graph "
+                         "(--learner_cuda_graph=True; measured 40.4M vs 38.0M env-steps/s, profiles/r01_m_*).  With the graph "
+                         "the per-kernel roofline timings come from three extra eager iterations after the timed region")
     ap.add_argument("--no-e2e", dest="no_e2e", action="store_true")
     ap.add_argument("--no-async", dest="no_async", action="store_true")
     ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")

@@ -11,6 +11,7 @@ Differences from the reference that are deliberate (B200-first) and do not chang
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, List, Optional
 
 import numpy as np
@@ -225,10 +226,12 @@ class Learner:
         self.opt_step = 0
         self.kernel_launches = 0
         # CUDA-graph replay of the whole train() (cfg.learner_cuda_graph): possible when nothing in it depends on host
-        # state -- constant lr schedule, one epoch (no early-stopping read-back), Adam, single process.  The step
-        # counters and the learning rate then live in device memory (read by the *_dev entry points).
+        # state -- constant lr schedule, one epoch (no early-stopping read-back), Adam.  The step counters and the
+        # learning rate then live in device memory (read by the *_dev entry points).  Data parallel: the NCCL all-reduces
+        # are captured with the kernels (SFB200_DP_GRAPH=0 keeps the multi-rank learner eager).
+        dp_graph = os.environ.get("SFB200_DP_GRAPH", "1") != "0"
         self.use_graph = (bool(getattr(cfg, "learner_cuda_graph", False)) and cfg.lr_schedule == "constant" and
-                          cfg.num_epochs == 1 and cfg.optimizer == "adam" and self.world_size == 1)
+                          cfg.num_epochs == 1 and cfg.optimizer == "adam" and (self.world_size == 1 or dp_graph))
         self.counters_dev = torch.zeros(2, dtype=torch.int64, device=dev)     # [optimizer steps taken, train_step]
         self.lr_dev = torch.full((1,), float(cfg.learning_rate), dtype=torch.float64, device=dev)
         self._graph: Optional[torch.cuda.CUDAGraph] = None
@@ -559,7 +562,9 @@ class Learner:
             if self._graph is None:
                 torch.cuda.synchronize()
                 self._graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(self._graph):
+                # (multi-rank: NCCL's watchdog thread polls events while this thread captures -> thread-local mode)
+                mode = "thread_local" if self.world_size > 1 else "global"
+                with torch.cuda.graph(self._graph, capture_error_mode=mode):
                     self._train_body(batch)
                 self._graph_batch_ptrs = ptrs
             self._graph.replay()

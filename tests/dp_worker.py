@@ -35,12 +35,12 @@ def main():
                            batch_size=N * T // NMB // world, num_batches_per_epoch=NMB, kl_loss_coeff=0.1)
     st0 = O.init_state(ocfg_full, seed=7)
     gen = torch.Generator().manual_seed(5)
-    # two iterations of data from an oracle rollout (identical on every rank: same seeds)
+    # three iterations of data from an oracle rollout (identical on every rank: same seeds)
     tape = torch.randn(2 * T + 1, N, 64, generator=gen)
     env = O.TapeVecEnv(tape, 8)
     last = env.reset()
     batches = []
-    for it in range(2):
+    for it in range(3):
         traj = O.alloc_trajectories(ocfg_full, N)
         noise = torch.empty(T, N, 8).exponential_(generator=gen)
         last = O.rollout(ocfg_full, st0, env, last, traj, noise, 0)
@@ -54,11 +54,12 @@ def main():
 
     spec = ModelSpec(64, 8, [256, 256])
 
-    def run(n_envs, ocfg, sel, data_parallel):
+    def run(n_envs, ocfg, sel, data_parallel, graph=False):
         model = PolicyModel(spec, dev)
         model.load_state_dict(st0)
         traj_dev = alloc_trajectory_tensors(64, 8, n_envs, T, dev)
-        learner = Learner(make_cfg(ocfg), model, n_envs, engine=engine, data_parallel=data_parallel)
+        learner = Learner(make_cfg(ocfg, learner_cuda_graph=graph), model, n_envs, engine=engine, data_parallel=data_parallel)
+        assert learner.use_graph == graph
         logs = []
         for b in batches:
             for k, v in b.items():
@@ -79,6 +80,19 @@ def main():
     ref_s = stats.clone()
     dist.broadcast(ref_s, src=0)
     assert torch.equal(stats, ref_s)
+
+    # the same data-parallel training with Learner.train() captured as ONE CUDA graph (kernels + NCCL all-reduces): call 1
+    # runs eagerly, call 2 captures and replays, call 3 replays -- same kernels, so the replicas must match the eager run
+    if os.environ.get("SFB200_DP_GRAPH", "1") != "0":
+        model_g, learner_g, logs_g = run(N // world, ocfg_loc, idx, True, graph=True)
+        assert learner_g._graph is not None and learner_g.graph_replay_launches > 0
+        np.testing.assert_allclose(model_g.flat.cpu().numpy(), model_dp.flat.cpu().numpy(), atol=1e-7, rtol=0)
+        assert torch.equal(torch.cat([model_g.obs_mean, model_g.obs_var, model_g.ret_mean, model_g.ret_var]), stats)
+        for lg, ld in zip(logs_g, logs_dp):
+            np.testing.assert_allclose(lg, ld, rtol=1e-6, atol=1e-7)
+        assert learner_g.train_step == learner_dp.train_step and learner_g.env_steps == learner_dp.env_steps
+        if rank == 0:
+            print("DP_GRAPH_OK")
 
     if rank == 0:
         model_1, learner_1, logs_1 = run(N, ocfg_full, None, False)
