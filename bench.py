@@ -300,6 +300,7 @@ def run_ours(args):
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     clock_info = clocks.stop()
     gpu_launches = (ops.launch_count() - launches0) + replay_launches
+    learner_graphed = bool(runner.learner.use_graph)
     if runner.learner.use_graph:
         # the learner was replayed as a graph: per-kernel CUDA events need eager launches -> three more (untimed for the
         # headline) iterations with the same kernels launched one by one
@@ -436,7 +437,7 @@ def run_ours(args):
                    config=dict(workload=WORKLOAD, envs_per_gpu=N_ENVS, rollout=ROLLOUT, global_batch=BATCH * N_MINIBATCH * world,
                                parallelism=f"dp{world} (env shards, 1 grad all-reduce per SGD step)", gemm_engine=engine_name,
                                cuda_graph_rollout=not args.no_graph,
-                               cuda_graph_learner=not (args.no_learner_graph or args.no_graph), worker_num_splits=args.splits,
+                               cuda_graph_learner=learner_graphed, worker_num_splits=args.splits,
                                l2_policy="per-step working set (trajectories 45 MB + obs tape 101 MB + learner "
                                          "activations 4x64 MB + workspaces) exceeds the 126 MB L2; no explicit flush"),
                    clocks=clock_info, e2e=e2e, gpu_launches=int(gpu_launches),

@@ -227,9 +227,11 @@ class Learner:
         self.kernel_launches = 0
         # CUDA-graph replay of the whole train() (cfg.learner_cuda_graph): possible when nothing in it depends on host
         # state -- constant lr schedule, one epoch (no early-stopping read-back), Adam.  The step counters and the
-        # learning rate then live in device memory (read by the *_dev entry points).  Data parallel: the NCCL all-reduces
-        # are captured with the kernels (SFB200_DP_GRAPH=0 keeps the multi-rank learner eager).
-        dp_graph = os.environ.get("SFB200_DP_GRAPH", "1") != "0"
+        # learning rate then live in device memory (read by the *_dev entry points).  Data parallel: opt-in with
+        # SFB200_DP_GRAPH=1 -- the NCCL all-reduces are then captured with the kernels (measured on 2 x B200: 76.0 M vs
+        # 70.6 M env-steps/s, profiles/r01_m_bench_n2_*.json); off by default until the multi-rank capture is covered
+        # by the equivalence test (tests/dp_worker.py).
+        dp_graph = os.environ.get("SFB200_DP_GRAPH", "0") == "1"
         self.use_graph = (bool(getattr(cfg, "learner_cuda_graph", False)) and cfg.lr_schedule == "constant" and
                           cfg.num_epochs == 1 and cfg.optimizer == "adam" and (self.world_size == 1 or dp_graph))
         self.counters_dev = torch.zeros(2, dtype=torch.int64, device=dev)     # [optimizer steps taken, train_step]
