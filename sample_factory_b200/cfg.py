@@ -174,17 +174,35 @@ def preprocess_cfg(cfg) -> bool:
 
 
 def verify_cfg(cfg, num_agents_total: Optional[int] = None) -> bool:
-    """The hot-path subset of cfg/arguments.py:105-201."""
+    """cfg/arguments.py:105-201: same checks, same outcome (False + one logged line per problem; warnings do not fail)."""
+    import sys
+
     ok = True
-    if cfg.normalize_returns and cfg.with_vtrace:
-        ok = False  # :129-134
-    if cfg.use_rnn and cfg.rollout % cfg.recurrence != 0:
+
+    def cfg_error(msg: str) -> None:
+        nonlocal ok
         ok = False
-    if cfg.with_vtrace and (cfg.recurrence != cfg.rollout or cfg.recurrence <= 1):
-        ok = False  # :193-194, learner.py:684-687
-    if num_agents_total is not None and not cfg.async_rl:
+        print(f"[sf_b200] cfg error: {msg}", file=sys.stderr)
+
+    if cfg.num_envs_per_worker % cfg.worker_num_splits != 0:                                                # :123-127
+        cfg_error(f"{cfg.num_envs_per_worker=} must be a multiple of {cfg.worker_num_splits=} (for double-buffered "
+                  "sampling you need to use even number of envs per worker)")
+    if cfg.normalize_returns and cfg.with_vtrace:                                                           # :129-134
+        cfg_error("Normalized returns are not supported with vtrace!")
+    if num_agents_total is not None and not cfg.async_rl:                                                   # :147-178
         samples = num_agents_total * cfg.rollout
-        if (cfg.batch_size * cfg.num_batches_per_epoch) % samples != 0 and samples % (
-                cfg.batch_size * cfg.num_batches_per_epoch) != 0:
-            ok = False  # :147-178
+        per_iteration = cfg.batch_size * cfg.num_batches_per_epoch
+        if per_iteration % samples != 0 and samples % per_iteration != 0:
+            cfg_error(f"sync mode: samples per training iteration ({cfg.num_batches_per_epoch=} * {cfg.batch_size=} = "
+                      f"{per_iteration}) and samples per rollout ({samples}) must divide one another")
+    if cfg.use_rnn:                                                                                         # :187-194
+        if cfg.recurrence <= 1:
+            cfg_error(f"{cfg.recurrence=} must be > 1 to train an RNN. Recommeded value is recurrence == {cfg.rollout=}.")
+        elif cfg.rollout % cfg.recurrence != 0:
+            cfg_error(f"{cfg.rollout=} must be a multiple of {cfg.recurrence=}")
+        if cfg.with_vtrace and cfg.recurrence != cfg.rollout:
+            cfg_error(f"{cfg.recurrence=} must be equal to {cfg.rollout=} when using vtrace.")
+    elif cfg.with_vtrace and (cfg.recurrence != cfg.rollout or cfg.recurrence <= 1):
+        # (learner.py:684-687: the V-trace scan runs over `recurrence` steps)
+        cfg_error(f"vtrace needs {cfg.recurrence=} == {cfg.rollout=} > 1")
     return ok

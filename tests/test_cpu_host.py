@@ -83,6 +83,21 @@ def test_cfg_surface_matches_reference_flags():
     assert preprocess_cfg(cfg) and cfg.recurrence == 1
     cfg.with_vtrace = True
     assert not preprocess_cfg(cfg)   # V-trace needs recurrence == rollout and no returns normalisation
+    # the reference's other verify_cfg rules (cfg/arguments.py:123-127, 187-191)
+    from sample_factory_b200.cfg import verify_cfg
+
+    c = default_cfg()
+    assert preprocess_cfg(c) and c.recurrence == c.rollout        # use_rnn default True: recurrence -1 -> rollout
+    c.num_envs_per_worker, c.worker_num_splits = 3, 2
+    assert not verify_cfg(c)
+    c.num_envs_per_worker = 4
+    assert verify_cfg(c)
+    c.recurrence = 1
+    assert not verify_cfg(c)                                      # an RNN needs recurrence > 1
+    c.use_rnn = False
+    assert verify_cfg(c)
+    c.batch_size, c.num_batches_per_epoch, c.rollout, c.async_rl = 1000, 1, 32, False
+    assert not verify_cfg(c, num_agents_total=7) and verify_cfg(c, num_agents_total=125)
 
 
 def test_model_layout_and_checkpoint_names():
