@@ -2,6 +2,7 @@
 the same parameters, normalizer statistics and advantage statistics as one process with N envs.
 The CPU-only gloo test of the same host logic is tests/test_cpu_host.py::test_data_parallel_host_logic_gloo_world2."""
 import os
+import signal
 import subprocess
 import sys
 
@@ -19,6 +20,13 @@ def test_data_parallel_equivalence_nccl(world):
     port = 29600 + (os.getpid() % 300)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "dp_worker.py")]
-    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
-    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
-    assert "DP_EQUIVALENCE_OK" in res.stdout
+    # own process group + hard limit: a stalled collective must not outlive the test (nor its pytest-timeout)
+    proc = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, cwd=ROOT, start_new_session=True)
+    try:
+        out, err = proc.communicate(timeout=300)
+    except subprocess.TimeoutExpired:
+        os.killpg(proc.pid, signal.SIGKILL)
+        out, err = proc.communicate()
+        pytest.fail("data-parallel worker did not finish in 300 s\n" + out[-2000:] + err[-2000:])
+    assert proc.returncode == 0, out[-3000:] + err[-3000:]
+    assert "DP_EQUIVALENCE_OK" in out
