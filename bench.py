@@ -156,17 +156,66 @@ def oracle_cpu_run(steps: int, warmup: int, n_envs: int = N_ENVS, calibrate: boo
     return dict(value=n_envs * ROLLOUT * len(times) / total, ms_per_step=1e3 * total / len(times), cores=cores)
 
 
+def _ref_driver_call(n_envs: int, steps: int, warmup: int, threads: int, timeout: int = 1500):
+    """One run of the UNMODIFIED reference (baseline/_ref, driven by oracle/ref_driver.py) in a subprocess (its logger is
+    chatty and its thread settings are process-wide).  Returns the result dict or None."""
+    cmd = [sys.executable, "-m", "oracle.ref_driver", "--n_envs", str(n_envs), "--rollout", str(ROLLOUT), "--obs_dim",
+           str(OBS_DIM), "--num_actions", str(N_ACTIONS), "--batch_size", str(n_envs * ROLLOUT // N_MINIBATCH),
+           "--num_batches_per_epoch", str(N_MINIBATCH), "--num_epochs", str(N_EPOCHS), "--steps", str(steps), "--warmup",
+           str(warmup), "--tape_len", str(TAPE_LEN), "--threads", str(threads), "--hidden"] + [str(h) for h in HIDDEN]
+    try:
+        res = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=timeout)
+    except subprocess.TimeoutExpired:
+        return None
+    for line in reversed(res.stdout.splitlines()):
+        if line.startswith("REF_DRIVER_RESULT "):
+            return json.loads(line[len("REF_DRIVER_RESULT "):])
+    sys.stderr.write(res.stdout[-2000:] + res.stderr[-2000:])
+    return None
+
+
+def reference_cpu_run(steps: int, warmup: int, n_envs: int = N_ENVS):
+    """The reference's own CPU implementation of the path (sample-factory 2.1.3 installed in baseline/_ref): serial mode,
+    batched sampling, torch CPU.  torch CPU throughput on this workload is not monotone in the thread count, so the count
+    is calibrated on a reduced run (1024 envs) and reported as `cores`.  None when baseline/_ref is absent."""
+    from oracle import ref_driver
+
+    if not ref_driver.available():
+        return None
+    total = os.cpu_count() or 1
+    best, best_v = None, 0.0
+    for c in sorted({c for c in (8, 16, 32, 64, total) if c <= total}):
+        r = _ref_driver_call(1024, 1, 1, c, timeout=300)
+        if r is not None and r["value"] > best_v:
+            best, best_v = c, r["value"]
+    if best is None:
+        return None
+    return _ref_driver_call(n_envs, steps, warmup, best)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    r = oracle_cpu_run(args.steps, args.warmup)
-    sample = (f"{args.steps} full iterations (4096 envs x 32 steps + learner) after {args.warmup} warm-up, oracle port, "
-              f"torch CPU with the best-performing intra-op thread count ({r['cores']} of {os.cpu_count()} host threads)")
+    # same GLOBAL env count as our arm at this N (weak scaling: 4096 envs per GPU) -- on one host, like the reference runs
+    n_envs = N_ENVS * args.gpus
+    what = f"{args.steps} full iterations ({n_envs} envs x {ROLLOUT} steps + learner) after {args.warmup} warm-up"
+    r = reference_cpu_run(args.steps, args.warmup, n_envs)
+    if r is not None:
+        kind = "reference"
+        sample = (f"{what}; the unmodified reference (sample-factory 2.1.3 pip-installed into baseline/_ref) driven through "
+                  f"BatchedVectorEnvRunner + ActorCritic forward + Learner.train, serial mode, torch CPU, "
+                  f"{r['cores']} of {os.cpu_count()} host threads (best of a calibration sweep)")
+    else:
+        kind = "port"
+        r = oracle_cpu_run(args.steps, args.warmup, n_envs)
+        sample = (f"{what}; oracle port (baseline/_ref absent), torch CPU with the best-performing intra-op thread count "
+                  f"({r['cores']} of {os.cpu_count()} host threads)")
+    workload = WORKLOAD if args.gpus == 1 else WORKLOAD.replace("4096 envs per GPU", f"{n_envs} envs (= 4096 per GPU of our arm)")
     out = dict(impl="reference", metric=METRIC, value=r["value"], unit=UNIT, n_gpus=args.gpus, steps=args.steps,
                warmup=args.warmup, ms_per_step=r["ms_per_step"], higher_is_better=True, scaling="weak",
-               vs_baseline=None, dtype="f32", data="synthetic", config=dict(workload=WORKLOAD),
-               cpu_baseline=dict(value=r["value"], unit=UNIT, cores=r["cores"], kind="port", sample=sample),
+               vs_baseline=None, dtype="f32", data="synthetic", config=dict(workload=workload, global_envs=n_envs),
+               cpu_baseline=dict(value=r["value"], unit=UNIT, cores=r["cores"], kind=kind, sample=sample),
                e2e=dict(value=r["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(out), flush=True)
 
@@ -424,10 +473,20 @@ def run_ours(args):
 
     cpu_baseline = None
     if world == 1 and rank == 0 and not args.no_cpu_baseline:
-        r = oracle_cpu_run(steps=6, warmup=2)
-        cpu_baseline = dict(value=r["value"], unit=UNIT, cores=r["cores"], kind="port",
-                            sample="6 full iterations (4096 envs x 32 steps + learner) after 2 warm-up, oracle port, torch CPU "
-                                   f"with the best-performing intra-op thread count of {os.cpu_count()} host threads", ms_per_step=r["ms_per_step"])
+        r = reference_cpu_run(steps=6, warmup=2)
+        if r is not None:
+            cpu_baseline = dict(value=r["value"], unit=UNIT, cores=r["cores"], kind="reference", ms_per_step=r["ms_per_step"],
+                                sample="6 full iterations (4096 envs x 32 steps + learner) after 2 warm-up; the unmodified reference "
+                                       "(sample-factory 2.1.3 in baseline/_ref: BatchedVectorEnvRunner + ActorCritic + Learner.train, "
+                                       f"serial mode, torch CPU), {r['cores']} of {os.cpu_count()} host threads")
+        rp = oracle_cpu_run(steps=6, warmup=2)
+        port = dict(value=rp["value"], unit=UNIT, cores=rp["cores"], kind="port", ms_per_step=rp["ms_per_step"],
+                    sample="6 full iterations after 2 warm-up, oracle port (oracle/appo_oracle.py), torch CPU with the "
+                           f"best-performing intra-op thread count of {os.cpu_count()} host threads")
+        if cpu_baseline is None:
+            cpu_baseline = port
+        else:
+            cpu_baseline["oracle_port"] = port
 
     if rank == 0:
         out = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,

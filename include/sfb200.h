@@ -498,6 +498,42 @@ int sfb200_clip_lamb_step(float* p, float* g, float* m, float* v, int64_t n, con
                           double max_grad_norm, const double* lr_scale_num, const double* lr_scale_den,
                           float* grad_norm_out, void* workspace, void* stream);
 
+/* ---------------------------------------------------------------- data parallel (NVLink peer memory) ----
+ * New functionality (the reference has no collective): G ranks x N envs == one process with G*N envs.
+ * Equivalence target: learner.py:774-821 applied to the concatenated batch.  Every rank owns one comm buffer
+ *   [16 KiB header | scratch_bytes of fp64 scratch | flat fp32 gradient]
+ * that its peers map with CUDA IPC (sfb200_ipc_export on the owner, sfb200_ipc_import on each peer; the pointer may lie
+ * anywhere inside a cudaMalloc allocation -- the handle names the allocation, `offset` the position inside it).  The
+ * buffer must be zero-filled before the first collective.  sfb200_dp_create returns a communicator id (>= 0) or -1;
+ * peer_ptrs_host[r] = device address of rank r's comm buffer as seen from THIS process (own buffer at [rank]).
+ * All collectives only enqueue kernels; their sequence numbers live in device memory (CUDA-graph replayable).  Every
+ * rank must issue the same sequence of dp_* calls. */
+int sfb200_ipc_export(const void* ptr, void* handle_out_host, int64_t* offset_out_host);
+int sfb200_ipc_import(const void* handle_host, int64_t offset, void** ptr_out_host);
+int sfb200_ipc_close(void* ptr, int64_t offset);
+int64_t sfb200_dp_header_bytes(void);
+int sfb200_dp_create(int rank, int world, const uint64_t* peer_ptrs_host, int64_t scratch_bytes);
+int sfb200_dp_destroy(int comm);
+/* g_out[0..n) = sum over ranks (rank order 0..G-1) of the gradient regions of all comm buffers; workspace >= 4 KiB */
+int sfb200_dp_grad_allreduce(int comm, float* g_out, int64_t n, void* workspace, void* stream);
+/* the same all-reduce fused with sfb200_clip_adam_step(_dev) on the reduced gradient in ONE kernel (one-shot peer pull ->
+ * device-wide barrier for the global norm -> clip -> Adam).  steps_done_dev / lr_dev non-NULL select the device-side
+ * counters of sfb200_clip_adam_step_dev (then `step` / `lr` are ignored). */
+int sfb200_dp_grad_allreduce_clip_adam(int comm, float* g_out, float* p, float* m, float* v, int64_t n, int64_t step,
+                                       const int64_t* steps_done_dev, double lr, const double* lr_dev, double beta1,
+                                       double beta2, double eps, double max_grad_norm, const double* lr_scale_num,
+                                       const double* lr_scale_den, float* grad_norm_out, void* workspace, void* stream);
+/* in-place all-reduce of n doubles; element i is column i % row_len (row_len <= 64; 0 = plain sum): columns in max_mask /
+ * min_mask are combined with max / min, columns in keep_mask are left untouched, columns in avg_mask are averaged over
+ * the ranks, all others are summed */
+int sfb200_dp_allreduce_f64(int comm, double* buf, int n, int row_len, uint64_t max_mask, uint64_t min_mask,
+                            uint64_t keep_mask, uint64_t avg_mask, void* stream);
+/* per-rank (mean, UNBIASED var) over rows_per_rank rows -> moments of the concatenation of all ranks' rows, in place
+ * (what makes G ranks update the running normalizers, running_mean_std.py:72-77, like one process with all rows) */
+int sfb200_dp_pooled_moments(int comm, float* batch_mean, float* batch_var, int dim, double rows_per_rank, void* stream);
+/* out[0] = sum_r src[r * stride + col] (global valid count from the all-reduced minibatch partials) */
+int sfb200_colsum_f64(const double* src, int rows, int stride, int col, double* out, void* stream);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

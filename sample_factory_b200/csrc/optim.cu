@@ -3,6 +3,7 @@
 #include <math.h>
 
 #include "common.cuh"
+#include "adam_core.cuh"
 
 namespace sfb {
 
@@ -25,53 +26,8 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g,
     }
 }
 
-__global__ void __launch_bounds__(256) clip_adam_kernel(float* __restrict__ p, const float* __restrict__ g,
-                                                        float* __restrict__ m, float* __restrict__ v, int64_t n,
-                                                        double lr, const double* __restrict__ lr_dev, double beta1,
-                                                        double beta2, int64_t step_host,
-                                                        const int64_t* __restrict__ step_dev, float omb1, float beta2f,
-                                                        float omb2,
-                                                        float eps, float max_norm, const double* __restrict__ part,
-                                                        int nparts, const double* __restrict__ lr_num,
-                                                        const double* __restrict__ lr_den,
-                                                        float* __restrict__ grad_norm_out, float* __restrict__ p_lo) {
-    __shared__ float s_coef;
-    __shared__ float s_step;
-    __shared__ float s_bc2;
-    if (threadIdx.x < 32) {
-        // every block reduces the (<= 480) partials itself, in the same order -> identical coefficient everywhere
-        double t = 0.0;
-        for (int k = threadIdx.x; k < nparts; k += 32) t += part[k];
-        t = warp_sum(t);
-        if (threadIdx.x == 0) {
-            const float total = (float)sqrt(t);
-            float coef = 1.f;
-            if (max_norm > 0.f) coef = fminf(__fdiv_rn(max_norm, total + 1e-6f), 1.0f);   // clip_grad.py
-            s_coef = coef;
-            // step count and learning rate may live on the device (a CUDA-graph-captured learner replays this launch)
-            const double step = (double)(step_dev ? step_dev[0] + 1 : step_host);
-            const double bc1 = 1.0 - pow(beta1, step), bc2 = 1.0 - pow(beta2, step);
-            double lr_eff = lr_dev ? lr_dev[0] : lr;
-            if (lr_num && lr_den) lr_eff = lr_eff * lr_num[0] / lr_den[0];                  // learner.py:788-794
-            s_step = (float)(lr_eff / bc1);                                                 // adam.py step_size
-            s_bc2 = (float)sqrt(bc2);
-            if (grad_norm_out && blockIdx.x == 0) grad_norm_out[0] = total;
-        }
-    }
-    __syncthreads();
-    const float coef = s_coef, step_size = s_step, bc2_sqrt = s_bc2;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const float gi = g[i] * coef;
-        float mi = m[i], vi = v[i];
-        mi = mi + omb1 * (gi - mi);                        // exp_avg.lerp_(grad, 1-beta1)
-        vi = vi * beta2f + (omb2 * gi) * gi;               // exp_avg_sq.mul_(b2).addcmul_(g, g, value=1-b2)
-        const float denom = __fdiv_rn(__fsqrt_rn(vi), bc2_sqrt) + eps;
-        const float pn = p[i] - step_size * __fdiv_rn(mi, denom);   // param.addcdiv_(exp_avg, denom, value=-step_size)
-        p[i] = pn;
-        if (p_lo) p_lo[i] = __uint_as_float(tf32_lo_bits(__float_as_uint(pn)));   // registered tf32 low half stays current
-        m[i] = mi;
-        v[i] = vi;
-    }
+__global__ void __launch_bounds__(256) clip_adam_kernel(const AdamArgs a, const double* __restrict__ part, int nparts) {
+    clip_adam_body(a, part, nparts);
 }
 
 
@@ -199,10 +155,9 @@ static int clip_adam_impl(float* p, float* g, float* m, float* v, int64_t n, int
     int64_t blocks = ceil_div(n, 256 * 2);
     const int64_t cap = (int64_t)sm_count() * 4;
     if (blocks > cap) blocks = cap;
-    clip_adam_kernel<<<(unsigned)blocks, 256, 0, st>>>(p, g, m, v, n, lr, lr_dev, beta1, beta2, step, step_dev,
-                                                       (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), (float)eps,
-                                                       (float)max_grad_norm, part, (int)nb, lr_scale_num, lr_scale_den,
-                                                       grad_norm_out, tf32_lo_lookup_mut(p, n));
+    const AdamArgs aa = make_adam_args(p, g, m, v, n, lr, lr_dev, beta1, beta2, step, step_dev, eps, max_grad_norm,
+                                       lr_scale_num, lr_scale_den, grad_norm_out);
+    clip_adam_kernel<<<(unsigned)blocks, 256, 0, st>>>(aa, part, (int)nb);
     SFB_LAUNCH_OK();
     return 0;
 }

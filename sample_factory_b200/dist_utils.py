@@ -65,3 +65,69 @@ def pooled_moments_(batch_mean: Tensor, batch_var: Tensor, rows_per_rank: int, g
     batch_mean.copy_(gmean.to(batch_mean.dtype))
     batch_var.copy_((gm2 / (total - 1.0)).to(batch_var.dtype))
     return total
+
+
+# loss-statistics rows (ops.LS): how each column combines across ranks.  Every rank's row holds rank-local sums divided by
+# the GLOBAL valid count, so the means add up; num_valid / adv_mean / adv_std are already global; extrema take max / min;
+# value_mean is a mean over the rank's whole minibatch (valid or not; equal sizes) -> mean over the ranks.
+def _ls_masks():
+    from . import ops
+
+    keep = sum(1 << ops.LS[k] for k in ("num_valid", "adv_mean", "adv_std"))
+    mx = sum(1 << ops.LS[k] for k in ("kl_old_max", "ratio_max"))
+    mn = 1 << ops.LS["ratio_min"]
+    avg = 1 << ops.LS["value_mean"]
+    return keep, mx, mn, avg
+
+
+class PeerComm:
+    """One NVLink peer-memory communicator (csrc/comm.cu): a zero-filled comm buffer in this rank's HBM
+    [header | fp64 scratch | flat fp32 gradient], exported through CUDA IPC and mapped by every peer.  torch.distributed
+    is used once, to exchange the 64-byte handles; the collectives themselves are libsfb200 kernels."""
+
+    SCRATCH_BYTES = 1 << 20
+
+    def __init__(self, device: torch.device, grad_numel: int, group=None):
+        from . import ops
+
+        assert dist.is_initialized()
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        if "expandable_segments:True" in os.environ.get("PYTORCH_CUDA_ALLOC_CONF", ""):
+            raise RuntimeError("PeerComm needs cudaMalloc-backed allocations (CUDA IPC): disable expandable_segments")
+        self.header = ops.dp_header_bytes()
+        total = self.header + self.SCRATCH_BYTES + 4 * grad_numel
+        # an allocation of its own (>= 20 MB blocks are never shared with other tensors by the caching allocator)
+        self.buf = torch.zeros(max(total, 21 << 20), dtype=torch.uint8, device=device)
+        torch.cuda.synchronize(device)
+        handle, offset = ops.ipc_export(self.buf)
+        gathered = [None] * self.world
+        dist.all_gather_object(gathered, (handle, offset), group=group)
+        self._imported = []
+        ptrs = []
+        for r, (h, off) in enumerate(gathered):
+            if r == self.rank:
+                ptrs.append(self.buf.data_ptr())
+            else:
+                p = ops.ipc_import(h, off)
+                self._imported.append((p, off))
+                ptrs.append(p)
+        self.comm = ops.dp_create(self.rank, self.world, ptrs, self.SCRATCH_BYTES)
+        g0 = self.header + self.SCRATCH_BYTES
+        self.grad = self.buf[g0: g0 + 4 * grad_numel].view(torch.float32)
+        self.workspace = torch.zeros(1024, dtype=torch.float32, device=device)
+        dist.barrier(group=group)      # every rank's buffer is zeroed and mapped before the first collective
+
+    def close(self) -> None:
+        from . import ops
+
+        if getattr(self, "comm", None) is not None:
+            ops.dp_destroy(self.comm)
+            for p, off in self._imported:
+                ops.ipc_close(p, off)
+            self.comm = None
+
+
+def peer_comm_wanted() -> bool:
+    """SFB200_DP_COMM=nccl keeps every exchange on torch.distributed (NCCL); the default is the NVLink peer kernels."""
+    return os.environ.get("SFB200_DP_COMM", "peer") != "nccl"

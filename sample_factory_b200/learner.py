@@ -20,7 +20,7 @@ import torch.distributed as dist
 from torch import Tensor
 
 from . import ops
-from .dist_utils import pooled_moments_
+from .dist_utils import PeerComm, _ls_masks, peer_comm_wanted, pooled_moments_
 from .model import PolicyModel
 from .policy import HeadsPlan, forward_policy
 from .rnn_core import RnnCore
@@ -231,7 +231,16 @@ class Learner:
         # SFB200_DP_GRAPH=1 -- the NCCL all-reduces are then captured with the kernels (measured on 2 x B200: 76.0 M vs
         # 70.6 M env-steps/s, profiles/r01_m_bench_n2_*.json); off by default until the multi-rank capture is covered
         # by the equivalence test (tests/dp_worker.py).
-        dp_graph = os.environ.get("SFB200_DP_GRAPH", "0") == "1"
+        # Data parallel: every exchange is a libsfb200 kernel over NVLink peer memory (csrc/comm.cu) -- the gradient lives in
+        # the comm buffer the peers read, so train() is kernels only and is captured like the single-GPU learner.
+        # SFB200_DP_COMM=nccl keeps the exchanges on torch.distributed (then the graph needs SFB200_DP_GRAPH=1).
+        self.comm: Optional[PeerComm] = None
+        if self.world_size > 1 and model.flat.is_cuda and peer_comm_wanted():
+            self.comm = PeerComm(dev, model.flat.numel(), self.pg)
+            model.rebind_grad(self.comm.grad)
+            self.grad_reduced = torch.zeros_like(model.flat)
+            self._ls_keep, self._ls_max, self._ls_min, self._ls_avg = _ls_masks()
+        dp_graph = self.comm is not None or os.environ.get("SFB200_DP_GRAPH", "0") == "1"
         self.use_graph = (bool(getattr(cfg, "learner_cuda_graph", False)) and cfg.lr_schedule == "constant" and
                           cfg.num_epochs == 1 and cfg.optimizer == "adam" and (self.world_size == 1 or dp_graph))
         self.counters_dev = torch.zeros(2, dtype=torch.int64, device=dev)     # [optimizer steps taken, train_step]
@@ -243,15 +252,45 @@ class Learner:
 
     # ------------------------------------------------------------------------------------------------------------
     def _allreduce(self, t: Tensor) -> None:
-        if self.world_size > 1:
+        """sum of a small float64 buffer over the ranks, in place"""
+        if self.world_size == 1:
+            return
+        if self.comm is not None:
+            ops.dp_allreduce_f64(self.comm.comm, t)
+        else:
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.pg)
+
+    def _allreduce_loss_rows(self, rows: Tensor) -> None:
+        """per-minibatch loss statistics rows [k, LS_SIZE] -> global values (means add up, extrema take max / min)"""
+        if self.world_size == 1:
+            return
+        if self.comm is not None:
+            ops.dp_allreduce_f64(self.comm.comm, rows, ops.LS_SIZE, self._ls_max, self._ls_min, self._ls_keep, self._ls_avg)
+            return
+        from .dist_utils import _ls_masks
+        keep, mx, mn, avg = _ls_masks()
+        summed = rows.clone()
+        dist.all_reduce(summed, op=dist.ReduceOp.SUM, group=self.pg)
+        big, small = rows.clone(), rows.clone()
+        dist.all_reduce(big, op=dist.ReduceOp.MAX, group=self.pg)
+        dist.all_reduce(small, op=dist.ReduceOp.MIN, group=self.pg)
+        for c in range(ops.LS_SIZE):
+            bit = 1 << c
+            if bit & keep:
+                continue
+            rows[..., c] = big[..., c] if bit & mx else (small[..., c] if bit & mn else summed[..., c])
+            if bit & avg:
+                rows[..., c] /= self.world_size
 
     def _update_rms(self, x2d: Tensor, mean: Tensor, var: Tensor, count: Tensor, bmean: Tensor, bvar: Tensor) -> None:
         """running_mean_std.py:66-77 on device. Under data parallelism the batch moments are made global first."""
         rows, dim = x2d.shape
         ops.batch_moments(x2d, bmean[:dim], bvar[:dim], self.moments_ws)
         total = rows
-        if self.world_size > 1:
+        if self.comm is not None:
+            ops.dp_pooled_moments(self.comm.comm, bmean[:dim], bvar[:dim], rows)
+            total = rows * self.world_size
+        elif self.world_size > 1:
             total = pooled_moments_(bmean[:dim], bvar[:dim], rows, self.pg)
         ops.rms_merge(mean, var, count, bmean[:dim], bvar[:dim], float(total))
 
@@ -320,7 +359,7 @@ class Learner:
                               self.mb_partials[b], self.loss_ws)
             if self.world_size > 1:
                 self._allreduce(self.mb_partials)
-            torch.sum(self.mb_partials[:, 0], dim=0, keepdim=True, out=self.num_valid_dev)   # global valid count
+            ops.colsum_f64(self.mb_partials, 0, self.num_valid_dev)                            # global valid count
 
     # ------------------------------------------------------------------------------------------------------------
     def _minibatch_step(self, batch: Dict[str, Tensor], b: int, log_idx: int) -> None:
@@ -394,21 +433,39 @@ class Learner:
             self._backward_shared(batch, x, x0, sl, valids)
         # gradient all-reduce: ONE NCCL call on the flat buffer; mean over ranks is folded into the sums:
         # each rank's loss already divides by the GLOBAL valid count, so the rank gradients simply add up.
-        self._allreduce(m.grad)
         # :781-797 clip + Adam (+ lr scaling by the valid fraction, on device)
         self.opt_step += 1
+        grad = m.grad
+        if self.comm is not None:
+            grad = self.grad_reduced
+            if cfg.optimizer == "adam":
+                # peer pull + sum + grad-norm + clip + Adam in ONE kernel (csrc/comm.cu)
+                dev_ctr = self.use_graph
+                ops.dp_grad_allreduce_clip_adam(
+                    self.comm.comm, grad, m.flat, m.exp_avg, m.exp_avg_sq, self.opt_step,
+                    self.counters_dev[0:1] if dev_ctr else None, self.curr_lr, self.lr_dev if dev_ctr else None,
+                    cfg.adam_beta1, cfg.adam_beta2, cfg.adam_eps, cfg.max_grad_norm, self.num_valid_dev,
+                    self.exp_size_total_dev(), self.grad_norm_log[log_idx: log_idx + 1], self.comm.workspace)
+                if dev_ctr:
+                    ops.advance_counters(self.counters_dev[0:1], self.counters_dev[1:2])
+                m.refresh_cat_heads()
+                self.train_step += 1
+                return
+            ops.dp_grad_allreduce(self.comm.comm, grad, self.comm.workspace)
+        elif self.world_size > 1:
+            dist.all_reduce(m.grad, op=dist.ReduceOp.SUM, group=self.pg)
         if cfg.optimizer == "lamb":
-            ops.clip_lamb_step(m.flat, m.grad, m.exp_avg, m.exp_avg_sq, self.lamb_off, self.lamb_numel, self.lamb_max,
+            ops.clip_lamb_step(m.flat, grad, m.exp_avg, m.exp_avg_sq, self.lamb_off, self.lamb_numel, self.lamb_max,
                                self.opt_step, self.curr_lr, cfg.adam_beta1, cfg.adam_beta2, cfg.adam_eps, 1e-4, 0.01,
                                cfg.max_grad_norm, self.num_valid_dev, self.exp_size_total_dev(),
                                self.grad_norm_log[log_idx : log_idx + 1], self.lamb_ws)
         elif self.use_graph:
-            ops.clip_adam_step_dev(m.flat, m.grad, m.exp_avg, m.exp_avg_sq, self.counters_dev[0:1], self.lr_dev,
+            ops.clip_adam_step_dev(m.flat, grad, m.exp_avg, m.exp_avg_sq, self.counters_dev[0:1], self.lr_dev,
                                    cfg.adam_beta1, cfg.adam_beta2, cfg.adam_eps, cfg.max_grad_norm, self.num_valid_dev,
                                    self.exp_size_total_dev(), self.grad_norm_log[log_idx : log_idx + 1], self.adam_ws)
             ops.advance_counters(self.counters_dev[0:1], self.counters_dev[1:2])
         else:
-            ops.clip_adam_step(m.flat, m.grad, m.exp_avg, m.exp_avg_sq, self.opt_step, self.curr_lr, cfg.adam_beta1,
+            ops.clip_adam_step(m.flat, grad, m.exp_avg, m.exp_avg_sq, self.opt_step, self.curr_lr, cfg.adam_beta1,
                                cfg.adam_beta2, cfg.adam_eps, cfg.max_grad_norm, self.num_valid_dev,
                                self.exp_size_total_dev(), self.grad_norm_log[log_idx : log_idx + 1], self.adam_ws)
         m.refresh_cat_heads()        # separate actor / critic weights: re-embed the updated head weights (no-op otherwise)
@@ -508,18 +565,25 @@ class Learner:
         self._prepare_batch(batch)
         recent_kls: List[float] = []
         prev_epoch_actor_loss = 1e9
-        log_idx = 0
+        log_idx = reduced_upto = 0
         nmb = cfg.num_batches_per_epoch
-        stats_rows = None
         for epoch in range(cfg.num_epochs):
             first = log_idx
             for b in range(nmb):
                 self._minibatch_step(batch, b, log_idx)
                 log_idx += 1
-                if self.lr_scheduler.invoke_after_each_minibatch():
+                if isinstance(self.lr_scheduler, KlAdaptiveScheduler) and self.lr_scheduler.invoke_after_each_minibatch():
+                    # data parallel: the decision must be taken on the GLOBAL KL or the replicas' learning rates diverge
+                    self._allreduce_loss_rows(self.loss_stats_log[log_idx - 1: log_idx])
+                    reduced_upto = log_idx
                     kl = float(self.loss_stats_log[log_idx - 1, ops.LS["kl_old_mean"]].item())   # host sync by request
                     recent_kls.append(kl)
                     self.curr_lr = self.lr_scheduler.update(self.curr_lr, recent_kls)
+                elif self.lr_scheduler.invoke_after_each_minibatch():
+                    self.curr_lr = self.lr_scheduler.update(self.curr_lr, recent_kls)       # (linear decay: no KL needed)
+            if reduced_upto < log_idx:     # data parallel: global loss statistics before any host decision / report
+                self._allreduce_loss_rows(self.loss_stats_log[reduced_upto: log_idx])
+                reduced_upto = log_idx
             need_host = cfg.num_epochs > 1 or self.lr_scheduler.invoke_after_each_epoch()
             if need_host:
                 rows = self.loss_stats_log[first:log_idx].cpu()        # one sync per epoch (reference: per minibatch)
@@ -542,6 +606,7 @@ class Learner:
         self._prepare_batch(batch)
         for b in range(self.cfg.num_batches_per_epoch):
             self._minibatch_step(batch, b, b)
+        self._allreduce_loss_rows(self.loss_stats_log[: self.cfg.num_batches_per_epoch])
 
     def _train_graphed(self, batch: Dict[str, Tensor]) -> Dict[str, float]:
         """train() as ONE graph launch: the first call runs eagerly (kernel attributes, allocator warm-up), the second

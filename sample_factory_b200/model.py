@@ -266,6 +266,13 @@ class PolicyModel:
             ops.refresh_tf32_lo(self.flat)
         self.refresh_cat_heads()
 
+    def rebind_grad(self, grad: Tensor) -> None:
+        """Move the flat gradient buffer (data parallel: into the NVLink comm buffer the peers read, dist_utils.PeerComm)"""
+        assert grad.shape == self.flat.shape and grad.dtype == torch.float32 and grad.is_contiguous()
+        grad.zero_()
+        self.grad = grad
+        self.grads = {n: grad[o: o + math.prod(shp)].view(shp) for n, (o, shp) in self._slices.items()}
+
     def __del__(self):
         try:
             if getattr(self, "flat_lo", None) is not None:

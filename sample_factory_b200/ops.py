@@ -724,3 +724,82 @@ def mask_rows(src: Tensor, dst: Tensor, reset: Tensor) -> None:
     rows, dim = src.shape
     lib().call("sfb200_mask_rows", _p(src, F32), src.stride(0), _p(dst, F32), dst.stride(0), reset.data_ptr(),
                _rs(reset), rows, dim, _stream())
+
+
+# ------------------------------------------------------------------------------------------------ data parallel (NVLink peers)
+def ipc_export(t: Tensor):
+    """(64-byte CUDA IPC handle of the allocation `t` lives in, byte offset of t inside it)"""
+    import ctypes
+
+    handle = ctypes.create_string_buffer(64)
+    off = ctypes.c_int64(0)
+    lib().call("sfb200_ipc_export", t.data_ptr(), ctypes.cast(handle, ctypes.c_void_p), ctypes.cast(ctypes.byref(off), ctypes.c_void_p))
+    return bytes(handle.raw), int(off.value)
+
+
+def ipc_import(handle: bytes, offset: int) -> int:
+    """device address (in THIS process) of a peer's exported buffer"""
+    import ctypes
+
+    h = ctypes.create_string_buffer(handle, 64)
+    out = ctypes.c_void_p(0)
+    lib().call("sfb200_ipc_import", ctypes.cast(h, ctypes.c_void_p), offset, ctypes.cast(ctypes.byref(out), ctypes.c_void_p))
+    return int(out.value)
+
+
+def ipc_close(ptr: int, offset: int) -> None:
+    lib().call("sfb200_ipc_close", ptr, offset)
+
+
+def dp_header_bytes() -> int:
+    return lib().query("sfb200_dp_header_bytes")
+
+
+def dp_create(rank: int, world: int, peer_ptrs, scratch_bytes: int) -> int:
+    import ctypes
+
+    arr = (ctypes.c_uint64 * world)(*[int(p) for p in peer_ptrs])
+    comm = lib().query("sfb200_dp_create", rank, world, ctypes.cast(arr, ctypes.c_void_p), scratch_bytes)
+    if comm < 0:
+        msg = lib().cdll.sfb200_last_error()
+        raise RuntimeError(f"sfb200_dp_create failed: {msg.decode() if msg else '?'}")
+    return comm
+
+
+def dp_destroy(comm: int) -> None:
+    lib().call("sfb200_dp_destroy", comm)
+
+
+def dp_grad_allreduce(comm: int, g_out: Tensor, workspace: Tensor) -> None:
+    assert workspace.numel() * workspace.element_size() >= 4096
+    lib().call("sfb200_dp_grad_allreduce", comm, _p(g_out, F32), g_out.numel(), workspace.data_ptr(), _stream())
+
+
+def dp_grad_allreduce_clip_adam(comm: int, g_out: Tensor, p: Tensor, m: Tensor, v: Tensor, step: int,
+                                steps_done_dev: Optional[Tensor], lr: float, lr_dev: Optional[Tensor], beta1: float,
+                                beta2: float, eps: float, max_grad_norm: float, lr_scale_num: Optional[Tensor],
+                                lr_scale_den: Optional[Tensor], grad_norm_out: Optional[Tensor], workspace: Tensor) -> None:
+    for t in (p, g_out, m, v):
+        assert t.is_contiguous() and t.dim() == 1
+    assert workspace.numel() * workspace.element_size() >= 4096
+    lib().call("sfb200_dp_grad_allreduce_clip_adam", comm, _p(g_out, F32), _p(p, F32), _p(m, F32), _p(v, F32), p.numel(),
+               step, _p(steps_done_dev, I64), lr, _p(lr_dev, F64), beta1, beta2, eps, max_grad_norm,
+               _p(lr_scale_num, F64), _p(lr_scale_den, F64), _p(grad_norm_out, F32), workspace.data_ptr(), _stream())
+
+
+def dp_allreduce_f64(comm: int, buf: Tensor, row_len: int = 0, max_mask: int = 0, min_mask: int = 0, keep_mask: int = 0,
+                     avg_mask: int = 0) -> None:
+    assert buf.is_contiguous()
+    lib().call("sfb200_dp_allreduce_f64", comm, _p(buf, F64), buf.numel(), row_len, max_mask, min_mask, keep_mask, avg_mask,
+               _stream())
+
+
+def dp_pooled_moments(comm: int, batch_mean: Tensor, batch_var: Tensor, rows_per_rank: int) -> None:
+    lib().call("sfb200_dp_pooled_moments", comm, _p(batch_mean, F32), _p(batch_var, F32), batch_mean.numel(),
+               float(rows_per_rank), _stream())
+
+
+def colsum_f64(src: Tensor, col: int, out: Tensor) -> None:
+    """out[0] = src[:, col].sum() for a dense float64 [rows, stride] tensor"""
+    assert src.dim() == 2 and src.is_contiguous()
+    lib().call("sfb200_colsum_f64", _p(src, F64), src.shape[0], src.shape[1], col, _p(out, F64), _stream())

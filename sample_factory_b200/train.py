@@ -212,6 +212,19 @@ class Runner:
         self._join()
         self.env_steps = self.learner.env_steps
 
+    def _time_is_up(self, t_start: float) -> bool:
+        """train_for_seconds.  Data parallel: a per-rank wall clock would let one rank leave the loop while the others
+        enter the next collective, so the ranks decide together (max elapsed time, every 8th iteration)."""
+        elapsed = time.time() - t_start
+        if self.world_size == 1:
+            return elapsed >= self.cfg.train_for_seconds
+        self._stop_checks = getattr(self, "_stop_checks", 0) + 1
+        if self._stop_checks % 8 != 1:
+            return False
+        t = torch.tensor([elapsed], dtype=torch.float64, device=self.device)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        return float(t.item()) >= self.cfg.train_for_seconds
+
     def run(self) -> int:
         cfg = self.cfg
         assert self.initialized
@@ -219,7 +232,7 @@ class Runner:
         steps_at_report = self.env_steps
         status = StatusCode.SUCCESS
         try:
-            while self.env_steps < cfg.train_for_env_steps and time.time() - t_start < cfg.train_for_seconds:
+            while self.env_steps < cfg.train_for_env_steps and not self._time_is_up(t_start):
                 self.iteration()
                 now = time.time()
                 if now - last_report >= cfg.experiment_summaries_interval:
