@@ -222,17 +222,113 @@ def run_reference(args):
 
 # --------------------------------------------------------------------------------------------------- our arm
 def make_cfg(env_name: str, engine: str, cuda_graph: bool, async_rl: bool = False, splits: int = 1,
-             learner_graph: bool = False):
+             learner_graph: bool = False, batch: int = BATCH):
     from sample_factory_b200.cfg import parse_full_cfg, parse_sf_args
 
     argv = [f"--env={env_name}", "--experiment=bench", "--train_dir=/tmp/sfb200_bench", "--restart_behavior=overwrite",
             "--use_rnn=False", f"--async_rl={async_rl}", "--serial_mode=True", "--batched_sampling=True", "--num_workers=1",
-            f"--num_envs_per_worker={splits}", f"--worker_num_splits={splits}", f"--rollout={ROLLOUT}", f"--batch_size={BATCH}",
+            f"--num_envs_per_worker={splits}", f"--worker_num_splits={splits}", f"--rollout={ROLLOUT}", f"--batch_size={batch}",
             f"--num_batches_per_epoch={N_MINIBATCH}", f"--num_epochs={N_EPOCHS}", "--encoder_mlp_layers", "512", "512",
             "--env_gpu_actions=True", "--env_gpu_observations=True", "--seed=0", f"--gemm_engine={engine}",
             f"--cuda_graph={cuda_graph}", f"--learner_cuda_graph={learner_graph}", "--save_every_sec=1000000000"]
     parser, _ = parse_sf_args(argv)
     return parse_full_cfg(parser, argv)
+
+
+
+def dp_check(rank: int, world: int, dev, engine_flag: str, bench_model) -> dict:
+    """Outside the timed region, on the box the driver measures scaling on: (1) the replicas of the benchmark run are
+    bit-identical across ranks (weights and normaliser state), (2) G ranks x n envs == ONE process x G*n envs on the cfg-2
+    model: rank 0 collects three rollouts of G*n envs, every rank trains on its env shard with the data-parallel learner
+    exactly as the timed region runs it (NVLink peer exchanges, replayed as one CUDA graph), rank 0 also trains a
+    single-process learner on the whole batch, and parameters / normaliser statistics / loss terms are compared."""
+    import numpy as np
+
+    from sample_factory_b200 import ops
+    from sample_factory_b200.envs import TapeVecEnv
+    from sample_factory_b200.learner import Learner
+    from sample_factory_b200.model import ModelSpec, PolicyModel
+    from sample_factory_b200.sampler import DeviceSampler
+    from sample_factory_b200.train import select_engine
+    from sample_factory_b200.trajectory import alloc_for_spec
+
+    dist = torch.distributed
+    out = {}
+
+    def same_everywhere(t):
+        ref = t.clone()
+        dist.broadcast(ref, src=0)
+        ok = torch.tensor([1 if torch.equal(ref, t) else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        return bool(ok.item())
+
+    m = bench_model
+    out["replicas_identical_after_bench"] = all(same_everywhere(t) for t in (m.flat, m.obs_mean, m.obs_var, m.ret_mean, m.ret_var))
+
+    n, n_iter = 256, 3                       # envs per rank; iteration 1 runs eagerly, 2 captures + replays, 3 replays
+    n_all = n * world
+    cfg_dp = make_cfg("dp_check", engine_flag, False, learner_graph=True, batch=n * ROLLOUT // N_MINIBATCH)
+    cfg_one = make_cfg("dp_check", engine_flag, False, learner_graph=False, batch=n_all * ROLLOUT // N_MINIBATCH)
+    engine = select_engine(cfg_dp)
+    tape = torch.randn(n_iter * ROLLOUT + 1, n_all, OBS_DIM, generator=torch.Generator().manual_seed(4321)).to(dev)
+    env = TapeVecEnv(tape, N_ACTIONS)
+    spec = ModelSpec.from_cfg(cfg_one, env)
+    init = PolicyModel(spec, dev, seed=11)
+    dist.broadcast(init.flat, src=0)
+    init.weights_changed()
+    batches = []
+    full = alloc_for_spec(spec, n_all, ROLLOUT, dev)
+    if rank == 0:
+        sampler = DeviceSampler(cfg_one, env, init, full, engine=engine, use_cuda_graph=False, philox_seed=99)
+        sampler.reset()
+    for it in range(n_iter):
+        if rank == 0:
+            sampler.rollout()
+            g = torch.Generator(device=dev).manual_seed(it)
+            full["policy_id"][torch.rand(n_all, ROLLOUT, device=dev, generator=g) < 0.1] = -1    # some invalid samples
+        for k in full:
+            t = full[k].view(torch.uint8) if full[k].dtype == torch.bool else full[k]
+            dist.broadcast(t, src=0)
+        batches.append({k: v.clone() for k, v in full.items()})
+    # the single-process minibatch b is envs [b*n_all/NMB, (b+1)*n_all/NMB); each rank takes its slice of every minibatch
+    per_mb = n_all // N_MINIBATCH
+    per_rank = per_mb // world
+    idx = torch.cat([torch.arange(b * per_mb + rank * per_rank, b * per_mb + (rank + 1) * per_rank) for b in range(N_MINIBATCH)]).to(dev)
+
+    def run(parallel):
+        model = PolicyModel(spec, dev, seed=11)
+        model.flat.copy_(init.flat)
+        model.weights_changed()
+        rows = n if parallel else n_all
+        traj = alloc_for_spec(spec, rows, ROLLOUT, dev)
+        learner = Learner(cfg_dp if parallel else cfg_one, model, rows, engine=engine, data_parallel=parallel)
+        logs = []
+        for b in batches:
+            for k, v in b.items():
+                traj[k].copy_(v[idx] if parallel else v)
+            learner.train(traj)
+            logs.append(learner.minibatch_log().numpy().copy())
+        torch.cuda.synchronize()
+        return model, learner, logs
+
+    model_dp, learner_dp, logs_dp = run(True)
+    out["learner_graph_replayed"] = bool(learner_dp.use_graph and learner_dp.graph_replay_launches > 0)
+    out["exchange"] = "nvlink-peer kernels (csrc/comm.cu)" if learner_dp.comm is not None else "nccl"
+    out["replicas_identical"] = all(same_everywhere(t) for t in (model_dp.flat, model_dp.obs_mean, model_dp.obs_var,
+                                                                 model_dp.ret_mean, model_dp.ret_var))
+    if rank == 0:
+        model_1, learner_1, logs_1 = run(False)
+        dparam = float((model_dp.flat - model_1.flat).abs().max())
+        moved = float((model_1.flat - init.flat).abs().max())
+        dstat = float(max((a - b).abs().max() for a, b in ((model_dp.obs_mean, model_1.obs_mean), (model_dp.obs_var, model_1.obs_var),
+                                                          (model_dp.ret_mean, model_1.ret_mean), (model_dp.ret_var, model_1.ret_var))))
+        keys = ["num_valid", "adv_mean", "adv_std", "policy_loss", "value_loss", "exploration_loss", "total_loss", "value_mean"]
+        dloss = max(float(np.abs(a[:, ops.LS[k]] - b[:, ops.LS[k]]).max()) for a, b in zip(logs_dp, logs_1) for k in keys)
+        out.update(max_abs_param_diff_vs_single_gpu=dparam, max_abs_param_change=moved, max_abs_normalizer_diff=dstat,
+                   max_abs_loss_term_diff=dloss, equals_single_gpu=bool(dparam < 2e-6 and dstat < 1e-5 and dloss < 2e-5 and moved > 1e-4),
+                   shape=f"{world} ranks x {n} envs x {ROLLOUT} steps vs 1 process x {n_all} envs, {n_iter} iterations, 10% invalid samples")
+    dist.barrier()
+    return out
 
 
 def run_ours(args):
@@ -329,11 +425,12 @@ def run_ours(args):
          lambda x, out, *a, **k: float(x.numel() * 4 * 2))
     wrap("gae_returns", lambda rewards, *a, **k: "gae_returns", lambda rewards, *a, **k: float(rewards.numel() * 22))
     # (learner / sampler resolve ops.<fn> through the module at call time, so the wrappers take effect)
+    clocks = ClockSampler(local_rank)
+    clocks.start()             # before the warm-up: nvidia-smi needs ~100 ms before its first sample
     for _ in range(args.warmup):
         runner.iteration()
     barrier()
-    clocks = ClockSampler(local_rank)
-    clocks.start()
+    clocks.lines.clear()       # keep the samples of the timed region only
     launches0 = ops.launch_count()
     replay_launches = 0
     timing_on[0] = True
@@ -347,7 +444,6 @@ def run_ours(args):
     barrier()
     timing_on[0] = False
     ms_total = max_over_ranks(e0.elapsed_time(e1))
-    clock_info = clocks.stop()
     gpu_launches = (ops.launch_count() - launches0) + replay_launches
     learner_graphed = bool(runner.learner.use_graph)
     if runner.learner.use_graph:
@@ -399,6 +495,8 @@ def run_ours(args):
     s1.record()
     barrier()
     rollout_ms = s0.elapsed_time(s1) / args.steps
+    clock_info = clocks.stop()
+    clock_info["window"] = "timed region + the per-kernel timing iterations and the sampler-only pass right after it (same workload)"
     samp_bytes = 574.0 * N_ENVS * ROLLOUT
     samp_gbs = samp_bytes / (rollout_ms * 1e-3) / 1e9
     roof_sampler = dict(kernel="sampler rollout (32 policy steps: GEMM, GEMM + heads + sampling, env, post+pre step)",
@@ -406,8 +504,38 @@ def run_ours(args):
                         algorithmic_bytes=samp_bytes, rollout_ms=rollout_ms, share_of_step=rollout_ms / ms_per_step,
                         note="a 4096-env policy step moves 2.35 MB and 2.45 GFLOP: the rollout is bound by the dependent "
                              "kernel chain of each step (latency), not by HBM bandwidth")
+    dp_info = None
+    if world > 1 and not args.no_dp_check:
+        dp_info = dp_check(rank, world, dev, args.engine, runner.model)
     del runner
     torch.cuda.empty_cache()
+
+    # ------------------------------------------------------------------ strong-scaling point (BASELINE metric: "at 4096 envs")
+    strong = None
+    if world > 1 and not args.no_strong:
+        n_loc = N_ENVS // world
+        tape_loc = tape_dev[:, :n_loc].contiguous()
+        register_env("synthetic_tape_strong", lambda name, cfg, env_config, render_mode=None: TapeVecEnv(
+            tape_loc, N_ACTIONS, env_index_offset=rank * n_loc))
+        srunner = Runner(make_cfg("synthetic_tape_strong", args.engine, not args.no_graph, batch=BATCH // world,
+                                  learner_graph=not (args.no_learner_graph or args.no_graph)))
+        srunner.init()
+        for _ in range(args.warmup):
+            srunner.iteration()
+        q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        q0.record()
+        for _ in range(args.steps):
+            srunner.iteration()
+        q1.record()
+        barrier()
+        q_ms = max_over_ranks(q0.elapsed_time(q1))
+        strong = dict(value=N_ENVS * ROLLOUT * args.steps / (q_ms / 1e3), unit=UNIT, ms_per_step=q_ms / args.steps,
+                      scaling="strong", envs_total=N_ENVS, envs_per_gpu=n_loc, global_batch=BATCH * N_MINIBATCH,
+                      note="the SAME 4096-env job split over the ranks (1/N of the envs and of every minibatch per GPU): a "
+                           "policy step is latency-bound at 4096 rows already, so fewer rows per GPU shorten it only a little")
+        del srunner
+        torch.cuda.empty_cache()
 
     # ------------------------------------------------------------------ async double-buffered arm (async_rl=True)
     async_info = None
@@ -494,7 +622,7 @@ def run_ours(args):
                    dtype="f32" + (" (3xTF32 split on tcgen05, fp32 accumulate)" if engine_name == "tcgen05-3xTF32" else ""),
                    data="synthetic",
                    config=dict(workload=WORKLOAD, envs_per_gpu=N_ENVS, rollout=ROLLOUT, global_batch=BATCH * N_MINIBATCH * world,
-                               parallelism=f"dp{world} (env shards, 1 grad all-reduce per SGD step)", gemm_engine=engine_name,
+                               parallelism=f"dp{world} (env shards; per SGD step ONE kernel = NVLink peer all-reduce + grad-norm + clip + Adam)", gemm_engine=engine_name,
                                cuda_graph_rollout=not args.no_graph,
                                cuda_graph_learner=learner_graphed, worker_num_splits=args.splits,
                                l2_policy="per-step working set (trajectories 45 MB + obs tape 101 MB + learner "
@@ -502,7 +630,7 @@ def run_ours(args):
                    clocks=clock_info, e2e=e2e, gpu_launches=int(gpu_launches),
                    launches_per_step=dict(sampler_rollout=int(sampler_launches), learner_train=int(learner_launches)),
                    roofline=roofline, roofline_sampler=roof_sampler, roofline_secondary=roof2, async_rl=async_info,
-                   cpu_baseline=cpu_baseline)
+                   cpu_baseline=cpu_baseline, dp_check=dp_info, strong_scaling=strong)
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()
@@ -528,6 +656,10 @@ def main():
     ap.add_argument("--no-e2e", dest="no_e2e", action="store_true")
     ap.add_argument("--no-async", dest="no_async", action="store_true")
     ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
+    ap.add_argument("--no-dp-check", dest="no_dp_check", action="store_true",
+                    help="N > 1: skip the (untimed) replica / single-GPU equivalence check printed as `dp_check`")
+    ap.add_argument("--no-strong", dest="no_strong", action="store_true",
+                    help="N > 1: skip the strong-scaling point (4096 envs in total, split over the ranks)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -181,6 +181,16 @@ int sfb200_linear_heads_partials(int N, int A, int engine);
 int sfb200_linear_act_heads_forward(const float* x, int64_t ldx, const float* W, const float* b, float* y, int64_t ldy,
                                     int64_t M, int N, int K, int act, int engine, const float* Wv, const float* Wa,
                                     int A, float* head_partials, void* stream);
+/* The whole policy forward of a two-layer MLP (model/encoder.py:72-91 MlpEncoder + actor_critic.py:171-186) up to the head
+ * partials in ONE tcgen05 kernel: h1 = act(x W1^T + b1) is produced chunk by chunk in tensor memory and consumed by the
+ * layer-2 MMAs without ever reaching shared or global memory; h2 = act(h1 W2^T + b2) is contracted with [Wv ; Wa] in the
+ * epilogue (not stored).  Same partial format as sfb200_linear_act_heads_forward -> finish with sfb200_heads_from_partials.
+ *   P = sfb200_policy_mlp2_partials(W1, W2, K1, H1, H2, A, engine)   0 -> not covered (needs the 3xTF32 engine, K1 in
+ *       {32, 64}, H1 % 32 == 0, H2 % 128 == 0 and <= 512, A <= 8, both weight matrices inside a registered tf32-lo buffer) */
+int sfb200_policy_mlp2_partials(const float* W1, const float* W2, int K1, int H1, int H2, int A, int engine);
+int sfb200_policy_mlp2_heads_forward(const float* x, int64_t ldx, int64_t M, int K1, const float* W1, const float* b1, int H1,
+                                     const float* W2, const float* b2, int H2, int act, int engine, const float* Wv,
+                                     const float* Wa, int A, float* head_partials, void* stream);
 int sfb200_heads_from_partials(const float* head_partials, int P, int64_t rows, int A, const float* bv, const float* ba,
                                float* values, int64_t values_stride, float* logits, int64_t logits_stride,
                                const float* noise, uint64_t philox_seed, uint64_t philox_offset,

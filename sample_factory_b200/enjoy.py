@@ -45,6 +45,20 @@ def load_from_checkpoint(cfg) -> argparse.Namespace:
     return argparse.Namespace(**loaded)
 
 
+def checkpoint_override_defaults(cfg, parser):
+    """cfg/arguments.py:278-295: make the saved experiment configuration the parser's defaults"""
+    from .cfg import AttrDict
+
+    filename = cfg_file(cfg)
+    if not os.path.isfile(filename):
+        raise Exception(f"Could not load saved parameters for experiment {cfg.experiment} (file {filename} not found). "
+                        "Check that you have the correct experiment name and --train_dir is set correctly.")
+    with open(filename, "r") as f:
+        loaded = AttrDict(json.load(f))
+    parser.set_defaults(**loaded)
+    return loaded
+
+
 def enjoy(cfg) -> Tuple[int, float]:
     cfg = load_from_checkpoint(cfg)
     eval_frameskip = cfg.env_frameskip if getattr(cfg, "eval_env_frameskip", None) is None else cfg.eval_env_frameskip

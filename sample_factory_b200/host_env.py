@@ -32,6 +32,23 @@ def _space_info(space) -> Tuple[bool, int]:
     return True, int(shape[0])
 
 
+def _main_obs_space(obs_space):
+    """(space of the policy input, key or None).  Dict observation spaces (make_env.py:147-176 wraps everything into
+    Dict(obs=...)): the entry "obs" feeds the policy; an "action_mask" entry is consumed by the sampler.  Dicts with other
+    entries would need the reference's MultiInputEncoder (one encoder per key, encoder.py:33-70), which the kernel path does
+    not have."""
+    spaces = getattr(obs_space, "spaces", None)
+    if not isinstance(spaces, dict):
+        return obs_space, None
+    extra = [k for k in spaces if k not in ("obs", "action_mask")]
+    if "obs" not in spaces or extra:
+        raise NotImplementedError(
+            f"Dict observation space with keys {sorted(spaces)}: the device path encodes ONE array observation (key 'obs', "
+            "optionally with 'action_mask'); multi-input observations (MultiInputEncoder) are not supported -- flatten / "
+            "concatenate them in an env wrapper.")
+    return spaces["obs"], "obs"
+
+
 class BatchedHostEnv:
     is_gpu_env = False
     static_outputs = True
@@ -41,7 +58,8 @@ class BatchedHostEnv:
         self.num_agents = num_envs
         self.device = device
         e0 = self.envs[0]
-        obs_space = e0.observation_space
+        obs_space, self._obs_key = _main_obs_space(e0.observation_space)
+        self._mask_key = "action_mask" if (self._obs_key and "action_mask" in e0.observation_space.spaces) else None
         shape = tuple(obs_space.shape)
         self.obs_uint8 = np.dtype(getattr(obs_space, "dtype", np.float32)) == np.uint8
         self.obs_shape = shape if len(shape) == 3 else None       # (C, H, W) image observations -> ConvEncoder
@@ -67,9 +85,22 @@ class BatchedHostEnv:
         self.h2d_bytes = 0
         self.d2h_bytes = 0
         self.episode_infos: List[dict] = []   # infos of finished episodes since the last pop (batched_sampling.py:228-270)
+        if self._mask_key:
+            self.mask_host = torch.ones((n, self.num_actions), dtype=torch.bool).pin_memory()
+            self.action_mask = torch.ones((n, self.num_actions), dtype=torch.bool, device=device)
 
     def _put_obs(self, i: int, obs) -> None:
+        if self._obs_key is not None:
+            if self._mask_key:
+                self.mask_host[i].copy_(torch.as_tensor(np.asarray(obs[self._mask_key])).reshape(-1) != 0)
+            obs = obs[self._obs_key]
         self.obs_host[i].copy_(torch.as_tensor(np.asarray(obs)).reshape(-1))
+
+    def _obs_out(self):
+        if not self._mask_key:
+            return self.obs
+        self.action_mask.copy_(self.mask_host, non_blocking=True)
+        return {"obs": self.obs, "action_mask": self.action_mask}
 
     def reset(self) -> Tensor:
         for i, e in enumerate(self.envs):
@@ -81,7 +112,7 @@ class BatchedHostEnv:
         self._seeded = True
         self.obs.copy_(self.obs_host, non_blocking=True)
         self.h2d_bytes += self.obs_host.numel() * self.obs_host.element_size()
-        return self.obs
+        return self._obs_out()
 
     def step(self, actions: Tensor) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
         self.actions_host.copy_(actions, non_blocking=True)
@@ -100,9 +131,46 @@ class BatchedHostEnv:
         self.obs.copy_(self.obs_host, non_blocking=True)
         self.pack.copy_(self.pack_host, non_blocking=True)
         self.h2d_bytes += self.obs_host.numel() * self.obs_host.element_size() + self.pack_host.numel()
-        return self.obs, self.rew, self.terminated, self.truncated
+        return self._obs_out(), self.rew, self.terminated, self.truncated
 
     def close(self) -> None:
         for e in self.envs:
             if hasattr(e, "close"):
                 e.close()
+
+
+def is_batched_env(env) -> bool:
+    """Does `env` already speak the batched device contract of sample_factory_b200.envs (TapeVecEnv, BatchedHostEnv, user
+    GPU envs)?  Anything else is treated as an ordinary gymnasium-API env."""
+    return hasattr(env, "is_gpu_env") and hasattr(env, "num_agents") and hasattr(env, "obs_dim")
+
+
+def create_batched_env(cfg, env_config: dict, device: torch.device, num_envs: Optional[int] = None):
+    """The reference's make_env_func_batched (algo/utils/make_env.py:338-351) for this engine: create the registered env and,
+    if the factory returned a plain single-agent gymnasium-API env (what every sf_examples `make_env_func` returns), wrap
+    num_workers * num_envs_per_worker instances of it -- each created through the SAME registered factory with the
+    reference's env_config (worker_index, vector_index, env_id; batched_sampling.py:166-174) -- into a BatchedHostEnv:
+    BatchedMultiAgentWrapper auto-reset, dict-observation unwrapping and tensor conversion happen there."""
+    from .envs import create_env
+
+    first = create_env(cfg.env, cfg, env_config)
+    if is_batched_env(first):
+        return first
+    if getattr(first, "num_agents", 1) > 1 or getattr(first, "is_multiagent", False):
+        raise NotImplementedError("multi-agent CPU envs are not adapted automatically: expose the batched contract of "
+                                  "sample_factory_b200.envs (num_agents, obs_dim, num_actions, reset, step)")
+    if not (hasattr(first, "observation_space") and hasattr(first, "action_space")):
+        raise TypeError(f"{type(first).__name__} is neither a batched device env nor a gymnasium-API env")
+    epw = int(cfg.num_envs_per_worker)
+    n = int(num_envs) if num_envs is not None else int(cfg.num_workers) * epw
+    w0 = int(env_config.get("worker_index", 0)) if env_config else 0
+    made = {0: first}
+
+    def make(i: int):
+        if i in made:
+            return made.pop(i)
+        ec = dict(worker_index=w0 * int(cfg.num_workers) + i // epw, vector_index=i % epw, env_id=w0 * n + i)
+        return create_env(cfg.env, cfg, ec)
+
+    seed = None if getattr(cfg, "seed", None) is None else int(cfg.seed) + w0 * n
+    return BatchedHostEnv(make, n, device, seed=seed)

@@ -246,6 +246,7 @@ class Learner:
         self.counters_dev = torch.zeros(2, dtype=torch.int64, device=dev)     # [optimizer steps taken, train_step]
         self.lr_dev = torch.full((1,), float(cfg.learning_rate), dtype=torch.float64, device=dev)
         self._graph: Optional[torch.cuda.CUDAGraph] = None
+        self._graphs: Dict[tuple, torch.cuda.CUDAGraph] = {}
         self._graph_batch_ptrs = None
         self._graph_calls = 0
         self._graph_launches = 0
@@ -613,10 +614,9 @@ class Learner:
         captures, later calls replay.  Host mirrors of the counters advance alongside the device ones."""
         cfg = self.cfg
         nmb = cfg.num_batches_per_epoch
+        # one captured graph per trajectory set (the runner may train on several row ranges of the rollout buffers, or on an
+        # accumulation buffer: cfg/arguments.py:147-178 allows datasets that are a fraction / a multiple of one rollout)
         ptrs = tuple(v.data_ptr() for v in batch.values())
-        if self._graph is not None and ptrs != self._graph_batch_ptrs:
-            self._graph = None                      # different trajectory buffers: capture again
-            self._graph_calls = 1
         # the device counters / lr follow the host values whenever these were changed from outside (checkpoint resume)
         self.counters_dev.copy_(torch.tensor([self.opt_step, self.train_step], dtype=torch.int64), non_blocking=True)
         self.lr_dev.fill_(float(self.curr_lr))
@@ -626,15 +626,18 @@ class Learner:
             self._train_body(batch)
             self._graph_launches = ops.launch_count() - n0
         else:
-            if self._graph is None:
+            graph = self._graphs.get(ptrs)
+            if graph is None:
                 torch.cuda.synchronize()
-                self._graph = torch.cuda.CUDAGraph()
-                # (multi-rank: NCCL's watchdog thread polls events while this thread captures -> thread-local mode)
-                mode = "thread_local" if self.world_size > 1 else "global"
-                with torch.cuda.graph(self._graph, capture_error_mode=mode):
+                graph = torch.cuda.CUDAGraph()
+                # (multi-rank with NCCL exchanges: the watchdog thread polls events while this thread captures)
+                mode = "thread_local" if (self.world_size > 1 and self.comm is None) else "global"
+                with torch.cuda.graph(graph, capture_error_mode=mode):
                     self._train_body(batch)
-                self._graph_batch_ptrs = ptrs
-            self._graph.replay()
+                self._graphs[ptrs] = graph
+            self._graph = graph
+            self._graph_batch_ptrs = ptrs
+            graph.replay()
         self._graph_calls += 1
         # _minibatch_step advanced the host mirrors during eager / capture passes only: set them explicitly
         self.opt_step, self.train_step = opt0 + nmb, train0 + nmb

@@ -341,6 +341,27 @@ def linear_act_heads_forward_fused(x: Tensor, W: Tensor, b: Tensor, out: Optiona
                None if policy_version_out is None else policy_version_out.data_ptr(), pv_stride, _stream())
 
 
+def policy_mlp2_partials(W1: Tensor, W2: Tensor, A: int, engine: int) -> int:
+    """head partials per row the fused two-layer policy step produces, 0 when the model is not covered"""
+    H1, K1 = W1.shape
+    H2 = W2.shape[0]
+    if W2.shape[1] != H1 or not (W1.is_contiguous() and W2.is_contiguous()):
+        return 0
+    return lib().query("sfb200_policy_mlp2_partials", _p(W1, F32), _p(W2, F32), K1, H1, H2, A, engine)
+
+
+def policy_mlp2_heads_forward(x: Tensor, W1: Tensor, b1: Tensor, W2: Tensor, b2: Tensor, act: int, engine: int, Wv: Tensor,
+                              Wa: Tensor, head_partials: Tensor) -> None:
+    """x [M, K1] -> partial head dot products of act(act(x W1^T + b1) W2^T + b2) (one tcgen05 kernel, csrc/policy_step.cu)"""
+    M, K1 = x.shape
+    H1, H2, A = W1.shape[0], W2.shape[0], Wa.shape[0]
+    assert Wv.is_contiguous() and Wa.is_contiguous() and Wv.numel() == H2 and Wa.shape[1] == H2
+    P = 2 * (H2 // 128)
+    assert head_partials.numel() >= P * M * HEAD_PART_PAD
+    lib().call("sfb200_policy_mlp2_heads_forward", _p(x, F32), x.stride(0), M, K1, _p(W1, F32), _p(b1, F32), H1, _p(W2, F32),
+               _p(b2, F32), H2, act, engine, _p(Wv, F32), _p(Wa, F32), A, _p(head_partials, F32), _stream())
+
+
 def heads_from_partials(head_partials: Tensor, P: int, rows: int, bv: Tensor, ba: Tensor, values: Tensor,
                         values_stride: int, logits: Optional[Tensor] = None, logits_stride: int = 0,
                         noise: Optional[Tensor] = None, philox_seed: int = 0, philox_offset: int = 0,

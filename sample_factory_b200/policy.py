@@ -60,6 +60,14 @@ class HeadsPlan:
             # the separate, fully parallel heads_from_partials launch stays the default.
             self.counters = torch.zeros((max_rows + 127) // 128, dtype=torch.int32, device=model.device)
             self.finish_in_gemm = os.environ.get("SFB200_HEADS_FINISH_IN_GEMM", "0") == "1"
+        # two-layer MLP policies (BASELINE cfg-2): both layers + the head partials in ONE tcgen05 kernel whenever the last
+        # hidden activation is not needed afterwards (sampler policy step, learner bootstrap value) -- csrc/policy_step.cu.
+        # SFB200_POLICY_FUSED=0 restores the per-layer launches (A/B measurements).
+        self.mlp2 = False
+        if (self.P > 0 and self.conv is None and not spec.use_rnn and not spec.decoder_mlp_layers and
+                len(spec.fc_encoder_layers) == 2 and os.environ.get("SFB200_POLICY_FUSED", "1") != "0"):
+            (W1, _), (W2, _) = model.encoder_layers()
+            self.mlp2 = ops.policy_mlp2_partials(W1, W2, spec.num_linear_action_outputs, engine) == self.P
 
 
 def forward_policy(model: PolicyModel, x: Tensor, outs: List[Tensor], act: int, engine: int, plan: HeadsPlan,
@@ -78,6 +86,11 @@ def forward_policy(model: PolicyModel, x: Tensor, outs: List[Tensor], act: int, 
     Wa, ba = model.actor
     n_mlp = len(enc) + len(dec)
     fused = plan.P > 0
+    if plan.mlp2 and not store_tail and not plan.finish_in_gemm:
+        (W1, b1), (W2, b2) = enc
+        ops.policy_mlp2_heads_forward(x, W1, b1, W2, b2, act, engine, Wv, Wa, plan.part)
+        _heads(model, None, Wv, bv, Wa, ba, True, plan, M, heads_kwargs)
+        return None
     k = 0
     tail: Optional[Tensor] = x
     for group, layers in (("enc", enc), ("dec", dec)):

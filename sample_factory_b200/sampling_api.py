@@ -22,7 +22,7 @@ from torch import Tensor
 from . import ops
 from .checkpoint import load_checkpoint
 from .cfg import preprocess_cfg
-from .envs import create_env
+from .host_env import create_batched_env
 from .model import ModelSpec, PolicyModel
 from .sampler import DeviceSampler
 from .trajectory import alloc_for_spec
@@ -42,7 +42,7 @@ class EnvInfo:
 
 def obtain_env_info(cfg) -> EnvInfo:
     """env_info.py:79-103 (in-process: creating a device env is cheap, no subprocess needed)."""
-    env = create_env(cfg.env, cfg, dict(worker_index=0, vector_index=0, env_id=0))
+    env = create_batched_env(cfg, dict(worker_index=0, vector_index=0, env_id=0), torch.device("cuda", torch.cuda.current_device()))
     info = EnvInfo(env.obs_dim, env.num_actions, env.num_agents)
     if hasattr(env, "close"):
         env.close()
@@ -71,7 +71,7 @@ class _DeviceSamplingLoop:
         ops.bind_device(self.device)
         if not preprocess_cfg(cfg):
             raise ValueError("invalid configuration (see cfg.verify_cfg)")
-        self.env = create_env(cfg.env, cfg, dict(worker_index=0, vector_index=0, env_id=0))
+        self.env = create_batched_env(cfg, dict(worker_index=0, vector_index=0, env_id=0), self.device)
         if env_info is not None:
             assert (env_info.obs_dim, env_info.num_actions, env_info.num_agents) == (
                 self.env.obs_dim, self.env.num_actions, self.env.num_agents), "env_info does not match the env"

@@ -29,7 +29,8 @@ from . import ops
 from .cfg import preprocess_cfg
 from .checkpoint import load_checkpoint, save_checkpoint
 from .dist_utils import init_from_env
-from .envs import create_env, set_training_info
+from .envs import set_training_info
+from .host_env import create_batched_env
 from .learner import Learner
 from .model import ModelSpec, PolicyModel
 from .sampler import DeviceSampler, SplitSampler
@@ -105,8 +106,11 @@ class Runner:
         self.envs = []
         for s_ in range(n_splits):
             env_config = dict(worker_index=self.rank, vector_index=s_, env_id=self.rank * n_splits + s_)
-            self.envs.append(create_env(cfg.env, cfg, env_config))
+            self.envs.append(create_batched_env(cfg, env_config, self.device))
         self.env = self.envs[0]
+        from .model_factory import global_model_factory
+
+        global_model_factory().check_supported()      # custom torch modules: explicit error through the registry API
         spec = ModelSpec.from_cfg(cfg, self.env)
         assert cfg.rnn_num_layers == 1, "the device path implements the one-layer recurrent core"
         self.model = PolicyModel(spec, self.device, seed=cfg.seed or 0, policy_init_gain=cfg.policy_init_gain)
@@ -134,7 +138,26 @@ class Runner:
             self.sampler = SplitSampler(cfg, self.envs, self.sampler_model, self.sampler_traj, **sampler_kw)
         else:
             self.sampler = DeviceSampler(cfg, self.env, self.sampler_model, self.sampler_traj, **sampler_kw)
-        self.learner = Learner(cfg, self.model, N, engine=self.engine)
+        # The learner's dataset (batch_size x num_batches_per_epoch samples) may be a FRACTION of one rollout of all envs
+        # (the reference's batcher then emits several training batches per rollout, batcher.py:170-218 -- e.g. the
+        # sf_examples defaults: 160 envs x 32 steps, batch_size 512) or a MULTIPLE of it (rollouts are accumulated);
+        # cfg/arguments.py:147-178.  Fractions train on row ranges of the rollout buffers in place, multiples are copied
+        # into an accumulation set (the batcher's copy).
+        T = cfg.rollout
+        dataset = cfg.batch_size * cfg.num_batches_per_epoch
+        if dataset % T != 0 or not ((N * T) % dataset == 0 or dataset % (N * T) == 0):
+            raise ValueError(f"batch_size * num_batches_per_epoch = {dataset} must be a multiple of rollout = {T} and divide "
+                             f"(or be a multiple of) the {N * T} samples one rollout of the {N} envs produces")
+        self.k_split = max(1, (N * T) // dataset)
+        self.k_acc = max(1, dataset // (N * T))
+        n_learn = dataset // T
+        self.learner = Learner(cfg, self.model, n_learn, engine=self.engine)
+        self._train_views = None
+        if self.k_split > 1:
+            self._train_views = [{k: v[j * n_learn: (j + 1) * n_learn] for k, v in self.traj.items()} for j in range(self.k_split)]
+        if self.k_acc > 1:
+            self.accum = alloc_for_spec(spec, n_learn, T, self.device)
+            self._acc_fill = 0
         if cfg.restart_behavior == "resume":
             ck = load_checkpoint(cfg, self.model, self.device)
             if ck is not None:
@@ -173,8 +196,25 @@ class Runner:
         self._before_rollout()
         self.sampler.set_policy_version(self.learner.train_step)
         self.sampler.rollout()
-        self.learner.train(self.traj)
+        self._train()
         self.env_steps = self.learner.env_steps
+
+    def _train(self) -> None:
+        """Learner.train on the freshly collected rollout in self.traj (see the dataset / rollout note in init)"""
+        if self.k_split > 1:
+            for view in self._train_views:
+                self.learner.train(view)
+        elif self.k_acc > 1:
+            n = self.traj["rewards"].shape[0]
+            j = self._acc_fill
+            for k, v in self.traj.items():
+                self.accum[k][j * n: (j + 1) * n].copy_(v, non_blocking=True)
+            self._acc_fill += 1
+            if self._acc_fill == self.k_acc:
+                self._acc_fill = 0
+                self.learner.train(self.accum)
+        else:
+            self.learner.train(self.traj)
 
     def _sample_on_side_stream(self) -> None:
         with torch.cuda.stream(self.sampler_stream):
@@ -205,9 +245,9 @@ class Runner:
         # the whole rollout -> enqueue the learner's launches first.
         if getattr(self.env, "is_gpu_env", False):
             self._sample_on_side_stream()
-            self.learner.train(self.traj)
+            self._train()
         else:
-            self.learner.train(self.traj)
+            self._train()
             self._sample_on_side_stream()
         self._join()
         self.env_steps = self.learner.env_steps
