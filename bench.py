@@ -643,6 +643,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5],
+                    help="BASELINE.json config (1-based): 2 = the headline synthetic 4096-env MLP job (default); 3 / 4 / 5 = the "
+                         "mujoco-, atari- and isaacgym-shaped jobs (bench_configs.py), same JSON contract")
     ap.add_argument("--engine", default="auto", choices=["auto", "simt", "3xtf32", "tf32"])
     ap.add_argument("--splits", type=int, default=1,
                     help="worker_num_splits: env groups whose per-step kernel chains run concurrently on separate streams "
@@ -662,7 +665,14 @@ def main():
                     help="N > 1: skip the strong-scaling point (4096 envs in total, split over the ranks)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    if args.impl == "reference":
+    if args.config != 2:
+        import bench_configs
+
+        if args.impl == "reference":
+            bench_configs.run_config_reference(args)
+        else:
+            bench_configs.run_config(args, load_peaks, ClockSampler)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

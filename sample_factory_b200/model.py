@@ -212,7 +212,10 @@ def _align(n: int, a: int = 64) -> int:
 class PolicyModel:
     """Flat parameter storage + normalizer buffers on one device."""
 
-    def __init__(self, spec: ModelSpec, device: torch.device, seed: int = 0, policy_init_gain: float = 1.0):
+    def __init__(self, spec: ModelSpec, device: torch.device, seed: int = 0, policy_init_gain: float = 1.0,
+                 policy_initialization: str = "orthogonal"):
+        assert policy_initialization in ("orthogonal", "xavier_uniform", "torch_default"), policy_initialization
+        self.policy_initialization = policy_initialization
         self.spec = spec
         self.device = device
         shapes = spec.param_shapes()
@@ -283,7 +286,9 @@ class PolicyModel:
             pass
 
     def _init_weights(self, seed: int, gain: float) -> None:
-        """ActorCritic.initialize_weights (actor_critic.py:73-96): bias 0, orthogonal(gain) on Linear weights."""
+        """ActorCritic.initialize_weights (actor_critic.py:73-96): biases 0 in every mode; Linear / Conv2d weights orthogonal
+        (gain), xavier_uniform (gain), or left at the PyTorch default U(-1/sqrt(fan_in), 1/sqrt(fan_in)) (torch_default)."""
+        mode = self.policy_initialization
         g = torch.Generator(device="cpu").manual_seed(seed)
         for name in self.names:
             p = self.params[name]
@@ -297,7 +302,13 @@ class PolicyModel:
                 p.zero_()
             else:
                 w = torch.empty(p.shape, dtype=torch.float32)
-                torch.nn.init.orthogonal_(w, gain=gain, generator=g)
+                if mode == "orthogonal":
+                    torch.nn.init.orthogonal_(w, gain=gain, generator=g)
+                elif mode == "xavier_uniform":
+                    torch.nn.init.xavier_uniform_(w, gain=gain, generator=g)
+                else:   # nn.Linear / nn.Conv2d reset_parameters: kaiming_uniform_(a=sqrt(5)) == U(-1/sqrt(fan_in), 1/sqrt(fan_in))
+                    bound = 1.0 / math.sqrt(math.prod(p.shape[1:]))
+                    w.uniform_(-bound, bound, generator=g)
                 p.copy_(w)
 
     # ---- inference-side weight snapshot (async_rl: the reference's inference workers hold their own copy of the

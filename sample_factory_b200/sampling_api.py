@@ -77,7 +77,8 @@ class _DeviceSamplingLoop:
                 self.env.obs_dim, self.env.num_actions, self.env.num_agents), "env_info does not match the env"
         spec = _model_spec(cfg, self.env)
         self.model = model if model is not None else PolicyModel(spec, self.device, seed=cfg.seed or 0,
-                                                                 policy_init_gain=cfg.policy_init_gain)
+                                                                 policy_init_gain=cfg.policy_init_gain,
+                                 policy_initialization=getattr(cfg, "policy_initialization", "orthogonal"))
         engine = ops.ENGINES[getattr(cfg, "gemm_engine", "auto")] if getattr(cfg, "gemm_engine", "auto") != "auto" else (
             ops.GEMM_TC_3XTF32 if ops.tc_available() else ops.GEMM_SIMT)
         self.traj = alloc_for_spec(spec, self.env.num_agents, cfg.rollout, self.device)

@@ -27,7 +27,7 @@ import torch
 
 from . import ops
 from .cfg import preprocess_cfg
-from .checkpoint import load_checkpoint, save_checkpoint
+from .checkpoint import load_checkpoint, save_best, save_checkpoint
 from .dist_utils import init_from_env
 from .envs import set_training_info
 from .host_env import create_batched_env
@@ -113,7 +113,8 @@ class Runner:
         global_model_factory().check_supported()      # custom torch modules: explicit error through the registry API
         spec = ModelSpec.from_cfg(cfg, self.env)
         assert cfg.rnn_num_layers == 1, "the device path implements the one-layer recurrent core"
-        self.model = PolicyModel(spec, self.device, seed=cfg.seed or 0, policy_init_gain=cfg.policy_init_gain)
+        self.model = PolicyModel(spec, self.device, seed=cfg.seed or 0, policy_init_gain=cfg.policy_init_gain,
+                                 policy_initialization=getattr(cfg, "policy_initialization", "orthogonal"))
         N = sum(e.num_agents for e in self.envs)
         self.engine = select_engine(cfg)
         self.traj = alloc_for_spec(spec, N, cfg.rollout, self.device)
@@ -268,7 +269,7 @@ class Runner:
     def run(self) -> int:
         cfg = self.cfg
         assert self.initialized
-        t_start = last_report = last_save = time.time()
+        t_start = last_report = last_save = last_best = time.time()
         steps_at_report = self.env_steps
         status = StatusCode.SUCCESS
         try:
@@ -296,6 +297,13 @@ class Runner:
                 if now - last_save >= cfg.save_every_sec and self.rank == 0:
                     save_checkpoint(cfg, self.model, self.learner)
                     last_save = now
+                if now - last_best >= cfg.save_best_every_sec and self.rank == 0:          # runner.py:459-476
+                    last_best = now
+                    hist = self.policy_avg_stats.get(cfg.save_best_metric)
+                    if hist and len(hist[0]) > 0 and self.env_steps >= cfg.save_best_after:
+                        vals = [v for v in hist[0] if v == v]
+                        if vals:
+                            save_best(cfg, self.model, self.learner, cfg.save_best_metric, float(sum(vals) / len(vals)))
         except KeyboardInterrupt:
             status = StatusCode.INTERRUPTED
         torch.cuda.synchronize()
