@@ -181,6 +181,27 @@ int sfb200_linear_heads_partials(int N, int A, int engine);
 int sfb200_linear_act_heads_forward(const float* x, int64_t ldx, const float* W, const float* b, float* y, int64_t ldy,
                                     int64_t M, int N, int K, int act, int engine, const float* Wv, const float* Wa,
                                     int A, float* head_partials, void* stream);
+/* Everything of a sampler step that follows the policy GEMMs, for the synthetic tape env of BASELINE config 2
+ * (sample_factory_b200.envs.TapeVecEnv), in ONE launch: sfb200_heads_from_partials (finish heads, sample, log-prob, version
+ * stamp into traj[:, t]) -> the env step (sfb200_tape_env_step rules; the env's own obs / rew / terminated / truncated
+ * buffers are kept current) -> sfb200_sampler_post_step for step t -> generate_policy_request + normalisation for step t+1
+ * (sfb200_sampler_pre_step; x_norm == NULL at the last step of a rollout).  One warp walks one env through all stages.
+ * sampler_step is the Philox offset counter (read, then advanced by one), env_step_counter the env's {step, ticket}. */
+int sfb200_sampler_tail_tape_step(const float* head_partials, int P, int64_t n_envs, int A, const float* bv, const float* ba,
+                                  float* values_t, int64_t values_stride, float* logits_t, int64_t logits_stride,
+                                  const float* noise, uint64_t philox_seed, int64_t* sampler_step, float* actions_t,
+                                  int64_t actions_stride, int32_t* env_actions, float* log_prob_t, int64_t log_prob_stride,
+                                  const float* policy_version_scalar, float* policy_version_t, int64_t pv_stride,
+                                  const float* tape, int64_t tape_len, int dim, int64_t env_index_offset, int term_period,
+                                  int trunc_period, int64_t* env_step_counter, float* env_obs, float* env_rew,
+                                  uint8_t* env_terminated, uint8_t* env_truncated, float reward_scale, float reward_clip,
+                                  int32_t policy_id, float* traj_rewards_t, uint8_t* traj_dones_t, uint8_t* traj_time_outs_t,
+                                  int32_t* traj_policy_id_t, int64_t traj_stride, float* ep_return, int32_t* ep_len,
+                                  float* ep_min_raw, float* ep_max_raw, int32_t len_increment, double* stats,
+                                  float* fin_return_t, int32_t* fin_len_t, float* traj_obs_next, int64_t traj_obs_stride,
+                                  const float* rnn, int rnn_dim, float* traj_rnn_next, int64_t traj_rnn_stride, float* x_norm,
+                                  const double* mean, const double* var, float sub_mean, float inv_scale, float eps,
+                                  float clip, void* stream);
 /* The whole policy forward of a two-layer MLP (model/encoder.py:72-91 MlpEncoder + actor_critic.py:171-186) up to the head
  * partials in ONE tcgen05 kernel: h1 = act(x W1^T + b1) is produced chunk by chunk in tensor memory and consumed by the
  * layer-2 MMAs without ever reaching shared or global memory; h2 = act(h1 W2^T + b2) is contracted with [Wv ; Wa] in the

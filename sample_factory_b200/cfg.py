@@ -131,11 +131,16 @@ def parse_sf_args(argv: Optional[List[str]] = None, evaluation: bool = False) ->
         argv = sys.argv[1:]
     parser = _build_parser()
     if evaluation:
-        # cfg/cfg.py add_eval_args subset that example scripts reference
-        for name, typ, default in [("fps", int, 0), ("eval_env_frameskip", int, None), ("no_render", str2bool, False),
-                                   ("save_video", str2bool, False), ("max_num_episodes", int, int(1e9)),
-                                   ("max_num_frames", int, int(1e9)), ("eval_deterministic", str2bool, False),
-                                   ("sample_env_episodes", int, 256), ("csv_folder_name", str, None)]:
+        # cfg/cfg.py:640-720 add_eval_args: the full evaluation surface (rendering / video / hub flags are accepted; they
+        # configure host-side tooling outside the hot path)
+        for name in ("no_render", "save_video", "push_to_hub"):
+            parser.add_argument(f"--{name}", action="store_true")
+        for name, typ, default in [("fps", int, 0), ("eval_env_frameskip", int, None), ("video_frames", int, int(1e9)),
+                                   ("video_name", str, None), ("max_num_frames", int, int(1e9)),
+                                   ("max_num_episodes", int, int(1e9)), ("hf_repository", str, None), ("policy_index", int, 0),
+                                   ("eval_deterministic", str2bool, False), ("train_script", str, None),
+                                   ("enjoy_script", str, None), ("sample_env_episodes", int, 256),
+                                   ("csv_folder_name", str, None)]:
             parser.add_argument(f"--{name}", type=typ, default=default)
     partial_cfg, _ = parser.parse_known_args(argv)
     return parser, partial_cfg

@@ -169,20 +169,20 @@ struct EpiCtx {
 // lane quadrant, warps 10..13 take [BN/2, BN).  One warp per scheduler was latency-bound (ncu: the epilogue warps were
 // ~100% busy at IPC 0.12 and paced the whole kernel for short-K tiles).  The bias for ALL N columns is staged once per
 // kernel in shared memory (persistent CTA).
-template <int BN>
+template <int BN, int EPI_WARP0 = 6>
 __device__ __forceinline__ EpiCtx make_epi_ctx(int warp, int lane, const float* C, int64_t ldc, int N, int splits,
                                                const TcEpilogue& epi, float* bias_s, int bias_floats) {
     EpiCtx ec;
     ec.lane_base = (warp & 3) * 32;
     ec.lane = lane;
-    ec.col0 = ((warp - 6) >> 2) * (BN / 2);
+    ec.col0 = ((warp - EPI_WARP0) >> 2) * (BN / 2);
     ec.vec_ok = (ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15u) == 0);
     ec.aux_vec = epi.aux && (epi.ld_aux % 4 == 0) && ((reinterpret_cast<uintptr_t>(epi.aux) & 15u) == 0);
     ec.st_v8 = (ldc % 8 == 0) && ((reinterpret_cast<uintptr_t>(C) & 31u) == 0);
     ec.aux_v8 = epi.aux && (epi.ld_aux % 8 == 0) && ((reinterpret_cast<uintptr_t>(epi.aux) & 31u) == 0);
     const bool bias_smem = epi.bias != nullptr && N <= bias_floats;
     if (bias_smem) {
-        for (int i = threadIdx.x - 192; i < N; i += 256) bias_s[i] = epi.bias[i];
+        for (int i = threadIdx.x - EPI_WARP0 * 32; i < N; i += 256) bias_s[i] = epi.bias[i];
         asm volatile("bar.sync 1, 256;" ::: "memory");
     }
     ec.bias_base = bias_smem ? bias_s : epi.bias;
@@ -555,6 +555,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 // TMEM budget (512 columns): accumulator [0,256) (single slot), A stages [256, 256 + 64*STAGES).
 constexpr int TA_STAGES = 4;
 constexpr uint32_t TA_ACOL0 = 256;
+// Operand warps of the TMEM-A kernel.  With 4 (one per TMEM lane quadrant, each thread converting a whole 32-column row of
+// the k-block) the conversion paced the main loop: one warp per SM sub-partition cannot overlap its own shared-memory /
+// tcgen05.st / mbarrier latencies.  8 warps = two per quadrant, each thread converts 16 columns.
+// Used where the conversion is the bottleneck: the dW GEMM (both operands are MN-major activations: 32-bit shared-memory
+// reads for A and an in-kernel split of B).  576 threads leave 96 registers per thread, which makes the epilogue spill;
+// dW tiles run ~100 k-blocks per epilogue, the forward / dX tiles 16, so those keep 4 operand warps and 128 registers.
+constexpr int ta_threads(int opw) { return 32 * (2 + opw + 8); }   // 448 (4 operand warps) or 576 (8)
 
 template <int STAGES>
 struct TaSmem {
@@ -573,12 +580,13 @@ struct TaSmem {
 // no shared-memory work for B at all.
 // (Tried and dropped: two extra warps taking over the B-tile split of the dW-type GEMM so that A and B work of a stage
 // proceed in parallel -- 230.6 vs 232.4 us for dW + dX at M=32768, N=K=512, i.e. the B split is not what paces that GEMM.)
-template <bool A_MN, bool B_MN, bool SPLIT3, bool HEADS, bool BLO>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+template <bool A_MN, bool B_MN, bool SPLIT3, bool HEADS, bool BLO, int TA_OPW>
+__global__ void __launch_bounds__(ta_threads(TA_OPW), 1)
 gemm_tc_ta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                   const __grid_constant__ CUtensorMap tmap_b_lo, float* __restrict__ C, int64_t ldc, int64_t M, int N,
                   int K, int k_chunk, int splits, TcEpilogue epi, int raw_hi) {
     constexpr int BN = 128, STAGES = TA_STAGES;
+    constexpr int TA_EPI_WARP0 = 2 + TA_OPW;                // first of the 8 epilogue warps
     using S = TaSmem<STAGES>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -602,7 +610,7 @@ gemm_tc_ta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         if (BLO) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b_lo) : "memory");
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&conv[s], 128);
+            mbar_init(&conv[s], 32 * TA_OPW);
             mbar_init(&empty[s], 1);
         }
         mbar_init(acc_full, 1);
@@ -680,11 +688,14 @@ gemm_tc_ta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 __syncwarp();
             }
         }
-    } else if (warp < 6) {
+    } else if (warp < TA_EPI_WARP0) {
         // ===================================================== operand warps: A smem -> registers -> TMEM, B split in smem
-        const int ct = threadIdx.x - 64;                       // 0..127
+        constexpr int NCT = 32 * TA_OPW;                       // operand threads
+        constexpr int CPT = 128 * TBK / NCT;                   // k-columns of its row a thread converts per k-block: 32 or 16
+        const int ct = threadIdx.x - 64;                       // 0..NCT-1
         const int row = (warp & 3) * 32 + lane;                // tile row == TMEM lane this thread may access
-        const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + TA_ACOL0;
+        const int c0 = ((warp - 2) >> 2) * CPT;                // first k-column of this thread
+        const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + TA_ACOL0 + (uint32_t)c0;
         const int sw = row & 7;                                // 128B swizzle: 16 B chunk index XOR (row % 8)
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -696,15 +707,16 @@ gemm_tc_ta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 mbar_wait(&full[s], ph);
                 tc_fence_after();
                 uint8_t* sb = smem + s * S::STAGE_BYTES;
-                uint32_t hi[32], lo[32];
+                uint32_t hi[CPT], lo[CPT];
                 if (A_MN) {
                     // MN-major tile: box (row/32) of [32 k][32 rows], k-rows 128 B apart, 32 B chunks XOR (k % 4)
                     // (SWIZZLE_128B_ATOM_32B).  A warp reads one whole 128 B k-row per instruction: conflict-free.
                     const uint8_t* abox = sb + 2 * S::B_BYTES + (row >> 5) * 4096 + (lane & 7) * 4;
                     const int chunk = lane >> 3;
 #pragma unroll
-                    for (int kk = 0; kk < 32; ++kk) {
-                        const uint32_t v = *reinterpret_cast<const uint32_t*>(abox + kk * 128 + ((chunk ^ (kk & 3)) << 5));
+                    for (int kk = 0; kk < CPT; ++kk) {
+                        const int kabs = c0 + kk;
+                        const uint32_t v = *reinterpret_cast<const uint32_t*>(abox + kabs * 128 + ((chunk ^ (kabs & 3)) << 5));
                         if (SPLIT3) {
                             const uint32_t h = v & 0xffffe000u;
                             hi[kk] = raw_hi ? v : h;
@@ -716,8 +728,8 @@ gemm_tc_ta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 } else {
                     const uint4* arow = reinterpret_cast<const uint4*>(sb + 2 * S::B_BYTES + row * 128);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const uint4 q = arow[j ^ sw];
+                    for (int j = 0; j < CPT / 4; ++j) {
+                        const uint4 q = arow[(c0 / 4 + j) ^ sw];
                         const uint32_t v[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
@@ -731,13 +743,13 @@ gemm_tc_ta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                         }
                     }
                 }
-                tmem_st_32x32b_x32(lane_addr + (uint32_t)s * 64u, hi);
-                if (SPLIT3) tmem_st_32x32b_x32(lane_addr + (uint32_t)s * 64u + 32u, lo);
+                tmem_st_cols<CPT>(lane_addr + (uint32_t)s * 64u, hi);
+                if (SPLIT3) tmem_st_cols<CPT>(lane_addr + (uint32_t)s * 64u + 32u, lo);
                 if (SPLIT3 && !BLO) {
                     uint4* h4 = reinterpret_cast<uint4*>(sb);
                     uint4* l4 = reinterpret_cast<uint4*>(sb + S::B_BYTES);
 #pragma unroll 4
-                    for (int i = ct; i < S::B_BYTES / 16; i += 128) {
+                    for (int i = ct; i < S::B_BYTES / 16; i += NCT) {
                         const uint4 v = h4[i];
                         uint4 h, l;
                         h.x = v.x & 0xffffe000u; h.y = v.y & 0xffffe000u; h.z = v.z & 0xffffe000u; h.w = v.w & 0xffffe000u;
@@ -760,13 +772,13 @@ gemm_tc_ta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         float* headw_s = bias_s + S::BIAS_FLOATS;
         if (HEADS) {
             // [kHeadAP][N]: row 0 = critic weights, rows 1..A = distribution_linear rows, the rest zero
-            for (int i = threadIdx.x - 192; i < kHeadAP * N; i += 256) {
+            for (int i = threadIdx.x - TA_EPI_WARP0 * 32; i < kHeadAP * N; i += 256) {
                 const int a = i / N, n = i - a * N;
                 headw_s[i] = (a == 0) ? epi.head_wv[n] : (a <= epi.head_A ? epi.head_wa[(int64_t)(a - 1) * N + n] : 0.f);
             }
             asm volatile("bar.sync 1, 256;" ::: "memory");
         }
-        const EpiCtx ec = make_epi_ctx<BN>(warp, lane, C, ldc, N, splits, epi, bias_s, S::BIAS_FLOATS);
+        const EpiCtx ec = make_epi_ctx<BN, TA_EPI_WARP0>(warp, lane, C, ldc, N, splits, epi, bias_s, S::BIAS_FLOATS);
         uint32_t tile_iter = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_iter) {
             const TileCoord tc = tile_coord(tile, tiles_n, tiles_per_z, BN, K, k_chunk);
@@ -795,17 +807,17 @@ gemm_tc_ta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                     const int mb = (int)(tc.m0 / TBM);
                     __threadfence();
                     asm volatile("bar.sync 1, 256;" ::: "memory");
-                    if (threadIdx.x == 192) *s_last = (atomicAdd(&epi.fin_counters[mb], 1) == tiles_n - 1) ? 1 : 0;
+                    if (threadIdx.x == TA_EPI_WARP0 * 32) *s_last = (atomicAdd(&epi.fin_counters[mb], 1) == tiles_n - 1) ? 1 : 0;
                     asm volatile("bar.sync 1, 256;" ::: "memory");
                     if (*s_last) {
                         __threadfence();
                         const float pv = epi.fin.pv_scalar ? *epi.fin.pv_scalar : 0.f;
                         const uint64_t offset = epi.fin.offset_host + (epi.fin.offset_dev ? (uint64_t)*epi.fin.offset_dev : 0ull);
-                        for (int r = warp - 6; r < TBM; r += 8) {
+                        for (int r = warp - TA_EPI_WARP0; r < TBM; r += 8) {
                             const int64_t row = tc.m0 + r;
                             if (row < M) heads_finish_row(epi.head_part, 2 * tiles_n, M, row, lane, epi.fin, pv, offset);
                         }
-                        if (threadIdx.x == 192) epi.fin_counters[mb] = 0;
+                        if (threadIdx.x == TA_EPI_WARP0 * 32) epi.fin_counters[mb] = 0;
                     }
                 }
             } else {
@@ -899,7 +911,8 @@ template <bool A_MN, bool B_MN, bool SPLIT3, bool HEADS = false, bool BLO = fals
 static int launch_tc_ta(const CUtensorMap& ta, const CUtensorMap& tb, float* C, int64_t ldc, int64_t M, int N, int K,
                         int k_chunk, int splits, const TcEpilogue& epi, cudaStream_t st, const CUtensorMap* tb_lo = nullptr) {
     using S = TaSmem<TA_STAGES>;
-    auto kern = gemm_tc_ta_kernel<A_MN, B_MN, SPLIT3, HEADS, BLO>;
+    constexpr int OPW = (A_MN && B_MN) ? 8 : 4;     // 8 operand warps for the dW-type GEMM (see ta_threads)
+    auto kern = gemm_tc_ta_kernel<A_MN, B_MN, SPLIT3, HEADS, BLO, OPW>;
     constexpr int SMEM = HEADS ? S::TOTAL_HEADS : S::TOTAL;
     static bool attr_set = false;
     if (!attr_set) {
@@ -908,7 +921,7 @@ static int launch_tc_ta(const CUtensorMap& ta, const CUtensorMap& tb, float* C, 
     }
     const int64_t tiles = ceil_div(N, 128) * ceil_div(M, TBM) * splits;
     const int64_t grid = tiles < sm_count() ? tiles : sm_count();
-    SFB_CUDA_OK(launch_pdl(kern, dim3((unsigned)grid), dim3(TC_THREADS), (size_t)SMEM, st, ta, tb, tb_lo ? *tb_lo : tb, C, ldc, M,
+    SFB_CUDA_OK(launch_pdl(kern, dim3((unsigned)grid), dim3(ta_threads(OPW)), (size_t)SMEM, st, ta, tb, tb_lo ? *tb_lo : tb, C, ldc, M,
                            N, K, k_chunk, splits, epi, raw_hi_enabled() ? 1 : 0));
     SFB_LAUNCH_OK();
     return 0;

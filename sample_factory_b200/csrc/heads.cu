@@ -570,6 +570,105 @@ static int heads_from_partials_impl(const float* head_partials, int P, int64_t r
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// The rest of a sampler step after the policy GEMMs, for the synthetic tape env (envs.TapeVecEnv, BASELINE config 2), in
+// ONE launch: finish the heads + sample (heads_finish_row) -> env step (the rules of tape_env_kernel, elementwise.cu)
+// -> advance_rollouts part 2 (post_step_body: reward scale / clip, dones, episode accounting, batched_sampling.py:319-357)
+// -> generate_policy_request + normalisation of step t+1 (normalize_body).  Everything is per env, so one warp walks one
+// env through all four stages; the three kernel boundaries (and two of the five launches of a policy step) disappear.
+// Same device functions / same arithmetic as the separate kernels -> identical trajectories.
+struct TapeStepArgs {
+    const float* tape; int64_t tape_len; int dim; int num_actions; int64_t env_off; int term_period, trunc_period;
+    int64_t* env_step;                                   // [0] env step, [1] block ticket
+    float* env_obs; float* env_rew; uint8_t* env_term; uint8_t* env_trunc;
+    float reward_scale, reward_clip; int32_t policy_id;
+    float* t_rew; uint8_t* t_done; uint8_t* t_to; int32_t* t_pid; int64_t stride;
+    float* ep_ret; int32_t* ep_len; float* ep_min; float* ep_max; int32_t len_inc; double* stats;
+    int64_t* sampler_step; float* fin_ret; int32_t* fin_len;
+    float* traj_obs_next; int64_t traj_obs_stride; float* x_norm; const double* mean; const double* var;
+    float sub, inv_scale; int do_sub, do_scale; float eps, clip;
+    const float* rnn; int rnn_dim; float* traj_rnn_next; int64_t traj_rnn_stride;
+};
+
+__global__ void __launch_bounds__(256) sampler_tail_tape_kernel(const float* __restrict__ part, int P, int64_t rows,
+                                                                const HeadsFinish f, const TapeStepArgs a) {
+    pdl_wait();
+    pdl_trigger();
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const float pv = f.pv_scalar ? *f.pv_scalar : 0.f;
+    const uint64_t offset = f.offset_host + (f.offset_dev ? (uint64_t)*f.offset_dev : 0ull);
+    const int64_t step = a.env_step[0];
+    const bool do_rms = a.mean != nullptr;
+    const float* src_step = a.tape + ((step + 1) % a.tape_len) * rows * a.dim;
+    for (int64_t row = warp; row < rows; row += nwarps) {
+        heads_finish_row(part, P, rows, row, lane, f, pv, offset);
+        __syncwarp();
+        const int act = f.out.env_actions[row];          // written by lane 0 just above
+        // ---- env step
+        const int64_t env = a.env_off + row;
+        const float r_raw = (float)act / (float)a.num_actions;
+        const bool tm = ((step * 7 + env * 13) % a.term_period) == 0;
+        const bool tr = (((step + env) % a.trunc_period) == 0) && !tm;
+        // ---- next observation: env buffer, trajectory slot t+1, normalised policy input
+        const float* src = src_step + row * a.dim;
+        for (int c = lane; c < a.dim; c += 32) {
+            const float v = src[c];
+            a.env_obs[row * a.dim + c] = v;
+            a.traj_obs_next[row * a.traj_obs_stride + c] = v;
+            if (a.x_norm) {
+                float mu = 0.f, is = 1.f;
+                if (do_rms) col_stats(a.mean, a.var, c, a.eps, mu, is);
+                a.x_norm[row * a.dim + c] = norm_one(v, a.sub, a.inv_scale, a.do_sub, a.do_scale, do_rms, mu, is, a.clip);
+            }
+        }
+        if (a.rnn)
+            for (int j = lane; j < a.rnn_dim; j += 32) a.traj_rnn_next[row * a.traj_rnn_stride + j] = a.rnn[row * a.rnn_dim + j];
+        // ---- post step (lane 0 owns the env's scalars)
+        if (lane == 0) {
+            a.env_rew[row] = r_raw;
+            a.env_term[row] = tm;
+            a.env_trunc[row] = tr;
+            const bool done = tm || tr;                                     // batched_sampling.py:317
+            float r = __fmul_rn(r_raw, a.reward_scale);                     // :209
+            r = clampf(r, -a.reward_clip, a.reward_clip);                   // :210
+            a.t_rew[row * a.stride] = r;
+            a.t_done[row * a.stride] = done ? 1 : 0;
+            a.t_to[row * a.stride] = tr ? 1 : 0;                            // :328
+            a.t_pid[row * a.stride] = a.policy_id;
+            if (a.ep_ret) {                                                 // _process_env_step :215-287 (raw reward)
+                float er = a.ep_ret[row] + r_raw;
+                int32_t el = a.ep_len[row] + a.len_inc;
+                float mn = fminf(a.ep_min[row], r_raw), mx = fmaxf(a.ep_max[row], r_raw);
+                if (a.fin_ret) {
+                    a.fin_ret[row * a.stride] = done ? er : __int_as_float(0x7fc00000);
+                    a.fin_len[row * a.stride] = done ? el : -1;
+                }
+                if (done) {
+                    if (a.stats) {
+                        atomicAdd(a.stats + 0, 1.0); atomicAdd(a.stats + 1, (double)er); atomicAdd(a.stats + 2, (double)el);
+                        atomicAdd(a.stats + 3, (double)mn); atomicAdd(a.stats + 4, (double)mx);
+                    }
+                    er = 0.f; el = 0; mn = INFINITY; mx = -INFINITY;
+                }
+                a.ep_ret[row] = er; a.ep_len[row] = el; a.ep_min[row] = mn; a.ep_max[row] = mx;
+            }
+        }
+    }
+    // every block has read both counters before taking its ticket, so the last ticket holder may advance them
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        unsigned long long* ticket = reinterpret_cast<unsigned long long*>(a.env_step + 1);
+        if (atomicAdd(ticket, 1ull) == (unsigned long long)gridDim.x - 1ull) {
+            *ticket = 0ull;
+            a.env_step[0] = step + 1;
+            if (a.sampler_step) *a.sampler_step += 1;
+        }
+    }
+}
+
 static int make_gaussian_out(HeadsOut& out, int act_dim, int adaptive_stddev, const float* learned_log_std,
                              float tanh_scale, float* values, int64_t values_stride, float* params,
                              int64_t params_stride, float* actions_f32, int64_t actions_stride, float* env_actions_f32,
@@ -620,6 +719,51 @@ int sfb200_heads_from_partials(const float* head_partials, int P, int64_t rows, 
                        log_prob, log_prob_stride, policy_version_out, pv_stride, 0, 0, nullptr, 0.f, nullptr};
     return heads_from_partials_impl(head_partials, P, rows, A, bv, ba, out, noise, philox_seed, philox_offset,
                                     philox_offset_dev, policy_version_scalar, (cudaStream_t)stream);
+}
+
+int sfb200_sampler_tail_tape_step(const float* head_partials, int P, int64_t n_envs, int A, const float* bv, const float* ba,
+                                  float* values_t, int64_t values_stride, float* logits_t, int64_t logits_stride,
+                                  const float* noise, uint64_t philox_seed, int64_t* sampler_step, float* actions_t,
+                                  int64_t actions_stride, int32_t* env_actions, float* log_prob_t, int64_t log_prob_stride,
+                                  const float* policy_version_scalar, float* policy_version_t, int64_t pv_stride,
+                                  const float* tape, int64_t tape_len, int dim, int64_t env_index_offset, int term_period,
+                                  int trunc_period, int64_t* env_step_counter, float* env_obs, float* env_rew,
+                                  uint8_t* env_terminated, uint8_t* env_truncated, float reward_scale, float reward_clip,
+                                  int32_t policy_id, float* traj_rewards_t, uint8_t* traj_dones_t, uint8_t* traj_time_outs_t,
+                                  int32_t* traj_policy_id_t, int64_t traj_stride, float* ep_return, int32_t* ep_len,
+                                  float* ep_min_raw, float* ep_max_raw, int32_t len_increment, double* stats,
+                                  float* fin_return_t, int32_t* fin_len_t, float* traj_obs_next, int64_t traj_obs_stride,
+                                  const float* rnn, int rnn_dim, float* traj_rnn_next, int64_t traj_rnn_stride, float* x_norm,
+                                  const double* mean, const double* var, float sub_mean, float inv_scale, float eps,
+                                  float clip, void* stream) {
+    HeadsOut out{values_t, values_stride, logits_t, logits_stride, actions_t, actions_stride, env_actions,
+                 log_prob_t, log_prob_stride, policy_version_t, pv_stride, 0, 0, nullptr, 0.f, nullptr};
+    if (int rc = apply_sampling_mode(out, A)) return rc;
+    SFB_CHECK_ARG(head_partials && bv && ba && values_t && actions_t && env_actions && n_envs >= 0 && P >= 1 && A >= 1 &&
+                      A + 1 <= kHeadPartPad, "sampler_tail_tape_step: bad heads arguments");
+    SFB_CHECK_ARG(tape && tape_len > 0 && dim > 0 && term_period > 0 && trunc_period > 0 && env_step_counter && env_obs &&
+                      env_rew && env_terminated && env_truncated, "sampler_tail_tape_step: bad env arguments");
+    SFB_CHECK_ARG(traj_rewards_t && traj_dones_t && traj_time_outs_t && traj_policy_id_t && traj_obs_next,
+                  "sampler_tail_tape_step: bad trajectory arguments");
+    SFB_CHECK_ARG((mean == nullptr) == (var == nullptr), "sampler_tail_tape_step: mean/var must both be set or both NULL");
+    SFB_CHECK_ARG((ep_return == nullptr) == (ep_len == nullptr) && (ep_return == nullptr) == (ep_min_raw == nullptr) &&
+                      (ep_return == nullptr) == (ep_max_raw == nullptr), "sampler_tail_tape_step: episode buffers all or none");
+    if (n_envs == 0) return 0;
+    const bool with_rnn = rnn && traj_rnn_next && rnn_dim > 0;
+    const TapeStepArgs a{tape, tape_len, dim, A, env_index_offset, term_period, trunc_period, env_step_counter, env_obs, env_rew,
+                         env_terminated, env_truncated, reward_scale, reward_clip, policy_id, traj_rewards_t, traj_dones_t,
+                         traj_time_outs_t, traj_policy_id_t, traj_stride, ep_return, ep_len, ep_min_raw, ep_max_raw,
+                         len_increment, stats, sampler_step, fin_return_t, fin_len_t, traj_obs_next, traj_obs_stride, x_norm,
+                         mean, var, sub_mean, inv_scale, fabsf(sub_mean) > 1e-8f ? 1 : 0, fabsf(inv_scale - 1.0f) > 1e-8f ? 1 : 0,
+                         eps, clip, with_rnn ? rnn : nullptr, rnn_dim, traj_rnn_next, traj_rnn_stride};
+    const HeadsFinish fin{out, bv, ba, noise, philox_seed, 0ull, sampler_step, policy_version_scalar, A};
+    int64_t blocks = ceil_div(n_envs, 8);
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    SFB_CUDA_OK(launch_pdl(sampler_tail_tape_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, head_partials, P,
+                           n_envs, fin, a));
+    SFB_LAUNCH_OK();
+    return 0;
 }
 
 static int make_tuple_out(HeadsOut& out, int A, int num_seg, const int32_t* seg_lens) {

@@ -449,6 +449,32 @@ def sampler_post_pre_step(rew: Tensor, terminated: Tensor, truncated: Tensor, re
                sub_mean, inv_scale, eps, clip, _stream())
 
 
+def sampler_tail_tape_step(head_partials: Tensor, P: int, rows: int, bv: Tensor, ba: Tensor, *, values: Tensor,
+                           values_stride: int, logits: Tensor, logits_stride: int, noise: Optional[Tensor], philox_seed: int,
+                           sampler_step: Tensor, actions_f32: Tensor, actions_stride: int, env_actions: Tensor,
+                           log_prob: Tensor, log_prob_stride: int, policy_version_scalar: Tensor, policy_version_out: Tensor,
+                           pv_stride: int, env, reward_scale: float, reward_clip: float, policy_id: int, traj_rewards: Tensor,
+                           traj_dones: Tensor, traj_time_outs: Tensor, traj_policy_id: Tensor, ep_return: Tensor,
+                           ep_len: Tensor, ep_min_raw: Tensor, ep_max_raw: Tensor, len_increment: int, stats: Tensor,
+                           fin_return: Optional[Tensor], fin_len: Optional[Tensor], traj_obs_next: Tensor, rnn: Tensor,
+                           traj_rnn_next: Tensor, x_norm: Optional[Tensor], mean: Optional[Tensor], var: Optional[Tensor],
+                           sub_mean: float, inv_scale: float, eps: float = 1e-5, clip: float = 5.0) -> None:
+    """heads finish + sampling, the tape env's step, post-step(t) and pre-step(t+1) in ONE launch (csrc/heads.cu,
+    sampler_tail_tape_kernel).  `env` is a sample_factory_b200.envs.TapeVecEnv (float32 obs, Discrete actions)."""
+    A = ba.numel()
+    lib().call("sfb200_sampler_tail_tape_step", _p(head_partials, F32), P, rows, A, _p(bv, F32), _p(ba, F32),
+               _p(values, F32), values_stride, _p(logits, F32), logits_stride, _p(noise, F32), philox_seed,
+               _p(sampler_step, I64), _p(actions_f32, F32), actions_stride, _p(env_actions, I32), _p(log_prob, F32),
+               log_prob_stride, _p(policy_version_scalar, F32), _p(policy_version_out, F32), pv_stride,
+               _p(env.tape, F32), env.tape_len, env.obs_dim, env.env_index_offset, env.term_period, env.trunc_period,
+               _p(env.step_counter, I64), _p(env.obs, F32), _p(env.rew, F32), _p(env.terminated, U8), _p(env.truncated, U8),
+               reward_scale, reward_clip, policy_id, _p(traj_rewards, F32), _p(traj_dones, U8), _p(traj_time_outs, U8),
+               _p(traj_policy_id, I32), traj_rewards.stride(0), _p(ep_return, F32), _p(ep_len, I32), _p(ep_min_raw, F32),
+               _p(ep_max_raw, F32), len_increment, _p(stats, F64), _p(fin_return, F32), _p(fin_len, I32),
+               _p(traj_obs_next, F32), traj_obs_next.stride(0), _p(rnn, F32), rnn.shape[1], _p(traj_rnn_next, F32),
+               traj_rnn_next.stride(0), _p(x_norm, F32), _p(mean, F64), _p(var, F64), sub_mean, inv_scale, eps, clip, _stream())
+
+
 def copy_rows(src: Tensor, dst: Tensor) -> None:
     rows, dim = src.shape
     lib().call("sfb200_copy_rows", _p(src, F32), src.stride(0), dst.data_ptr(), dst.stride(0), rows, dim, _stream())

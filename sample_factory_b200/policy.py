@@ -72,7 +72,7 @@ class HeadsPlan:
 
 def forward_policy(model: PolicyModel, x: Tensor, outs: List[Tensor], act: int, engine: int, plan: HeadsPlan,
                    heads_kwargs: Dict, rnn_fn: Optional[Callable[[Tensor], Tensor]] = None,
-                   store_tail: bool = True) -> Tensor:
+                   store_tail: bool = True, finish_fn: Optional[Callable] = None) -> Tensor:
     """x [M, D] (rows may be strided) -> heads outputs described by `heads_kwargs` (the keyword arguments of
     ops.heads_forward after the weights).  outs: one [>=M, h] buffer per MLP layer.  Returns the tensor that fed the
     heads (None if it was not stored)."""
@@ -89,7 +89,10 @@ def forward_policy(model: PolicyModel, x: Tensor, outs: List[Tensor], act: int, 
     if plan.mlp2 and not store_tail and not plan.finish_in_gemm:
         (W1, b1), (W2, b2) = enc
         ops.policy_mlp2_heads_forward(x, W1, b1, W2, b2, act, engine, Wv, Wa, plan.part)
-        _heads(model, None, Wv, bv, Wa, ba, True, plan, M, heads_kwargs)
+        if finish_fn is not None:
+            finish_fn(plan.part, plan.P, M, bv, ba)
+        else:
+            _heads(model, None, Wv, bv, Wa, ba, True, plan, M, heads_kwargs)
         return None
     k = 0
     tail: Optional[Tensor] = x
@@ -114,7 +117,10 @@ def forward_policy(model: PolicyModel, x: Tensor, outs: List[Tensor], act: int, 
                 ops.linear_act_forward(tail, W, b, outs[k][:M], act, engine)
                 tail = outs[k][:M]
             k += 1
-    _heads(model, tail, Wv, bv, Wa, ba, fused, plan, M, heads_kwargs)
+    if finish_fn is not None and fused:
+        finish_fn(plan.part, plan.P, M, bv, ba)
+    else:
+        _heads(model, tail, Wv, bv, Wa, ba, fused, plan, M, heads_kwargs)
     return tail
 
 

@@ -94,6 +94,18 @@ class DeviceSampler:
         self._step_graphs = None
         self._eager_rollouts = 0
         self.kernel_launches_per_rollout = 0
+        # Fused step tail (csrc/heads.cu sampler_tail_tape_kernel): for the synthetic tape env the heads' finishing step,
+        # the env step, post-step(t) and pre-step(t+1) are ONE launch -- with the fused two-layer policy kernel a policy
+        # step is two launches.  Needs the fused-partials heads path, a plain Discrete action space, float32 observations,
+        # no recurrent core and an env whose step is the tape rule.  SFB200_TAIL_FUSED=0 restores the separate launches.
+        import os
+
+        from .envs import TapeVecEnv
+        self.fused_tail = (os.environ.get("SFB200_TAIL_FUSED", "1") != "0" and type(env) is TapeVecEnv and
+                           not env.continuous and not env.action_segments and not env.with_action_mask and
+                           not env.obs_uint8 and self.rnn is None and self.heads_plan.P > 0 and
+                           not self.heads_plan.finish_in_gemm and not self.heads_plan.separate and
+                           not spec.continuous and not spec.action_segments)
 
     # ------------------------------------------------------------------------------------------------------------
     def _take_obs(self, obs):
@@ -126,8 +138,9 @@ class DeviceSampler:
         ops.sampler_pre_step(self.last_obs, tr["obs"][:, t], self.last_rnn_state, tr["rnn_states"][:, t], self.x_norm,
                              mean, var, spec.obs_subtract_mean, 1.0 / spec.obs_scale)
 
-    def _policy_step(self, t: int) -> None:
-        """policy forward + sampling on the pre-step's x_norm; outputs go straight into traj[:, t]"""
+    def _policy_step(self, t: int, fused_tail: bool = False) -> None:
+        """policy forward + sampling on the pre-step's x_norm; outputs go straight into traj[:, t].  fused_tail: the same
+        launch that finishes the heads also steps the tape env and runs post-step(t) + pre-step(t+1)."""
         cfg, m, spec, tr = self.cfg, self.model, self.model.spec, self.traj
         rnn_fn = None
         if self.rnn is not None:   # ModelCoreRNN.forward (core.py:37-64), one step
@@ -147,9 +160,33 @@ class DeviceSampler:
         special = self.action_mask is not None or self.deterministic
         if special:
             ops.set_sampling_mode(self.action_mask, self.deterministic)
+        finish_fn = None
+        if fused_tail:
+            last = t + 1 == self.T
+            env = self.env
+
+            def finish_fn(part, P, M, bv, ba):
+                ops.sampler_tail_tape_step(
+                    part, P, M, bv, ba, values=tr["values"][:, t], values_stride=tr["values"].stride(0),
+                    logits=tr["action_logits"][:, t], logits_stride=tr["action_logits"].stride(0), noise=noise_t,
+                    philox_seed=self.philox_seed, sampler_step=self.step_counter, actions_f32=tr["actions"][:, t],
+                    actions_stride=tr["actions"].stride(0), env_actions=self.env_actions,
+                    log_prob=tr["log_prob_actions"][:, t], log_prob_stride=tr["log_prob_actions"].stride(0),
+                    policy_version_scalar=self.policy_version, policy_version_out=tr["policy_version"][:, t],
+                    pv_stride=tr["policy_version"].stride(0), env=env, reward_scale=cfg.reward_scale,
+                    reward_clip=cfg.reward_clip, policy_id=cfg.policy_id, traj_rewards=tr["rewards"][:, t],
+                    traj_dones=tr["dones"][:, t], traj_time_outs=tr["time_outs"][:, t], traj_policy_id=tr["policy_id"][:, t],
+                    ep_return=self.ep_return, ep_len=self.ep_len, ep_min_raw=self.ep_min_raw, ep_max_raw=self.ep_max_raw,
+                    len_increment=cfg.env_frameskip if cfg.summaries_use_frameskip else 1, stats=self.episode_stats,
+                    fin_return=None if self.fin_return is None else self.fin_return[:, t],
+                    fin_len=None if self.fin_len is None else self.fin_len[:, t], traj_obs_next=tr["obs"][:, t + 1],
+                    rnn=self.last_rnn_state, traj_rnn_next=tr["rnn_states"][:, t + 1], x_norm=None if last else self.x_norm,
+                    mean=m.obs_mean if spec.normalize_input else None, var=m.obs_var if spec.normalize_input else None,
+                    sub_mean=spec.obs_subtract_mean, inv_scale=1.0 / spec.obs_scale)
+
         try:
             forward_policy(m, self.x_norm, self.h, self.act, self.engine, self.heads_plan, heads_kwargs, rnn_fn,
-                           store_tail=False)
+                           store_tail=False, finish_fn=finish_fn)
         finally:
             if special:
                 ops.set_sampling_mode(None, False)
@@ -191,6 +228,9 @@ class DeviceSampler:
 
     def advance_rollouts(self, t: int) -> None:
         """One env step for all envs: policy step then env step (reference: inference then advance_rollouts)."""
+        if self.fused_tail and self.last_obs is self.env.obs:
+            self._policy_step(t, fused_tail=True)      # heads + env step + post-step(t) + pre-step(t+1): one launch
+            return
         self._policy_step(t)
         self._env_and_post_step(t)
 

@@ -470,3 +470,51 @@ def test_graphed_learner_matches_eager():
         sa, sb = learnerA.fetch_stats(), learnerB.fetch_stats()
         assert sa["grad_norm"] == sb["grad_norm"] and sa["loss"] == sb["loss"]
     assert learnerB.graph_replay_launches > 0 and learnerB.kernel_launches == learnerA.kernel_launches + 2  # + advance_counters
+
+
+@pytest.mark.parametrize("explicit_noise", [True, False])
+def test_fused_policy_step_matches_separate_launches(explicit_noise, monkeypatch):
+    """A policy step as TWO launches (csrc/policy_step.cu: both MLP layers + head partials; csrc/heads.cu
+    sampler_tail_tape_kernel: heads finish + sampling + tape-env step + post-step(t) + pre-step(t+1)) produces the same
+    trajectories, episode statistics, env state and next policy input as the per-layer / per-stage launches: bit-identical
+    for everything downstream of the logits (same device functions), logits / values at rounding level."""
+    _need("3xtf32")
+    dev = torch.device("cuda", 0)
+    N, T = 1000, 12
+    ocfg = O.OracleCfg(rollout=T, recurrence=1, batch_size=N * T // 4, num_batches_per_epoch=4)
+    st0 = O.init_state(ocfg, seed=9)
+    gen = torch.Generator().manual_seed(3)
+    tape = torch.randn(2 * T + 1, N, ocfg.obs_dim, generator=gen)
+    noise = torch.empty(T, N, ocfg.num_actions).exponential_(generator=gen).to(dev)
+    runs = {}
+    for mode in ("separate", "fused"):
+        monkeypatch.setenv("SFB200_TAIL_FUSED", "1" if mode == "fused" else "0")
+        monkeypatch.setenv("SFB200_POLICY_FUSED", "1" if mode == "fused" else "0")
+        cfg, model, traj, env, sampler, learner = build(ocfg, N, st0, tape, dev, engine="3xtf32")
+        assert sampler.fused_tail == (mode == "fused") and sampler.heads_plan.mlp2 == (mode == "fused")
+        sampler.reset()
+        out = []
+        for it in range(2):
+            if explicit_noise:
+                sampler.noise = noise
+            sampler.set_policy_version(5 + it)
+            sampler.rollout()
+            out.append({k: v.clone() for k, v in traj.items()})
+        torch.cuda.synchronize()
+        runs[mode] = dict(traj=out, x_norm=sampler.x_norm.clone(), obs=env.obs.clone(), rew=env.rew.clone(),
+                          term=env.terminated.clone(), step=env.step_counter.clone(), pstep=sampler.step_counter.clone(),
+                          stats=sampler.episode_stats.clone(), ep=(sampler.ep_return.clone(), sampler.ep_len.clone()),
+                          launches=sampler.kernel_launches_per_rollout)
+    a, b = runs["separate"], runs["fused"]
+    # (the test-suite runs with SFB200_CHECK_LO=1: two extra verification launches per fused GEMM call)
+    assert b["launches"] in (1 + 2 * T, 1 + 4 * T) and a["launches"] > b["launches"], (a["launches"], b["launches"])
+    for ta, tb in zip(a["traj"], b["traj"]):
+        for k in ta:
+            if k in ("action_logits", "values", "log_prob_actions"):
+                np.testing.assert_allclose(ta[k].cpu().numpy(), tb[k].cpu().numpy(), rtol=0, atol=2e-6, err_msg=k)
+            elif k != "valids":
+                assert torch.equal(ta[k], tb[k]), k
+    for k in ("x_norm", "obs", "rew", "term", "step", "pstep"):
+        assert torch.equal(a[k], b[k]), k
+    np.testing.assert_allclose(a["stats"].cpu().numpy(), b["stats"].cpu().numpy(), rtol=1e-12)
+    assert torch.equal(a["ep"][0], b["ep"][0]) and torch.equal(a["ep"][1], b["ep"][1])
