@@ -277,6 +277,12 @@ int sfb200_sampler_post_pre_step(const float* rew, const uint8_t* terminated, co
                                  float* x_norm, const double* mean, const double* var, float sub_mean, float inv_scale,
                                  float eps, float clip, void* stream);
 
+/* Shuffled minibatches (learner.py:498-526: `buffer[indices]` with indices = a permutation of recurrence-length chunks):
+ * dst[r, :] = src[idx[r], :] for `rows` rows of `row_bytes` bytes each (any element type; dense rows). */
+/* strided row copy of any element type (bool masks, int32 ids): rows of row_bytes bytes, row strides in bytes */
+int sfb200_copy_rows_bytes(const void* src, int64_t src_stride_bytes, void* dst, int64_t dst_stride_bytes, int64_t rows,
+                           int64_t row_bytes, void* stream);
+int sfb200_gather_rows(const void* src, int64_t row_bytes, const int32_t* idx, int64_t rows, void* dst, void* stream);
 /* strided row copy dst[i*dst_stride + 0..dim) = src[i*src_stride + 0..dim) (_finalize_trajectories :289-296) */
 int sfb200_copy_rows(const float* src, int64_t src_stride, float* dst, int64_t dst_stride, int64_t rows, int dim,
                      void* stream);

@@ -996,8 +996,10 @@ class OracleLearner:
         self.env_steps = 0
         self.log: List[Dict[str, float]] = []
 
-    def train(self, batch: Dict[str, Tensor]) -> Dict[str, Tensor]:
-        """learner.py:1036-1067 -> _prepare_batch -> _train (:671-841). Returns the prepared flat buffer."""
+    def train(self, batch: Dict[str, Tensor], mb_indices: Optional[Tensor] = None) -> Dict[str, Tensor]:
+        """learner.py:1036-1067 -> _prepare_batch -> _train (:671-841). Returns the prepared flat buffer.
+        mb_indices (shuffle_minibatches, learner.py:498-526): a permutation of the flat sample indices built from
+        recurrence-length chunks; minibatch b is buffer[mb_indices[b*B:(b+1)*B]] (`_get_minibatch` :528-535)."""
         cfg = self.cfg
         buff, experience_size, num_invalids = prepare_batch(cfg, self.st, batch, self.train_step)
         if num_invalids >= experience_size:
@@ -1009,6 +1011,9 @@ class OracleLearner:
             for b in range(nmb):
                 if nmb == 1:
                     mb = buff
+                elif mb_indices is not None:
+                    ind = mb_indices[b * cfg.batch_size: (b + 1) * cfg.batch_size].long()   # :509-517
+                    mb = {k: v[ind] for k, v in buff.items()}
                 else:
                     sl = slice(b * cfg.batch_size, (b + 1) * cfg.batch_size)  # :521
                     mb = {k: v[sl] for k, v in buff.items()}

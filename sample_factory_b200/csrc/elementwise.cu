@@ -140,6 +140,38 @@ __global__ void copy_rows_kernel(const float* __restrict__ src, int64_t ss, floa
     }
 }
 
+// ---- row gather (shuffled minibatches: learner.py:498-526 `buffer[indices]`) --------------------------------------------
+// dst[r, :] = src[idx[r], :] for rows of row_bytes bytes; WB = bytes moved per thread access (16 / 4 / 1)
+template <int WB>
+__global__ void __launch_bounds__(256) gather_rows_kernel(const uint8_t* __restrict__ src, int64_t row_bytes,
+                                                          const int32_t* __restrict__ idx, int64_t rows,
+                                                          uint8_t* __restrict__ dst) {
+    const int64_t per_row = row_bytes / WB;
+    const int64_t total = rows * per_row;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / per_row, c = (i - r * per_row) * WB;
+        const uint8_t* s = src + (int64_t)idx[r] * row_bytes + c;
+        uint8_t* d = dst + r * row_bytes + c;
+        if (WB == 16) *reinterpret_cast<uint4*>(d) = *reinterpret_cast<const uint4*>(s);
+        else if (WB == 4) *reinterpret_cast<uint32_t*>(d) = *reinterpret_cast<const uint32_t*>(s);
+        else *d = *s;
+    }
+}
+
+template <int WB>
+__global__ void __launch_bounds__(256) copy_rows_bytes_kernel(const uint8_t* __restrict__ src, int64_t ss,
+                                                              uint8_t* __restrict__ dst, int64_t ds, int64_t rows,
+                                                              int64_t row_bytes) {
+    const int64_t per_row = row_bytes / WB;
+    const int64_t total = rows * per_row;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / per_row, c = (i - r * per_row) * WB;
+        if (WB == 16) *reinterpret_cast<uint4*>(dst + r * ds + c) = *reinterpret_cast<const uint4*>(src + r * ss + c);
+        else if (WB == 4) *reinterpret_cast<uint32_t*>(dst + r * ds + c) = *reinterpret_cast<const uint32_t*>(src + r * ss + c);
+        else dst[r * ds + c] = src[r * ss + c];
+    }
+}
+
 // ---- post env step -------------------------------------------------------------------------------------------------
 struct PostArgs {
     const float* rew; const uint8_t* term; const uint8_t* trunc; int64_t n;
@@ -340,6 +372,46 @@ int sfb200_sampler_pre_step_u8(const uint8_t* obs, int64_t n_envs, int dim, uint
                                float clip, void* stream) {
     return sampler_pre_step_impl(obs, true, n_envs, dim, traj_obs_t, traj_obs_stride, rnn, rnn_dim, traj_rnn_t,
                                  traj_rnn_stride, x_norm, mean, var, sub_mean, inv_scale, eps, clip, stream);
+}
+
+int sfb200_copy_rows_bytes(const void* src, int64_t src_stride_bytes, void* dst, int64_t dst_stride_bytes, int64_t rows,
+                           int64_t row_bytes, void* stream) {
+    SFB_CHECK_ARG(src && dst && rows >= 0 && row_bytes > 0, "copy_rows_bytes: bad arguments");
+    if (rows == 0) return 0;
+    const uintptr_t al = reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst) | (uintptr_t)row_bytes |
+                         (uintptr_t)src_stride_bytes | (uintptr_t)dst_stride_bytes;
+    const int wb = (al % 16 == 0) ? 16 : ((al % 4 == 0) ? 4 : 1);
+    int64_t blocks = ceil_div(rows * (row_bytes / wb), 256);
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    const dim3 g((unsigned)blocks), b(256);
+    cudaStream_t st = (cudaStream_t)stream;
+    const uint8_t* s8 = (const uint8_t*)src;
+    uint8_t* d8 = (uint8_t*)dst;
+    if (wb == 16) copy_rows_bytes_kernel<16><<<g, b, 0, st>>>(s8, src_stride_bytes, d8, dst_stride_bytes, rows, row_bytes);
+    else if (wb == 4) copy_rows_bytes_kernel<4><<<g, b, 0, st>>>(s8, src_stride_bytes, d8, dst_stride_bytes, rows, row_bytes);
+    else copy_rows_bytes_kernel<1><<<g, b, 0, st>>>(s8, src_stride_bytes, d8, dst_stride_bytes, rows, row_bytes);
+    SFB_LAUNCH_OK();
+    return 0;
+}
+
+int sfb200_gather_rows(const void* src, int64_t row_bytes, const int32_t* idx, int64_t rows, void* dst, void* stream) {
+    SFB_CHECK_ARG(src && idx && dst && row_bytes > 0 && rows >= 0, "gather_rows: bad arguments");
+    if (rows == 0) return 0;
+    const uintptr_t al = reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst) | (uintptr_t)row_bytes;
+    const int wb = (al % 16 == 0) ? 16 : ((al % 4 == 0) ? 4 : 1);
+    int64_t blocks = ceil_div(rows * (row_bytes / wb), 256);
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    const dim3 g((unsigned)blocks), b(256);
+    cudaStream_t st = (cudaStream_t)stream;
+    const uint8_t* s8 = (const uint8_t*)src;
+    uint8_t* d8 = (uint8_t*)dst;
+    if (wb == 16) gather_rows_kernel<16><<<g, b, 0, st>>>(s8, row_bytes, idx, rows, d8);
+    else if (wb == 4) gather_rows_kernel<4><<<g, b, 0, st>>>(s8, row_bytes, idx, rows, d8);
+    else gather_rows_kernel<1><<<g, b, 0, st>>>(s8, row_bytes, idx, rows, d8);
+    SFB_LAUNCH_OK();
+    return 0;
 }
 
 int sfb200_copy_rows(const float* src, int64_t src_stride, float* dst, int64_t dst_stride, int64_t rows, int dim,

@@ -558,9 +558,9 @@ constexpr uint32_t TA_ACOL0 = 256;
 // Operand warps of the TMEM-A kernel.  With 4 (one per TMEM lane quadrant, each thread converting a whole 32-column row of
 // the k-block) the conversion paced the main loop: one warp per SM sub-partition cannot overlap its own shared-memory /
 // tcgen05.st / mbarrier latencies.  8 warps = two per quadrant, each thread converts 16 columns.
-// Used where the conversion is the bottleneck: the dW GEMM (both operands are MN-major activations: 32-bit shared-memory
-// reads for A and an in-kernel split of B).  576 threads leave 96 registers per thread, which makes the epilogue spill;
-// dW tiles run ~100 k-blocks per epilogue, the forward / dX tiles 16, so those keep 4 operand warps and 128 registers.
+// Instantiated for the dW GEMM only (both operands are MN-major activations: 32-bit shared-memory reads for A and an
+// in-kernel split of B; 576 threads leave 96 registers per thread, which makes the epilogue spill -- tolerable there
+// because a dW tile runs ~100 k-blocks per epilogue).  Opt-in, see dw_operand_warps().
 constexpr int ta_threads(int opw) { return 32 * (2 + opw + 8); }   // 448 (4 operand warps) or 576 (8)
 
 template <int STAGES>
@@ -907,11 +907,21 @@ static bool raw_hi_enabled() {
     return v == 1;
 }
 
-template <bool A_MN, bool B_MN, bool SPLIT3, bool HEADS = false, bool BLO = false>
-static int launch_tc_ta(const CUtensorMap& ta, const CUtensorMap& tb, float* C, int64_t ldc, int64_t M, int N, int K,
-                        int k_chunk, int splits, const TcEpilogue& epi, cudaStream_t st, const CUtensorMap* tb_lo = nullptr) {
+// SFB200_TA_DW_OPW=8 runs the dW-type GEMM (both operands MN-major) with eight operand warps instead of four (A/B switch;
+// measured on B200, tools/dw_bench.py: no gain -- the dW GEMM is bound by the tf32 MMA rate like the others)
+static int dw_operand_warps() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("SFB200_TA_DW_OPW");
+        v = (e && e[0] == '8') ? 8 : 4;
+    }
+    return v;
+}
+
+template <bool A_MN, bool B_MN, bool SPLIT3, bool HEADS, bool BLO, int OPW>
+static int launch_tc_ta_opw(const CUtensorMap& ta, const CUtensorMap& tb, float* C, int64_t ldc, int64_t M, int N, int K,
+                            int k_chunk, int splits, const TcEpilogue& epi, cudaStream_t st, const CUtensorMap* tb_lo) {
     using S = TaSmem<TA_STAGES>;
-    constexpr int OPW = (A_MN && B_MN) ? 8 : 4;     // 8 operand warps for the dW-type GEMM (see ta_threads)
     auto kern = gemm_tc_ta_kernel<A_MN, B_MN, SPLIT3, HEADS, BLO, OPW>;
     constexpr int SMEM = HEADS ? S::TOTAL_HEADS : S::TOTAL;
     static bool attr_set = false;
@@ -925,6 +935,16 @@ static int launch_tc_ta(const CUtensorMap& ta, const CUtensorMap& tb, float* C, 
                            N, K, k_chunk, splits, epi, raw_hi_enabled() ? 1 : 0));
     SFB_LAUNCH_OK();
     return 0;
+}
+
+template <bool A_MN, bool B_MN, bool SPLIT3, bool HEADS = false, bool BLO = false>
+static int launch_tc_ta(const CUtensorMap& ta, const CUtensorMap& tb, float* C, int64_t ldc, int64_t M, int N, int K,
+                        int k_chunk, int splits, const TcEpilogue& epi, cudaStream_t st, const CUtensorMap* tb_lo = nullptr) {
+    if constexpr (A_MN && B_MN) {
+        if (dw_operand_warps() == 8)
+            return launch_tc_ta_opw<A_MN, B_MN, SPLIT3, HEADS, BLO, 8>(ta, tb, C, ldc, M, N, K, k_chunk, splits, epi, st, tb_lo);
+    }
+    return launch_tc_ta_opw<A_MN, B_MN, SPLIT3, HEADS, BLO, 4>(ta, tb, C, ldc, M, N, K, k_chunk, splits, epi, st, tb_lo);
 }
 
 // SFB200_TC_B_LO=0 ignores registered tf32-lo buffers (A/B comparison)

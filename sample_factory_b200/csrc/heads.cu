@@ -592,35 +592,57 @@ struct TapeStepArgs {
 
 __global__ void __launch_bounds__(256) sampler_tail_tape_kernel(const float* __restrict__ part, int P, int64_t rows,
                                                                 const HeadsFinish f, const TapeStepArgs a) {
+    // per-column normaliser constants once per block (instead of a double load + sqrt + divide per element)
+    extern __shared__ float cstat[];   // [2][dim]: mu, 1 / sigma
+    const bool do_rms = a.mean != nullptr && a.x_norm != nullptr;
     pdl_wait();
     pdl_trigger();
+    if (do_rms) {
+        for (int c = threadIdx.x; c < a.dim; c += blockDim.x) col_stats(a.mean, a.var, c, a.eps, cstat[c], cstat[a.dim + c]);
+        __syncthreads();
+    }
     const int lane = threadIdx.x & 31;
     const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const float pv = f.pv_scalar ? *f.pv_scalar : 0.f;
     const uint64_t offset = f.offset_host + (f.offset_dev ? (uint64_t)*f.offset_dev : 0ull);
     const int64_t step = a.env_step[0];
-    const bool do_rms = a.mean != nullptr;
     const float* src_step = a.tape + ((step + 1) % a.tape_len) * rows * a.dim;
+    const bool two = (a.dim == 64);    // the common case: one float2 per lane, issued before the heads math
     for (int64_t row = warp; row < rows; row += nwarps) {
-        heads_finish_row(part, P, rows, row, lane, f, pv, offset);
-        __syncwarp();
-        const int act = f.out.env_actions[row];          // written by lane 0 just above
+        // ---- everything that does not depend on the sampled action is loaded first (the next observation comes from the
+        //      tape whatever the action is; the episode accumulators are lane 0's)
+        const float* src = src_step + row * a.dim;
+        float2 o2 = make_float2(0.f, 0.f);
+        if (two) o2 = *reinterpret_cast<const float2*>(src + 2 * lane);
+        float er0 = 0.f, mn0 = 0.f, mx0 = 0.f;
+        int32_t el0 = 0;
+        if (lane == 0 && a.ep_ret) { er0 = a.ep_ret[row]; el0 = a.ep_len[row]; mn0 = a.ep_min[row]; mx0 = a.ep_max[row]; }
+        const int act = heads_finish_row(part, P, rows, row, lane, f, pv, offset);
         // ---- env step
         const int64_t env = a.env_off + row;
         const float r_raw = (float)act / (float)a.num_actions;
         const bool tm = ((step * 7 + env * 13) % a.term_period) == 0;
         const bool tr = (((step + env) % a.trunc_period) == 0) && !tm;
         // ---- next observation: env buffer, trajectory slot t+1, normalised policy input
-        const float* src = src_step + row * a.dim;
-        for (int c = lane; c < a.dim; c += 32) {
-            const float v = src[c];
-            a.env_obs[row * a.dim + c] = v;
-            a.traj_obs_next[row * a.traj_obs_stride + c] = v;
+        if (two) {
+            const int c = 2 * lane;
+            *reinterpret_cast<float2*>(a.env_obs + row * a.dim + c) = o2;
+            *reinterpret_cast<float2*>(a.traj_obs_next + row * a.traj_obs_stride + c) = o2;
             if (a.x_norm) {
-                float mu = 0.f, is = 1.f;
-                if (do_rms) col_stats(a.mean, a.var, c, a.eps, mu, is);
-                a.x_norm[row * a.dim + c] = norm_one(v, a.sub, a.inv_scale, a.do_sub, a.do_scale, do_rms, mu, is, a.clip);
+                float2 y;
+                y.x = norm_one(o2.x, a.sub, a.inv_scale, a.do_sub, a.do_scale, do_rms, do_rms ? cstat[c] : 0.f, do_rms ? cstat[a.dim + c] : 1.f, a.clip);
+                y.y = norm_one(o2.y, a.sub, a.inv_scale, a.do_sub, a.do_scale, do_rms, do_rms ? cstat[c + 1] : 0.f, do_rms ? cstat[a.dim + c + 1] : 1.f, a.clip);
+                *reinterpret_cast<float2*>(a.x_norm + row * a.dim + c) = y;
+            }
+        } else {
+            for (int c = lane; c < a.dim; c += 32) {
+                const float v = src[c];
+                a.env_obs[row * a.dim + c] = v;
+                a.traj_obs_next[row * a.traj_obs_stride + c] = v;
+                if (a.x_norm)
+                    a.x_norm[row * a.dim + c] = norm_one(v, a.sub, a.inv_scale, a.do_sub, a.do_scale, do_rms,
+                                                         do_rms ? cstat[c] : 0.f, do_rms ? cstat[a.dim + c] : 1.f, a.clip);
             }
         }
         if (a.rnn)
@@ -638,9 +660,9 @@ __global__ void __launch_bounds__(256) sampler_tail_tape_kernel(const float* __r
             a.t_to[row * a.stride] = tr ? 1 : 0;                            // :328
             a.t_pid[row * a.stride] = a.policy_id;
             if (a.ep_ret) {                                                 // _process_env_step :215-287 (raw reward)
-                float er = a.ep_ret[row] + r_raw;
-                int32_t el = a.ep_len[row] + a.len_inc;
-                float mn = fminf(a.ep_min[row], r_raw), mx = fmaxf(a.ep_max[row], r_raw);
+                float er = er0 + r_raw;
+                int32_t el = el0 + a.len_inc;
+                float mn = fminf(mn0, r_raw), mx = fmaxf(mx0, r_raw);
                 if (a.fin_ret) {
                     a.fin_ret[row * a.stride] = done ? er : __int_as_float(0x7fc00000);
                     a.fin_len[row * a.stride] = done ? el : -1;
@@ -760,8 +782,9 @@ int sfb200_sampler_tail_tape_step(const float* head_partials, int P, int64_t n_e
     int64_t blocks = ceil_div(n_envs, 8);
     const int64_t cap = (int64_t)sm_count() * 8;
     if (blocks > cap) blocks = cap;
-    SFB_CUDA_OK(launch_pdl(sampler_tail_tape_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, head_partials, P,
-                           n_envs, fin, a));
+    SFB_CHECK_ARG(dim <= 4096, "sampler_tail_tape_step: observation rows of up to 4096 floats");
+    SFB_CUDA_OK(launch_pdl(sampler_tail_tape_kernel, dim3((unsigned)blocks), dim3(256), (size_t)(2 * dim * sizeof(float)),
+                           (cudaStream_t)stream, head_partials, P, n_envs, fin, a));
     SFB_LAUNCH_OK();
     return 0;
 }

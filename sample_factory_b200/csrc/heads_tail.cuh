@@ -81,19 +81,20 @@ __device__ __forceinline__ void tuple_row_tail(float mine, int lane, int A, int6
 
 // Lane a of the warp holds output a of one row (0 = value, 1..A = logits, bias included): store them and, in sampling
 // mode, run CategoricalActionDistribution (action_distributions.py:110-148) on the lanes.
-__device__ __forceinline__ void heads_row_tail(float mine, int lane, int A, int64_t row, const HeadsOut& out,
-                                               const float* __restrict__ noise, uint64_t seed, uint64_t offset, float pv) {
+// Returns the sampled action index of a plain Discrete space (the same value in every lane), -1 otherwise.
+__device__ __forceinline__ int heads_row_tail(float mine, int lane, int A, int64_t row, const HeadsOut& out,
+                                              const float* __restrict__ noise, uint64_t seed, uint64_t offset, float pv) {
     if (lane == 0) out.values[row * out.values_stride] = mine;
     if (out.dist != 0) {
         gaussian_row_tail(mine, lane, row, out, noise, seed, offset, pv);
-        return;
+        return -1;
     }
     const bool is_logit = lane >= 1 && lane <= A;
     if (out.logits && is_logit) out.logits[row * out.logits_stride + (lane - 1)] = mine;
-    if (out.actions_f32 == nullptr) return;   // values / logits only (warp-uniform)
+    if (out.actions_f32 == nullptr) return -1;   // values / logits only (warp-uniform)
     if (out.num_seg > 1) {
         tuple_row_tail(mine, lane, A, row, out, noise, seed, offset, pv);
-        return;
+        return -1;
     }
 
     const bool masked = out.action_mask != nullptr;
@@ -136,6 +137,7 @@ __device__ __forceinline__ void heads_row_tail(float mine, int lane, int A, int6
         if (out.log_prob) out.log_prob[row * out.log_prob_stride] = lp;
         if (out.pv_out) out.pv_out[row * out.pv_stride] = pv;
     }
+    return idx;
 }
 
 // TupleActionDistribution on the lanes: every head runs the categorical recipe on its own lane range; actions_f32 gets K
@@ -202,14 +204,14 @@ struct HeadsFinish {
 };
 
 // one warp finishes one row: fixed-order sum of the P partials (deterministic) + bias, then the distribution tail
-__device__ __forceinline__ void heads_finish_row(const float* __restrict__ part, int P, int64_t rows, int64_t row, int lane,
-                                                 const HeadsFinish& f, float pv, uint64_t offset) {
+__device__ __forceinline__ int heads_finish_row(const float* __restrict__ part, int P, int64_t rows, int64_t row, int lane,
+                                                const HeadsFinish& f, float pv, uint64_t offset) {
     float mine = 0.f;
     if (lane <= f.A) {
         for (int p = 0; p < P; ++p) mine += part[((int64_t)p * rows + row) * kHeadPartPad + lane];
     }
     mine += (lane == 0) ? f.bv[0] : (lane <= f.A ? f.ba[lane - 1] : 0.f);
-    heads_row_tail(mine, lane, f.A, row, f.out, f.noise, f.seed, offset, pv);
+    return heads_row_tail(mine, lane, f.A, row, f.out, f.noise, f.seed, offset, pv);
 }
 
 }  // namespace sfb

@@ -15,9 +15,12 @@
 //   warp 0      TMA producer: x tile once, then per chunk W1[c*32.., :] and W2[n0.., c*32..] (raw weights + tf32-lo twins)
 //   warp 1      TMEM allocator + single-thread MMA issuer (layer-1 chunk c is issued before layer-2 chunk c-1: the
 //               tensor pipe works on chunk c while the epilogue warps convert chunk c-1)
-//   warps 2-5   h1 chunks 0, 2, 4, ...  (TMEM lane quadrant = warp % 4)
-//   warps 6-9   h1 chunks 1, 3, 5, ...
-//   warps 2-9   final epilogue: h2 = act(acc + b2), head partials (warps 2-5 columns 0-63, warps 6-9 columns 64-127)
+//   warps 2-9   h1 chunks 0, 2, 4, ...  (TMEM lane quadrant = warp % 4; warps 2-5 convert columns 0-15 of the chunk,
+//               warps 6-9 columns 16-31)
+//   warps 10-17 h1 chunks 1, 3, 5, ...
+//   warps 2-17  final epilogue: h2 = act(acc + b2), head partials (four 32-column groups per 128-column tile)
+// The chunk conversion is the critical path (accumulator -> bias/activation/split -> A operand: ~4.8 k cycles with four
+// warps per chunk against 2.3 k cycles of MMA work per chunk, ncu r02_d); two sets of eight warps keep it off it.
 //
 // TMEM (512 columns): [0,256) layer-2 accumulator (main | cross), [256,384) two layer-1 accumulators (32 main | 32 cross),
 // [384,512) two A-operand stages (32 hi | 32 lo).
@@ -30,7 +33,7 @@
 
 namespace sfb {
 
-constexpr int PS_THREADS = 320;
+constexpr int PS_THREADS = 576;           // TMA warp, MMA warp, 16 epilogue warps
 constexpr int PS_STAGES = 3;
 constexpr int PS_HEAD_AP = 9;            // value + up to 8 action outputs (same partial format as the fused GEMM epilogue)
 constexpr int PS_W2_BYTES = 2 * 128 * 128;   // [hi 128 rows x 128 B | lo]
@@ -81,7 +84,7 @@ struct PsArgs {
     const float* head_wv;
     const float* head_wa;
     int head_A;
-    float* head_part;   // [H2/64][M][kHeadPartPad]
+    float* head_part;   // [H2/32][M][kHeadPartPad]
 };
 
 template <int KA, int ACT>
@@ -122,15 +125,15 @@ policy_mlp2_heads_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w2) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w2lo) : "memory");
         mbar_init(x_full, 1);
-        mbar_init(x_ready, 256);
+        mbar_init(x_ready, 512);
         for (int s = 0; s < PS_STAGES; ++s) {
             mbar_init(&w_full[s], 1);
             mbar_init(&w_empty[s], 1);
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&d1_full[b], 1);
-            mbar_init(&d1_empty[b], 128);
-            mbar_init(&a2_full[b], 128);
+            mbar_init(&d1_empty[b], 256);
+            mbar_init(&a2_full[b], 256);
             mbar_init(&a2_empty[b], 1);
         }
         mbar_init(d2_full, 1);
@@ -217,15 +220,16 @@ policy_mlp2_heads_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
             }
         }
     } else {
-        // ===================================================== epilogue warps (2..9)
-        const int et = threadIdx.x - 64;                 // 0..255
-        const int set = (warp - 2) >> 2;                 // 0: even h1 chunks / h2 columns 0-63, 1: odd chunks / columns 64-127
+        // ===================================================== epilogue warps (2..17)
+        const int et = threadIdx.x - 64;                 // 0..511
+        const int set = (warp - 2) >> 3;                 // 0: even h1 chunks, 1: odd chunks
+        const int half = ((warp - 2) >> 2) & 1;          // which 16 of the chunk's 32 columns this warp converts
         const int quad = warp & 3;                       // TMEM lane quadrant this warp may access
         const uint32_t lane_sel = (uint32_t)(quad * 32) << 16;
         // biases + head weights of this CTA's column slice -> shared memory
-        for (int i = et; i < a.H1; i += 256) b1_s[i] = a.b1[i];
+        for (int i = et; i < a.H1; i += 512) b1_s[i] = a.b1[i];
         if (et < 128) b2_s[et] = a.b2[n0 + et];
-        for (int i = et; i < PS_HEAD_AP * 128; i += 256) {
+        for (int i = et; i < PS_HEAD_AP * 128; i += 512) {
             const int r = i >> 7, n = i & 127;
             headw_s[i] = (r == 0) ? a.head_wv[n0 + n] : (r <= a.head_A ? a.head_wa[(int64_t)(r - 1) * a.H2 + n0 + n] : 0.f);
         }
@@ -235,7 +239,7 @@ policy_mlp2_heads_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
             const uint4* h4 = reinterpret_cast<const uint4*>(x_hi);
             uint4* l4 = reinterpret_cast<uint4*>(x_lo);
 #pragma unroll 4
-            for (int i = et; i < S::X_BYTES / 16; i += 256) {
+            for (int i = et; i < S::X_BYTES / 16; i += 512) {
                 const uint4 v = h4[i];
                 uint4 l;
                 l.x = tf32_lo_bits(v.x); l.y = tf32_lo_bits(v.y); l.z = tf32_lo_bits(v.z); l.w = tf32_lo_bits(v.w);
@@ -244,24 +248,24 @@ policy_mlp2_heads_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
         }
         fence_proxy_async_smem();
         mbar_arrive(x_ready);
-        asm volatile("bar.sync 1, 256;" ::: "memory");   // b1_s / b2_s / headw_s visible to all epilogue threads
+        asm volatile("bar.sync 1, 512;" ::: "memory");   // b1_s / b2_s / headw_s visible to all epilogue threads
 
         // ---- layer-1 chunks of this set: accumulator -> act(. + b1) -> (hi, lo) -> A stage
         for (int c = set; c < NC; c += 2) {
             const uint32_t u = (uint32_t)(c >> 1);
             ps_wait(&d1_full[set], u & 1);
             tc_fence_after();
-            const uint32_t d1 = tmem_base + lane_sel + PS_D1_COL + 64u * set;
-            uint32_t mainv[32], crossv[32];
-            tmem_ld_32x32b_x32(d1, mainv);
-            tmem_ld_32x32b_x32(d1 + 32, crossv);
+            const uint32_t d1 = tmem_base + lane_sel + PS_D1_COL + 64u * set + 16u * half;
+            uint32_t mainv[16], crossv[16];
+            tmem_ld_32x32b_x16(d1, mainv);
+            tmem_ld_32x32b_x16(d1 + 32, crossv);
             tmem_ld_wait();
             tc_fence_before();
             mbar_arrive(&d1_empty[set]);
-            const float* bias = b1_s + c * 32;
-            uint32_t lo[32];
+            const float* bias = b1_s + c * 32 + 16 * half;
+            uint32_t lo[16];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
+            for (int j = 0; j < 16; ++j) {
                 const float z = (__uint_as_float(mainv[j]) + __uint_as_float(crossv[j])) + bias[j];
                 const uint32_t hbits = __float_as_uint(act_fwd_ct<ACT>(z));
                 mainv[j] = hbits;                      // raw fp32 word = hi operand
@@ -269,21 +273,22 @@ policy_mlp2_heads_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
             }
             ps_wait(&a2_empty[set], (u & 1) ^ 1);
             tc_fence_after();
-            const uint32_t a2 = tmem_base + lane_sel + PS_A2_COL + 64u * set;
-            tmem_st_32x32b_x32(a2, mainv);
-            tmem_st_32x32b_x32(a2 + 32, lo);
+            const uint32_t a2 = tmem_base + lane_sel + PS_A2_COL + 64u * set + 16u * half;
+            tmem_st_32x32b_x16(a2, mainv);
+            tmem_st_32x32b_x16(a2 + 32, lo);
             tmem_st_wait();
             tc_fence_before();
             mbar_arrive(&a2_full[set]);
         }
 
-        // ---- final epilogue: h2 = act(acc + b2) for 64 columns of this thread's row, contracted with the head rows
+        // ---- final epilogue: h2 = act(acc + b2) for 32 columns of this thread's row, contracted with the head rows
         ps_wait(d2_full, 0);
         tc_fence_after();
-        const int col0 = set * 64;
-        float o[64];
+        const int grp = (warp - 2) >> 2;                 // 0..3: columns [32*grp, 32*grp + 32) of the tile
+        const int col0 = grp * 32;
+        float o[32];
 #pragma unroll
-        for (int c0 = 0; c0 < 64; c0 += 16) {
+        for (int c0 = 0; c0 < 32; c0 += 16) {
             uint32_t r[16], r2[16];
             tmem_ld_32x32b_x16(tmem_base + lane_sel + (uint32_t)(col0 + c0), r);
             tmem_ld_32x32b_x16(tmem_base + lane_sel + (uint32_t)(128 + col0 + c0), r2);
@@ -300,7 +305,7 @@ policy_mlp2_heads_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
                 const float* w = headw_s + r * 128 + col0;   // warp-uniform address: shared-memory broadcast
                 float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-                for (int j = 0; j < 64; j += 4) {
+                for (int j = 0; j < 32; j += 4) {
                     const float4 wv = *reinterpret_cast<const float4*>(w + j);
                     s0 = fmaf(o[j], wv.x, s0);
                     s1 = fmaf(o[j + 1], wv.y, s1);
@@ -309,7 +314,7 @@ policy_mlp2_heads_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
                 }
                 hp[r] = s0 + s1;
             }
-            const int p = blockIdx.x * 2 + set;
+            const int p = blockIdx.x * 4 + grp;
             float4* dst = reinterpret_cast<float4*>(a.head_part + ((int64_t)p * a.M + m) * kHeadPartPad);
             dst[0] = make_float4(hp[0], hp[1], hp[2], hp[3]);
             dst[1] = make_float4(hp[4], hp[5], hp[6], hp[7]);
@@ -347,7 +352,7 @@ int tc_policy_mlp2_supported(const float* W1, const float* W2, int K1, int H1, i
     if (!(K1 == 32 || K1 == 64) || H1 % 32 != 0 || H1 < 32 || H1 > PS_MAX_H1 || H2 % 128 != 0 || H2 < 128 || H2 > 512) return 0;
     if (A < 1 || A + 1 > PS_HEAD_AP) return 0;
     if (!tf32_lo_lookup(W1, (int64_t)H1 * K1) || !tf32_lo_lookup(W2, (int64_t)H2 * H1)) return 0;
-    return 2 * (H2 / 128);
+    return 4 * (H2 / 128);
 }
 
 int tc_policy_mlp2_heads_forward(const float* x, int64_t ldx, int64_t M, int K1, const float* W1, const float* b1, int H1,

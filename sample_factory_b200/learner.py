@@ -131,7 +131,11 @@ class Learner:
             "symmetric_kl_with_uniform_prior in the reference either)")
         assert not (spec.continuous and spec.adaptive_stddev and spec.continuous_tanh_scale > 0), (
             "continuous_tanh_scale is only read by the non-adaptive parameterization (action_parameterization.py:33-78)")
-        assert not cfg.shuffle_minibatches, "shuffle_minibatches is not on the device path yet"
+        # learner.py:498-526: minibatches = a random permutation of recurrence-length chunks of the dataset, drawn once per
+        # train() call.  Device path: the permutation is drawn on the host (np.random, like the reference), copied to the
+        # device, and ONE gather pass per train() rearranges every per-sample array the minibatch steps read; the steps then
+        # run on contiguous slices exactly as in the unshuffled case.
+        self.shuffle = bool(cfg.shuffle_minibatches) and cfg.num_batches_per_epoch > 1
         assert len(spec.hidden) > 0 or spec.use_rnn, "the device path needs at least one hidden layer or an RNN core"
         assert spec.obs_shape is None or len(spec.fc_encoder_layers) > 0, (
             "ConvEncoder on the device path needs at least one fully connected layer after the conv head "
@@ -225,6 +229,15 @@ class Learner:
             self.lamb_ws = torch.empty(ops.lamb_workspace_bytes(len(segs), self.lamb_max) // 4 + 4, **f32)
         self.opt_step = 0
         self.kernel_launches = 0
+        self._mb: Dict[str, Tensor] = {}
+        if self.shuffle:
+            chunk = cfg.recurrence if spec.use_rnn or cfg.with_vtrace else max(1, cfg.recurrence)
+            assert E % chunk == 0
+            self._perm_chunk = chunk
+            self.perm_host = torch.empty(E, dtype=torch.int32).pin_memory()
+            self.perm_dev = torch.arange(E, dtype=torch.int32, device=dev)
+            self._next_perm: Optional[np.ndarray] = None
+            self._sh: Dict[str, Tensor] = {}
         # CUDA-graph replay of the whole train() (cfg.learner_cuda_graph): possible when nothing in it depends on host
         # state -- constant lr schedule, one epoch (no early-stopping read-back), Adam.  The step counters and the
         # learning rate then live in device memory (read by the *_dev entry points).  Data parallel: opt-in with
@@ -337,7 +350,7 @@ class Learner:
         # :1006-1012 drop the T+1 column and flatten: strided copies into dense [N*T, ...] buffers
         ops.copy_rows(self.normalized_obs.view(N, (T + 1) * D)[:, : T * D], self.obs_flat_compact.view(N, T * D))
         ops.copy_rows(batch["values"][:, :T], self.values_old)
-        self.valids_flat.copy_(batch["valids"][:, :T])
+        ops.copy_rows_bytes(batch["valids"][:, :T], self.valids_flat)
         if self.rnn is not None:
             S = spec.rnn_state_size
             ops.copy_rows(batch["rnn_states"].view(N, (T + 1) * S)[:, : T * S], self.rnn_states_flat.view(N, T * S))
@@ -345,16 +358,17 @@ class Learner:
             r = self.returns.view(-1, 1)
             self._update_rms(r, m.ret_mean, m.ret_var, m.ret_count, self.rmean, self.rvar)
             ops.rms_apply_scalar(self.returns.view(-1), m.ret_mean, m.ret_var, denormalize=False)
+        self._bind_minibatch_arrays(batch)
         # :1021 num_invalids, kept on the device (lr scaling :788-794 happens inside the Adam kernel)
         if cfg.with_vtrace:
             ops.adv_stats(self.advantages.view(-1), self.valids_flat.view(-1), self.batch_stats, None, self.loss_ws)
             nv = self.batch_stats[ops.LS["num_valid"] : ops.LS["num_valid"] + 1]
             if self.world_size > 1:
                 self._allreduce(nv)
-            self.num_valid_dev.copy_(nv)
+            ops.copy_rows_bytes(nv.view(1, 1), self.num_valid_dev.view(1, 1))
         else:
             B = cfg.batch_size
-            adv_flat, val_flat = self.advantages.view(self.E), self.valids_flat.view(self.E)
+            adv_flat, val_flat = self._mb["adv"], self._mb["valids"]
             for b in range(cfg.num_batches_per_epoch):
                 ops.adv_stats(adv_flat[b * B : (b + 1) * B], val_flat[b * B : (b + 1) * B], self.batch_stats,
                               self.mb_partials[b], self.loss_ws)
@@ -362,25 +376,63 @@ class Learner:
                 self._allreduce(self.mb_partials)
             ops.colsum_f64(self.mb_partials, 0, self.num_valid_dev)                            # global valid count
 
+    def set_minibatch_permutation(self, indices) -> None:
+        """The sample order of the NEXT train() call (shuffle_minibatches): `indices` [E] as learner.py:498-526 builds them.
+        Without it every train() draws np.random.permutation over the recurrence-length chunks like the reference."""
+        assert self.shuffle
+        idx = np.asarray(indices, dtype=np.int64).reshape(-1)
+        assert idx.shape[0] == self.E and np.array_equal(np.sort(idx), np.arange(self.E))
+        self._next_perm = idx
+
+    def _upload_permutation(self) -> None:
+        """host side of the shuffle (outside any graph capture): draw / take the permutation, enqueue its H2D copy"""
+        if self._next_perm is not None:
+            idx, self._next_perm = self._next_perm, None
+        else:
+            c = self._perm_chunk
+            starts = np.random.permutation(np.arange(0, self.E, c))                   # :505-506
+            idx = (starts[:, None] + np.arange(c)[None, :]).reshape(-1)              # :509-510
+        self.perm_host.copy_(torch.from_numpy(idx.astype(np.int32)))
+        self.perm_dev.copy_(self.perm_host, non_blocking=True)
+
+    def _bind_minibatch_arrays(self, batch: Dict[str, Tensor]) -> None:
+        """flat [E, ...] views of everything a minibatch step reads; with shuffle_minibatches: gathered copies in the
+        permuted order (minibatch b is then rows [b*B, (b+1)*B) as usual)"""
+        spec, E = self.model.spec, self.E
+        src = dict(obs=self.obs_flat_compact, actions=batch["actions"].view(E, spec.action_width),
+                   lp_old=batch["log_prob_actions"].view(E, 1), logits_old=batch["action_logits"].view(E, spec.num_action_params),
+                   valids=self.valids_flat.view(E, 1), v_old=self.values_old.view(E, 1), adv=self.advantages.view(E, 1),
+                   ret=self.returns.view(E, 1), dones=batch["dones"].view(E, 1), rewards=batch["rewards"].view(E, 1))
+        if self.rnn is not None:
+            src["rnn"] = self.rnn_states_flat
+        if self.shuffle:
+            for k, v in src.items():
+                if k not in self._sh:
+                    self._sh[k] = torch.empty_like(v)
+                ops.gather_rows(v, self.perm_dev, self._sh[k])
+            src = self._sh
+        self._mb = {k: (v if k in ("obs", "actions", "logits_old", "rnn") else v.view(E)) for k, v in src.items()}
+
     # ------------------------------------------------------------------------------------------------------------
     def _minibatch_step(self, batch: Dict[str, Tensor], b: int, log_idx: int) -> None:
         cfg, m, spec = self.cfg, self.model, self.model.spec
         B = cfg.batch_size
         sl = slice(b * B, (b + 1) * B)                                                               # :521
+        loss_stats = self.loss_stats_log[log_idx]      # the kernels write this minibatch's statistics row in place
         A = spec.num_action_params
-        x0 = self.obs_flat_compact[sl]
-        actions = batch["actions"].view(self.E, spec.action_width)[sl]
+        mbv = self._mb
+        x0 = mbv["obs"][sl]
+        actions = mbv["actions"][sl]
         if not spec.continuous and not spec.action_segments:
             actions = actions.view(-1)
-        lp_old = batch["log_prob_actions"].view(self.E)[sl]
-        logits_old = batch["action_logits"].view(self.E, A)[sl]
-        valids = self.valids_flat.view(self.E)[sl]
-        v_old = self.values_old.view(self.E)[sl]
+        lp_old = mbv["lp_old"][sl]
+        logits_old = mbv["logits_old"][sl]
+        valids = mbv["valids"][sl]
+        v_old = mbv["v_old"][sl]
         # forward (:553-579)
         mb_rnn = None
         if self.rnn is not None:
-            mb_rnn = lambda head: self.rnn.forward_bptt(head, self.rnn_states_flat[sl], batch["dones"].view(self.E)[sl],
-                                                        valids, self.rnn_bufs)
+            mb_rnn = lambda head: self.rnn.forward_bptt(head, mbv["rnn"][sl], mbv["dones"][sl], valids, self.rnn_bufs)
         x = forward_policy(m, x0, self.h, self.act, self.engine, self.heads_plan,
                            dict(values=self.mb_values, values_stride=1, logits=self.mb_logits, logits_stride=A), mb_rnn,
                            store_tail=True)
@@ -393,41 +445,41 @@ class Learner:
                 ops.action_ratio_continuous(self.mb_logits, actions, lp_old, self.ratio)
             else:
                 ops.action_ratio(self.mb_logits, actions, lp_old, self.ratio)
-            ops.vtrace(self.ratio, self.mb_values, batch["rewards"].view(self.E)[sl], batch["dones"].view(self.E)[sl],
+            ops.vtrace(self.ratio, self.mb_values, mbv["rewards"][sl], mbv["dones"][sl],
                        cfg.recurrence, cfg.gamma, cfg.vtrace_rho, cfg.vtrace_c, self.vs, self.vt_adv)
             adv, targets = self.vt_adv, self.vs
         else:
-            adv, targets = self.advantages.view(self.E)[sl], self.returns.view(self.E)[sl]            # :643-644
+            adv, targets = mbv["adv"][sl], mbv["ret"][sl]                                              # :643-644
         # :646-647 advantage statistics (global under data parallelism)
         if not cfg.with_vtrace:
-            ops.adv_stats_finalize(self.mb_partials[b], self.loss_stats)       # partials taken in _prepare_batch
+            ops.adv_stats_finalize(self.mb_partials[b], loss_stats)       # partials taken in _prepare_batch
         elif self.world_size > 1:
-            ops.adv_stats(adv, valids, self.loss_stats, self.dp_partials, self.loss_ws)
+            ops.adv_stats(adv, valids, loss_stats, self.dp_partials, self.loss_ws)
             self._allreduce(self.dp_partials)
-            ops.adv_stats_finalize(self.dp_partials, self.loss_stats)
+            ops.adv_stats_finalize(self.dp_partials, loss_stats)
         else:
-            ops.adv_stats(adv, valids, self.loss_stats, None, self.loss_ws)
+            ops.adv_stats(adv, valids, loss_stats, None, self.loss_ws)
         # losses forward + backward (:651-657, :779)
         if spec.action_segments:
             ops.ppo_loss_fwd_bwd_tuple(self.mb_logits, self.mb_values, spec.action_segments, actions, lp_old, v_old, adv,
                                        targets, valids, logits_old, cfg.ppo_clip_ratio, cfg.ppo_clip_value,
                                        cfg.exploration_loss_coeff, cfg.value_loss_coeff, cfg.kl_loss_coeff, 1.0,
-                                       self.dlogits, self.dvalues, self.loss_stats, self.loss_ws,
+                                       self.dlogits, self.dvalues, loss_stats, self.loss_ws,
                                        exploration_loss=cfg.exploration_loss)
         elif spec.continuous:
             ops.ppo_loss_fwd_bwd_continuous(self.mb_logits, self.mb_values, spec.adaptive_stddev, spec.continuous_tanh_scale,
                                             actions, lp_old, v_old, adv, targets, valids, logits_old, cfg.ppo_clip_ratio,
                                             cfg.ppo_clip_value, cfg.exploration_loss_coeff, cfg.value_loss_coeff,
                                             cfg.kl_loss_coeff, 1.0, self.dlogits, self.dlogstd, self.dvalues,
-                                            self.loss_stats, self.loss_ws)
+                                            loss_stats, self.loss_ws)
             if self.dlogstd is not None:   # gradient of the learned log-stddev vector = column sum over the minibatch
                 ops.colsum(self.dlogstd, m.grads["action_parameterization.learned_stddev"], self.colsum_ws)
         else:
             ops.ppo_loss_fwd_bwd(self.mb_logits, self.mb_values, actions, lp_old, v_old, adv, targets, valids, logits_old,
                                  cfg.ppo_clip_ratio, cfg.ppo_clip_value, cfg.exploration_loss_coeff, cfg.value_loss_coeff,
-                                 cfg.kl_loss_coeff, 1.0, self.dlogits, self.dvalues, self.loss_stats, self.loss_ws,
+                                 cfg.kl_loss_coeff, 1.0, self.dlogits, self.dvalues, loss_stats, self.loss_ws,
                                  exploration_loss=cfg.exploration_loss)
-        self.loss_stats_log[log_idx].copy_(self.loss_stats)
+        self.loss_stats_log[log_idx].copy_(loss_stats)
         if self.heads_plan.separate:
             self._backward_separate(x0)
         else:
@@ -563,6 +615,8 @@ class Learner:
         if self.use_graph:
             return self._train_graphed(batch)
         launches0 = ops.launch_count()
+        if self.shuffle:
+            self._upload_permutation()
         self._prepare_batch(batch)
         recent_kls: List[float] = []
         prev_epoch_actor_loss = 1e9
@@ -621,6 +675,8 @@ class Learner:
         self.counters_dev.copy_(torch.tensor([self.opt_step, self.train_step], dtype=torch.int64), non_blocking=True)
         self.lr_dev.fill_(float(self.curr_lr))
         opt0, train0 = self.opt_step, self.train_step
+        if self.shuffle:
+            self._upload_permutation()           # (H2D copy enqueued in front of the graph; the gathers are captured)
         if self._graph_calls == 0:
             n0 = ops.launch_count()
             self._train_body(batch)
@@ -657,8 +713,12 @@ class Learner:
         fetch_stats() is asked for the policy lag."""
         bi = (n - 1) % self.cfg.num_batches_per_epoch          # position of the last minibatch inside its epoch
         sl = slice(bi * self.cfg.batch_size, (bi + 1) * self.cfg.batch_size)
-        self._lag = (batch["policy_version"].view(self.E)[sl].clone(), batch["policy_id"].view(self.E)[sl].clone(),
-                     self.train_step - 1)
+        if not hasattr(self, "_lag_pv"):
+            self._lag_pv = torch.empty(self.cfg.batch_size, dtype=torch.float32, device=self.device)
+            self._lag_pid = torch.empty(self.cfg.batch_size, dtype=torch.int32, device=self.device)
+        ops.copy_rows_bytes(batch["policy_version"].view(self.E)[sl].view(1, -1), self._lag_pv.view(1, -1))
+        ops.copy_rows_bytes(batch["policy_id"].view(self.E)[sl].view(1, -1), self._lag_pid.view(1, -1))
+        self._lag = (self._lag_pv, self._lag_pid, self.train_step - 1)
 
     def fetch_stats(self) -> Dict[str, float]:
         """Loss summaries of the LAST minibatch of the last train() (learner.py:843-923 keys). Host sync."""

@@ -356,7 +356,7 @@ def policy_mlp2_heads_forward(x: Tensor, W1: Tensor, b1: Tensor, W2: Tensor, b2:
     M, K1 = x.shape
     H1, H2, A = W1.shape[0], W2.shape[0], Wa.shape[0]
     assert Wv.is_contiguous() and Wa.is_contiguous() and Wv.numel() == H2 and Wa.shape[1] == H2
-    P = 2 * (H2 // 128)
+    P = 4 * (H2 // 128)
     assert head_partials.numel() >= P * M * HEAD_PART_PAD
     lib().call("sfb200_policy_mlp2_heads_forward", _p(x, F32), x.stride(0), M, K1, _p(W1, F32), _p(b1, F32), H1, _p(W2, F32),
                _p(b2, F32), H2, act, engine, _p(Wv, F32), _p(Wa, F32), A, _p(head_partials, F32), _stream())
@@ -462,17 +462,40 @@ def sampler_tail_tape_step(head_partials: Tensor, P: int, rows: int, bv: Tensor,
     """heads finish + sampling, the tape env's step, post-step(t) and pre-step(t+1) in ONE launch (csrc/heads.cu,
     sampler_tail_tape_kernel).  `env` is a sample_factory_b200.envs.TapeVecEnv (float32 obs, Discrete actions)."""
     A = ba.numel()
+    # (the trajectory slots [:, t] are strided columns: element strides are passed explicitly)
+    for t_ in (values, logits, actions_f32, log_prob, policy_version_out, traj_rewards, traj_dones, traj_time_outs, traj_policy_id):
+        assert t_.is_cuda
+    assert traj_dones.stride(0) == traj_rewards.stride(0) == traj_time_outs.stride(0) == traj_policy_id.stride(0)
+    assert values.dtype == F32 and logits.dtype == F32 and traj_rewards.dtype == F32 and traj_policy_id.dtype == I32
     lib().call("sfb200_sampler_tail_tape_step", _p(head_partials, F32), P, rows, A, _p(bv, F32), _p(ba, F32),
-               _p(values, F32), values_stride, _p(logits, F32), logits_stride, _p(noise, F32), philox_seed,
-               _p(sampler_step, I64), _p(actions_f32, F32), actions_stride, _p(env_actions, I32), _p(log_prob, F32),
-               log_prob_stride, _p(policy_version_scalar, F32), _p(policy_version_out, F32), pv_stride,
+               values.data_ptr(), values_stride, logits.data_ptr(), logits_stride, _p(noise, F32), philox_seed,
+               _p(sampler_step, I64), actions_f32.data_ptr(), actions_stride, _p(env_actions, I32), log_prob.data_ptr(),
+               log_prob_stride, _p(policy_version_scalar, F32), policy_version_out.data_ptr(), pv_stride,
                _p(env.tape, F32), env.tape_len, env.obs_dim, env.env_index_offset, env.term_period, env.trunc_period,
                _p(env.step_counter, I64), _p(env.obs, F32), _p(env.rew, F32), _p(env.terminated, U8), _p(env.truncated, U8),
-               reward_scale, reward_clip, policy_id, _p(traj_rewards, F32), _p(traj_dones, U8), _p(traj_time_outs, U8),
-               _p(traj_policy_id, I32), traj_rewards.stride(0), _p(ep_return, F32), _p(ep_len, I32), _p(ep_min_raw, F32),
-               _p(ep_max_raw, F32), len_increment, _p(stats, F64), _p(fin_return, F32), _p(fin_len, I32),
+               reward_scale, reward_clip, policy_id, traj_rewards.data_ptr(), traj_dones.data_ptr(), traj_time_outs.data_ptr(),
+               traj_policy_id.data_ptr(), traj_rewards.stride(0), _p(ep_return, F32), _p(ep_len, I32), _p(ep_min_raw, F32),
+               _p(ep_max_raw, F32), len_increment, _p(stats, F64), None if fin_return is None else fin_return.data_ptr(),
+               None if fin_len is None else fin_len.data_ptr(),
                _p(traj_obs_next, F32), traj_obs_next.stride(0), _p(rnn, F32), rnn.shape[1], _p(traj_rnn_next, F32),
                traj_rnn_next.stride(0), _p(x_norm, F32), _p(mean, F64), _p(var, F64), sub_mean, inv_scale, eps, clip, _stream())
+
+
+def gather_rows(src: Tensor, idx: Tensor, dst: Tensor) -> None:
+    """dst[r] = src[idx[r]] along dim 0 (dense rows of any dtype) -- the shuffled-minibatch gather"""
+    assert src.is_contiguous() and dst.is_contiguous() and src.dtype == dst.dtype and src.shape[1:] == dst.shape[1:]
+    assert idx.dtype == torch.int32 and idx.is_contiguous() and idx.numel() == dst.shape[0]
+    row_bytes = src.element_size() * (src.numel() // max(src.shape[0], 1))
+    lib().call("sfb200_gather_rows", src.data_ptr(), row_bytes, _p(idx, I32), dst.shape[0], dst.data_ptr(), _stream())
+
+
+def copy_rows_bytes(src: Tensor, dst: Tensor) -> None:
+    """dst[r, :] = src[r, :] for 2-D tensors of any (equal) dtype with dense rows and free row strides"""
+    assert src.dim() == 2 and dst.dim() == 2 and src.shape == dst.shape and src.dtype == dst.dtype
+    assert src.is_cuda and dst.is_cuda and (src.shape[1] == 1 or (src.stride(1) == 1 and dst.stride(1) == 1))
+    es = src.element_size()
+    lib().call("sfb200_copy_rows_bytes", src.data_ptr(), src.stride(0) * es, dst.data_ptr(), dst.stride(0) * es, src.shape[0],
+               src.shape[1] * es, _stream())
 
 
 def copy_rows(src: Tensor, dst: Tensor) -> None:

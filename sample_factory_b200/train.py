@@ -65,7 +65,7 @@ class Runner:
         self.total_train_seconds = 0.0
         self.policy_avg_stats: Dict[str, List[deque]] = {}
         self.policy_lag: List[Dict[str, float]] = [dict()]     # runner.py:132,289: version_diff_{min,avg,max} per policy
-        self.writers: Dict[int, object] = {}                   # runner.py: tensorboard writers (none: tensorboardX is absent)
+        self.writers: Dict[int, object] = {}                   # runner.py:199-205: one tensorboard SummaryWriter per policy
         self.observers: List = []
         self.msg_handlers: Dict[str, List[Callable]] = {}
         self.fps_history: deque = deque(maxlen=64)
@@ -172,6 +172,10 @@ class Runner:
         if self.rank == 0:
             with open(os.path.join(experiment_dir(cfg), "config.json"), "w") as f:
                 json.dump({k: v for k, v in vars(cfg).items() if _jsonable(v)}, f, indent=2)
+            from .tb_writer import SummaryWriter
+
+            # runner.py:199-205: <experiment_dir>/.summary/<policy_id>/events.out.tfevents.*
+            self.writers[0] = SummaryWriter(os.path.join(experiment_dir(cfg), ".summary", "0"))
         self.sampler.reset()
         self.initialized = True
         return StatusCode.SUCCESS
@@ -253,6 +257,32 @@ class Runner:
         self._join()
         self.env_steps = self.learner.env_steps
 
+    def _report_experiment_summaries(self, fps: float, train_stats: Dict[str, float]) -> None:
+        """runner.py:368-423 (+ the learner's train summaries, learner.py:843-923) as tensorboard scalars"""
+        w = self.writers.get(0)
+        if w is None:
+            return
+        steps = self.env_steps
+        if fps == fps:
+            w.add_scalar("perf/_fps", fps, steps)
+        for key, stat in self.policy_avg_stats.items():
+            vals = [v for v in stat[0] if isinstance(v, (int, float)) and v == v]
+            if not vals:
+                continue
+            if key in ("reward", "len"):
+                tag = f"{key}/{key}"
+                w.add_scalar(tag + "_min", float(min(vals)), steps)
+                w.add_scalar(tag + "_max", float(max(vals)), steps)
+            else:
+                tag = key if "/" in key else f"policy_stats/avg_{key}"
+            w.add_scalar(tag, float(sum(vals) / len(vals)), steps)
+        for key, val in train_stats.items():
+            if isinstance(val, (int, float)) and val == val:
+                w.add_scalar(f"train/{key}", float(val), steps)
+        for key, val in self.policy_lag[0].items():
+            w.add_scalar(f"train/{key}", float(val), steps)
+        w.flush()
+
     def _time_is_up(self, t_start: float) -> bool:
         """train_for_seconds.  Data parallel: a per-rank wall clock would let one rank leave the loop while the others
         enter the next collective, so the ranks decide together (max elapsed time, every 8th iteration)."""
@@ -291,6 +321,7 @@ class Runner:
                     for h in self.msg_handlers.get("episodic", []):
                         h(self, ep, 0)
                     if self.rank == 0:
+                        self._report_experiment_summaries(fps, st)
                         print(f"[sf_b200] env_steps {self.env_steps} fps {fps:.0f} loss {st.get('loss', float('nan')):.4f} "
                               f"reward {ep.get('reward', float('nan')):.3f} episodes {ep.get('episodes', 0)}", flush=True)
                     last_report, steps_at_report = now, self.env_steps
@@ -312,6 +343,8 @@ class Runner:
             save_checkpoint(cfg, self.model, self.learner)
             fps = self.env_steps / max(self.total_train_seconds, 1e-9)
             print(f"[sf_b200] Collected {{0: {self.env_steps}}}, FPS: {fps:.1f}", flush=True)   # runner.py:763-764
+            for w in self.writers.values():
+                w.close()
         return status
 
 

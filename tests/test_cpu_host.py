@@ -334,3 +334,19 @@ def test_enjoy_load_from_checkpoint_cli_overrides(tmp_path):
     assert loaded.gamma == 0.9 and loaded.batch_size == 4096 and loaded.encoder_mlp_layers == [64, 64]   # from the file
     assert loaded.eval_deterministic is True         # not in the file: from the current cfg
     assert loaded.max_num_episodes == cfg.max_num_episodes
+
+
+def test_tensorboard_event_writer_roundtrip(tmp_path):
+    """sample_factory_b200/tb_writer.py: TFRecord framing (masked crc32c) + hand-encoded Event protos read back intact"""
+    from sample_factory_b200.tb_writer import SummaryWriter, crc32c, read_scalars
+
+    assert crc32c(b"123456789") == 0xE3069283           # the CRC-32C check value
+    w = SummaryWriter(str(tmp_path))
+    w.add_scalar("perf/_fps", 40.4e6, 131072)
+    w.add_scalar("reward/reward", -1.5, 2 ** 40)
+    w.add_scalar("train/a_tag_longer_than_127_characters_" + "x" * 120, 3.0, 7)
+    w.close()
+    got = read_scalars(w.path)
+    assert got[0] == (131072, "perf/_fps", np.float32(40.4e6)) and got[1] == (2 ** 40, "reward/reward", -1.5)
+    assert got[2][0] == 7 and got[2][2] == 3.0 and len(got[2][1]) > 127
+    assert os.path.basename(w.path).startswith("events.out.tfevents.")

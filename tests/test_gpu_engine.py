@@ -518,3 +518,60 @@ def test_fused_policy_step_matches_separate_launches(explicit_noise, monkeypatch
         assert torch.equal(a[k], b[k]), k
     np.testing.assert_allclose(a["stats"].cpu().numpy(), b["stats"].cpu().numpy(), rtol=1e-12)
     assert torch.equal(a["ep"][0], b["ep"][0]) and torch.equal(a["ep"][1], b["ep"][1])
+
+
+@pytest.mark.parametrize("rnn", [False, True])
+@pytest.mark.parametrize("engine", ENGINES)
+def test_shuffle_minibatches_matches_oracle(engine, rnn):
+    """cfg.shuffle_minibatches (learner.py:498-526): the same permutation of recurrence-length chunks on both sides ->
+    same minibatches -> same losses and post-Adam weights; with a recurrent core the chunks keep their BPTT structure."""
+    from sample_factory_b200 import ops
+
+    _need(engine)
+    dev = torch.device("cuda", 0)
+    N, T = 64, 16
+    R = 8 if rnn else 1
+    kw = dict(use_rnn=True, rnn_type="gru", rnn_size=64, recurrence=R) if rnn else dict(recurrence=1)
+    ocfg = O.OracleCfg(obs_dim=24, num_actions=5, encoder_mlp_layers=[128, 128], rollout=T, batch_size=N * T // 4,
+                       num_batches_per_epoch=4, num_epochs=2, **kw)
+    st0 = O.init_state(ocfg, seed=2)
+    gen = torch.Generator().manual_seed(8)
+    tape = torch.randn(T + 1, N, ocfg.obs_dim, generator=gen)
+    cfg, model, traj, env, sampler, learner = build(ocfg, N, st0, tape, dev, engine=engine)
+    # (build() copies the oracle cfg; switch shuffling on in a fresh learner)
+    from sample_factory_b200.learner import Learner
+    cfg.shuffle_minibatches = True
+    learner = Learner(cfg, model, N, engine=ops.ENGINES[engine])
+    assert learner.shuffle
+    olearner = O.OracleLearner(ocfg, st0)
+    oenv = O.TapeVecEnv(tape, ocfg.num_actions)
+    otraj = O.alloc_trajectories(ocfg, N)
+    noise = torch.empty(T, N, ocfg.num_actions).exponential_(generator=gen)
+    O.rollout(ocfg, olearner.st, oenv, oenv.reset(), otraj, noise, 0)
+    otraj["policy_id"][torch.rand(N, T, generator=gen) < 0.1] = -1
+    for k, v in otraj.items():
+        if k in traj:
+            traj[k].copy_(v.view(traj[k].shape))
+    E = N * T
+    rng = np.random.RandomState(4)
+    starts = rng.permutation(np.arange(0, E, R))
+    perm = (starts[:, None] + np.arange(R)[None, :]).reshape(-1)
+    learner.set_minibatch_permutation(perm)
+    buff = olearner.train(otraj, mb_indices=torch.from_numpy(perm))
+    learner.train(traj)
+    log = learner.minibatch_log().numpy()
+    assert log.shape[0] == len(olearner.log) == 8
+    for j, d in enumerate(olearner.log):
+        for key in ["policy_loss", "value_loss", "exploration_loss", "kl_loss"]:
+            assert abs(log[j, ops.LS[key]] - d[key]) < TOL, (j, key, log[j, ops.LS[key]], d[key])
+        assert abs(log[j, ops.LS["adv_mean"]] - d["adv_mean"]) < TOL
+    sd = model.state_dict()
+    for k in O.param_names(ocfg):
+        np.testing.assert_allclose(sd[k].cpu().numpy(), olearner.st[k].numpy(), atol=2e-5, err_msg=k)
+    # without an explicit permutation every train() draws its own (np.random, like the reference)
+    np.random.seed(0)
+    learner.train(traj)
+    p1 = learner.perm_host.clone()
+    learner.train(traj)
+    assert not torch.equal(p1, learner.perm_host) and torch.equal(torch.sort(p1.long())[0], torch.arange(E))
+    assert torch.isfinite(model.flat).all()

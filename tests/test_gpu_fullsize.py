@@ -37,9 +37,12 @@ CASES = {
         obs_dim=4 * 84 * 84, obs_shape=(4, 84, 84), num_actions=6, encoder_conv_architecture="convnet_atari",
         encoder_conv_mlp_layers=[512], encoder_mlp_layers=[], nonlinearity="relu", obs_scale=255.0, rollout=8, recurrence=1,
         batch_size=512, num_batches_per_epoch=4, exploration_loss_coeff=0.01, max_grad_norm=0.5, adam_eps=1e-5),
-        # four SGD steps with adam_eps = 1e-5 on 1.7 M conv / FC weights: the few whose |g| ~ eps move by lr = 1e-4 per step in
-        # a direction a 1e-7 gradient difference decides (measured: 1 of 32768 conv2 weights off by 2.4e-5)
-        w_atol=6e-5),
+        # four SGD steps with adam_eps = 1e-5 on 1.7 M conv / FC weights: the few whose |g| ~ eps move by up to lr = 1e-4 per
+        # step in a direction a 1e-7 gradient difference decides (measured: 104 of 1 605 632 FC weights off by > 6e-5, max 1.5e-4)
+        w_atol=6e-5, w_frac=3e-4,
+        # (after ONE step the first moments agree to 1.4e-7 / 7.7e-4 relative, tools/conv_grad_check.py; the amplified weight
+        # differences feed back into the gradients of steps 2-4)
+        m_atol=2e-5),
     # configs[4]: Box(256), MLP 512-256-128 -> LSTM-512, rollout = recurrence = 16, value bootstrap (one GPU's shard, 1024 envs)
     "cfg5_lstm_1024x16": dict(N=1024, T=16, iters=1, ocfg=dict(
         obs_dim=256, encoder_mlp_layers=[512, 256, 128], use_rnn=True, rnn_type="lstm", rnn_size=512, rollout=16, recurrence=16,
@@ -117,8 +120,19 @@ def test_full_size_parity_vs_oracle(name):
             gn = learner.grad_norm_log[j].item()
             assert abs(gn - d["grad_norm"]) <= 5e-4 * max(1.0, abs(d["grad_norm"])), (j, gn, d["grad_norm"])
         sd = model.state_dict()
+        n_sgd = len(olearner.log) - n0
         for k in O.param_names(ocfg):
-            np.testing.assert_allclose(sd[k].cpu().numpy(), olearner.st[k].numpy(), atol=case.get("w_atol", 2e-5), err_msg=f"{name} {k}")
+            # Adam's first moment is linear in the gradients of the SGD steps: the well-conditioned check of the backward pass
+            off, shp = model._slices[k]
+            m_dev = model.exp_avg[off: off + int(np.prod(shp))].view(shp).cpu().numpy()
+            np.testing.assert_allclose(m_dev, olearner.m[k].numpy(), atol=case.get("m_atol", 2e-6), err_msg=f"{name} exp_avg {k}")
+            # the weights themselves: lr * m / (sqrt(v) + eps) amplifies a 1e-7 gradient difference where |g| ~ adam_eps (dead
+            # ReLU units, saturated inputs) up to a full lr-sized step, so: all but a vanishing fraction within w_atol, and
+            # nobody further away than the n_sgd * lr such elements can move
+            d = np.abs(sd[k].cpu().numpy() - olearner.st[k].numpy())
+            frac = float((d > case.get("w_atol", 2e-5)).mean())
+            assert frac < case.get("w_frac", 0.0) + 1e-12, (name, k, frac, float(d.max()))
+            assert float(d.max()) < n_sgd * ocfg.learning_rate * 1.05 + 2e-5, (name, k, float(d.max()))
         for k in (O.OBS_MEAN, O.OBS_VAR):
             np.testing.assert_allclose(sd[k].cpu().numpy().reshape(-1), olearner.st[k].numpy().reshape(-1), rtol=1e-6, atol=1e-6)
         # keep the two closed loops on identical weights for the next iteration (differences stay at rounding level anyway)
