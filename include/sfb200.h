@@ -202,6 +202,35 @@ int sfb200_sampler_tail_tape_step(const float* head_partials, int P, int64_t n_e
                                   const float* rnn, int rnn_dim, float* traj_rnn_next, int64_t traj_rnn_stride, float* x_norm,
                                   const double* mean, const double* var, float sub_mean, float inv_scale, float eps,
                                   float clip, void* stream);
+/* A WHOLE ROLLOUT of a two-layer MLP policy over the synthetic tape env as one persistent kernel (csrc/rollout_fused.cu):
+ * T x { layer 1, layer 2 + head partials, sfb200_sampler_tail_tape_step } with thread-block clusters of H2/128 CTAs owning a
+ * 128-env row block for all T steps (cluster barriers only; no kernel boundary inside the rollout).  Replaces, per rollout,
+ * T x (sfb200_linear_act_forward + sfb200_linear_act_heads_forward + sfb200_sampler_tail_tape_step); the caller runs
+ * sfb200_sampler_pre_step for step 0 first (x_norm holds the normalised step-0 observations).  Pointers with suffix _0 are
+ * the trajectory slots of step 0 ([:, 0]); step t is at + t elements (x A for logits, x dim for traj_obs / rnn rows).
+ *   P = sfb200_rollout_mlp2_partials(...)   0 -> not covered (3xTF32 engine, K1 in {32,64,96,128}, H1 == H2 in {128,256,512},
+ *       A <= 8, both weight matrices inside a registered tf32-lo buffer); head_partials: P * n_envs * 12 floats,
+ *       h1_scratch: n_envs * H1 floats. */
+int sfb200_rollout_mlp2_partials(const float* W1, const float* W2, int K1, int H1, int H2, int A, int engine);
+/* debug aid: device buffer of T x 12 uint64 that the following rollouts fill with %globaltimer stamps of one CTA's phases
+ * (tools/rollout_trace.py); NULL switches it off */
+int sfb200_rollout_set_trace(void* trace_dev);
+int sfb200_rollout_mlp2_tape(int64_t n_envs, int T, int K1, const float* W1, const float* b1, int H1, const float* W2,
+                             const float* b2, int H2, int act, int engine, const float* Wv, const float* bv, const float* Wa,
+                             const float* ba, int A, float* h1_scratch, float* head_partials, float* x_norm,
+                             float* values_0, int64_t values_stride, float* logits_0, int64_t logits_stride,
+                             const float* noise, uint64_t philox_seed, int64_t* sampler_step, float* actions_0,
+                             int64_t actions_stride, int32_t* env_actions, float* log_prob_0, int64_t log_prob_stride,
+                             const float* policy_version_scalar, float* policy_version_0, int64_t pv_stride,
+                             const float* tape, int64_t tape_len, int64_t env_index_offset, int term_period, int trunc_period,
+                             int64_t* env_step_counter, float* env_obs, float* env_rew, uint8_t* env_terminated,
+                             uint8_t* env_truncated, float reward_scale, float reward_clip, int32_t policy_id,
+                             float* traj_rewards_0, uint8_t* traj_dones_0, uint8_t* traj_time_outs_0, int32_t* traj_policy_id_0,
+                             int64_t traj_stride, float* ep_return, int32_t* ep_len, float* ep_min_raw, float* ep_max_raw,
+                             int32_t len_increment, double* stats, float* fin_return_0, int32_t* fin_len_0, float* traj_obs_0,
+                             int64_t traj_obs_stride, const float* rnn, int rnn_dim, float* traj_rnn_0, int64_t traj_rnn_stride,
+                             const double* mean, const double* var, float sub_mean, float inv_scale, float eps, float clip,
+                             void* stream);
 /* The whole policy forward of a two-layer MLP (model/encoder.py:72-91 MlpEncoder + actor_critic.py:171-186) up to the head
  * partials in ONE tcgen05 kernel: h1 = act(x W1^T + b1) is produced chunk by chunk in tensor memory and consumed by the
  * layer-2 MMAs without ever reaching shared or global memory; h2 = act(h1 W2^T + b2) is contracted with [Wv ; Wa] in the

@@ -651,8 +651,8 @@ class Learner:
                     break
                 prev_epoch_actor_loss = new_loss
         self.num_minibatches_done = log_idx
-        self._snapshot_policy_lag(batch, log_idx)
         self.kernel_launches = ops.launch_count() - launches0   # counted by the library itself
+        self._snapshot_policy_lag(batch, log_idx)
         self.env_steps += self.E * self.world_size * (cfg.env_frameskip if cfg.summaries_use_frameskip else 1)
         return dict(env_steps=self.env_steps, train_step=self.train_step)
 

@@ -481,6 +481,47 @@ def sampler_tail_tape_step(head_partials: Tensor, P: int, rows: int, bv: Tensor,
                traj_rnn_next.stride(0), _p(x_norm, F32), _p(mean, F64), _p(var, F64), sub_mean, inv_scale, eps, clip, _stream())
 
 
+def rollout_mlp2_partials(W1: Tensor, W2: Tensor, A: int, engine: int) -> int:
+    """head partials per row of the persistent whole-rollout kernel, 0 when the model is not covered"""
+    H1, K1 = W1.shape
+    H2 = W2.shape[0]
+    if W2.shape[1] != H1 or not (W1.is_contiguous() and W2.is_contiguous()):
+        return 0
+    return lib().query("sfb200_rollout_mlp2_partials", _p(W1, F32), _p(W2, F32), K1, H1, H2, A, engine)
+
+
+def rollout_mlp2_tape(T: int, W1: Tensor, b1: Tensor, W2: Tensor, b2: Tensor, act: int, engine: int, Wv: Tensor, bv: Tensor,
+                      Wa: Tensor, ba: Tensor, h1_scratch: Tensor, head_partials: Tensor, x_norm: Tensor, traj, env,
+                      noise: Optional[Tensor], philox_seed: int, sampler_step: Tensor, env_actions: Tensor,
+                      policy_version_scalar: Tensor, reward_scale: float, reward_clip: float, policy_id: int,
+                      ep_return: Tensor, ep_len: Tensor, ep_min_raw: Tensor, ep_max_raw: Tensor, len_increment: int,
+                      stats: Tensor, fin_return: Optional[Tensor], fin_len: Optional[Tensor], rnn: Tensor,
+                      mean: Optional[Tensor], var: Optional[Tensor], sub_mean: float, inv_scale: float, eps: float = 1e-5,
+                      clip: float = 5.0) -> None:
+    """One launch = a whole rollout (csrc/rollout_fused.cu).  `traj` is the trajectory dict ([N, T(+1), ...] tensors), `env` a
+    sample_factory_b200.envs.TapeVecEnv; x_norm must hold the normalised observations of step 0 (sampler_pre_step)."""
+    N, K1 = x_norm.shape
+    H1, H2, A = W1.shape[0], W2.shape[0], ba.numel()
+    tr = traj
+    assert tr["rewards"].shape == (N, T) and tr["obs"].shape[1] == T + 1 and h1_scratch.shape[0] >= N and h1_scratch.shape[1] == H1
+    assert all(tr[k].is_contiguous() for k in ("values", "action_logits", "actions", "log_prob_actions", "policy_version",
+                                              "rewards", "dones", "time_outs", "policy_id", "obs", "rnn_states"))
+    lib().call("sfb200_rollout_mlp2_tape", N, T, K1, _p(W1, F32), _p(b1, F32), H1, _p(W2, F32), _p(b2, F32), H2, act, engine,
+               _p(Wv, F32), _p(bv, F32), _p(Wa, F32), _p(ba, F32), A, _p(h1_scratch, F32), _p(head_partials, F32), _p(x_norm, F32),
+               tr["values"].data_ptr(), tr["values"].stride(0), tr["action_logits"].data_ptr(), tr["action_logits"].stride(0),
+               _p(noise, F32), philox_seed, _p(sampler_step, I64), tr["actions"].data_ptr(), tr["actions"].stride(0),
+               _p(env_actions, I32), tr["log_prob_actions"].data_ptr(), tr["log_prob_actions"].stride(0),
+               _p(policy_version_scalar, F32), tr["policy_version"].data_ptr(), tr["policy_version"].stride(0),
+               _p(env.tape, F32), env.tape_len, env.env_index_offset, env.term_period, env.trunc_period,
+               _p(env.step_counter, I64), _p(env.obs, F32), _p(env.rew, F32), _p(env.terminated, U8), _p(env.truncated, U8),
+               reward_scale, reward_clip, policy_id, tr["rewards"].data_ptr(), tr["dones"].data_ptr(), tr["time_outs"].data_ptr(),
+               tr["policy_id"].data_ptr(), tr["rewards"].stride(0), _p(ep_return, F32), _p(ep_len, I32), _p(ep_min_raw, F32),
+               _p(ep_max_raw, F32), len_increment, _p(stats, F64), None if fin_return is None else fin_return.data_ptr(),
+               None if fin_len is None else fin_len.data_ptr(), tr["obs"].data_ptr(), tr["obs"].stride(0), _p(rnn, F32),
+               rnn.shape[1], tr["rnn_states"].data_ptr(), tr["rnn_states"].stride(0), _p(mean, F64), _p(var, F64), sub_mean,
+               inv_scale, eps, clip, _stream())
+
+
 def gather_rows(src: Tensor, idx: Tensor, dst: Tensor) -> None:
     """dst[r] = src[idx[r]] along dim 0 (dense rows of any dtype) -- the shuffled-minibatch gather"""
     assert src.is_contiguous() and dst.is_contiguous() and src.dtype == dst.dtype and src.shape[1:] == dst.shape[1:]

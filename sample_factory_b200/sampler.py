@@ -106,6 +106,14 @@ class DeviceSampler:
                            not env.obs_uint8 and self.rnn is None and self.heads_plan.P > 0 and
                            not self.heads_plan.finish_in_gemm and not self.heads_plan.separate and
                            not spec.continuous and not spec.action_segments)
+        # Whole rollout as ONE persistent kernel (csrc/rollout_fused.cu): clusters of H2/128 CTAs own a 128-env row block for
+        # all T steps.  Same conditions as the fused tail plus a two-layer MLP the kernel covers.  SFB200_ROLLOUT_FUSED=0
+        # restores the per-step launches.
+        self.fused_rollout = False
+        if (self.fused_tail and os.environ.get("SFB200_ROLLOUT_FUSED", "1") != "0" and not deterministic and
+                len(spec.fc_encoder_layers) == 2 and not spec.decoder_mlp_layers and self.heads_plan.conv is None):
+            (W1, _), (W2, _) = model.encoder_layers()
+            self.fused_rollout = ops.rollout_mlp2_partials(W1, W2, spec.num_linear_action_outputs, engine) == self.heads_plan.P
 
     # ------------------------------------------------------------------------------------------------------------
     def _take_obs(self, obs):
@@ -242,11 +250,29 @@ class DeviceSampler:
             tr["obs"][:, self.T].copy_(self.last_obs)                            # uint8 frames (recurrent path only)
         ops.copy_rows(self.last_rnn_state, tr["rnn_states"][:, self.T])          # :293
 
+    def _rollout_persistent(self) -> None:
+        """pre-step(0) + ONE kernel for the T steps of the rollout"""
+        cfg, m, spec = self.cfg, self.model, self.model.spec
+        (W1, b1), (W2, b2) = m.encoder_layers()
+        Wv, bv = m.critic
+        Wa, ba = m.actor
+        assert self.noise is None or (self.noise.is_contiguous() and self.noise.shape[0] >= self.T)
+        ops.rollout_mlp2_tape(
+            self.T, W1, b1, W2, b2, self.act, self.engine, Wv, bv, Wa, ba, self.h[0], self.heads_plan.part, self.x_norm,
+            self.traj, self.env, self.noise, self.philox_seed, self.step_counter, self.env_actions, self.policy_version,
+            cfg.reward_scale, cfg.reward_clip, cfg.policy_id, self.ep_return, self.ep_len, self.ep_min_raw, self.ep_max_raw,
+            cfg.env_frameskip if cfg.summaries_use_frameskip else 1, self.episode_stats, self.fin_return, self.fin_len,
+            self.last_rnn_state, m.obs_mean if spec.normalize_input else None, m.obs_var if spec.normalize_input else None,
+            spec.obs_subtract_mean, 1.0 / spec.obs_scale)
+
     def _rollout_eager(self) -> None:
         n0 = ops.launch_count()
         self._pre_step(0)
-        for t in range(self.T):
-            self.advance_rollouts(t)
+        if self.fused_rollout and self.action_mask is None and self.last_obs is self.env.obs:
+            self._rollout_persistent()
+        else:
+            for t in range(self.T):
+                self.advance_rollouts(t)
         self.kernel_launches_per_rollout = ops.launch_count() - n0   # counted by the library itself
 
     def rollout(self) -> None:

@@ -487,11 +487,13 @@ def test_fused_policy_step_matches_separate_launches(explicit_noise, monkeypatch
     tape = torch.randn(2 * T + 1, N, ocfg.obs_dim, generator=gen)
     noise = torch.empty(T, N, ocfg.num_actions).exponential_(generator=gen).to(dev)
     runs = {}
-    for mode in ("separate", "fused"):
-        monkeypatch.setenv("SFB200_TAIL_FUSED", "1" if mode == "fused" else "0")
+    for mode in ("separate", "fused", "persistent"):
+        monkeypatch.setenv("SFB200_TAIL_FUSED", "0" if mode == "separate" else "1")
         monkeypatch.setenv("SFB200_POLICY_FUSED", "1" if mode == "fused" else "0")
+        monkeypatch.setenv("SFB200_ROLLOUT_FUSED", "1" if mode == "persistent" else "0")
         cfg, model, traj, env, sampler, learner = build(ocfg, N, st0, tape, dev, engine="3xtf32")
-        assert sampler.fused_tail == (mode == "fused") and sampler.heads_plan.mlp2 == (mode == "fused")
+        assert sampler.fused_tail == (mode != "separate") and sampler.heads_plan.mlp2 == (mode == "fused")
+        assert sampler.fused_rollout == (mode == "persistent")
         sampler.reset()
         out = []
         for it in range(2):
@@ -505,17 +507,22 @@ def test_fused_policy_step_matches_separate_launches(explicit_noise, monkeypatch
                           term=env.terminated.clone(), step=env.step_counter.clone(), pstep=sampler.step_counter.clone(),
                           stats=sampler.episode_stats.clone(), ep=(sampler.ep_return.clone(), sampler.ep_len.clone()),
                           launches=sampler.kernel_launches_per_rollout)
-    a, b = runs["separate"], runs["fused"]
     # (the test-suite runs with SFB200_CHECK_LO=1: two extra verification launches per fused GEMM call)
-    assert b["launches"] in (1 + 2 * T, 1 + 4 * T) and a["launches"] > b["launches"], (a["launches"], b["launches"])
+    assert runs["fused"]["launches"] in (1 + 2 * T, 1 + 4 * T) and runs["separate"]["launches"] > runs["fused"]["launches"]
+    assert runs["persistent"]["launches"] in (2, 4), runs["persistent"]["launches"]     # pre-step(0) + ONE kernel for T steps
+    for other in ("fused", "persistent"):
+        _compare_rollout_runs(runs["separate"], runs[other], other)
+
+
+def _compare_rollout_runs(a, b, what):
     for ta, tb in zip(a["traj"], b["traj"]):
         for k in ta:
             if k in ("action_logits", "values", "log_prob_actions"):
-                np.testing.assert_allclose(ta[k].cpu().numpy(), tb[k].cpu().numpy(), rtol=0, atol=2e-6, err_msg=k)
+                np.testing.assert_allclose(ta[k].cpu().numpy(), tb[k].cpu().numpy(), rtol=0, atol=2e-6, err_msg=f"{what} {k}")
             elif k != "valids":
-                assert torch.equal(ta[k], tb[k]), k
-    for k in ("x_norm", "obs", "rew", "term", "step", "pstep"):
-        assert torch.equal(a[k], b[k]), k
+                assert torch.equal(ta[k], tb[k]), (what, k)
+    for k in ("obs", "rew", "term", "step", "pstep"):
+        assert torch.equal(a[k], b[k]), (what, k)
     np.testing.assert_allclose(a["stats"].cpu().numpy(), b["stats"].cpu().numpy(), rtol=1e-12)
     assert torch.equal(a["ep"][0], b["ep"][0]) and torch.equal(a["ep"][1], b["ep"][1])
 

@@ -42,7 +42,7 @@ CASES = {
         w_atol=6e-5, w_frac=3e-4,
         # (after ONE step the first moments agree to 1.4e-7 / 7.7e-4 relative, tools/conv_grad_check.py; the amplified weight
         # differences feed back into the gradients of steps 2-4)
-        m_atol=2e-5),
+        m_atol=5e-5),
     # configs[4]: Box(256), MLP 512-256-128 -> LSTM-512, rollout = recurrence = 16, value bootstrap (one GPU's shard, 1024 envs)
     "cfg5_lstm_1024x16": dict(N=1024, T=16, iters=1, ocfg=dict(
         obs_dim=256, encoder_mlp_layers=[512, 256, 128], use_rnn=True, rnn_type="lstm", rnn_size=512, rollout=16, recurrence=16,
