@@ -212,7 +212,7 @@ int sfb200_sampler_tail_tape_step(const float* head_partials, int P, int64_t n_e
  *       A <= 8, both weight matrices inside a registered tf32-lo buffer); head_partials: P * n_envs * 12 floats,
  *       h1_scratch: n_envs * H1 floats. */
 int sfb200_rollout_mlp2_partials(const float* W1, const float* W2, int K1, int H1, int H2, int A, int engine);
-/* debug aid: device buffer of T x 12 uint64 that the following rollouts fill with %globaltimer stamps of one CTA's phases
+/* debug aid: device buffer of T x 16 uint64 that the following rollouts fill with %globaltimer stamps of one CTA's phases
  * (tools/rollout_trace.py); NULL switches it off */
 int sfb200_rollout_set_trace(void* trace_dev);
 int sfb200_rollout_mlp2_tape(int64_t n_envs, int T, int K1, const float* W1, const float* b1, int H1, const float* W2,

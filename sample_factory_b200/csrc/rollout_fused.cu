@@ -18,7 +18,7 @@
 //
 //   warp 0      TMA producer            warp 1      MMA issuer (+ TMEM allocation)
 //   warps 2-5   operand warps           warps 6-13  epilogues (h1 tile store; h2 -> head partials)
-//   warps 2-13  the step tail (three rows per warp and pass, all loads first)
+//   warps 6-13  the step tail (an 8-lane group per row: four rows per warp, the CTA's 32 rows in one pass)
 #include <cuda.h>
 
 #include "common.cuh"
@@ -63,7 +63,7 @@ struct RolloutArgs {
     float* traj_obs; int64_t traj_obs_rs; const float* rnn; int rnn_dim; float* traj_rnn; int64_t traj_rnn_rs;
     const double* mean; const double* var; float sub, inv_scale; int do_sub, do_scale; float eps, clip;
     unsigned int* ticket;
-    unsigned long long* trace;   // debug: [T][12] globaltimer stamps of CTA (0,0)'s first epilogue thread, or NULL
+    unsigned long long* trace;   // debug: [T][16] globaltimer stamps of CTA (0,0)'s first epilogue thread, or NULL
 };
 
 __device__ __forceinline__ void cluster_sync_all() {
@@ -128,7 +128,12 @@ rollout_mlp2_tape_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
     float* headw_s = reinterpret_cast<float*>(smem + S::OFF_HEADW);   // [9][128]
     float* cstat = reinterpret_cast<float*>(smem + S::OFF_CSTAT);     // [2][K1]: mu, 1 / sigma of the observation normaliser
 
+    // episode statistics of finished episodes: accumulated per CTA over the WHOLE rollout in shared memory, five global
+    // atomics per CTA at the end (the per-step launches issue them per finished episode: ~370 per step on five addresses --
+    // inside this kernel every cluster barrier's release would have to wait for those same-address atomics to drain)
+    __shared__ double s_stats[5];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x < 5) s_stats[threadIdx.x] = 0.0;
     const int cx = (int)cluster_ctarank();           // == blockIdx.x (cluster spans the x dimension)
     const int CX = gridDim.x;
     const int n0 = cx * 128;
@@ -178,7 +183,7 @@ rollout_mlp2_tape_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
 
     int pref = 0;             // producer: stages of the current tile already armed + weight tiles requested
     const bool tracer = a.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 192;
-#define RF_TRACE(slot) do { if (tracer) a.trace[(int64_t)t * 12 + (slot)] = rf_now(); } while (0)
+#define RF_TRACE(slot) do { if (tracer) a.trace[(int64_t)t * 16 + (slot)] = rf_now(); } while (0)
     uint32_t it = 0;          // stage use counter (every role advances it identically)
     uint32_t tile_iter = 0;   // accumulator use counter
 
@@ -302,6 +307,7 @@ rollout_mlp2_tape_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
                 const float* bias = (layer == 0 ? b1_s : b2_s) + half * 64;
 #pragma unroll
                 for (int j = 0; j < 64; ++j) o[j] = act_fwd_ct<ACT>(o[j] + bias[j]);
+                RF_TRACE(11 + layer);             // bias + activation done
                 const int64_t m = m0 + quad * 32 + lane;
                 if (m < a.N) {
                     if (layer == 0) {
@@ -324,6 +330,7 @@ rollout_mlp2_tape_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
                             }
                             hp[r] = s0 + s1;
                         }
+                        RF_TRACE(13);             // head partial dot products done
                         float4* dst = reinterpret_cast<float4*>(a.part + ((int64_t)(cx * 2 + half) * a.N + m) * kHeadPartPad);
                         dst[0] = make_float4(hp[0], hp[1], hp[2], hp[3]);
                         dst[1] = make_float4(hp[4], hp[5], hp[6], hp[7]);
@@ -339,97 +346,142 @@ rollout_mlp2_tape_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
             RF_TRACE(4 + 4 * layer);              // past the cluster barrier
         }
 
-        // ===================================================== step tail: this CTA's share of the block's rows (warps 2-13).
-        // A warp takes three rows per pass and issues ALL their loads (head partials, next observation, episode accumulators)
-        // before the per-row math: the rows' L2 / HBM latencies overlap instead of adding up.
-        if (warp >= 2) {
-            const int e = warp - 2;                       // 0..11
+        // ===================================================== step tail: this CTA's share of the block's rows.
+        // FOUR rows per warp at a time: an 8-lane group owns a row (one lane per action logit, the group leader also the value
+        // and the env's scalars), so the 32 rows of a CTA are ONE pass of eight warps -- the per-row dependency chain (partial
+        // sums from L2 -> softmax -> Philox -> argmax -> env rule -> stores, ~4.7 us measured) is paid once per step, not once
+        // per row a warp owns.  Bit-identical to heads_row_tail: logit a sits at group position (a + 1) % 8, which reproduces
+        // the association order of the 32-lane butterfly sums there (lanes 1..8 after the xor-16 / xor-8 steps).
+        if (warp >= 6) {
+            const int g = lane & 7;                       // position inside the 8-lane group
+            const int grp = lane >> 3;                    // which of the warp's four rows
+            const int act_idx = (g + 7) & 7;              // action index held by this lane (position (a + 1) % 8)
+            const bool has_logit = act_idx < a.A;
+            const bool leader = g == 0;
             const bool last = (t + 1 == a.T);
             const int64_t step = env_step0 + t;
             const uint64_t offset = philox0 + (uint64_t)t;
             const float* src_step = a.tape + ((step + 1) % a.tape_len) * a.N * a.K1;
-            HeadsOut out{a.values + t, a.values_rs, a.logits + (int64_t)t * a.A, a.logits_rs, a.actions + t, a.actions_rs,
-                         a.env_actions, a.log_prob + t, a.lp_rs, a.pv_out + t, a.pv_rs, 0, 0, nullptr, 0.f, nullptr};
             const float* noise_t = a.noise ? a.noise + (int64_t)t * a.N * a.A : nullptr;
-            const float my_bias = (lane == 0) ? a.bv[0] : (lane <= a.A ? a.ba[lane - 1] : 0.f);
             const int rpc = 128 / CX;                     // rows of the block this CTA finishes
-            constexpr int RPW = 3;
-            for (int base = 0; base < rpc; base += 12 * RPW) {
-                int64_t rows_[RPW];
-                bool ok[RPW];
-                float mine[RPW], v[RPW][4], er0[RPW], mn0[RPW], mx0[RPW];
-                int32_t el0[RPW];
+            const unsigned gmask = 0xffu << (grp * 8);
+            for (int base = 0; base < rpc; base += 32) {
+                const int rr = base + (warp - 6) * 4 + grp;
+                const int64_t row = m0 + cx * rpc + rr;
+                const bool ok = rr < rpc && row < a.N;
+                // ---- loads first: head partials, next observation (K1 / 8 floats per lane), episode accumulators
+                float x = 0.f, val = 0.f;
+                float ob[RF_MAX_DIM / 8];
+                float er0 = 0.f, mn0 = 0.f, mx0 = 0.f;
+                int32_t el0 = 0;
+                const int cpl = a.K1 >> 3;                // observation columns per lane (K1 is a multiple of 32)
+                if (ok) {
+                    if (has_logit)
+                        for (int p = 0; p < P; ++p) x += a.part[((int64_t)p * a.N + row) * kHeadPartPad + 1 + act_idx];
+                    if (leader)
+                        for (int p = 0; p < P; ++p) val += a.part[((int64_t)p * a.N + row) * kHeadPartPad];
+                    const float4* src4 = reinterpret_cast<const float4*>(src_step + row * a.K1 + g * cpl);
 #pragma unroll
-                for (int k = 0; k < RPW; ++k) {
-                    const int rr = base + e + 12 * k;
-                    rows_[k] = m0 + cx * rpc + rr;
-                    ok[k] = rr < rpc && rows_[k] < a.N;
-                    mine[k] = 0.f; er0[k] = mn0[k] = mx0[k] = 0.f; el0[k] = 0;
-                    v[k][0] = v[k][1] = v[k][2] = v[k][3] = 0.f;
-                    if (ok[k]) {
-                        const int64_t row = rows_[k];
-                        if (lane <= a.A)
-                            for (int p = 0; p < P; ++p) mine[k] += a.part[((int64_t)p * a.N + row) * kHeadPartPad + lane];
-                        const float* src = src_step + row * a.K1;
-                        if (lane < a.K1) v[k][0] = src[lane];
-                        if (lane + 32 < a.K1) v[k][1] = src[lane + 32];
-                        if (lane + 64 < a.K1) v[k][2] = src[lane + 64];
-                        if (lane + 96 < a.K1) v[k][3] = src[lane + 96];
-                        if (lane == 0 && a.ep_ret) { er0[k] = a.ep_ret[row]; el0[k] = a.ep_len[row]; mn0[k] = a.ep_min[row]; mx0[k] = a.ep_max[row]; }
+                    for (int q = 0; q < RF_MAX_DIM / 32; ++q)
+                        if (4 * q < cpl) {
+                            const float4 f4 = src4[q];
+                            ob[4 * q] = f4.x; ob[4 * q + 1] = f4.y; ob[4 * q + 2] = f4.z; ob[4 * q + 3] = f4.w;
+                        }
+                    if (leader && a.ep_ret) { er0 = a.ep_ret[row]; el0 = a.ep_len[row]; mn0 = a.ep_min[row]; mx0 = a.ep_max[row]; }
+                }
+                // ---- CategoricalActionDistribution on the group (action_distributions.py:110-148), as heads_row_tail
+                x += has_logit ? a.ba[act_idx] : 0.f;
+                val += a.bv[0];
+                const float xl = has_logit ? x : -INFINITY;
+                float m = xl;
+#pragma unroll
+                for (int o = 4; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+                const float ex = has_logit ? expf(xl - m) : 0.f;
+                float ssum = ex;
+#pragma unroll
+                for (int o = 4; o > 0; o >>= 1) ssum += __shfl_xor_sync(0xffffffffu, ssum, o);
+                const float pr = __fdiv_rn(ex, ssum);                       // softmax :116
+                const float logp = (xl - m) - logf(ssum);                   // log_softmax :125
+                float q = 1.f;
+                if (ok && has_logit) {
+                    if (noise_t) q = noise_t[row * a.A + act_idx];
+                    else {
+                        curandStatePhilox4_32_10_t st;
+                        curand_init(a.seed, (unsigned long long)(row * a.A + act_idx), offset, &st);
+                        q = fmaxf(-logf(curand_uniform(&st)), 1.0e-30f);    // Exp(1)
                     }
                 }
+                float best = has_logit ? __fdiv_rn(pr, q) : -INFINITY;      // multinomial == argmax(p / q), first index on ties
+                int idx = has_logit ? act_idx : 0x7fffffff;
 #pragma unroll
-                for (int k = 0; k < RPW; ++k) {
-                    if (!ok[k]) continue;                 // (warp-uniform)
-                    const int64_t row = rows_[k];
-                    const int act = heads_row_tail(mine[k] + my_bias, lane, a.A, row, out, noise_t, a.seed, offset, pv);
-                    const int64_t env = a.env_off + row;
-                    const float r_raw = (float)act / (float)a.A;
-                    const bool tm = ((step * 7 + env * 13) % a.term_period) == 0;
-                    const bool tr = (((step + env) % a.trunc_period) == 0) && !tm;
-                    float* obs_next = a.traj_obs + row * a.traj_obs_rs + (int64_t)(t + 1) * a.K1;
+                for (int o = 4; o > 0; o >>= 1) {
+                    const float ob_ = __shfl_xor_sync(0xffffffffu, best, o);
+                    const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+                    if (ob_ > best || (ob_ == best && oi < idx)) { best = ob_; idx = oi; }
+                }
+                const float lp = __shfl_sync(0xffffffffu, logp, (grp << 3) | ((idx + 1) & 7));   // log_prob :145-148
+                (void)gmask;
+                if (!ok) continue;
+                // ---- trajectory slot t, env step, post step, pre step of t + 1
+                if (has_logit) a.logits[row * a.logits_rs + (int64_t)t * a.A + act_idx] = x;
+                const int64_t env = a.env_off + row;
+                const float r_raw = (float)idx / (float)a.A;
+                const bool tm = ((step * 7 + env * 13) % a.term_period) == 0;
+                const bool tr = (((step + env) % a.trunc_period) == 0) && !tm;
+                float* obs_next = a.traj_obs + row * a.traj_obs_rs + (int64_t)(t + 1) * a.K1 + g * cpl;
+                float* env_o = a.env_obs + row * a.K1 + g * cpl;
+                float* xn = a.x_norm + row * a.K1 + g * cpl;
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const int c = lane + 32 * q;
-                        if (c < a.K1) {
-                            a.env_obs[row * a.K1 + c] = v[k][q];
-                            obs_next[c] = v[k][q];
-                            if (!last)
-                                a.x_norm[row * a.K1 + c] = norm_one(v[k][q], a.sub, a.inv_scale, a.do_sub, a.do_scale, do_rms,
-                                                                    do_rms ? cstat[c] : 0.f, do_rms ? cstat[a.K1 + c] : 1.f, a.clip);
+                for (int q4 = 0; q4 < RF_MAX_DIM / 32; ++q4)
+                    if (4 * q4 < cpl) {
+                        const float4 f4 = make_float4(ob[4 * q4], ob[4 * q4 + 1], ob[4 * q4 + 2], ob[4 * q4 + 3]);
+                        reinterpret_cast<float4*>(env_o)[q4] = f4;
+                        reinterpret_cast<float4*>(obs_next)[q4] = f4;
+                        if (!last) {
+                            const int c = g * cpl + 4 * q4;
+                            float4 y;
+                            y.x = norm_one(f4.x, a.sub, a.inv_scale, a.do_sub, a.do_scale, do_rms, do_rms ? cstat[c] : 0.f, do_rms ? cstat[a.K1 + c] : 1.f, a.clip);
+                            y.y = norm_one(f4.y, a.sub, a.inv_scale, a.do_sub, a.do_scale, do_rms, do_rms ? cstat[c + 1] : 0.f, do_rms ? cstat[a.K1 + c + 1] : 1.f, a.clip);
+                            y.z = norm_one(f4.z, a.sub, a.inv_scale, a.do_sub, a.do_scale, do_rms, do_rms ? cstat[c + 2] : 0.f, do_rms ? cstat[a.K1 + c + 2] : 1.f, a.clip);
+                            y.w = norm_one(f4.w, a.sub, a.inv_scale, a.do_sub, a.do_scale, do_rms, do_rms ? cstat[c + 3] : 0.f, do_rms ? cstat[a.K1 + c + 3] : 1.f, a.clip);
+                            reinterpret_cast<float4*>(xn)[q4] = y;
                         }
                     }
-                    if (a.rnn)
-                        for (int j = lane; j < a.rnn_dim; j += 32)
-                            a.traj_rnn[row * a.traj_rnn_rs + (int64_t)(t + 1) * a.rnn_dim + j] = a.rnn[row * a.rnn_dim + j];
-                    if (lane == 0) {
-                        a.env_rew[row] = r_raw;
-                        a.env_term[row] = tm;
-                        a.env_trunc[row] = tr;
-                        const bool done = tm || tr;                                     // batched_sampling.py:317
-                        float r = __fmul_rn(r_raw, a.reward_scale);                     // :209
-                        r = clampf(r, -a.reward_clip, a.reward_clip);                   // :210
-                        a.t_rew[row * a.stride + t] = r;
-                        a.t_done[row * a.stride + t] = done ? 1 : 0;
-                        a.t_to[row * a.stride + t] = tr ? 1 : 0;                        // :328
-                        a.t_pid[row * a.stride + t] = a.policy_id;
-                        if (a.ep_ret) {                                                 // _process_env_step :215-287 (raw reward)
-                            float er = er0[k] + r_raw;
-                            int32_t el = el0[k] + a.len_inc;
-                            float mn = fminf(mn0[k], r_raw), mx = fmaxf(mx0[k], r_raw);
-                            if (a.fin_ret) {
-                                a.fin_ret[row * a.stride + t] = done ? er : __int_as_float(0x7fc00000);
-                                a.fin_len[row * a.stride + t] = done ? el : -1;
-                            }
-                            if (done) {
-                                if (a.stats) {
-                                    atomicAdd(a.stats + 0, 1.0); atomicAdd(a.stats + 1, (double)er); atomicAdd(a.stats + 2, (double)el);
-                                    atomicAdd(a.stats + 3, (double)mn); atomicAdd(a.stats + 4, (double)mx);
-                                }
-                                er = 0.f; el = 0; mn = INFINITY; mx = -INFINITY;
-                            }
-                            a.ep_ret[row] = er; a.ep_len[row] = el; a.ep_min[row] = mn; a.ep_max[row] = mx;
+                if (a.rnn)
+                    for (int j = g; j < a.rnn_dim; j += 8)
+                        a.traj_rnn[row * a.traj_rnn_rs + (int64_t)(t + 1) * a.rnn_dim + j] = a.rnn[row * a.rnn_dim + j];
+                if (leader) {
+                    a.values[row * a.values_rs + t] = val;
+                    a.actions[row * a.actions_rs + t] = (float)idx;
+                    a.env_actions[row] = idx;
+                    a.log_prob[row * a.lp_rs + t] = lp;
+                    a.pv_out[row * a.pv_rs + t] = pv;
+                    a.env_rew[row] = r_raw;
+                    a.env_term[row] = tm;
+                    a.env_trunc[row] = tr;
+                    const bool done = tm || tr;                                     // batched_sampling.py:317
+                    float r = __fmul_rn(r_raw, a.reward_scale);                     // :209
+                    r = clampf(r, -a.reward_clip, a.reward_clip);                   // :210
+                    a.t_rew[row * a.stride + t] = r;
+                    a.t_done[row * a.stride + t] = done ? 1 : 0;
+                    a.t_to[row * a.stride + t] = tr ? 1 : 0;                        // :328
+                    a.t_pid[row * a.stride + t] = a.policy_id;
+                    if (a.ep_ret) {                                                 // _process_env_step :215-287 (raw reward)
+                        float er = er0 + r_raw;
+                        int32_t el = el0 + a.len_inc;
+                        float mn = fminf(mn0, r_raw), mx = fmaxf(mx0, r_raw);
+                        if (a.fin_ret) {
+                            a.fin_ret[row * a.stride + t] = done ? er : __int_as_float(0x7fc00000);
+                            a.fin_len[row * a.stride + t] = done ? el : -1;
                         }
+                        if (done) {
+                            if (a.stats) {
+                                atomicAdd(&s_stats[0], 1.0); atomicAdd(&s_stats[1], (double)er); atomicAdd(&s_stats[2], (double)el);
+                                atomicAdd(&s_stats[3], (double)mn); atomicAdd(&s_stats[4], (double)mx);
+                            }
+                            er = 0.f; el = 0; mn = INFINITY; mx = -INFINITY;
+                        }
+                        a.ep_ret[row] = er; a.ep_len[row] = el; a.ep_min[row] = mn; a.ep_max[row] = mx;
                     }
                 }
             }
@@ -443,6 +495,7 @@ rollout_mlp2_tape_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
 
     // every block has read the two step counters at its start; the last one to finish advances them by T
     __syncthreads();
+    if (threadIdx.x < 5 && a.stats && s_stats[0] > 0.0) atomicAdd(a.stats + threadIdx.x, s_stats[threadIdx.x]);
     if (threadIdx.x == 0) {
         __threadfence();
         if (atomicAdd(a.ticket, 1u) == gridDim.x * gridDim.y - 1u) {

@@ -22,16 +22,17 @@ runner.init()
 assert runner.sampler.fused_rollout
 for _ in range(3):
     runner.sampler.rollout()
-trace = torch.zeros(ROLLOUT * 12, dtype=torch.int64, device=dev)
+trace = torch.zeros(ROLLOUT * 16, dtype=torch.int64, device=dev)
 lib().call("sfb200_rollout_set_trace", trace.data_ptr())
 runner.sampler.rollout()
 torch.cuda.synchronize()
 lib().call("sfb200_rollout_set_trace", None)
-tr = trace.view(ROLLOUT, 12).cpu().double()
-names = ["tile1: start -> accumulator complete", "tile1: drain", "tile1: act + h1 store + fence", "tile1: cluster barrier",
-         "tile2: barrier -> accumulator complete", "tile2: drain", "tile2: act + heads partials store", "tile2: cluster barrier",
-         "tail: compute + stores + fence", "tail: cluster barrier"]
-idx = [(0, 1), (1, 2), (2, 3), (3, 4), (4, 5), (5, 6), (6, 7), (7, 8), (8, 9), (9, 10)]
+tr = trace.view(ROLLOUT, 16).cpu().double()
+names = ["tile1: start -> accumulator complete", "tile1: drain", "tile1: bias + activation", "tile1: h1 store + fence",
+         "tile1: cluster barrier", "tile2: barrier -> accumulator complete", "tile2: drain", "tile2: bias + activation",
+         "tile2: head partial dot products", "tile2: partials store", "tile2: cluster barrier", "tail: compute + stores + fence",
+         "tail: cluster barrier"]
+idx = [(0, 1), (1, 2), (2, 11), (11, 3), (3, 4), (4, 5), (5, 6), (6, 12), (12, 13), (13, 7), (7, 8), (8, 9), (9, 10)]
 tot = 0.0
 for n, (i, j) in zip(names, idx):
     d = (tr[1:, j] - tr[1:, i]).mean().item()
