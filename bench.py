@@ -499,11 +499,22 @@ def run_ours(args):
     clock_info["window"] = "timed region + the per-kernel timing iterations and the sampler-only pass right after it (same workload)"
     samp_bytes = 574.0 * N_ENVS * ROLLOUT
     samp_gbs = samp_bytes / (rollout_ms * 1e-3) / 1e9
-    roof_sampler = dict(kernel="sampler rollout (32 policy steps: GEMM, GEMM + heads + sampling, env, post+pre step)",
+    persistent = bool(getattr(runner.sampler, "fused_rollout", False))
+    samp_flops = 2.0 * (OBS_DIM * HIDDEN[0] + HIDDEN[0] * HIDDEN[1] + HIDDEN[1] * (N_ACTIONS + 1)) * N_ENVS * ROLLOUT
+    samp_tf = samp_flops / (rollout_ms * 1e-3) / 1e12
+    roof_sampler = dict(kernel=("sampler rollout = pre-step(0) + ONE persistent cluster kernel for the 32 policy steps "
+                                "(csrc/rollout_fused.cu)" if persistent else
+                                "sampler rollout (32 policy steps: layer-1 GEMM, layer-2 GEMM + head partials, fused step tail)"),
                         bound="hbm", achieved=samp_gbs, peak=peaks["hbm_gbs"], unit="GB/s", frac=samp_gbs / peaks["hbm_gbs"],
                         algorithmic_bytes=samp_bytes, rollout_ms=rollout_ms, share_of_step=rollout_ms / ms_per_step,
-                        note="a 4096-env policy step moves 2.35 MB and 2.45 GFLOP: the rollout is bound by the dependent "
-                             "kernel chain of each step (latency), not by HBM bandwidth")
+                        launches=int(sampler_launches),
+                        tensor=dict(achieved=samp_tf, unit="TFLOP/s", peak=peaks["tflops_burst"], frac=samp_tf / peaks["tflops_burst"],
+                                    algorithmic_flops=samp_flops,
+                                    note="policy forward only (0.599 MFLOP per env step, SURVEY 8d) over the whole rollout time; "
+                                         "3xTF32 ceiling = peak / 6; 128 of 148 SMs hold a CTA"),
+                        note="a 4096-env policy step moves 2.35 MB and 2.45 GFLOP: the rollout is bound by the per-step dependency "
+                             "chain (tensor-pipe time of the two layers + epilogues + cluster barriers, profiles/r02_k_rollout_trace.md), "
+                             "not by HBM bandwidth")
     dp_info = None
     if world > 1 and not args.no_dp_check:
         dp_info = dp_check(rank, world, dev, args.engine, runner.model)
