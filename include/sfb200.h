@@ -57,6 +57,27 @@ int sfb200_tc_available(void);
 int sfb200_register_tf32_lo(const float* base, float* lo, int64_t n);
 int sfb200_unregister_tf32_lo(const float* base);
 int sfb200_refresh_tf32_lo(const float* base, void* stream);
+/* The fp16-split form of the same 3-pass engine (fp32 accuracy class of 3xTF32 -- 22 significand bits per operand --
+ * on the kind::f16 tensor-core path: twice the MMA rate, 2/3 of the operand bytes).  A 3xTF32 GEMM takes it when
+ *   (1) its WEIGHT operand lies inside a buffer with registered fp16 twins: twins = [hi16[n] | lo16[n]],
+ *       hi = fp16(w * 2^8), lo = fp16((w * 2^8 - hi) * 2^11) (|w| < 255); for dX = dz . W, where the weight matrix is read
+ *       transposed, a per-matrix transposed copy [hiT[K][N] | loT[K][N]] registered with ..._f16_transposed; and
+ *   (2) its ACTIVATION operand lies inside a buffer with a registered bound: a device float >= max|x| (fp16 has five
+ *       exponent bits: the kernel scales the operand by the power of two that places the bound in [2^14, 2^15)).
+ * sfb200_clip_adam_step keeps registered twins current; the transposed copies and the twins after any other write to
+ * the weights are refreshed by the refresh_* calls.  sfb200_linear_out_bound derives the bound of a layer's output from
+ * the bound of its input: in_bound * max_n sum_k |W[n][k]| + max_n |b[n]| (tanh: at most 1).  SFB200_TC_F16=0 disables
+ * the form (A/B comparison).  No counterpart in the reference (its nn.Linear runs cuBLAS fp32 / CPU). */
+int sfb200_register_f16_twins(const float* base, void* twins, int64_t n);
+int sfb200_unregister_f16_twins(const float* base);
+int sfb200_refresh_f16_twins(const float* base, void* stream);
+int sfb200_register_f16_transposed(const float* W, int N, int K, void* twinsT);
+int sfb200_unregister_f16_transposed(const float* W);
+int sfb200_refresh_f16_transposed(const float* W, void* stream);
+int sfb200_register_operand_bound(const void* base, int64_t bytes, const float* bound_dev);
+int sfb200_unregister_operand_bound(const void* base);
+int sfb200_linear_out_bound(const float* W, const float* b, int N, int K, const float* in_bound_dev, float* out_bound_dev,
+                            int act, void* stream);
 /* total number of CUDA kernels this library has launched (or recorded into a stream capture) in this process */
 uint64_t sfb200_launch_count(void);
 

@@ -13,15 +13,18 @@ struct AdamArgs {
     float omb1, beta2f, omb2, eps, max_norm;
     const double* lr_num; const double* lr_den;
     float* grad_norm_out; float* p_lo;
+    uint16_t* p_hi16; int64_t lo16_offset;      // registered fp16 twins of the parameters (api.cu), or NULL
 };
 
 static inline AdamArgs make_adam_args(float* p, const float* g, float* m, float* v, int64_t n, double lr, const double* lr_dev,
                                       double beta1, double beta2, int64_t step, const int64_t* step_dev, double eps,
                                       double max_grad_norm, const double* lr_scale_num, const double* lr_scale_den,
                                       float* grad_norm_out) {
-    return AdamArgs{p, g, m, v, n, lr, lr_dev, beta1, beta2, step, step_dev,
-                    (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), (float)eps, (float)max_grad_norm,
-                    lr_scale_num, lr_scale_den, grad_norm_out, tf32_lo_lookup_mut(p, n)};
+    AdamArgs a{p, g, m, v, n, lr, lr_dev, beta1, beta2, step, step_dev,
+               (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), (float)eps, (float)max_grad_norm,
+               lr_scale_num, lr_scale_den, grad_norm_out, tf32_lo_lookup_mut(p, n), nullptr, 0};
+    a.p_hi16 = f16_twin_lookup_mut(p, n, &a.lo16_offset);
+    return a;
 }
 
 // Called by every thread of a 256-thread block (grid-stride over the parameters).  `part[0..nparts)` are the partial
@@ -60,6 +63,7 @@ __device__ __forceinline__ void clip_adam_body(const AdamArgs& a, const double* 
         const float pn = a.p[i] - step_size * __fdiv_rn(mi, denom);   // param.addcdiv_(exp_avg, denom, value=-step_size)
         a.p[i] = pn;
         if (a.p_lo) a.p_lo[i] = __uint_as_float(tf32_lo_bits(__float_as_uint(pn)));   // registered tf32 low half stays current
+        if (a.p_hi16) f16_split1(pn * (float)(1 << kF16WShift), a.p_hi16[i], a.p_hi16[i + a.lo16_offset]);   // and the fp16 twins
         a.m[i] = mi;
         a.v[i] = vi;
     }

@@ -36,6 +36,91 @@ float* tf32_lo_lookup_mut(float* p, int64_t count) {
 }
 const float* tf32_lo_lookup(const float* p, int64_t count) { return tf32_lo_lookup_mut(const_cast<float*>(p), count); }
 
+// ---- fp16 twins of weight buffers, their transposed per-matrix copies, activation bounds (the fp16-split GEMM engine)
+struct F16Range { const float* base; uint16_t* twins; int64_t n; };            // twins = [hi16[n] | lo16[n]]
+struct F16TRange { const float* W; int N, K; uint16_t* twins; };               // twins = [hiT[K][N] | loT[K][N]]
+struct BoundRange { const char* base; int64_t bytes; const float* bound; };
+static F16Range g_f16[32];
+static int g_f16_n = 0;
+static F16TRange g_f16t[64];
+static int g_f16t_n = 0;
+static BoundRange g_bound[64];
+static int g_bound_n = 0;
+
+uint16_t* f16_twin_lookup_mut(float* p, int64_t count, int64_t* lo_offset) {
+    for (int i = 0; i < g_f16_n; ++i) {
+        const F16Range& r = g_f16[i];
+        if (p >= r.base && p + count <= r.base + r.n) {
+            if (lo_offset) *lo_offset = r.n;
+            return r.twins + (p - r.base);
+        }
+    }
+    return nullptr;
+}
+F16Twin f16_twin_lookup(const float* p, int64_t count) {
+    int64_t off = 0;
+    const uint16_t* hi = f16_twin_lookup_mut(const_cast<float*>(p), count, &off);
+    return F16Twin{hi, hi ? hi + off : nullptr};
+}
+F16Twin f16_twinT_lookup(const float* W, int N, int K) {
+    for (int i = 0; i < g_f16t_n; ++i)
+        if (g_f16t[i].W == W && g_f16t[i].N == N && g_f16t[i].K == K)
+            return F16Twin{g_f16t[i].twins, g_f16t[i].twins + (int64_t)N * K};
+    return F16Twin{nullptr, nullptr};
+}
+const float* operand_bound_lookup(const void* p, int64_t bytes) {
+    const char* c = static_cast<const char*>(p);
+    for (int i = 0; i < g_bound_n; ++i)
+        if (c >= g_bound[i].base && c + bytes <= g_bound[i].base + g_bound[i].bytes) return g_bound[i].bound;
+    return nullptr;
+}
+
+__global__ void f16_split_kernel(const float* __restrict__ w, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        f16_split1(w[i] * (float)(1 << kF16WShift), hi[i], lo[i]);
+}
+
+// W[N][K] fp32 -> hiT / loT [K][N] fp16 (32 x 32 tiles through shared memory: coalesced on both sides)
+__global__ void __launch_bounds__(256) f16_split_transposed_kernel(const float* __restrict__ W, int N, int K,
+                                                                   uint16_t* __restrict__ hiT, uint16_t* __restrict__ loT) {
+    __shared__ float tile[32][33];
+    const int n0 = blockIdx.y * 32, k0 = blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int r = ty; r < 32; r += 8)
+        tile[r][tx] = (n0 + r < N && k0 + tx < K) ? W[(int64_t)(n0 + r) * K + k0 + tx] : 0.f;
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int k = k0 + r, n = n0 + tx;
+        if (k < K && n < N) f16_split1(tile[tx][r] * (float)(1 << kF16WShift), hiT[(int64_t)k * N + n], loT[(int64_t)k * N + n]);
+    }
+}
+
+// Upper bound of |act(x W^T + b)| over all inputs with |x| <= in_bound: in_bound * max_n sum_k |W[n][k]| + max_n |b[n]|
+// (ELU / ReLU / tanh are 1-Lipschitz with act(0) = 0; tanh additionally <= 1).  One block.
+__global__ void __launch_bounds__(1024) linear_out_bound_kernel(const float* __restrict__ W, const float* __restrict__ b, int N,
+                                                               int K, const float* __restrict__ in_bound,
+                                                               float* __restrict__ out_bound, int act) {
+    __shared__ float s_row[32], s_b[32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float row_max = 0.f, b_max = 0.f;
+    for (int n = warp; n < N; n += 32) {
+        float t = 0.f;
+        for (int k = lane; k < K; k += 32) t += fabsf(W[(int64_t)n * K + k]);
+        t = warp_sum(t);
+        row_max = fmaxf(row_max, t);
+        if (b) b_max = fmaxf(b_max, fabsf(b[n]));
+    }
+    if (lane == 0) { s_row[warp] = row_max; s_b[warp] = b_max; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float r = 0.f, bb = 0.f;
+        for (int i = 0; i < 32; ++i) { r = fmaxf(r, s_row[i]); bb = fmaxf(bb, s_b[i]); }
+        float out = in_bound[0] * r * 1.0001f + bb;      // (row sums are rounded: a hair of slack)
+        if (act == SFB200_ACT_TANH) out = fminf(out, 1.f);
+        out_bound[0] = out;
+    }
+}
+
 bool tf32_lo_check_enabled() {
     static int v = -1;
     if (v < 0) {
@@ -136,6 +221,106 @@ int sfb200_refresh_tf32_lo(const float* base, void* stream) {
         }
     sfb::set_error("refresh_tf32_lo: buffer is not registered");
     return 1;
+}
+
+int sfb200_register_f16_twins(const float* base, void* twins, int64_t n) {
+    SFB_CHECK_ARG(base && twins && n > 0, "register_f16_twins: bad arguments");
+    for (int i = 0; i < sfb::g_f16_n; ++i)
+        if (sfb::g_f16[i].base == base) {
+            sfb::g_f16[i] = sfb::F16Range{base, static_cast<uint16_t*>(twins), n};
+            return 0;
+        }
+    SFB_CHECK_ARG(sfb::g_f16_n < 32, "register_f16_twins: table full");
+    sfb::g_f16[sfb::g_f16_n++] = sfb::F16Range{base, static_cast<uint16_t*>(twins), n};
+    return 0;
+}
+
+int sfb200_unregister_f16_twins(const float* base) {
+    for (int i = 0; i < sfb::g_f16_n; ++i)
+        if (sfb::g_f16[i].base == base) {
+            sfb::g_f16[i] = sfb::g_f16[--sfb::g_f16_n];
+            break;
+        }
+    // transposed per-matrix twins of matrices inside this buffer go with it
+    return 0;
+}
+
+int sfb200_refresh_f16_twins(const float* base, void* stream) {
+    for (int i = 0; i < sfb::g_f16_n; ++i)
+        if (sfb::g_f16[i].base == base) {
+            const sfb::F16Range& r = sfb::g_f16[i];
+            int64_t blocks = sfb::ceil_div(r.n, 256);
+            if (blocks > 1184) blocks = 1184;
+            sfb::f16_split_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(r.base, r.twins, r.twins + r.n, r.n);
+            SFB_LAUNCH_OK();
+            return 0;
+        }
+    sfb::set_error("refresh_f16_twins: buffer is not registered");
+    return 1;
+}
+
+int sfb200_register_f16_transposed(const float* W, int N, int K, void* twinsT) {
+    SFB_CHECK_ARG(W && twinsT && N > 0 && K > 0, "register_f16_transposed: bad arguments");
+    for (int i = 0; i < sfb::g_f16t_n; ++i)
+        if (sfb::g_f16t[i].W == W) {
+            sfb::g_f16t[i] = sfb::F16TRange{W, N, K, static_cast<uint16_t*>(twinsT)};
+            return 0;
+        }
+    SFB_CHECK_ARG(sfb::g_f16t_n < 64, "register_f16_transposed: table full");
+    sfb::g_f16t[sfb::g_f16t_n++] = sfb::F16TRange{W, N, K, static_cast<uint16_t*>(twinsT)};
+    return 0;
+}
+
+int sfb200_unregister_f16_transposed(const float* W) {
+    for (int i = 0; i < sfb::g_f16t_n; ++i)
+        if (sfb::g_f16t[i].W == W) {
+            sfb::g_f16t[i] = sfb::g_f16t[--sfb::g_f16t_n];
+            return 0;
+        }
+    return 0;
+}
+
+int sfb200_refresh_f16_transposed(const float* W, void* stream) {
+    for (int i = 0; i < sfb::g_f16t_n; ++i)
+        if (sfb::g_f16t[i].W == W) {
+            const sfb::F16TRange& r = sfb::g_f16t[i];
+            dim3 grid((unsigned)sfb::ceil_div(r.K, 32), (unsigned)sfb::ceil_div(r.N, 32));
+            sfb::f16_split_transposed_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(r.W, r.N, r.K, r.twins,
+                                                                                      r.twins + (int64_t)r.N * r.K);
+            SFB_LAUNCH_OK();
+            return 0;
+        }
+    sfb::set_error("refresh_f16_transposed: matrix is not registered");
+    return 1;
+}
+
+int sfb200_register_operand_bound(const void* base, int64_t bytes, const float* bound_dev) {
+    SFB_CHECK_ARG(base && bytes > 0 && bound_dev, "register_operand_bound: bad arguments");
+    for (int i = 0; i < sfb::g_bound_n; ++i)
+        if (sfb::g_bound[i].base == base) {
+            sfb::g_bound[i] = sfb::BoundRange{static_cast<const char*>(base), bytes, bound_dev};
+            return 0;
+        }
+    SFB_CHECK_ARG(sfb::g_bound_n < 64, "register_operand_bound: table full");
+    sfb::g_bound[sfb::g_bound_n++] = sfb::BoundRange{static_cast<const char*>(base), bytes, bound_dev};
+    return 0;
+}
+
+int sfb200_unregister_operand_bound(const void* base) {
+    for (int i = 0; i < sfb::g_bound_n; ++i)
+        if (sfb::g_bound[i].base == base) {
+            sfb::g_bound[i] = sfb::g_bound[--sfb::g_bound_n];
+            return 0;
+        }
+    return 0;
+}
+
+int sfb200_linear_out_bound(const float* W, const float* b, int N, int K, const float* in_bound_dev, float* out_bound_dev,
+                            int act, void* stream) {
+    SFB_CHECK_ARG(W && in_bound_dev && out_bound_dev && N > 0 && K > 0, "linear_out_bound: bad arguments");
+    sfb::linear_out_bound_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(W, b, N, K, in_bound_dev, out_bound_dev, act);
+    SFB_LAUNCH_OK();
+    return 0;
 }
 
 uint64_t sfb200_launch_count(void) { return __atomic_load_n(&sfb::g_launches, __ATOMIC_RELAXED); }

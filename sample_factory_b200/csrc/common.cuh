@@ -1,5 +1,6 @@
 // Shared helpers for libsfb200 kernels (sm_100a).
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -46,6 +47,15 @@ const float* tf32_lo_lookup(const float* p, int64_t count);
 float* tf32_lo_lookup_mut(float* p, int64_t count);
 int tf32_lo_check(const float* w, const float* lo, int64_t count, cudaStream_t st);   // SFB200_CHECK_LO=1: trap if stale
 bool tf32_lo_check_enabled();
+// Registered fp16 twins of weight buffers (api.cu): [hi16[n] | lo16[n]] with hi = fp16(w * 2^kF16WShift),
+// lo = fp16((w * 2^kF16WShift - hi) * 2^kF16LoShift) -- the weight operand of the fp16-split GEMM (gemm_tc.cu, "F16" kernel).
+struct F16Twin { const uint16_t* hi; const uint16_t* lo; };
+F16Twin f16_twin_lookup(const float* p, int64_t count);
+uint16_t* f16_twin_lookup_mut(float* p, int64_t count, int64_t* lo_offset);
+// the same twins stored TRANSPOSED ([K][N] for a weight matrix W[N][K]): the weight operand of dX = dz . W, K-major
+F16Twin f16_twinT_lookup(const float* W, int N, int K);
+// device float holding an upper bound of |x| over an activation buffer that contains [p, p + bytes), else NULL
+const float* operand_bound_lookup(const void* p, int64_t bytes);
 bool pdl_enabled();   // SFB200_PDL=0 turns programmatic dependent launch off (api.cu)
 
 // Programmatic dependent launch: kernels launched through launch_pdl() may be made resident while their predecessor on
@@ -118,6 +128,35 @@ __device__ __forceinline__ float act_bwd_from_out(float h, int act) {
 __device__ __forceinline__ uint32_t tf32_lo_bits(uint32_t w) {
     const uint32_t h = w & 0xffffe000u;
     return __float_as_uint(__uint_as_float(w) - __uint_as_float(h)) & 0xffffe000u;
+}
+
+// ---- fp16 operand split (the "3xFP16" engine) ---------------------------------------------------------------------
+// v = x * 2^e is represented as hi + lo * 2^-11 with hi = fp16(v) (round to nearest) and lo = fp16((v - hi) * 2^11): 22
+// significand bits like the tf32 pair, but on the fp16 tensor-core path (twice the MMA rate, half the operand bytes).
+// fp16 has 5 exponent bits, so e is chosen from a known bound of |x|: bound * 2^e lands in [2^14, 2^15) -- one binade of
+// headroom below the largest fp16 -- and elements down to 2^-29 of the bound keep full relative precision (smaller ones
+// keep an ABSOLUTE error of 2^-36 * 2^-e, i.e. 2^-50 of the bound).  Weights use the fixed shift kF16WShift (|w| < 255).
+constexpr int kF16WShift = 8;
+constexpr int kF16LoShift = 11;
+__device__ __forceinline__ int f16_shift_for_bound(float bound) {
+    const int eb = (int)((__float_as_uint(bound) >> 23) & 0xffu) - 127;      // floor(log2(bound)) for normal floats
+    int e = 14 - eb;
+    return e < -100 ? -100 : (e > 100 ? 100 : e);                            // (bound 0 / denormal -> huge e: clamp)
+}
+__device__ __forceinline__ float pow2f_int(int e) { return __uint_as_float((uint32_t)(e + 127) << 23); }
+// two scaled values -> packed (hi, lo) half2 words, element 0 in the low 16 bits
+__device__ __forceinline__ void f16_split2(float v0, float v1, uint32_t& hi, uint32_t& lo) {
+    const __half2 h = __floats2half2_rn(v0, v1);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn((v0 - hf.x) * 2048.f, (v1 - hf.y) * 2048.f);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+__device__ __forceinline__ void f16_split1(float v, uint16_t& hi, uint16_t& lo) {
+    const __half h = __float2half_rn(v);
+    const __half l = __float2half_rn((v - __half2float(h)) * 2048.f);
+    hi = *reinterpret_cast<const uint16_t*>(&h);
+    lo = *reinterpret_cast<const uint16_t*>(&l);
 }
 
 __device__ __forceinline__ float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }

@@ -163,6 +163,7 @@ struct EpiCtx {
     int lane_base, lane, col0, mode;
     bool vec_ok, aux_vec, bias_vec, st_v8, aux_v8;
     const float* bias_base;
+    float out_scale;     // fp16-split engine: 2^-(operand shifts); 1 otherwise
 };
 
 // Epilogue warps 6..13: warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32); warps 6..9 take columns [0, BN/2) of their
@@ -188,15 +189,18 @@ __device__ __forceinline__ EpiCtx make_epi_ctx(int warp, int lane, const float* 
     ec.bias_base = bias_smem ? bias_s : epi.bias;
     ec.bias_vec = epi.bias && (bias_smem || ((reinterpret_cast<uintptr_t>(epi.bias) & 15u) == 0));
     ec.mode = splits == 1 ? epi.mode : 0;
+    ec.out_scale = 1.f;
     return ec;
 }
 
 // Whole accumulator row segment of this thread (CH columns, main + cross terms summed) -> registers, then the TMEM slot
 // is handed back at once: all of the epilogue's arithmetic and global traffic overlaps the next tile's main loop (the
 // TMEM-A kernel has a single accumulator slot, so whatever runs before the release is serialised with the MMAs).
-template <int BN, int CH, bool SPLIT3>
+// F16 (fp16-split engine): the cross columns hold the two hi x lo terms scaled by 2^11, and everything carries the
+// operands' power-of-two shifts: acc = (main + cross * 2^-11) * out_scale, exact scalings.
+template <int BN, int CH, bool SPLIT3, bool F16 = false>
 __device__ __forceinline__ void tmem_drain(uint32_t t_main, float (&acc)[CH], uint64_t* acc_full_bar, uint32_t acc_ph,
-                                           uint64_t* acc_empty_bar) {
+                                           uint64_t* acc_empty_bar, float out_scale = 1.f) {
     mbar_wait(acc_full_bar, acc_ph);
     tc_fence_after();
 #pragma unroll
@@ -208,7 +212,10 @@ __device__ __forceinline__ void tmem_drain(uint32_t t_main, float (&acc)[CH], ui
             tmem_ld_32x32b_x16(t_main + (uint32_t)(BN + c0), r2);
             tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 16; ++j) acc[c0 + j] = __uint_as_float(r[j]) + __uint_as_float(r2[j]);
+            for (int j = 0; j < 16; ++j) {
+                if (F16) acc[c0 + j] = fmaf(__uint_as_float(r2[j]), 1.f / 2048.f, __uint_as_float(r[j])) * out_scale;
+                else acc[c0 + j] = __uint_as_float(r[j]) + __uint_as_float(r2[j]);
+            }
         } else {
             tmem_ld_wait();
 #pragma unroll
@@ -220,7 +227,7 @@ __device__ __forceinline__ void tmem_drain(uint32_t t_main, float (&acc)[CH], ui
 }
 
 // One output tile: TMEM accumulator slot (main at column 0, cross terms at column BN) -> registers -> global.
-template <int BN, bool SPLIT3>
+template <int BN, bool SPLIT3, bool F16 = false>
 __device__ __forceinline__ void tc_epilogue_tile(uint32_t tmem_slot_addr, uint64_t* acc_full_bar, uint32_t acc_ph,
                                                  uint64_t* acc_empty_bar, const TileCoord& tc, const EpiCtx& ec,
                                                  float* __restrict__ C, int64_t ldc, int64_t M, int N, int splits,
@@ -248,8 +255,8 @@ __device__ __forceinline__ void tc_epilogue_tile(uint32_t tmem_slot_addr, uint64
         }
     }
     float acc_all[CH];
-    tmem_drain<BN, CH, SPLIT3>(tmem_slot_addr + ((uint32_t)lane_base << 16) + (uint32_t)col0, acc_all, acc_full_bar, acc_ph,
-                               acc_empty_bar);
+    tmem_drain<BN, CH, SPLIT3, F16>(tmem_slot_addr + ((uint32_t)lane_base << 16) + (uint32_t)col0, acc_all, acc_full_bar, acc_ph,
+                                    acc_empty_bar, ec.out_scale);
     if (m >= M) return;
     float* Cz = C + (splits > 1 ? (int64_t)tc.z * M * ldc : 0);
     float* dst_row = Cz + m * ldc + nbeg;
@@ -311,7 +318,7 @@ __device__ __forceinline__ void tc_epilogue_tile(uint32_t tmem_slot_addr, uint64
 // with the (A+1) head weight rows staged in shared memory -- the separate heads kernel's re-read of y (4*N bytes per
 // row) disappears, and in the sampler y is not written at all.  16-column chunks keep the live set (16 + 16 accumulator
 // words, 9 partial sums) inside the 128-register budget.
-template <int BN, bool SPLIT3, int ACT>
+template <int BN, bool SPLIT3, int ACT, bool F16 = false>
 __device__ __forceinline__ void tc_epilogue_tile_heads(uint32_t tmem_slot_addr, uint64_t* acc_full_bar, uint32_t acc_ph,
                                                        uint64_t* acc_empty_bar, const TileCoord& tc, const EpiCtx& ec,
                                                        float* __restrict__ C, int64_t ldc, int64_t M, int N,
@@ -320,8 +327,8 @@ __device__ __forceinline__ void tc_epilogue_tile_heads(uint32_t tmem_slot_addr, 
     const int64_t m = tc.m0 + ec.lane_base + ec.lane;
     const int nbeg = tc.n0 + ec.col0;
     float o[CH];
-    tmem_drain<BN, CH, SPLIT3>(tmem_slot_addr + ((uint32_t)ec.lane_base << 16) + (uint32_t)ec.col0, o, acc_full_bar, acc_ph,
-                               acc_empty_bar);
+    tmem_drain<BN, CH, SPLIT3, F16>(tmem_slot_addr + ((uint32_t)ec.lane_base << 16) + (uint32_t)ec.col0, o, acc_full_bar, acc_ph,
+                                    acc_empty_bar, ec.out_scale);
     if (m >= M) return;   // (the caller's named barriers come after this function: every thread still reaches them)
     float hp[kHeadAP];
 #pragma unroll
@@ -375,7 +382,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                float* __restrict__ C, int64_t ldc, int64_t M, int N, int K, int k_chunk, int splits, TcEpilogue epi) {
     using S = TcSmem<BN, STAGES>;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_align_1024(smem_raw);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES);
     uint64_t* full = bars;                      // TMA bytes landed             (count 1 + tx)
     uint64_t* conv = bars + STAGES;             // operands split & visible      (count 128)
@@ -563,10 +570,12 @@ constexpr uint32_t TA_ACOL0 = 256;
 // because a dW tile runs ~100 k-blocks per epilogue).  Opt-in, see dw_operand_warps().
 constexpr int ta_threads(int opw) { return 32 * (2 + opw + 8); }   // 448 (4 operand warps) or 576 (8)
 
-template <int STAGES>
+// F16 (fp16-split engine): a stage covers 64 k: B tiles are [128][64] fp16 (the same 16 KB), A is two fp32 boxes of 32 k
+constexpr int TA_F16_STAGES = 3;
+template <int STAGES, bool F16 = false>
 struct TaSmem {
     static constexpr int B_BYTES = 128 * TBK * 4;
-    static constexpr int A_BYTES = TBM * TBK * 4;
+    static constexpr int A_BYTES = TBM * TBK * 4 * (F16 ? 2 : 1);
     static constexpr int STAGE_BYTES = 2 * B_BYTES + A_BYTES;   // [B hi | B lo | A raw]
     static constexpr int NUM_BARS = 3 * STAGES + 2;
     static constexpr int BIAS_FLOATS = 2048;
@@ -580,16 +589,23 @@ struct TaSmem {
 // no shared-memory work for B at all.
 // (Tried and dropped: two extra warps taking over the B-tile split of the dW-type GEMM so that A and B work of a stage
 // proceed in parallel -- 230.6 vs 232.4 us for dW + dX at M=32768, N=K=512, i.e. the B split is not what paces that GEMM.)
-template <bool A_MN, bool B_MN, bool SPLIT3, bool HEADS, bool BLO, int TA_OPW>
+// F16: the fp16-split engine (A K-major fp32 with a known bound -> scaled fp16 hi/lo pairs in TMEM; B = registered fp16
+// twins of a weight matrix by TMA; kind::f16 MMAs; see common.cuh "fp16 operand split").  Same roles and barriers.
+template <bool A_MN, bool B_MN, bool SPLIT3, bool HEADS, bool BLO, int TA_OPW, bool F16 = false>
 __global__ void __launch_bounds__(ta_threads(TA_OPW), 1)
 gemm_tc_ta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                   const __grid_constant__ CUtensorMap tmap_b_lo, float* __restrict__ C, int64_t ldc, int64_t M, int N,
-                  int K, int k_chunk, int splits, TcEpilogue epi, int raw_hi) {
-    constexpr int BN = 128, STAGES = TA_STAGES;
+                  int K, int k_chunk, int splits, TcEpilogue epi, int flags, const float* __restrict__ a_bound) {
+    static_assert(!F16 || (!A_MN && !B_MN && SPLIT3 && BLO && TA_OPW == 4), "fp16-split engine: K-major operands, weight twins");
+    constexpr int BN = 128, STAGES = F16 ? TA_F16_STAGES : TA_STAGES;
+    constexpr int KB_K = F16 ? 64 : TBK;                    // k per pipeline stage
+    const int raw_hi = flags & 1;
+    const bool probe_no_b = flags & 2, probe_no_a = flags & 4, probe_no_cross = flags & 8, probe_no_blo = flags & 16;
+    const int a_prefetch = (flags & 32) ? 4 : (flags & 64) ? 8 : (flags & 128) ? 16 : 0;
     constexpr int TA_EPI_WARP0 = 2 + TA_OPW;                // first of the 8 epilogue warps
-    using S = TaSmem<STAGES>;
+    using S = TaSmem<STAGES, F16>;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_align_1024(smem_raw);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES);
     uint64_t* full = bars;                  // A and B tiles landed (TMA)
     uint64_t* conv = bars + STAGES;         // A in TMEM + B split, visible to the tensor core (count 128)
@@ -626,6 +642,8 @@ gemm_tc_ta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     // launch it overlaps the tail of the previous kernel; global memory is only touched after the wait
     pdl_wait();
     pdl_trigger();
+    // fp16-split engine: binary shift of the A operand from its bound (written by an earlier kernel of the stream)
+    const int a_shift = F16 ? f16_shift_for_bound(a_bound[0]) : 0;
 
     if (warp == 0) {
         // ===================================================== TMA producer
@@ -633,12 +651,24 @@ gemm_tc_ta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             uint32_t it = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const TileCoord tc = tile_coord(tile, tiles_n, tiles_per_z, BN, K, k_chunk);
-                for (int kb = 0; kb < tc.num_kb; ++kb, ++it) {
+                const int nkb = F16 ? tc.num_kb / 2 : tc.num_kb;
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const int s = it % STAGES;
                     mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
                     uint8_t* sb = smem + s * S::STAGE_BYTES;
-                    mbar_expect_tx(&full[s], (BLO ? 2 : 1) * S::B_BYTES + S::A_BYTES);
-                    const int k0 = tc.k_begin + kb * TBK;
+                    mbar_expect_tx(&full[s], ((BLO && !probe_no_blo) ? 2 : 1) * S::B_BYTES + S::A_BYTES);
+                    const int k0 = tc.k_begin + kb * KB_K;
+                    if (F16) {
+                        tma_load_2d(sb + 2 * S::B_BYTES, &tmap_a, &full[s], k0, (int)tc.m0);
+                        tma_load_2d(sb + 2 * S::B_BYTES + 16384, &tmap_a, &full[s], k0 + 32, (int)tc.m0);
+                        tma_load_2d(sb, &tmap_b, &full[s], k0, tc.n0);                    // hi16 [128 n][64 k]
+                        tma_load_2d(sb + S::B_BYTES, &tmap_b_lo, &full[s], k0, tc.n0);    // lo16
+                        continue;
+                    }
+                    if (!A_MN && a_prefetch && kb + a_prefetch < tc.num_kb)
+                        asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(&tmap_a),
+                                     "r"(k0 + a_prefetch * TBK), "r"((int)tc.m0)
+                                     : "memory");
                     if (A_MN) {
                         for (int j = 0; j < TBM / 32; ++j)
                             tma_load_2d(sb + 2 * S::B_BYTES + j * 4096, &tmap_a, &full[s], (int)tc.m0 + 32 * j, k0);
@@ -652,22 +682,23 @@ gemm_tc_ta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                                 tma_load_2d(sb + S::B_BYTES + j * 4096, &tmap_b_lo, &full[s], tc.n0 + 32 * j, k0);
                     } else {
                         tma_load_2d(sb, &tmap_b, &full[s], k0, tc.n0);
-                        if (BLO) tma_load_2d(sb + S::B_BYTES, &tmap_b_lo, &full[s], k0, tc.n0);
+                        if (BLO && !probe_no_blo) tma_load_2d(sb + S::B_BYTES, &tmap_b_lo, &full[s], k0, tc.n0);
                     }
                 }
             }
         }
     } else if (warp == 1) {
         // ===================================================== MMA issuer
-        constexpr uint32_t idesc_wide = make_idesc(false, B_MN, TBM, SPLIT3 ? 2 * BN : BN);
-        constexpr uint32_t idesc_cross = make_idesc(false, B_MN, TBM, BN);
-        constexpr uint32_t B_KSTEP = B_MN ? (1024u >> 4) : (UMMA_K * 4u >> 4);
+        constexpr uint32_t idesc_wide = F16 ? make_idesc_f16(TBM, 2 * BN) : make_idesc(false, B_MN, TBM, SPLIT3 ? 2 * BN : BN);
+        constexpr uint32_t idesc_cross = F16 ? make_idesc_f16(TBM, BN) : make_idesc(false, B_MN, TBM, BN);
+        constexpr uint32_t B_KSTEP = B_MN ? (1024u >> 4) : (UMMA_K * 4u >> 4);     // 32 B per k-step (8 tf32 = 16 fp16)
         uint32_t it = 0, tile_iter = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_iter) {
             const TileCoord tc = tile_coord(tile, tiles_n, tiles_per_z, BN, K, k_chunk);
+            const int nkb = F16 ? tc.num_kb / 2 : tc.num_kb;
             mbar_wait(acc_empty, (tile_iter & 1) ^ 1);
             tc_fence_after();
-            for (int kb = 0; kb < tc.num_kb; ++kb, ++it) {
+            for (int kb = 0; kb < nkb; ++kb, ++it) {
                 const int s = it % STAGES;
                 if (BLO) mbar_wait(&full[s], (it / STAGES) & 1);   // B tiles come straight from TMA: observe their barrier here too
                 mbar_wait(&conv[s], (it / STAGES) & 1);
@@ -678,12 +709,18 @@ gemm_tc_ta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 #pragma unroll
                     for (int k = 0; k < TBK / UMMA_K; ++k) {
                         const uint64_t bo = (uint64_t)(k * B_KSTEP);
+                        if (F16) {
+                            // 16 k per instruction = 8 TMEM columns of packed pairs; A_hi at +0, A_lo at +32 of the stage
+                            umma_f16_ts(tmem_base, a_hi + k * 8, db_hi + bo, idesc_wide, (kb | k) != 0);
+                            umma_f16_ts(tmem_base + BN, a_hi + 32 + k * 8, db_hi + bo, idesc_cross, 1);
+                            continue;
+                        }
                         // [main | cross] (+)= A_hi x [B_hi ; B_lo]   (plain tf32 mode: main (+)= A x B)
                         umma_tf32_ts(tmem_base, a_hi + k * UMMA_K, db_hi + bo, idesc_wide, (kb | k) != 0);
-                        if (SPLIT3) umma_tf32_ts(tmem_base + BN, a_hi + 32 + k * UMMA_K, db_hi + bo, idesc_cross, 1);
+                        if (SPLIT3 && !probe_no_cross) umma_tf32_ts(tmem_base + BN, a_hi + 32 + k * UMMA_K, db_hi + bo, idesc_cross, 1);
                     }
                     umma_commit(&empty[s]);
-                    if (kb == tc.num_kb - 1) umma_commit(acc_full);
+                    if (kb == nkb - 1) umma_commit(acc_full);
                 }
                 __syncwarp();
             }
@@ -698,17 +735,44 @@ gemm_tc_ta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + TA_ACOL0 + (uint32_t)c0;
         const int sw = row & 7;                                // 128B swizzle: 16 B chunk index XOR (row % 8)
         uint32_t it = 0;
+        const float a_scale = pow2f_int(a_shift);
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const TileCoord tc = tile_coord(tile, tiles_n, tiles_per_z, BN, K, k_chunk);
-            for (int kb = 0; kb < tc.num_kb; ++kb, ++it) {
+            const int nkb = F16 ? tc.num_kb / 2 : tc.num_kb;
+            for (int kb = 0; kb < nkb; ++kb, ++it) {
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1;
                 // full[s] of this phase implies empty[s] of the previous one: the MMAs that read TMEM stage s have retired
                 mbar_wait(&full[s], ph);
                 tc_fence_after();
                 uint8_t* sb = smem + s * S::STAGE_BYTES;
+                if constexpr (F16) {
+                    // 64 k of this thread's row: two 128 B swizzled rows (one per 32-k box) -> 32 + 32 packed half2 words
+                    uint32_t h16[32], l16[32];
+#pragma unroll
+                    for (int box = 0; box < 2; ++box) {
+                        const uint4* arow = reinterpret_cast<const uint4*>(sb + 2 * S::B_BYTES + box * 16384 + row * 128);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const uint4 q = arow[j ^ sw];
+                            f16_split2(__uint_as_float(q.x) * a_scale, __uint_as_float(q.y) * a_scale, h16[box * 16 + 2 * j],
+                                       l16[box * 16 + 2 * j]);
+                            f16_split2(__uint_as_float(q.z) * a_scale, __uint_as_float(q.w) * a_scale, h16[box * 16 + 2 * j + 1],
+                                       l16[box * 16 + 2 * j + 1]);
+                        }
+                    }
+                    tmem_st_32x32b_x32(lane_addr + (uint32_t)s * 64u, h16);
+                    tmem_st_32x32b_x32(lane_addr + (uint32_t)s * 64u + 32u, l16);
+                    tmem_st_wait();
+                    tc_fence_before();
+                    mbar_arrive(&conv[s]);
+                    continue;
+                }
                 uint32_t hi[CPT], lo[CPT];
-                if (A_MN) {
+                if (probe_no_a) {
+#pragma unroll
+                    for (int kk = 0; kk < CPT; ++kk) hi[kk] = lo[kk] = 0u;
+                } else if (A_MN) {
                     // MN-major tile: box (row/32) of [32 k][32 rows], k-rows 128 B apart, 32 B chunks XOR (k % 4)
                     // (SWIZZLE_128B_ATOM_32B).  A warp reads one whole 128 B k-row per instruction: conflict-free.
                     const uint8_t* abox = sb + 2 * S::B_BYTES + (row >> 5) * 4096 + (lane & 7) * 4;
@@ -745,7 +809,7 @@ gemm_tc_ta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 }
                 tmem_st_cols<CPT>(lane_addr + (uint32_t)s * 64u, hi);
                 if (SPLIT3) tmem_st_cols<CPT>(lane_addr + (uint32_t)s * 64u + 32u, lo);
-                if (SPLIT3 && !BLO) {
+                if (SPLIT3 && !BLO && !probe_no_b) {
                     uint4* h4 = reinterpret_cast<uint4*>(sb);
                     uint4* l4 = reinterpret_cast<uint4*>(sb + S::B_BYTES);
 #pragma unroll 4
@@ -778,26 +842,27 @@ gemm_tc_ta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             }
             asm volatile("bar.sync 1, 256;" ::: "memory");
         }
-        const EpiCtx ec = make_epi_ctx<BN, TA_EPI_WARP0>(warp, lane, C, ldc, N, splits, epi, bias_s, S::BIAS_FLOATS);
+        EpiCtx ec = make_epi_ctx<BN, TA_EPI_WARP0>(warp, lane, C, ldc, N, splits, epi, bias_s, S::BIAS_FLOATS);
+        if (F16) ec.out_scale = pow2f_int(-(a_shift + kF16WShift));
         uint32_t tile_iter = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_iter) {
             const TileCoord tc = tile_coord(tile, tiles_n, tiles_per_z, BN, K, k_chunk);
             if (HEADS) {
                 switch (epi.act) {
                     case SFB200_ACT_ELU:
-                        tc_epilogue_tile_heads<BN, SPLIT3, SFB200_ACT_ELU>(tmem_base, acc_full, tile_iter & 1, acc_empty, tc, ec, C,
+                        tc_epilogue_tile_heads<BN, SPLIT3, SFB200_ACT_ELU, F16>(tmem_base, acc_full, tile_iter & 1, acc_empty, tc, ec, C,
                                                                            ldc, M, N, epi, headw_s);
                         break;
                     case SFB200_ACT_RELU:
-                        tc_epilogue_tile_heads<BN, SPLIT3, SFB200_ACT_RELU>(tmem_base, acc_full, tile_iter & 1, acc_empty, tc, ec,
+                        tc_epilogue_tile_heads<BN, SPLIT3, SFB200_ACT_RELU, F16>(tmem_base, acc_full, tile_iter & 1, acc_empty, tc, ec,
                                                                             C, ldc, M, N, epi, headw_s);
                         break;
                     case SFB200_ACT_TANH:
-                        tc_epilogue_tile_heads<BN, SPLIT3, SFB200_ACT_TANH>(tmem_base, acc_full, tile_iter & 1, acc_empty, tc, ec,
+                        tc_epilogue_tile_heads<BN, SPLIT3, SFB200_ACT_TANH, F16>(tmem_base, acc_full, tile_iter & 1, acc_empty, tc, ec,
                                                                             C, ldc, M, N, epi, headw_s);
                         break;
                     default:
-                        tc_epilogue_tile_heads<BN, SPLIT3, SFB200_ACT_NONE>(tmem_base, acc_full, tile_iter & 1, acc_empty, tc, ec,
+                        tc_epilogue_tile_heads<BN, SPLIT3, SFB200_ACT_NONE, F16>(tmem_base, acc_full, tile_iter & 1, acc_empty, tc, ec,
                                                                             C, ldc, M, N, epi, headw_s);
                         break;
                 }
@@ -821,7 +886,7 @@ gemm_tc_ta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                     }
                 }
             } else {
-                tc_epilogue_tile<BN, SPLIT3>(tmem_base, acc_full, tile_iter & 1, acc_empty, tc, ec, C, ldc, M, N, splits, epi);
+                tc_epilogue_tile<BN, SPLIT3, F16>(tmem_base, acc_full, tile_iter & 1, acc_empty, tc, ec, C, ldc, M, N, splits, epi);
             }
         }
     }
@@ -918,11 +983,23 @@ static int dw_operand_warps() {
     return v;
 }
 
-template <bool A_MN, bool B_MN, bool SPLIT3, bool HEADS, bool BLO, int OPW>
+// SFB200_TA_PROBE (tools/dw_bench.py only; results are garbage): 2 = operand warps skip the B split, 4 = skip the A
+// load / convert, 8 = MMA issuer skips the cross MMA.  Which stage paces the kernel = which skip makes it faster.
+static int ta_probe_bits() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("SFB200_TA_PROBE");
+        v = e ? (atoi(e) & 0xfe) : 0;   // 16 = skip the B_lo TMA load, 32/64/128 = L2 prefetch of the A tiles 4/8/16 k-blocks ahead
+    }
+    return v;
+}
+
+template <bool A_MN, bool B_MN, bool SPLIT3, bool HEADS, bool BLO, int OPW, bool F16 = false>
 static int launch_tc_ta_opw(const CUtensorMap& ta, const CUtensorMap& tb, float* C, int64_t ldc, int64_t M, int N, int K,
-                            int k_chunk, int splits, const TcEpilogue& epi, cudaStream_t st, const CUtensorMap* tb_lo) {
-    using S = TaSmem<TA_STAGES>;
-    auto kern = gemm_tc_ta_kernel<A_MN, B_MN, SPLIT3, HEADS, BLO, OPW>;
+                            int k_chunk, int splits, const TcEpilogue& epi, cudaStream_t st, const CUtensorMap* tb_lo,
+                            const float* a_bound = nullptr) {
+    using S = TaSmem<F16 ? TA_F16_STAGES : TA_STAGES, F16>;
+    auto kern = gemm_tc_ta_kernel<A_MN, B_MN, SPLIT3, HEADS, BLO, OPW, F16>;
     constexpr int SMEM = HEADS ? S::TOTAL_HEADS : S::TOTAL;
     static bool attr_set = false;
     if (!attr_set) {
@@ -932,7 +1009,7 @@ static int launch_tc_ta_opw(const CUtensorMap& ta, const CUtensorMap& tb, float*
     const int64_t tiles = ceil_div(N, 128) * ceil_div(M, TBM) * splits;
     const int64_t grid = tiles < sm_count() ? tiles : sm_count();
     SFB_CUDA_OK(launch_pdl(kern, dim3((unsigned)grid), dim3(ta_threads(OPW)), (size_t)SMEM, st, ta, tb, tb_lo ? *tb_lo : tb, C, ldc, M,
-                           N, K, k_chunk, splits, epi, raw_hi_enabled() ? 1 : 0));
+                           N, K, k_chunk, splits, epi, (raw_hi_enabled() ? 1 : 0) | ta_probe_bits(), a_bound));
     SFB_LAUNCH_OK();
     return 0;
 }
@@ -945,6 +1022,28 @@ static int launch_tc_ta(const CUtensorMap& ta, const CUtensorMap& tb, float* C, 
             return launch_tc_ta_opw<A_MN, B_MN, SPLIT3, HEADS, BLO, 8>(ta, tb, C, ldc, M, N, K, k_chunk, splits, epi, st, tb_lo);
     }
     return launch_tc_ta_opw<A_MN, B_MN, SPLIT3, HEADS, BLO, 4>(ta, tb, C, ldc, M, N, K, k_chunk, splits, epi, st, tb_lo);
+}
+
+bool make_tmap_f16(CUtensorMap* out, const uint16_t* base, uint64_t dim0, uint64_t dim1, uint64_t stride1_elems, uint32_t box0,
+                   uint32_t box1) {
+    cuuint64_t gdim[2] = {dim0, dim1};
+    cuuint64_t gstride[1] = {stride1_elems * sizeof(uint16_t)};
+    cuuint32_t box[2] = {box0, box1};
+    cuuint32_t estride[2] = {1, 1};
+    CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<uint16_t*>(base), gdim, gstride, box, estride,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+// SFB200_TC_F16=0 turns the fp16-split engine off (every 3-pass GEMM then runs the tf32 split; A/B comparison)
+static bool f16_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("SFB200_TC_F16");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
 }
 
 // SFB200_TC_B_LO=0 ignores registered tf32-lo buffers (A/B comparison)
@@ -992,6 +1091,30 @@ static int gemm_tc(bool a_mn, const float* A, int64_t lda, bool b_mn, const floa
     const int64_t ld_out = splits > 1 ? N : ldc;
 
     if (epi.head_part && !(BN == 128 && ta_enabled() && !a_mn && !b_mn && splits == 1)) return SFB_TC_UNSUPPORTED;
+    // fp16-split engine: A is a K-major activation buffer with a registered bound, B a weight matrix with registered fp16
+    // twins (the transposed twins when B is read MN-major, i.e. dX = dz . W), K a multiple of the 64-k stage
+    if (BN == 128 && ta_enabled() && !a_mn && split3 && splits == 1 && K % 64 == 0 && f16_enabled() && blo_enabled()) {
+        const float* a_bound = operand_bound_lookup(A, ((int64_t)(M - 1) * lda + K) * (int64_t)sizeof(float));
+        F16Twin tw{nullptr, nullptr};
+        if (a_bound) {
+            if (!b_mn && ldb == K) tw = f16_twin_lookup(B, (int64_t)N * K);
+            else if (b_mn && ldb == N) tw = f16_twinT_lookup(B, K, N);      // B = W[K][N] row-major, twins stored as [N][K]
+        }
+        if (tw.hi) {
+            CUtensorMap tb_hi, tb_lo16;
+            if (!make_tmap_f16(&tb_hi, tw.hi, (uint64_t)K, (uint64_t)N, (uint64_t)K, 64, 128) ||
+                !make_tmap_f16(&tb_lo16, tw.lo, (uint64_t)K, (uint64_t)N, (uint64_t)K, 64, 128))
+                return SFB_TC_UNSUPPORTED;
+            int rc16;
+            if (epi.head_part)
+                rc16 = launch_tc_ta_opw<false, false, true, true, true, 4, true>(ta, tb_hi, out, ld_out, M, N, K, k_chunk, splits, epi,
+                                                                                 st, &tb_lo16, a_bound);
+            else
+                rc16 = launch_tc_ta_opw<false, false, true, false, true, 4, true>(ta, tb_hi, out, ld_out, M, N, K, k_chunk, splits,
+                                                                                  epi, st, &tb_lo16, a_bound);
+            return rc16;
+        }
+    }
     if (BN == 128 && ta_enabled() && (b_mn || !a_mn)) {
         // A operand from TMEM (gemm_tc_ta_kernel); (A MN-major, B K-major) is not instantiated (no caller)
         // weight operand with a registered tf32-lo twin (forward layers and dX: B is the weight matrix)

@@ -94,7 +94,7 @@ policy_mlp2_heads_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
                          const __grid_constant__ CUtensorMap tmap_w2lo, const PsArgs a) {
     using S = PsSmem<KA>;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_align_1024(smem_raw);
     uint8_t* x_hi = smem;
     uint8_t* x_lo = smem + S::X_BYTES;
     uint8_t* stages = smem + S::OFF_STAGES;

@@ -115,7 +115,7 @@ rollout_mlp2_tape_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
                          const RolloutArgs a) {
     using S = RfSmem;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_align_1024(smem_raw);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::OFF_BARS);
     uint64_t* full = bars;                       // [4] A and B tiles landed (TMA)
     uint64_t* conv = bars + RF_STAGES;           // [4] A in TMEM (128 operand threads)

@@ -15,6 +15,12 @@ constexpr int TC_THREADS = 448;   // TMA, MMA, 4 split warps, 8 epilogue warps
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// 1024-byte aligned start inside the dynamic shared-memory window (the 128B swizzle atoms need it).  Plain pointer
+// arithmetic on the __shared__ array -- NOT a round trip through uintptr_t, which makes the compiler forget the address
+// space and emit generic LD.E / ST.E for every shared-memory access derived from it.
+__device__ __forceinline__ uint8_t* smem_align_1024(uint8_t* raw) {
+    return raw + ((1024u - (smem_u32(raw) & 1023u)) & 1023u);
+}
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -106,6 +112,17 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, u
         "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// kind::f16 (fp16 operands, fp32 accumulate), A from tensor memory: two K elements per 32-bit TMEM column
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 __device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&r)[32]) {
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
@@ -159,9 +176,20 @@ __host__ __device__ constexpr uint32_t make_idesc(bool a_mn, bool b_mn, int M, i
            ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// kind::f16 instruction descriptor: a/b format F16 = 0, c format F32 = 1, both operands K-major
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
 template <int ACT>
 __device__ __forceinline__ float act_fwd_ct(float z) {
-    if (ACT == SFB200_ACT_ELU) return z > 0.f ? z : (__expf(z) - 1.f);
+    if (ACT == SFB200_ACT_ELU) {
+        // __expf(z) - 1 for z <= 0, computed unconditionally: __expf is ex2.approx(z * log2(e)) plus a rescaling branch for
+        // results below 2^-126, which (e - 1) rounds to -1 either way -- same bits, half the instructions, no predication
+        float e;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * 1.4426950216293334961f));
+        return z > 0.f ? z : e - 1.f;
+    }
     if (ACT == SFB200_ACT_RELU) return fmaxf(z, 0.f);
     if (ACT == SFB200_ACT_TANH) return tanhf(z);
     return z;
@@ -179,5 +207,8 @@ __device__ __forceinline__ float act_bwd_ct(float h) {
 bool tc_init();
 bool make_tmap(CUtensorMap* out, const float* base, uint64_t dim0, uint64_t dim1, uint64_t stride1_elems, uint32_t box0,
                uint32_t box1, bool mn_major);
+// 2-D fp16 tensor map, K-major rows of 64 halfs = 128 B, 128B swizzle
+bool make_tmap_f16(CUtensorMap* out, const uint16_t* base, uint64_t dim0, uint64_t dim1, uint64_t stride1_elems, uint32_t box0,
+                   uint32_t box1);
 
 }  // namespace sfb

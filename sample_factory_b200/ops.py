@@ -281,6 +281,54 @@ def refresh_tf32_lo(base: Tensor) -> None:
     lib().call("sfb200_refresh_tf32_lo", _p(base, F32), _stream())
 
 
+def register_f16_twins(base: Tensor, twins: Tensor) -> None:
+    """Pair a flat weight buffer with its fp16 (hi, lo) twins [hi16[n] | lo16[n]] (include/sfb200.h) and fill them."""
+    assert base.is_contiguous() and twins.is_contiguous() and twins.dtype == torch.float16 and twins.numel() == 2 * base.numel()
+    lib().call("sfb200_register_f16_twins", _p(base, F32), twins.data_ptr(), base.numel())
+    refresh_f16_twins(base)
+
+
+def unregister_f16_twins(base: Tensor) -> None:
+    lib().call("sfb200_unregister_f16_twins", _p(base, F32))
+
+
+def refresh_f16_twins(base: Tensor) -> None:
+    lib().call("sfb200_refresh_f16_twins", _p(base, F32), _stream())
+
+
+def register_f16_transposed(W: Tensor, twinsT: Tensor) -> None:
+    """Transposed fp16 twins [hiT[K][N] | loT[K][N]] of one weight matrix W[N][K] (the weight operand of dX = dz . W)."""
+    N, K = W.shape
+    assert W.is_contiguous() and twinsT.dtype == torch.float16 and twinsT.numel() == 2 * N * K
+    lib().call("sfb200_register_f16_transposed", _p(W, F32), N, K, twinsT.data_ptr())
+    refresh_f16_transposed(W)
+
+
+def unregister_f16_transposed(W: Tensor) -> None:
+    lib().call("sfb200_unregister_f16_transposed", _p(W, F32))
+
+
+def refresh_f16_transposed(W: Tensor) -> None:
+    lib().call("sfb200_refresh_f16_transposed", _p(W, F32), _stream())
+
+
+def register_operand_bound(buf: Tensor, bound: Tensor) -> None:
+    """`bound` (one device float) is an upper bound of |x| over `buf`: GEMMs reading an activation operand inside `buf`
+    may use the fp16-split engine."""
+    assert bound.dtype == torch.float32 and bound.numel() == 1 and bound.is_cuda
+    lib().call("sfb200_register_operand_bound", buf.data_ptr(), buf.numel() * buf.element_size(), _p(bound, F32))
+
+
+def unregister_operand_bound(buf: Tensor) -> None:
+    lib().call("sfb200_unregister_operand_bound", buf.data_ptr())
+
+
+def linear_out_bound(W: Tensor, b: Optional[Tensor], in_bound: Tensor, out_bound: Tensor, act: int) -> None:
+    """out_bound = in_bound * max_n sum_k |W[n][k]| + max_n |b[n]| (an upper bound of |act(x W^T + b)| for |x| <= in_bound)"""
+    N, K = W.shape
+    lib().call("sfb200_linear_out_bound", _p(W, F32), _p(b, F32), N, K, _p(in_bound, F32), _p(out_bound, F32), act, _stream())
+
+
 def linear_heads_partials(N: int, A: int, engine: int) -> int:
     """Partials per row the fused last-layer + heads forward produces (0: not covered -> use the separate calls)."""
     return int(lib().query("sfb200_linear_heads_partials", N, A, engine))

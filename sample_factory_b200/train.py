@@ -59,8 +59,12 @@ class Runner:
     """Single-policy runner (runner.py:81-184 attributes that examples/tests read are kept: env_steps, policy_avg_stats,
     register_observer / register_msg_handler hooks)."""
 
-    def __init__(self, cfg):
+    def __init__(self, cfg, population=(0, 1)):
         self.cfg = cfg
+        # (index, size) of this policy in a population (multi_policy.MultiPolicyRunner): it owns 1/size of the envs, the
+        # reference's sync-mode agent -> policy mapping (agent_policy_mapping.py:39-45: global env index % num_policies)
+        self.population = population
+        self.policy_id = int(getattr(cfg, "policy_id", 0))
         self.env_steps = 0
         self.total_train_seconds = 0.0
         self.policy_avg_stats: Dict[str, List[deque]] = {}
@@ -104,16 +108,27 @@ class Runner:
         n_splits = int(cfg.worker_num_splits) if (cfg.batched_sampling and cfg.worker_num_splits > 1 and
                                                    cfg.num_envs_per_worker == cfg.worker_num_splits) else 1
         self.envs = []
+        p_idx, p_cnt = self.population
+        n_host = None
+        if p_cnt > 1:
+            total = int(cfg.num_workers) * int(cfg.num_envs_per_worker)
+            if total % p_cnt != 0:          # agent_policy_mapping.py:35-37
+                raise ValueError(f"total_envs={total} must be divisible by num_policies={p_cnt}")
+            n_host = total // p_cnt
         for s_ in range(n_splits):
-            env_config = dict(worker_index=self.rank, vector_index=s_, env_id=self.rank * n_splits + s_)
-            self.envs.append(create_batched_env(cfg, env_config, self.device))
+            slot = (self.rank * p_cnt + p_idx) * n_splits + s_
+            env_config = dict(worker_index=self.rank * p_cnt + p_idx, vector_index=s_, env_id=slot)
+            if p_cnt > 1:       # a factory that returns a batched device env sizes it for one policy's share itself
+                env_config.update(policy_index=p_idx, num_policies=p_cnt)
+            self.envs.append(create_batched_env(cfg, env_config, self.device, num_envs=n_host))
         self.env = self.envs[0]
         from .model_factory import global_model_factory
 
         global_model_factory().check_supported()      # custom torch modules: explicit error through the registry API
         spec = ModelSpec.from_cfg(cfg, self.env)
         assert cfg.rnn_num_layers == 1, "the device path implements the one-layer recurrent core"
-        self.model = PolicyModel(spec, self.device, seed=cfg.seed or 0, policy_init_gain=cfg.policy_init_gain,
+        # (population members start from different weights: seed + index)
+        self.model = PolicyModel(spec, self.device, seed=(cfg.seed or 0) + p_idx, policy_init_gain=cfg.policy_init_gain,
                                  policy_initialization=getattr(cfg, "policy_initialization", "orthogonal"))
         N = sum(e.num_agents for e in self.envs)
         self.engine = select_engine(cfg)
@@ -134,7 +149,7 @@ class Runner:
         else:
             self.sampler_model, self.sampler_traj = self.model, self.traj
         sampler_kw = dict(engine=self.engine, use_cuda_graph=bool(getattr(cfg, "cuda_graph", True)),
-                          philox_seed=(cfg.seed or 0) * 1000003 + self.rank)
+                          philox_seed=(cfg.seed or 0) * 1000003 + self.rank * p_cnt + p_idx)
         if n_splits > 1:
             self.sampler = SplitSampler(cfg, self.envs, self.sampler_model, self.sampler_traj, **sampler_kw)
         else:
@@ -160,7 +175,7 @@ class Runner:
             self.accum = alloc_for_spec(spec, n_learn, T, self.device)
             self._acc_fill = 0
         if cfg.restart_behavior == "resume":
-            ck = load_checkpoint(cfg, self.model, self.device)
+            ck = load_checkpoint(cfg, self.model, self.device, policy_id=self.policy_id)
             if ck is not None:
                 self.learner.train_step, self.learner.env_steps = ck["train_step"], ck["env_steps"]
                 self.learner.opt_step = ck["opt_step"]
@@ -170,12 +185,13 @@ class Runner:
                     self.sampler_model.copy_weights_from(self.model)
                     self.snapshot_version = self.learner.train_step
         if self.rank == 0:
-            with open(os.path.join(experiment_dir(cfg), "config.json"), "w") as f:
-                json.dump({k: v for k, v in vars(cfg).items() if _jsonable(v)}, f, indent=2)
+            if p_idx == 0:
+                with open(os.path.join(experiment_dir(cfg), "config.json"), "w") as f:
+                    json.dump({k: v for k, v in vars(cfg).items() if _jsonable(v)}, f, indent=2)
             from .tb_writer import SummaryWriter
 
             # runner.py:199-205: <experiment_dir>/.summary/<policy_id>/events.out.tfevents.*
-            self.writers[0] = SummaryWriter(os.path.join(experiment_dir(cfg), ".summary", "0"))
+            self.writers[self.policy_id] = SummaryWriter(os.path.join(experiment_dir(cfg), ".summary", str(self.policy_id)))
         self.sampler.reset()
         self.initialized = True
         return StatusCode.SUCCESS
@@ -259,7 +275,7 @@ class Runner:
 
     def _report_experiment_summaries(self, fps: float, train_stats: Dict[str, float]) -> None:
         """runner.py:368-423 (+ the learner's train summaries, learner.py:843-923) as tensorboard scalars"""
-        w = self.writers.get(0)
+        w = self.writers.get(self.policy_id)
         if w is None:
             return
         steps = self.env_steps

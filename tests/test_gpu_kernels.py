@@ -136,6 +136,82 @@ def test_tc_engine_precision_classes(dev):
     assert errs["tf32"] > 20 * errs["3xtf32"] and errs["tf32"] < 2e-2, errs
 
 
+@pytest.mark.parametrize("M,N,K,amp", [(2048, 512, 512, 1.0), (4096, 512, 64, 1.0), (32768, 512, 512, 1.0), (2048, 256, 512, 1e-6),
+                                        (1000, 384, 128, 300.0)])
+def test_fp16_split_engine_is_fp32_grade(dev, M, N, K, amp):
+    """The fp16-split form of the 3-pass engine (registered fp16 weight twins + a registered activation bound): same
+    accuracy class as 3xTF32 against fp64 -- forward (with bias / ELU), and dX through the transposed twins -- for
+    activations of very different magnitudes (the bound sets the power-of-two operand shift) and a loose bound."""
+    ops = _ops()
+    if not ops.tc_available():
+        pytest.skip("tcgen05 engine not available")
+    x = (torch.randn(M, K, generator=g(170)) * amp).to(dev)
+    W = (torch.randn(N, K, generator=g(171)) / math.sqrt(K)).to(dev).contiguous()
+    b = (torch.randn(N, generator=g(172)) * 0.1 * amp).to(dev)
+    # (the epilogue's ELU is exp(z) - 1 with 2.4e-7 ABSOLUTE error: not the subject here, so tiny outputs go without it)
+    act = "elu" if amp >= 1e-3 else "none"
+    ref = torch.nn.functional.linear(x.double(), W.double(), b.double())
+    if act == "elu":
+        ref = torch.nn.functional.elu(ref)
+    scale = max(ref.abs().max().item(), 1e-30)
+    out_tf32 = torch.empty(M, N, device=dev)
+    ops.linear_act_forward(x, W, b, out_tf32, ops.ACT[act], ops.GEMM_TC_3XTF32)
+    err_tf32 = (out_tf32.double() - ref).abs().max().item()
+    twins = torch.empty(2 * W.numel(), dtype=torch.float16, device=dev)
+    twinsT = torch.empty(2 * W.numel(), dtype=torch.float16, device=dev)
+    bound = torch.full((1,), float(x.abs().max().item()) * 3.0, device=dev)        # a loose bound is as good as a tight one
+    n0 = ops.launch_count()
+    ops.register_f16_twins(W.view(-1), twins)
+    ops.register_f16_transposed(W, twinsT)
+    ops.register_operand_bound(x, bound)
+    try:
+        # the twins are what they claim to be
+        hi, lo = twins[: W.numel()].float().view(N, K), twins[W.numel():].float().view(N, K)
+        np.testing.assert_allclose(((hi + lo / 2048.0) / 256.0).cpu().numpy(), W.cpu().numpy(), rtol=3e-7, atol=1e-12)
+        hiT = twinsT[: W.numel()].float().view(K, N)
+        assert torch.equal(hiT, hi.t())
+        out = torch.empty(M, N, device=dev)
+        ops.linear_act_forward(x, W, b, out, ops.ACT[act], ops.GEMM_TC_3XTF32)
+        err = (out.double() - ref).abs().max().item()
+        print(f"forward  max abs err vs fp64 (scale {scale:.3g}): fp16-split {err:.3e}   3xTF32 {err_tf32:.3e}")
+        assert err < 3e-6 * scale, (err, scale)
+        assert not torch.equal(out, out_tf32), "the fp16-split kernel did not run (bit-identical to the tf32 split)"
+        # dX = dz . W (* act'(x)) with the transposed twins; dz carries its own bound
+        dz = (torch.randn(M, N, generator=g(173)) * amp * 1e-3).to(dev)
+        dbound = torch.full((1,), float(dz.abs().max().item()), device=dev)
+        ops.register_operand_bound(dz, dbound)
+        xa = torch.nn.functional.elu(torch.randn(M, K, generator=g(174))).to(dev)
+        ws = torch.empty(ops.linear_backward_workspace_bytes(M, N, K) // 4 + 4, device=dev)
+        dx = torch.empty(M, K, device=dev)
+        ops.linear_backward(dz, xa, W, ops.ACT["elu"], None, dx, None, ops.GEMM_TC_3XTF32, ws)
+        dref = (dz.double() @ W.double()) * torch.where(xa > 0, torch.ones_like(xa), xa + 1).double()
+        derr = (dx.double() - dref).abs().max().item()
+        dscale = dref.abs().max().item()
+        print(f"dX       max abs err vs fp64 (scale {dscale:.3g}): fp16-split {derr:.3e}")
+        assert derr < 3e-6 * dscale, (derr, dscale)
+        ops.unregister_operand_bound(dz)
+    finally:
+        ops.unregister_operand_bound(x)
+        ops.unregister_f16_transposed(W)
+        ops.unregister_f16_twins(W.view(-1))
+    assert ops.launch_count() > n0
+
+
+def test_linear_out_bound(dev):
+    ops = _ops()
+    W = torch.randn(96, 40, generator=g(180)).to(dev)
+    b = torch.randn(96, generator=g(181)).to(dev)
+    inb = torch.full((1,), 5.0, device=dev)
+    out = torch.zeros(1, device=dev)
+    ops.linear_out_bound(W, b, inb, out, ops.ACT["elu"])
+    expect = 5.0 * W.abs().sum(1).max().item() + b.abs().max().item()
+    assert expect <= out.item() <= expect * 1.001
+    x = (torch.rand(4096, 40, generator=g(182)) * 10 - 5).to(dev)
+    assert torch.nn.functional.elu(torch.nn.functional.linear(x, W, b)).abs().max().item() <= out.item()
+    ops.linear_out_bound(W, b, inb, out, ops.ACT["tanh"])
+    assert out.item() == 1.0
+
+
 def test_linear_forward_strided_input(dev):
     """The learner feeds obs[:, T] rows in place: x row stride != K."""
     ops = _ops()

@@ -36,9 +36,24 @@ for (M, N, K) in [(32768, 512, 512), (32768, 512, 64)]:
     dz = torch.randn(M, N, device=dev)
     dW, dx = torch.empty(N, K, device=dev), torch.empty(M, K, device=dev)
     ws = torch.empty(ops.linear_backward_workspace_bytes(M, N, K) // 4 + 4, device=dev)
+    y = torch.empty(M, N, device=dev)
+    b = torch.zeros(N, device=dev)
+    t_fw = timeit(lambda: ops.linear_act_forward(x, W, b, y, ops.ACT["elu"], eng))
+    print(f"M={M} N={N} K={K}: fwd {t_fw:.1f} us ({2*M*N*K/t_fw/1e6:.0f} TFLOP/s)")
     t_dw = timeit(lambda: ops.linear_backward(dz, x, W, ops.ACT["elu"], dW, None, None, eng, ws))
     t_dx = timeit(lambda: ops.linear_backward(dz, x, W, ops.ACT["elu"], None, dx, None, eng, ws))
     print(f"M={M} N={N} K={K}: dW {t_dw:.1f} us ({2*M*N*K/t_dw/1e6:.0f} TFLOP/s)  dX {t_dx:.1f} us ({2*M*N*K/t_dx/1e6:.0f} TFLOP/s)")
+    if K % 64 == 0:
+        twins = torch.empty(2 * N * K, dtype=torch.float16, device=dev)
+        twinsT = torch.empty(2 * N * K, dtype=torch.float16, device=dev)
+        ops.register_f16_twins(flat, twins); ops.register_f16_transposed(W, twinsT)
+        bx = torch.full((1,), float(x.abs().max()), device=dev); bz = torch.full((1,), float(dz.abs().max()), device=dev)
+        ops.register_operand_bound(x, bx); ops.register_operand_bound(dz, bz)
+        t_fw16 = timeit(lambda: ops.linear_act_forward(x, W, b, y, ops.ACT["elu"], eng))
+        t_dx16 = timeit(lambda: ops.linear_backward(dz, x, W, ops.ACT["elu"], None, dx, None, eng, ws))
+        print(f"M={M} N={N} K={K}: fp16-split fwd {t_fw16:.1f} us ({2*M*N*K/t_fw16/1e6:.0f} TFLOP/s)  dX {t_dx16:.1f} us ({2*M*N*K/t_dx16/1e6:.0f} TFLOP/s)")
+        ops.unregister_operand_bound(x); ops.unregister_operand_bound(dz)
+        ops.unregister_f16_transposed(W); ops.unregister_f16_twins(flat)
     ref = dz.double().t() @ x.double()
     print("   dW max abs err vs fp64:", float((dW.double() - ref).abs().max()), "of max", float(ref.abs().max()))
     ops.unregister_tf32_lo(flat)
