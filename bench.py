@@ -630,7 +630,7 @@ def run_ours(args):
     if rank == 0:
         out = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                    ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None,
-                   dtype="f32" + (" (3xTF32 split on tcgen05, fp32 accumulate)" if engine_name == "tcgen05-3xTF32" else ""),
+                   dtype="f32" + (" (3-pass operand split on tcgen05 -- scaled fp16 hi/lo pairs where the operand ranges are known, tf32 hi/lo pairs elsewhere -- fp32 accumulate in TMEM)" if engine_name == "tcgen05-3xTF32" else ""),
                    data="synthetic",
                    config=dict(workload=WORKLOAD, envs_per_gpu=N_ENVS, rollout=ROLLOUT, global_batch=BATCH * N_MINIBATCH * world,
                                parallelism=f"dp{world} (env shards; per SGD step ONE kernel = NVLink peer all-reduce + grad-norm + clip + Adam)", gemm_engine=engine_name,

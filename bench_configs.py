@@ -317,7 +317,7 @@ def run_config(args, load_peaks, ClockSampler):
     if rank == 0:
         out = dict(metric=METRIC + f" -- {c['name']}", value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                    ms_per_step=ms_total / args.steps, higher_is_better=True, scaling="strong" if c["envs_total"] else "weak",
-                   vs_baseline=None, dtype="f32 (3xTF32 split on tcgen05, fp32 accumulate)", data="synthetic",
+                   vs_baseline=None, dtype="f32 (3-pass operand split on tcgen05 -- scaled fp16 hi/lo pairs where the operand ranges are known, tf32 hi/lo pairs elsewhere -- fp32 accumulate in TMEM)", data="synthetic",
                    config=dict(workload=c["name"], envs_per_gpu=n_envs, rollout=T, global_batch=world * n_envs * T,
                                parallelism=f"dp{world}", async_rl=c["async_rl"], cuda_graph_learner=learner_graph,
                                l2_policy="trajectory set + learner activations exceed the 126 MB L2; no explicit flush"),

@@ -78,6 +78,11 @@ int sfb200_register_operand_bound(const void* base, int64_t bytes, const float* 
 int sfb200_unregister_operand_bound(const void* base);
 int sfb200_linear_out_bound(const float* W, const float* b, int N, int K, const float* in_bound_dev, float* out_bound_dev,
                             int act, void* stream);
+/* bound of the gradient sfb200_heads_backward writes for the last hidden layer (the activation operand of dX):
+ * max_m (|dvalues[m]| + sum_a |dlogits[m][a]|) * max(|Wv|_inf, |Wa|_inf); act' <= 1 for every supported activation.
+ * out_bound_dev: THREE 32-bit words [bound, scratch, counter], the last two zero on entry and on return. */
+int sfb200_heads_dz_bound(const float* dlogits, const float* dvalues, int64_t rows, int A, const float* Wv, const float* Wa,
+                          int H, float* out_bound_dev, void* stream);
 /* total number of CUDA kernels this library has launched (or recorded into a stream capture) in this process */
 uint64_t sfb200_launch_count(void);
 

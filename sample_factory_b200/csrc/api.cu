@@ -121,6 +121,50 @@ __global__ void __launch_bounds__(1024) linear_out_bound_kernel(const float* __r
     }
 }
 
+// Upper bound of the gradient that heads_backward writes for the last hidden layer:
+// |dz[m][j]| = |dv[m] Wv[j] + sum_a dl[m][a] Wa[a][j]| * |act'| <= (|dv[m]| + sum_a |dl[m][a]|) * max(|Wv|_inf, |Wa|_inf),
+// act' <= 1 for ELU / ReLU / tanh.  1.2 MB of per-sample gradients at the cfg-2 minibatch: 64 blocks take the row maxima
+// (atomicMax on the bit pattern of a non-negative float), the block that arrives last folds in the weight maximum.
+// out = [bound, scratch bits, arrival counter]; scratch and counter are left at zero.
+__global__ void __launch_bounds__(256) heads_dz_bound_kernel(const float* __restrict__ dlogits, const float* __restrict__ dvalues,
+                                                            int64_t rows, int A, const float* __restrict__ Wv,
+                                                            const float* __restrict__ Wa, int H, float* __restrict__ out) {
+    __shared__ float s_r[8];
+    __shared__ int s_last;
+    unsigned int* scratch = reinterpret_cast<unsigned int*>(out) + 1;
+    float r = 0.f;
+    for (int64_t m = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; m < rows; m += (int64_t)gridDim.x * blockDim.x) {
+        float t = fabsf(dvalues[m]);
+        for (int a = 0; a < A; ++a) t += fabsf(dlogits[m * A + a]);
+        r = fmaxf(r, t);
+    }
+    for (int o = 16; o > 0; o >>= 1) r = fmaxf(r, __shfl_xor_sync(0xffffffffu, r, o));
+    if ((threadIdx.x & 31) == 0) s_r[threadIdx.x >> 5] = r;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < 8; ++i) r = fmaxf(r, s_r[i]);
+        atomicMax(scratch, __float_as_uint(r));
+        __threadfence();
+        s_last = atomicAdd(scratch + 1, 1u) == gridDim.x - 1 ? 1 : 0;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    float w = 0.f;
+    for (int i = threadIdx.x; i < H; i += blockDim.x) w = fmaxf(w, fabsf(Wv[i]));
+    for (int i = threadIdx.x; i < A * H; i += blockDim.x) w = fmaxf(w, fabsf(Wa[i]));
+    for (int o = 16; o > 0; o >>= 1) w = fmaxf(w, __shfl_xor_sync(0xffffffffu, w, o));
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s_r[threadIdx.x >> 5] = w;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < 8; ++i) w = fmaxf(w, s_r[i]);
+        out[0] = __uint_as_float(*reinterpret_cast<volatile unsigned int*>(scratch)) * w * 1.0001f;
+        scratch[0] = 0u;
+        scratch[1] = 0u;
+    }
+}
+
 bool tf32_lo_check_enabled() {
     static int v = -1;
     if (v < 0) {
@@ -319,6 +363,14 @@ int sfb200_linear_out_bound(const float* W, const float* b, int N, int K, const 
                             int act, void* stream) {
     SFB_CHECK_ARG(W && in_bound_dev && out_bound_dev && N > 0 && K > 0, "linear_out_bound: bad arguments");
     sfb::linear_out_bound_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(W, b, N, K, in_bound_dev, out_bound_dev, act);
+    SFB_LAUNCH_OK();
+    return 0;
+}
+
+int sfb200_heads_dz_bound(const float* dlogits, const float* dvalues, int64_t rows, int A, const float* Wv, const float* Wa,
+                          int H, float* out_bound_dev, void* stream) {
+    SFB_CHECK_ARG(dlogits && dvalues && Wv && Wa && out_bound_dev && rows > 0 && A > 0 && H > 0, "heads_dz_bound: bad arguments");
+    sfb::heads_dz_bound_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(dlogits, dvalues, rows, A, Wv, Wa, H, out_bound_dev);
     SFB_LAUNCH_OK();
     return 0;
 }

@@ -164,6 +164,7 @@ struct EpiCtx {
     bool vec_ok, aux_vec, bias_vec, st_v8, aux_v8;
     const float* bias_base;
     float out_scale;     // fp16-split engine: 2^-(operand shifts); 1 otherwise
+    bool probe_no_store;
 };
 
 // Epilogue warps 6..13: warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32); warps 6..9 take columns [0, BN/2) of their
@@ -190,6 +191,7 @@ __device__ __forceinline__ EpiCtx make_epi_ctx(int warp, int lane, const float* 
     ec.bias_vec = epi.bias && (bias_smem || ((reinterpret_cast<uintptr_t>(epi.bias) & 15u) == 0));
     ec.mode = splits == 1 ? epi.mode : 0;
     ec.out_scale = 1.f;
+    ec.probe_no_store = false;
     return ec;
 }
 
@@ -273,6 +275,13 @@ __device__ __forceinline__ void tc_epilogue_tile(uint32_t tmem_slot_addr, uint64
             }
         }
         float* dst = dst_row + c0;
+        if (ec.probe_no_store) {          // SFB200_TA_PROBE=256: how much of a tile is the epilogue's arithmetic + global stores?
+            float t = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) t += acc[j];
+            if (t == 123.456f) dst[0] = t;
+            continue;
+        }
         if (fast) {
             // whole row segment in bounds, 128-bit everything; mode / activation resolved once per chunk into
             // a straight-line specialisation (a per-element switch cost 4x the instructions)
@@ -596,7 +605,7 @@ __global__ void __launch_bounds__(ta_threads(TA_OPW), 1)
 gemm_tc_ta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                   const __grid_constant__ CUtensorMap tmap_b_lo, float* __restrict__ C, int64_t ldc, int64_t M, int N,
                   int K, int k_chunk, int splits, TcEpilogue epi, int flags, const float* __restrict__ a_bound) {
-    static_assert(!F16 || (!A_MN && !B_MN && SPLIT3 && BLO && TA_OPW == 4), "fp16-split engine: K-major operands, weight twins");
+    static_assert(!F16 || (!A_MN && !B_MN && SPLIT3 && BLO), "fp16-split engine: K-major operands, weight twins");
     constexpr int BN = 128, STAGES = F16 ? TA_F16_STAGES : TA_STAGES;
     constexpr int KB_K = F16 ? 64 : TBK;                    // k per pipeline stage
     const int raw_hi = flags & 1;
@@ -747,22 +756,28 @@ gemm_tc_ta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 tc_fence_after();
                 uint8_t* sb = smem + s * S::STAGE_BYTES;
                 if constexpr (F16) {
-                    // 64 k of this thread's row: two 128 B swizzled rows (one per 32-k box) -> 32 + 32 packed half2 words
-                    uint32_t h16[32], l16[32];
+                    // 64 k of a tile row = two 128 B swizzled rows (one per 32-k box) -> 32 + 32 packed half2 words of TMEM.
+                    // Four operand warps: a thread converts both boxes of its row; eight: one box each (the warps of a
+                    // lane quadrant work on the same stage at the same time: half the per-stage conversion latency).
+                    constexpr int BOXES = TA_OPW == 8 ? 1 : 2;
+                    const int box0 = TA_OPW == 8 ? ((warp - 2) >> 2) : 0;
+                    uint32_t h16[16 * BOXES], l16[16 * BOXES];
 #pragma unroll
-                    for (int box = 0; box < 2; ++box) {
-                        const uint4* arow = reinterpret_cast<const uint4*>(sb + 2 * S::B_BYTES + box * 16384 + row * 128);
+                    for (int bx = 0; bx < BOXES; ++bx) {
+                        const uint4* arow = reinterpret_cast<const uint4*>(sb + 2 * S::B_BYTES + (box0 + bx) * 16384 + row * 128);
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             const uint4 q = arow[j ^ sw];
-                            f16_split2(__uint_as_float(q.x) * a_scale, __uint_as_float(q.y) * a_scale, h16[box * 16 + 2 * j],
-                                       l16[box * 16 + 2 * j]);
-                            f16_split2(__uint_as_float(q.z) * a_scale, __uint_as_float(q.w) * a_scale, h16[box * 16 + 2 * j + 1],
-                                       l16[box * 16 + 2 * j + 1]);
+                            f16_split2(__uint_as_float(q.x) * a_scale, __uint_as_float(q.y) * a_scale, h16[bx * 16 + 2 * j],
+                                       l16[bx * 16 + 2 * j]);
+                            f16_split2(__uint_as_float(q.z) * a_scale, __uint_as_float(q.w) * a_scale, h16[bx * 16 + 2 * j + 1],
+                                       l16[bx * 16 + 2 * j + 1]);
                         }
                     }
-                    tmem_st_32x32b_x32(lane_addr + (uint32_t)s * 64u, h16);
-                    tmem_st_32x32b_x32(lane_addr + (uint32_t)s * 64u + 32u, l16);
+                    const uint32_t st_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + TA_ACOL0 + (uint32_t)s * 64u +
+                                             (uint32_t)box0 * 16u;
+                    tmem_st_cols<16 * BOXES>(st_addr, h16);
+                    tmem_st_cols<16 * BOXES>(st_addr + 32u, l16);
                     tmem_st_wait();
                     tc_fence_before();
                     mbar_arrive(&conv[s]);
@@ -844,6 +859,7 @@ gemm_tc_ta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         }
         EpiCtx ec = make_epi_ctx<BN, TA_EPI_WARP0>(warp, lane, C, ldc, N, splits, epi, bias_s, S::BIAS_FLOATS);
         if (F16) ec.out_scale = pow2f_int(-(a_shift + kF16WShift));
+        ec.probe_no_store = (flags & 256) != 0;
         uint32_t tile_iter = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_iter) {
             const TileCoord tc = tile_coord(tile, tiles_n, tiles_per_z, BN, K, k_chunk);
@@ -989,7 +1005,7 @@ static int ta_probe_bits() {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("SFB200_TA_PROBE");
-        v = e ? (atoi(e) & 0xfe) : 0;   // 16 = skip the B_lo TMA load, 32/64/128 = L2 prefetch of the A tiles 4/8/16 k-blocks ahead
+        v = e ? (atoi(e) & 0x1fe) : 0;   // 16 = skip the B_lo TMA load, 32/64/128 = L2 prefetch of the A tiles 4/8/16 k-blocks ahead
     }
     return v;
 }
@@ -1106,12 +1122,22 @@ static int gemm_tc(bool a_mn, const float* A, int64_t lda, bool b_mn, const floa
                 !make_tmap_f16(&tb_lo16, tw.lo, (uint64_t)K, (uint64_t)N, (uint64_t)K, 64, 128))
                 return SFB_TC_UNSUPPORTED;
             int rc16;
-            if (epi.head_part)
-                rc16 = launch_tc_ta_opw<false, false, true, true, true, 4, true>(ta, tb_hi, out, ld_out, M, N, K, k_chunk, splits, epi,
-                                                                                 st, &tb_lo16, a_bound);
-            else
-                rc16 = launch_tc_ta_opw<false, false, true, false, true, 4, true>(ta, tb_hi, out, ld_out, M, N, K, k_chunk, splits,
-                                                                                  epi, st, &tb_lo16, a_bound);
+            static int opw = -1;
+            if (opw < 0) {
+                const char* e = getenv("SFB200_F16_OPW");
+                opw = (e && e[0] == '8') ? 8 : 4;      // (measured: eight operand warps gain nothing, the epilogue spills)
+            }
+            if (epi.head_part) {
+                rc16 = opw == 8 ? launch_tc_ta_opw<false, false, true, true, true, 8, true>(ta, tb_hi, out, ld_out, M, N, K, k_chunk,
+                                                                                            splits, epi, st, &tb_lo16, a_bound)
+                                : launch_tc_ta_opw<false, false, true, true, true, 4, true>(ta, tb_hi, out, ld_out, M, N, K, k_chunk,
+                                                                                            splits, epi, st, &tb_lo16, a_bound);
+            } else {
+                rc16 = opw == 8 ? launch_tc_ta_opw<false, false, true, false, true, 8, true>(ta, tb_hi, out, ld_out, M, N, K, k_chunk,
+                                                                                             splits, epi, st, &tb_lo16, a_bound)
+                                : launch_tc_ta_opw<false, false, true, false, true, 4, true>(ta, tb_hi, out, ld_out, M, N, K, k_chunk,
+                                                                                             splits, epi, st, &tb_lo16, a_bound);
+            }
             return rc16;
         }
     }

@@ -29,15 +29,20 @@
 namespace sfb {
 
 constexpr int RF_THREADS = 448;
-constexpr int RF_STAGES = 4;
-constexpr int RF_TILE_BYTES = 128 * TBK * 4;          // 16 KB: one [128 rows][32 fp32] K-major swizzled tile
-constexpr int RF_STAGE_BYTES = 3 * RF_TILE_BYTES;     // [B hi | B lo | A raw]
+constexpr int RF_TILE_BYTES = 128 * TBK * 4;          // 16 KB: one [128 rows][32 fp32] (or [128][64 fp16]) K-major swizzled tile
+// tf32 split: 4 stages of 32 k, [B hi | B lo | A raw].  fp16 split (F16): 3 stages of 64 k, [B hi16 | B lo16 | A raw x 2]
+template <bool F16> struct RfPipe {
+    static constexpr int STAGES = F16 ? 3 : 4;
+    static constexpr int KB_K = F16 ? 64 : 32;
+    static constexpr int STAGE_BYTES = (F16 ? 4 : 3) * RF_TILE_BYTES;
+};
+constexpr int RF_MAX_STAGES = 4;
 constexpr uint32_t RF_ACOL0 = 256;                    // TMEM: accumulator [0,256) (main | cross), A stages [256, 512)
 constexpr int RF_HEAD_AP = 9;
 constexpr int RF_MAX_DIM = 128;
 
 struct RfSmem {
-    static constexpr int OFF_BARS = RF_STAGES * RF_STAGE_BYTES;
+    static constexpr int OFF_BARS = 4 * 3 * RF_TILE_BYTES;      // == 3 * 4 * RF_TILE_BYTES: both pipelines fill 192 KB
     static constexpr int OFF_B1 = OFF_BARS + 256;
     static constexpr int OFF_B2 = OFF_B1 + 128 * 4;
     static constexpr int OFF_HEADW = OFF_B2 + 128 * 4;
@@ -64,6 +69,7 @@ struct RolloutArgs {
     const double* mean; const double* var; float sub, inv_scale; int do_sub, do_scale; float eps, clip;
     unsigned int* ticket;
     unsigned long long* trace;   // debug: [T][16] globaltimer stamps of CTA (0,0)'s first epilogue thread, or NULL
+    const float* bound_x; const float* bound_h1;   // fp16-split form: bounds of |x_norm| and |h1| (device floats), else NULL
 };
 
 __device__ __forceinline__ void cluster_sync_all() {
@@ -107,22 +113,23 @@ __device__ __forceinline__ void rf_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
-template <int ACT>
+template <int ACT, bool F16>
 __global__ void __launch_bounds__(RF_THREADS, 1)
 rollout_mlp2_tape_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w1,
                          const __grid_constant__ CUtensorMap tmap_w1lo, const __grid_constant__ CUtensorMap tmap_h1,
                          const __grid_constant__ CUtensorMap tmap_w2, const __grid_constant__ CUtensorMap tmap_w2lo,
                          const RolloutArgs a) {
     using S = RfSmem;
+    constexpr int RF_STAGES = RfPipe<F16>::STAGES, RF_STAGE_BYTES = RfPipe<F16>::STAGE_BYTES, KB_K = RfPipe<F16>::KB_K;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_align_1024(smem_raw);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::OFF_BARS);
-    uint64_t* full = bars;                       // [4] A and B tiles landed (TMA)
-    uint64_t* conv = bars + RF_STAGES;           // [4] A in TMEM (128 operand threads)
-    uint64_t* empty = bars + 2 * RF_STAGES;      // [4] MMAs of the stage retired
-    uint64_t* acc_full = bars + 3 * RF_STAGES;
-    uint64_t* acc_empty = bars + 3 * RF_STAGES + 1;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * RF_STAGES + 2);
+    uint64_t* full = bars;                       // [stages] A and B tiles landed (TMA)
+    uint64_t* conv = bars + RF_MAX_STAGES;       // [stages] A in TMEM (128 operand threads)
+    uint64_t* empty = bars + 2 * RF_MAX_STAGES;  // [stages] MMAs of the stage retired
+    uint64_t* acc_full = bars + 3 * RF_MAX_STAGES;
+    uint64_t* acc_empty = bars + 3 * RF_MAX_STAGES + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * RF_MAX_STAGES + 2);
     float* b1_s = reinterpret_cast<float*>(smem + S::OFF_B1);         // this CTA's 128 columns of b1
     float* b2_s = reinterpret_cast<float*>(smem + S::OFF_B2);
     float* headw_s = reinterpret_cast<float*>(smem + S::OFF_HEADW);   // [9][128]
@@ -138,7 +145,7 @@ rollout_mlp2_tape_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
     const int CX = gridDim.x;
     const int n0 = cx * 128;
     const int64_t m0 = (int64_t)blockIdx.y * 128;
-    const int KB1 = a.K1 / 32, KB2 = a.H1 / 32;
+    const int KB1 = a.K1 / KB_K, KB2 = a.H1 / KB_K;
     const int P = 2 * CX;
     const bool do_rms = a.mean != nullptr;
 
@@ -177,6 +184,10 @@ rollout_mlp2_tape_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
             for (int c = et; c < a.K1; c += 256) col_stats(a.mean, a.var, c, a.eps, cstat[c], cstat[a.K1 + c]);
     }
     __syncthreads();
+    // fp16-split form: binary shifts of the two activation operands from their bounds (constant over the rollout: the
+    // weights, hence the bounds, do not change inside a rollout)
+    const int shift_x = F16 ? f16_shift_for_bound(a.bound_x[0]) : 0;
+    const int shift_h = F16 ? f16_shift_for_bound(a.bound_h1[0]) : 0;
     const int64_t env_step0 = a.env_step[0];
     const uint64_t philox0 = a.sampler_step ? (uint64_t)*a.sampler_step : 0ull;
     const float pv = a.pv_scalar ? *a.pv_scalar : 0.f;
@@ -206,10 +217,11 @@ rollout_mlp2_tape_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
                         if (kb >= pref) {      // (the first `pref` stages were armed and their weight tiles requested before the barrier)
                             rf_wait(&empty[s], ((i / RF_STAGES) & 1) ^ 1);
                             mbar_expect_tx(&full[s], RF_STAGE_BYTES);
-                            tma_load_2d(sb, tb, &full[s], kb * 32, n0);
-                            tma_load_2d(sb + RF_TILE_BYTES, tbl, &full[s], kb * 32, n0);
+                            tma_load_2d(sb, tb, &full[s], kb * KB_K, n0);
+                            tma_load_2d(sb + RF_TILE_BYTES, tbl, &full[s], kb * KB_K, n0);
                         }
-                        tma_load_2d(sb + 2 * RF_TILE_BYTES, ta, &full[s], kb * 32, (int)m0);
+                        tma_load_2d(sb + 2 * RF_TILE_BYTES, ta, &full[s], kb * KB_K, (int)m0);
+                        if (F16) tma_load_2d(sb + 3 * RF_TILE_BYTES, ta, &full[s], kb * KB_K + 32, (int)m0);
                     }
                     // weight tiles of the NEXT tile do not depend on the cluster barrier: request them now, so that only the
                     // activation tiles' latency is exposed after it
@@ -226,16 +238,16 @@ rollout_mlp2_tape_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
                             uint8_t* sb = smem + s * RF_STAGE_BYTES;
                             rf_wait(&empty[s], ((i / RF_STAGES) & 1) ^ 1);
                             mbar_expect_tx(&full[s], RF_STAGE_BYTES);
-                            tma_load_2d(sb, nb, &full[s], kb * 32, n0);
-                            tma_load_2d(sb + RF_TILE_BYTES, nbl, &full[s], kb * 32, n0);
+                            tma_load_2d(sb, nb, &full[s], kb * KB_K, n0);
+                            tma_load_2d(sb + RF_TILE_BYTES, nbl, &full[s], kb * KB_K, n0);
                         }
                     }
                 }
                 __syncwarp();
             } else if (warp == 1) {
                 // ===================================================== MMA issuer
-                constexpr uint32_t idesc_wide = make_idesc(false, false, TBM, 256);
-                constexpr uint32_t idesc_cross = make_idesc(false, false, TBM, 128);
+                constexpr uint32_t idesc_wide = F16 ? make_idesc_f16(TBM, 256) : make_idesc(false, false, TBM, 256);
+                constexpr uint32_t idesc_cross = F16 ? make_idesc_f16(TBM, 128) : make_idesc(false, false, TBM, 128);
                 rf_wait(acc_empty, (tile_iter & 1) ^ 1);
                 tc_fence_after();
                 for (int kb = 0; kb < num_kb; ++kb) {
@@ -249,7 +261,12 @@ rollout_mlp2_tape_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
                         const uint32_t a_hi = tmem_base + RF_ACOL0 + (uint32_t)s * 64u;
 #pragma unroll
                         for (int k = 0; k < TBK / UMMA_K; ++k) {
-                            const uint64_t bo = (uint64_t)(k * (UMMA_K * 4 >> 4));
+                            const uint64_t bo = (uint64_t)(k * (UMMA_K * 4 >> 4));     // 32 B per k-step: 8 tf32 or 16 fp16
+                            if (F16) {
+                                umma_f16_ts(tmem_base, a_hi + k * 8, db + bo, idesc_wide, (kb | k) != 0);
+                                umma_f16_ts(tmem_base + 128, a_hi + 32 + k * 8, db + bo, idesc_cross, 1);
+                                continue;
+                            }
                             umma_tf32_ts(tmem_base, a_hi + k * UMMA_K, db + bo, idesc_wide, (kb | k) != 0);
                             umma_tf32_ts(tmem_base + 128, a_hi + 32 + k * UMMA_K, db + bo, idesc_cross, 1);
                         }
@@ -270,12 +287,28 @@ rollout_mlp2_tape_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
                     tc_fence_after();
                     const uint4* arow = reinterpret_cast<const uint4*>(smem + s * RF_STAGE_BYTES + 2 * RF_TILE_BYTES + row * 128);
                     uint32_t hi[32], lo[32];
+                    if constexpr (F16) {
+                        // 64 k of this thread's row (two 32-k boxes) -> scaled fp16 (hi, lo) pairs, two k per TMEM column
+                        const float a_scale = pow2f_int(layer == 0 ? shift_x : shift_h);
+#pragma unroll
+                        for (int bx = 0; bx < 2; ++bx) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const uint4 q = arow[bx * (RF_TILE_BYTES / 16) + (j ^ sw)];
+                                f16_split2(__uint_as_float(q.x) * a_scale, __uint_as_float(q.y) * a_scale, hi[bx * 16 + 2 * j],
+                                           lo[bx * 16 + 2 * j]);
+                                f16_split2(__uint_as_float(q.z) * a_scale, __uint_as_float(q.w) * a_scale, hi[bx * 16 + 2 * j + 1],
+                                           lo[bx * 16 + 2 * j + 1]);
+                            }
+                        }
+                    } else {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const uint4 q = arow[j ^ sw];
                         hi[4 * j] = q.x; hi[4 * j + 1] = q.y; hi[4 * j + 2] = q.z; hi[4 * j + 3] = q.w;   // raw word = hi operand
                         lo[4 * j] = tf32_lo_bits(q.x); lo[4 * j + 1] = tf32_lo_bits(q.y);
                         lo[4 * j + 2] = tf32_lo_bits(q.z); lo[4 * j + 3] = tf32_lo_bits(q.w);
+                    }
                     }
                     tmem_st_32x32b_x32(lane_addr + (uint32_t)s * 64u, hi);
                     tmem_st_32x32b_x32(lane_addr + (uint32_t)s * 64u + 32u, lo);
@@ -288,6 +321,7 @@ rollout_mlp2_tape_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
                 const int quad = warp & 3;
                 const int half = (warp - 6) >> 2;                  // columns [64*half, 64*half + 64) of the 128-column tile
                 const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * 64);
+                const float out_scale = F16 ? pow2f_int(-((layer == 0 ? shift_x : shift_h) + kF16WShift)) : 1.f;
                 rf_wait(acc_full, tile_iter & 1);
                 RF_TRACE(1 + 4 * layer);          // accumulator complete
                 tc_fence_after();
@@ -299,7 +333,10 @@ rollout_mlp2_tape_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
                     tmem_ld_32x32b_x16(taddr + 128u + (uint32_t)c0, r2);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) o[c0 + j] = __uint_as_float(r[j]) + __uint_as_float(r2[j]);
+                    for (int j = 0; j < 16; ++j) {
+                        if (F16) o[c0 + j] = fmaf(__uint_as_float(r2[j]), 1.f / 2048.f, __uint_as_float(r[j])) * out_scale;
+                        else o[c0 + j] = __uint_as_float(r[j]) + __uint_as_float(r2[j]);
+                    }
                 }
                 tc_fence_before();
                 mbar_arrive(acc_empty);
@@ -512,9 +549,9 @@ rollout_mlp2_tape_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
     }
 }
 
-template <int ACT>
+template <int ACT, bool F16>
 static int launch_rollout(const CUtensorMap* tm, const RolloutArgs& a, int CX, cudaStream_t st) {
-    auto kern = rollout_mlp2_tape_kernel<ACT>;
+    auto kern = rollout_mlp2_tape_kernel<ACT, F16>;
     static bool attr_set = false;
     if (!attr_set) {
         SFB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, RfSmem::TOTAL));
@@ -547,8 +584,44 @@ int tc_rollout_mlp2_supported(const float* W1, const float* W2, int K1, int H1, 
     return 2 * (H2 / 128);
 }
 
-int tc_rollout_mlp2_tape(const float* W1, const float* W2, int act, int engine, const RolloutArgs& a, cudaStream_t st) {
-    if (!tc_rollout_mlp2_supported(W1, W2, a.K1, a.H1, a.H2, a.A, engine)) return SFB_TC_UNSUPPORTED;
+// fp16-split form (common.cuh): taken when the weights have registered fp16 twins and both activation buffers (x_norm, the
+// h1 scratch) have registered bounds; SFB200_TC_F16=0 keeps the tf32 split
+static bool rollout_f16_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("SFB200_TC_F16");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
+}
+
+int tc_rollout_mlp2_tape(const float* W1, const float* W2, int act, int engine, const RolloutArgs& a_in, cudaStream_t st) {
+    if (!tc_rollout_mlp2_supported(W1, W2, a_in.K1, a_in.H1, a_in.H2, a_in.A, engine)) return SFB_TC_UNSUPPORTED;
+    RolloutArgs a = a_in;
+    if (rollout_f16_enabled() && a.K1 % 64 == 0 && a.H1 % 64 == 0) {
+        const F16Twin t1 = f16_twin_lookup(W1, (int64_t)a.H1 * a.K1), t2 = f16_twin_lookup(W2, (int64_t)a.H2 * a.H1);
+        const float* bx = operand_bound_lookup(a.x_norm, a.N * a.K1 * (int64_t)sizeof(float));
+        const float* bh = operand_bound_lookup(a.h1, a.N * a.H1 * (int64_t)sizeof(float));
+        if (t1.hi && t2.hi && bx && bh) {
+            a.bound_x = bx;
+            a.bound_h1 = bh;
+            CUtensorMap tm[6];
+            bool ok = make_tmap(&tm[0], a.x_norm, (uint64_t)a.K1, (uint64_t)a.N, (uint64_t)a.K1, 32, 128, false);
+            ok = ok && make_tmap_f16(&tm[1], t1.hi, (uint64_t)a.K1, (uint64_t)a.H1, (uint64_t)a.K1, 64, 128);
+            ok = ok && make_tmap_f16(&tm[2], t1.lo, (uint64_t)a.K1, (uint64_t)a.H1, (uint64_t)a.K1, 64, 128);
+            ok = ok && make_tmap(&tm[3], a.h1, (uint64_t)a.H1, (uint64_t)a.N, (uint64_t)a.H1, 32, 128, false);
+            ok = ok && make_tmap_f16(&tm[4], t2.hi, (uint64_t)a.H1, (uint64_t)a.H2, (uint64_t)a.H1, 64, 128);
+            ok = ok && make_tmap_f16(&tm[5], t2.lo, (uint64_t)a.H1, (uint64_t)a.H2, (uint64_t)a.H1, 64, 128);
+            if (!ok) return SFB_TC_UNSUPPORTED;
+            const int CX = a.H2 / 128;
+            switch (act) {
+                case SFB200_ACT_ELU: return launch_rollout<SFB200_ACT_ELU, true>(tm, a, CX, st);
+                case SFB200_ACT_RELU: return launch_rollout<SFB200_ACT_RELU, true>(tm, a, CX, st);
+                case SFB200_ACT_TANH: return launch_rollout<SFB200_ACT_TANH, true>(tm, a, CX, st);
+                default: return launch_rollout<SFB200_ACT_NONE, true>(tm, a, CX, st);
+            }
+        }
+    }
     const float* W1lo = tf32_lo_lookup(W1, (int64_t)a.H1 * a.K1);
     const float* W2lo = tf32_lo_lookup(W2, (int64_t)a.H2 * a.H1);
     if (tf32_lo_check_enabled()) {
@@ -566,10 +639,10 @@ int tc_rollout_mlp2_tape(const float* W1, const float* W2, int act, int engine, 
     if (!ok) return SFB_TC_UNSUPPORTED;
     const int CX = a.H2 / 128;
     switch (act) {
-        case SFB200_ACT_ELU: return launch_rollout<SFB200_ACT_ELU>(tm, a, CX, st);
-        case SFB200_ACT_RELU: return launch_rollout<SFB200_ACT_RELU>(tm, a, CX, st);
-        case SFB200_ACT_TANH: return launch_rollout<SFB200_ACT_TANH>(tm, a, CX, st);
-        default: return launch_rollout<SFB200_ACT_NONE>(tm, a, CX, st);
+        case SFB200_ACT_ELU: return launch_rollout<SFB200_ACT_ELU, false>(tm, a, CX, st);
+        case SFB200_ACT_RELU: return launch_rollout<SFB200_ACT_RELU, false>(tm, a, CX, st);
+        case SFB200_ACT_TANH: return launch_rollout<SFB200_ACT_TANH, false>(tm, a, CX, st);
+        default: return launch_rollout<SFB200_ACT_NONE, false>(tm, a, CX, st);
     }
 }
 
@@ -629,7 +702,7 @@ int sfb200_rollout_mlp2_tape(int64_t n_envs, int T, int K1, const float* W1, con
                         traj_time_outs_0, traj_policy_id_0, traj_stride, ep_return, ep_len, ep_min_raw, ep_max_raw, len_increment,
                         stats, fin_return_0, fin_len_0, traj_obs_0, traj_obs_stride, with_rnn ? rnn : nullptr, rnn_dim, traj_rnn_0,
                         traj_rnn_stride, mean, var, sub_mean, inv_scale, fabsf(sub_mean) > 1e-8f ? 1 : 0,
-                        fabsf(inv_scale - 1.0f) > 1e-8f ? 1 : 0, eps, clip, ticket, g_rollout_trace};
+                        fabsf(inv_scale - 1.0f) > 1e-8f ? 1 : 0, eps, clip, ticket, g_rollout_trace, nullptr, nullptr};
     const int rc = tc_rollout_mlp2_tape(W1, W2, act, engine, a, (cudaStream_t)stream);
     SFB_CHECK_ARG(rc != SFB_TC_UNSUPPORTED, "rollout_mlp2_tape: model not covered (K1=%d H1=%d H2=%d A=%d engine=%d); "
                   "sfb200_rollout_mlp2_partials() tells when to use the per-step calls", K1, H1, H2, A, engine);

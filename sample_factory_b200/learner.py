@@ -170,6 +170,15 @@ class Learner:
         # minibatch activations
         self.h = [torch.empty((B, h), **f32) for h in spec.hidden]
         self.dz = [torch.empty((B, h), **f32) for h in spec.hidden]
+        # fp16-split form of the GEMM engine (model._register_f16): tell the library the bounds of the activation buffers the
+        # forward GEMMs (normalised observations, hidden activations) and dX (gradient of the last hidden layer) read
+        self.dz_bound = None
+        if getattr(self.model, "f16_twins", None) is not None and self.engine == ops.GEMM_TC_3XTF32:
+            self.dz_bound = torch.zeros(4, **f32)        # [bound, scratch, counter, -] (sfb200_heads_dz_bound)
+            ops.register_operand_bounds(self, [(self.obs_flat_compact, self.model.bound_x), (self.dz[-1], self.dz_bound[0:1])] +
+                                        [(self.h[i], self.model.bound_h[i: i + 1]) for i in range(len(spec.hidden) - 1)])
+            for i in range(1, len(spec.hidden)):            # layers whose input gradient is needed: dX reads W transposed
+                self.model.enable_f16_transposed(spec.fc_encoder_name(i, "weight"))
         self.mb_values = torch.empty(B, **f32)
         self.mb_logits = torch.empty((B, A), **f32)
         self.dlogits = torch.empty((B, A_lin), **f32)
@@ -502,6 +511,7 @@ class Learner:
                 if dev_ctr:
                     ops.advance_counters(self.counters_dev[0:1], self.counters_dev[1:2])
                 m.refresh_cat_heads()
+                m.refresh_bounds()
                 self.train_step += 1
                 return
             ops.dp_grad_allreduce(self.comm.comm, grad, self.comm.workspace)
@@ -522,6 +532,10 @@ class Learner:
                                cfg.adam_beta2, cfg.adam_eps, cfg.max_grad_norm, self.num_valid_dev,
                                self.exp_size_total_dev(), self.grad_norm_log[log_idx : log_idx + 1], self.adam_ws)
         m.refresh_cat_heads()        # separate actor / critic weights: re-embed the updated head weights (no-op otherwise)
+        if m.f16_twins is not None:
+            if cfg.optimizer == "lamb":
+                ops.refresh_f16_twins(m.flat)      # (the Adam kernels keep the fp16 twins current themselves)
+            m.refresh_bounds()         # activation bounds + transposed twins follow the new weights (fp16-split GEMM engine)
         self.train_step += 1                                                                         # :388-392
 
     def _backward_shared(self, batch: Dict[str, Tensor], x: Tensor, x0: Tensor, sl: slice, valids: Tensor) -> None:
@@ -539,6 +553,8 @@ class Learner:
         tail_is_mlp = Ld > 0 or not rnn            # is the tensor feeding the heads an activated MLP output?
         tail_dz = self.dz[Le + Ld - 1] if tail_is_mlp else self.d_core
         tail_db = gdec[-1][1] if Ld > 0 else (None if rnn else genc[-1][1])
+        if self.dz_bound is not None and tail_is_mlp:
+            ops.heads_dz_bound(self.dlogits, self.dvalues, Wv, Wa, self.dz_bound)
         ops.heads_backward(x, Wv, Wa, self.dlogits, self.dvalues, self.act if tail_is_mlp else none, tail_dz,
                            g["critic_linear.weight"].view(-1), g["critic_linear.bias"],
                            g["action_parameterization.distribution_linear.weight"],

@@ -260,6 +260,52 @@ class PolicyModel:
 
             self.flat_lo = torch.empty_like(self.flat)
             ops.register_tf32_lo(self.flat, self.flat_lo)
+        self._register_f16()
+
+    # ---- fp16-split form of the 3-pass GEMM engine (include/sfb200.h): fp16 twins of the weights + activation bounds ----
+    def _register_f16(self) -> None:
+        """Plain MLP policies with normalised inputs: every hidden activation has a bound that follows from the weights
+        (normalised observations are clipped to +-5, running_mean_std.py:96-110; |act(x W^T + b)| <= |x|_inf * max_n
+        |W[n,:]|_1 + |b|_inf), so the forward GEMMs -- and dX, through transposed twins -- can take the fp16 operand path."""
+        sp = self.spec
+        self.f16_twins = None
+        self.f16_T: Dict[str, Tensor] = {}
+        self.bound_x = self.bound_h = None
+        ok = (self.flat.is_cuda and sp.normalize_input and sp.obs_shape is None and not sp.use_rnn and sp.share_weights
+              and not sp.decoder_mlp_layers and len(sp.hidden) >= 1)
+        if not ok:
+            return
+        from . import ops
+
+        self.f16_twins = torch.empty(2 * self.flat.numel(), dtype=torch.float16, device=self.device)
+        ops.register_f16_twins(self.flat, self.f16_twins)
+        self.bound_x = torch.full((1,), 5.0, dtype=torch.float32, device=self.device)
+        self.bound_h = torch.zeros(len(sp.hidden), dtype=torch.float32, device=self.device)
+        self.refresh_bounds()
+
+    def refresh_bounds(self) -> None:
+        """bounds of the hidden activations from the current weights (one tiny kernel per layer) + the transposed twins"""
+        if self.f16_twins is None:
+            return
+        from . import ops
+
+        act = ops.ACT[self.spec.nonlinearity]
+        inb = self.bound_x
+        for i, (W, b) in enumerate(self.hidden_layers()[:-1]):       # (the last hidden layer feeds the heads, not a GEMM)
+            ops.linear_out_bound(W, b, inb, self.bound_h[i: i + 1], act)
+            inb = self.bound_h[i: i + 1]
+        for name in self.f16_T:
+            ops.refresh_f16_transposed(self.params[name])
+
+    def enable_f16_transposed(self, name: str) -> None:
+        """transposed fp16 twins of one weight matrix (the learner's dX = dz . W reads W along its other axis)"""
+        if self.f16_twins is None or name in self.f16_T:
+            return
+        from . import ops
+
+        W = self.params[name]
+        self.f16_T[name] = torch.empty(2 * W.numel(), dtype=torch.float16, device=self.device)
+        ops.register_f16_transposed(W, self.f16_T[name])
 
     def weights_changed(self) -> None:
         """Call after writing `flat` / `params[...]` by anything other than the Adam kernel (which keeps lo current)."""
@@ -267,6 +313,9 @@ class PolicyModel:
             from . import ops
 
             ops.refresh_tf32_lo(self.flat)
+            if self.f16_twins is not None:
+                ops.refresh_f16_twins(self.flat)
+                self.refresh_bounds()
         self.refresh_cat_heads()
 
     def rebind_grad(self, grad: Tensor) -> None:
@@ -282,6 +331,10 @@ class PolicyModel:
                 from . import ops
 
                 ops.unregister_tf32_lo(self.flat)
+                if getattr(self, "f16_twins", None) is not None:
+                    for name in self.f16_T:
+                        ops.unregister_f16_transposed(self.params[name])
+                    ops.unregister_f16_twins(self.flat)
         except Exception:
             pass
 
@@ -332,6 +385,9 @@ class PolicyModel:
         self.flat.copy_(other.flat)
         if self.flat_lo is not None and other.flat_lo is not None:
             self.flat_lo.copy_(other.flat_lo)
+            if self.f16_twins is not None and other.f16_twins is not None:
+                self.f16_twins.copy_(other.f16_twins)
+                self.bound_h.copy_(other.bound_h)
             self.refresh_cat_heads()
         else:
             self.weights_changed()

@@ -323,10 +323,37 @@ def unregister_operand_bound(buf: Tensor) -> None:
     lib().call("sfb200_unregister_operand_bound", buf.data_ptr())
 
 
+def _drop_bounds(ptrs) -> None:
+    try:
+        for p in ptrs:
+            lib().call("sfb200_unregister_operand_bound", p)
+    except Exception:
+        pass
+
+
+def register_operand_bounds(owner, pairs) -> None:
+    """register (buffer, bound) pairs for as long as `owner` lives: the registry is keyed by device address, so entries must
+    not outlive the buffers (the allocator hands the address to somebody else)"""
+    import weakref
+
+    for buf, bound in pairs:
+        register_operand_bound(buf, bound)
+    weakref.finalize(owner, _drop_bounds, [buf.data_ptr() for buf, _ in pairs])
+
+
 def linear_out_bound(W: Tensor, b: Optional[Tensor], in_bound: Tensor, out_bound: Tensor, act: int) -> None:
     """out_bound = in_bound * max_n sum_k |W[n][k]| + max_n |b[n]| (an upper bound of |act(x W^T + b)| for |x| <= in_bound)"""
     N, K = W.shape
     lib().call("sfb200_linear_out_bound", _p(W, F32), _p(b, F32), N, K, _p(in_bound, F32), _p(out_bound, F32), act, _stream())
+
+
+def heads_dz_bound(dlogits: Tensor, dvalues: Tensor, Wv: Tensor, Wa: Tensor, out_bound: Tensor) -> None:
+    """out_bound = max_m (|dvalues[m]| + sum_a |dlogits[m][a]|) * max(|Wv|, |Wa|): bound of heads_backward's dz output"""
+    rows, A = dlogits.shape
+    H = Wv.numel()
+    assert Wa.numel() == A * H and dlogits.is_contiguous() and Wa.is_contiguous() and out_bound.numel() >= 3
+    lib().call("sfb200_heads_dz_bound", _p(dlogits, F32), _p(dvalues, F32), rows, A, _p(Wv, F32), _p(Wa, F32), H,
+               _p(out_bound, F32), _stream())
 
 
 def linear_heads_partials(N: int, A: int, engine: int) -> int:

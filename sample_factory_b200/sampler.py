@@ -53,6 +53,10 @@ class DeviceSampler:
         # per-step scratch (never reallocated)
         self.x_norm = torch.empty((self.N, spec.obs_dim), **f32)
         self.h = [torch.empty((self.N, h), **f32) for h in spec.hidden]
+        if getattr(model, "f16_twins", None) is not None and engine == ops.GEMM_TC_3XTF32:
+            # fp16-split form of the GEMM engine: bounds of the activation buffers the per-step GEMMs read (model._register_f16)
+            ops.register_operand_bounds(self, [(self.x_norm, model.bound_x)] +
+                                        [(self.h[i], model.bound_h[i: i + 1]) for i in range(len(spec.hidden) - 1)])
         # what env.step() receives (preprocess_actions, batched_sampling.py:30-82): int32 [N] for Discrete, float32 [N, A]
         # for a Box action space
         if spec.continuous:

@@ -515,10 +515,13 @@ def test_fused_policy_step_matches_separate_launches(explicit_noise, monkeypatch
 
 
 def _compare_rollout_runs(a, b, what):
+    # the two-layer kernel of policy_step.cu ("fused") splits its operands into tf32 pairs, the per-layer and the persistent
+    # kernels into scaled fp16 pairs (same 22 significand bits, different roundings): logits agree to ~2 ulp of their size
+    atol = 5e-6 if what == "fused" else 2e-6
     for ta, tb in zip(a["traj"], b["traj"]):
         for k in ta:
             if k in ("action_logits", "values", "log_prob_actions"):
-                np.testing.assert_allclose(ta[k].cpu().numpy(), tb[k].cpu().numpy(), rtol=0, atol=2e-6, err_msg=f"{what} {k}")
+                np.testing.assert_allclose(ta[k].cpu().numpy(), tb[k].cpu().numpy(), rtol=0, atol=atol, err_msg=f"{what} {k}")
             elif k != "valids":
                 assert torch.equal(ta[k], tb[k]), (what, k)
     for k in ("obs", "rew", "term", "step", "pstep"):
