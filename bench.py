@@ -473,8 +473,9 @@ def run_ours(args):
                         achieved=ach, peak=peaks["tflops_sustained"], unit="TFLOP/s", frac=ach / peaks["tflops_sustained"],
                         traffic=_ncu_traffic("gemm_fwd_l2"), avg_kernel_ms=k["avg_ms"], launches_timed=k["launches"],
                         peak_source=peaks["source"] + ", bf16 sustained (kernel timed inside a long step)",
-                        note="fp32-parity GEMM: 3xTF32 costs 3 tf32 MMAs per product and tf32 peak is half of bf16, so "
-                             "the ceiling of this engine is peak/6; the simt engine runs on CUDA cores (no tensor pipe)")
+                        note="fp32-parity GEMM = 3 tensor-core passes per product (hi*hi, hi*lo, lo*hi): the forward layers and dX run "
+                             "them as kind::f16 MMAs on scaled fp16 operand pairs (ceiling = peak/3), dW as kind::tf32 MMAs "
+                             "(ceiling = peak/6); the simt engine runs on CUDA cores (no tensor pipe)")
     roof2 = []
     for name in ("heads_backward", "normalize_obs", "gae_returns"):
         if name in kern:
@@ -511,9 +512,9 @@ def run_ours(args):
                         tensor=dict(achieved=samp_tf, unit="TFLOP/s", peak=peaks["tflops_burst"], frac=samp_tf / peaks["tflops_burst"],
                                     algorithmic_flops=samp_flops,
                                     note="policy forward only (0.599 MFLOP per env step, SURVEY 8d) over the whole rollout time; "
-                                         "3xTF32 ceiling = peak / 6; 128 of 148 SMs hold a CTA"),
+                                         "3-pass fp16-split ceiling = peak / 3; 128 of 148 SMs hold a CTA"),
                         note="a 4096-env policy step moves 2.35 MB and 2.45 GFLOP: the rollout is bound by the per-step dependency "
-                             "chain (tensor-pipe time of the two layers + epilogues + cluster barriers, profiles/r02_k_rollout_trace.md), "
+                             "chain (tensor-pipe time of the two layers + epilogues + cluster barriers, profiles/r02_r_rollout_trace.md), "
                              "not by HBM bandwidth")
     dp_info = None
     if world > 1 and not args.no_dp_check:
