@@ -206,8 +206,8 @@ def verify_cfg(cfg, num_agents_total: Optional[int] = None) -> bool:
                   "convnet_atari, model/encoder.py:127-134) run on the device path; resnet_impala (encoder.py:153-221) does not")
     if getattr(cfg, "rnn_num_layers", 1) != 1:
         cfg_error(f"{cfg.rnn_num_layers=}: the device path implements the one-layer recurrent core (model/core.py:27-64)")
-    if getattr(cfg, "num_policies", 1) != 1:
-        cfg_error(f"{cfg.num_policies=}: single-policy path (multi-policy / PBT is out of scope, SURVEY section 8f row 4)")
+    if getattr(cfg, "num_policies", 1) < 1:
+        cfg_error(f"{cfg.num_policies=} must be >= 1")
     if cfg.use_rnn:                                                                                         # :187-194
         if cfg.recurrence <= 1:
             cfg_error(f"{cfg.recurrence=} must be > 1 to train an RNN. Recommeded value is recurrence == {cfg.rollout=}.")

@@ -55,9 +55,15 @@ class BatchedHostEnv:
 
     def __init__(self, make_env: Callable[[int], object], num_envs: int, device: torch.device, seed: Optional[int] = None):
         self.envs: List = [make_env(i) for i in range(num_envs)]
-        self.num_agents = num_envs
-        self.device = device
         e0 = self.envs[0]
+        # Multi-agent envs (envs/env_utils.py "is_multiagent": lists of per-agent observations / rewards / dones in and out,
+        # the env resets itself -- sf_examples/train_custom_multi_env.py): agent j of env i is row i * A + j.  An agent can
+        # report info["is_active"] = False: its next step is recorded with policy id -1 and masked by the learner
+        # (non_batched_sampling.py:82-84,197-203).
+        self.agents_per_env = int(getattr(e0, "num_agents", 1))
+        self.multi_agent = bool(getattr(e0, "is_multiagent", False)) or self.agents_per_env > 1
+        self.num_agents = num_envs * self.agents_per_env
+        self.device = device
         obs_space, self._obs_key = _main_obs_space(e0.observation_space)
         self._mask_key = "action_mask" if (self._obs_key and "action_mask" in e0.observation_space.spaces) else None
         shape = tuple(obs_space.shape)
@@ -67,7 +73,12 @@ class BatchedHostEnv:
         self.continuous, self.num_actions = _space_info(e0.action_space)
         self._seed = seed
         self._seeded = False
-        n = num_envs
+        n = self.num_agents
+        self.inactive = None        # device bool [num_agents]: rows whose agent was inactive when the last step was taken
+        if self.multi_agent:
+            self.inactive_next = torch.zeros(n, dtype=torch.bool).pin_memory()
+            self.inactive_host = torch.zeros(n, dtype=torch.bool).pin_memory()
+            self.inactive = torch.zeros(n, dtype=torch.bool, device=device)
         odt = torch.uint8 if self.obs_uint8 else torch.float32
         self.obs_host = torch.empty((n, self.obs_dim), dtype=odt).pin_memory()
         self.obs = torch.empty((n, self.obs_dim), dtype=odt, device=device)
@@ -108,7 +119,11 @@ class BatchedHostEnv:
             if self._seed is not None and not self._seeded:
                 kw["seed"] = self._seed + i        # per-env seed = global env id (batched_sampling.py:177)
             obs, _info = e.reset(**kw)
-            self._put_obs(i, obs)
+            if self.multi_agent:
+                for j in range(self.agents_per_env):
+                    self._put_obs(i * self.agents_per_env + j, obs[j])
+            else:
+                self._put_obs(i, obs)
         self._seeded = True
         self.obs.copy_(self.obs_host, non_blocking=True)
         self.h2d_bytes += self.obs_host.numel() * self.obs_host.element_size()
@@ -120,6 +135,8 @@ class BatchedHostEnv:
         self.d2h_bytes += self.actions_host.numel() * self.actions_host.element_size()
         a = self.actions_host.numpy()
         rew, term, trunc = self.rew_host.numpy(), self.term_host.numpy(), self.trunc_host.numpy()
+        if self.multi_agent:
+            return self._step_multi_agent(a, rew, term, trunc)
         for i, e in enumerate(self.envs):
             obs, r, tm, tr, info = e.step(a[i] if self.continuous else int(a[i]))
             rew[i], term[i], trunc[i] = r, bool(tm), bool(tr)
@@ -132,6 +149,42 @@ class BatchedHostEnv:
         self.pack.copy_(self.pack_host, non_blocking=True)
         self.h2d_bytes += self.obs_host.numel() * self.obs_host.element_size() + self.pack_host.numel()
         return self._obs_out(), self.rew, self.terminated, self.truncated
+
+    def _step_multi_agent(self, a, rew, term, trunc):
+        A = self.agents_per_env
+        self.inactive_host.copy_(self.inactive_next)          # the status the agents had when these actions were computed
+        nxt = self.inactive_next.numpy()
+        for i, e in enumerate(self.envs):
+            acts = [a[i * A + j] if self.continuous else int(a[i * A + j]) for j in range(A)]
+            obs, r, tm, tr, infos = e.step(acts)               # (multi-agent envs auto-reset themselves)
+            for j in range(A):
+                row = i * A + j
+                rew[row], term[row], trunc[row] = r[j], bool(tm[j]), bool(tr[j])
+                info = infos[j] if infos else {}
+                nxt[row] = not info.get("is_active", True)
+                if (tm[j] or tr[j]) and info:
+                    self.episode_infos.append(info)
+                self._put_obs(row, obs[j])
+        self.obs.copy_(self.obs_host, non_blocking=True)
+        self.pack.copy_(self.pack_host, non_blocking=True)
+        self.inactive.copy_(self.inactive_host, non_blocking=True)
+        self.h2d_bytes += self.obs_host.numel() * self.obs_host.element_size() + self.pack_host.numel() + self.num_agents
+        return self._obs_out(), self.rew, self.terminated, self.truncated
+
+    def set_reward_shaping(self, reward_shaping, agent_idx=None) -> None:
+        """RewardShapingInterface pass-through (PBT mutates the scheme, envs/env_utils.py:74-90)"""
+        for e in self.envs:
+            if hasattr(e, "set_reward_shaping"):
+                e.set_reward_shaping(reward_shaping, slice(0, self.agents_per_env))
+
+    def get_default_reward_shaping(self):
+        e0 = self.envs[0]
+        return e0.get_default_reward_shaping() if hasattr(e0, "get_default_reward_shaping") else None
+
+    def set_training_info(self, training_info) -> None:
+        for e in self.envs:
+            if hasattr(e, "set_training_info"):
+                e.set_training_info(training_info)
 
     def close(self) -> None:
         for e in self.envs:
@@ -156,9 +209,6 @@ def create_batched_env(cfg, env_config: dict, device: torch.device, num_envs: Op
     first = create_env(cfg.env, cfg, env_config)
     if is_batched_env(first):
         return first
-    if getattr(first, "num_agents", 1) > 1 or getattr(first, "is_multiagent", False):
-        raise NotImplementedError("multi-agent CPU envs are not adapted automatically: expose the batched contract of "
-                                  "sample_factory_b200.envs (num_agents, obs_dim, num_actions, reset, step)")
     if not (hasattr(first, "observation_space") and hasattr(first, "action_space")):
         raise TypeError(f"{type(first).__name__} is neither a batched device env nor a gymnasium-API env")
     epw = int(cfg.num_envs_per_worker)

@@ -672,6 +672,37 @@ class Learner:
         self.env_steps += self.E * self.world_size * (cfg.env_frameskip if cfg.summaries_use_frameskip else 1)
         return dict(env_steps=self.env_steps, train_step=self.train_step)
 
+    # ---- population-based training hooks (learner.py:388-428) ---------------------------------------------------
+    def set_new_cfg(self, new_cfg: Dict) -> None:
+        """Replace hyper-parameters (PBT, learner.py:394-408).  The kernels take them as launch arguments, so captured graphs
+        are dropped and re-captured on the next train(); a changed learning rate applies only with lr_schedule=constant."""
+        changed = False
+        for key, value in new_cfg.items():
+            if getattr(self.cfg, key) != value:
+                setattr(self.cfg, key, value)
+                changed = True
+        if self.cfg.lr_schedule == "constant" and self.curr_lr != self.cfg.learning_rate:
+            self.curr_lr = self.cfg.learning_rate
+            changed = True
+        if changed:
+            self._graphs.clear()
+            self._graph = None
+
+    def load_policy_from(self, other: "Learner") -> None:
+        """Take weights, normaliser and optimiser state of another policy's learner (PBT replacement: the reference loads the
+        donor's checkpoint with load_progress=False, learner.py:300-310, then advances the policy version by max_policy_lag + 1
+        so that experience collected with the old weights is dropped, :415-428).  Same device: device-to-device copies."""
+        m, o = self.model, other.model
+        m.flat.copy_(o.flat)
+        m.exp_avg.copy_(o.exp_avg)
+        m.exp_avg_sq.copy_(o.exp_avg_sq)
+        for k in ("obs_mean", "obs_var", "obs_count", "ret_mean", "ret_var", "ret_count"):
+            getattr(m, k).copy_(getattr(o, k))
+        m.weights_changed()
+        self.opt_step = other.opt_step
+        self.curr_lr = other.curr_lr
+        self.train_step += self.cfg.max_policy_lag + 1
+
     def _train_body(self, batch: Dict[str, Tensor]) -> None:
         """one epoch of minibatch steps with no host dependence (the graph-capturable form of train())"""
         self._prepare_batch(batch)

@@ -207,6 +207,9 @@ class DeviceSampler:
         obs, rew, terminated, truncated = self.env.step(self.env_actions)   # batched_sampling.py:316
         self.last_obs = self._take_obs(obs)
         self._post_step(t, rew, terminated, truncated)
+        inactive = getattr(self.env, "inactive", None)
+        if inactive is not None:      # multi-agent host envs: steps of inactive agents carry policy id -1 (masked by the learner)
+            self.traj["policy_id"][:, t].masked_fill_(inactive, -1)
 
     def _post_step(self, t: int, rew: Tensor, terminated: Tensor, truncated: Tensor) -> None:
         """advance_rollouts part 2 for step t, then the pre-step of t+1 (or, at t = T-1, _finalize_trajectories

@@ -373,7 +373,11 @@ def _jsonable(v) -> bool:
 
 
 def make_runner(cfg):
-    """train.py:12-28"""
+    """train.py:12-28 (+ the population runner for num_policies > 1, multi_policy.py)"""
+    if getattr(cfg, "num_policies", 1) > 1:
+        from .multi_policy import MultiPolicyRunner
+
+        return cfg, MultiPolicyRunner(cfg)
     return cfg, Runner(cfg)
 
 

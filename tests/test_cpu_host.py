@@ -350,3 +350,68 @@ def test_tensorboard_event_writer_roundtrip(tmp_path):
     assert got[0] == (131072, "perf/_fps", np.float32(40.4e6)) and got[1] == (2 ** 40, "reward/reward", -1.5)
     assert got[2][0] == 7 and got[2][2] == 3.0 and len(got[2][1]) > 127
     assert os.path.basename(w.path).startswith("events.out.tfevents.")
+
+
+def test_pbt_rules_match_the_reference_selection_and_mutation():
+    """pbt.py on a fake runner: mutation range, the untouched best, policy 0 never mutated, replacement only across the reward
+    gap, the reference's json files"""
+    import json
+    import random
+    import tempfile
+    from types import SimpleNamespace
+
+    from sample_factory_b200.pbt import PopulationBasedTraining, perturb_exponential_decay, policy_cfg_file
+
+    random.seed(11)
+    cfg = SimpleNamespace(num_policies=4, with_pbt=True, pbt_optimize_gamma=True, pbt_mutation_rate=1.0, pbt_perturb_min=1.1,
+                          pbt_perturb_max=1.5, pbt_replace_fraction=0.3, pbt_replace_reward_gap=0.1,
+                          pbt_replace_reward_gap_absolute=1e-6, pbt_target_objective="true_objective", pbt_period_env_steps=10,
+                          pbt_start_mutation=10, env="my_env", learning_rate=1e-4, exploration_loss_coeff=0.003,
+                          value_loss_coeff=0.5, max_grad_norm=4.0, ppo_clip_ratio=0.1, ppo_clip_value=1.0, gamma=0.99,
+                          batch_size=1024, rollout=32)
+    calls = []
+    runner = SimpleNamespace(update_policy_cfg=lambda p, c: calls.append(("cfg", p, dict(c))),
+                             update_reward_shaping=lambda p, s: calls.append(("rew", p, s)),
+                             replace_policy=lambda p, donor: calls.append(("replace", p, donor)),
+                             policy_avg_stats={}, writers={}, env_steps_per_policy=[100] * 4)
+    runner.pbt_decide = lambda pbt, p: (pbt.decide(p, pbt.objectives()) if pbt.objectives() is not None else None)
+    pbt = PopulationBasedTraining(cfg, runner, log=lambda *a: None)
+    with tempfile.TemporaryDirectory() as d:
+        pbt.on_init(d, dict(delta=dict(health=(-1.0, 2.0)), kill=5.0))
+        assert pbt.policy_cfg[0]["learning_rate"] == 1e-4 and set(pbt.policy_cfg[0]) == {
+            "learning_rate", "exploration_loss_coeff", "value_loss_coeff", "max_grad_norm", "ppo_clip_ratio", "ppo_clip_value", "gamma"}
+        for p in range(1, 4):       # mutation rate 1: every parameter moved by a factor in [1/1.5, 1/1.1] or [1.1, 1.5]
+            ratio = pbt.policy_cfg[p]["learning_rate"] / 1e-4
+            assert 1.1 - 1e-9 <= max(ratio, 1 / ratio) <= 1.5 + 1e-9
+            assert 0.0 < pbt.policy_cfg[p]["gamma"] < 1.0 and pbt.policy_cfg[p]["gamma"] != 0.99
+            assert pbt.policy_reward_shaping[p]["delta"]["health"] != (-1.0, 2.0)
+        assert json.load(open(policy_cfg_file(d, 2))) == pbt.policy_cfg[2]
+        pbt.on_start()
+        assert [c[0] for c in calls].count("cfg") == 4
+        # not enough data -> nothing happens
+        calls.clear()
+        pbt.on_training_step()
+        assert not [c for c in calls if c[0] == "replace"] and pbt.last_update == [100] * 4
+        # objectives: 3 best, 1 worst (big gap), 2 close to the best, 0 in between
+        from collections import deque
+        runner.policy_avg_stats["true_objective"] = [deque([2.0]), deque([-3.0]), deque([9.9]), deque([10.0])]
+        runner.env_steps_per_policy = [200] * 4
+        cfg2, cfg3 = dict(pbt.policy_cfg[2]), dict(pbt.policy_cfg[3])
+        calls.clear()
+        pbt.on_training_step()
+        # ceil(0.3 * 4) = 2: best = {3, 2} (left alone), worst = {0, 1}: both clear the reward gap and take a best member's weights
+        repl = {c[1]: c[2] for c in calls if c[0] == "replace"}
+        assert set(repl) == {0, 1} and set(repl.values()) <= {2, 3}
+        assert pbt.policy_cfg[3] == cfg3 and pbt.policy_cfg[2] == cfg2
+        donors = {2: cfg2, 3: cfg3}
+        assert pbt.policy_cfg[0] == donors[repl[0]]            # policy 0 is never MUTATED: it takes the donor's parameters as they are
+        assert pbt.policy_cfg[1] != donors[repl[1]]            # everybody else gets a mutated copy
+        assert json.load(open(policy_cfg_file(d, 1))) == pbt.policy_cfg[1]
+        # a small gap: the worst keeps its weights (but still mutates its own parameters)
+        runner.policy_avg_stats["true_objective"] = [deque([9.95]), deque([9.9]), deque([9.99]), deque([10.0])]
+        runner.env_steps_per_policy = [300] * 4
+        calls.clear()
+        pbt.on_training_step()
+        assert not [c for c in calls if c[0] == "replace"]
+    g = [perturb_exponential_decay(0.99, None) for _ in range(200)]
+    assert all(0.97 < x < 0.9992 for x in g) and min(g) < 0.99 < max(g)
