@@ -212,6 +212,8 @@ def create_batched_env(cfg, env_config: dict, device: torch.device, num_envs: Op
     if not (hasattr(first, "observation_space") and hasattr(first, "action_space")):
         raise TypeError(f"{type(first).__name__} is neither a batched device env nor a gymnasium-API env")
     epw = int(cfg.num_envs_per_worker)
+    if num_envs is not None and num_envs < 1:
+        raise ValueError(f"total_envs={int(cfg.num_workers) * epw} must be divisible by the number of policies")
     n = int(num_envs) if num_envs is not None else int(cfg.num_workers) * epw
     w0 = int(env_config.get("worker_index", 0)) if env_config else 0
     made = {0: first}

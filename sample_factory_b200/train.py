@@ -111,10 +111,10 @@ class Runner:
         p_idx, p_cnt = self.population
         n_host = None
         if p_cnt > 1:
+            # plain CPU envs: this member wraps 1/P of the env instances (agent_policy_mapping.py:35-37 demands divisibility; a
+            # factory that returns a batched device env sizes the member's share itself and ignores this)
             total = int(cfg.num_workers) * int(cfg.num_envs_per_worker)
-            if total % p_cnt != 0:          # agent_policy_mapping.py:35-37
-                raise ValueError(f"total_envs={total} must be divisible by num_policies={p_cnt}")
-            n_host = total // p_cnt
+            n_host = total // p_cnt if total % p_cnt == 0 else -1
         for s_ in range(n_splits):
             slot = (self.rank * p_cnt + p_idx) * n_splits + s_
             env_config = dict(worker_index=self.rank * p_cnt + p_idx, vector_index=s_, env_id=slot)

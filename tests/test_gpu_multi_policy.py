@@ -143,6 +143,7 @@ class _TwoAgentEnv:
         self.rng = np.random.RandomState(seed)
         self.episode_len, self.t = episode_len, 0
         self.inactive_steps = [3, 0]
+        self.total_steps = 0
         self.shaping = dict(rew=-1.0)
 
     def _obs(self):
@@ -157,9 +158,10 @@ class _TwoAgentEnv:
         for j in range(2):
             if self.inactive_steps[j] > 0:
                 self.inactive_steps[j] -= 1
-            elif self.rng.rand() < 0.05:
-                self.inactive_steps[j] = int(self.rng.randint(1, 6))
+            elif j == 1 and self.total_steps == 5:
+                self.inactive_steps[j] = 2          # agent 1 reports "inactive" at its steps 5 and 6
             infos.append(dict(is_active=self.inactive_steps[j] <= 0))
+        self.total_steps += 1
         self.t += 1
         r = 0.0 if actions[0] == actions[1] else self.shaping["rew"]
         rewards = [r if infos[j]["is_active"] else 0.0 for j in range(2)]
@@ -201,12 +203,15 @@ def test_multi_agent_host_env_rows_inactive_agents_and_reward_shaping():
     rew = r.traj["rewards"].cpu()
     dones = r.traj["dones"].cpu()
     assert set(pid.unique().tolist()) == {-1, 0}
-    assert (pid[0, :3] == -1).all() and (pid[0, 3] == 0)          # agent 0 of env 0 starts with three inactive steps
-    assert (pid[1, :3] == 0).all()
+    # agent 0 of env 0 reports is_active=False after its first two steps: the status an agent reported at step t - 1 marks
+    # step t (non_batched_sampling.py:197-203)
+    assert pid[0, 0] == 0 and (pid[0, 1:3] == -1).all() and pid[0, 3] == 0
+    assert (pid[1, :6] == 0).all() and (pid[1, 6:8] == -1).all() and (pid[1, 8:] == 0).all()
     assert set(rew.unique().tolist()) <= {0.0, -2.0 * cfg.reward_scale}
     assert dones[:, 9].all() and not dones[:, :9].any()           # episode_len 10, the env resets itself
-    assert (rew[0::2] == rew[1::2])[(pid[0::2] == 0) & (pid[1::2] == 0)].all()      # both agents of an env share the payout
+    # both agents of an env share the payout on steps where both REPORT active (steps 2-4 and 7-9 of the first episode)
+    assert (rew[0::2, 2:5] == rew[1::2, 2:5]).all() and (rew[0::2, 7:10] == rew[1::2, 7:10]).all()
+    assert (rew[0::2, :2] == 0).all() and (rew[1::2, 5:7] == 0).all()             # the env pays nothing to an inactive agent
     st = r.learner.fetch_stats()
     assert np.isfinite(st["loss"])
-    frac_invalid = float((pid == -1).float().mean())
-    assert 0.0 < frac_invalid < 0.5
+    assert int((pid == -1).sum()) == n_envs * 4
