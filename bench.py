@@ -358,8 +358,15 @@ def run_ours(args):
         return TapeVecEnv(tape_g, N_ACTIONS, env_index_offset=rank * N_ENVS + g * n)
 
     register_env("synthetic_tape", make_tape_env)
-    register_env("synthetic_tape_host", lambda name, cfg, env_config, render_mode=None: HostTapeVecEnv(
-        tape_cpu.numpy(), N_ACTIONS, dev, env_index_offset=rank * N_ENVS))
+    def make_host_env(name, cfg, env_config, render_mode=None):
+        # the same env simulated on the host; worker_num_splits groups -> double-buffered sampling (the reference's default 2)
+        splits = int(cfg.worker_num_splits) if cfg.num_envs_per_worker == cfg.worker_num_splits else 1
+        n = N_ENVS // splits
+        g = int(env_config["vector_index"]) if splits > 1 else 0
+        tape_g = tape_cpu.numpy() if splits == 1 else tape_cpu[:, g * n: (g + 1) * n].contiguous().numpy()
+        return HostTapeVecEnv(tape_g, N_ACTIONS, dev, env_index_offset=rank * N_ENVS + g * n)
+
+    register_env("synthetic_tape_host", make_host_env)
 
     def barrier():
         if world > 1:
@@ -578,14 +585,14 @@ def run_ours(args):
         def run_e2e(async_rl: bool):
             # the host is the bottleneck of this arm (it steps the envs): the learner's ~90 launches are replayed as one graph
             r2 = Runner(make_cfg("synthetic_tape_host", args.engine, not args.no_graph, async_rl=async_rl,
-                                 learner_graph=not args.no_graph))
+                                 learner_graph=not args.no_graph, splits=args.e2e_splits))
             r2.init()
             for _ in range(max(3, args.warmup)):
                 r2.iteration()
                 r2.learner.fetch_stats()
             barrier()
-            env = r2.env
-            h0, d0 = env.h2d_bytes, env.d2h_bytes
+            envs = r2.envs
+            h0, d0 = sum(e.h2d_bytes for e in envs), sum(e.d2h_bytes for e in envs)
             stats_bytes = 0
             t0 = time.perf_counter()
             for _ in range(args.steps):
@@ -595,8 +602,8 @@ def run_ours(args):
             barrier()
             dt = max_over_ranks(time.perf_counter() - t0)
             out = dict(value=world * N_ENVS * ROLLOUT * args.steps / dt, unit=UNIT,
-                       h2d_bytes_per_step=(env.h2d_bytes - h0) // args.steps,
-                       d2h_bytes_per_step=(env.d2h_bytes - d0 + stats_bytes) // args.steps,
+                       h2d_bytes_per_step=(sum(e.h2d_bytes for e in envs) - h0) // args.steps,
+                       d2h_bytes_per_step=(sum(e.d2h_bytes for e in envs) - d0 + stats_bytes) // args.steps,
                        ms_per_step=1e3 * dt / args.steps)
             del r2
             torch.cuda.empty_cache()
@@ -604,7 +611,10 @@ def run_ours(args):
 
         e2e = run_e2e(False)
         e2e["api"] = ("sample_factory_b200.train.Runner.iteration() with a HOST env (numpy simulator, pinned staging): "
-                      "obs H2D + actions D2H every env step, loss stats D2H every iteration; learner_cuda_graph=True")
+                      "obs H2D + actions D2H every env step, loss stats D2H every iteration; learner_cuda_graph=True; "
+                      f"worker_num_splits={args.e2e_splits} env groups (the reference's default: double-buffered sampling, the GPU "
+                      "serves one group while the host steps the other)")
+        e2e["worker_num_splits"] = args.e2e_splits
         if not args.no_async:
             ea = run_e2e(True)
             e2e["async_rl"] = dict(value=ea["value"], ms_per_step=ea["ms_per_step"],
@@ -663,6 +673,8 @@ def main():
                     help="worker_num_splits: env groups whose per-step kernel chains run concurrently on separate streams "
                          "(measured at 4096 envs: 1.29 ms per rollout with 2 or 4 groups vs 1.32 ms with 1 -- a policy step is "
                          "a chain of one-wave kernels, so halving the rows per kernel does not shorten it)")
+    ap.add_argument("--e2e-splits", dest="e2e_splits", type=int, default=2,
+                    help="worker_num_splits of the end-to-end (host env) arm: 2 = the reference's default double-buffered sampling")
     ap.add_argument("--no-graph", dest="no_graph", action="store_true")
     ap.add_argument("--no-learner-graph", dest="no_learner_graph", action="store_true",
                     help="launch the learner's kernels one by one instead of replaying Learner.train() as one CUDA graph "

@@ -66,7 +66,8 @@ int sfb200_refresh_tf32_lo(const float* base, void* stream);
  *       exponent bits: the kernel scales the operand by the power of two that places the bound in [2^14, 2^15)).
  * sfb200_clip_adam_step keeps registered twins current; the transposed copies and the twins after any other write to
  * the weights are refreshed by the refresh_* calls.  sfb200_linear_out_bound derives the bound of a layer's output from
- * the bound of its input: in_bound * max_n sum_k |W[n][k]| + max_n |b[n]| (tanh: at most 1).  SFB200_TC_F16=0 disables
+ * the bound of its input: max_n (in_bound * sum_k |W[n][k]| + |b[n]|) (tanh: at most 1); out_bound_dev is FOUR 32-bit words
+ * [bound, scratch, counter, -], the middle two zero on entry and on return.  SFB200_TC_F16=0 disables
  * the form (A/B comparison).  No counterpart in the reference (its nn.Linear runs cuBLAS fp32 / CPU). */
 int sfb200_register_f16_twins(const float* base, void* twins, int64_t n);
 int sfb200_unregister_f16_twins(const float* base);

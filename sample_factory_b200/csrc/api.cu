@@ -95,29 +95,38 @@ __global__ void __launch_bounds__(256) f16_split_transposed_kernel(const float* 
     }
 }
 
-// Upper bound of |act(x W^T + b)| over all inputs with |x| <= in_bound: in_bound * max_n sum_k |W[n][k]| + max_n |b[n]|
-// (ELU / ReLU / tanh are 1-Lipschitz with act(0) = 0; tanh additionally <= 1).  One block.
-__global__ void __launch_bounds__(1024) linear_out_bound_kernel(const float* __restrict__ W, const float* __restrict__ b, int N,
-                                                               int K, const float* __restrict__ in_bound,
-                                                               float* __restrict__ out_bound, int act) {
-    __shared__ float s_row[32], s_b[32];
+// Upper bound of |act(x W^T + b)| over all inputs with |x| <= in_bound: max_n (in_bound * sum_k |W[n][k]| + |b[n]|)
+// (ELU / ReLU / tanh are 1-Lipschitz with act(0) = 0; tanh additionally <= 1).  One warp per output row, eight rows per
+// block; block maxima meet in an atomicMax on the bit pattern (non-negative floats order like unsigned ints), the block that
+// arrives last publishes the bound.  out = [bound, scratch bits, arrival counter, -]; scratch and counter are left at zero.
+__global__ void __launch_bounds__(256) linear_out_bound_kernel(const float* __restrict__ W, const float* __restrict__ b, int N,
+                                                              int K, const float* __restrict__ in_bound,
+                                                              float* __restrict__ out, int act) {
+    __shared__ float s_v[8];
+    unsigned int* scratch = reinterpret_cast<unsigned int*>(out) + 1;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float row_max = 0.f, b_max = 0.f;
-    for (int n = warp; n < N; n += 32) {
+    const int n = blockIdx.x * 8 + warp;
+    float v = 0.f;
+    if (n < N) {
         float t = 0.f;
         for (int k = lane; k < K; k += 32) t += fabsf(W[(int64_t)n * K + k]);
         t = warp_sum(t);
-        row_max = fmaxf(row_max, t);
-        if (b) b_max = fmaxf(b_max, fabsf(b[n]));
+        v = in_bound[0] * t * 1.0001f + (b ? fabsf(b[n]) : 0.f);      // (the row sum is rounded: a hair of slack)
     }
-    if (lane == 0) { s_row[warp] = row_max; s_b[warp] = b_max; }
+    if (lane == 0) s_v[warp] = v;
     __syncthreads();
     if (threadIdx.x == 0) {
-        float r = 0.f, bb = 0.f;
-        for (int i = 0; i < 32; ++i) { r = fmaxf(r, s_row[i]); bb = fmaxf(bb, s_b[i]); }
-        float out = in_bound[0] * r * 1.0001f + bb;      // (row sums are rounded: a hair of slack)
-        if (act == SFB200_ACT_TANH) out = fminf(out, 1.f);
-        out_bound[0] = out;
+        for (int i = 1; i < 8; ++i) v = fmaxf(v, s_v[i]);
+        atomicMax(scratch, __float_as_uint(v));
+        __threadfence();
+        if (atomicAdd(scratch + 1, 1u) == gridDim.x - 1) {
+            __threadfence();
+            float r = __uint_as_float(*reinterpret_cast<volatile unsigned int*>(scratch));
+            if (act == SFB200_ACT_TANH) r = fminf(r, 1.f);
+            out[0] = r;
+            scratch[0] = 0u;
+            scratch[1] = 0u;
+        }
     }
 }
 
@@ -129,39 +138,33 @@ __global__ void __launch_bounds__(1024) linear_out_bound_kernel(const float* __r
 __global__ void __launch_bounds__(256) heads_dz_bound_kernel(const float* __restrict__ dlogits, const float* __restrict__ dvalues,
                                                             int64_t rows, int A, const float* __restrict__ Wv,
                                                             const float* __restrict__ Wa, int H, float* __restrict__ out) {
-    __shared__ float s_r[8];
-    __shared__ int s_last;
+    __shared__ float s_r[8], s_w[8];
     unsigned int* scratch = reinterpret_cast<unsigned int*>(out) + 1;
-    float r = 0.f;
+    float r = 0.f, w = 0.f;
+    // (every block takes the weight maximum itself -- 4.6 K elements from L2 -- instead of leaving it to a serial last phase)
+    for (int i = threadIdx.x; i < H; i += blockDim.x) w = fmaxf(w, fabsf(Wv[i]));
+    for (int i = threadIdx.x; i < A * H; i += blockDim.x) w = fmaxf(w, fabsf(Wa[i]));
     for (int64_t m = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; m < rows; m += (int64_t)gridDim.x * blockDim.x) {
         float t = fabsf(dvalues[m]);
         for (int a = 0; a < A; ++a) t += fabsf(dlogits[m * A + a]);
         r = fmaxf(r, t);
     }
-    for (int o = 16; o > 0; o >>= 1) r = fmaxf(r, __shfl_xor_sync(0xffffffffu, r, o));
-    if ((threadIdx.x & 31) == 0) s_r[threadIdx.x >> 5] = r;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int i = 1; i < 8; ++i) r = fmaxf(r, s_r[i]);
-        atomicMax(scratch, __float_as_uint(r));
-        __threadfence();
-        s_last = atomicAdd(scratch + 1, 1u) == gridDim.x - 1 ? 1 : 0;
+    for (int o = 16; o > 0; o >>= 1) {
+        r = fmaxf(r, __shfl_xor_sync(0xffffffffu, r, o));
+        w = fmaxf(w, __shfl_xor_sync(0xffffffffu, w, o));
     }
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    float w = 0.f;
-    for (int i = threadIdx.x; i < H; i += blockDim.x) w = fmaxf(w, fabsf(Wv[i]));
-    for (int i = threadIdx.x; i < A * H; i += blockDim.x) w = fmaxf(w, fabsf(Wa[i]));
-    for (int o = 16; o > 0; o >>= 1) w = fmaxf(w, __shfl_xor_sync(0xffffffffu, w, o));
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) s_r[threadIdx.x >> 5] = w;
+    if ((threadIdx.x & 31) == 0) { s_r[threadIdx.x >> 5] = r; s_w[threadIdx.x >> 5] = w; }
     __syncthreads();
     if (threadIdx.x == 0) {
-        for (int i = 1; i < 8; ++i) w = fmaxf(w, s_r[i]);
-        out[0] = __uint_as_float(*reinterpret_cast<volatile unsigned int*>(scratch)) * w * 1.0001f;
-        scratch[0] = 0u;
-        scratch[1] = 0u;
+        for (int i = 1; i < 8; ++i) { r = fmaxf(r, s_r[i]); w = fmaxf(w, s_w[i]); }
+        atomicMax(scratch, __float_as_uint(r * w * 1.0001f));
+        __threadfence();
+        if (atomicAdd(scratch + 1, 1u) == gridDim.x - 1) {
+            __threadfence();
+            out[0] = __uint_as_float(*reinterpret_cast<volatile unsigned int*>(scratch));
+            scratch[0] = 0u;
+            scratch[1] = 0u;
+        }
     }
 }
 
@@ -362,7 +365,7 @@ int sfb200_unregister_operand_bound(const void* base) {
 int sfb200_linear_out_bound(const float* W, const float* b, int N, int K, const float* in_bound_dev, float* out_bound_dev,
                             int act, void* stream) {
     SFB_CHECK_ARG(W && in_bound_dev && out_bound_dev && N > 0 && K > 0, "linear_out_bound: bad arguments");
-    sfb::linear_out_bound_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(W, b, N, K, in_bound_dev, out_bound_dev, act);
+    sfb::linear_out_bound_kernel<<<(unsigned)sfb::ceil_div(N, 8), 256, 0, (cudaStream_t)stream>>>(W, b, N, K, in_bound_dev, out_bound_dev, act);
     SFB_LAUNCH_OK();
     return 0;
 }
@@ -370,7 +373,7 @@ int sfb200_linear_out_bound(const float* W, const float* b, int N, int K, const 
 int sfb200_heads_dz_bound(const float* dlogits, const float* dvalues, int64_t rows, int A, const float* Wv, const float* Wa,
                           int H, float* out_bound_dev, void* stream) {
     SFB_CHECK_ARG(dlogits && dvalues && Wv && Wa && out_bound_dev && rows > 0 && A > 0 && H > 0, "heads_dz_bound: bad arguments");
-    sfb::heads_dz_bound_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(dlogits, dvalues, rows, A, Wv, Wa, H, out_bound_dev);
+    sfb::heads_dz_bound_kernel<<<128, 256, 0, (cudaStream_t)stream>>>(dlogits, dvalues, rows, A, Wv, Wa, H, out_bound_dev);
     SFB_LAUNCH_OK();
     return 0;
 }

@@ -190,9 +190,20 @@ class HostTapeVecEnv:
         return self.obs
 
     def step(self, actions: Tensor) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
-        # D2H: the actions the host simulator needs (synchronises -- a host env cannot start before it has them)
+        self.step_async(actions)
+        return self.step_wait()
+
+    def step_async(self, actions: Tensor) -> None:
+        """first half of step(): enqueue the D2H copy of the actions (the sampler's double-buffered mode lets the GPU work
+        on another env group while the host waits for this copy and simulates, rollout_worker.py:97-143)"""
         self.actions_host.copy_(actions, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        if not hasattr(self, "_actions_ready"):
+            self._actions_ready = torch.cuda.Event()
+        self._actions_ready.record(torch.cuda.current_stream())
+
+    def step_wait(self) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+        # D2H: the actions the host simulator needs (synchronises -- a host env cannot start before it has them)
+        self._actions_ready.synchronize()
         self.d2h_bytes += self.actions_host.numel() * 4
         a = self.actions_host.numpy()
         t = self.t

@@ -130,8 +130,19 @@ class BatchedHostEnv:
         return self._obs_out()
 
     def step(self, actions: Tensor) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+        self.step_async(actions)
+        return self.step_wait()
+
+    def step_async(self, actions: Tensor) -> None:
+        """first half of step(): enqueue the D2H copy of the actions (double-buffered sampling: the GPU serves another env
+        group while the host waits for this copy and steps these envs, rollout_worker.py:97-143)"""
         self.actions_host.copy_(actions, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        if not hasattr(self, "_actions_ready"):
+            self._actions_ready = torch.cuda.Event()
+        self._actions_ready.record(torch.cuda.current_stream())
+
+    def step_wait(self) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+        self._actions_ready.synchronize()
         self.d2h_bytes += self.actions_host.numel() * self.actions_host.element_size()
         a = self.actions_host.numpy()
         rew, term, trunc = self.rew_host.numpy(), self.term_host.numpy(), self.trunc_host.numpy()

@@ -176,7 +176,7 @@ class Learner:
         if getattr(self.model, "f16_twins", None) is not None and self.engine == ops.GEMM_TC_3XTF32:
             self.dz_bound = torch.zeros(4, **f32)        # [bound, scratch, counter, -] (sfb200_heads_dz_bound)
             ops.register_operand_bounds(self, [(self.obs_flat_compact, self.model.bound_x), (self.dz[-1], self.dz_bound[0:1])] +
-                                        [(self.h[i], self.model.bound_h[i: i + 1]) for i in range(len(spec.hidden) - 1)])
+                                        [(self.h[i], self.model.bound_h[4 * i: 4 * i + 1]) for i in range(len(spec.hidden) - 1)])
             for i in range(1, len(spec.hidden)):            # layers whose input gradient is needed: dX reads W transposed
                 self.model.enable_f16_transposed(spec.fc_encoder_name(i, "weight"))
         self.mb_values = torch.empty(B, **f32)

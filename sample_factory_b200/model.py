@@ -280,7 +280,7 @@ class PolicyModel:
         self.f16_twins = torch.empty(2 * self.flat.numel(), dtype=torch.float16, device=self.device)
         ops.register_f16_twins(self.flat, self.f16_twins)
         self.bound_x = torch.full((1,), 5.0, dtype=torch.float32, device=self.device)
-        self.bound_h = torch.zeros(len(sp.hidden), dtype=torch.float32, device=self.device)
+        self.bound_h = torch.zeros(4 * len(sp.hidden), dtype=torch.float32, device=self.device)   # [bound, scratch, counter, -] per layer
         self.refresh_bounds()
 
     def refresh_bounds(self) -> None:
@@ -292,8 +292,8 @@ class PolicyModel:
         act = ops.ACT[self.spec.nonlinearity]
         inb = self.bound_x
         for i, (W, b) in enumerate(self.hidden_layers()[:-1]):       # (the last hidden layer feeds the heads, not a GEMM)
-            ops.linear_out_bound(W, b, inb, self.bound_h[i: i + 1], act)
-            inb = self.bound_h[i: i + 1]
+            ops.linear_out_bound(W, b, inb, self.bound_h[4 * i: 4 * i + 4], act)
+            inb = self.bound_h[4 * i: 4 * i + 1]
         for name in self.f16_T:
             ops.refresh_f16_transposed(self.params[name])
 
@@ -387,7 +387,7 @@ class PolicyModel:
             self.flat_lo.copy_(other.flat_lo)
             if self.f16_twins is not None and other.f16_twins is not None:
                 self.f16_twins.copy_(other.f16_twins)
-                self.bound_h.copy_(other.bound_h)
+                self.bound_h.copy_(other.bound_h)      # (scratch words are zero between launches)
             self.refresh_cat_heads()
         else:
             self.weights_changed()

@@ -342,8 +342,10 @@ def register_operand_bounds(owner, pairs) -> None:
 
 
 def linear_out_bound(W: Tensor, b: Optional[Tensor], in_bound: Tensor, out_bound: Tensor, act: int) -> None:
-    """out_bound = in_bound * max_n sum_k |W[n][k]| + max_n |b[n]| (an upper bound of |act(x W^T + b)| for |x| <= in_bound)"""
+    """out_bound[0] = max_n (in_bound * sum_k |W[n][k]| + |b[n]|): an upper bound of |act(x W^T + b)| for |x| <= in_bound;
+    out_bound = four floats [bound, scratch, counter, -], the middle two zero before and after"""
     N, K = W.shape
+    assert out_bound.numel() >= 4
     lib().call("sfb200_linear_out_bound", _p(W, F32), _p(b, F32), N, K, _p(in_bound, F32), _p(out_bound, F32), act, _stream())
 
 

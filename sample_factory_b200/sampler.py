@@ -56,7 +56,7 @@ class DeviceSampler:
         if getattr(model, "f16_twins", None) is not None and engine == ops.GEMM_TC_3XTF32:
             # fp16-split form of the GEMM engine: bounds of the activation buffers the per-step GEMMs read (model._register_f16)
             ops.register_operand_bounds(self, [(self.x_norm, model.bound_x)] +
-                                        [(self.h[i], model.bound_h[i: i + 1]) for i in range(len(spec.hidden) - 1)])
+                                        [(self.h[i], model.bound_h[4 * i: 4 * i + 1]) for i in range(len(spec.hidden) - 1)])
         # what env.step() receives (preprocess_actions, batched_sampling.py:30-82): int32 [N] for Discrete, float32 [N, A]
         # for a Box action space
         if spec.continuous:
@@ -390,6 +390,12 @@ class SplitSampler:
         self.env = envs[0]
         self.side_streams = [torch.cuda.Stream(device=model.device) for _ in envs[1:]]
         self.use_cuda_graph = use_cuda_graph and all(getattr(e, "is_gpu_env", False) for e in envs)
+        # host envs that can split step() into step_async / step_wait: step-interleaved double buffering
+        self.host_interleaved = (not any(getattr(e, "is_gpu_env", False) for e in envs) and
+                                 all(hasattr(e, "step_async") and hasattr(e, "step_wait") for e in envs))
+        if self.host_interleaved and use_cuda_graph:
+            for sub in self.subs:          # the per-step graphs of the host-env path (DeviceSampler._rollout_step_graphs)
+                sub.use_step_graphs = (getattr(sub.env, "static_outputs", False) and sub.noise is None)
         self._graph: Optional[torch.cuda.CUDAGraph] = None
         self._graph_launches = 0
         self.kernel_launches_per_rollout = 0
@@ -427,9 +433,61 @@ class SplitSampler:
             main.wait_stream(st)
         self.kernel_launches_per_rollout = ops.launch_count() - n0
 
+    def _rollout_host_interleaved(self) -> None:
+        """Double-buffered sampling over HOST env groups (rollout_worker.py:97-143: "while one group of envs waits for actions
+        the other one is stepping"): group g's GPU work -- results H2D, post-step(t), policy step(t+1), actions D2H -- runs on
+        its own stream while the host waits for and steps the next group.  Same per-step launches (or per-step graphs) as the
+        single-group path; only the order in which the host issues them changes."""
+        main = torch.cuda.current_stream()
+        streams = [main] + self.side_streams
+        T = self.T
+        graphs = [sub._step_graphs for sub in self.subs]
+
+        def policy(sub, g, t):
+            if graphs[g] is not None:
+                graphs[g][t][0].replay()
+            else:
+                if t == 0:
+                    sub._pre_step(0)
+                sub._policy_step(t)
+            sub.env.step_async(sub.env_actions)
+
+        for st in self.side_streams:
+            st.wait_stream(main)
+        n0 = ops.launch_count()
+        for g, sub in enumerate(self.subs):
+            with torch.cuda.stream(streams[g]):
+                policy(sub, g, 0)
+        for t in range(T):
+            for g, sub in enumerate(self.subs):
+                with torch.cuda.stream(streams[g]):
+                    obs, rew, term, trunc = sub.env.step_wait()
+                    sub.last_obs = sub._take_obs(obs)
+                    if graphs[g] is not None:
+                        graphs[g][t][1].replay()
+                    else:
+                        sub._post_step(t, rew, term, trunc)
+                    inactive = getattr(sub.env, "inactive", None)
+                    if inactive is not None:
+                        sub.traj["policy_id"][:, t].masked_fill_(inactive, -1)
+                    if t + 1 < T:
+                        policy(sub, g, t + 1)
+        for st in self.side_streams:
+            main.wait_stream(st)
+        n = ops.launch_count() - n0
+        self.kernel_launches_per_rollout = n if n else sum(s._graph_launches for s in self.subs)
+
     def rollout(self) -> None:
         if any(s.last_obs is None for s in self.subs):
             self.reset()
+        if self.host_interleaved:
+            if any(s.use_step_graphs and s._step_graphs is None for s in self.subs):
+                for s in self.subs:        # warm-up / capture of the groups' per-step graphs, one group after the other
+                    s.rollout()
+                self.kernel_launches_per_rollout = sum(s.kernel_launches_per_rollout for s in self.subs)
+                return
+            self._rollout_host_interleaved()
+            return
         if not self.use_cuda_graph:
             self._rollout_all()
             return
@@ -451,6 +509,8 @@ class SplitSampler:
 
     @property
     def graph_replay_launches(self) -> int:
+        if self.host_interleaved:
+            return sum(s.graph_replay_launches for s in self.subs)
         return self._graph_launches if self._graph is not None else 0
 
     def pop_episode_stats(self) -> Dict[str, float]:

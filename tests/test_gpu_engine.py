@@ -434,6 +434,50 @@ def test_split_sampler_matches_single_sampler():
             assert torch.equal(a[k], b[k]), k
 
 
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_double_buffered_host_sampling_matches_one_group_after_the_other(use_graph):
+    """worker_num_splits = 2 over HOST envs (rollout_worker.py:97-143): stepping the two env groups interleaved -- the GPU serves
+    one group on its own stream while the host simulates the other -- fills the trajectory buffers exactly like running the
+    groups' rollouts one after the other (same weights, tapes, Philox streams), with per-step launches and with per-step graphs"""
+    from sample_factory_b200 import ops
+    from sample_factory_b200.envs import HostTapeVecEnv
+    from sample_factory_b200.sampler import SplitSampler
+
+    dev = torch.device("cuda", 0)
+    N, T = 256, 8
+    ocfg = O.OracleCfg(rollout=T, recurrence=1, batch_size=N * T, num_batches_per_epoch=1, encoder_mlp_layers=[128, 128])
+    st0 = O.init_state(ocfg, seed=8)
+    tape = torch.randn(5 * T + 1, N, ocfg.obs_dim, generator=torch.Generator().manual_seed(5)) * 1.1
+    cfg, model, traj, env, sampler, _ = build(ocfg, N, st0, tape, dev, engine="3xtf32" if ops.tc_available() else "simt")
+    h = N // 2
+
+    def run(interleaved, n):
+        es = [HostTapeVecEnv(tape[:, :h].contiguous().numpy(), ocfg.num_actions, dev, env_index_offset=0),
+              HostTapeVecEnv(tape[:, h:].contiguous().numpy(), ocfg.num_actions, dev, env_index_offset=h)]
+        sp = SplitSampler(cfg, es, model, traj, engine=sampler.engine, use_cuda_graph=use_graph, philox_seed=3)
+        assert sp.host_interleaved
+        if not interleaved:
+            sp.host_interleaved = False      # the groups' whole rollouts one after the other (sub-samplers on their streams)
+        sp.reset()
+        outs = []
+        for _ in range(n):
+            sp.rollout()
+            torch.cuda.synchronize()
+            outs.append({k: traj[k].clone() for k in ("actions", "values", "rewards", "dones", "obs", "policy_version")})
+        return outs, sp
+
+    seq, _ = run(False, 4)
+    inter, sp = run(True, 4)
+    if use_graph:
+        assert all(s._step_graphs is not None for s in sp.subs) and sp.graph_replay_launches > 0
+    for a, b in zip(seq, inter):
+        for k in a:
+            if k == "values":
+                assert torch.equal(a[k][:, :T], b[k][:, :T]), k
+            else:
+                assert torch.equal(a[k], b[k]), k
+
+
 def test_graphed_learner_matches_eager():
     """cfg.learner_cuda_graph: Learner.train() replayed as ONE CUDA graph (device-resident step counters / lr) produces the
     same parameters, Adam moments and loss statistics as the launch-by-launch learner, iteration after iteration."""

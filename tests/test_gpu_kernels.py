@@ -202,14 +202,27 @@ def test_linear_out_bound(dev):
     W = torch.randn(96, 40, generator=g(180)).to(dev)
     b = torch.randn(96, generator=g(181)).to(dev)
     inb = torch.full((1,), 5.0, device=dev)
-    out = torch.zeros(1, device=dev)
-    ops.linear_out_bound(W, b, inb, out, ops.ACT["elu"])
-    expect = 5.0 * W.abs().sum(1).max().item() + b.abs().max().item()
-    assert expect <= out.item() <= expect * 1.001
+    out = torch.zeros(4, device=dev)
+    for _ in range(2):          # (second launch: the scratch words were left at zero)
+        ops.linear_out_bound(W, b, inb, out, ops.ACT["elu"])
+        expect = (5.0 * W.abs().sum(1) + b.abs()).max().item()
+        assert expect <= out[0].item() <= expect * 1.001 and out[1:3].abs().sum().item() == 0
     x = (torch.rand(4096, 40, generator=g(182)) * 10 - 5).to(dev)
-    assert torch.nn.functional.elu(torch.nn.functional.linear(x, W, b)).abs().max().item() <= out.item()
+    assert torch.nn.functional.elu(torch.nn.functional.linear(x, W, b)).abs().max().item() <= out[0].item()
     ops.linear_out_bound(W, b, inb, out, ops.ACT["tanh"])
-    assert out.item() == 1.0
+    assert out[0].item() == 1.0
+    # the dz bound of heads_backward
+    dl = torch.randn(5000, 6, generator=g(183)).to(dev) * 1e-4
+    dv = torch.randn(5000, generator=g(184)).to(dev) * 1e-4
+    Wv = torch.randn(1, 96, generator=g(185)).to(dev)
+    Wa = torch.randn(6, 96, generator=g(186)).to(dev)
+    zb = torch.zeros(4, device=dev)
+    for _ in range(2):
+        ops.heads_dz_bound(dl, dv, Wv, Wa, zb)
+        expect = (dv.abs() + dl.abs().sum(1)).max().item() * max(Wv.abs().max().item(), Wa.abs().max().item())
+        assert expect <= zb[0].item() <= expect * 1.001 and zb[1:3].abs().sum().item() == 0
+    dz = (dv[:, None] * Wv + dl @ Wa)
+    assert dz.abs().max().item() <= zb[0].item()
 
 
 def test_linear_forward_strided_input(dev):
