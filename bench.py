@@ -612,8 +612,8 @@ def run_ours(args):
         e2e = run_e2e(False)
         e2e["api"] = ("sample_factory_b200.train.Runner.iteration() with a HOST env (numpy simulator, pinned staging): "
                       "obs H2D + actions D2H every env step, loss stats D2H every iteration; learner_cuda_graph=True; "
-                      f"worker_num_splits={args.e2e_splits} env groups (the reference's default: double-buffered sampling, the GPU "
-                      "serves one group while the host steps the other)")
+                      f"worker_num_splits={args.e2e_splits}; per env step ONE graph replay (post-step(t) + policy step(t+1) + the "
+                      "actions' D2H copy) between the env's host simulation and its H2D copies")
         e2e["worker_num_splits"] = args.e2e_splits
         if not args.no_async:
             ea = run_e2e(True)
@@ -673,8 +673,11 @@ def main():
                     help="worker_num_splits: env groups whose per-step kernel chains run concurrently on separate streams "
                          "(measured at 4096 envs: 1.29 ms per rollout with 2 or 4 groups vs 1.32 ms with 1 -- a policy step is "
                          "a chain of one-wave kernels, so halving the rows per kernel does not shorten it)")
-    ap.add_argument("--e2e-splits", dest="e2e_splits", type=int, default=2,
-                    help="worker_num_splits of the end-to-end (host env) arm: 2 = the reference's default double-buffered sampling")
+    ap.add_argument("--e2e-splits", dest="e2e_splits", type=int, default=1,
+                    help="worker_num_splits of the end-to-end (host env) arm: 2 = double-buffered sampling over two env groups (the "
+                         "GPU serves one group while the host steps the other).  Measured with the numpy tape env, whose host step "
+                         "costs ~25 us: 22.8 M env-steps/s with 2 groups vs 25.0 M with 1 -- the host thread's per-call overhead, "
+                         "not the GPU, is what a second group doubles; the mode pays off for envs whose host step is expensive")
     ap.add_argument("--no-graph", dest="no_graph", action="store_true")
     ap.add_argument("--no-learner-graph", dest="no_learner_graph", action="store_true",
                     help="launch the learner's kernels one by one instead of replaying Learner.train() as one CUDA graph "

@@ -168,6 +168,8 @@ class HostTapeVecEnv:
         self.device = device
         self.t = 0
         self.env_idx = np.arange(self.num_agents, dtype=np.int64) + env_index_offset
+        self._res_term = ((self.env_idx * 13) % term_period).astype(np.int32)
+        self._res_trunc = (self.env_idx % trunc_period).astype(np.int32)
         n = self.num_agents
         self.actions_host = torch.empty(n, dtype=torch.int32).pin_memory()
         # reward / terminated / truncated travel in ONE packed staging buffer (one H2D copy instead of three)
@@ -193,13 +195,20 @@ class HostTapeVecEnv:
         self.step_async(actions)
         return self.step_wait()
 
-    def step_async(self, actions: Tensor) -> None:
-        """first half of step(): enqueue the D2H copy of the actions (the sampler's double-buffered mode lets the GPU work
-        on another env group while the host waits for this copy and simulates, rollout_worker.py:97-143)"""
+    def enqueue_actions_d2h(self, actions: Tensor) -> None:
+        """the D2H copy of the actions into the pinned staging buffer (static pointers: may be captured into a CUDA graph)"""
         self.actions_host.copy_(actions, non_blocking=True)
+
+    def mark_actions_enqueued(self) -> None:
         if not hasattr(self, "_actions_ready"):
             self._actions_ready = torch.cuda.Event()
         self._actions_ready.record(torch.cuda.current_stream())
+
+    def step_async(self, actions: Tensor) -> None:
+        """first half of step(): enqueue the D2H copy of the actions (the sampler's double-buffered mode lets the GPU work
+        on another env group while the host waits for this copy and simulates, rollout_worker.py:97-143)"""
+        self.enqueue_actions_d2h(actions)
+        self.mark_actions_enqueued()
 
     def step_wait(self) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
         # D2H: the actions the host simulator needs (synchronises -- a host env cannot start before it has them)
@@ -208,10 +217,12 @@ class HostTapeVecEnv:
         a = self.actions_host.numpy()
         t = self.t
         np.divide(a, float(self.num_actions), out=self.rew_host.numpy(), casting="unsafe")
-        term = ((t * 7 + self.env_idx * 13) % self.term_period) == 0
-        trunc = (((t + self.env_idx) % self.trunc_period) == 0) & ~term
-        self.term_host.numpy()[:] = term
-        self.trunc_host.numpy()[:] = trunc
+        # terminated / truncated rules of the tape env: (7 t + 13 i) % P == 0  <=>  (13 i) % P == (-7 t) % P, so one comparison of
+        # a precomputed residue array against a scalar per rule (no integer divisions, no temporaries per step)
+        term, trunc = self.term_host.numpy(), self.trunc_host.numpy()
+        np.equal(self._res_term, (-7 * t) % self.term_period, out=term)
+        np.equal(self._res_trunc, (-t) % self.trunc_period, out=trunc)
+        np.greater(trunc, term, out=trunc)               # trunc & ~term
         self.t += 1
         # H2D: next observation batch + step results
         self.obs.copy_(self.tape[self.t % self.tape_len], non_blocking=True)

@@ -133,13 +133,20 @@ class BatchedHostEnv:
         self.step_async(actions)
         return self.step_wait()
 
-    def step_async(self, actions: Tensor) -> None:
-        """first half of step(): enqueue the D2H copy of the actions (double-buffered sampling: the GPU serves another env
-        group while the host waits for this copy and steps these envs, rollout_worker.py:97-143)"""
+    def enqueue_actions_d2h(self, actions: Tensor) -> None:
+        """the D2H copy of the actions into the pinned staging buffer (static pointers: may be captured into a CUDA graph)"""
         self.actions_host.copy_(actions, non_blocking=True)
+
+    def mark_actions_enqueued(self) -> None:
         if not hasattr(self, "_actions_ready"):
             self._actions_ready = torch.cuda.Event()
         self._actions_ready.record(torch.cuda.current_stream())
+
+    def step_async(self, actions: Tensor) -> None:
+        """first half of step(): enqueue the D2H copy of the actions (double-buffered sampling: the GPU serves another env
+        group while the host waits for this copy and steps these envs, rollout_worker.py:97-143)"""
+        self.enqueue_actions_d2h(actions)
+        self.mark_actions_enqueued()
 
     def step_wait(self) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
         self._actions_ready.synchronize()

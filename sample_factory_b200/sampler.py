@@ -96,6 +96,7 @@ class DeviceSampler:
         self.use_step_graphs = (use_cuda_graph and not getattr(env, "is_gpu_env", False)
                                 and getattr(env, "static_outputs", False))
         self._step_graphs = None
+        self._merged_graphs = None
         self._eager_rollouts = 0
         self.kernel_launches_per_rollout = 0
         # Fused step tail (csrc/heads.cu sampler_tail_tape_kernel): for the synthetic tape env the heads' finishing step,
@@ -207,6 +208,9 @@ class DeviceSampler:
         obs, rew, terminated, truncated = self.env.step(self.env_actions)   # batched_sampling.py:316
         self.last_obs = self._take_obs(obs)
         self._post_step(t, rew, terminated, truncated)
+        self._mask_inactive(t)
+
+    def _mask_inactive(self, t: int) -> None:
         inactive = getattr(self.env, "inactive", None)
         if inactive is not None:      # multi-agent host envs: steps of inactive agents carry policy id -1 (masked by the learner)
             self.traj["policy_id"][:, t].masked_fill_(inactive, -1)
@@ -316,7 +320,62 @@ class DeviceSampler:
             self._rollout_eager()
             self._eager_rollouts += 1
             return
+        if all(hasattr(self.env, a) for a in ("enqueue_actions_d2h", "mark_actions_enqueued", "step_wait")):
+            self._rollout_merged_graphs()
+            return
         if self._step_graphs is None:
+            self._capture_step_graph_pairs()
+        for t in range(self.T):
+            gp, gq = self._step_graphs[t]
+            gp.replay()
+            obs, _, _, _ = self.env.step(self.env_actions)
+            assert self._take_obs(obs) is self.last_obs
+            gq.replay()
+        self.kernel_launches_per_rollout = self._graph_launches
+
+    def _rollout_merged_graphs(self) -> None:
+        """Host envs whose step() splits into "enqueue the D2H copy of the actions" / "wait, simulate, enqueue the H2D copies":
+        ONE graph per env step = post-step(t) + policy step(t+1) + the actions' D2H copy (pinned staging buffer: static
+        pointers), so the host issues one replay, one event record and the env's own copies per step."""
+        env, T = self.env, self.T
+        if self._merged_graphs is None:
+            assert self.last_obs is env.obs, "host env must expose static output buffers (obs/rew/terminated/truncated)"
+            torch.cuda.synchronize()
+            n0 = ops.launch_count()
+            first, last = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(first):
+                self._pre_step(0)
+                self._policy_step(0)
+                env.enqueue_actions_d2h(self.env_actions)
+            mids = []
+            for t in range(T - 1):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._post_step(t, env.rew, env.terminated, env.truncated)
+                    self._mask_inactive(t)
+                    self._policy_step(t + 1)
+                    env.enqueue_actions_d2h(self.env_actions)
+                mids.append(g)
+            with torch.cuda.graph(last):
+                self._post_step(T - 1, env.rew, env.terminated, env.truncated)
+                self._mask_inactive(T - 1)
+            self._merged_graphs = (first, mids, last)
+            self._graph_launches = ops.launch_count() - n0
+        first, mids, last = self._merged_graphs
+        first.replay()
+        env.mark_actions_enqueued()
+        for t in range(T):
+            obs, _, _, _ = env.step_wait()
+            assert self._take_obs(obs) is self.last_obs
+            if t + 1 < T:
+                mids[t].replay()
+                env.mark_actions_enqueued()
+            else:
+                last.replay()
+        self.kernel_launches_per_rollout = self._graph_launches
+
+    def _capture_step_graph_pairs(self) -> None:
+        if True:
             env = self.env
             assert self.last_obs is env.obs, "host env must expose static output buffers (obs/rew/terminated/truncated)"
             torch.cuda.synchronize()
@@ -330,21 +389,15 @@ class DeviceSampler:
                     self._policy_step(t)
                 with torch.cuda.graph(gq):
                     self._post_step(t, env.rew, env.terminated, env.truncated)
+                    self._mask_inactive(t)
                 graphs.append((gp, gq))
             self._step_graphs = graphs
             self._graph_launches = ops.launch_count() - n0
-        for t in range(self.T):
-            gp, gq = self._step_graphs[t]
-            gp.replay()
-            obs, _, _, _ = self.env.step(self.env_actions)
-            assert self._take_obs(obs) is self.last_obs
-            gq.replay()
-        self.kernel_launches_per_rollout = self._graph_launches
 
     @property
     def graph_replay_launches(self) -> int:
         """Kernel launches per rollout that happen through graph replay (not seen by the library's launch counter)."""
-        if self._graph is not None or self._step_graphs is not None:
+        if self._graph is not None or self._step_graphs is not None or self._merged_graphs is not None:
             return self._graph_launches
         return 0
 
@@ -467,9 +520,7 @@ class SplitSampler:
                         graphs[g][t][1].replay()
                     else:
                         sub._post_step(t, rew, term, trunc)
-                    inactive = getattr(sub.env, "inactive", None)
-                    if inactive is not None:
-                        sub.traj["policy_id"][:, t].masked_fill_(inactive, -1)
+                        sub._mask_inactive(t)
                     if t + 1 < T:
                         policy(sub, g, t + 1)
         for st in self.side_streams:
@@ -482,10 +533,14 @@ class SplitSampler:
             self.reset()
         if self.host_interleaved:
             if any(s.use_step_graphs and s._step_graphs is None for s in self.subs):
-                for s in self.subs:        # warm-up / capture of the groups' per-step graphs, one group after the other
-                    s.rollout()
-                self.kernel_launches_per_rollout = sum(s.kernel_launches_per_rollout for s in self.subs)
-                return
+                if any(s._eager_rollouts < 1 for s in self.subs):
+                    for s in self.subs:        # first rollout: every group eager, one after the other (kernel warm-up)
+                        s._rollout_eager()
+                        s._eager_rollouts += 1
+                    self.kernel_launches_per_rollout = sum(s.kernel_launches_per_rollout for s in self.subs)
+                    return
+                for s in self.subs:            # then capture the groups' per-step graph pairs (nothing executes here)
+                    s._capture_step_graph_pairs()
             self._rollout_host_interleaved()
             return
         if not self.use_cuda_graph:
