@@ -306,9 +306,20 @@ class DeviceSampler:
                 self._rollout_eager()   # warm-up on the side stream (allocator-free path, but be safe)
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
+            # the capture bakes in the address of the observation tensor step 0 reads: a device env must hand out the SAME
+            # tensors from every step() / reset() -- otherwise fall back to eager launches instead of replaying
+            # stale pointers
+            obs_ptr = self.last_obs.data_ptr()
             self._graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self._graph):
                 self._rollout_eager()
+            if self.last_obs.data_ptr() != obs_ptr:
+                print("[sf_b200] the env returns fresh observation tensors from step(): rollout CUDA graph disabled "
+                      "(expose static output buffers to enable it)", flush=True)
+                self._graph = None
+                self.use_cuda_graph = False
+                self._rollout_eager()
+                return
             self._graph_launches = self.kernel_launches_per_rollout
         self._graph.replay()
         self.kernel_launches_per_rollout = self._graph_launches
