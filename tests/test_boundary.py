@@ -42,6 +42,13 @@ from sample_factory.algo.utils.torch_utils import calc_num_elements
 from sample_factory.algo.utils.gymnasium_utils import convert_space
 from sample_factory.utils.utils import str2bool, is_module_available, log
 from sample_factory.utils.attr_dict import AttrDict
+from sample_factory.pbt.population_based_training import PopulationBasedTraining, perturb_float, policy_cfg_file
+from sample_factory.algo.utils.agent_policy_mapping import AgentPolicyMapping
+import sample_factory_b200.multi_policy
+cfg = sample_factory_b200.cfg.default_cfg(env="x", experiment="y")
+cfg.num_policies = 3
+assert isinstance(make_runner(cfg)[1], sample_factory_b200.multi_policy.MultiPolicyRunner)
+assert [AgentPolicyMapping(cfg).get_policy_for_agent(0, 0, i) for i in range(4)] == [0, 1, 2, 0]
 assert run_rl is sample_factory_b200.train.run_rl and parse_sf_args is sample_factory_b200.cfg.parse_sf_args
 register_env("x", lambda *a, **k: None)
 assert "x" in global_env_registry() and global_env_registry() is sample_factory_b200.envs.global_env_registry()
