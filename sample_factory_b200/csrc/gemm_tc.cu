@@ -988,13 +988,13 @@ static bool raw_hi_enabled() {
     return v == 1;
 }
 
-// SFB200_TA_DW_OPW=8 runs the dW-type GEMM (both operands MN-major) with eight operand warps instead of four (A/B switch;
-// measured on B200, tools/dw_bench.py: no gain -- the dW GEMM is bound by the tf32 MMA rate like the others)
+// The dW-type GEMM (both operands MN-major) runs with eight operand warps: 120.8 vs 128.0 us at 32768 x 512 x 512
+// (tools/dw_bench.py, call r02_y; before the shared-memory address-space fix the two were equal).  SFB200_TA_DW_OPW=4 restores four.
 static int dw_operand_warps() {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("SFB200_TA_DW_OPW");
-        v = (e && e[0] == '8') ? 8 : 4;
+        v = (e && e[0] == '4') ? 4 : 8;
     }
     return v;
 }
