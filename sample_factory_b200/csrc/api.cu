@@ -191,6 +191,30 @@ __global__ void tf32_check_lo_kernel(const float* __restrict__ w, const float* _
         }
 }
 
+// SFB200_CHECK_LO=1 also verifies fp16 twins (row-major: ld = K; transposed: element (n, k) at k * N + n) before every use
+__global__ void f16_check_twins_kernel(const float* __restrict__ W, const uint16_t* __restrict__ hi, const uint16_t* __restrict__ lo,
+                                       int N, int K, int transposed) {
+    const int64_t n_el = (int64_t)N * K;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_el; i += (int64_t)gridDim.x * blockDim.x) {
+        uint16_t h, l;
+        f16_split1(W[i] * (float)(1 << kF16WShift), h, l);
+        const int64_t j = transposed ? (i % K) * N + i / K : i;
+        if (hi[j] != h || lo[j] != l) {
+            printf("libsfb200: STALE fp16 twins at element %lld (call sfb200_refresh_f16_twins / _transposed after writing weights)\n",
+                   (long long)i);
+            __trap();
+        }
+    }
+}
+
+int f16_twins_check(const float* W, F16Twin tw, int N, int K, bool transposed, cudaStream_t st) {
+    int64_t blocks = ceil_div((int64_t)N * K, 256);
+    if (blocks > 1024) blocks = 1024;
+    f16_check_twins_kernel<<<(unsigned)blocks, 256, 0, st>>>(W, tw.hi, tw.lo, N, K, transposed ? 1 : 0);
+    SFB_LAUNCH_OK();
+    return 0;
+}
+
 int tf32_lo_check(const float* w, const float* lo, int64_t count, cudaStream_t st) {
     int64_t blocks = ceil_div(count, 256);
     if (blocks > 1024) blocks = 1024;

@@ -1117,6 +1117,11 @@ static int gemm_tc(bool a_mn, const float* A, int64_t lda, bool b_mn, const floa
             else if (b_mn && ldb == N) tw = f16_twinT_lookup(B, K, N);      // B = W[K][N] row-major, twins stored as [N][K]
         }
         if (tw.hi) {
+            if (tf32_lo_check_enabled()) {
+                // B = W[N][K] row-major (forward) or W[K][N] row-major read along its other axis (dX: twins transposed)
+                const int rc_chk = b_mn ? f16_twins_check(B, tw, K, N, true, st) : f16_twins_check(B, tw, N, K, false, st);
+                if (rc_chk) return rc_chk;
+            }
             CUtensorMap tb_hi, tb_lo16;
             if (!make_tmap_f16(&tb_hi, tw.hi, (uint64_t)K, (uint64_t)N, (uint64_t)K, 64, 128) ||
                 !make_tmap_f16(&tb_lo16, tw.lo, (uint64_t)K, (uint64_t)N, (uint64_t)K, 64, 128))
