@@ -191,7 +191,7 @@ __global__ void tf32_check_lo_kernel(const float* __restrict__ w, const float* _
         }
 }
 
-// SFB200_CHECK_LO=1 also verifies fp16 twins (row-major: ld = K; transposed: element (n, k) at k * N + n) before every use
+// SFB200_CHECK_F16=1 verifies fp16 twins (row-major: ld = K; transposed: element (n, k) at k * N + n) before every use
 __global__ void f16_check_twins_kernel(const float* __restrict__ W, const uint16_t* __restrict__ hi, const uint16_t* __restrict__ lo,
                                        int N, int K, int transposed) {
     const int64_t n_el = (int64_t)N * K;

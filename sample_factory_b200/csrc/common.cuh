@@ -54,7 +54,8 @@ F16Twin f16_twin_lookup(const float* p, int64_t count);
 uint16_t* f16_twin_lookup_mut(float* p, int64_t count, int64_t* lo_offset);
 // the same twins stored TRANSPOSED ([K][N] for a weight matrix W[N][K]): the weight operand of dX = dz . W, K-major
 F16Twin f16_twinT_lookup(const float* W, int N, int K);
-int f16_twins_check(const float* W, F16Twin tw, int N, int K, bool transposed, cudaStream_t st);   // SFB200_CHECK_LO=1
+int f16_twins_check(const float* W, F16Twin tw, int N, int K, bool transposed, cudaStream_t st);
+bool f16_check_enabled();   // SFB200_CHECK_F16=1 (gemm_tc.cu)
 // device float holding an upper bound of |x| over an activation buffer that contains [p, p + bytes), else NULL
 const float* operand_bound_lookup(const void* p, int64_t bytes);
 bool pdl_enabled();   // SFB200_PDL=0 turns programmatic dependent launch off (api.cu)

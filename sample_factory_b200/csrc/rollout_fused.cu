@@ -603,7 +603,7 @@ int tc_rollout_mlp2_tape(const float* W1, const float* W2, int act, int engine, 
         const float* bx = operand_bound_lookup(a.x_norm, a.N * a.K1 * (int64_t)sizeof(float));
         const float* bh = operand_bound_lookup(a.h1, a.N * a.H1 * (int64_t)sizeof(float));
         if (t1.hi && t2.hi && bx && bh) {
-            if (tf32_lo_check_enabled()) {
+            if (f16_check_enabled()) {
                 int rc = f16_twins_check(W1, t1, a.H1, a.K1, false, st);
                 if (!rc) rc = f16_twins_check(W2, t2, a.H2, a.H1, false, st);
                 if (rc) return rc;
