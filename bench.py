@@ -69,6 +69,9 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def num_samples(self) -> int:
+        return sum(1 for ln in self.lines if len(ln.split(",")) >= 9)
+
     def stop(self):
         if self.proc is None:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
@@ -503,8 +506,19 @@ def run_ours(args):
     s1.record()
     barrier()
     rollout_ms = s0.elapsed_time(s1) / args.steps
+    # nvidia-smi needs 0.1 s (one GPU) to well over a second (eight GPUs) before its first sample, and the timed region is
+    # ~60 ms: keep the SAME workload running (untimed) until a few samples of the clocks under load exist
+    # (sampler rollouts only: they involve no cross-rank exchange, so every rank can wait for its own nvidia-smi)
+    extra_rollouts = 0
+    t_wait = time.perf_counter()
+    while clocks.proc is not None and clocks.num_samples() < 3 and time.perf_counter() - t_wait < 6.0:
+        for _ in range(16):
+            runner.sampler.rollout()
+        torch.cuda.synchronize()
+        extra_rollouts += 16
     clock_info = clocks.stop()
-    clock_info["window"] = "timed region + the per-kernel timing iterations and the sampler-only pass right after it (same workload)"
+    clock_info["window"] = ("timed region + the per-kernel timing iterations and the sampler-only pass right after it (same workload)"
+                            + (f" + {extra_rollouts} more untimed rollouts until nvidia-smi had delivered samples" if extra_rollouts else ""))
     samp_bytes = 574.0 * N_ENVS * ROLLOUT
     samp_gbs = samp_bytes / (rollout_ms * 1e-3) / 1e9
     persistent = bool(getattr(runner.sampler, "fused_rollout", False))
