@@ -196,6 +196,63 @@ def test_data_parallel_host_logic_gloo_world2(tmp_path):
         assert p.returncode == 0, out
 
 
+_PBT_GLOO_WORKER = r"""
+import os, random, sys
+sys.path.insert(0, sys.argv[1])
+from collections import deque
+from types import SimpleNamespace
+import torch.distributed as dist
+from sample_factory_b200.multi_policy import MultiPolicyRunner
+from sample_factory_b200.pbt import PopulationBasedTraining
+
+rank = int(os.environ["RANK"])
+dist.init_process_group("gloo", rank=rank, world_size=2)
+random.seed(100 + rank)                 # the ranks' Python RNGs differ on purpose: only rank 0's draws may count
+cfg = SimpleNamespace(num_policies=3, with_pbt=True, pbt_optimize_gamma=False, pbt_mutation_rate=1.0, pbt_perturb_min=1.1,
+                      pbt_perturb_max=1.5, pbt_replace_fraction=0.3, pbt_replace_reward_gap=0.1, pbt_replace_reward_gap_absolute=1e-6,
+                      pbt_target_objective="true_objective", pbt_period_env_steps=10, pbt_start_mutation=10, env="e",
+                      learning_rate=1e-4, exploration_loss_coeff=0.003, value_loss_coeff=0.5, max_grad_norm=4.0,
+                      ppo_clip_ratio=0.1, ppo_clip_value=1.0, gamma=0.99, batch_size=1024, rollout=32)
+mp = MultiPolicyRunner.__new__(MultiPolicyRunner)          # the decision plumbing only: no device members on a CPU box
+mp.cfg, mp.rank, mp.world_size, mp.writers = cfg, rank, 2, {}
+applied = []
+mp.update_policy_cfg = lambda p, c: applied.append(("cfg", p, dict(c)))
+mp.update_reward_shaping = lambda p, s: None
+mp.replace_policy = lambda p, donor: applied.append(("replace", p, donor))
+mp.subs = [SimpleNamespace(env_steps=100) for _ in range(3)]
+mp.policy_avg_stats = {"true_objective": [deque([1.0 + rank]), deque([-5.0]), deque([4.0 - rank])]}   # rank-local statistics differ too
+mp.pbt = PopulationBasedTraining(cfg, mp, log=lambda *a: None)
+mp.pbt.dir, mp.pbt.default_reward_shaping = sys.argv[2] + f"/r{rank}", None
+os.makedirs(mp.pbt.dir, exist_ok=True)
+if rank == 0:
+    mp.pbt.on_init(mp.pbt.dir, None)
+mp._pbt_broadcast_all()
+mp.pbt.on_training_step()
+box = [None, None]
+dist.all_gather_object(box, (mp.pbt.policy_cfg, applied))
+assert box[0] == box[1], box                 # same hyper-parameters, same replacements, same order on both ranks
+assert ("replace", 1, 2) in applied, applied
+dist.barrier()
+print("PBT_GLOO_OK")
+"""
+
+
+def test_pbt_decisions_are_rank0s_on_every_rank_gloo_world2(tmp_path):
+    """data parallel + PBT: every rank must apply the SAME replacement and the SAME mutated hyper-parameters although their
+    Python RNGs and local episode statistics differ (multi_policy.MultiPolicyRunner.pbt_decide: rank 0 decides, broadcast)"""
+    script = tmp_path / "pbt_gloo_worker.py"
+    script.write_text(_PBT_GLOO_WORKER)
+    procs = []
+    port = 31000 + (os.getpid() % 2000)
+    for rank in range(2):
+        env = dict(os.environ, RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, str(script), ROOT, str(tmp_path)], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    for p in procs:
+        out, _ = p.communicate(timeout=240)
+        assert p.returncode == 0 and "PBT_GLOO_OK" in out, out
+
+
 # ------------------------------------------------------------------------------------ checkpoint compatibility (8f-2)
 def _tiny_gae_model():
     from sample_factory_b200.model import ModelSpec, PolicyModel
