@@ -405,6 +405,14 @@ if __name__ == "__main__":
                        recurrence=4),
         poison=False,
     )
+    # BASELINE cfg-5's real layer stack (sf_examples/isaacgym_examples/train_isaacgym.py:310-324 AllegroHandLSTM: MLP
+    # 512-256-128 -> LSTM-512, rollout = recurrence = 16, reward_scale 0.01, max_grad_norm 1.0, value bootstrap), few envs
+    run_case(
+        "cfg5_stack", N=16, T=16, obs_dim=64, A=8, hidden=[512, 256, 128], iters=1,
+        overrides=dict(batch_size=128, num_batches_per_epoch=2, num_epochs=2, use_rnn=True, rnn_type="lstm", rnn_size=512,
+                       recurrence=16, value_bootstrap=True, reward_scale=0.01, max_grad_norm=1.0),
+        poison=True,
+    )
     # continuous actions (BASELINE cfg-3, mujoco-style flags sf_examples/mujoco/mujoco_params.py:1-38): Box(6) actions,
     # tanh MLP [64,64], one learned log-stddev vector (adaptive_stddev=False) with tanh-squashed means, fixed-KL loss,
     # value bootstrap, no entropy bonus; and the default adaptive-stddev parameterization (2A linear outputs)
