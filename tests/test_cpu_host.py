@@ -472,3 +472,21 @@ def test_pbt_rules_match_the_reference_selection_and_mutation():
         assert not [c for c in calls if c[0] == "replace"]
     g = [perturb_exponential_decay(0.99, None) for _ in range(200)]
     assert all(0.97 < x < 0.9992 for x in g) and min(g) < 0.99 < max(g)
+
+
+def test_bench_clock_sampler_counts_only_complete_nvidia_smi_lines():
+    """bench.ClockSampler: the median SM clock / throttle reasons come from complete query lines only; `num_samples` is what the
+    bench waits on (it keeps the sampler's rollouts running until nvidia-smi has delivered a few samples -- N = 8 lines had none)"""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    cs = bench.ClockSampler(0)
+    cs.proc = type("P", (), dict(terminate=lambda self: None, wait=lambda self, timeout=None: 0, kill=lambda self: None))()
+    cs.lines = ["0, 1965, 1965, 801.2, 0x0000000000000000, Not Active, Not Active, Not Active, Not Active",
+                "0, 1950, 1965, 990.0, 0x0000000000000004, Not Active, Not Active, Not Active, Active",
+                "garbage", ""]
+    assert cs.num_samples() == 2
+    info = cs.stop()
+    assert info["samples"] == 2 and info["sm_mhz"] == 1957.5 and info["sm_max_mhz"] == 1965.0 and info["reasons"] == ["sw_power_cap"]
