@@ -44,3 +44,8 @@ class ModelModule(nn.Module):
 
     def get_out_size(self):
         raise NotImplementedError()
+
+
+def model_device(model):
+    """device of a torch module's first parameter (model_utils.py)"""
+    return next(model.parameters()).device

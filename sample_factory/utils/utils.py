@@ -34,3 +34,25 @@ def ensure_dir_exists(path: str) -> str:
 
 def debug_log_every_n(n, msg, *args, **kwargs):
     log.debug(msg, *args, **kwargs)
+
+
+def safe_ensure_dir_exists(path: str) -> str:
+    os.makedirs(path, exist_ok=True)
+    return path
+
+
+def project_tmp_dir(mkdir: bool = True) -> str:
+    import tempfile
+
+    d = os.path.join(tempfile.gettempdir(), f"sample_factory_{os.environ.get('USER', 'user')}")
+    return ensure_dir_exists(d) if mkdir else d
+
+
+def static_vars(**kwargs):
+    """decorator: attach attributes to a function (utils/utils.py)"""
+    def decorate(func):
+        for k, v in kwargs.items():
+            setattr(func, k, v)
+        return func
+
+    return decorate

@@ -83,6 +83,13 @@ class Runner:
     def register_observer(self, observer) -> None:
         self.observers.append(observer)
 
+    def _notify(self, hook: str, *args) -> None:
+        """AlgoObserver hooks (runner.py:52-73): on_init / on_start / on_training_step / extra_summaries / on_stop"""
+        for o in self.observers:
+            fn = getattr(o, hook, None)
+            if fn is not None:
+                fn(self, *args)
+
     def register_msg_handler(self, key: str, func: Callable) -> None:
         self.msg_handlers.setdefault(key, []).append(func)
 
@@ -194,6 +201,7 @@ class Runner:
             self.writers[self.policy_id] = SummaryWriter(os.path.join(experiment_dir(cfg), ".summary", str(self.policy_id)))
         self.sampler.reset()
         self.initialized = True
+        self._notify("on_init")
         return StatusCode.SUCCESS
 
     def load_state_dict(self, state_dict, strict: bool = False) -> None:
@@ -318,9 +326,14 @@ class Runner:
         t_start = last_report = last_save = last_best = time.time()
         steps_at_report = self.env_steps
         status = StatusCode.SUCCESS
+        self._notify("on_start")
+        iterations = 0
         try:
             while self.env_steps < cfg.train_for_env_steps and not self._time_is_up(t_start):
                 self.iteration()
+                iterations += 1
+                if self.observers:
+                    self._notify("on_training_step", iterations)
                 now = time.time()
                 if now - last_report >= cfg.experiment_summaries_interval:
                     torch.cuda.synchronize()
@@ -338,6 +351,8 @@ class Runner:
                         h(self, ep, 0)
                     if self.rank == 0:
                         self._report_experiment_summaries(fps, st)
+                        if self.observers and self.writers.get(self.policy_id) is not None:
+                            self._notify("extra_summaries", self.policy_id, self.env_steps, self.writers[self.policy_id])
                         print(f"[sf_b200] env_steps {self.env_steps} fps {fps:.0f} loss {st.get('loss', float('nan')):.4f} "
                               f"reward {ep.get('reward', float('nan')):.3f} episodes {ep.get('episodes', 0)}", flush=True)
                     last_report, steps_at_report = now, self.env_steps
@@ -355,6 +370,7 @@ class Runner:
             status = StatusCode.INTERRUPTED
         torch.cuda.synchronize()
         self.total_train_seconds = time.time() - t_start
+        self._notify("on_stop")
         if self.rank == 0:
             save_checkpoint(cfg, self.model, self.learner)
             fps = self.env_steps / max(self.total_train_seconds, 1e-9)

@@ -44,8 +44,30 @@ from sample_factory.utils.utils import str2bool, is_module_available, log
 from sample_factory.utils.attr_dict import AttrDict
 from sample_factory.pbt.population_based_training import PopulationBasedTraining, perturb_float, policy_cfg_file
 from sample_factory.algo.utils.agent_policy_mapping import AgentPolicyMapping
+from sample_factory.algo.runners.runner import AlgoObserver, Runner
+from sample_factory.algo.utils.misc import EPS, EPISODIC, ExperimentStatus
+from sample_factory.algo.utils.rl_utils import make_dones, samples_per_trajectory, total_num_envs
+from sample_factory.algo.sampling.sync_sampling_api import SyncSamplingAPI
+from sample_factory.eval import do_eval
+from sample_factory.utils.algo_version import ALGO_VERSION
+from sample_factory.utils.utils import static_vars, project_tmp_dir, safe_ensure_dir_exists, experiment_dir, ensure_dir_exists
+from sample_factory.model.utils import orthogonal_init, he_normal_init
+from sample_factory.model.model_utils import model_device
+from sample_factory.launcher.run_description import Experiment, ParamGrid, RunDescription
+from sample_factory.launcher.launcher_utils import seeds
+rd = RunDescription("run", [Experiment("exp", "python -m x", ParamGrid([("seed", [1, 2]), (("a", "b"), [(3, 4), (5, 6)])]).generate_params())])
+cmds = list(rd.generate_experiments("/tmp/t"))
+assert len(cmds) == 4 and cmds[0][0] == "python -m x --seed=1 --a=3 --b=4 --experiment=00_exp_s_1_a_3_b_4 --train_dir=/tmp/t/run/exp", cmds[0]
+assert make_dones([True, False], [False, True]) == [True, True] and ExperimentStatus.INTERRUPTED == 2
+# observers: hooks of AlgoObserver are called by the runner (only the ones an observer defines)
+class Obs(AlgoObserver):
+    def __init__(self): self.calls = []
+    def on_start(self, runner): self.calls.append("start")
+    def on_training_step(self, runner, it): self.calls.append(("step", it))
 import sample_factory_b200.multi_policy
 cfg = sample_factory_b200.cfg.default_cfg(env="x", experiment="y")
+r0 = Runner(cfg); o = Obs(); r0.register_observer(o); r0._notify("on_start"); r0._notify("on_training_step", 3); r0._notify("on_stop")
+assert o.calls == ["start", ("step", 3)]
 cfg.num_policies = 3
 assert isinstance(make_runner(cfg)[1], sample_factory_b200.multi_policy.MultiPolicyRunner)
 assert [AgentPolicyMapping(cfg).get_policy_for_agent(0, 0, i) for i in range(4)] == [0, 1, 2, 0]
