@@ -996,10 +996,12 @@ class OracleLearner:
         self.env_steps = 0
         self.log: List[Dict[str, float]] = []
 
-    def train(self, batch: Dict[str, Tensor], mb_indices: Optional[Tensor] = None) -> Dict[str, Tensor]:
+    def train(self, batch: Dict[str, Tensor], mb_indices=None) -> Dict[str, Tensor]:
         """learner.py:1036-1067 -> _prepare_batch -> _train (:671-841). Returns the prepared flat buffer.
         mb_indices (shuffle_minibatches, learner.py:498-526): a permutation of the flat sample indices built from
-        recurrence-length chunks; minibatch b is buffer[mb_indices[b*B:(b+1)*B]] (`_get_minibatch` :528-535)."""
+        recurrence-length chunks; minibatch b is buffer[mb_indices[b*B:(b+1)*B]] (`_get_minibatch` :528-535).  The reference
+        draws a NEW permutation at the start of every epoch (`_get_minibatches` is called inside the epoch loop, :707-713):
+        pass a sequence with one permutation per epoch (a single tensor is used for every epoch)."""
         cfg = self.cfg
         buff, experience_size, num_invalids = prepare_batch(cfg, self.st, batch, self.train_step)
         if num_invalids >= experience_size:
@@ -1008,11 +1010,12 @@ class OracleLearner:
         for _epoch in range(cfg.num_epochs):
             nmb = cfg.num_batches_per_epoch
             epoch_actor_losses = []
+            epoch_indices = mb_indices[_epoch] if isinstance(mb_indices, (list, tuple)) else mb_indices
             for b in range(nmb):
                 if nmb == 1:
                     mb = buff
-                elif mb_indices is not None:
-                    ind = mb_indices[b * cfg.batch_size: (b + 1) * cfg.batch_size].long()   # :509-517
+                elif epoch_indices is not None:
+                    ind = epoch_indices[b * cfg.batch_size: (b + 1) * cfg.batch_size].long()   # :509-517
                     mb = {k: v[ind] for k, v in buff.items()}
                 else:
                     sl = slice(b * cfg.batch_size, (b + 1) * cfg.batch_size)  # :521

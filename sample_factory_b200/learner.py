@@ -131,8 +131,8 @@ class Learner:
             "symmetric_kl_with_uniform_prior in the reference either)")
         assert not (spec.continuous and spec.adaptive_stddev and spec.continuous_tanh_scale > 0), (
             "continuous_tanh_scale is only read by the non-adaptive parameterization (action_parameterization.py:33-78)")
-        # learner.py:498-526: minibatches = a random permutation of recurrence-length chunks of the dataset, drawn once per
-        # train() call.  Device path: the permutation is drawn on the host (np.random, like the reference), copied to the
+        # learner.py:498-526, :707-713: minibatches = a random permutation of recurrence-length chunks of the dataset, drawn
+        # at the start of every epoch.  Device path: the permutation is drawn on the host (np.random, like the reference), copied to the
         # device, and ONE gather pass per train() rearranges every per-sample array the minibatch steps read; the steps then
         # run on contiguous slices exactly as in the unshuffled case.
         self.shuffle = bool(cfg.shuffle_minibatches) and cfg.num_batches_per_epoch > 1
@@ -245,7 +245,7 @@ class Learner:
             self._perm_chunk = chunk
             self.perm_host = torch.empty(E, dtype=torch.int32).pin_memory()
             self.perm_dev = torch.arange(E, dtype=torch.int32, device=dev)
-            self._next_perm: Optional[np.ndarray] = None
+            self._perm_queue: List[np.ndarray] = []      # explicit permutations for the next epochs (tests); else np.random
             self._sh: Dict[str, Tensor] = {}
         # CUDA-graph replay of the whole train() (cfg.learner_cuda_graph): possible when nothing in it depends on host
         # state -- constant lr schedule, one epoch (no early-stopping read-back), Adam.  The step counters and the
@@ -386,17 +386,20 @@ class Learner:
             ops.colsum_f64(self.mb_partials, 0, self.num_valid_dev)                            # global valid count
 
     def set_minibatch_permutation(self, indices) -> None:
-        """The sample order of the NEXT train() call (shuffle_minibatches): `indices` [E] as learner.py:498-526 builds them.
-        Without it every train() draws np.random.permutation over the recurrence-length chunks like the reference."""
+        """The sample order of the epochs of the NEXT train() call (shuffle_minibatches): one array [E] as learner.py:498-526
+        builds them, or a sequence of them, one per epoch.  Epochs without an explicit permutation draw np.random.permutation
+        over the recurrence-length chunks like the reference."""
         assert self.shuffle
-        idx = np.asarray(indices, dtype=np.int64).reshape(-1)
-        assert idx.shape[0] == self.E and np.array_equal(np.sort(idx), np.arange(self.E))
-        self._next_perm = idx
+        arr = np.asarray(indices, dtype=np.int64)
+        rows = arr.reshape(1, -1) if arr.ndim == 1 else arr.reshape(arr.shape[0], -1)
+        for idx in rows:
+            assert idx.shape[0] == self.E and np.array_equal(np.sort(idx), np.arange(self.E))
+        self._perm_queue = [idx.copy() for idx in rows]
 
     def _upload_permutation(self) -> None:
         """host side of the shuffle (outside any graph capture): draw / take the permutation, enqueue its H2D copy"""
-        if self._next_perm is not None:
-            idx, self._next_perm = self._next_perm, None
+        if self._perm_queue:
+            idx = self._perm_queue.pop(0)
         else:
             c = self._perm_chunk
             starts = np.random.permutation(np.arange(0, self.E, c))                   # :505-506
@@ -640,6 +643,11 @@ class Learner:
         nmb = cfg.num_batches_per_epoch
         for epoch in range(cfg.num_epochs):
             first = log_idx
+            if self.shuffle and epoch > 0:
+                # the reference reshuffles at the start of every epoch (learner.py:707-713): new permutation, new gather pass
+                # (the previous epoch ended with a host sync, so the pinned index buffer is free)
+                self._upload_permutation()
+                self._bind_minibatch_arrays(batch)
             for b in range(nmb):
                 self._minibatch_step(batch, b, log_idx)
                 log_idx += 1
@@ -666,6 +674,8 @@ class Learner:
                 if abs(prev_epoch_actor_loss - new_loss) < 1e-6:        # :829-837 early stopping
                     break
                 prev_epoch_actor_loss = new_loss
+        if self.shuffle:
+            self._perm_queue = []          # (permutations set for epochs an early stop skipped do not leak into the next call)
         self.num_minibatches_done = log_idx
         self.kernel_launches = ops.launch_count() - launches0   # counted by the library itself
         self._snapshot_policy_lag(batch, log_idx)

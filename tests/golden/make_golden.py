@@ -265,9 +265,23 @@ def run_case(name: str, N: int, T: int, obs_dim: int, A: int, hidden, iters: int
             return buff, n, ninv
 
         learner._prepare_batch = prep_wrapper
+        # shuffle_minibatches: record the permutations the reference drew (learner.py:507-519; a new one every epoch, :713)
+        drawn = []
+        orig_get_mbs = learner._get_minibatches
+
+        def get_mbs_wrapper(batch_size, experience_size):
+            mbs = orig_get_mbs(batch_size, experience_size)
+            if cfg.shuffle_minibatches and mbs[0] is not None:
+                drawn.append(np.concatenate(mbs).astype(np.int64))
+            return mbs
+
+        learner._get_minibatches = get_mbs_wrapper
         n_before = len(rec_losses)
         learner.train(batch)
         learner._prepare_batch = orig_prepare
+        learner._get_minibatches = orig_get_mbs
+        if drawn:      # one permutation per epoch that ran (learner.py:707-713)
+            out[f"it{it}/mb_indices"] = np.stack(drawn)
         for k, v in captured.items():
             out[f"it{it}/prep/{k}"] = v
         ls = rec_losses[n_before:]
@@ -411,6 +425,19 @@ if __name__ == "__main__":
         "cfg5_stack", N=16, T=16, obs_dim=64, A=8, hidden=[512, 256, 128], iters=1,
         overrides=dict(batch_size=128, num_batches_per_epoch=2, num_epochs=2, use_rnn=True, rnn_type="lstm", rnn_size=512,
                        recurrence=16, value_bootstrap=True, reward_scale=0.01, max_grad_norm=1.0),
+        poison=True,
+    )
+    # shuffle_minibatches (learner.py:498-526): the permutation of recurrence-length chunks the reference drew is recorded, so the
+    # oracle (and through it the device learner) can be fed the same minibatches; MLP (chunks of 1) and GRU (chunks of 4)
+    run_case(
+        "tiny_shuffle", N=32, T=8, obs_dim=16, A=8, hidden=[64, 64], iters=2,
+        overrides=dict(batch_size=64, num_batches_per_epoch=4, num_epochs=2, shuffle_minibatches=True),
+        poison=True,
+    )
+    run_case(
+        "tiny_shuffle_gru", N=32, T=8, obs_dim=16, A=8, hidden=[64], iters=2,
+        overrides=dict(batch_size=64, num_batches_per_epoch=4, num_epochs=1, use_rnn=True, rnn_type="gru", rnn_size=32,
+                       recurrence=4, shuffle_minibatches=True),
         poison=True,
     )
     # continuous actions (BASELINE cfg-3, mujoco-style flags sf_examples/mujoco/mujoco_params.py:1-38): Box(6) actions,

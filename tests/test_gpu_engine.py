@@ -577,8 +577,9 @@ def _compare_rollout_runs(a, b, what):
 @pytest.mark.parametrize("rnn", [False, True])
 @pytest.mark.parametrize("engine", ENGINES)
 def test_shuffle_minibatches_matches_oracle(engine, rnn):
-    """cfg.shuffle_minibatches (learner.py:498-526): the same permutation of recurrence-length chunks on both sides ->
-    same minibatches -> same losses and post-Adam weights; with a recurrent core the chunks keep their BPTT structure."""
+    """cfg.shuffle_minibatches (learner.py:498-526, a new permutation every epoch :707-713): the same permutations of
+    recurrence-length chunks on both sides -> same minibatches -> same losses and post-Adam weights; with a recurrent core the
+    chunks keep their BPTT structure."""
     from sample_factory_b200 import ops
 
     _need(engine)
@@ -608,10 +609,13 @@ def test_shuffle_minibatches_matches_oracle(engine, rnn):
             traj[k].copy_(v.view(traj[k].shape))
     E = N * T
     rng = np.random.RandomState(4)
-    starts = rng.permutation(np.arange(0, E, R))
-    perm = (starts[:, None] + np.arange(R)[None, :]).reshape(-1)
-    learner.set_minibatch_permutation(perm)
-    buff = olearner.train(otraj, mb_indices=torch.from_numpy(perm))
+    perms = []
+    for _ in range(ocfg.num_epochs):
+        starts = rng.permutation(np.arange(0, E, R))
+        perms.append((starts[:, None] + np.arange(R)[None, :]).reshape(-1))
+    assert not np.array_equal(perms[0], perms[1])
+    learner.set_minibatch_permutation(np.stack(perms))
+    buff = olearner.train(otraj, mb_indices=[torch.from_numpy(p) for p in perms])
     learner.train(traj)
     log = learner.minibatch_log().numpy()
     assert log.shape[0] == len(olearner.log) == 8
