@@ -376,14 +376,20 @@ class Learner:
                 self._allreduce(nv)
             ops.copy_rows_bytes(nv.view(1, 1), self.num_valid_dev.view(1, 1))
         else:
-            B = cfg.batch_size
-            adv_flat, val_flat = self._mb["adv"], self._mb["valids"]
-            for b in range(cfg.num_batches_per_epoch):
-                ops.adv_stats(adv_flat[b * B : (b + 1) * B], val_flat[b * B : (b + 1) * B], self.batch_stats,
-                              self.mb_partials[b], self.loss_ws)
-            if self.world_size > 1:
-                self._allreduce(self.mb_partials)
-            ops.colsum_f64(self.mb_partials, 0, self.num_valid_dev)                            # global valid count
+            self._minibatch_adv_partials()
+
+    def _minibatch_adv_partials(self) -> None:
+        """GAE mode: (count, sum, sum of squares) of the advantages of every minibatch of the CURRENT sample order (the
+        normalisation statistics of learner.py:646-647), made global with one all-reduce; + the global valid count"""
+        cfg = self.cfg
+        B = cfg.batch_size
+        adv_flat, val_flat = self._mb["adv"], self._mb["valids"]
+        for b in range(cfg.num_batches_per_epoch):
+            ops.adv_stats(adv_flat[b * B : (b + 1) * B], val_flat[b * B : (b + 1) * B], self.batch_stats,
+                          self.mb_partials[b], self.loss_ws)
+        if self.world_size > 1:
+            self._allreduce(self.mb_partials)
+        ops.colsum_f64(self.mb_partials, 0, self.num_valid_dev)                            # global valid count
 
     def set_minibatch_permutation(self, indices) -> None:
         """The sample order of the epochs of the NEXT train() call (shuffle_minibatches): one array [E] as learner.py:498-526
@@ -648,6 +654,8 @@ class Learner:
                 # (the previous epoch ended with a host sync, so the pinned index buffer is free)
                 self._upload_permutation()
                 self._bind_minibatch_arrays(batch)
+                if not cfg.with_vtrace:
+                    self._minibatch_adv_partials()     # the minibatches' advantage statistics follow the new composition
             for b in range(nmb):
                 self._minibatch_step(batch, b, log_idx)
                 log_idx += 1
