@@ -42,6 +42,23 @@ def test_sass_is_sm100a_only():
     assert archs == {"sm_100a"}, archs
 
 
+def test_gemm_kernels_are_blackwell_native_by_instruction_mix():
+    """Not just the arch tag: the GEMM engine's and the persistent rollout kernel's SASS must contain the 5th-gen tensor-core
+    path -- UTCHMMA (tcgen05.mma), UTMALDG (TMA), LDTM / STTM (tcgen05.ld / st), UTCBAR (tcgen05.commit) -- and no legacy HMMA
+    (mma.sync); the fp16 operand split shows up as F2FP packs.  (profiles/r02_sass_mix.md is the full table, tools/sass_mix.py.)"""
+    csrc = os.path.join(ROOT, "sample_factory_b200", "csrc")
+    for obj, need_f2fp in (("gemm_tc.o", True), ("rollout_fused.o", True), ("policy_step.o", False)):
+        path = os.path.join(csrc, obj)
+        if not os.path.isfile(path):
+            pytest.skip(f"{obj} not in tree (objects are built by __graft_entry__.build() and do not travel to the GPU box)")
+        sass = subprocess.run(["cuobjdump", "-sass", path], capture_output=True, text=True, timeout=600).stdout
+        count = lambda op: sum(1 for ln in sass.splitlines() if f" {op}" in ln and "/*" in ln)   # noqa: E731
+        assert count("UTCHMMA") > 0 and count("UTMALDG") > 0 and count("LDTM") > 0 and count("STTM") > 0 and count("UTCBAR") > 0, obj
+        assert count("HMMA.") == 0, f"{obj}: legacy mma.sync instructions"
+        if need_f2fp:
+            assert count("F2FP") > 0, f"{obj}: no fp16 operand split"
+
+
 def test_no_cpu_fallback():
     """The product path must fail loudly without a device, not silently compute on the CPU."""
     from sample_factory_b200 import ops
